@@ -1,0 +1,247 @@
+/*
+ * acb200.h — C-ABI of the B200-native Aho-Corasick matcher (libacb200.so).
+ *
+ * This is the drop-in boundary for the hot path of ph4r05/php_aho_corasick:
+ * ahocorasick_match() -> ac_trie_search().  The PHP extension's Zend glue
+ * (reference src/php_ahocorasick.c) reaches its bundled matcher through exactly
+ * five calls; this header declares those five with the same names, argument
+ * meaning, return codes and value-type layouts, so the glue compiles against it
+ * unchanged.  Every declaration cites the reference
+ * interface it replaces as  file:line  relative to the reference tree.
+ *
+ * The handle (AC_TRIE_t) is opaque here: the glue never dereferences it
+ * (reference src/php_ahocorasick.c only stores it in ahocorasick_master_t.acap,
+ * src/php_ahocorasick.h:181).
+ *
+ * Plain C, plain pointers and sizes; no CUDA or torch types cross this line.
+ */
+#ifndef ACB200_H_
+#define ACB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------ *
+ * Value types crossing the seam.  Layouts are identical to the reference's  *
+ * (src/multifast/actypes.h:41-138) so that callers built against either     *
+ * header are binary compatible.                                             *
+ * ------------------------------------------------------------------------ */
+
+/* replaces src/multifast/actypes.h:41 */
+typedef char AC_ALPHABET_t;
+
+/* replaces src/multifast/actypes.h:47-51 — borrowed byte string, binary safe */
+typedef struct ac_text
+{
+    const AC_ALPHABET_t *astring;
+    size_t length;
+} AC_TEXT_t;
+
+/* replaces src/multifast/actypes.h:57-62 */
+enum ac_pattid_type
+{
+    AC_PATTID_TYPE_DEFAULT = 0,
+    AC_PATTID_TYPE_NUMBER,
+    AC_PATTID_TYPE_STRING
+};
+
+/* replaces src/multifast/actypes.h:68-77 */
+typedef struct ac_pattid
+{
+    union
+    {
+        const char *stringy;
+        long number;
+    } u;
+    enum ac_pattid_type type;
+} AC_PATTID_t;
+
+/* replaces src/multifast/actypes.h:83-89 (56 bytes on LP64) */
+typedef struct ac_pattern
+{
+    AC_TEXT_t ptext;   /* the search string                                  */
+    AC_TEXT_t rtext;   /* replacement string — carried, never interpreted     */
+    AC_PATTID_t id;    /* returned verbatim in match events                   */
+    void *aux;         /* caller's opaque pointer, returned verbatim          */
+} AC_PATTERN_t;
+
+/* replaces src/multifast/actypes.h:106-113 — one event: every pattern that
+ * ends at `position` (exclusive end offset), longest pattern first.         */
+typedef struct ac_match
+{
+    AC_PATTERN_t *patterns;
+    size_t size;
+    size_t position;
+} AC_MATCH_t;
+
+/* replaces src/multifast/actypes.h:118-125 */
+typedef enum ac_status
+{
+    ACERR_SUCCESS = 0,
+    ACERR_DUPLICATE_PATTERN,
+    ACERR_LONG_PATTERN,
+    ACERR_ZERO_PATTERN,
+    ACERR_TRIE_CLOSED
+} AC_STATUS_t;
+
+/* replaces src/multifast/actypes.h:138 — non-zero return stops the search   */
+typedef int (*AC_MATCH_CALBACK_f)(AC_MATCH_t *, void *);
+
+/* replaces src/multifast/actypes.h:148 — longer patterns are rejected; this
+ * constant changes results, so it is part of the contract.                  */
+#define AC_PATTRN_MAX_LENGTH 1024
+
+/* replaces src/multifast/ahocorasick.h:37-66 — opaque in this library       */
+typedef struct ac_trie AC_TRIE_t;
+
+/* ------------------------------------------------------------------------ *
+ * The five entry points the Zend glue binds.                                *
+ * ------------------------------------------------------------------------ */
+
+/* replaces src/multifast/ahocorasick.h:73 (called at php_ahocorasick.c:812).
+ * Returns an open (not finalized) automaton; NULL only on host OOM.         */
+AC_TRIE_t *ac_trie_create(void);
+
+/* replaces src/multifast/ahocorasick.h:74 (called at php_ahocorasick.c:484).
+ * Acceptance rules of src/multifast/ahocorasick.c:91-131: TRIE_CLOSED after
+ * finalize, ZERO_PATTERN for length 0, LONG_PATTERN for length > 1024,
+ * DUPLICATE_PATTERN when the same bytes were accepted before (first wins).
+ * copy!=0: bytes and string id are copied (binary safe); copy==0: borrowed.  */
+AC_STATUS_t ac_trie_add(AC_TRIE_t *thiz, AC_PATTERN_t *patt, int copy);
+
+/* replaces src/multifast/ahocorasick.h:75 (called at php_ahocorasick.c:140).
+ * Computes failure/output links, flattens the automaton into the dense
+ * transition table and uploads it to the GPU (once).  On a CUDA failure the
+ * automaton is closed but unusable; see acb200_last_error().                */
+void ac_trie_finalize(AC_TRIE_t *thiz);
+
+/* replaces src/multifast/ahocorasick.h:79-80 (called at php_ahocorasick.c:745).
+ * Returns -1 if not finalized (or on a device error — acb200_last_error()
+ * tells which), 0 if the text was scanned to its end, 1 if the callback
+ * stopped the search.  keep==0 starts from the root at offset 0; keep!=0
+ * continues from the state and base offset the previous call ended at
+ * (src/multifast/ahocorasick.c:162-163,191-194,236-238).  Events arrive in
+ * ascending position, at most one per position.                             */
+int ac_trie_search(AC_TRIE_t *thiz, AC_TEXT_t *text, int keep,
+                   AC_MATCH_CALBACK_f callback, void *user);
+
+/* replaces src/multifast/ahocorasick.h:76 (called at php_ahocorasick.c:504,821).
+ * Frees host and device memory of the automaton.                            */
+void ac_trie_release(AC_TRIE_t *thiz);
+
+/* ------------------------------------------------------------------------ *
+ * Additions (not in the reference).                                         *
+ * ------------------------------------------------------------------------ */
+
+/* Batched callback: like AC_MATCH_CALBACK_f plus the index of the haystack.
+ * Non-zero return stops the search of THAT haystack only.                   */
+typedef int (*ACB200_BATCH_CALLBACK_f)(size_t text_idx, AC_MATCH_t *, void *);
+
+/* Searches n independent haystacks in one device launch; every haystack
+ * starts at the root at offset 0 (the keep=0 rule of php_ahocorasick.c:745).
+ * first_only!=0 reports only the first event of each haystack
+ * (php_ahocorasick.c:588 — findAll=false).  Callbacks arrive ordered by
+ * (text_idx, position).  Returns 0, or -1 on error.                         */
+int ac_trie_search_batch(AC_TRIE_t *thiz, const AC_TEXT_t *texts, size_t n,
+                         int first_only, ACB200_BATCH_CALLBACK_f callback,
+                         void *user);
+
+/* Same, for haystacks already laid end to end in one host buffer:
+ * haystack i is bytes [offsets[i], offsets[i+1]) of `bytes` (n+1 offsets).
+ * Avoids the gather copy; `bytes` may be pinned (acb200_host_alloc).        */
+int ac_trie_search_flat(AC_TRIE_t *thiz, const char *bytes,
+                        const uint64_t *offsets, size_t n, int first_only,
+                        ACB200_BATCH_CALLBACK_f callback, void *user);
+
+/* One raw match event as the device produces it. `end` is the exclusive end
+ * offset inside haystack `text_idx`; `state` indexes the automaton's output
+ * lists (acb200_state_patterns).                                            */
+typedef struct acb200_event
+{
+    uint64_t end;
+    uint32_t state;
+    uint32_t text_idx;
+} ACB200_EVENT_t;
+
+/* Event-level search (no callback replay): fills up to `cap` events sorted by
+ * (text_idx, end) and stores the total number found in *n_events (which may
+ * exceed cap).  Inputs as ac_trie_search_flat.  Returns 0 / -1.             */
+int acb200_search_events(AC_TRIE_t *thiz, const char *bytes,
+                         const uint64_t *offsets, size_t n, int first_only,
+                         ACB200_EVENT_t *events, size_t cap, size_t *n_events);
+
+/* Device-resident variant: `d_bytes` is a CUDA device pointer on the
+ * automaton's device holding total = offsets[n] bytes (offsets is a HOST
+ * array).  Events stay on the device: *d_events receives a device pointer to
+ * packed {uint32 end_in_buffer, uint32 state} records (library-owned, valid
+ * until the next call on this handle), sorted by buffer offset.  `stream` is
+ * a cudaStream_t passed as void* (NULL = the handle's own stream).  The call
+ * returns after the kernels are enqueued and the event count has been read
+ * back.  Used by bench.py's kernel-only leg and by callers that already hold
+ * haystacks in HBM.  Returns 0 / -1.                                        */
+int acb200_search_device(AC_TRIE_t *thiz, const void *d_bytes,
+                         const uint64_t *offsets, size_t n, int first_only,
+                         void *stream, const void **d_events,
+                         size_t *n_events);
+
+/* Patterns reported by automaton state `state` (longest first); returns the
+ * count and stores a library-owned array in *patterns (NULL if none).       */
+size_t acb200_state_patterns(const AC_TRIE_t *thiz, uint32_t state,
+                             const AC_PATTERN_t **patterns);
+
+/* Automaton facts after finalize. */
+typedef struct acb200_info
+{
+    uint64_t n_patterns;      /* accepted patterns                           */
+    uint64_t n_states;        /* automaton states incl. root                 */
+    uint32_t n_classes;       /* byte classes = table columns                */
+    uint32_t entry_bytes;     /* 2 or 4                                      */
+    uint32_t max_pattern_len; /* Lmax of accepted patterns                   */
+    uint32_t first_final;     /* states >= this report patterns              */
+    uint64_t table_bytes;     /* dense transition table in HBM               */
+    int32_t device;           /* CUDA device ordinal                         */
+    int32_t finalized;
+} ACB200_INFO_t;
+int acb200_info(const AC_TRIE_t *thiz, ACB200_INFO_t *out);
+
+/* Statistics of the most recent search on this handle. */
+typedef struct acb200_stats
+{
+    uint64_t bytes;           /* haystack bytes scanned                      */
+    uint64_t events;          /* events found                                */
+    uint64_t kernel_launches; /* this library's kernels launched             */
+    uint32_t chunk_bytes;     /* bytes per thread slice                      */
+    uint32_t halo_bytes;      /* overlap re-read before each slice           */
+    float kernel_ms;          /* device time of the scan kernel(s)           */
+    float h2d_ms, d2h_ms;     /* copies, 0 for the device-resident entry     */
+} ACB200_STATS_t;
+int acb200_last_stats(const AC_TRIE_t *thiz, ACB200_STATS_t *out);
+
+/* Out-of-band error text of the last failed call on this thread ("" if none).
+ * The reference's void/ignored returns leave no room for CUDA errors.       */
+const char *acb200_last_error(void);
+
+/* Device selection for automata finalized afterwards by this thread
+ * (default: env ACB200_DEVICE, else the current CUDA device).               */
+int acb200_set_device(int device);
+int acb200_device_count(void);
+
+/* Pinned host memory for haystacks (optional; pageable memory works too).   */
+void *acb200_host_alloc(size_t bytes);
+void acb200_host_free(void *p);
+
+/* Tuning knobs (0 = automatic). chunk_bytes: bytes per thread slice. */
+int acb200_set_tuning(AC_TRIE_t *thiz, uint32_t chunk_bytes,
+                      uint32_t smem_table_bytes);
+
+const char *acb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ACB200_H_ */

@@ -1,0 +1,262 @@
+// automaton.cpp — see automaton.hpp.
+#include "automaton.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+namespace acb200 {
+
+// ----------------------------------------------------------------- EdgeMap --
+
+static inline uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
+EdgeMap::EdgeMap() : keys_(1024, 0), vals_(1024, 0), used_(0), mask_(1023) {}
+
+uint32_t EdgeMap::find(uint32_t node, uint8_t byte) const {
+    const uint64_t key = (((uint64_t)node << 8) | byte) + 1;
+    size_t i = mix64(key) & mask_;
+    while (true) {
+        const uint64_t k = keys_[i];
+        if (k == key) return vals_[i];
+        if (k == 0) return NONE;
+        i = (i + 1) & mask_;
+    }
+}
+
+void EdgeMap::insert(uint32_t node, uint8_t byte, uint32_t child) {
+    if ((used_ + 1) * 10 > keys_.size() * 6) grow();
+    const uint64_t key = (((uint64_t)node << 8) | byte) + 1;
+    size_t i = mix64(key) & mask_;
+    while (keys_[i] != 0) i = (i + 1) & mask_;
+    keys_[i] = key;
+    vals_[i] = child;
+    ++used_;
+}
+
+void EdgeMap::grow() {
+    std::vector<uint64_t> ok; ok.swap(keys_);
+    std::vector<uint32_t> ov; ov.swap(vals_);
+    keys_.assign(ok.size() * 2, 0);
+    vals_.assign(ok.size() * 2, 0);
+    mask_ = keys_.size() - 1;
+    for (size_t j = 0; j < ok.size(); ++j) {
+        if (!ok[j]) continue;
+        size_t i = mix64(ok[j]) & mask_;
+        while (keys_[i] != 0) i = (i + 1) & mask_;
+        keys_[i] = ok[j];
+        vals_[i] = ov[j];
+    }
+}
+
+// ---------------------------------------------------------------- HostTrie --
+
+HostTrie::HostTrie() {
+    parent_.push_back(0);
+    in_byte_.push_back(0);
+    depth_.push_back(0);
+    own_.push_back(-1);
+}
+
+const char *HostTrie::keep_bytes(const char *p, size_t n) {
+    arena_.emplace_back(p ? p : "", p ? n : 0);
+    return arena_.back().data();
+}
+
+// Acceptance rules of the reference's ac_trie_add (src/multifast/ahocorasick.c:91-131):
+// empty -> ZERO_PATTERN, longer than AC_PATTRN_MAX_LENGTH -> LONG_PATTERN, the
+// path is created first and only then is an already-accepting node reported as
+// DUPLICATE_PATTERN (first pattern wins).  The closed-trie check lives in the
+// C-ABI wrapper, which owns the finalized flag.
+AC_STATUS_t HostTrie::add(const AC_PATTERN_t *patt, int copy) {
+    const size_t len = patt->ptext.length;
+    if (len == 0) return ACERR_ZERO_PATTERN;
+    if (len > AC_PATTRN_MAX_LENGTH) return ACERR_LONG_PATTERN;
+
+    const uint8_t *bytes = (const uint8_t *)patt->ptext.astring;
+    uint32_t n = 0;
+    for (size_t i = 0; i < len; ++i) {
+        uint32_t next = edges_.find(n, bytes[i]);
+        if (next == EdgeMap::NONE) {
+            next = (uint32_t)parent_.size();
+            parent_.push_back(n);
+            in_byte_.push_back(bytes[i]);
+            depth_.push_back((uint16_t)(depth_[n] + 1));
+            own_.push_back(-1);
+            edges_.insert(n, bytes[i], next);
+        }
+        n = next;
+    }
+    if (own_[n] >= 0) return ACERR_DUPLICATE_PATTERN;
+
+    AC_PATTERN_t rec = *patt;
+    if (copy) {
+        // Binary-safe deep copy (the reference's pooled copy is strncpy-based,
+        // src/multifast/mpool.c:174, but is never read on the match path).
+        rec.ptext.astring = keep_bytes(patt->ptext.astring, len);
+        rec.rtext.astring = patt->rtext.length ? keep_bytes(patt->rtext.astring, patt->rtext.length) : NULL;
+        if (patt->id.type == AC_PATTID_TYPE_STRING && patt->id.u.stringy)
+            rec.id.u.stringy = keep_bytes(patt->id.u.stringy, strlen(patt->id.u.stringy));
+    }
+    own_[n] = (int32_t)patterns_.size();
+    patterns_.push_back(rec);
+    return ACERR_SUCCESS;
+}
+
+void HostTrie::release_build_memory() {
+    std::vector<uint32_t>().swap(parent_);
+    std::vector<uint8_t>().swap(in_byte_);
+    std::vector<uint16_t>().swap(depth_);
+    std::vector<int32_t>().swap(own_);
+    edges_ = EdgeMap();
+}
+
+// Breadth-first construction of the automaton the reference builds with its
+// depth-first passes (src/multifast/ahocorasick.c:143-155):
+//  * fail(v)  = deepest trie node that is a proper suffix of path(v), else root
+//               (definition at ahocorasick.c:344-368);
+//  * final(v) = v or any node on its failure chain accepts a pattern
+//               (node.c:432-436);
+//  * matched(v) = own pattern, then the patterns along the failure chain in
+//               chain order = strictly decreasing length (node.c:424-437; the
+//               by-text de-duplication of node.c:150-175 never fires because two
+//               suffixes of one string with equal length are equal).
+void HostTrie::flatten(FlatAutomaton &flat) {
+    const uint32_t N = (uint32_t)parent_.size();
+    const uint32_t NONE = EdgeMap::NONE;
+
+    // children lists (counting sort by parent), each sorted by byte
+    std::vector<uint32_t> child_off(N + 1, 0);
+    for (uint32_t v = 1; v < N; ++v) child_off[parent_[v] + 1]++;
+    for (uint32_t v = 0; v < N; ++v) child_off[v + 1] += child_off[v];
+    std::vector<uint32_t> children(N ? N - 1 : 0);
+    {
+        std::vector<uint32_t> cur(child_off.begin(), child_off.end() - 1);
+        for (uint32_t v = 1; v < N; ++v) children[cur[parent_[v]]++] = v;
+    }
+    for (uint32_t v = 0; v < N; ++v) {
+        auto b = children.begin() + child_off[v], e = children.begin() + child_off[v + 1];
+        if (e - b > 1)
+            std::sort(b, e, [&](uint32_t x, uint32_t y) { return in_byte_[x] < in_byte_[y]; });
+    }
+
+    // BFS order (old ids), level offsets
+    std::vector<uint32_t> order; order.reserve(N);
+    std::vector<uint32_t> level_off;
+    order.push_back(0);
+    level_off.push_back(0);
+    size_t head = 0;
+    while (head < order.size()) {
+        const size_t level_end = order.size();
+        for (; head < level_end; ++head) {
+            const uint32_t v = order[head];
+            for (uint32_t k = child_off[v]; k < child_off[v + 1]; ++k) order.push_back(children[k]);
+        }
+        level_off.push_back((uint32_t)level_end);   // end of this level = start of the next
+    }
+
+    // failure + dictionary-suffix links in BFS order
+    std::vector<uint32_t> fail(N, 0), dlink(N, NONE);
+    std::vector<uint8_t> is_final(N, 0);
+    for (uint32_t idx = 1; idx < N; ++idx) {
+        const uint32_t v = order[idx];
+        const uint32_t p = parent_[v];
+        const uint8_t c = in_byte_[v];
+        uint32_t f = 0;
+        if (p != 0) {
+            uint32_t g = fail[p];
+            while (true) {
+                const uint32_t t = edges_.find(g, c);
+                if (t != NONE) { f = t; break; }
+                if (g == 0) { f = 0; break; }
+                g = fail[g];
+            }
+        }
+        fail[v] = f;
+        dlink[v] = (own_[f] >= 0) ? f : dlink[f];
+        is_final[v] = (own_[v] >= 0 || dlink[v] != NONE) ? 1 : 0;
+    }
+
+    // final numbering: non-final states breadth-first from 0, final states after them
+    uint32_t n_final = 0;
+    for (uint32_t v = 0; v < N; ++v) n_final += is_final[v];
+    const uint32_t first_final = N - n_final;
+    std::vector<uint32_t> newid(N);
+    {
+        uint32_t a = 0, b = first_final;
+        for (uint32_t idx = 0; idx < N; ++idx) {
+            const uint32_t v = order[idx];
+            newid[v] = is_final[v] ? b++ : a++;
+        }
+    }
+
+    flat.n_states = N;
+    flat.first_final = first_final;
+
+    // byte classes
+    bool used[256] = {false};
+    for (uint32_t v = 1; v < N; ++v) used[in_byte_[v]] = true;
+    uint32_t n_used = 0; int lo = -1, hi = -1;
+    for (int b = 0; b < 256; ++b) if (used[b]) { if (lo < 0) lo = b; hi = b; ++n_used; }
+    flat.n_used_bytes = n_used;
+    flat.n_classes = n_used + (n_used < 256 ? 1 : 0);
+    flat.range_map = (n_used == 0) || ((uint32_t)(hi - lo + 1) == n_used);
+    flat.range_lo = n_used ? (uint32_t)lo : 0;
+    {
+        uint32_t r = 0;
+        for (int b = 0; b < 256; ++b) flat.cls_map[b] = used[b] ? (uint8_t)(r++) : (uint8_t)n_used;
+        // n_used == 256 never takes the else branch; n_used < 256 keeps the value <= 255
+    }
+
+    // device expansion inputs
+    flat.bfs_order.resize(N);
+    flat.fail.resize(N);
+    for (uint32_t idx = 0; idx < N; ++idx) flat.bfs_order[idx] = newid[order[idx]];
+    for (uint32_t v = 0; v < N; ++v) flat.fail[newid[v]] = newid[fail[v]];
+    flat.level_off = level_off;
+    const size_t n_levels = level_off.size() - 1;
+    flat.edge_src.clear(); flat.edge_dst.clear(); flat.edge_cls.clear();
+    flat.edge_src.reserve(N); flat.edge_dst.reserve(N); flat.edge_cls.reserve(N);
+    flat.level_edge_off.assign(n_levels + 1, 0);
+    for (size_t d = 0; d < n_levels; ++d) {
+        flat.level_edge_off[d] = (uint32_t)flat.edge_src.size();
+        for (uint32_t idx = level_off[d]; idx < level_off[d + 1]; ++idx) {
+            const uint32_t v = order[idx];
+            for (uint32_t k = child_off[v]; k < child_off[v + 1]; ++k) {
+                const uint32_t w = children[k];
+                flat.edge_src.push_back(newid[v]);
+                flat.edge_dst.push_back(newid[w]);
+                flat.edge_cls.push_back(flat.cls_map[in_byte_[w]]);
+            }
+        }
+    }
+    flat.level_edge_off[n_levels] = (uint32_t)flat.edge_src.size();
+
+    // output lists, indexed by (state - first_final)
+    flat.max_pattern_len = 0;
+    for (const AC_PATTERN_t &p : patterns_)
+        flat.max_pattern_len = std::max<uint32_t>(flat.max_pattern_len, (uint32_t)p.ptext.length);
+    std::vector<uint32_t> old_of_final(n_final);
+    for (uint32_t v = 0; v < N; ++v) if (is_final[v]) old_of_final[newid[v] - first_final] = v;
+    flat.out_off.assign((size_t)n_final + 1, 0);
+    for (uint32_t i = 0; i < n_final; ++i) {
+        uint64_t cnt = 0;
+        uint32_t v = old_of_final[i];
+        if (own_[v] >= 0) ++cnt;
+        for (uint32_t d = dlink[v]; d != NONE; d = dlink[d]) ++cnt;
+        flat.out_off[i + 1] = flat.out_off[i] + cnt;
+    }
+    flat.out_pat.resize(flat.out_off[n_final]);
+    for (uint32_t i = 0; i < n_final; ++i) {
+        uint64_t o = flat.out_off[i];
+        uint32_t v = old_of_final[i];
+        if (own_[v] >= 0) flat.out_pat[o++] = patterns_[own_[v]];
+        for (uint32_t d = dlink[v]; d != NONE; d = dlink[d]) flat.out_pat[o++] = patterns_[own_[d]];
+    }
+}
+
+} // namespace acb200

@@ -1,0 +1,87 @@
+// automaton.hpp — host side of ahocorasick_finalize(): byte trie with the
+// reference's acceptance rules, breadth-first failure/output links, and the
+// flat description the device expands into the dense transition table.
+//
+// Semantics follow (not the code of) the reference:
+//   acceptance rules        src/multifast/ahocorasick.c:91-131
+//   failure link definition src/multifast/ahocorasick.c:344-368
+//   output lists + finality src/multifast/node.c:424-441
+#pragma once
+
+#include <cstdint>
+#include <cstddef>
+#include <string>
+#include <vector>
+#include <deque>
+
+#include "acb200.h"
+
+namespace acb200 {
+
+// Open-addressing map (state, byte) -> child used while patterns are added.
+class EdgeMap {
+public:
+    EdgeMap();
+    uint32_t find(uint32_t node, uint8_t byte) const;   // NONE if absent
+    void insert(uint32_t node, uint8_t byte, uint32_t child);
+    size_t size() const { return used_; }
+    static constexpr uint32_t NONE = 0xffffffffu;
+private:
+    void grow();
+    std::vector<uint64_t> keys_;   // ((node << 8) | byte) + 1 ; 0 = empty slot
+    std::vector<uint32_t> vals_;
+    size_t used_ = 0;
+    size_t mask_ = 0;
+};
+
+// Flat automaton in FINAL state numbering: all pattern-reporting ("final")
+// states have ids >= first_final, both groups ordered breadth-first so that the
+// shallow, hot rows of the table are contiguous from id 0.
+struct FlatAutomaton {
+    uint32_t n_states = 1;
+    uint32_t n_classes = 1;       // table columns
+    uint32_t first_final = 1;     // == n_states when nothing is final
+    uint32_t max_pattern_len = 0; // Lmax over accepted patterns
+    uint32_t n_used_bytes = 0;
+    uint8_t  cls_map[256];        // byte -> column; unused bytes share the last column
+    bool     range_map = true;    // used bytes are one contiguous range [range_lo, range_lo+n_used)
+    uint32_t range_lo = 0;
+
+    // breadth-first description consumed by the device expansion kernels
+    std::vector<uint32_t> bfs_order;       // state ids level by level (root first)
+    std::vector<uint32_t> level_off;       // level d = bfs_order[level_off[d] .. level_off[d+1])
+    std::vector<uint32_t> fail;            // failure state per state id
+    std::vector<uint32_t> edge_src;        // trie edges grouped by depth of src (same grouping as level_off)
+    std::vector<uint32_t> edge_dst;
+    std::vector<uint16_t> edge_cls;
+    std::vector<uint32_t> level_edge_off;  // edges leaving level d = [level_edge_off[d], level_edge_off[d+1])
+
+    // output lists for final states (index: state - first_final), longest pattern first
+    std::vector<uint64_t> out_off;
+    std::vector<AC_PATTERN_t> out_pat;
+};
+
+class HostTrie {
+public:
+    HostTrie();
+    AC_STATUS_t add(const AC_PATTERN_t *patt, int copy);
+    // Computes links and fills `flat`. Idempotent guard is the caller's job.
+    void flatten(FlatAutomaton &flat);
+
+    size_t n_nodes() const { return parent_.size(); }
+    size_t n_patterns() const { return patterns_.size(); }
+    void release_build_memory();
+
+private:
+    const char *keep_bytes(const char *p, size_t n);
+
+    std::vector<uint32_t> parent_;
+    std::vector<uint8_t>  in_byte_;
+    std::vector<uint16_t> depth_;
+    std::vector<int32_t>  own_;          // index into patterns_ or -1
+    EdgeMap edges_;
+    std::vector<AC_PATTERN_t> patterns_; // accepted patterns, acceptance order
+    std::deque<std::string> arena_;      // owned copies of pattern bytes / string ids
+};
+
+} // namespace acb200

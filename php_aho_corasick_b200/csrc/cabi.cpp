@@ -1,0 +1,244 @@
+// cabi.cpp — extern "C" surface declared in include/acb200.h.
+//
+// Mirrors the five MultiFast entry points the reference's Zend glue calls
+// (src/multifast/ahocorasick.h:73-80) and adds the batched / event-level /
+// device-resident entry points.  The device does the scan; this file replays
+// the compact (position, state) events through the caller's callback exactly
+// as the reference's loop would have called it
+// (src/multifast/ahocorasick.c:214-233).
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime_api.h>
+
+#include "acb200.h"
+#include "automaton.hpp"
+#include "engine.hpp"
+
+using namespace acb200;
+
+struct ac_trie {
+    HostTrie trie;
+    FlatAutomaton flat;
+    Engine engine;
+    bool open = true;          // patterns may still be added (reference: trie_open)
+    bool device_ok = false;    // finalize reached the device
+    uint32_t last_state = 0;   // keep=1 continuation (reference: last_node)
+    size_t base_position = 0;  // keep=1 continuation (reference: base_position)
+    std::vector<char> gather;  // batch gather buffer
+    std::vector<uint64_t> gather_off;
+};
+
+static inline size_t patterns_of(const ac_trie *t, uint32_t state, const AC_PATTERN_t **p)
+{
+    if (state < t->flat.first_final || state >= t->flat.n_states) { if (p) *p = nullptr; return 0; }
+    const uint32_t i = state - t->flat.first_final;
+    const uint64_t b = t->flat.out_off[i], e = t->flat.out_off[i + 1];
+    if (p) *p = t->flat.out_pat.data() + b;
+    return (size_t)(e - b);
+}
+
+extern "C" {
+
+const char *acb200_version(void) { return "acb200 0.1 (sm_100a)"; }
+const char *acb200_last_error(void) { return get_error(); }
+
+int acb200_set_device(int device) { set_preferred_device(device); return 0; }
+
+int acb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+void *acb200_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        set_error("cudaMallocHost failed");
+        return nullptr;
+    }
+    return p;
+}
+
+void acb200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+AC_TRIE_t *ac_trie_create(void)
+{
+    return new (std::nothrow) ac_trie();
+}
+
+AC_STATUS_t ac_trie_add(AC_TRIE_t *t, AC_PATTERN_t *patt, int copy)
+{
+    if (!t->open) return ACERR_TRIE_CLOSED;      // src/multifast/ahocorasick.c:98-99
+    return t->trie.add(patt, copy);
+}
+
+void ac_trie_finalize(AC_TRIE_t *t)
+{
+    if (!t->open) return;
+    t->trie.flatten(t->flat);
+    t->open = false;                             // src/multifast/ahocorasick.c:154
+    set_error("");
+    t->device_ok = t->engine.build(t->flat);
+    t->engine.info.n_patterns = t->trie.n_patterns();
+    t->engine.info.finalized = 1;
+    t->trie.release_build_memory();
+    // the expansion inputs are only needed once
+    std::vector<uint32_t>().swap(t->flat.bfs_order);
+    std::vector<uint32_t>().swap(t->flat.fail);
+    std::vector<uint32_t>().swap(t->flat.edge_src);
+    std::vector<uint32_t>().swap(t->flat.edge_dst);
+    std::vector<uint16_t>().swap(t->flat.edge_cls);
+}
+
+int ac_trie_search(AC_TRIE_t *t, AC_TEXT_t *text, int keep, AC_MATCH_CALBACK_f callback, void *user)
+{
+    if (t->open) return -1;                      // src/multifast/ahocorasick.c:183-184
+    if (!t->device_ok) return -1;
+    if (!keep) { t->last_state = 0; t->base_position = 0; }   // ac_trie_reset, ahocorasick.c:330-335
+    const uint64_t offs[2] = {0, (uint64_t)text->length};
+    if (!t->engine.scan_host(text->astring, offs, 1, false, t->last_state)) return -1;
+    const PackedEvent *ev = t->engine.host_events();
+    const size_t n = t->engine.n_events();
+    for (size_t i = 0; i < n; ++i) {
+        const AC_PATTERN_t *pats;
+        AC_MATCH_t m;
+        m.size = patterns_of(t, ev[i].state, &pats);
+        m.patterns = const_cast<AC_PATTERN_t *>(pats);
+        m.position = (size_t)ev[i].end + t->base_position;
+        if (callback(&m, user)) return 1;        // state is not saved on a stop (ahocorasick.c:226-232)
+    }
+    t->last_state = t->engine.end_state();       // ahocorasick.c:236-238
+    t->base_position += text->length;
+    return 0;
+}
+
+static int replay_batch(ac_trie *t, const uint64_t *offsets, size_t n, int first_only,
+                        ACB200_BATCH_CALLBACK_f callback, void *user)
+{
+    const PackedEvent *ev = t->engine.host_events();
+    const size_t ne = t->engine.n_events();
+    size_t h = 0;
+    size_t stopped = (size_t)-1;                 // haystack whose callback asked to stop
+    for (size_t i = 0; i < ne; ++i) {
+        const uint64_t end = ev[i].end;
+        while (h < n && end > offsets[h + 1]) ++h;
+        if (h == stopped) continue;
+        const AC_PATTERN_t *pats;
+        AC_MATCH_t m;
+        m.size = patterns_of(t, ev[i].state, &pats);
+        m.patterns = const_cast<AC_PATTERN_t *>(pats);
+        m.position = (size_t)(end - offsets[h]);
+        const int r = callback(h, &m, user);
+        if (r || first_only) stopped = h;
+    }
+    return 0;
+}
+
+int ac_trie_search_flat(AC_TRIE_t *t, const char *bytes, const uint64_t *offsets, size_t n,
+                        int first_only, ACB200_BATCH_CALLBACK_f callback, void *user)
+{
+    if (t->open) { set_error("automaton is not finalized"); return -1; }
+    if (!t->device_ok) return -1;
+    if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return -1; }
+    if (!t->engine.scan_host(bytes, offsets, n, first_only != 0, 0)) return -1;
+    return replay_batch(t, offsets, n, first_only, callback, user);
+}
+
+int ac_trie_search_batch(AC_TRIE_t *t, const AC_TEXT_t *texts, size_t n, int first_only,
+                         ACB200_BATCH_CALLBACK_f callback, void *user)
+{
+    if (t->open) { set_error("automaton is not finalized"); return -1; }
+    if (!t->device_ok) return -1;
+    t->gather_off.resize(n + 1);
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; ++i) { t->gather_off[i] = total; total += texts[i].length; }
+    t->gather_off[n] = total;
+    if (t->gather.size() < total) t->gather.resize(total);
+    for (size_t i = 0; i < n; ++i)
+        if (texts[i].length) memcpy(t->gather.data() + t->gather_off[i], texts[i].astring, texts[i].length);
+    if (!t->engine.scan_host(t->gather.data(), t->gather_off.data(), n, first_only != 0, 0)) return -1;
+    return replay_batch(t, t->gather_off.data(), n, first_only, callback, user);
+}
+
+int acb200_search_events(AC_TRIE_t *t, const char *bytes, const uint64_t *offsets, size_t n,
+                         int first_only, ACB200_EVENT_t *events, size_t cap, size_t *n_events)
+{
+    if (t->open) { set_error("automaton is not finalized"); return -1; }
+    if (!t->device_ok) return -1;
+    if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return -1; }
+    if (!t->engine.scan_host(bytes, offsets, n, first_only != 0, 0)) return -1;
+    const PackedEvent *ev = t->engine.host_events();
+    const size_t ne = t->engine.n_events();
+    size_t h = 0, w = 0;
+    size_t last_h = (size_t)-1;
+    for (size_t i = 0; i < ne; ++i) {
+        const uint64_t end = ev[i].end;
+        while (h < n && end > offsets[h + 1]) ++h;
+        if (first_only) { if (h == last_h) continue; last_h = h; }
+        if (w < cap) {
+            events[w].end = end - offsets[h];
+            events[w].state = ev[i].state;
+            events[w].text_idx = (uint32_t)h;
+        }
+        ++w;
+    }
+    if (n_events) *n_events = w;
+    return 0;
+}
+
+int acb200_search_device(AC_TRIE_t *t, const void *d_bytes, const uint64_t *offsets, size_t n,
+                         int first_only, void *stream, const void **d_events, size_t *n_events)
+{
+    if (t->open) { set_error("automaton is not finalized"); return -1; }
+    if (!t->device_ok) return -1;
+    if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return -1; }
+    if (!t->engine.scan_device(d_bytes, offsets, n, first_only != 0, 0, stream)) return -1;
+    if (d_events) *d_events = t->engine.device_events();
+    if (n_events) *n_events = t->engine.n_events();
+    return 0;
+}
+
+size_t acb200_state_patterns(const AC_TRIE_t *t, uint32_t state, const AC_PATTERN_t **patterns)
+{
+    if (t->open) { if (patterns) *patterns = nullptr; return 0; }
+    return patterns_of(t, state, patterns);
+}
+
+int acb200_info(const AC_TRIE_t *t, ACB200_INFO_t *out)
+{
+    if (!out) return -1;
+    *out = t->engine.info;
+    out->n_patterns = t->open ? t->trie.n_patterns() : t->engine.info.n_patterns;
+    out->finalized = t->open ? 0 : 1;
+    if (t->open || !t->device_ok) {
+        out->n_states = t->open ? t->trie.n_nodes() : t->flat.n_states;
+        out->device = -1;
+    }
+    return 0;
+}
+
+int acb200_last_stats(const AC_TRIE_t *t, ACB200_STATS_t *out)
+{
+    if (!out) return -1;
+    *out = t->engine.stats;
+    return 0;
+}
+
+int acb200_set_tuning(AC_TRIE_t *t, uint32_t chunk_bytes, uint32_t smem_table_bytes)
+{
+    t->engine.tune_chunk = chunk_bytes;
+    t->engine.tune_smem_bytes = smem_table_bytes;
+    return 0;
+}
+
+void ac_trie_release(AC_TRIE_t *t)
+{
+    delete t;
+}
+
+} // extern "C"

@@ -1,0 +1,425 @@
+// engine.cu — see engine.hpp.
+#include "engine.hpp"
+#include "scan_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace acb200 {
+
+// ------------------------------------------------------------ error state --
+
+static thread_local std::string g_error;
+static thread_local int g_device = -2;   // -2: not chosen yet
+
+void set_error(const std::string &msg) { g_error = msg; }
+const char *get_error() { return g_error.c_str(); }
+
+int preferred_device()
+{
+    if (g_device == -2) {
+        const char *e = getenv("ACB200_DEVICE");
+        if (e && *e) g_device = atoi(e);
+        else {
+            int d = 0;
+            if (cudaGetDevice(&d) != cudaSuccess) d = 0;
+            g_device = d;
+        }
+    }
+    return g_device;
+}
+void set_preferred_device(int d) { g_device = d; }
+
+#define CU_OK(call)                                                                        \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                 \
+            return false;                                                                  \
+        }                                                                                  \
+    } while (0)
+
+static inline cudaStream_t S(void *p) { return static_cast<cudaStream_t>(p); }
+static inline cudaEvent_t EV(void *p) { return static_cast<cudaEvent_t>(p); }
+
+// --------------------------------------------------------------- lifetime --
+
+Engine::Engine() {}
+Engine::~Engine() { release(); }
+
+void Engine::release()
+{
+    if (device_ < 0) return;
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(S(stream_));
+    cudaFree(d_table_); cudaFree(d_cls_); cudaFree(d_text_); cudaFree(d_off_);
+    cudaFree(d_first_); cudaFree(d_events_); cudaFree(d_tiles_); cudaFree(d_counters_);
+    if (h_counters_) cudaFreeHost(h_counters_);
+    if (h_events_) cudaFreeHost(h_events_);
+    if (h_stage_) cudaFreeHost(h_stage_);
+    for (auto &e : ev_) if (e) { cudaEventDestroy(EV(e)); e = nullptr; }
+    if (stream_) cudaStreamDestroy(S(stream_));
+    d_table_ = nullptr; d_cls_ = nullptr; d_text_ = nullptr; d_off_ = nullptr; d_first_ = nullptr;
+    d_events_ = nullptr; d_tiles_ = nullptr; d_counters_ = nullptr;
+    h_counters_ = nullptr; h_events_ = nullptr; h_stage_ = nullptr; stream_ = nullptr;
+    device_ = -1;
+}
+
+// --------------------------------------------------------------- finalize --
+
+template <typename E>
+static bool expand_table(E *table, const FlatAutomaton &f, cudaStream_t st, uint64_t *launches)
+{
+    const uint32_t N = f.n_states;
+    uint32_t *d_order = nullptr, *d_fail = nullptr, *d_src = nullptr, *d_dst = nullptr;
+    uint16_t *d_cls = nullptr;
+    const size_t ne = f.edge_src.size();
+    bool ok = true;
+    auto fail_with = [&](const char *what, cudaError_t e) {
+        set_error(std::string(what) + ": " + cudaGetErrorString(e));
+        ok = false;
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_order, sizeof(uint32_t) * N)) != cudaSuccess) fail_with("cudaMalloc(order)", e);
+    if (ok && (e = cudaMalloc(&d_fail, sizeof(uint32_t) * N)) != cudaSuccess) fail_with("cudaMalloc(fail)", e);
+    if (ok && ne) {
+        if ((e = cudaMalloc(&d_src, sizeof(uint32_t) * ne)) != cudaSuccess) fail_with("cudaMalloc(edge_src)", e);
+        if (ok && (e = cudaMalloc(&d_dst, sizeof(uint32_t) * ne)) != cudaSuccess) fail_with("cudaMalloc(edge_dst)", e);
+        if (ok && (e = cudaMalloc(&d_cls, sizeof(uint16_t) * ne)) != cudaSuccess) fail_with("cudaMalloc(edge_cls)", e);
+    }
+    if (ok) {
+        cudaMemcpyAsync(d_order, f.bfs_order.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_fail, f.fail.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st);
+        if (ne) {
+            cudaMemcpyAsync(d_src, f.edge_src.data(), sizeof(uint32_t) * ne, cudaMemcpyHostToDevice, st);
+            cudaMemcpyAsync(d_dst, f.edge_dst.data(), sizeof(uint32_t) * ne, cudaMemcpyHostToDevice, st);
+            cudaMemcpyAsync(d_cls, f.edge_cls.data(), sizeof(uint16_t) * ne, cudaMemcpyHostToDevice, st);
+        }
+        const size_t n_levels = f.level_off.size() - 1;
+        for (size_t d = 0; d < n_levels; ++d) {
+            const uint32_t lb = f.level_off[d], le = f.level_off[d + 1];
+            const unsigned long long cells = (unsigned long long)(le - lb) * f.n_classes;
+            if (cells) {
+                const unsigned blocks = (unsigned)((cells + EXPAND_THREADS - 1) / EXPAND_THREADS);
+                expand_inherit_kernel<E><<<blocks, EXPAND_THREADS, 0, st>>>(table, d_order, d_fail, lb, le, f.n_classes);
+                ++*launches;
+            }
+            const uint32_t eb = f.level_edge_off[d], ee = f.level_edge_off[d + 1];
+            if (ee > eb) {
+                const unsigned blocks = (ee - eb + EXPAND_THREADS - 1) / EXPAND_THREADS;
+                expand_edges_kernel<E><<<blocks, EXPAND_THREADS, 0, st>>>(table, d_src, d_dst, d_cls, eb, ee, f.n_classes);
+                ++*launches;
+            }
+        }
+        if ((e = cudaGetLastError()) != cudaSuccess) fail_with("expand launch", e);
+        if (ok && (e = cudaStreamSynchronize(st)) != cudaSuccess) fail_with("expand sync", e);
+    }
+    cudaFree(d_order); cudaFree(d_fail); cudaFree(d_src); cudaFree(d_dst); cudaFree(d_cls);
+    return ok;
+}
+
+template <typename E, bool RANGE, bool FIRST>
+static cudaError_t set_smem_attr(int bytes)
+{
+    return cudaFuncSetAttribute(ac_scan_kernel<E, RANGE, FIRST>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+bool Engine::build(const FlatAutomaton &f)
+{
+    int n_dev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n_dev);
+    if (ce != cudaSuccess || n_dev == 0) {
+        set_error(std::string("no CUDA device available: ") + cudaGetErrorString(ce));
+        return false;
+    }
+    int dev = preferred_device();
+    if (dev < 0 || dev >= n_dev) { set_error("ACB200 device ordinal out of range"); return false; }
+    CU_OK(cudaSetDevice(dev));
+    device_ = dev;
+    cudaDeviceProp prop;
+    CU_OK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) {
+        set_error("libacb200 is built for sm_100a (B200) only; found " + std::string(prop.name));
+        return false;
+    }
+    n_sms_ = prop.multiProcessorCount;
+    max_smem_optin_ = (int)prop.sharedMemPerBlockOptin;
+
+    cudaStream_t st;
+    CU_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    stream_ = st;
+    for (auto &e : ev_) { cudaEvent_t x; CU_OK(cudaEventCreate(&x)); e = x; }
+
+    n_states_ = f.n_states; ncls_ = f.n_classes; first_final_ = f.first_final;
+    halo_ = f.max_pattern_len ? f.max_pattern_len - 1 : 0;
+    range_map_ = f.range_map; range_lo_ = f.range_lo; n_used_ = f.n_used_bytes;
+    table_entries_ = (uint64_t)n_states_ * ncls_;
+    if (table_entries_ >= (1ull << 32)) {
+        set_error("automaton too large: states x classes must stay below 2^32 table entries");
+        return false;
+    }
+    entry_bytes_ = (n_states_ <= 65536u) ? 2 : 4;
+    const size_t table_bytes = (size_t)table_entries_ * entry_bytes_;
+
+    CU_OK(cudaMalloc(&d_table_, table_bytes + 16));
+    CU_OK(cudaMalloc(&d_cls_, 256));
+    CU_OK(cudaMemcpyAsync(d_cls_, f.cls_map, 256, cudaMemcpyHostToDevice, st));
+    CU_OK(cudaMalloc(&d_counters_, 64));
+    CU_OK(cudaMemsetAsync(d_counters_, 0, 64, st));
+    CU_OK(cudaMallocHost(&h_counters_, 64));
+
+    uint64_t launches = 0;
+    bool ok = (entry_bytes_ == 2) ? expand_table<uint16_t>((uint16_t *)d_table_, f, st, &launches)
+                                  : expand_table<uint32_t>((uint32_t *)d_table_, f, st, &launches);
+    if (!ok) return false;
+
+    const int dyn = max_smem_optin_ - 2048;   // static shared memory of the kernel + slack
+    CU_OK((set_smem_attr<uint16_t, true, false>(dyn)));
+    CU_OK((set_smem_attr<uint16_t, true, true>(dyn)));
+    CU_OK((set_smem_attr<uint16_t, false, false>(dyn)));
+    CU_OK((set_smem_attr<uint16_t, false, true>(dyn)));
+    CU_OK((set_smem_attr<uint32_t, true, false>(dyn)));
+    CU_OK((set_smem_attr<uint32_t, true, true>(dyn)));
+    CU_OK((set_smem_attr<uint32_t, false, false>(dyn)));
+    CU_OK((set_smem_attr<uint32_t, false, true>(dyn)));
+
+    info.n_states = n_states_;
+    info.n_classes = ncls_;
+    info.entry_bytes = (uint32_t)entry_bytes_;
+    info.max_pattern_len = f.max_pattern_len;
+    info.first_final = first_final_;
+    info.table_bytes = table_bytes;
+    info.device = device_;
+    stats = ACB200_STATS_t{};
+    stats.kernel_launches = launches;
+    return true;
+}
+
+// ---------------------------------------------------------------- scratch --
+
+bool Engine::ensure_text(size_t bytes)
+{
+    if (bytes <= text_cap_) return true;
+    cudaFree(d_text_); d_text_ = nullptr; text_cap_ = 0;
+    const size_t cap = std::max(bytes + bytes / 4, (size_t)1 << 20);
+    CU_OK(cudaMalloc(&d_text_, cap));
+    text_cap_ = cap;
+    return true;
+}
+
+bool Engine::ensure_events(size_t n)
+{
+    if (n <= events_cap_) return true;
+    cudaFree(d_events_); d_events_ = nullptr; events_cap_ = 0;
+    CU_OK(cudaMalloc(&d_events_, n * sizeof(PackedEvent)));
+    events_cap_ = n;
+    return true;
+}
+
+bool Engine::ensure_host_events(size_t n)
+{
+    if (n <= h_events_cap_) return true;
+    if (h_events_) cudaFreeHost(h_events_);
+    h_events_ = nullptr; h_events_cap_ = 0;
+    const size_t cap = std::max(n + n / 4, (size_t)4096);
+    CU_OK(cudaMallocHost(&h_events_, cap * sizeof(PackedEvent)));
+    h_events_cap_ = cap;
+    return true;
+}
+
+bool Engine::ensure_offsets(size_t n)
+{
+    if (n > off_cap_) {
+        cudaFree(d_off_); d_off_ = nullptr; off_cap_ = 0;
+        const size_t cap = std::max(n + n / 4, (size_t)1024);
+        CU_OK(cudaMalloc(&d_off_, cap * sizeof(uint32_t)));
+        off_cap_ = cap;
+    }
+    return true;
+}
+
+bool Engine::ensure_tiles(size_t n)
+{
+    if (n <= tiles_cap_) return true;
+    cudaFree(d_tiles_); d_tiles_ = nullptr; tiles_cap_ = 0;
+    const size_t cap = std::max(n + n / 4, (size_t)1024);
+    CU_OK(cudaMalloc(&d_tiles_, cap * sizeof(unsigned long long)));
+    tiles_cap_ = cap;
+    return true;
+}
+
+// Converts the caller's 64-bit offsets to the 32-bit device array.  Batches whose
+// haystacks all have one length need no array at all (*uniform_len > 0).
+bool Engine::upload_offsets(const uint64_t *offsets, size_t n, uint32_t *uniform_len)
+{
+    *uniform_len = 0;
+    const uint64_t total = offsets[n];
+    if (n <= 1 || total == 0) { *uniform_len = (uint32_t)std::max<uint64_t>(total, 1); return true; }
+    const uint64_t L = offsets[1] - offsets[0];
+    bool uniform = L > 0;
+    for (size_t i = 1; uniform && i < n; ++i) uniform = (offsets[i + 1] - offsets[i]) == L;
+    if (uniform) { *uniform_len = (uint32_t)L; return true; }
+    off32_.resize(n + 1);
+    for (size_t i = 0; i <= n; ++i) off32_[i] = (uint32_t)offsets[i];
+    if (!ensure_offsets(n + 1)) return false;
+    CU_OK(cudaMemcpyAsync(d_off_, off32_.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, S(stream_)));
+    return true;
+}
+
+// ------------------------------------------------------------------- scan --
+
+uint32_t Engine::pick_chunk(uint64_t total) const
+{
+    if (tune_chunk) return std::max(16u, (tune_chunk + 15u) & ~15u);
+    // Enough slices to give every SM several tiles, but each slice long enough
+    // that re-reading the (Lmax-1)-byte halo stays a small fraction of the work.
+    const uint64_t want_slices = (uint64_t)n_sms_ * SCAN_THREADS * 4;
+    uint64_t c = total / std::max<uint64_t>(want_slices, 1);
+    const uint64_t lo = std::max<uint64_t>(64, (uint64_t)halo_ * 8);
+    c = std::max(c, lo);
+    c = std::min<uint64_t>(c, std::max<uint64_t>(4096, lo));
+    return (uint32_t)((c + 15) & ~15ull);
+}
+
+template <typename E, bool RANGE, bool FIRST>
+static void launch_kernel(const ScanArgs &a, unsigned grid, size_t smem, cudaStream_t st)
+{
+    ac_scan_kernel<E, RANGE, FIRST><<<grid, SCAN_THREADS, smem, st>>>(a);
+}
+
+bool Engine::launch_scan(const void *d_text, uint32_t total, size_t n_hay, uint32_t uniform_len,
+                         bool first_only, uint32_t init_state, void *stream)
+{
+    cudaStream_t st = stream ? S(stream) : S(stream_);
+    n_events_ = 0;
+    end_state_ = init_state;
+    stats.bytes = total; stats.events = 0; stats.kernel_launches = 0; stats.kernel_ms = 0;
+    stats.halo_bytes = halo_;
+    if (total == 0) { stats.chunk_bytes = 0; return true; }
+
+    const uint32_t chunk = pick_chunk(total);
+    const uint32_t n_chunks = (uint32_t)(((uint64_t)total + chunk - 1) / chunk);
+    const uint32_t n_tiles = (n_chunks + SCAN_THREADS - 1) / SCAN_THREADS;
+    stats.chunk_bytes = chunk;
+    if (!ensure_tiles(n_tiles)) return false;
+    if (events_cap_ == 0 && !ensure_events(std::max<size_t>(1 << 16, total / 64))) return false;
+    if (first_only) {
+        if (n_hay > first_cap_) {
+            cudaFree(d_first_); d_first_ = nullptr; first_cap_ = 0;
+            CU_OK(cudaMalloc(&d_first_, (n_hay + n_hay / 4 + 16) * sizeof(uint32_t)));
+            first_cap_ = n_hay + n_hay / 4 + 16;
+        }
+    }
+
+    const int dyn_max = max_smem_optin_ - 2048;
+    size_t smem_budget = (size_t)dyn_max;
+    if (tune_smem_bytes) smem_budget = std::min<size_t>(smem_budget, tune_smem_bytes);
+    uint64_t smem_entries = std::min<uint64_t>(table_entries_, smem_budget / entry_bytes_);
+    const size_t smem_bytes = (size_t)smem_entries * entry_bytes_;
+
+    ScanArgs a{};
+    a.text = (const uint8_t *)d_text;
+    a.hay_off = uniform_len ? nullptr : d_off_;
+    a.n_hay = (uint32_t)n_hay;
+    a.uniform_len = uniform_len;
+    a.total = total;
+    a.chunk = chunk;
+    a.halo = halo_;
+    a.chunk_begin = 0;
+    a.chunk_end = n_chunks;
+    a.n_tiles = n_tiles;
+    a.table = d_table_;
+    a.cls_map = d_cls_;
+    a.ncls = ncls_;
+    a.first_final = first_final_;
+    a.smem_entries = (uint32_t)smem_entries;
+    a.range_lo = range_lo_;
+    a.n_used = n_used_;
+    a.init_state = init_state;
+    a.tile_status = d_tiles_;
+    a.counters = d_counters_;
+    a.first_end = d_first_;
+    const unsigned grid = std::min<uint32_t>(n_tiles, (uint32_t)n_sms_);
+
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        a.out = (uint2 *)d_events_;
+        a.capacity = (uint32_t)std::min<size_t>(events_cap_, 0xffffffffu);
+        CU_OK(cudaMemsetAsync(d_tiles_, 0, (size_t)n_tiles * sizeof(unsigned long long), st));
+        CU_OK(cudaMemsetAsync(d_counters_, 0, 16, st));
+        if (first_only) CU_OK(cudaMemsetAsync(d_first_, 0xff, n_hay * sizeof(uint32_t), st));
+        CU_OK(cudaEventRecord(EV(ev_[0]), st));
+        if (entry_bytes_ == 2) {
+            if (range_map_) { if (first_only) launch_kernel<uint16_t, true, true>(a, grid, smem_bytes, st); else launch_kernel<uint16_t, true, false>(a, grid, smem_bytes, st); }
+            else            { if (first_only) launch_kernel<uint16_t, false, true>(a, grid, smem_bytes, st); else launch_kernel<uint16_t, false, false>(a, grid, smem_bytes, st); }
+        } else {
+            if (range_map_) { if (first_only) launch_kernel<uint32_t, true, true>(a, grid, smem_bytes, st); else launch_kernel<uint32_t, true, false>(a, grid, smem_bytes, st); }
+            else            { if (first_only) launch_kernel<uint32_t, false, true>(a, grid, smem_bytes, st); else launch_kernel<uint32_t, false, false>(a, grid, smem_bytes, st); }
+        }
+        CU_OK(cudaGetLastError());
+        CU_OK(cudaEventRecord(EV(ev_[1]), st));
+        stats.kernel_launches += 1;
+        CU_OK(cudaMemcpyAsync(h_counters_, d_counters_, 16, cudaMemcpyDeviceToHost, st));
+        CU_OK(cudaStreamSynchronize(st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, EV(ev_[0]), EV(ev_[1]));
+        stats.kernel_ms += ms;
+        const size_t found = h_counters_[1];
+        end_state_ = h_counters_[2];
+        if (found <= events_cap_) { n_events_ = found; stats.events = found; return true; }
+        // event buffer too small: grow to the exact need and scan again
+        if (!ensure_events(found + found / 16 + 1024)) return false;
+    }
+    set_error("event buffer overflow persisted after regrow");
+    return false;
+}
+
+bool Engine::scan_device(const void *d_bytes, const uint64_t *offsets, size_t n, bool first_only,
+                         uint32_t init_state, void *stream)
+{
+    if (device_ < 0) { set_error("automaton has no device table (finalize failed?)"); return false; }
+    CU_OK(cudaSetDevice(device_));
+    const uint64_t total = offsets[n];
+    if (total >= 0xffffff00ull) { set_error("haystack stream exceeds 4 GiB per call"); return false; }
+    if (((uintptr_t)d_bytes & 15u) != 0) { set_error("device haystack pointer must be 16-byte aligned"); return false; }
+    uint32_t uniform_len = 0;
+    if (!upload_offsets(offsets, n, &uniform_len)) return false;
+    if (!uniform_len && stream && S(stream) != S(stream_)) CU_OK(cudaStreamSynchronize(S(stream_)));
+    stats.h2d_ms = 0; stats.d2h_ms = 0;
+    return launch_scan(d_bytes, (uint32_t)total, n, uniform_len, first_only, init_state, stream);
+}
+
+bool Engine::scan_host(const char *bytes, const uint64_t *offsets, size_t n, bool first_only,
+                       uint32_t init_state)
+{
+    if (device_ < 0) { set_error("automaton has no device table (finalize failed?)"); return false; }
+    CU_OK(cudaSetDevice(device_));
+    cudaStream_t st = S(stream_);
+    const uint64_t total = offsets[n];
+    if (total >= 0xffffff00ull) { set_error("haystack stream exceeds 4 GiB per call"); return false; }
+    if (!ensure_text(total + 64)) return false;
+    uint32_t uniform_len = 0;
+    if (!upload_offsets(offsets, n, &uniform_len)) return false;
+    CU_OK(cudaEventRecord(EV(ev_[2]), st));
+    if (total) CU_OK(cudaMemcpyAsync(d_text_, bytes, total, cudaMemcpyHostToDevice, st));
+    CU_OK(cudaEventRecord(EV(ev_[3]), st));
+    if (!launch_scan(d_text_, (uint32_t)total, n, uniform_len, first_only, init_state, nullptr)) return false;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, EV(ev_[2]), EV(ev_[3]));
+    stats.h2d_ms = ms;
+    stats.d2h_ms = 0;
+    if (n_events_) {
+        if (!ensure_host_events(n_events_)) return false;
+        CU_OK(cudaEventRecord(EV(ev_[2]), st));
+        CU_OK(cudaMemcpyAsync(h_events_, d_events_, n_events_ * sizeof(PackedEvent), cudaMemcpyDeviceToHost, st));
+        CU_OK(cudaEventRecord(EV(ev_[3]), st));
+        CU_OK(cudaStreamSynchronize(st));
+        cudaEventElapsedTime(&ms, EV(ev_[2]), EV(ev_[3]));
+        stats.d2h_ms = ms;
+    }
+    return true;
+}
+
+} // namespace acb200

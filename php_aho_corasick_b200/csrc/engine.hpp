@@ -1,0 +1,92 @@
+// engine.hpp — device side of one automaton handle: the dense table in HBM,
+// per-handle scratch (haystack staging, event buffer, look-back words) and the
+// launch logic of the scan.  Host code only; CUDA types stay behind void*.
+#pragma once
+
+#include <cstdint>
+#include <cstddef>
+#include <string>
+#include <vector>
+
+#include "acb200.h"
+#include "automaton.hpp"
+
+namespace acb200 {
+
+struct PackedEvent { uint32_t end; uint32_t state; };   // as written by the kernel
+
+void set_error(const std::string &msg);
+const char *get_error();
+int preferred_device();
+void set_preferred_device(int d);
+
+class Engine {
+public:
+    Engine();
+    ~Engine();
+
+    // Uploads `flat` and expands the dense table on the device. false on error.
+    bool build(const FlatAutomaton &flat);
+
+    // Scans a flat haystack stream that lives in HOST memory.  Events are left in
+    // host_events() sorted by stream offset; returns false on error.
+    bool scan_host(const char *bytes, const uint64_t *offsets, size_t n, bool first_only,
+                   uint32_t init_state);
+    // Same for a stream already resident in device memory; events stay on the device.
+    bool scan_device(const void *d_bytes, const uint64_t *offsets, size_t n, bool first_only,
+                     uint32_t init_state, void *stream);
+
+    const PackedEvent *host_events() const { return h_events_; }
+    const void *device_events() const { return d_events_; }
+    size_t n_events() const { return n_events_; }
+    uint32_t end_state() const { return end_state_; }
+
+    ACB200_STATS_t stats{};
+    ACB200_INFO_t info{};
+    uint32_t tune_chunk = 0;
+    uint32_t tune_smem_bytes = 0;
+
+private:
+    bool ensure_text(size_t bytes);
+    bool ensure_events(size_t n);
+    bool ensure_offsets(size_t n);
+    bool ensure_tiles(size_t n);
+    bool ensure_host_events(size_t n);
+    bool upload_offsets(const uint64_t *offsets, size_t n, uint32_t *uniform_len);
+    bool launch_scan(const void *d_text, uint32_t total, size_t n_hay, uint32_t uniform_len,
+                     bool first_only, uint32_t init_state, void *stream);
+    uint32_t pick_chunk(uint64_t total) const;
+    void release();
+
+    int device_ = -1;
+    int n_sms_ = 0;
+    int max_smem_optin_ = 0;
+    void *stream_ = nullptr;       // cudaStream_t
+    void *ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+
+    // automaton
+    void *d_table_ = nullptr;
+    uint8_t *d_cls_ = nullptr;
+    uint32_t ncls_ = 1, first_final_ = 1, n_states_ = 1, halo_ = 0;
+    uint32_t range_lo_ = 0, n_used_ = 0;
+    bool range_map_ = true;
+    int entry_bytes_ = 2;
+    uint64_t table_entries_ = 1;
+
+    // scratch
+    uint8_t *d_text_ = nullptr;   size_t text_cap_ = 0;
+    uint32_t *d_off_ = nullptr;   size_t off_cap_ = 0;
+    uint32_t *d_first_ = nullptr; size_t first_cap_ = 0;
+    void *d_events_ = nullptr;    size_t events_cap_ = 0;
+    unsigned long long *d_tiles_ = nullptr; size_t tiles_cap_ = 0;
+    uint32_t *d_counters_ = nullptr;
+    uint32_t *h_counters_ = nullptr;          // pinned
+    PackedEvent *h_events_ = nullptr; size_t h_events_cap_ = 0;   // pinned
+    uint8_t *h_stage_ = nullptr;  size_t stage_cap_ = 0;          // pinned staging for pageable input
+    std::vector<uint32_t> off32_;
+
+    size_t n_events_ = 0;
+    uint32_t end_state_ = 0;
+};
+
+} // namespace acb200

@@ -1,0 +1,263 @@
+"""ctypes binding of libacb200.so (the C-ABI in include/acb200.h).
+
+There is no fallback: if the CUDA library is missing or no B200 is visible the
+calls raise.  Nothing here imports or calls anything under oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libacb200.so")
+_lib = None
+
+
+class AcText(C.Structure):
+    _fields_ = [("astring", C.c_void_p), ("length", C.c_size_t)]
+
+
+class _PattIdU(C.Union):
+    _fields_ = [("stringy", C.c_char_p), ("number", C.c_long)]
+
+
+class AcPattId(C.Structure):
+    _fields_ = [("u", _PattIdU), ("type", C.c_int)]
+
+
+class AcPattern(C.Structure):
+    _fields_ = [("ptext", AcText), ("rtext", AcText), ("id", AcPattId), ("aux", C.c_void_p)]
+
+
+class AcMatch(C.Structure):
+    _fields_ = [("patterns", C.POINTER(AcPattern)), ("size", C.c_size_t), ("position", C.c_size_t)]
+
+
+class Event(C.Structure):
+    _fields_ = [("end", C.c_uint64), ("state", C.c_uint32), ("text_idx", C.c_uint32)]
+
+
+EVENT_DTYPE = np.dtype([("end", np.uint64), ("state", np.uint32), ("text_idx", np.uint32)])
+PACKED_EVENT_DTYPE = np.dtype([("end", np.uint32), ("state", np.uint32)])
+
+
+class Info(C.Structure):
+    _fields_ = [("n_patterns", C.c_uint64), ("n_states", C.c_uint64), ("n_classes", C.c_uint32),
+                ("entry_bytes", C.c_uint32), ("max_pattern_len", C.c_uint32), ("first_final", C.c_uint32),
+                ("table_bytes", C.c_uint64), ("device", C.c_int32), ("finalized", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("bytes", C.c_uint64), ("events", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("chunk_bytes", C.c_uint32), ("halo_bytes", C.c_uint32), ("kernel_ms", C.c_float),
+                ("h2d_ms", C.c_float), ("d2h_ms", C.c_float)]
+
+
+MATCH_CB = C.CFUNCTYPE(C.c_int, C.POINTER(AcMatch), C.c_void_p)
+BATCH_CB = C.CFUNCTYPE(C.c_int, C.c_size_t, C.POINTER(AcMatch), C.c_void_p)
+
+# every symbol include/acb200.h declares
+EXPORTS = [
+    "ac_trie_create", "ac_trie_add", "ac_trie_finalize", "ac_trie_search", "ac_trie_release",
+    "ac_trie_search_batch", "ac_trie_search_flat", "acb200_search_events", "acb200_search_device",
+    "acb200_state_patterns", "acb200_info", "acb200_last_stats", "acb200_last_error",
+    "acb200_set_device", "acb200_device_count", "acb200_host_alloc", "acb200_host_free",
+    "acb200_set_tuning", "acb200_version",
+]
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is not built — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.ac_trie_create.restype = C.c_void_p
+    L.ac_trie_add.argtypes = [C.c_void_p, C.POINTER(AcPattern), C.c_int]
+    L.ac_trie_add.restype = C.c_int
+    L.ac_trie_finalize.argtypes = [C.c_void_p]
+    L.ac_trie_finalize.restype = None
+    L.ac_trie_search.argtypes = [C.c_void_p, C.POINTER(AcText), C.c_int, MATCH_CB, C.c_void_p]
+    L.ac_trie_search.restype = C.c_int
+    L.ac_trie_release.argtypes = [C.c_void_p]
+    L.ac_trie_release.restype = None
+    L.ac_trie_search_batch.argtypes = [C.c_void_p, C.POINTER(AcText), C.c_size_t, C.c_int, BATCH_CB, C.c_void_p]
+    L.ac_trie_search_batch.restype = C.c_int
+    L.ac_trie_search_flat.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, BATCH_CB, C.c_void_p]
+    L.ac_trie_search_flat.restype = C.c_int
+    L.acb200_search_events.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                                       C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.acb200_search_events.restype = C.c_int
+    L.acb200_search_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.acb200_search_device.restype = C.c_int
+    L.acb200_state_patterns.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(AcPattern))]
+    L.acb200_state_patterns.restype = C.c_size_t
+    L.acb200_info.argtypes = [C.c_void_p, C.POINTER(Info)]
+    L.acb200_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.acb200_last_error.restype = C.c_char_p
+    L.acb200_set_device.argtypes = [C.c_int]
+    L.acb200_device_count.restype = C.c_int
+    L.acb200_host_alloc.argtypes = [C.c_size_t]
+    L.acb200_host_alloc.restype = C.c_void_p
+    L.acb200_host_free.argtypes = [C.c_void_p]
+    L.acb200_host_free.restype = None
+    L.acb200_set_tuning.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    L.acb200_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+class AcError(RuntimeError):
+    pass
+
+
+def last_error() -> str:
+    return lib().acb200_last_error().decode("utf-8", "replace")
+
+
+def _as_u8(buf) -> np.ndarray:
+    if isinstance(buf, (bytes, bytearray, memoryview)):
+        return np.frombuffer(bytes(buf), dtype=np.uint8)
+    return np.ascontiguousarray(buf, dtype=np.uint8).reshape(-1)
+
+
+class Automaton:
+    """Thin object over an AC_TRIE_t*.  Pattern ordinals are the order of add()."""
+
+    def __init__(self, device: int | None = None):
+        self.L = lib()
+        if device is not None:
+            self.L.acb200_set_device(int(device))
+        self.h = self.L.ac_trie_create()
+        self.n_added = 0
+        self._keep = []   # keeps pattern bytes alive for copy=0 callers (unused: we copy)
+
+    # -- build ------------------------------------------------------------
+    def _add(self, pattern: bytes, ordinal: int) -> int:
+        p = AcPattern()
+        buf = C.create_string_buffer(pattern, len(pattern))
+        p.ptext.astring = C.cast(buf, C.c_void_p)
+        p.ptext.length = len(pattern)
+        p.rtext.astring = None
+        p.rtext.length = 0
+        p.id.type = 1
+        p.id.u.number = ordinal
+        p.aux = ordinal + 1
+        return self.L.ac_trie_add(self.h, C.byref(p), 1)
+
+    def add(self, pattern: bytes) -> int:
+        o = self.n_added
+        self.n_added += 1
+        return self._add(pattern, o)
+
+    def add_php_order(self, patterns) -> None:
+        """One init()/add_patterns() call: ordinals follow array order, insertion is last-first
+        (reference src/php_ahocorasick.c:410-421, 457-486); statuses ignored."""
+        patterns = list(patterns)
+        base = self.n_added
+        for k in range(len(patterns) - 1, -1, -1):
+            self._add(patterns[k], base + k)
+        self.n_added += len(patterns)
+
+    def finalize(self) -> None:
+        self.L.ac_trie_finalize(self.h)
+        inf = self.info()
+        if inf.device < 0:
+            raise AcError("finalize did not reach the GPU: " + last_error())
+
+    def set_tuning(self, chunk_bytes: int = 0, smem_table_bytes: int = 0) -> None:
+        self.L.acb200_set_tuning(self.h, int(chunk_bytes), int(smem_table_bytes))
+
+    # -- search -----------------------------------------------------------
+    def search_events(self, flat, offsets=None, first_only: bool = False) -> np.ndarray:
+        """Haystacks laid end to end in `flat`; -> structured array (end, state, text_idx)."""
+        buf = _as_u8(flat)
+        if offsets is None:
+            offsets = np.array([0, buf.size], dtype=np.uint64)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = off.size - 1
+        cap = 1 << 12
+        while True:
+            ev = np.empty(cap, dtype=EVENT_DTYPE)
+            ne = C.c_size_t(0)
+            rc = self.L.acb200_search_events(self.h, buf.ctypes.data if buf.size else None, off.ctypes.data, n,
+                                             int(first_only), ev.ctypes.data, cap, C.byref(ne))
+            if rc != 0:
+                raise AcError(last_error())
+            if ne.value <= cap:
+                return ev[:ne.value]
+            cap = int(ne.value)
+
+    def search_device(self, dev_ptr: int, offsets, first_only: bool = False, stream: int = 0):
+        """Haystack stream already in HBM. -> (device pointer of packed events, n_events)"""
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        out = C.c_void_p(0)
+        ne = C.c_size_t(0)
+        rc = self.L.acb200_search_device(self.h, C.c_void_p(dev_ptr), off.ctypes.data, off.size - 1, int(first_only),
+                                         C.c_void_p(stream), C.byref(out), C.byref(ne))
+        if rc != 0:
+            raise AcError(last_error())
+        return out.value, int(ne.value)
+
+    def search_callback(self, text: bytes, keep: bool = False, stop_after_first: bool = False):
+        """ac_trie_search() with a recording callback. -> (rc, [(position, [ordinals...]), ...])"""
+        got = []
+
+        def cb(mp, _user):
+            m = mp.contents
+            got.append((int(m.position), [int(m.patterns[j].aux) - 1 for j in range(m.size)]))
+            return 1 if stop_after_first else 0
+
+        t = AcText()
+        buf = C.create_string_buffer(text, len(text))
+        t.astring = C.cast(buf, C.c_void_p)
+        t.length = len(text)
+        rc = self.L.ac_trie_search(self.h, C.byref(t), int(keep), MATCH_CB(cb), None)
+        return rc, got
+
+    def state_patterns(self, state: int):
+        """-> list of (ordinal, length) reported by `state`, longest first"""
+        pp = C.POINTER(AcPattern)()
+        n = self.L.acb200_state_patterns(self.h, int(state), C.byref(pp))
+        return [(int(pp[j].aux) - 1, int(pp[j].ptext.length)) for j in range(n)]
+
+    def expand(self, events: np.ndarray):
+        """events -> hits in callback order: (text_idx[], pos[], ordinal[], length[])"""
+        cache = {}
+        ti, pos, pat, ln = [], [], [], []
+        for e in events:
+            st = int(e["state"])
+            lst = cache.get(st)
+            if lst is None:
+                lst = cache[st] = self.state_patterns(st)
+            for (o, l) in lst:
+                ti.append(int(e["text_idx"])); pos.append(int(e["end"])); pat.append(o); ln.append(l)
+        return (np.array(ti, dtype=np.uint32), np.array(pos, dtype=np.uint64),
+                np.array(pat, dtype=np.uint32), np.array(ln, dtype=np.uint32))
+
+    # -- facts ------------------------------------------------------------
+    def info(self) -> Info:
+        i = Info()
+        self.L.acb200_info(self.h, C.byref(i))
+        return i
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self.L.acb200_last_stats(self.h, C.byref(s))
+        return s
+
+    def release(self) -> None:
+        if self.h:
+            self.L.ac_trie_release(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass

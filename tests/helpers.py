@@ -1,0 +1,44 @@
+"""Shared helpers for the parity tests (TEST code: may use oracle/)."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle.pydriver import Driver
+
+
+def oracle_hits(patterns_calls, haystacks, first_only=False, kind="oracle"):
+    """patterns_calls: list of pattern lists, one per init()/add_patterns() call.
+    -> list per haystack of (pos[], ordinal[], n_events, hash)"""
+    d = Driver(kind)
+    for call in patterns_calls:
+        d.add_php_order(call)
+    d.finalize()
+    out = []
+    for h in haystacks:
+        r = d.search(h, first_only=first_only)
+        out.append((r["pos"].copy(), r["pat"].copy(), r["n_events"], r["hash"]))
+    d.release()
+    return out
+
+
+def split(flat: np.ndarray, offsets: np.ndarray):
+    return [flat[int(offsets[i]):int(offsets[i + 1])] for i in range(len(offsets) - 1)]
+
+
+def gpu_hits_by_haystack(aut, events, n_hay):
+    ti, pos, pat, _ln = aut.expand(events)
+    out = []
+    for h in range(n_hay):
+        m = ti == h
+        out.append((pos[m], pat[m], int((events["text_idx"] == h).sum())))
+    return out
+
+
+def assert_same(aut, events, n_hay, expected):
+    got = gpu_hits_by_haystack(aut, events, n_hay)
+    for h in range(n_hay):
+        epos, epat, enev, _ = expected[h]
+        gpos, gpat, gnev = got[h]
+        assert gnev == enev, f"haystack {h}: {gnev} events, oracle {enev}"
+        assert np.array_equal(gpos, epos), f"haystack {h}: positions differ"
+        assert np.array_equal(gpat, epat), f"haystack {h}: pattern order differs"

@@ -1,0 +1,168 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the CPU oracle, bit-exact, order included."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle.pydriver import Driver, flatten
+from php_aho_corasick_b200 import workloads as W
+from php_aho_corasick_b200.native import Automaton
+from tests.helpers import assert_same, oracle_hits, split
+
+pytestmark = pytest.mark.gpu
+
+
+def build(pattern_calls):
+    a = Automaton()
+    for call in pattern_calls:
+        a.add_php_order(call)
+    a.finalize()
+    return a
+
+
+def test_cfg1_readme_vector_through_reference_style_driver():
+    pats = [p["value"].encode() for p in W.CFG1_PATTERNS]
+    res = {}
+    for kind in ("oracle", "gpu"):
+        d = Driver(kind)
+        d.add_php_order(pats)
+        d.finalize()
+        r = d.search(W.CFG1_HAYSTACK)
+        res[kind] = (r["rc"], r["n_events"], r["hash"], r["pos"].tolist(), r["pat"].tolist(), r["len"].tolist())
+        d.release()
+    assert res["gpu"] == res["oracle"]
+    # tests/test1.phpt:60-119 — pos 14,19,24,28,28 ; 'alfa' before 'lfa' at 28
+    assert res["gpu"][3] == [14, 19, 24, 28, 28]
+    assert res["gpu"][4] == [2, 4, 5, 0, 6]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_small_dictionaries_callback_path(seed):
+    rng = random.Random(seed)
+    for trial in range(40):
+        alpha = rng.choice([b"ab", b"abc", bytes(range(256)), b"a", b"\x00\xff\x80a", b"abcdef"])
+        n = rng.randint(0, 40)
+        pats = [bytes(rng.choice(alpha) for _ in range(rng.randint(0, 9))) for _ in range(n)]
+        text = bytes(rng.choice(alpha) for _ in range(rng.randint(0, 700)))
+        first = trial % 4 == 3
+        got = {}
+        for kind in ("oracle", "gpu"):
+            d = Driver(kind)
+            half = len(pats) // 2
+            d.add_php_order(pats[:half])
+            d.add_php_order(pats[half:])
+            d.finalize()
+            r = d.search(text, first_only=first)
+            got[kind] = (r["rc"], r["n_events"], r["hash"], r["pos"].tolist(), r["pat"].tolist())
+            d.release()
+        assert got["gpu"] == got["oracle"], (seed, trial, pats, text)
+
+
+def test_cfg2_benchmark_shape_planted():
+    needles, hay, off = W.cfg2()
+    a = build([needles])
+    ev = a.search_events(hay, off)
+    exp = oracle_hits([needles], split(hay, off))
+    assert sum(e[2] for e in exp) >= 256 * 8
+    assert_same(a, ev, 256, exp)
+    st = a.stats()
+    assert st.kernel_launches >= 1 and st.bytes == hay.size
+
+
+@pytest.mark.parametrize("chunk,smem", [(16, 0), (48, 4096), (256, 0), (1024, 512), (4096, 0)])
+def test_slice_and_table_placement_do_not_change_results(chunk, smem):
+    needles, hay, off = W.cfg2(n_hay=16, hay_len=3000, n_needles=300, planted_per_hay=6, seed=11)
+    a = build([needles])
+    a.set_tuning(chunk, smem)
+    ev = a.search_events(hay, off)
+    assert_same(a, ev, 16, oracle_hits([needles], split(hay, off)))
+
+
+def test_ragged_batch_with_empty_haystacks():
+    rng = np.random.default_rng(5)
+    needles, _, _ = W.cfg2(n_hay=1, hay_len=64, n_needles=64, needle_len=5, planted_per_hay=0, seed=3)
+    lens = [0, 1, 4, 5, 0, 0, 17, 1000, 3, 0, 64, 65, 4097, 0]
+    hays = [np.frombuffer(b"abcdef", dtype=np.uint8)[rng.integers(0, 6, size=n)] for n in lens]
+    flat = np.concatenate(hays) if hays else np.zeros(0, np.uint8)
+    off = np.zeros(len(lens) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    a = build([needles])
+    for chunk in (0, 16, 64):
+        a.set_tuning(chunk, 0)
+        ev = a.search_events(flat, off)
+        assert_same(a, ev, len(lens), oracle_hits([needles], hays))
+        ev1 = a.search_events(flat, off, first_only=True)
+        exp1 = oracle_hits([needles], hays, first_only=True)
+        assert_same(a, ev1, len(lens), exp1)
+
+
+def test_cfg3_signature_shape_reduced():
+    pats, hay, off = W.cfg3(n_patterns=20_000, hay_bytes=8 << 20, plant_every=1 << 16)
+    a = build([pats])
+    inf = a.info()
+    assert inf.entry_bytes == 4 and inf.n_classes == 256
+    ev = a.search_events(hay, off)
+    exp = oracle_hits([pats], [hay])
+    assert exp[0][2] >= 100
+    assert_same(a, ev, 1, exp)
+
+
+def test_cfg5_adversarial_reduced_and_closed_form():
+    n = 1 << 20
+    pats, hay, off = W.cfg5(n_patterns=1100, hay_bytes=n)
+    a = build([pats])
+    assert a.info().n_patterns == 1024          # a^1025.. rejected (AC_PATTRN_MAX_LENGTH)
+    ev = a.search_events(hay, off)
+    events, hits = W.cfg5_expected(n, 1100)
+    assert len(ev) == events
+    assert np.array_equal(ev["end"], np.arange(1, n + 1, dtype=np.uint64))
+    sizes = np.array([len(a.state_patterns(int(s))) for s in np.unique(ev["state"])])
+    uniq, counts = np.unique(ev["state"], return_counts=True)
+    assert int((sizes * counts).sum()) == hits
+    # event-level hash against the oracle through the reference-style callback path
+    res = {}
+    for kind in ("oracle", "gpu"):
+        d = Driver(kind)
+        d.add_php_order(pats)
+        d.finalize()
+        r = d.search(hay, cap=16)
+        res[kind] = (r["rc"], r["n_events"], r["n_hits"], r["hash"])
+        d.release()
+    assert res["gpu"] == res["oracle"]
+    assert res["gpu"][2] == hits
+
+
+def test_keep_streams_state_across_calls():
+    needles, hay, _ = W.cfg2(n_hay=1, hay_len=5000, n_needles=200, planted_per_hay=8, seed=21)
+    cuts = [0, 7, 8, 1000, 1003, 4096, 5000]
+    res = {}
+    for kind in ("oracle", "gpu"):
+        d = Driver(kind)
+        d.add_php_order(needles)
+        d.finalize()
+        pos, pat = [], []
+        for i in range(len(cuts) - 1):
+            r = d.search(hay[cuts[i]:cuts[i + 1]], keep=(i > 0))
+            pos += r["pos"].tolist()
+            pat += r["pat"].tolist()
+        whole = d.search(hay)
+        assert pos == whole["pos"].tolist() and pat == whole["pat"].tolist()
+        res[kind] = (pos, pat)
+        d.release()
+    assert res["gpu"] == res["oracle"] and len(res["gpu"][0]) >= 8
+
+
+def test_not_finalized_returns_minus_one_and_add_statuses():
+    for kind in ("oracle", "gpu"):
+        d = Driver(kind)
+        assert d.add(b"abc") == 0
+        assert d.add(b"abc") == 1            # duplicate
+        assert d.add(b"") == 3               # empty
+        assert d.add(b"x" * 1025) == 2       # too long
+        assert d.add(b"x" * 1024) == 0
+        assert d.search(b"abc")["rc"] == -1  # not finalized
+        d.finalize()
+        assert d.add(b"zzz") == 4            # closed
+        r = d.search(b"zabcz")
+        assert r["rc"] == 0 and r["pos"].tolist() == [4]
+        d.release()
