@@ -201,10 +201,12 @@ typedef struct acb200_info
     uint32_t n_classes;       /* byte classes = table columns                */
     uint32_t entry_bytes;     /* 2 or 4                                      */
     uint32_t max_pattern_len; /* Lmax of accepted patterns                   */
-    uint32_t first_final;     /* states >= this report patterns              */
+    uint32_t final_bound;     /* event states are in [1, final_bound)        */
+    uint32_t root;            /* id of the root state                        */
     uint64_t table_bytes;     /* dense transition table in HBM               */
     int32_t device;           /* CUDA device ordinal                         */
     int32_t finalized;
+    int32_t reserved_;
 } ACB200_INFO_t;
 int acb200_info(const AC_TRIE_t *thiz, ACB200_INFO_t *out);
 

@@ -181,21 +181,28 @@ void HostTrie::flatten(FlatAutomaton &flat) {
         is_final[v] = (own_[v] >= 0 || dlink[v] != NONE) ? 1 : 0;
     }
 
-    // final numbering: non-final states breadth-first from 0, final states after them
+    // State numbering (ids are what the device reports in events):
+    //   0                      reserved "left the hot set" marker, never a real state
+    //   [1, final_bound)       final states, DEEPEST first, so the shallow finals sit next to
+    //   [final_bound, N+1)     the non-final states, breadth-first (root = final_bound).
+    // The shared-memory window of the scan kernel is one contiguous id range around
+    // final_bound: the shallowest finals below it and the shallowest non-finals above it.
     uint32_t n_final = 0;
     for (uint32_t v = 0; v < N; ++v) n_final += is_final[v];
-    const uint32_t first_final = N - n_final;
+    const uint32_t final_bound = 1 + n_final;
     std::vector<uint32_t> newid(N);
     {
-        uint32_t a = 0, b = first_final;
+        uint32_t a = final_bound, b = final_bound - 1;
         for (uint32_t idx = 0; idx < N; ++idx) {
             const uint32_t v = order[idx];
-            newid[v] = is_final[v] ? b++ : a++;
+            newid[v] = is_final[v] ? b-- : a++;
         }
     }
 
     flat.n_states = N;
-    flat.first_final = first_final;
+    flat.n_rows = N + 1;
+    flat.final_bound = final_bound;
+    flat.root = final_bound;
 
     // byte classes
     bool used[256] = {false};
@@ -214,7 +221,7 @@ void HostTrie::flatten(FlatAutomaton &flat) {
 
     // device expansion inputs
     flat.bfs_order.resize(N);
-    flat.fail.resize(N);
+    flat.fail.assign((size_t)N + 1, flat.root);
     for (uint32_t idx = 0; idx < N; ++idx) flat.bfs_order[idx] = newid[order[idx]];
     for (uint32_t v = 0; v < N; ++v) flat.fail[newid[v]] = newid[fail[v]];
     flat.level_off = level_off;
@@ -236,12 +243,12 @@ void HostTrie::flatten(FlatAutomaton &flat) {
     }
     flat.level_edge_off[n_levels] = (uint32_t)flat.edge_src.size();
 
-    // output lists, indexed by (state - first_final)
+    // output lists, indexed by (state - 1)
     flat.max_pattern_len = 0;
     for (const AC_PATTERN_t &p : patterns_)
         flat.max_pattern_len = std::max<uint32_t>(flat.max_pattern_len, (uint32_t)p.ptext.length);
     std::vector<uint32_t> old_of_final(n_final);
-    for (uint32_t v = 0; v < N; ++v) if (is_final[v]) old_of_final[newid[v] - first_final] = v;
+    for (uint32_t v = 0; v < N; ++v) if (is_final[v]) old_of_final[newid[v] - 1] = v;
     flat.out_off.assign((size_t)n_final + 1, 0);
     for (uint32_t i = 0; i < n_final; ++i) {
         uint64_t cnt = 0;

@@ -34,13 +34,15 @@ private:
     size_t mask_ = 0;
 };
 
-// Flat automaton in FINAL state numbering: all pattern-reporting ("final")
-// states have ids >= first_final, both groups ordered breadth-first so that the
-// shallow, hot rows of the table are contiguous from id 0.
+// Flat automaton in device state numbering (see HostTrie::flatten): id 0 is a
+// reserved marker, ids [1, final_bound) are the pattern-reporting ("final")
+// states, ids [final_bound, n_rows) the others, root == final_bound.
 struct FlatAutomaton {
-    uint32_t n_states = 1;
+    uint32_t n_states = 1;        // real states incl. root
+    uint32_t n_rows = 2;          // table rows = n_states + 1 (row 0 unused)
     uint32_t n_classes = 1;       // table columns
-    uint32_t first_final = 1;     // == n_states when nothing is final
+    uint32_t final_bound = 1;     // states < final_bound (and != 0) report patterns
+    uint32_t root = 1;
     uint32_t max_pattern_len = 0; // Lmax over accepted patterns
     uint32_t n_used_bytes = 0;
     uint8_t  cls_map[256];        // byte -> column; unused bytes share the last column
@@ -56,7 +58,7 @@ struct FlatAutomaton {
     std::vector<uint16_t> edge_cls;
     std::vector<uint32_t> level_edge_off;  // edges leaving level d = [level_edge_off[d], level_edge_off[d+1])
 
-    // output lists for final states (index: state - first_final), longest pattern first
+    // output lists for final states (index: state - 1), longest pattern first
     std::vector<uint64_t> out_off;
     std::vector<AC_PATTERN_t> out_pat;
 };

@@ -25,7 +25,7 @@ struct ac_trie {
     Engine engine;
     bool open = true;          // patterns may still be added (reference: trie_open)
     bool device_ok = false;    // finalize reached the device
-    uint32_t last_state = 0;   // keep=1 continuation (reference: last_node)
+    uint32_t last_state = ROOT_STATE;   // keep=1 continuation (reference: last_node)
     size_t base_position = 0;  // keep=1 continuation (reference: base_position)
     std::vector<char> gather;  // batch gather buffer
     std::vector<uint64_t> gather_off;
@@ -33,8 +33,8 @@ struct ac_trie {
 
 static inline size_t patterns_of(const ac_trie *t, uint32_t state, const AC_PATTERN_t **p)
 {
-    if (state < t->flat.first_final || state >= t->flat.n_states) { if (p) *p = nullptr; return 0; }
-    const uint32_t i = state - t->flat.first_final;
+    if (state == 0 || state >= t->flat.final_bound) { if (p) *p = nullptr; return 0; }
+    const uint32_t i = state - 1;
     const uint64_t b = t->flat.out_off[i], e = t->flat.out_off[i + 1];
     if (p) *p = t->flat.out_pat.data() + b;
     return (size_t)(e - b);
@@ -99,7 +99,7 @@ int ac_trie_search(AC_TRIE_t *t, AC_TEXT_t *text, int keep, AC_MATCH_CALBACK_f c
 {
     if (t->open) return -1;                      // src/multifast/ahocorasick.c:183-184
     if (!t->device_ok) return -1;
-    if (!keep) { t->last_state = 0; t->base_position = 0; }   // ac_trie_reset, ahocorasick.c:330-335
+    if (!keep) { t->last_state = ROOT_STATE; t->base_position = 0; }   // ac_trie_reset, ahocorasick.c:330-335
     const uint64_t offs[2] = {0, (uint64_t)text->length};
     if (!t->engine.scan_host(text->astring, offs, 1, false, t->last_state)) return -1;
     const PackedEvent *ev = t->engine.host_events();
@@ -145,7 +145,7 @@ int ac_trie_search_flat(AC_TRIE_t *t, const char *bytes, const uint64_t *offsets
     if (t->open) { set_error("automaton is not finalized"); return -1; }
     if (!t->device_ok) return -1;
     if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return -1; }
-    if (!t->engine.scan_host(bytes, offsets, n, first_only != 0, 0)) return -1;
+    if (!t->engine.scan_host(bytes, offsets, n, first_only != 0, ROOT_STATE)) return -1;
     return replay_batch(t, offsets, n, first_only, callback, user);
 }
 
@@ -161,7 +161,7 @@ int ac_trie_search_batch(AC_TRIE_t *t, const AC_TEXT_t *texts, size_t n, int fir
     if (t->gather.size() < total) t->gather.resize(total);
     for (size_t i = 0; i < n; ++i)
         if (texts[i].length) memcpy(t->gather.data() + t->gather_off[i], texts[i].astring, texts[i].length);
-    if (!t->engine.scan_host(t->gather.data(), t->gather_off.data(), n, first_only != 0, 0)) return -1;
+    if (!t->engine.scan_host(t->gather.data(), t->gather_off.data(), n, first_only != 0, ROOT_STATE)) return -1;
     return replay_batch(t, t->gather_off.data(), n, first_only, callback, user);
 }
 
@@ -171,7 +171,7 @@ int acb200_search_events(AC_TRIE_t *t, const char *bytes, const uint64_t *offset
     if (t->open) { set_error("automaton is not finalized"); return -1; }
     if (!t->device_ok) return -1;
     if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return -1; }
-    if (!t->engine.scan_host(bytes, offsets, n, first_only != 0, 0)) return -1;
+    if (!t->engine.scan_host(bytes, offsets, n, first_only != 0, ROOT_STATE)) return -1;
     const PackedEvent *ev = t->engine.host_events();
     const size_t ne = t->engine.n_events();
     size_t h = 0, w = 0;
@@ -197,7 +197,7 @@ int acb200_search_device(AC_TRIE_t *t, const void *d_bytes, const uint64_t *offs
     if (t->open) { set_error("automaton is not finalized"); return -1; }
     if (!t->device_ok) return -1;
     if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return -1; }
-    if (!t->engine.scan_device(d_bytes, offsets, n, first_only != 0, 0, stream)) return -1;
+    if (!t->engine.scan_device(d_bytes, offsets, n, first_only != 0, ROOT_STATE, stream)) return -1;
     if (d_events) *d_events = t->engine.device_events();
     if (n_events) *n_events = t->engine.n_events();
     return 0;

@@ -73,6 +73,7 @@ template <typename E>
 static bool expand_table(E *table, const FlatAutomaton &f, cudaStream_t st, uint64_t *launches)
 {
     const uint32_t N = f.n_states;
+    const uint32_t NR = f.n_rows;
     uint32_t *d_order = nullptr, *d_fail = nullptr, *d_src = nullptr, *d_dst = nullptr;
     uint16_t *d_cls = nullptr;
     const size_t ne = f.edge_src.size();
@@ -83,7 +84,7 @@ static bool expand_table(E *table, const FlatAutomaton &f, cudaStream_t st, uint
     };
     cudaError_t e;
     if ((e = cudaMalloc(&d_order, sizeof(uint32_t) * N)) != cudaSuccess) fail_with("cudaMalloc(order)", e);
-    if (ok && (e = cudaMalloc(&d_fail, sizeof(uint32_t) * N)) != cudaSuccess) fail_with("cudaMalloc(fail)", e);
+    if (ok && (e = cudaMalloc(&d_fail, sizeof(uint32_t) * NR)) != cudaSuccess) fail_with("cudaMalloc(fail)", e);
     if (ok && ne) {
         if ((e = cudaMalloc(&d_src, sizeof(uint32_t) * ne)) != cudaSuccess) fail_with("cudaMalloc(edge_src)", e);
         if (ok && (e = cudaMalloc(&d_dst, sizeof(uint32_t) * ne)) != cudaSuccess) fail_with("cudaMalloc(edge_dst)", e);
@@ -91,7 +92,7 @@ static bool expand_table(E *table, const FlatAutomaton &f, cudaStream_t st, uint
     }
     if (ok) {
         cudaMemcpyAsync(d_order, f.bfs_order.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(d_fail, f.fail.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_fail, f.fail.data(), sizeof(uint32_t) * NR, cudaMemcpyHostToDevice, st);
         if (ne) {
             cudaMemcpyAsync(d_src, f.edge_src.data(), sizeof(uint32_t) * ne, cudaMemcpyHostToDevice, st);
             cudaMemcpyAsync(d_dst, f.edge_dst.data(), sizeof(uint32_t) * ne, cudaMemcpyHostToDevice, st);
@@ -103,7 +104,7 @@ static bool expand_table(E *table, const FlatAutomaton &f, cudaStream_t st, uint
             const unsigned long long cells = (unsigned long long)(le - lb) * f.n_classes;
             if (cells) {
                 const unsigned blocks = (unsigned)((cells + EXPAND_THREADS - 1) / EXPAND_THREADS);
-                expand_inherit_kernel<E><<<blocks, EXPAND_THREADS, 0, st>>>(table, d_order, d_fail, lb, le, f.n_classes);
+                expand_inherit_kernel<E><<<blocks, EXPAND_THREADS, 0, st>>>(table, d_order, d_fail, lb, le, f.n_classes, f.root);
                 ++*launches;
             }
             const uint32_t eb = f.level_edge_off[d], ee = f.level_edge_off[d + 1];
@@ -153,18 +154,19 @@ bool Engine::build(const FlatAutomaton &f)
     stream_ = st;
     for (auto &e : ev_) { cudaEvent_t x; CU_OK(cudaEventCreate(&x)); e = x; }
 
-    n_states_ = f.n_states; ncls_ = f.n_classes; first_final_ = f.first_final;
+    n_states_ = f.n_states; n_rows_ = f.n_rows; ncls_ = f.n_classes; final_bound_ = f.final_bound; root_ = f.root;
     halo_ = f.max_pattern_len ? f.max_pattern_len - 1 : 0;
     range_map_ = f.range_map; range_lo_ = f.range_lo; n_used_ = f.n_used_bytes;
-    table_entries_ = (uint64_t)n_states_ * ncls_;
+    table_entries_ = (uint64_t)n_rows_ * ncls_;
     if (table_entries_ >= (1ull << 32)) {
         set_error("automaton too large: states x classes must stay below 2^32 table entries");
         return false;
     }
-    entry_bytes_ = (n_states_ <= 65536u) ? 2 : 4;
+    entry_bytes_ = (n_rows_ <= 65536u) ? 2 : 4;
     const size_t table_bytes = (size_t)table_entries_ * entry_bytes_;
 
     CU_OK(cudaMalloc(&d_table_, table_bytes + 16));
+    CU_OK(cudaMemsetAsync(d_table_, 0, table_bytes + 16, st));
     CU_OK(cudaMalloc(&d_cls_, 256));
     CU_OK(cudaMemcpyAsync(d_cls_, f.cls_map, 256, cudaMemcpyHostToDevice, st));
     CU_OK(cudaMalloc(&d_counters_, 64));
@@ -190,7 +192,8 @@ bool Engine::build(const FlatAutomaton &f)
     info.n_classes = ncls_;
     info.entry_bytes = (uint32_t)entry_bytes_;
     info.max_pattern_len = f.max_pattern_len;
-    info.first_final = first_final_;
+    info.final_bound = final_bound_;
+    info.root = root_;
     info.table_bytes = table_bytes;
     info.device = device_;
     stats = ACB200_STATS_t{};
@@ -290,19 +293,19 @@ static void launch_kernel(const ScanArgs &a, unsigned grid, size_t smem, cudaStr
     ac_scan_kernel<E, RANGE, FIRST><<<grid, SCAN_THREADS, smem, st>>>(a);
 }
 
-bool Engine::launch_scan(const void *d_text, uint32_t total, size_t n_hay, uint32_t uniform_len,
+bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, size_t n_hay, uint32_t uniform_len,
                          bool first_only, uint32_t init_state, void *stream)
 {
     cudaStream_t st = stream ? S(stream) : S(stream_);
     n_events_ = 0;
-    end_state_ = init_state;
+    end_state_ = (init_state == ROOT_STATE) ? root_ : init_state;
     stats.bytes = total; stats.events = 0; stats.kernel_launches = 0; stats.kernel_ms = 0;
     stats.halo_bytes = halo_;
     if (total == 0) { stats.chunk_bytes = 0; return true; }
 
     const uint32_t chunk = pick_chunk(total);
     const uint32_t n_chunks = (uint32_t)(((uint64_t)total + chunk - 1) / chunk);
-    const uint32_t n_tiles = (n_chunks + SCAN_THREADS - 1) / SCAN_THREADS;
+    const uint32_t n_tiles = (n_chunks + 31u) / 32u;
     stats.chunk_bytes = chunk;
     if (!ensure_tiles(n_tiles)) return false;
     if (events_cap_ == 0 && !ensure_events(std::max<size_t>(1 << 16, total / 64))) return false;
@@ -314,11 +317,22 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, size_t n_hay, uint3
         }
     }
 
+    // Hot window in shared memory: B shallowest finals + A shallowest non-finals (root first).
     const int dyn_max = max_smem_optin_ - 2048;
     size_t smem_budget = (size_t)dyn_max;
     if (tune_smem_bytes) smem_budget = std::min<size_t>(smem_budget, tune_smem_bytes);
-    uint64_t smem_entries = std::min<uint64_t>(table_entries_, smem_budget / entry_bytes_);
-    const size_t smem_bytes = (size_t)smem_entries * entry_bytes_;
+    const size_t row_bytes = (size_t)ncls_ * entry_bytes_;
+    const uint64_t rows_fit = smem_budget / row_bytes;
+    const uint64_t n_final = final_bound_ - 1, n_plain = n_rows_ - final_bound_;
+    uint64_t B = std::min<uint64_t>(n_final, rows_fit / 4);
+    uint64_t A = std::min<uint64_t>(n_plain, rows_fit - B);
+    B = std::min<uint64_t>(n_final, rows_fit - A);
+    // a window that covers only a sliver of a huge automaton cannot pay for itself
+    if (!tune_smem_bytes && A * 64 < n_plain) { A = 0; B = 0; }
+    if (A == 0) B = 0;
+    const uint32_t win_lo = final_bound_ - (uint32_t)B;
+    const uint32_t win_rows = (uint32_t)(A + B);
+    const size_t smem_bytes = std::max<size_t>(16, (size_t)win_rows * row_bytes);
 
     ScanArgs a{};
     a.text = (const uint8_t *)d_text;
@@ -326,6 +340,7 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, size_t n_hay, uint3
     a.n_hay = (uint32_t)n_hay;
     a.uniform_len = uniform_len;
     a.total = total;
+    a.readable = readable;
     a.chunk = chunk;
     a.halo = halo_;
     a.chunk_begin = 0;
@@ -334,15 +349,17 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, size_t n_hay, uint3
     a.table = d_table_;
     a.cls_map = d_cls_;
     a.ncls = ncls_;
-    a.first_final = first_final_;
-    a.smem_entries = (uint32_t)smem_entries;
+    a.final_bound = final_bound_;
+    a.root = root_;
+    a.win_lo = win_lo;
+    a.win_rows = win_rows;
     a.range_lo = range_lo_;
     a.n_used = n_used_;
-    a.init_state = init_state;
+    a.init_state = (init_state == ROOT_STATE) ? root_ : init_state;
     a.tile_status = d_tiles_;
     a.counters = d_counters_;
     a.first_end = d_first_;
-    const unsigned grid = std::min<uint32_t>(n_tiles, (uint32_t)n_sms_);
+    const unsigned grid = std::min<uint32_t>((n_tiles + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32), (uint32_t)n_sms_);
 
     for (int attempt = 0; attempt < 2; ++attempt) {
         a.out = (uint2 *)d_events_;
@@ -388,7 +405,7 @@ bool Engine::scan_device(const void *d_bytes, const uint64_t *offsets, size_t n,
     if (!upload_offsets(offsets, n, &uniform_len)) return false;
     if (!uniform_len && stream && S(stream) != S(stream_)) CU_OK(cudaStreamSynchronize(S(stream_)));
     stats.h2d_ms = 0; stats.d2h_ms = 0;
-    return launch_scan(d_bytes, (uint32_t)total, n, uniform_len, first_only, init_state, stream);
+    return launch_scan(d_bytes, (uint32_t)total, (uint32_t)total, n, uniform_len, first_only, init_state, stream);
 }
 
 bool Engine::scan_host(const char *bytes, const uint64_t *offsets, size_t n, bool first_only,
@@ -405,7 +422,7 @@ bool Engine::scan_host(const char *bytes, const uint64_t *offsets, size_t n, boo
     CU_OK(cudaEventRecord(EV(ev_[2]), st));
     if (total) CU_OK(cudaMemcpyAsync(d_text_, bytes, total, cudaMemcpyHostToDevice, st));
     CU_OK(cudaEventRecord(EV(ev_[3]), st));
-    if (!launch_scan(d_text_, (uint32_t)total, n, uniform_len, first_only, init_state, nullptr)) return false;
+    if (!launch_scan(d_text_, (uint32_t)total, (uint32_t)std::min<uint64_t>(text_cap_, 0xffffffffu), n, uniform_len, first_only, init_state, nullptr)) return false;
     float ms = 0;
     cudaEventElapsedTime(&ms, EV(ev_[2]), EV(ev_[3]));
     stats.h2d_ms = ms;

@@ -14,6 +14,7 @@
 namespace acb200 {
 
 struct PackedEvent { uint32_t end; uint32_t state; };   // as written by the kernel
+constexpr uint32_t ROOT_STATE = 0xffffffffu;            // init_state value meaning "start at the root"
 
 void set_error(const std::string &msg);
 const char *get_error();
@@ -53,7 +54,7 @@ private:
     bool ensure_tiles(size_t n);
     bool ensure_host_events(size_t n);
     bool upload_offsets(const uint64_t *offsets, size_t n, uint32_t *uniform_len);
-    bool launch_scan(const void *d_text, uint32_t total, size_t n_hay, uint32_t uniform_len,
+    bool launch_scan(const void *d_text, uint32_t total, uint32_t readable, size_t n_hay, uint32_t uniform_len,
                      bool first_only, uint32_t init_state, void *stream);
     uint32_t pick_chunk(uint64_t total) const;
     void release();
@@ -67,7 +68,7 @@ private:
     // automaton
     void *d_table_ = nullptr;
     uint8_t *d_cls_ = nullptr;
-    uint32_t ncls_ = 1, first_final_ = 1, n_states_ = 1, halo_ = 0;
+    uint32_t ncls_ = 1, final_bound_ = 1, root_ = 1, n_states_ = 1, n_rows_ = 2, halo_ = 0;
     uint32_t range_lo_ = 0, n_used_ = 0;
     bool range_map_ = true;
     int entry_bytes_ = 2;

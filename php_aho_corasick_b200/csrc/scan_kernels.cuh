@@ -16,10 +16,11 @@
 // from the root equals the state of an uninterrupted scan (every trie node is
 // at most Lmax deep), so event lists are identical to a sequential walk.
 //
-// Events leave the kernel already in ascending buffer order: threads count
-// their events, the CTA prefix-sums the counts, and CTAs chain their totals
-// through a decoupled look-back over `tile_status` (tiles are handed out by an
-// atomic ticket, so a tile only ever waits for tiles that already started).
+// Events leave the kernel already in ascending buffer order: lanes count their
+// events, the warp prefix-sums the counts, and warps chain their totals through
+// a decoupled look-back over `tile_status` (tiles of 32 slices are handed out by
+// an atomic ticket, so a tile only ever waits for tiles that already started).
+// After the table is staged there is no CTA-wide barrier.
 #pragma once
 
 #include <cstdint>
@@ -36,19 +37,22 @@ struct ScanArgs {
     uint32_t n_hay;
     uint32_t uniform_len;         // >0: every haystack is exactly this long (hay_off unused)
     uint32_t total;               // bytes in the stream
+    uint32_t readable;            // bytes that may be read from `text` (>= total; staging buffers are padded)
     uint32_t chunk;               // bytes per thread slice, multiple of 16
     uint32_t halo;                // Lmax-1
     uint32_t chunk_begin;         // this launch covers slices [chunk_begin, chunk_end)
     uint32_t chunk_end;
-    uint32_t n_tiles;             // ceil((chunk_end-chunk_begin)/SCAN_THREADS)
-    const void *table;            // dense delta, n_states x ncls entries
+    uint32_t n_tiles;             // ceil((chunk_end-chunk_begin)/32): a tile is one warp's 32 slices
+    const void *table;            // dense delta, n_rows x ncls entries (row 0 unused)
     const uint8_t *cls_map;       // 256-byte byte->class map
     uint32_t ncls;
-    uint32_t first_final;
-    uint32_t smem_entries;        // leading table entries cached in shared memory
+    uint32_t final_bound;         // states in [1, final_bound) report patterns
+    uint32_t root;                // == final_bound
+    uint32_t win_lo;              // states [win_lo, win_lo + win_rows) have their rows in shared memory
+    uint32_t win_rows;            // 0: no hot window, every byte takes the careful path
     uint32_t range_lo;            // RANGE kernels: class = min(byte - range_lo, n_used)
     uint32_t n_used;
-    uint32_t init_state;          // state at offset 0 of haystack 0 (keep=1 continuation)
+    uint32_t init_state;          // state at offset 0 of haystack 0 (root, or the keep=1 continuation)
     uint2 *out;                   // events {end offset in stream, state}
     uint32_t capacity;            // events that fit in `out`
     unsigned long long *tile_status;  // n_tiles words, zeroed before launch
@@ -59,11 +63,12 @@ struct ScanArgs {
 // ------------------------------------------------------------ finalize ----
 
 // delta[s][*] = delta[fail(s)][*] for every state s of one breadth-first level
-// (root: all zero).  fail(s) is shallower, so its row is already complete.
+// (root: every byte leads back to the root).  fail(s) is shallower, so its row
+// is already complete.
 template <typename E>
 __global__ void expand_inherit_kernel(E *__restrict__ table, const uint32_t *__restrict__ order,
                                       const uint32_t *__restrict__ fail, uint32_t lvl_begin,
-                                      uint32_t lvl_end, uint32_t ncls)
+                                      uint32_t lvl_end, uint32_t ncls, uint32_t root)
 {
     const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long n = (unsigned long long)(lvl_end - lvl_begin) * ncls;
@@ -71,8 +76,8 @@ __global__ void expand_inherit_kernel(E *__restrict__ table, const uint32_t *__r
     const uint32_t si = (uint32_t)(idx / ncls);
     const uint32_t c = (uint32_t)(idx - (unsigned long long)si * ncls);
     const uint32_t s = order[lvl_begin + si];
-    E v = 0;
-    if (s != 0) v = table[(size_t)fail[s] * ncls + c];
+    E v = (E)root;
+    if (s != root) v = table[(size_t)fail[s] * ncls + c];
     table[(size_t)s * ncls + c] = v;
 }
 
@@ -113,13 +118,40 @@ constexpr unsigned long long ST_AGG = 1ull << 62;     // tile total published
 constexpr unsigned long long ST_PREFIX = 2ull << 62;  // inclusive prefix published
 constexpr unsigned long long ST_MASK = (1ull << 62) - 1;
 
+// Shared-memory loads by 32-bit shared-window address (keeps the address math to one IMAD).
+template <typename E> __device__ __forceinline__ uint32_t lds_entry(uint32_t addr);
+template <> __device__ __forceinline__ uint32_t lds_entry<uint16_t>(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+template <> __device__ __forceinline__ uint32_t lds_entry<uint32_t>(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// Per-thread walker.
+//
+// Shared memory holds the rows of a contiguous window of state ids around
+// final_bound: the shallowest final states just below it and the shallowest
+// non-final states (root first) just above it — the rows a scan visits almost
+// all the time.  In that copy every entry whose target lies outside the window
+// is replaced by 0.  Real state ids start at 1 and finals are the ids below
+// final_bound, so ONE compare per byte (entry < final_bound) catches both rare
+// cases: a reporting state (record the event, keep walking) and a step out of
+// the window (finish the 16-byte group on the careful path, which reads true
+// entries from the table in HBM/L2).  The common byte costs
+// {PRMT, class, address, IMAD, LDS, ISETP}.
 template <typename E, bool RANGE, bool FIRST>
 struct Scanner {
     const E *__restrict__ gtab;
-    const E *s_tab;
-    const uint8_t *s_cls;
     const uint8_t *__restrict__ text;
-    uint32_t ncls, smem_entries, lo, n_used, first_final;
+    uint32_t s_tab;          // shared-window byte address of row `win_lo`, minus win_lo*row_bytes
+    uint32_t s_cls;          // shared-window byte address of the 256-byte class map
+    uint32_t ncls, row_bytes, win_lo, win_rows, lo, n_used, final_bound, readable;
 
     // per-thread event record
     uint32_t cnt;
@@ -129,16 +161,28 @@ struct Scanner {
     uint32_t obase, cap;
     bool found;   // FIRST: an event was taken in the current haystack segment
 
-    __device__ __forceinline__ uint32_t next(uint32_t s, uint32_t b) const
+    __device__ __forceinline__ uint32_t cls(uint32_t b) const
     {
-        uint32_t c;
-        if (RANGE) c = min(b - lo, n_used);
-        else c = s_cls[b];
-        const uint32_t idx = s * ncls + c;
-        E e;
-        if (idx < smem_entries) e = s_tab[idx];
-        else e = __ldg(gtab + idx);
-        return (uint32_t)e;
+        if (RANGE) return min(b - lo, n_used);
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(s_cls + b));
+        return v;
+    }
+
+    // fast step: s must be inside the window; returns 0 when the target is outside it
+    __device__ __forceinline__ uint32_t hot_next(uint32_t s, uint32_t b) const
+    {
+        // t is off the dependent chain; the chain is LDS -> IMAD -> LDS
+        const uint32_t t = s_tab + cls(b) * (uint32_t)sizeof(E);
+        uint32_t addr;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(s), "r"(row_bytes), "r"(t));
+        return lds_entry<E>(addr);
+    }
+
+    // careful step: any state, true entry from the full table
+    __device__ __forceinline__ uint32_t any_next(uint32_t s, uint32_t b) const
+    {
+        return (uint32_t)__ldg(gtab + (s * ncls + cls(b)));
     }
 
     template <bool EMIT>
@@ -158,54 +202,80 @@ struct Scanner {
         ++cnt;
     }
 
-    // walk bytes [i, end) without reporting (warm-up over the halo)
-    __device__ __forceinline__ uint32_t walk_quiet(uint32_t s, uint32_t i, uint32_t end) const
+    template <bool REPORT, bool EMIT>
+    __device__ __forceinline__ uint32_t byte_step(uint32_t s, uint32_t i)
     {
-        while (i < end && (i & 15u)) { s = next(s, text[i]); ++i; }
-        while (i + 16 <= end) {
-            const uint4 v = ld_text16(text + i);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) s = next(s, (w[q] >> (8 * k)) & 0xffu);
-            i += 16;
-        }
-        while (i < end) { s = next(s, text[i]); ++i; }
+        s = any_next(s, text[i]);
+        if (REPORT && s < final_bound) hit<EMIT>(i + 1, s);
         return s;
     }
 
-    // walk bytes [i, end) of one haystack, reporting every state >= first_final
-    template <bool EMIT>
-    __device__ __forceinline__ uint32_t walk_report(uint32_t s, uint32_t i, uint32_t end)
+    __device__ __forceinline__ static uint32_t group_byte(const uint4 &v, int j)
     {
-        while (i < end && (i & 15u)) {
-            s = next(s, text[i]); ++i;
-            if (s >= first_final) hit<EMIT>(i, s);
+        const uint32_t word = (j < 8) ? ((j < 4) ? v.x : v.y) : ((j < 12) ? v.z : v.w);
+        return (word >> ((j & 3) * 8)) & 0xffu;
+    }
+
+    // One 16-byte group.  Bytes are taken on the fast path while the state stays
+    // inside the shared-memory window; a step that leaves it is redone on the
+    // careful path (true entry from the full table) and the fast path is
+    // re-entered — through the switch, at the right byte — as soon as the state
+    // is back inside.
+    template <bool REPORT, bool EMIT>
+    __device__ __forceinline__ uint32_t walk_group(uint32_t s, const uint4 &v, uint32_t i)
+    {
+#define ACB_STEP(J, W)                                                                          \
+        case J: {                                                                               \
+            const uint32_t e = hot_next(s, __byte_perm(W, 0, 0x4440 | ((J) & 3)));              \
+            if (e < final_bound) {                                                              \
+                if (e == 0) { j = J; goto careful; }                                            \
+                if (REPORT) hit<EMIT>(i + (J) + 1, e);                                          \
+            }                                                                                   \
+            s = e;                                                                              \
         }
+        int j = 0;
+        while (j < 16) {
+            if (s - win_lo < win_rows) {
+                switch (j) {
+                    ACB_STEP(0, v.x) ACB_STEP(1, v.x) ACB_STEP(2, v.x) ACB_STEP(3, v.x)
+                    ACB_STEP(4, v.y) ACB_STEP(5, v.y) ACB_STEP(6, v.y) ACB_STEP(7, v.y)
+                    ACB_STEP(8, v.z) ACB_STEP(9, v.z) ACB_STEP(10, v.z) ACB_STEP(11, v.z)
+                    ACB_STEP(12, v.w) ACB_STEP(13, v.w) ACB_STEP(14, v.w) ACB_STEP(15, v.w)
+                }
+                return s;
+            }
+        careful:
+            s = any_next(s, group_byte(v, j));
+            if (REPORT && s < final_bound) hit<EMIT>(i + j + 1, s);
+            ++j;
+        }
+#undef ACB_STEP
+        return s;
+    }
+
+    // Walks bytes [i, end) of one haystack from state s.  REPORT: record every
+    // reporting state (EMIT: straight into the output, else count + keep 2).
+    // Text arrives through a three-deep register pipeline of 16-byte loads.
+    template <bool REPORT, bool EMIT>
+    __device__ __forceinline__ uint32_t walk(uint32_t s, uint32_t i, uint32_t end)
+    {
+        while (i < end && (i & 15u)) { s = byte_step<REPORT, EMIT>(s, i); ++i; }
         if (i + 16 <= end) {
-            uint4 v = ld_text16(text + i);
+            uint4 v0 = ld_text16(text + i);
+            uint4 v1 = v0, v2 = v0;
+            if (i + 32 <= readable) v1 = ld_text16(text + i + 16);
+            if (i + 48 <= readable) v2 = ld_text16(text + i + 32);
             while (true) {
-                // prefetch the following 16 bytes (the buffer is padded past `total`)
-                const uint4 nv = ld_text16(text + i + 16);
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        s = next(s, (w[q] >> (8 * k)) & 0xffu);
-                        if (s >= first_final) hit<EMIT>(i + q * 4 + k + 1, s);
-                    }
+                uint4 v3 = v2;
+                if (i + 64 <= readable) v3 = ld_text16(text + i + 48);
+                s = walk_group<REPORT, EMIT>(s, v0, i);
                 i += 16;
-                if (FIRST && found) return s;
+                if (REPORT && FIRST && found) return s;
                 if (i + 16 > end) break;
-                v = nv;
+                v0 = v1; v1 = v2; v2 = v3;
             }
         }
-        while (i < end) {
-            s = next(s, text[i]); ++i;
-            if (s >= first_final) hit<EMIT>(i, s);
-        }
+        while (i < end) { s = byte_step<REPORT, EMIT>(s, i); ++i; }
         return s;
     }
 };
@@ -243,11 +313,11 @@ __device__ __forceinline__ uint32_t scan_slice(const ScanArgs &a, SC &sc, uint32
     while (i < ce) {
         if (i == nb) {                       // haystack boundary: next haystack starts at the root
             do { ++h; nb = hay_end(a, h); } while (nb == i);   // skips empty haystacks
-            s = 0;
+            s = a.root;
             sc.found = false;
         }
         const uint32_t seg_end = min(ce, nb);
-        s = sc.template walk_report<EMIT>(s, i, seg_end);
+        s = sc.template walk<true, EMIT>(s, i, seg_end);
         i = seg_end;                         // FIRST kernels may have stopped early; the rest is irrelevant
     }
     return s;
@@ -259,32 +329,46 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_kernel(const ScanArgs
     extern __shared__ __align__(16) unsigned char smem_raw[];
     E *s_tab = reinterpret_cast<E *>(smem_raw);
     __shared__ uint8_t s_cls[256];
-    __shared__ uint32_t s_warp_tot[SCAN_THREADS / 32];
-    __shared__ uint32_t s_tile, s_base, s_total;
 
     const uint32_t tid = threadIdx.x;
-    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    const uint32_t lane = tid & 31u;
     const E *gtab = static_cast<const E *>(a.table);
 
-    for (uint32_t idx = tid; idx < a.smem_entries; idx += SCAN_THREADS) s_tab[idx] = gtab[idx];
+    // window rows, with targets outside the window replaced by 0
+    const uint32_t win_entries = a.win_rows * a.ncls;
+    const uint32_t win_first = a.win_lo * a.ncls;
+    for (uint32_t idx = tid; idx < win_entries; idx += SCAN_THREADS) {
+        uint32_t e = gtab[win_first + idx];
+        if (e - a.win_lo >= a.win_rows) e = 0;
+        s_tab[idx] = (E)e;
+    }
     if (tid < 256) s_cls[tid] = a.cls_map[tid];
-    __syncthreads();
+    __syncthreads();      // the only CTA-wide barrier: from here on warps run independently
 
     Scanner<E, RANGE, FIRST> sc;
-    sc.gtab = gtab; sc.s_tab = s_tab; sc.s_cls = s_cls; sc.text = a.text;
-    sc.ncls = a.ncls; sc.smem_entries = a.smem_entries; sc.lo = a.range_lo; sc.n_used = a.n_used;
-    sc.first_final = a.first_final;
+    sc.gtab = gtab; sc.text = a.text;
+    sc.ncls = a.ncls; sc.row_bytes = a.ncls * (uint32_t)sizeof(E);
+    sc.win_lo = a.win_lo; sc.win_rows = a.win_rows;
+    {   // opaque moves keep the shared-window addresses in registers instead of being rematerialised
+        const uint32_t t0 = (uint32_t)__cvta_generic_to_shared(s_tab) - a.win_lo * sc.row_bytes;
+        const uint32_t c0 = (uint32_t)__cvta_generic_to_shared(s_cls);
+        asm volatile("mov.u32 %0, %1;" : "=r"(sc.s_tab) : "r"(t0));
+        asm volatile("mov.u32 %0, %1;" : "=r"(sc.s_cls) : "r"(c0));
+    }
+    sc.lo = a.range_lo; sc.n_used = a.n_used;
+    sc.final_bound = a.final_bound; sc.readable = a.readable;
     sc.out = a.out; sc.cap = a.capacity;
 
     const uint32_t prior = a.counters[1];    // events of earlier launches in this call (stream-ordered)
 
+    // A tile is 32 consecutive slices, one per lane; warps take tiles by ticket.
     while (true) {
-        if (tid == 0) s_tile = atomicAdd(&a.counters[0], 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(&a.counters[0], 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= a.n_tiles) break;
 
-        const uint32_t chunk_id = a.chunk_begin + tile * SCAN_THREADS + tid;
+        const uint32_t chunk_id = a.chunk_begin + tile * 32u + lane;
         const bool active = chunk_id < a.chunk_end;
         uint32_t cs = 0, ce = 0, h = 0, s_cs = 0;
         sc.cnt = 0; sc.found = false;
@@ -302,8 +386,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_kernel(const ScanArgs
                 // warm-up start: (Lmax-1) bytes back, rounded down to 16, clamped to the haystack start
                 uint32_t ws = (cs - hb > a.halo) ? ((cs - a.halo) & ~15u) : hb;
                 if (ws < hb) ws = hb;
-                uint32_t s = (ws == hb && h == 0) ? a.init_state : 0u;
-                s = sc.walk_quiet(s, ws, cs);
+                uint32_t s = (ws == hb && h == 0) ? a.init_state : a.root;
+                s = sc.template walk<false, false>(s, ws, cs);
                 s_cs = s;
                 s = scan_slice<false>(a, sc, s, h, cs, ce);
                 if (ce == a.total) a.counters[2] = s;
@@ -314,65 +398,49 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_kernel(const ScanArgs
                 }
             }
         }
+        __syncwarp();
 
-        // CTA exclusive prefix of the per-thread event counts
+        // warp prefix of the per-lane event counts
         uint32_t incl = sc.cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += t;
         }
-        if (lane == 31) s_warp_tot[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t wt = s_warp_tot[lane];
-            uint32_t winc = wt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
-                if (lane >= d) winc += t;
-            }
-            s_warp_tot[lane] = winc - wt;                 // exclusive warp offsets
-            const uint32_t total = __shfl_sync(0xffffffffu, winc, 31);
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
 
-            // decoupled look-back over earlier tiles
-            unsigned long long excl = prior;
-            if (tile == 0) {
-                if (lane == 0) st_status(a.tile_status, ST_PREFIX | (excl + total));
-            } else {
-                if (lane == 0) st_status(a.tile_status + tile, ST_AGG | total);
-                long long j = (long long)tile - 1 - lane;
-                unsigned long long sum = 0;
-                while (true) {
-                    unsigned long long v = ST_PREFIX;     // before tile 0: empty prefix (prior added below)
-                    bool virt = j < 0;
-                    if (!virt) {
-                        do { v = ld_status(a.tile_status + j); } while ((v >> 62) == 0);
-                    }
-                    const bool is_prefix = (v >> 62) == 2;
-                    const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
-                    const int first_p = pm ? (__ffs(pm) - 1) : 32;
-                    unsigned long long contrib = ((int)lane <= first_p) ? (v & ST_MASK) : 0ull;
-                    if (virt && (int)lane == first_p) contrib = prior;
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
-                    sum += contrib;
-                    if (pm) break;
-                    j -= 32;
+        // decoupled look-back over earlier tiles, 32 predecessors per step
+        unsigned long long excl = prior;
+        if (tile == 0) {
+            if (lane == 0) st_status(a.tile_status, ST_PREFIX | (excl + total));
+        } else {
+            if (lane == 0) st_status(a.tile_status + tile, ST_AGG | total);
+            long long j = (long long)tile - 1 - lane;
+            unsigned long long sum = 0;
+            while (true) {
+                unsigned long long v = ST_PREFIX;         // before tile 0: the events of earlier launches
+                const bool virt = j < 0;
+                if (!virt) {
+                    do { v = ld_status(a.tile_status + j); } while ((v >> 62) == 0);
                 }
-                excl = sum;
-                if (lane == 0) st_status(a.tile_status + tile, ST_PREFIX | (excl + total));
+                const bool is_prefix = (v >> 62) == 2;
+                const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
+                const int first_p = pm ? (__ffs(pm) - 1) : 32;
+                unsigned long long contrib = ((int)lane <= first_p) ? (v & ST_MASK) : 0ull;
+                if (virt && (int)lane == first_p) contrib = prior;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+                sum += contrib;
+                if (pm) break;
+                j -= 32;
             }
-            if (lane == 0) {
-                s_base = (uint32_t)excl;
-                s_total = total;
-                if (tile == a.n_tiles - 1) a.counters[1] = (uint32_t)(excl + total);
-            }
+            excl = sum;
+            if (lane == 0) st_status(a.tile_status + tile, ST_PREFIX | (excl + total));
         }
-        __syncthreads();
+        if (lane == 0 && tile == a.n_tiles - 1) a.counters[1] = (uint32_t)(excl + total);
 
         if (sc.cnt) {
-            const uint32_t off = s_base + s_warp_tot[warp] + (incl - sc.cnt);
+            const uint32_t off = (uint32_t)excl + (incl - sc.cnt);
             if (sc.cnt <= 2) {
                 if (off < a.capacity) a.out[off] = make_uint2(sc.e0p, sc.e0s);
                 if (sc.cnt == 2 && off + 1 < a.capacity) a.out[off + 1] = make_uint2(sc.e1p, sc.e1s);
@@ -383,7 +451,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_kernel(const ScanArgs
                 scan_slice<true>(a, sc, s_cs, h, cs, ce);
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 

@@ -45,8 +45,9 @@ PACKED_EVENT_DTYPE = np.dtype([("end", np.uint32), ("state", np.uint32)])
 
 class Info(C.Structure):
     _fields_ = [("n_patterns", C.c_uint64), ("n_states", C.c_uint64), ("n_classes", C.c_uint32),
-                ("entry_bytes", C.c_uint32), ("max_pattern_len", C.c_uint32), ("first_final", C.c_uint32),
-                ("table_bytes", C.c_uint64), ("device", C.c_int32), ("finalized", C.c_int32)]
+                ("entry_bytes", C.c_uint32), ("max_pattern_len", C.c_uint32), ("final_bound", C.c_uint32),
+                ("root", C.c_uint32), ("table_bytes", C.c_uint64), ("device", C.c_int32),
+                ("finalized", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class Stats(C.Structure):

@@ -63,7 +63,7 @@ def test_cfg2_benchmark_shape_planted():
     a = build([needles])
     ev = a.search_events(hay, off)
     exp = oracle_hits([needles], split(hay, off))
-    assert sum(e[2] for e in exp) >= 256 * 8
+    assert sum(e[2] for e in exp) >= 256 * 7     # planted needles may overwrite each other
     assert_same(a, ev, 256, exp)
     st = a.stats()
     assert st.kernel_launches >= 1 and st.bytes == hay.size
