@@ -42,3 +42,40 @@ def assert_same(aut, events, n_hay, expected):
         assert gnev == enev, f"haystack {h}: {gnev} events, oracle {enev}"
         assert np.array_equal(gpos, epos), f"haystack {h}: positions differ"
         assert np.array_equal(gpat, epat), f"haystack {h}: pattern order differs"
+
+
+# ---- golden fixtures (tests/golden/phpt_golden.json, generated from the reference's tests/*.phpt) ----
+import json
+import os
+
+GOLDEN_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "phpt_golden.json")
+
+
+def load_golden():
+    with open(GOLDEN_PATH, encoding="utf-8") as f:
+        return json.load(f)
+
+
+def golden_record(rec):
+    """golden var_dump array -> (ordered key list, plain dict)"""
+    order = rec["__order__"]
+    return order, {k: rec[k] for k in order}
+
+
+def record_for(spec: dict, pos: int):
+    """What php_ahocorasick_match_handler (src/php_ahocorasick.c:542-589) builds for pattern `spec` ending at pos."""
+    d = {"pos": pos}
+    if "key" in spec:
+        d["key"] = spec["key"]
+    elif "id" in spec:
+        d["keyIdx"] = spec["id"]
+    if "aux" in spec:
+        d["aux"] = spec["aux"]
+    d["start_postion"] = pos - len(spec["value"].encode("utf-8"))
+    d["value"] = spec["value"]
+    return d
+
+
+def case_calls(case):
+    """pattern-array calls of a golden case: init(...) then each add_patterns(...)"""
+    return [case["init"]] + list(case.get("add_patterns", []))
