@@ -188,6 +188,24 @@ int acb200_search_device(AC_TRIE_t *thiz, const void *d_bytes,
                          void *stream, const void **d_events,
                          size_t *n_events);
 
+/* Copies up to max_events packed {uint32 end_in_buffer, uint32 state} records of the most recent
+ * device-resident search into the caller's DEVICE buffer `d_dst` (async on `stream`, NULL = the
+ * handle's stream).  Returns the number of records copied, or -1.                      */
+long acb200_copy_events(AC_TRIE_t *thiz, void *d_dst, size_t max_events, void *stream);
+
+/* A ready-made consumer for callers that only need totals: pass acb200_tally_cb as the
+ * ACB200_BATCH_CALLBACK_f (or acb200_tally_match_cb as the AC_MATCH_CALBACK_f) and an
+ * ACB200_TALLY_t as `user`.  `hash` folds (text_idx, position, size, first and last pattern's
+ * aux) in callback order, so equal hashes mean equal event sequences.                 */
+typedef struct acb200_tally
+{
+    uint64_t events;
+    uint64_t hits;
+    uint64_t hash;
+} ACB200_TALLY_t;
+int acb200_tally_cb(size_t text_idx, AC_MATCH_t *m, void *tally);
+int acb200_tally_match_cb(AC_MATCH_t *m, void *tally);
+
 /* Patterns reported by automaton state `state` (longest first); returns the
  * count and stores a library-owned array in *patterns (NULL if none).       */
 size_t acb200_state_patterns(const AC_TRIE_t *thiz, uint32_t state,

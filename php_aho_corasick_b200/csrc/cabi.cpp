@@ -6,6 +6,7 @@
 // the compact (position, state) events through the caller's callback exactly
 // as the reference's loop would have called it
 // (src/multifast/ahocorasick.c:214-233).
+#include <algorithm>
 #include <cstring>
 #include <new>
 #include <string>
@@ -202,6 +203,38 @@ int acb200_search_device(AC_TRIE_t *t, const void *d_bytes, const uint64_t *offs
     if (n_events) *n_events = t->engine.n_events();
     return 0;
 }
+
+long acb200_copy_events(AC_TRIE_t *t, void *d_dst, size_t max_events, void *stream)
+{
+    if (t->open || !t->device_ok) { set_error("automaton is not finalized"); return -1; }
+    const size_t n = std::min(max_events, t->engine.n_events());
+    if (n && !t->engine.copy_events_to(d_dst, n, stream)) return -1;
+    return (long)n;
+}
+
+static inline uint64_t tally_fold(uint64_t h, uint64_t v)
+{
+    h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+    return h * 0xff51afd7ed558ccdULL;
+}
+
+int acb200_tally_cb(size_t text_idx, AC_MATCH_t *m, void *tally)
+{
+    ACB200_TALLY_t *t = static_cast<ACB200_TALLY_t *>(tally);
+    t->events++;
+    t->hits += m->size;
+    uint64_t h = tally_fold(t->hash, (uint64_t)text_idx);
+    h = tally_fold(h, (uint64_t)m->position);
+    h = tally_fold(h, (uint64_t)m->size);
+    if (m->size) {
+        h = tally_fold(h, (uint64_t)(uintptr_t)m->patterns[0].aux);
+        h = tally_fold(h, (uint64_t)(uintptr_t)m->patterns[m->size - 1].aux);
+    }
+    t->hash = h;
+    return 0;
+}
+
+int acb200_tally_match_cb(AC_MATCH_t *m, void *tally) { return acb200_tally_cb(0, m, tally); }
 
 size_t acb200_state_patterns(const AC_TRIE_t *t, uint32_t state, const AC_PATTERN_t **patterns)
 {

@@ -37,6 +37,7 @@ public:
     bool scan_device(const void *d_bytes, const uint64_t *offsets, size_t n, bool first_only,
                      uint32_t init_state, void *stream);
 
+    bool copy_events_to(void *d_dst, size_t n, void *stream);
     const PackedEvent *host_events() const { return h_events_; }
     const void *device_events() const { return d_events_; }
     size_t n_events() const { return n_events_; }

@@ -43,6 +43,10 @@ EVENT_DTYPE = np.dtype([("end", np.uint64), ("state", np.uint32), ("text_idx", n
 PACKED_EVENT_DTYPE = np.dtype([("end", np.uint32), ("state", np.uint32)])
 
 
+class Tally(C.Structure):
+    _fields_ = [("events", C.c_uint64), ("hits", C.c_uint64), ("hash", C.c_uint64)]
+
+
 class Info(C.Structure):
     _fields_ = [("n_patterns", C.c_uint64), ("n_states", C.c_uint64), ("n_classes", C.c_uint32),
                 ("entry_bytes", C.c_uint32), ("max_pattern_len", C.c_uint32), ("final_bound", C.c_uint32),
@@ -65,7 +69,7 @@ EXPORTS = [
     "ac_trie_search_batch", "ac_trie_search_flat", "acb200_search_events", "acb200_search_device",
     "acb200_state_patterns", "acb200_info", "acb200_last_stats", "acb200_last_error",
     "acb200_set_device", "acb200_device_count", "acb200_host_alloc", "acb200_host_free",
-    "acb200_set_tuning", "acb200_version",
+    "acb200_set_tuning", "acb200_version", "acb200_copy_events", "acb200_tally_cb", "acb200_tally_match_cb",
 ]
 
 
@@ -109,6 +113,8 @@ def lib() -> C.CDLL:
     L.acb200_host_free.restype = None
     L.acb200_set_tuning.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
     L.acb200_version.restype = C.c_char_p
+    L.acb200_copy_events.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.acb200_copy_events.restype = C.c_long
     _lib = L
     return L
 
@@ -204,6 +210,24 @@ class Automaton:
         if rc != 0:
             raise AcError(last_error())
         return out.value, int(ne.value)
+
+    def search_flat_tally(self, host_ptr: int, offsets, first_only: bool = False) -> Tally:
+        """ac_trie_search_flat() on a HOST buffer (e.g. pinned) with the library's tally callback:
+        H2D copy, scan, D2H of the events and the host-side replay all happen inside this call."""
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        t = Tally()
+        cb = C.cast(self.L.acb200_tally_cb, BATCH_CB)
+        rc = self.L.ac_trie_search_flat(self.h, C.c_void_p(host_ptr), off.ctypes.data, off.size - 1, int(first_only),
+                                        cb, C.cast(C.byref(t), C.c_void_p))
+        if rc != 0:
+            raise AcError(last_error())
+        return t
+
+    def copy_events(self, dev_ptr: int, max_events: int, stream: int = 0) -> int:
+        n = self.L.acb200_copy_events(self.h, C.c_void_p(dev_ptr), int(max_events), C.c_void_p(stream))
+        if n < 0:
+            raise AcError(last_error())
+        return int(n)
 
     def search_callback(self, text: bytes, keep: bool = False, stop_after_first: bool = False):
         """ac_trie_search() with a recording callback. -> (rc, [(position, [ordinals...]), ...])"""

@@ -1,0 +1,77 @@
+"""Host logic of the multi-GPU path on CPU: byte-balanced sharding, the variable-length event gather
+(gloo, world_size 2) and the conversion back to per-haystack coordinates."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from php_aho_corasick_b200.dist import gather_packed_events, globalize, shard_ranges
+
+
+def test_shard_ranges_cover_and_balance():
+    off = np.concatenate([[0], np.cumsum([10, 0, 5, 100, 1, 1, 50, 0, 33])]).astype(np.uint64)
+    for world in (1, 2, 3, 4, 8, 16):
+        r = shard_ranges(off, world)
+        assert len(r) == world and r[0][0] == 0 and r[-1][1] == 9
+        assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+    off = np.arange(0, 65537, dtype=np.uint64) * 65536          # config 4 shape: 65536 x 64 KiB
+    r = shard_ranges(off, 8)
+    assert [b - a for a, b in r] == [8192] * 8
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # batch of 6 haystacks; rank 0 owns [0,3), rank 1 owns [3,6)
+    off = np.array([0, 100, 100, 250, 300, 420, 500], dtype=np.uint64)
+    ranges = shard_ranges(off, world)
+    if rank == 0:       # events (end offset in own stream, state)
+        local = torch.tensor([[5, 7], [100, 9], [101, 3], [250, 4]], dtype=torch.int32)
+    else:
+        base = int(off[ranges[1][0]])
+        local = torch.tensor([[300 - base, 11], [301 - base, 12], [500 - base, 13]], dtype=torch.int32) if ranges[1][1] > ranges[1][0] else torch.zeros((0, 2), dtype=torch.int32)
+    got = gather_packed_events(local, 0)
+    if rank == 0:
+        ev = globalize(got, ranges, off)
+        q.put((ranges, ev["text_idx"].tolist(), ev["end"].tolist(), ev["state"].tolist()))
+    else:
+        assert got is None
+    # second round with an empty contribution from rank 1
+    got = gather_packed_events(local if rank == 0 else torch.zeros((0, 2), dtype=torch.int32), 0)
+    if rank == 0:
+        q.put(sum(int(g.shape[0]) for g in got))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_two_rank_gather_and_globalize():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ranges, tidx, end, state = q.get(timeout=120)
+    n_second = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ranges == [(0, 3), (3, 6)]
+    # haystack 0 = (0,100], 2 = (100,250], 3 = (250,300], 4 = (300,420], 5 = (420,500]
+    assert tidx == [0, 0, 2, 2, 3, 4, 5]
+    assert end == [5, 100, 1, 150, 50, 1, 80]
+    assert state == [7, 9, 3, 4, 11, 12, 13]
+    assert n_second == 4
