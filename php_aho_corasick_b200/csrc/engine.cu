@@ -277,7 +277,7 @@ bool Engine::upload_offsets(const uint64_t *offsets, size_t n, uint32_t *uniform
 uint32_t Engine::pick_chunk(uint64_t total) const
 {
     if (tune_chunk) return std::max(16u, (tune_chunk + 15u) & ~15u);
-    auto up16 = [](uint64_t v) { return (v + 15) & ~15ull; };
+    auto up16 = [](uint64_t v) -> uint64_t { return (v + 15) & ~(uint64_t)15; };
     // Steady state: 512-byte slices measured best on B200 (adjacent lanes stay within a few DRAM
     // pages, the (Lmax-1)-byte halo re-read stays below ~12%); long patterns need longer slices.
     const uint64_t ideal = std::max<uint64_t>(512, up16(8ull * (halo_ + 1)));
