@@ -238,6 +238,8 @@ typedef struct acb200_stats
     uint32_t halo_bytes;      /* overlap re-read before each slice           */
     float kernel_ms;          /* device time of the scan kernel(s)           */
     float h2d_ms, d2h_ms;     /* copies, 0 for the device-resident entry     */
+    uint32_t ilp;             /* slices walked in lockstep per lane (1 or 4) */
+    uint32_t reserved_;
 } ACB200_STATS_t;
 int acb200_last_stats(const AC_TRIE_t *thiz, ACB200_STATS_t *out);
 
@@ -257,6 +259,9 @@ void acb200_host_free(void *p);
 /* Tuning knobs (0 = automatic). chunk_bytes: bytes per thread slice. */
 int acb200_set_tuning(AC_TRIE_t *thiz, uint32_t chunk_bytes,
                       uint32_t smem_table_bytes);
+
+/* Slices per lane: 0 = automatic, 1 or 4 force a kernel variant (benchmarks, tests). */
+int acb200_set_ilp(AC_TRIE_t *thiz, int ilp);
 
 const char *acb200_version(void);
 

@@ -269,6 +269,12 @@ int acb200_set_tuning(AC_TRIE_t *t, uint32_t chunk_bytes, uint32_t smem_table_by
     return 0;
 }
 
+int acb200_set_ilp(AC_TRIE_t *t, int ilp)
+{
+    t->engine.tune_ilp = ilp;
+    return 0;
+}
+
 void ac_trie_release(AC_TRIE_t *t)
 {
     delete t;

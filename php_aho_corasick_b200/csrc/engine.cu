@@ -1,6 +1,7 @@
 // engine.cu — see engine.hpp.
 #include "engine.hpp"
 #include "scan_kernels.cuh"
+#include "scan_kernel_x4.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -187,6 +188,10 @@ bool Engine::build(const FlatAutomaton &f)
     CU_OK((set_smem_attr<uint32_t, true, true>(dyn)));
     CU_OK((set_smem_attr<uint32_t, false, false>(dyn)));
     CU_OK((set_smem_attr<uint32_t, false, true>(dyn)));
+    CU_OK(cudaFuncSetAttribute(ac_scan_kernel_x4<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    CU_OK(cudaFuncSetAttribute(ac_scan_kernel_x4<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    CU_OK(cudaFuncSetAttribute(ac_scan_kernel_x4<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    CU_OK(cudaFuncSetAttribute(ac_scan_kernel_x4<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
 
     info.n_states = n_states_;
     info.n_classes = ncls_;
@@ -308,9 +313,7 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
 
     const uint32_t chunk = pick_chunk(total);
     const uint32_t n_chunks = (uint32_t)(((uint64_t)total + chunk - 1) / chunk);
-    const uint32_t n_tiles = (n_chunks + 31u) / 32u;
     stats.chunk_bytes = chunk;
-    if (!ensure_tiles(n_tiles)) return false;
     if (events_cap_ == 0 && !ensure_events(std::max<size_t>(1 << 16, total / 64))) return false;
     if (first_only) {
         if (n_hay > first_cap_) {
@@ -337,6 +340,15 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     const uint32_t win_rows = (uint32_t)(A + B);
     const size_t smem_bytes = std::max<size_t>(16, (size_t)win_rows * row_bytes);
 
+    // ac_scan_kernel_x4 (four slices per lane in lockstep) is opt-in for now: with text arriving through
+    // strided 16-byte loads the L1TEX pipe, not lookup latency, is the limit, and measured on B200 it is
+    // no faster than one slice per lane (940 vs 968 GB/s) and much slower when events are dense.
+    const bool x4 = (tune_ilp == 4) && !first_only && win_rows > 0;
+    const uint32_t per_tile = x4 ? 32u * X4 : 32u;
+    const uint32_t n_tiles = (n_chunks + per_tile - 1) / per_tile;
+
+    if (!ensure_tiles(n_tiles)) return false;
+
     ScanArgs a{};
     a.text = (const uint8_t *)d_text;
     a.hay_off = uniform_len ? nullptr : d_off_;
@@ -362,7 +374,9 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     a.tile_status = d_tiles_;
     a.counters = d_counters_;
     a.first_end = d_first_;
-    const unsigned grid = std::min<uint32_t>((n_tiles + SCAN_THREADS / 32 - 1) / (SCAN_THREADS / 32), (uint32_t)n_sms_);
+    if (win_rows == 0 && x4) { set_error("internal: x4 kernel chosen without a window"); return false; }
+    const unsigned warps_per_cta = (x4 ? X4_THREADS : SCAN_THREADS) / 32;
+    const unsigned grid = std::min<uint32_t>((n_tiles + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
 
     for (int attempt = 0; attempt < 2; ++attempt) {
         a.out = (uint2 *)d_events_;
@@ -371,7 +385,15 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
         CU_OK(cudaMemsetAsync(d_counters_, 0, 16, st));
         if (first_only) CU_OK(cudaMemsetAsync(d_first_, 0xff, n_hay * sizeof(uint32_t), st));
         CU_OK(cudaEventRecord(EV(ev_[0]), st));
-        if (entry_bytes_ == 2) {
+        if (x4) {
+            if (entry_bytes_ == 2) {
+                if (range_map_) ac_scan_kernel_x4<uint16_t, true><<<grid, X4_THREADS, smem_bytes, st>>>(a);
+                else ac_scan_kernel_x4<uint16_t, false><<<grid, X4_THREADS, smem_bytes, st>>>(a);
+            } else {
+                if (range_map_) ac_scan_kernel_x4<uint32_t, true><<<grid, X4_THREADS, smem_bytes, st>>>(a);
+                else ac_scan_kernel_x4<uint32_t, false><<<grid, X4_THREADS, smem_bytes, st>>>(a);
+            }
+        } else if (entry_bytes_ == 2) {
             if (range_map_) { if (first_only) launch_kernel<uint16_t, true, true>(a, grid, smem_bytes, st); else launch_kernel<uint16_t, true, false>(a, grid, smem_bytes, st); }
             else            { if (first_only) launch_kernel<uint16_t, false, true>(a, grid, smem_bytes, st); else launch_kernel<uint16_t, false, false>(a, grid, smem_bytes, st); }
         } else {
@@ -388,7 +410,12 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
         stats.kernel_ms += ms;
         const size_t found = h_counters_[1];
         end_state_ = h_counters_[2];
-        if (found <= events_cap_) { n_events_ = found; stats.events = found; return true; }
+        if (found <= events_cap_) {
+            n_events_ = found; stats.events = found;
+            last_density_ = (double)found / (double)total;
+            stats.ilp = x4 ? 4 : 1;
+            return true;
+        }
         // event buffer too small: grow to the exact need and scan again
         if (!ensure_events(found + found / 16 + 1024)) return false;
     }

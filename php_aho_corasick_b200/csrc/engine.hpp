@@ -47,6 +47,7 @@ public:
     ACB200_INFO_t info{};
     uint32_t tune_chunk = 0;
     uint32_t tune_smem_bytes = 0;
+    int tune_ilp = 0;              // 0 auto, 1 one slice per lane, 4 four slices per lane
 
 private:
     bool ensure_text(size_t bytes);
@@ -87,6 +88,7 @@ private:
     uint8_t *h_stage_ = nullptr;  size_t stage_cap_ = 0;          // pinned staging for pageable input
     std::vector<uint32_t> off32_;
 
+    double last_density_ = 0.0;    // events per byte of the previous scan (kernel choice)
     size_t n_events_ = 0;
     uint32_t end_state_ = 0;
 };

@@ -57,7 +57,7 @@ class Info(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("bytes", C.c_uint64), ("events", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("chunk_bytes", C.c_uint32), ("halo_bytes", C.c_uint32), ("kernel_ms", C.c_float),
-                ("h2d_ms", C.c_float), ("d2h_ms", C.c_float)]
+                ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("ilp", C.c_uint32), ("reserved_", C.c_uint32)]
 
 
 MATCH_CB = C.CFUNCTYPE(C.c_int, C.POINTER(AcMatch), C.c_void_p)
@@ -69,7 +69,7 @@ EXPORTS = [
     "ac_trie_search_batch", "ac_trie_search_flat", "acb200_search_events", "acb200_search_device",
     "acb200_state_patterns", "acb200_info", "acb200_last_stats", "acb200_last_error",
     "acb200_set_device", "acb200_device_count", "acb200_host_alloc", "acb200_host_free",
-    "acb200_set_tuning", "acb200_version", "acb200_copy_events", "acb200_tally_cb", "acb200_tally_match_cb",
+    "acb200_set_tuning", "acb200_version", "acb200_copy_events", "acb200_tally_cb", "acb200_tally_match_cb", "acb200_set_ilp",
 ]
 
 
@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
     L.acb200_host_free.restype = None
     L.acb200_set_tuning.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
     L.acb200_version.restype = C.c_char_p
+    L.acb200_set_ilp.argtypes = [C.c_void_p, C.c_int]
     L.acb200_copy_events.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.acb200_copy_events.restype = C.c_long
     _lib = L
@@ -177,8 +178,10 @@ class Automaton:
         if inf.device < 0:
             raise AcError("finalize did not reach the GPU: " + last_error())
 
-    def set_tuning(self, chunk_bytes: int = 0, smem_table_bytes: int = 0) -> None:
+    def set_tuning(self, chunk_bytes: int = 0, smem_table_bytes: int = 0, ilp: int | None = None) -> None:
         self.L.acb200_set_tuning(self.h, int(chunk_bytes), int(smem_table_bytes))
+        if ilp is not None:
+            self.L.acb200_set_ilp(self.h, int(ilp))
 
     # -- search -----------------------------------------------------------
     def search_events(self, flat, offsets=None, first_only: bool = False) -> np.ndarray:
