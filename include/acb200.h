@@ -224,7 +224,11 @@ typedef struct acb200_info
     uint64_t table_bytes;     /* dense transition table in HBM               */
     int32_t device;           /* CUDA device ordinal                         */
     int32_t finalized;
-    int32_t reserved_;
+    int32_t filter_word;      /* prefilter word size W (8 or 4), 0 = dictionary not eligible */
+    uint32_t min_pattern_len; /* shortest accepted pattern                   */
+    float filter_l1_fill;     /* fraction of level-1 prefilter bits set      */
+    uint32_t filter_l2_log2;  /* log2(bits) of the level-2 bitmap, 0 = none  */
+    uint32_t reserved_;
 } ACB200_INFO_t;
 int acb200_info(const AC_TRIE_t *thiz, ACB200_INFO_t *out);
 
@@ -239,7 +243,11 @@ typedef struct acb200_stats
     float kernel_ms;          /* device time of the scan kernel(s)           */
     float h2d_ms, d2h_ms;     /* copies, 0 for the device-resident entry     */
     uint32_t ilp;             /* slices walked in lockstep per lane (1 or 4) */
-    uint32_t reserved_;
+    uint32_t filtered;        /* 1: gram prefilter + verify kernels, 0: full automaton walk */
+    float filter_ms;          /* device time of the prefilter kernel (0 if unused) */
+    float verify_ms;          /* device time of the verify kernel (0 if unused) */
+    uint64_t flagged_words;   /* aligned words the prefilter handed to verification */
+    uint64_t dense_tiles;     /* 16 KiB tiles the verify kernel walked completely */
 } ACB200_STATS_t;
 int acb200_last_stats(const AC_TRIE_t *thiz, ACB200_STATS_t *out);
 
@@ -262,6 +270,11 @@ int acb200_set_tuning(AC_TRIE_t *thiz, uint32_t chunk_bytes,
 
 /* Slices per lane: 0 = automatic, 1 or 4 force a kernel variant (benchmarks, tests). */
 int acb200_set_ilp(AC_TRIE_t *thiz, int ilp);
+
+/* Gram prefilter (dictionaries whose accepted patterns are all >= 8 bytes): 0 = automatic,
+ * 1 = use it whenever the dictionary allows, -1 = never (always walk the full automaton).
+ * Results are identical either way.                                                     */
+int acb200_set_filter(AC_TRIE_t *thiz, int mode);
 
 const char *acb200_version(void);
 

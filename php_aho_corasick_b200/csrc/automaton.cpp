@@ -1,5 +1,6 @@
 // automaton.cpp — see automaton.hpp.
 #include "automaton.hpp"
+#include "filter_hash.hpp"
 
 #include <algorithm>
 #include <cstring>
@@ -263,6 +264,56 @@ void HostTrie::flatten(FlatAutomaton &flat) {
         uint32_t v = old_of_final[i];
         if (own_[v] >= 0) flat.out_pat[o++] = patterns_[own_[v]];
         for (uint32_t d = dlink[v]; d != NONE; d = dlink[d]) flat.out_pat[o++] = patterns_[own_[d]];
+    }
+
+    build_filter(flat);
+}
+
+// Gram prefilter tables (see FlatAutomaton).  Every ACCEPTED pattern contributes the W words that can be
+// "the last aligned word before the end offset" of one of its occurrences.
+void HostTrie::build_filter(FlatAutomaton &flat) const {
+    flat.filter_w = 0; flat.l1_bits = 0; flat.l1.clear(); flat.l2_log2 = 0; flat.l2.clear();
+    flat.n_grams = 0; flat.l1_fill = 0.0;
+    uint32_t min_len = 0;
+    for (const AC_PATTERN_t &p : patterns_)
+        min_len = min_len ? std::min<uint32_t>(min_len, (uint32_t)p.ptext.length) : (uint32_t)p.ptext.length;
+    flat.min_pattern_len = min_len;
+    const uint32_t W = (min_len >= 16) ? 8u : (min_len >= 8) ? 4u : 0u;
+    if (!W) return;
+
+    auto gram = [&](const AC_PATTERN_t &p, uint32_t r, uint32_t &lo, uint32_t &hi) {
+        const uint8_t *b = (const uint8_t *)p.ptext.astring + (p.ptext.length - W - r);
+        lo = hi = 0;
+        memcpy(&lo, b, 4);
+        if (W == 8) memcpy(&hi, b + 4, 4);
+    };
+    flat.filter_w = W;
+    flat.l1_bits = FILTER_L1_BITS;
+    flat.l1.assign(FILTER_L1_BITS / 32, 0);
+    for (const AC_PATTERN_t &p : patterns_)
+        for (uint32_t r = 1; r <= W; ++r) {
+            uint32_t lo, hi;
+            gram(p, r, lo, hi);
+            const uint32_t i = filter_reduce(filter_mix1(lo, hi), flat.l1_bits);
+            flat.l1[i >> 5] |= 1u << (i & 31);
+        }
+    flat.n_grams = (uint64_t)patterns_.size() * W;
+    uint64_t set = 0;
+    for (uint32_t w : flat.l1) set += (uint64_t)__builtin_popcount(w);
+    flat.l1_fill = (double)set / (double)flat.l1_bits;
+
+    if (flat.l1_fill > 0.04) {
+        uint32_t lg = 23;                                   // at least 1 MiB: ~256 bits per gram, capped at 128 MiB
+        while (lg < 30 && (1ull << lg) < flat.n_grams * 256) ++lg;
+        flat.l2_log2 = lg;
+        flat.l2.assign((size_t)1 << (lg - 5), 0);
+        for (const AC_PATTERN_t &p : patterns_)
+            for (uint32_t r = 1; r <= W; ++r) {
+                uint32_t lo, hi;
+                gram(p, r, lo, hi);
+                const uint32_t i = filter_mix2(lo, hi) >> (32 - lg);
+                flat.l2[i >> 5] |= 1u << (i & 31);
+            }
     }
 }
 

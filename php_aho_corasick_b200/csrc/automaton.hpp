@@ -61,6 +61,22 @@ struct FlatAutomaton {
     // output lists for final states (index: state - 1), longest pattern first
     std::vector<uint64_t> out_off;
     std::vector<AC_PATTERN_t> out_pat;
+
+    // Gram prefilter (filter_kernels.cuh).  With every accepted pattern at least 2W bytes long
+    // (W = 8 or 4), a match that ends at stream offset p contains the aligned W-byte word k with
+    // W(k+1) < p <= W(k+2) entirely inside its last 2W bytes.  `l1` is a bitmap over the hashes of
+    // the W such words of every pattern (pattern[L-W-r, L-r), r = 1..W): a haystack word whose bit
+    // is clear cannot be that word of any match, so only the W end offsets after a flagged word have
+    // to be verified with the automaton.  `l2` is a second, larger bitmap over an independent hash,
+    // built only when the first level is too full to be selective.
+    uint32_t min_pattern_len = 0;
+    uint32_t filter_w = 0;             // 0: dictionary not eligible (some pattern shorter than 8 bytes)
+    uint32_t l1_bits = 0;
+    std::vector<uint32_t> l1;          // l1_bits / 32 words
+    uint32_t l2_log2 = 0;              // level 2 holds 2^l2_log2 bits; 0: not used
+    std::vector<uint32_t> l2;
+    uint64_t n_grams = 0;
+    double l1_fill = 0.0;              // fraction of level-1 bits set
 };
 
 class HostTrie {
@@ -76,6 +92,7 @@ public:
 
 private:
     const char *keep_bytes(const char *p, size_t n);
+    void build_filter(FlatAutomaton &flat) const;
 
     std::vector<uint32_t> parent_;
     std::vector<uint8_t>  in_byte_;

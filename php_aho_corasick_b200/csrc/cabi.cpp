@@ -275,6 +275,12 @@ int acb200_set_ilp(AC_TRIE_t *t, int ilp)
     return 0;
 }
 
+int acb200_set_filter(AC_TRIE_t *t, int mode)
+{
+    t->engine.tune_filter = mode;
+    return 0;
+}
+
 void ac_trie_release(AC_TRIE_t *t)
 {
     delete t;

@@ -2,6 +2,7 @@
 #include "engine.hpp"
 #include "scan_kernels.cuh"
 #include "scan_kernel_x4.cuh"
+#include "filter_kernels.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -57,6 +58,8 @@ void Engine::release()
     if (stream_) cudaStreamSynchronize(S(stream_));
     cudaFree(d_table_); cudaFree(d_cls_); cudaFree(d_text_); cudaFree(d_off_);
     cudaFree(d_first_); cudaFree(d_events_); cudaFree(d_tiles_); cudaFree(d_counters_);
+    cudaFree(d_l1_); cudaFree(d_l2_); cudaFree(d_mask_);
+    d_l1_ = nullptr; d_l2_ = nullptr; d_mask_ = nullptr; mask_cap_ = 0;
     if (h_counters_) cudaFreeHost(h_counters_);
     if (h_events_) cudaFreeHost(h_events_);
     if (h_stage_) cudaFreeHost(h_stage_);
@@ -193,6 +196,34 @@ bool Engine::build(const FlatAutomaton &f)
     CU_OK(cudaFuncSetAttribute(ac_scan_kernel_x4<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     CU_OK(cudaFuncSetAttribute(ac_scan_kernel_x4<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
 
+    // gram prefilter tables
+    filter_w_ = f.filter_w; l1_bits_ = f.l1_bits; l2_log2_ = f.l2_log2;
+    if (filter_w_) {
+        CU_OK(cudaMalloc(&d_l1_, f.l1.size() * sizeof(uint32_t)));
+        CU_OK(cudaMemcpyAsync(d_l1_, f.l1.data(), f.l1.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        if (l2_log2_) {
+            CU_OK(cudaMalloc(&d_l2_, f.l2.size() * sizeof(uint32_t)));
+            CU_OK(cudaMemcpyAsync(d_l2_, f.l2.data(), f.l2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        }
+        CU_OK(cudaStreamSynchronize(st));
+        CU_OK(cudaFuncSetAttribute(ac_filter_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
+        CU_OK(cudaFuncSetAttribute(ac_filter_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
+        CU_OK(cudaFuncSetAttribute(ac_filter_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
+        CU_OK(cudaFuncSetAttribute(ac_filter_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
+        CU_OK(cudaFuncSetAttribute(ac_verify_kernel<uint16_t, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        CU_OK(cudaFuncSetAttribute(ac_verify_kernel<uint16_t, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        CU_OK(cudaFuncSetAttribute(ac_verify_kernel<uint32_t, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        CU_OK(cudaFuncSetAttribute(ac_verify_kernel<uint32_t, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        CU_OK(cudaFuncSetAttribute(ac_verify_kernel<uint16_t, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        CU_OK(cudaFuncSetAttribute(ac_verify_kernel<uint16_t, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        CU_OK(cudaFuncSetAttribute(ac_verify_kernel<uint32_t, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        CU_OK(cudaFuncSetAttribute(ac_verify_kernel<uint32_t, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    }
+    info.filter_word = (int32_t)filter_w_;
+    info.min_pattern_len = f.min_pattern_len;
+    info.filter_l1_fill = (float)f.l1_fill;
+    info.filter_l2_log2 = l2_log2_;
+
     info.n_states = n_states_;
     info.n_classes = ncls_;
     info.entry_bytes = (uint32_t)entry_bytes_;
@@ -249,6 +280,16 @@ bool Engine::ensure_offsets(size_t n)
     return true;
 }
 
+bool Engine::ensure_mask(size_t words)
+{
+    if (words <= mask_cap_) return true;
+    cudaFree(d_mask_); d_mask_ = nullptr; mask_cap_ = 0;
+    const size_t cap = std::max(words + words / 4, (size_t)4096);
+    CU_OK(cudaMalloc(&d_mask_, cap * sizeof(uint32_t)));
+    mask_cap_ = cap;
+    return true;
+}
+
 bool Engine::ensure_tiles(size_t n)
 {
     if (n <= tiles_cap_) return true;
@@ -295,6 +336,22 @@ uint32_t Engine::pick_chunk(uint64_t total) const
     return (uint32_t)std::min<uint64_t>(c, ideal);
 }
 
+// Rows of the dense table that go to shared memory: a contiguous id window around final_bound.
+void Engine::window_for(size_t smem_budget, uint32_t *win_lo, uint32_t *win_rows) const
+{
+    const size_t row_bytes = (size_t)ncls_ * entry_bytes_;
+    const uint64_t rows_fit = smem_budget / row_bytes;
+    const uint64_t n_final = final_bound_ - 1, n_plain = n_rows_ - final_bound_;
+    uint64_t B = std::min<uint64_t>(n_final, rows_fit / 4);
+    uint64_t A = std::min<uint64_t>(n_plain, rows_fit - B);
+    B = std::min<uint64_t>(n_final, rows_fit - A);
+    // a window that covers only a sliver of a huge automaton cannot pay for itself
+    if (!tune_smem_bytes && A * 64 < n_plain) { A = 0; B = 0; }
+    if (A == 0) B = 0;
+    *win_lo = final_bound_ - (uint32_t)B;
+    *win_rows = (uint32_t)(A + B);
+}
+
 template <typename E, bool RANGE, bool FIRST>
 static void launch_kernel(const ScanArgs &a, unsigned grid, size_t smem, cudaStream_t st)
 {
@@ -309,7 +366,17 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     end_state_ = (init_state == ROOT_STATE) ? root_ : init_state;
     stats.bytes = total; stats.events = 0; stats.kernel_launches = 0; stats.kernel_ms = 0;
     stats.halo_bytes = halo_;
+    stats.filtered = 0; stats.filter_ms = 0; stats.verify_ms = 0; stats.flagged_words = 0; stats.dense_tiles = 0;
     if (total == 0) { stats.chunk_bytes = 0; return true; }
+
+    // Gram prefilter: needs an eligible dictionary and a walk that starts at the root.  Automatic mode
+    // skips it for inputs too small to amortise a second launch and after a scan whose tiles were mostly
+    // walked completely anyway.
+    if (filter_w_ && tune_filter >= 0 && !first_only && (init_state == ROOT_STATE || init_state == root_)) {
+        const bool want = tune_filter > 0 || (total >= (1u << 20) && last_dense_frac_ < 0.5);
+        if (want) return launch_filtered(d_text, total, readable, n_hay, uniform_len, stream);
+        last_dense_frac_ *= 0.5;      // re-probe the prefilter now and then
+    }
 
     const uint32_t chunk = pick_chunk(total);
     const uint32_t n_chunks = (uint32_t)(((uint64_t)total + chunk - 1) / chunk);
@@ -327,17 +394,9 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     const int dyn_max = max_smem_optin_ - 2048;
     size_t smem_budget = (size_t)dyn_max;
     if (tune_smem_bytes) smem_budget = std::min<size_t>(smem_budget, tune_smem_bytes);
+    uint32_t win_lo = 0, win_rows = 0;
+    window_for(smem_budget, &win_lo, &win_rows);
     const size_t row_bytes = (size_t)ncls_ * entry_bytes_;
-    const uint64_t rows_fit = smem_budget / row_bytes;
-    const uint64_t n_final = final_bound_ - 1, n_plain = n_rows_ - final_bound_;
-    uint64_t B = std::min<uint64_t>(n_final, rows_fit / 4);
-    uint64_t A = std::min<uint64_t>(n_plain, rows_fit - B);
-    B = std::min<uint64_t>(n_final, rows_fit - A);
-    // a window that covers only a sliver of a huge automaton cannot pay for itself
-    if (!tune_smem_bytes && A * 64 < n_plain) { A = 0; B = 0; }
-    if (A == 0) B = 0;
-    const uint32_t win_lo = final_bound_ - (uint32_t)B;
-    const uint32_t win_rows = (uint32_t)(A + B);
     const size_t smem_bytes = std::max<size_t>(16, (size_t)win_rows * row_bytes);
 
     // ac_scan_kernel_x4 (four slices per lane in lockstep) is opt-in for now: with text arriving through
@@ -382,7 +441,7 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
         a.out = (uint2 *)d_events_;
         a.capacity = (uint32_t)std::min<size_t>(events_cap_, 0xffffffffu);
         CU_OK(cudaMemsetAsync(d_tiles_, 0, (size_t)n_tiles * sizeof(unsigned long long), st));
-        CU_OK(cudaMemsetAsync(d_counters_, 0, 16, st));
+        CU_OK(cudaMemsetAsync(d_counters_, 0, 32, st));
         if (first_only) CU_OK(cudaMemsetAsync(d_first_, 0xff, n_hay * sizeof(uint32_t), st));
         CU_OK(cudaEventRecord(EV(ev_[0]), st));
         if (x4) {
@@ -417,6 +476,131 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
             return true;
         }
         // event buffer too small: grow to the exact need and scan again
+        if (!ensure_events(found + found / 16 + 1024)) return false;
+    }
+    set_error("event buffer overflow persisted after regrow");
+    return false;
+}
+
+template <int W>
+static void launch_filter_k(const FilterArgs &fa, bool l2, unsigned grid, cudaStream_t st)
+{
+    if (l2) ac_filter_kernel<W, true><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa);
+    else ac_filter_kernel<W, false><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa);
+}
+
+template <typename E, int W>
+static void launch_verify_k(const ScanArgs &a, bool range, unsigned grid, size_t smem, cudaStream_t st)
+{
+    if (range) ac_verify_kernel<E, true, W><<<grid, SCAN_THREADS, smem, st>>>(a);
+    else ac_verify_kernel<E, false, W><<<grid, SCAN_THREADS, smem, st>>>(a);
+}
+
+// ahocorasick_match() through the gram prefilter: ac_filter_kernel streams the haystack and flags
+// aligned words, ac_verify_kernel walks the automaton around the flagged words only.
+bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readable, size_t n_hay,
+                             uint32_t uniform_len, void *stream)
+{
+    cudaStream_t st = stream ? S(stream) : S(stream_);
+    const uint32_t W = filter_w_;
+    const uint32_t NB = 16 / W;
+    const uint32_t n_spans = (uint32_t)(((uint64_t)total + SPAN_BYTES - 1) / SPAN_BYTES);
+    const uint32_t n_tiles = (n_spans + 31) / 32;
+    stats.chunk_bytes = SPAN_BYTES;
+    stats.filtered = 1;
+    if (events_cap_ == 0 && !ensure_events(std::max<size_t>(1 << 16, total / 64))) return false;
+    if (!ensure_tiles(n_tiles)) return false;
+    if (!ensure_mask((size_t)n_spans * NB)) return false;
+
+    const size_t fixed = (SCAN_THREADS / 32) * (VER_LIST_CAP * sizeof(uint16_t) + VER_STAGE_CAP * sizeof(uint2));
+    const int dyn_max = max_smem_optin_ - 2048;
+    size_t smem_budget = (size_t)dyn_max - fixed;
+    if (tune_smem_bytes) smem_budget = std::min<size_t>(smem_budget, tune_smem_bytes);
+    uint32_t win_lo = 0, win_rows = 0;
+    window_for(smem_budget, &win_lo, &win_rows);
+    const size_t smem_bytes = fixed + std::max<size_t>(16, (size_t)win_rows * ncls_ * entry_bytes_);
+
+    FilterArgs fa{};
+    fa.text = (const uint8_t *)d_text;
+    fa.total = total;
+    fa.l1 = d_l1_; fa.l1_bits = l1_bits_;
+    fa.l2 = d_l2_; fa.l2_shift = l2_log2_ ? 32 - l2_log2_ : 0;
+    fa.mask = d_mask_;
+    fa.n_spans = n_spans;
+    fa.counters = d_counters_;
+
+    ScanArgs a{};
+    a.text = (const uint8_t *)d_text;
+    a.hay_off = uniform_len ? nullptr : d_off_;
+    a.n_hay = (uint32_t)n_hay;
+    a.uniform_len = uniform_len;
+    a.total = total;
+    a.readable = readable;
+    a.chunk = SPAN_BYTES;
+    a.halo = halo_;
+    a.chunk_begin = 0;
+    a.chunk_end = n_spans;
+    a.n_tiles = n_tiles;
+    a.table = d_table_;
+    a.cls_map = d_cls_;
+    a.ncls = ncls_;
+    a.final_bound = final_bound_;
+    a.root = root_;
+    a.win_lo = win_lo;
+    a.win_rows = win_rows;
+    a.range_lo = range_lo_;
+    a.n_used = n_used_;
+    a.init_state = root_;
+    a.tile_status = d_tiles_;
+    a.counters = d_counters_;
+    a.first_end = nullptr;
+    a.mask = d_mask_;
+    a.n_spans = n_spans;
+
+    const unsigned warps_per_cta = SCAN_THREADS / 32;
+    const unsigned grid_f = std::min<uint32_t>((n_spans + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
+    const unsigned grid_v = std::min<uint32_t>((n_tiles + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
+
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        a.out = (uint2 *)d_events_;
+        a.capacity = (uint32_t)std::min<size_t>(events_cap_, 0xffffffffu);
+        CU_OK(cudaMemsetAsync(d_tiles_, 0, (size_t)n_tiles * sizeof(unsigned long long), st));
+        CU_OK(cudaMemsetAsync(d_counters_, 0, 32, st));
+        CU_OK(cudaEventRecord(EV(ev_[0]), st));
+        if (attempt == 0) {          // the bit planes survive a regrow of the event buffer
+            if (W == 8) launch_filter_k<8>(fa, d_l2_ != nullptr, grid_f, st);
+            else launch_filter_k<4>(fa, d_l2_ != nullptr, grid_f, st);
+            stats.kernel_launches += 1;
+        }
+        CU_OK(cudaEventRecord(EV(ev_[4]), st));
+        if (entry_bytes_ == 2) {
+            if (W == 8) launch_verify_k<uint16_t, 8>(a, range_map_, grid_v, smem_bytes, st);
+            else launch_verify_k<uint16_t, 4>(a, range_map_, grid_v, smem_bytes, st);
+        } else {
+            if (W == 8) launch_verify_k<uint32_t, 8>(a, range_map_, grid_v, smem_bytes, st);
+            else launch_verify_k<uint32_t, 4>(a, range_map_, grid_v, smem_bytes, st);
+        }
+        CU_OK(cudaGetLastError());
+        CU_OK(cudaEventRecord(EV(ev_[1]), st));
+        stats.kernel_launches += 1;
+        CU_OK(cudaMemcpyAsync(h_counters_, d_counters_, 32, cudaMemcpyDeviceToHost, st));
+        CU_OK(cudaStreamSynchronize(st));
+        float ms_f = 0, ms_v = 0;
+        cudaEventElapsedTime(&ms_f, EV(ev_[0]), EV(ev_[4]));
+        cudaEventElapsedTime(&ms_v, EV(ev_[4]), EV(ev_[1]));
+        stats.filter_ms += ms_f; stats.verify_ms += ms_v;
+        stats.kernel_ms += ms_f + ms_v;
+        const size_t found = h_counters_[1];
+        end_state_ = h_counters_[2];
+        if (attempt == 0) stats.flagged_words = h_counters_[3];
+        stats.dense_tiles = h_counters_[4];
+        if (found <= events_cap_) {
+            n_events_ = found; stats.events = found;
+            last_density_ = (double)found / (double)total;
+            last_dense_frac_ = (double)stats.dense_tiles / (double)n_tiles;
+            stats.ilp = 1;
+            return true;
+        }
         if (!ensure_events(found + found / 16 + 1024)) return false;
     }
     set_error("event buffer overflow persisted after regrow");

@@ -48,12 +48,17 @@ public:
     uint32_t tune_chunk = 0;
     uint32_t tune_smem_bytes = 0;
     int tune_ilp = 0;              // 0 auto, 1 one slice per lane, 4 four slices per lane
+    int tune_filter = 0;           // 0 auto, 1 always use the gram prefilter when the dictionary allows, -1 never
 
 private:
     bool ensure_text(size_t bytes);
     bool ensure_events(size_t n);
     bool ensure_offsets(size_t n);
     bool ensure_tiles(size_t n);
+    bool ensure_mask(size_t words);
+    bool launch_filtered(const void *d_text, uint32_t total, uint32_t readable, size_t n_hay, uint32_t uniform_len,
+                         void *stream);
+    void window_for(size_t smem_budget, uint32_t *win_lo, uint32_t *win_rows) const;
     bool ensure_host_events(size_t n);
     bool upload_offsets(const uint64_t *offsets, size_t n, uint32_t *uniform_len);
     bool launch_scan(const void *d_text, uint32_t total, uint32_t readable, size_t n_hay, uint32_t uniform_len,
@@ -65,7 +70,7 @@ private:
     int n_sms_ = 0;
     int max_smem_optin_ = 0;
     void *stream_ = nullptr;       // cudaStream_t
-    void *ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+    void *ev_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 
     // automaton
     void *d_table_ = nullptr;
@@ -75,6 +80,12 @@ private:
     bool range_map_ = true;
     int entry_bytes_ = 2;
     uint64_t table_entries_ = 1;
+
+    // gram prefilter
+    uint32_t filter_w_ = 0, l1_bits_ = 0, l2_log2_ = 0;
+    uint32_t *d_l1_ = nullptr, *d_l2_ = nullptr;
+    uint32_t *d_mask_ = nullptr;  size_t mask_cap_ = 0;
+    double last_dense_frac_ = 0.0; // tiles the verify kernel had to walk completely, previous filtered scan
 
     // scratch
     uint8_t *d_text_ = nullptr;   size_t text_cap_ = 0;

@@ -1,0 +1,44 @@
+// filter_hash.hpp — hash functions of the gram prefilter, shared by the host
+// (bitmap construction at finalize) and the device (filter kernel).
+//
+// A "gram" is an aligned W-byte word of the haystack stream (W = 8 or 4), read
+// little-endian as (lo, hi) 32-bit halves (hi = 0 for W = 4).
+#pragma once
+
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define ACB_HD __host__ __device__ __forceinline__
+#else
+#define ACB_HD inline
+#endif
+
+namespace acb200 {
+
+constexpr uint32_t FILTER_L1_BYTES = 220u * 1024u;          // level-1 bitmap, lives in shared memory
+constexpr uint32_t FILTER_L1_BITS = FILTER_L1_BYTES * 8u;
+
+// level 1: bit index in [0, n_bits) — multiplicative hash, range-reduced with a high multiply
+ACB_HD uint32_t filter_mix1(uint32_t lo, uint32_t hi)
+{
+    return lo * 0x9E3779B1u + hi * 0x85EBCA77u;
+}
+
+ACB_HD uint32_t filter_reduce(uint32_t t, uint32_t n_bits)
+{
+#if defined(__CUDA_ARCH__)
+    return __umulhi(t, n_bits);
+#else
+    return (uint32_t)(((uint64_t)t * n_bits) >> 32);
+#endif
+}
+
+// level 2: independent hash, top `log2_bits` bits index a 2^log2_bits-bit map in global memory
+ACB_HD uint32_t filter_mix2(uint32_t lo, uint32_t hi)
+{
+    uint32_t t = lo * 0xC2B2AE3Du + hi * 0x27D4EB2Fu;
+    t ^= t >> 15;
+    return t * 0x2C1B3C6Du;
+}
+
+} // namespace acb200

@@ -225,34 +225,7 @@ __global__ void __launch_bounds__(X4_THREADS, 1) ac_scan_kernel_x4(const ScanArg
             total += __shfl_sync(0xffffffffu, incl, 31);
         }
 
-        unsigned long long excl = prior;
-        if (tile == 0) {
-            if (lane == 0) st_status(a.tile_status, ST_PREFIX | (excl + total));
-        } else {
-            if (lane == 0) st_status(a.tile_status + tile, ST_AGG | total);
-            long long j = (long long)tile - 1 - lane;
-            unsigned long long sum = 0;
-            while (true) {
-                unsigned long long v = ST_PREFIX;
-                const bool virt = j < 0;
-                if (!virt) {
-                    do { v = ld_status(a.tile_status + j); } while ((v >> 62) == 0);
-                }
-                const bool is_prefix = (v >> 62) == 2;
-                const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
-                const int first_p = pm ? (__ffs(pm) - 1) : 32;
-                unsigned long long contrib = ((int)lane <= first_p) ? (v & ST_MASK) : 0ull;
-                if (virt && (int)lane == first_p) contrib = prior;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
-                sum += contrib;
-                if (pm) break;
-                j -= 32;
-            }
-            excl = sum;
-            if (lane == 0) st_status(a.tile_status + tile, ST_PREFIX | (excl + total));
-        }
-        if (lane == 0 && tile == a.n_tiles - 1) a.counters[1] = (uint32_t)(excl + total);
+        const unsigned long long excl = tile_lookback(a, tile, total, prior, lane);
 
 #pragma unroll
         for (int q = 0; q < X4; ++q) {

@@ -57,7 +57,10 @@ struct ScanArgs {
     uint32_t capacity;            // events that fit in `out`
     unsigned long long *tile_status;  // n_tiles words, zeroed before launch
     uint32_t *counters;           // [0] ticket (zeroed per launch) [1] running event total [2] end state
+                                  // [3] words flagged by the filter [4] tiles the verify kernel walked completely
     uint32_t *first_end;          // FIRST kernels: per haystack earliest event end seen (init 0xffffffff)
+    const uint32_t *mask;         // ac_verify_kernel: flagged-word bit planes written by ac_filter_kernel
+    uint32_t n_spans;             // ac_verify_kernel: 512-byte spans in the stream
 };
 
 // ------------------------------------------------------------ finalize ----
@@ -117,6 +120,45 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
 constexpr unsigned long long ST_AGG = 1ull << 62;     // tile total published
 constexpr unsigned long long ST_PREFIX = 2ull << 62;  // inclusive prefix published
 constexpr unsigned long long ST_MASK = (1ull << 62) - 1;
+
+// Decoupled look-back over earlier tiles, 32 predecessors per step: publishes this
+// tile's event total, returns the number of events of all earlier tiles (plus
+// `prior`, the events of earlier launches of the same call) and publishes the
+// inclusive prefix.  The last tile also stores the grand total in counters[1].
+// Must be called by all 32 lanes of the warp that owns `tile`.
+__device__ __forceinline__ unsigned long long tile_lookback(const ScanArgs &a, uint32_t tile, uint32_t total,
+                                                            uint32_t prior, uint32_t lane)
+{
+    unsigned long long excl = prior;
+    if (tile == 0) {
+        if (lane == 0) st_status(a.tile_status, ST_PREFIX | (excl + total));
+    } else {
+        if (lane == 0) st_status(a.tile_status + tile, ST_AGG | total);
+        long long j = (long long)tile - 1 - lane;
+        unsigned long long sum = 0;
+        while (true) {
+            unsigned long long v = ST_PREFIX;         // before tile 0: the events of earlier launches
+            const bool virt = j < 0;
+            if (!virt) {
+                do { v = ld_status(a.tile_status + j); } while ((v >> 62) == 0);
+            }
+            const bool is_prefix = (v >> 62) == 2;
+            const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
+            const int first_p = pm ? (__ffs(pm) - 1) : 32;
+            unsigned long long contrib = ((int)lane <= first_p) ? (v & ST_MASK) : 0ull;
+            if (virt && (int)lane == first_p) contrib = prior;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+            sum += contrib;
+            if (pm) break;
+            j -= 32;
+        }
+        excl = sum;
+        if (lane == 0) st_status(a.tile_status + tile, ST_PREFIX | (excl + total));
+    }
+    if (lane == 0 && tile == a.n_tiles - 1) a.counters[1] = (uint32_t)(excl + total);
+    return excl;
+}
 
 // Shared-memory loads by 32-bit shared-window address (keeps the address math to one IMAD).
 template <typename E> __device__ __forceinline__ uint32_t lds_entry(uint32_t addr);
@@ -409,35 +451,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_kernel(const ScanArgs
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
 
-        // decoupled look-back over earlier tiles, 32 predecessors per step
-        unsigned long long excl = prior;
-        if (tile == 0) {
-            if (lane == 0) st_status(a.tile_status, ST_PREFIX | (excl + total));
-        } else {
-            if (lane == 0) st_status(a.tile_status + tile, ST_AGG | total);
-            long long j = (long long)tile - 1 - lane;
-            unsigned long long sum = 0;
-            while (true) {
-                unsigned long long v = ST_PREFIX;         // before tile 0: the events of earlier launches
-                const bool virt = j < 0;
-                if (!virt) {
-                    do { v = ld_status(a.tile_status + j); } while ((v >> 62) == 0);
-                }
-                const bool is_prefix = (v >> 62) == 2;
-                const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
-                const int first_p = pm ? (__ffs(pm) - 1) : 32;
-                unsigned long long contrib = ((int)lane <= first_p) ? (v & ST_MASK) : 0ull;
-                if (virt && (int)lane == first_p) contrib = prior;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
-                sum += contrib;
-                if (pm) break;
-                j -= 32;
-            }
-            excl = sum;
-            if (lane == 0) st_status(a.tile_status + tile, ST_PREFIX | (excl + total));
-        }
-        if (lane == 0 && tile == a.n_tiles - 1) a.counters[1] = (uint32_t)(excl + total);
+        const unsigned long long excl = tile_lookback(a, tile, total, prior, lane);
 
         if (sc.cnt) {
             const uint32_t off = (uint32_t)excl + (incl - sc.cnt);

@@ -51,13 +51,16 @@ class Info(C.Structure):
     _fields_ = [("n_patterns", C.c_uint64), ("n_states", C.c_uint64), ("n_classes", C.c_uint32),
                 ("entry_bytes", C.c_uint32), ("max_pattern_len", C.c_uint32), ("final_bound", C.c_uint32),
                 ("root", C.c_uint32), ("table_bytes", C.c_uint64), ("device", C.c_int32),
-                ("finalized", C.c_int32), ("reserved_", C.c_int32)]
+                ("finalized", C.c_int32), ("filter_word", C.c_int32), ("min_pattern_len", C.c_uint32),
+                ("filter_l1_fill", C.c_float), ("filter_l2_log2", C.c_uint32), ("reserved_", C.c_uint32)]
 
 
 class Stats(C.Structure):
     _fields_ = [("bytes", C.c_uint64), ("events", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("chunk_bytes", C.c_uint32), ("halo_bytes", C.c_uint32), ("kernel_ms", C.c_float),
-                ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("ilp", C.c_uint32), ("reserved_", C.c_uint32)]
+                ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("ilp", C.c_uint32), ("filtered", C.c_uint32),
+                ("filter_ms", C.c_float), ("verify_ms", C.c_float), ("flagged_words", C.c_uint64),
+                ("dense_tiles", C.c_uint64)]
 
 
 MATCH_CB = C.CFUNCTYPE(C.c_int, C.POINTER(AcMatch), C.c_void_p)
@@ -70,6 +73,7 @@ EXPORTS = [
     "acb200_state_patterns", "acb200_info", "acb200_last_stats", "acb200_last_error",
     "acb200_set_device", "acb200_device_count", "acb200_host_alloc", "acb200_host_free",
     "acb200_set_tuning", "acb200_version", "acb200_copy_events", "acb200_tally_cb", "acb200_tally_match_cb", "acb200_set_ilp",
+    "acb200_set_filter",
 ]
 
 
@@ -114,6 +118,7 @@ def lib() -> C.CDLL:
     L.acb200_set_tuning.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
     L.acb200_version.restype = C.c_char_p
     L.acb200_set_ilp.argtypes = [C.c_void_p, C.c_int]
+    L.acb200_set_filter.argtypes = [C.c_void_p, C.c_int]
     L.acb200_copy_events.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.acb200_copy_events.restype = C.c_long
     _lib = L
@@ -182,6 +187,10 @@ class Automaton:
         self.L.acb200_set_tuning(self.h, int(chunk_bytes), int(smem_table_bytes))
         if ilp is not None:
             self.L.acb200_set_ilp(self.h, int(ilp))
+
+    def set_filter(self, mode: int) -> None:
+        """0 automatic, 1 prefilter whenever the dictionary allows, -1 always the full automaton walk"""
+        self.L.acb200_set_filter(self.h, int(mode))
 
     # -- search -----------------------------------------------------------
     def search_events(self, flat, offsets=None, first_only: bool = False) -> np.ndarray:

@@ -1,0 +1,175 @@
+"""GPU parity of the gram-prefilter path (ac_filter_kernel + ac_verify_kernel) against the CPU oracle and
+against the full automaton walk (ac_scan_kernel): same events, same order, through the C-ABI."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle.pydriver import Driver
+from php_aho_corasick_b200 import workloads as W
+from php_aho_corasick_b200.native import Automaton
+from tests.helpers import assert_same, oracle_hits, split
+
+pytestmark = pytest.mark.gpu
+
+
+def build(pattern_calls, filter_mode):
+    a = Automaton()
+    for call in pattern_calls:
+        a.add_php_order(call)
+    a.finalize()
+    a.set_filter(filter_mode)
+    return a
+
+
+def rand_bytes(rng, n, alphabet):
+    lut = np.frombuffer(alphabet, dtype=np.uint8)
+    return lut[rng.integers(0, len(alphabet), size=n)]
+
+
+def test_cfg2_planted_filtered_equals_oracle_and_full_walk():
+    needles, hay, off = W.cfg2()
+    exp = oracle_hits([needles], split(hay, off))
+    a = build([needles], 1)
+    inf = a.info()
+    assert inf.filter_word == 8 and inf.min_pattern_len == 16 and inf.filter_l2_log2 == 0
+    ev = a.search_events(hay, off)
+    st = a.stats()
+    assert st.filtered == 1 and st.kernel_launches == 2 and 0 < st.flagged_words < hay.size // 8 // 10
+    assert_same(a, ev, 256, exp)
+    a.set_filter(-1)
+    ev_full = a.search_events(hay, off)
+    assert a.stats().filtered == 0
+    assert np.array_equal(ev, ev_full)
+    # the same bytes as ONE haystack: matches may straddle the former boundaries
+    one = np.array([0, hay.size], dtype=np.uint64)
+    a.set_filter(1)
+    ev1 = a.search_events(hay, one)
+    assert_same(a, ev1, 1, oracle_hits([needles], [hay]))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_dictionaries_both_word_sizes_ragged_batches(seed):
+    rng = np.random.default_rng(100 + seed)
+    pyr = random.Random(seed)
+    for trial in range(6):
+        alphabet = pyr.choice([b"ab", b"abc", b"abcdef", bytes(range(256)), b"\x00\xff\x80a"])
+        min_len = pyr.choice([8, 9, 15, 16, 17, 24])
+        max_len = min_len + pyr.choice([0, 3, 20, 60])
+        n_pat = pyr.choice([1, 3, 40, 400])
+        pats = [rand_bytes(rng, pyr.randint(min_len, max_len), alphabet).tobytes() for _ in range(n_pat)]
+        lens = [pyr.choice([0, 1, 7, 8, 15, 16, 17, 100, 511, 512, 513, 4095, 20000, 70001]) for _ in range(pyr.randint(1, 12))]
+        hays = [rand_bytes(rng, n, alphabet) for n in lens]
+        # plant patterns (and pattern prefixes / suffixes) so that there is something to find
+        for h in hays:
+            for _ in range(max(1, h.size // 700)):
+                p = np.frombuffer(pyr.choice(pats), dtype=np.uint8)
+                if h.size >= p.size:
+                    at = pyr.randint(0, h.size - p.size)
+                    h[at:at + p.size] = p
+        if hays and hays[-1].size >= 64:
+            p = np.frombuffer(pats[0], dtype=np.uint8)
+            hays[-1][-p.size:] = p                      # a match that ends on the very last byte
+            hays[-1][:p.size] = p                       # and one at offset 0
+        flat = np.concatenate(hays) if hays else np.zeros(0, np.uint8)
+        off = np.zeros(len(lens) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(lens)
+        exp = oracle_hits([pats], hays)
+        a = build([pats], 1)
+        assert a.info().filter_word == (8 if min(len(p) for p in pats) >= 16 else 4)
+        ev = a.search_events(flat, off)
+        assert a.stats().filtered == (1 if flat.size else 0)
+        assert_same(a, ev, len(lens), exp)
+        a.set_filter(-1)
+        assert np.array_equal(ev, a.search_events(flat, off)), (seed, trial)
+        a.release()
+
+
+def test_every_word_flagged_falls_back_to_whole_tile_walks():
+    # nested patterns over one repeated byte: every aligned word is a pattern word, every offset an event
+    pats = [b"a" * n for n in range(16, 41)]
+    hay = np.full(300_000, ord("a"), dtype=np.uint8)
+    hay[100_000:100_050] = ord("b")
+    a = build([pats], 1)
+    ev = a.search_events(hay)
+    st = a.stats()
+    assert st.filtered == 1 and st.dense_tiles > 0
+    assert_same(a, ev, 1, oracle_hits([pats], [hay]))
+
+
+def test_event_burst_overflows_the_staging_buffer_and_is_still_ordered():
+    # few flagged words per 16 KiB tile, but each yields a run of events
+    rng = np.random.default_rng(9)
+    pats = [b"a" * 16, b"a" * 17, rand_bytes(rng, 16, b"bcdef").tobytes()]
+    hay = rand_bytes(rng, 1 << 18, b"bcdef")
+    for at in range(5000, hay.size - 400, 16384):
+        hay[at:at + 230] = ord("a")
+    a = build([pats], 1)
+    ev = a.search_events(hay)
+    st = a.stats()
+    assert st.filtered == 1 and st.dense_tiles > 0
+    assert len(ev) > 16 * 200
+    assert_same(a, ev, 1, oracle_hits([pats], [hay]))
+
+
+def test_cfg3_signature_shape_reduced_filtered_with_second_level():
+    pats, hay, off = W.cfg3(n_patterns=20_000, hay_bytes=8 << 20, plant_every=1 << 16)
+    a = build([pats], 1)
+    inf = a.info()
+    assert inf.filter_word == 4 and inf.filter_l2_log2 > 0 and inf.min_pattern_len == 8
+    ev = a.search_events(hay, off)
+    st = a.stats()
+    assert st.filtered == 1
+    exp = oracle_hits([pats], [hay])
+    assert exp[0][2] >= 100
+    assert_same(a, ev, 1, exp)
+    # the second level keeps the flagged share far below the first level's fill
+    assert st.flagged_words < (hay.size // 4) * 0.02
+
+
+def test_keep_continuation_after_a_filtered_first_chunk():
+    needles, hay, _ = W.cfg2(n_hay=1, hay_len=40_000, n_needles=200, planted_per_hay=8, seed=21)
+    cuts = [0, 30_000, 30_007, 30_008, 39_000, 40_000]
+    hay[29_990:30_006] = np.frombuffer(needles[5], dtype=np.uint8)      # straddles the first cut
+    res = {}
+    for kind in ("oracle", "gpu"):
+        d = Driver(kind)
+        d.add_php_order(needles)
+        d.finalize()
+        pos, pat = [], []
+        for i in range(len(cuts) - 1):
+            r = d.search(hay[cuts[i]:cuts[i + 1]], keep=(i > 0))
+            pos += r["pos"].tolist()
+            pat += r["pat"].tolist()
+        res[kind] = (pos, pat)
+        d.release()
+    assert res["gpu"] == res["oracle"] and len(res["gpu"][0]) >= 8
+    # and with the prefilter forced on the first chunk through the native binding
+    a = build([needles], 1)
+    rc, got0 = a.search_callback(hay[:30_000].tobytes())
+    assert a.stats().filtered == 1
+    rc, got1 = a.search_callback(hay[30_000:].tobytes(), keep=True)
+    assert a.stats().filtered == 0                     # a continuation does not start at the root
+    pos = [p for p, _ in got0] + [p for p, _ in got1]
+    assert pos == res["oracle"][0]
+
+
+def test_device_resident_stream_with_odd_length_is_not_read_past_its_end():
+    torch = pytest.importorskip("torch")
+    needles, hay, _ = W.cfg2(n_hay=1, hay_len=(1 << 20) + 13, n_needles=500, planted_per_hay=64, seed=5)
+    p = np.frombuffer(needles[3], dtype=np.uint8)
+    hay[-16:] = p
+    a = build([needles], 1)
+    t = torch.from_numpy(hay).cuda()
+    off = np.array([0, hay.size], dtype=np.uint64)
+    ptr, n = a.search_device(t.data_ptr(), off)
+    assert a.stats().filtered == 1
+    buf = torch.empty((n, 2), dtype=torch.int32, device="cuda")
+    a.copy_events(buf.data_ptr(), n)
+    torch.cuda.synchronize()
+    got = buf.cpu().numpy().view(np.uint32)
+    exp = oracle_hits([needles], [hay])[0]
+    assert n == exp[2]
+    assert int(got[-1, 0]) == hay.size
+    ev = a.search_events(hay, off)
+    assert np.array_equal(got[:, 0].astype(np.uint64), ev["end"]) and np.array_equal(got[:, 1], ev["state"])
