@@ -247,7 +247,9 @@ typedef struct acb200_stats
     float filter_ms;          /* device time of the prefilter kernel (0 if unused) */
     float verify_ms;          /* device time of the verify kernel (0 if unused) */
     uint64_t flagged_words;   /* aligned words the prefilter handed to verification */
-    uint64_t dense_tiles;     /* 16 KiB tiles the verify kernel walked completely */
+    uint64_t dense_tiles;     /* 16 KiB tiles handed to verification as whole spans */
+    float reorder_ms;         /* device time of the run reorder kernel (0 if unused) */
+    uint32_t reserved_;
 } ACB200_STATS_t;
 int acb200_last_stats(const AC_TRIE_t *thiz, ACB200_STATS_t *out);
 

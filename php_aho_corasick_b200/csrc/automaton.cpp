@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 namespace acb200 {
 
@@ -296,13 +297,19 @@ void HostTrie::build_filter(FlatAutomaton &flat) const {
             gram(p, r, lo, hi);
             const uint32_t i = filter_reduce(filter_mix1(lo, hi), flat.l1_bits);
             flat.l1[i >> 5] |= 1u << (i & 31);
+            const uint32_t i2 = filter_reduce(filter_mix2(lo, hi), flat.l1_bits);
+            flat.l1[i2 >> 5] |= 1u << (i2 & 31);
         }
     flat.n_grams = (uint64_t)patterns_.size() * W;
     uint64_t set = 0;
     for (uint32_t w : flat.l1) set += (uint64_t)__builtin_popcount(w);
     flat.l1_fill = (double)set / (double)flat.l1_bits;
 
-    if (flat.l1_fill > 0.04) {
+    // Level 1 is probed twice (two hashes, one bitmap): a random word passes with probability fill^2.
+    // Level 2 (global memory) is only worth its latency when that is still not selective.
+    double l2_min_fill = 0.15;
+    if (const char *e = getenv("ACB200_L2_MIN_FILL")) l2_min_fill = atof(e);
+    if (flat.l1_fill > l2_min_fill) {
         uint32_t lg = 23;                                   // at least 1 MiB: ~256 bits per gram, capped at 128 MiB
         while (lg < 30 && (1ull << lg) < flat.n_grams * 256) ++lg;
         flat.l2_log2 = lg;
@@ -311,7 +318,7 @@ void HostTrie::build_filter(FlatAutomaton &flat) const {
             for (uint32_t r = 1; r <= W; ++r) {
                 uint32_t lo, hi;
                 gram(p, r, lo, hi);
-                const uint32_t i = filter_mix2(lo, hi) >> (32 - lg);
+                const uint32_t i = filter_mix3(lo, hi) >> (32 - lg);
                 flat.l2[i >> 5] |= 1u << (i & 31);
             }
     }

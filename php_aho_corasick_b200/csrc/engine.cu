@@ -58,8 +58,9 @@ void Engine::release()
     if (stream_) cudaStreamSynchronize(S(stream_));
     cudaFree(d_table_); cudaFree(d_cls_); cudaFree(d_text_); cudaFree(d_off_);
     cudaFree(d_first_); cudaFree(d_events_); cudaFree(d_tiles_); cudaFree(d_counters_);
-    cudaFree(d_l1_); cudaFree(d_l2_); cudaFree(d_mask_);
-    d_l1_ = nullptr; d_l2_ = nullptr; d_mask_ = nullptr; mask_cap_ = 0;
+    cudaFree(d_l1_); cudaFree(d_l2_); cudaFree(d_mask_); cudaFree(d_runs_); cudaFree(d_events_tmp_);
+    d_l1_ = nullptr; d_l2_ = nullptr; d_mask_ = nullptr; mask_cap_ = 0; d_runs_ = nullptr; runs_cap_ = 0;
+    d_events_tmp_ = nullptr; events_tmp_cap_ = 0;
     if (h_counters_) cudaFreeHost(h_counters_);
     if (h_events_) cudaFreeHost(h_events_);
     if (h_stage_) cudaFreeHost(h_stage_);
@@ -290,6 +291,25 @@ bool Engine::ensure_mask(size_t words)
     return true;
 }
 
+bool Engine::ensure_runs(size_t n)
+{
+    if (n <= runs_cap_) return true;
+    cudaFree(d_runs_); d_runs_ = nullptr; runs_cap_ = 0;
+    const size_t cap = std::max(n + n / 4, (size_t)256);
+    CU_OK(cudaMalloc(&d_runs_, cap * 2 * sizeof(uint32_t)));
+    runs_cap_ = cap;
+    return true;
+}
+
+bool Engine::ensure_events_tmp(size_t n)
+{
+    if (n <= events_tmp_cap_) return true;
+    cudaFree(d_events_tmp_); d_events_tmp_ = nullptr; events_tmp_cap_ = 0;
+    CU_OK(cudaMalloc(&d_events_tmp_, n * sizeof(PackedEvent)));
+    events_tmp_cap_ = n;
+    return true;
+}
+
 bool Engine::ensure_tiles(size_t n)
 {
     if (n <= tiles_cap_) return true;
@@ -367,6 +387,7 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     stats.bytes = total; stats.events = 0; stats.kernel_launches = 0; stats.kernel_ms = 0;
     stats.halo_bytes = halo_;
     stats.filtered = 0; stats.filter_ms = 0; stats.verify_ms = 0; stats.flagged_words = 0; stats.dense_tiles = 0;
+    stats.reorder_ms = 0; stats.reserved_ = 0;
     if (total == 0) { stats.chunk_bytes = 0; return true; }
 
     // Gram prefilter: needs an eligible dictionary and a walk that starts at the root.  Automatic mode
@@ -505,20 +526,24 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     const uint32_t W = filter_w_;
     const uint32_t NB = 16 / W;
     const uint32_t n_spans = (uint32_t)(((uint64_t)total + SPAN_BYTES - 1) / SPAN_BYTES);
-    const uint32_t n_tiles = (n_spans + 31) / 32;
+    const uint32_t n_tiles = (n_spans + 31) / 32;      // 16 KiB tiles (statistics only)
     stats.chunk_bytes = SPAN_BYTES;
     stats.filtered = 1;
     if (events_cap_ == 0 && !ensure_events(std::max<size_t>(1 << 16, total / 64))) return false;
-    if (!ensure_tiles(n_tiles)) return false;
     if (!ensure_mask((size_t)n_spans * NB)) return false;
 
-    const size_t fixed = (SCAN_THREADS / 32) * (VER_LIST_CAP * sizeof(uint16_t) + VER_STAGE_CAP * sizeof(uint2));
+    const uint32_t warm = (halo_ + W - 1) / W * W;
+    // walking a whole tile costs ~(512 + halo) steps per lane, a flagged word (warm + W) steps on one lane
+    const uint32_t dense_max = std::max<uint32_t>(32u, std::min<uint32_t>(VER_DENSE_MAX, 32u * (SPAN_BYTES + halo_) / (warm + W)));
+    const uint32_t n_chunks = (n_spans + CHUNK_SPANS - 1) / CHUNK_SPANS;
+    if (!ensure_runs(n_chunks)) return false;
+
     const int dyn_max = max_smem_optin_ - 2048;
-    size_t smem_budget = (size_t)dyn_max - fixed;
+    size_t smem_budget = (size_t)dyn_max - VER_FIXED_SMEM;
     if (tune_smem_bytes) smem_budget = std::min<size_t>(smem_budget, tune_smem_bytes);
     uint32_t win_lo = 0, win_rows = 0;
     window_for(smem_budget, &win_lo, &win_rows);
-    const size_t smem_bytes = fixed + std::max<size_t>(16, (size_t)win_rows * ncls_ * entry_bytes_);
+    const size_t smem_bytes = VER_FIXED_SMEM + std::max<size_t>(16, (size_t)win_rows * ncls_ * entry_bytes_);
 
     FilterArgs fa{};
     fa.text = (const uint8_t *)d_text;
@@ -551,20 +576,24 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     a.range_lo = range_lo_;
     a.n_used = n_used_;
     a.init_state = root_;
-    a.tile_status = d_tiles_;
+    a.tile_status = nullptr;
     a.counters = d_counters_;
     a.first_end = nullptr;
     a.mask = d_mask_;
     a.n_spans = n_spans;
+    a.dense_max = dense_max;
+    a.runs = (uint2 *)d_runs_;
+    a.warm = warm;
+    a.want_end_state = (n_hay == 1) ? 1u : 0u;
 
     const unsigned warps_per_cta = SCAN_THREADS / 32;
     const unsigned grid_f = std::min<uint32_t>((n_spans + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
-    const unsigned grid_v = std::min<uint32_t>((n_tiles + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
+    const unsigned grid_v = std::min<uint32_t>(n_chunks, (uint32_t)n_sms_);
 
     for (int attempt = 0; attempt < 2; ++attempt) {
-        a.out = (uint2 *)d_events_;
+        if (!ensure_events_tmp(events_cap_)) return false;
+        a.out = (uint2 *)d_events_tmp_;        // runs in completion order; ac_reorder_kernel writes d_events_
         a.capacity = (uint32_t)std::min<size_t>(events_cap_, 0xffffffffu);
-        CU_OK(cudaMemsetAsync(d_tiles_, 0, (size_t)n_tiles * sizeof(unsigned long long), st));
         CU_OK(cudaMemsetAsync(d_counters_, 0, 32, st));
         CU_OK(cudaEventRecord(EV(ev_[0]), st));
         if (attempt == 0) {          // the bit planes survive a regrow of the event buffer
@@ -580,16 +609,20 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
             if (W == 8) launch_verify_k<uint32_t, 8>(a, range_map_, grid_v, smem_bytes, st);
             else launch_verify_k<uint32_t, 4>(a, range_map_, grid_v, smem_bytes, st);
         }
+        CU_OK(cudaEventRecord(EV(ev_[5]), st));
+        ac_reorder_kernel<<<n_chunks, REORDER_THREADS, 0, st>>>((const uint2 *)d_runs_, (const uint2 *)d_events_tmp_,
+                                                                (uint2 *)d_events_, a.capacity);
         CU_OK(cudaGetLastError());
         CU_OK(cudaEventRecord(EV(ev_[1]), st));
-        stats.kernel_launches += 1;
+        stats.kernel_launches += 2;
         CU_OK(cudaMemcpyAsync(h_counters_, d_counters_, 32, cudaMemcpyDeviceToHost, st));
         CU_OK(cudaStreamSynchronize(st));
-        float ms_f = 0, ms_v = 0;
+        float ms_f = 0, ms_v = 0, ms_r = 0;
         cudaEventElapsedTime(&ms_f, EV(ev_[0]), EV(ev_[4]));
-        cudaEventElapsedTime(&ms_v, EV(ev_[4]), EV(ev_[1]));
-        stats.filter_ms += ms_f; stats.verify_ms += ms_v;
-        stats.kernel_ms += ms_f + ms_v;
+        cudaEventElapsedTime(&ms_v, EV(ev_[4]), EV(ev_[5]));
+        cudaEventElapsedTime(&ms_r, EV(ev_[5]), EV(ev_[1]));
+        stats.filter_ms += ms_f; stats.verify_ms += ms_v; stats.reorder_ms += ms_r;
+        stats.kernel_ms += ms_f + ms_v + ms_r;
         const size_t found = h_counters_[1];
         end_state_ = h_counters_[2];
         if (attempt == 0) stats.flagged_words = h_counters_[3];

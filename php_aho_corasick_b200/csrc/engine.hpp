@@ -56,6 +56,8 @@ private:
     bool ensure_offsets(size_t n);
     bool ensure_tiles(size_t n);
     bool ensure_mask(size_t words);
+    bool ensure_runs(size_t n);
+    bool ensure_events_tmp(size_t n);
     bool launch_filtered(const void *d_text, uint32_t total, uint32_t readable, size_t n_hay, uint32_t uniform_len,
                          void *stream);
     void window_for(size_t smem_budget, uint32_t *win_lo, uint32_t *win_rows) const;
@@ -70,7 +72,7 @@ private:
     int n_sms_ = 0;
     int max_smem_optin_ = 0;
     void *stream_ = nullptr;       // cudaStream_t
-    void *ev_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *ev_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     // automaton
     void *d_table_ = nullptr;
@@ -85,6 +87,8 @@ private:
     uint32_t filter_w_ = 0, l1_bits_ = 0, l2_log2_ = 0;
     uint32_t *d_l1_ = nullptr, *d_l2_ = nullptr;
     uint32_t *d_mask_ = nullptr;  size_t mask_cap_ = 0;
+    uint32_t *d_runs_ = nullptr;  size_t runs_cap_ = 0;      // per chunk {offset, count} of its run of events
+    void *d_events_tmp_ = nullptr; size_t events_tmp_cap_ = 0;  // runs in completion order
     double last_dense_frac_ = 0.0; // tiles the verify kernel had to walk completely, previous filtered scan
 
     // scratch

@@ -33,12 +33,20 @@ ACB_HD uint32_t filter_reduce(uint32_t t, uint32_t n_bits)
 #endif
 }
 
-// level 2: independent hash, top `log2_bits` bits index a 2^log2_bits-bit map in global memory
+// level 1, second probe (same bitmap, independent hash; only evaluated when the first probe hits)
 ACB_HD uint32_t filter_mix2(uint32_t lo, uint32_t hi)
 {
     uint32_t t = lo * 0xC2B2AE3Du + hi * 0x27D4EB2Fu;
     t ^= t >> 15;
     return t * 0x2C1B3C6Du;
+}
+
+// level 2: third independent hash, top `log2_bits` bits index a 2^log2_bits-bit map in global memory
+ACB_HD uint32_t filter_mix3(uint32_t lo, uint32_t hi)
+{
+    uint32_t t = (lo ^ 0x5bd1e995u) * 0x165667B1u + (hi ^ 0x7feb352du) * 0xD3A2646Du;
+    t ^= t >> 16;
+    return t * 0x846CA68Bu;
 }
 
 } // namespace acb200

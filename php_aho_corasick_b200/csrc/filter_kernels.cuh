@@ -13,15 +13,24 @@
 //                     see FlatAutomaton) and writes one bit per word: "the W
 //                     end offsets after this word need a look".  No false
 //                     negatives by construction.
-//   ac_verify_kernel  reads the bit planes; for every flagged word it walks the
-//                     automaton from the root over the (Lmax-1)-byte warm-up
-//                     plus the W bytes after the word — exactly the halo
-//                     argument of ac_scan_kernel, so the states and events are
-//                     those of an uninterrupted walk — and emits the events in
-//                     ascending order through the same decoupled look-back.
-//                     A 16 KiB tile with too many flagged words is walked
-//                     completely, lane per 512-byte span, like ac_scan_kernel:
-//                     the worst case costs what the plain scan costs.
+//   ac_verify_kernel  a CTA takes a 512 KiB chunk of the stream at a time.  Its
+//                     warps turn the chunk's bit planes into a dense, ordered
+//                     list of work items in shared memory (ballot / popc /
+//                     prefix sums): one item per flagged word, or — for a
+//                     16 KiB tile with so many flagged words that walking all
+//                     of it is cheaper — one item per 512-byte span of the
+//                     tile.  Then one lane per item: for a flagged word the
+//                     lane walks the automaton from the root over the
+//                     (Lmax-1)-byte warm-up plus the W bytes after the word —
+//                     exactly the halo argument of ac_scan_kernel, so states
+//                     and events are those of an uninterrupted walk; a span
+//                     item is walked like an ac_scan_kernel slice.  The
+//                     chunk's events are written as one ordered run at an
+//                     offset taken from a global counter (no CTA ever waits
+//                     for another one).
+//   ac_reorder_kernel copies the runs into chunk order: the final event list
+//                     is ascending, as the callback contract requires.  The
+//                     worst case costs what the plain scan costs.
 //
 // Replaces the same reference loop as ac_scan_kernel
 // (src/multifast/ahocorasick.c:199-234); events are bit-identical.
@@ -34,8 +43,14 @@ namespace acb200 {
 
 constexpr uint32_t SPAN_BYTES = 512;       // one warp-wide 16-byte load; one verify lane
 constexpr int FILTER_UNROLL = 4;           // 16-byte loads in flight per thread
-constexpr int VER_LIST_CAP = 256;          // flagged words per tile the sparse path takes
-constexpr int VER_STAGE_CAP = 64;          // events per tile staged in shared memory
+constexpr uint32_t VER_DENSE_MAX = 128;    // flagged words per 16 KiB tile beyond which the whole tile is walked
+constexpr uint32_t ITEM_SPAN = 0x80000000u;// work item: walk 512-byte span (item & ~ITEM_SPAN) completely
+constexpr uint32_t ITEM_NONE = 0xffffffffu;
+constexpr uint32_t CHUNK_SPANS = 32u * (SCAN_THREADS / 32);   // spans per CTA chunk: one 32-span tile per warp (512 KiB)
+constexpr int VER_ROUNDS = VER_DENSE_MAX / 32;                // batches of 32 items a warp may get per chunk
+constexpr uint32_t VER_LIST_CAP = (SCAN_THREADS / 32) * VER_DENSE_MAX;   // items per chunk
+constexpr uint32_t VER_FIXED_SMEM = VER_LIST_CAP * 4u + 2048u;           // item list + scan scratch
+constexpr int REORDER_THREADS = 256;
 
 struct FilterArgs {
     const uint8_t *text;          // 16-byte aligned
@@ -99,11 +114,17 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const Filter
                 uint32_t word;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(s_base + ((idx >> 5) << 2)));
                 bool p = (word >> (idx & 31u)) & 1u;
-                if (L2) {
+                {   // second probe of the same bitmap, only where the first one hit
+                    const uint32_t idx2 = filter_reduce(filter_mix2(lo, hi), a.l1_bits);
                     uint32_t word2 = 0;
-                    const uint32_t i2 = filter_mix2(lo, hi) >> a.l2_shift;
-                    if (p) word2 = __ldg(a.l2 + (i2 >> 5));
-                    p = (word2 >> (i2 & 31u)) & 1u;
+                    if (p) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word2) : "r"(s_base + ((idx2 >> 5) << 2)));
+                    p = (word2 >> (idx2 & 31u)) & 1u;
+                }
+                if (L2) {
+                    uint32_t word3 = 0;
+                    const uint32_t i3 = filter_mix3(lo, hi) >> a.l2_shift;
+                    if (p) word3 = __ldg(a.l2 + (i3 >> 5));
+                    p = (word3 >> (i3 & 31u)) & 1u;
                 }
                 // the partial chunk at the very end is not read: its words are simply handed on
                 p = (c < n16) ? p : (c == tail_chunk);
@@ -133,51 +154,92 @@ __device__ __forceinline__ uint32_t dfa_step(const SC &sc, uint32_t s, uint32_t 
     return sc.any_next(s, b);
 }
 
-__device__ __forceinline__ uint4 ld_text16_guarded(const ScanArgs &a, uint32_t i)
+// W aligned bytes of the stream as 32-bit words (second word unused for W = 4)
+template <int W>
+__device__ __forceinline__ uint2 ld_group(const uint8_t *text, uint32_t i)
 {
-    if (i + 16u <= a.readable) return ld_text16(a.text + i);
-    uint32_t w[4] = {0, 0, 0, 0};
-    for (uint32_t j = 0; j < 16u; ++j)
-        if (i + j < a.readable) w[j >> 2] |= (uint32_t)a.text[i + j] << ((j & 3u) * 8u);
-    return make_uint4(w[0], w[1], w[2], w[3]);
+    if (W == 8) return __ldg(reinterpret_cast<const uint2 *>(text + i));
+    return make_uint2(__ldg(reinterpret_cast<const uint32_t *>(text + i)), 0u);
 }
 
-// Walks bytes [ws, re) of the stream from the root (ws is a multiple of 16; haystack starts inside
-// the window reset the state) and records the reporting states reached by bytes at index >= rs.
-// EMIT: events go to dst[0..); otherwise they are counted and the first one is kept in `first`.
-// Returns the number of events; *end_state receives the state after byte re-1.
-template <bool EMIT, typename SC>
-__device__ __forceinline__ uint32_t walk_window(const ScanArgs &a, const SC &sc, uint32_t ws, uint32_t rs,
-                                                uint32_t re, uint2 *dst, uint2 &first, uint32_t *end_state)
+template <int W>
+__device__ __forceinline__ uint2 ld_group_guarded(const ScanArgs &a, uint32_t i)
+{
+    if (i + W <= a.readable) return ld_group<W>(a.text, i);
+    uint32_t w[2] = {0, 0};
+    for (uint32_t j = 0; j < (uint32_t)W; ++j)
+        if (i + j < a.readable) w[j >> 2] |= (uint32_t)a.text[i + j] << ((j & 3u) * 8u);
+    return make_uint2(w[0], w[1]);
+}
+
+__device__ __forceinline__ uint32_t pair_byte(const uint2 &v, int j)
+{
+    return (((j < 4) ? v.x : v.y) >> ((j & 3) * 8)) & 0xffu;
+}
+
+// The W end offsets owned by flagged word k (bytes rs .. rs+W-1 with rs = W(k+1)): walk from the root over
+// the warm-up [ws, rs) and report the final states reached inside [rs, re).  Fast version: the window lies
+// inside one haystack and inside the stream.
+template <int W, bool EMIT, typename SC>
+__device__ __forceinline__ void walk_word_fast(const ScanArgs &a, SC &sc, uint32_t ws, uint32_t rs)
+{
+    uint32_t s = a.root;
+    uint2 cur = ld_group<W>(a.text, ws);
+    uint2 nxt = (ws + W <= rs) ? ld_group<W>(a.text, ws + W) : cur;
+    for (uint32_t i = ws; i < rs; i += W) {
+        uint2 nn = nxt;
+        if (i + 2u * W <= rs) nn = ld_group<W>(a.text, i + 2u * W);
+#pragma unroll
+        for (int j = 0; j < W; ++j) s = dfa_step(sc, s, pair_byte(cur, j));
+        cur = nxt; nxt = nn;
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        s = dfa_step(sc, s, pair_byte(cur, j));
+        if (s < a.final_bound) sc.template hit<EMIT>(rs + j + 1u, s);
+    }
+}
+
+// General version: haystack starts inside the window reset the state, the window may be clipped at the
+// end of the stream, nothing is read past `readable`.  rs = 0xffffffff: report nothing (end-state walk).
+template <int W, bool EMIT, typename SC>
+__device__ __forceinline__ uint32_t walk_word_careful(const ScanArgs &a, SC &sc, uint32_t ws, uint32_t rs, uint32_t re)
 {
     uint32_t h = find_haystack(a, ws);
     uint32_t nb = hay_end(a, h);
     uint32_t s = a.root;
-    uint32_t n = 0;
-    uint4 cur = ld_text16_guarded(a, ws);
-    for (uint32_t i = ws; i < re; i += 16u) {
-        uint4 nxt = cur;
-        if (i + 16u < re) nxt = ld_text16_guarded(a, i + 16u);
+    for (uint32_t i = ws; i < re; i += W) {
+        const uint2 cur = ld_group_guarded<W>(a, i);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < W; ++j) {
             const uint32_t ii = i + j;
             if (ii < re) {
                 if (ii == nb) {                      // a haystack starts here
                     do { ++h; nb = hay_end(a, h); } while (nb == ii);
                     s = a.root;
                 }
-                s = dfa_step(sc, s, SC::group_byte(cur, j));
-                if (ii >= rs && s < a.final_bound) {
-                    if (EMIT) dst[n] = make_uint2(ii + 1u, s);
-                    else if (n == 0) first = make_uint2(ii + 1u, s);
-                    ++n;
-                }
+                s = dfa_step(sc, s, pair_byte(cur, j));
+                if (ii >= rs && s < a.final_bound) sc.template hit<EMIT>(ii + 1u, s);
             }
         }
-        cur = nxt;
     }
-    if (end_state) *end_state = s;
-    return n;
+    return s;
+}
+
+template <int W, bool EMIT, typename SC>
+__device__ __forceinline__ void walk_word(const ScanArgs &a, SC &sc, uint32_t k)
+{
+    const uint32_t rs = (k + 1u) * W;
+    if (rs >= a.total) return;                       // nothing ends after this word
+    const uint32_t re = min(rs + W, a.total);
+    const uint32_t ws = (rs > a.warm) ? rs - a.warm : 0u;
+    bool plain = (re == rs + W);
+    if (plain) {
+        const uint32_t h = find_haystack(a, ws);
+        plain = hay_end(a, h) >= re;
+    }
+    if (plain) walk_word_fast<W, EMIT>(a, sc, ws, rs);
+    else walk_word_careful<W, EMIT>(a, sc, ws, rs, re);
 }
 
 template <typename E, bool RANGE, int W>
@@ -186,16 +248,21 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_verify_kernel(const ScanAr
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint8_t s_cls[256];
     constexpr int NB = 16 / W;
-    constexpr uint32_t WORDS_PER_TILE = 32u * 32u * NB;
+    constexpr uint32_t WORDS_PER_SPAN = 32u * NB;
+    constexpr int N_WARPS = SCAN_THREADS / 32;
+    constexpr int MAX_BATCHES = N_WARPS * VER_ROUNDS;
 
-    // dynamic shared memory: per-warp candidate lists, per-warp event staging, then the table window
-    uint16_t *s_list = reinterpret_cast<uint16_t *>(smem_raw);
-    uint2 *s_stage = reinterpret_cast<uint2 *>(smem_raw + (SCAN_THREADS / 32) * VER_LIST_CAP * sizeof(uint16_t));
-    E *s_tab = reinterpret_cast<E *>(smem_raw + (SCAN_THREADS / 32) * (VER_LIST_CAP * sizeof(uint16_t) +
-                                                                       VER_STAGE_CAP * sizeof(uint2)));
+    // dynamic shared memory: item list, scan scratch, then the table window
+    uint32_t *s_list = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *s_wcnt = s_list + VER_LIST_CAP;             // items per warp tile            [N_WARPS]
+    uint32_t *s_btot = s_wcnt + N_WARPS;                  // events per batch -> offsets    [MAX_BATCHES]
+    uint32_t *s_misc = s_btot + MAX_BATCHES;              // [0] offset of the chunk's run
+    E *s_tab = reinterpret_cast<E *>(smem_raw + VER_FIXED_SMEM);
+    static_assert((VER_LIST_CAP + N_WARPS + MAX_BATCHES + 4) * 4 <= VER_FIXED_SMEM, "scan scratch does not fit");
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
+    const uint32_t warp = tid >> 5;
     const E *gtab = static_cast<const E *>(a.table);
 
     const uint32_t win_entries = a.win_rows * a.ncls;
@@ -223,18 +290,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_verify_kernel(const ScanAr
     sc.out = a.out; sc.cap = a.capacity;
     sc.found = false;
 
-    uint16_t *my_list = s_list + (tid >> 5) * VER_LIST_CAP;
-    uint2 *my_stage = s_stage + (tid >> 5) * VER_STAGE_CAP;
-    const uint32_t prior = a.counters[1];
+    const uint32_t n_chunks = (a.n_spans + CHUNK_SPANS - 1) / CHUNK_SPANS;
     uint32_t dense_tiles = 0;
 
-    while (true) {
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(&a.counters[0], 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= a.n_tiles) break;
-
-        const uint32_t span = tile * 32u + lane;
+    for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        // ---- 1. flagged words of this warp's 32-span tile
+        const uint32_t span = chunk * CHUNK_SPANS + warp * 32u + lane;
         const bool active = span < a.n_spans;
         uint32_t planes[NB];
 #pragma unroll
@@ -258,109 +319,177 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_verify_kernel(const ScanAr
             if (lane >= d) incl += t;
         }
         const uint32_t n_cand = __shfl_sync(0xffffffffu, incl, 31);
+        const bool dense = n_cand > a.dense_max;       // cheaper to walk the whole tile
+        const uint32_t n_act = __popc(__ballot_sync(0xffffffffu, active));
+        if (lane == 0) {
+            s_wcnt[warp] = dense ? n_act : n_cand;
+            if (dense) ++dense_tiles;
+        }
+        __syncthreads();
 
-        bool dense = n_cand > (uint32_t)VER_LIST_CAP;
-        uint32_t total = 0;                        // events of this tile
-
-        if (!dense && n_cand) {
-            // flagged words of the tile in ascending stream order
-            uint32_t at = incl - cnt;
-            uint32_t any = 0;
+        // ---- 2. ordered item list of the chunk
+        uint32_t n_items;
+        {
+            const uint32_t v = s_wcnt[lane];
+            uint32_t wincl = v;
 #pragma unroll
-            for (int j = 0; j < NB; ++j) any |= planes[j];
-            while (any) {
-                const uint32_t c = __ffs(any) - 1;
-                any &= any - 1;
-#pragma unroll
-                for (int j = 0; j < NB; ++j)
-                    if ((planes[j] >> c) & 1u) my_list[at++] = (uint16_t)((lane * 32u + c) * NB + j);
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, wincl, d);
+                if (lane >= d) wincl += t;
             }
-            __syncwarp();
-
-            for (uint32_t b = 0; b < n_cand; b += 32u) {
-                const uint32_t idx = b + lane;
-                uint32_t n_ev = 0, ws = 0, rs = 0, re = 0;
-                uint2 first = make_uint2(0, 0);
-                if (idx < n_cand) {
-                    const uint32_t k = tile * WORDS_PER_TILE + my_list[idx];
-                    rs = (k + 1u) * W;             // the W end offsets owned by word k are rs+1 .. rs+W
-                    if (rs < a.total) {
-                        re = min(rs + W, a.total);
-                        ws = (rs > a.halo) ? ((rs - a.halo) & ~15u) : 0u;
-                        n_ev = walk_window<false>(a, sc, ws, rs, re, nullptr, first, nullptr);
-                    }
+            n_items = __shfl_sync(0xffffffffu, wincl, 31);
+            const uint32_t base = __shfl_sync(0xffffffffu, wincl - v, warp);
+            if (dense) {
+                if (active) s_list[base + lane] = ITEM_SPAN | span;
+            } else if (cnt) {
+                uint32_t at = base + incl - cnt;
+                uint32_t any = 0;
+#pragma unroll
+                for (int j = 0; j < NB; ++j) any |= planes[j];
+                while (any) {
+                    const uint32_t ch = __ffs(any) - 1;
+                    any &= any - 1;
+#pragma unroll
+                    for (int j = 0; j < NB; ++j)
+                        if ((planes[j] >> ch) & 1u) s_list[at++] = span * WORDS_PER_SPAN + ch * NB + j;
                 }
-                uint32_t bincl = n_ev;
+            }
+        }
+        __syncthreads();
+
+        // ---- 3. one lane per item: count events (first one kept in registers)
+        const uint32_t n_batches = (n_items + 31u) >> 5;
+        uint32_t r_item[VER_ROUNDS], r_cnt[VER_ROUNDS], r_excl[VER_ROUNDS], r_e0p[VER_ROUNDS], r_e0s[VER_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < VER_ROUNDS; ++r) {
+            r_item[r] = ITEM_NONE; r_cnt[r] = 0; r_excl[r] = 0; r_e0p[r] = 0; r_e0s[r] = 0;
+            const uint32_t b = warp + r * N_WARPS;
+            if (b < n_batches) {                       // warp-uniform
+                const uint32_t idx = b * 32u + lane;
+                const uint32_t item = (idx < n_items) ? s_list[idx] : ITEM_NONE;
+                sc.cnt = 0;
+                if (item == ITEM_NONE) {
+                } else if (item & ITEM_SPAN) {
+                    const uint32_t cs = (item & ~ITEM_SPAN) * SPAN_BYTES;
+                    const uint32_t ce = min(cs + SPAN_BYTES, a.total);
+                    const uint32_t h = find_haystack(a, cs);
+                    const uint32_t hb = hay_begin(a, h);
+                    uint32_t ws = (cs - hb > a.halo) ? ((cs - a.halo) & ~15u) : hb;
+                    if (ws < hb) ws = hb;
+                    const uint32_t s_cs = sc.template walk<false, false>(a.root, ws, cs);
+                    scan_slice<false>(a, sc, s_cs, h, cs, ce);
+                } else {
+                    walk_word<W, false>(a, sc, item);
+                }
+                __syncwarp();
+                uint32_t bincl = sc.cnt;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const uint32_t t = __shfl_up_sync(0xffffffffu, bincl, d);
                     if (lane >= d) bincl += t;
                 }
-                const uint32_t btotal = __shfl_sync(0xffffffffu, bincl, 31);
-                if (total + btotal > (uint32_t)VER_STAGE_CAP) { dense = true; break; }   // warp-uniform
-                if (n_ev == 1) my_stage[total + bincl - 1u] = first;
-                else if (n_ev > 1) walk_window<true>(a, sc, ws, rs, re, my_stage + (total + bincl - n_ev), first, nullptr);
-                total += btotal;
+                if (lane == 31) s_btot[b] = bincl;
+                r_item[r] = item; r_cnt[r] = sc.cnt; r_excl[r] = bincl - sc.cnt; r_e0p[r] = sc.e0p; r_e0s[r] = sc.e0s;
             }
-            __syncwarp();
         }
+        __syncthreads();
 
-        uint32_t cs = 0, ce = 0, h = 0, s_cs = 0;
-        sc.cnt = 0;
-        if (dense) {
-            // too many flagged words (or events): walk the whole tile, one 512-byte span per lane
-            ++dense_tiles;
-            if (active) {
-                cs = span * SPAN_BYTES;
-                ce = min(cs + SPAN_BYTES, a.total);
-                h = find_haystack(a, cs);
-                const uint32_t hb = hay_begin(a, h);
-                uint32_t ws = (cs - hb > a.halo) ? ((cs - a.halo) & ~15u) : hb;
-                if (ws < hb) ws = hb;
-                uint32_t s = sc.template walk<false, false>(a.root, ws, cs);
-                s_cs = s;
-                s = scan_slice<false>(a, sc, s, h, cs, ce);
-                if (ce == a.total) a.counters[2] = s;
+        // ---- 4. batch offsets inside the chunk's run; the run's place in the event buffer
+        if (warp == 0) {
+            constexpr int PER = MAX_BATCHES / 32;
+            uint32_t v[PER];
+            uint32_t sum = 0;
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                const uint32_t b = lane * PER + k;
+                v[k] = (b < n_batches) ? s_btot[b] : 0u;
+                sum += v[k];
             }
-            __syncwarp();
-            incl = sc.cnt;
+            uint32_t sincl = sum;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
+                const uint32_t t = __shfl_up_sync(0xffffffffu, sincl, d);
+                if (lane >= d) sincl += t;
             }
-            total = __shfl_sync(0xffffffffu, incl, 31);
-        } else if (tile == a.n_tiles - 1 && lane == 0) {
-            // state at the end of the stream (keep=1 continuation): the last Lmax bytes decide it
-            const uint32_t back = a.halo + 1u;
-            const uint32_t ws = (a.total > back) ? ((a.total - back) & ~15u) : 0u;
-            uint2 dummy;
-            uint32_t s_end = a.root;
-            walk_window<false>(a, sc, ws, 0xffffffffu, a.total, nullptr, dummy, &s_end);
-            a.counters[2] = s_end;
-        }
-
-        const unsigned long long excl = tile_lookback(a, tile, total, prior, lane);
-
-        if (!dense) {
-            for (uint32_t i = lane; i < total; i += 32u) {
-                const unsigned long long o = excl + i;
-                if (o < a.capacity) a.out[o] = my_stage[i];
+            uint32_t run = sincl - sum;
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                const uint32_t b = lane * PER + k;
+                if (b < n_batches) s_btot[b] = run;
+                run += v[k];
             }
-        } else if (sc.cnt) {
-            const uint32_t off = (uint32_t)excl + (incl - sc.cnt);
-            if (sc.cnt <= 2) {
-                if (off < a.capacity) a.out[off] = make_uint2(sc.e0p, sc.e0s);
-                if (sc.cnt == 2 && off + 1 < a.capacity) a.out[off + 1] = make_uint2(sc.e1p, sc.e1s);
-            } else if (off < a.capacity) {
-                sc.obase = off;
-                sc.cnt = 0;
-                scan_slice<true>(a, sc, s_cs, h, cs, ce);
+            if (lane == 31) {
+                const uint32_t base = sincl ? atomicAdd(&a.counters[1], sincl) : 0u;
+                a.runs[chunk] = make_uint2(base, sincl);
+                s_misc[0] = base;
             }
         }
-        __syncwarp();
+        __syncthreads();
+
+        // ---- 5. emit
+        const uint32_t run_base = s_misc[0];
+#pragma unroll
+        for (int r = 0; r < VER_ROUNDS; ++r) {
+            if (r_cnt[r]) {
+                const uint32_t b = warp + r * N_WARPS;
+                const uint32_t off = run_base + s_btot[b] + r_excl[r];
+                if (r_cnt[r] == 1) {
+                    if (off < a.capacity) a.out[off] = make_uint2(r_e0p[r], r_e0s[r]);
+                } else if (off < a.capacity) {
+                    sc.obase = off;
+                    sc.cnt = 0;
+                    const uint32_t item = r_item[r];
+                    if (item & ITEM_SPAN) {
+                        const uint32_t cs = (item & ~ITEM_SPAN) * SPAN_BYTES;
+                        const uint32_t ce = min(cs + SPAN_BYTES, a.total);
+                        const uint32_t h = find_haystack(a, cs);
+                        const uint32_t hb = hay_begin(a, h);
+                        uint32_t ws = (cs - hb > a.halo) ? ((cs - a.halo) & ~15u) : hb;
+                        if (ws < hb) ws = hb;
+                        const uint32_t s_cs = sc.template walk<false, false>(a.root, ws, cs);
+                        scan_slice<true>(a, sc, s_cs, h, cs, ce);
+                    } else {
+                        walk_word<W, true>(a, sc, item);
+                    }
+                }
+            }
+        }
+        // the next chunk's first barrier orders these reads before the scratch is overwritten
     }
     if (lane == 0 && dense_tiles) atomicAdd(&a.counters[4], dense_tiles);
+
+    // state at the end of the stream (keep=1 continuation): the last Lmax bytes decide it
+    if (a.want_end_state && blockIdx.x == gridDim.x - 1 && tid == SCAN_THREADS - 1) {
+        const uint32_t back = a.halo + 1u;
+        const uint32_t ws = (a.total > back) ? ((a.total - back) & ~(uint32_t)(W - 1)) : 0u;
+        a.counters[2] = walk_word_careful<W, false>(a, sc, ws, 0xffffffffu, a.total);
+    }
+}
+
+// ------------------------------------------------------------ reorder -----
+
+// One CTA per chunk: the run's final offset is the number of events of all earlier chunks.
+__global__ void __launch_bounds__(REORDER_THREADS) ac_reorder_kernel(const uint2 *__restrict__ runs,
+                                                                      const uint2 *__restrict__ tmp,
+                                                                      uint2 *__restrict__ out, uint32_t capacity)
+{
+    __shared__ uint32_t s_part[REORDER_THREADS / 32];
+    const uint32_t chunk = blockIdx.x;
+    const uint2 run = runs[chunk];
+    if (run.y == 0) return;                            // CTA-uniform
+    uint32_t part = 0;
+    for (uint32_t j = threadIdx.x; j < chunk; j += REORDER_THREADS) part += runs[j].y;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if ((threadIdx.x & 31u) == 0) s_part[threadIdx.x >> 5] = part;
+    __syncthreads();
+    uint32_t excl = 0;
+#pragma unroll
+    for (int w = 0; w < REORDER_THREADS / 32; ++w) excl += s_part[w];
+    for (uint32_t i = threadIdx.x; i < run.y; i += REORDER_THREADS) {
+        const unsigned long long src = (unsigned long long)run.x + i, dst = (unsigned long long)excl + i;
+        if (src < capacity && dst < capacity) out[dst] = tmp[src];
+    }
 }
 
 } // namespace acb200

@@ -57,10 +57,14 @@ struct ScanArgs {
     uint32_t capacity;            // events that fit in `out`
     unsigned long long *tile_status;  // n_tiles words, zeroed before launch
     uint32_t *counters;           // [0] ticket (zeroed per launch) [1] running event total [2] end state
-                                  // [3] words flagged by the filter [4] tiles the verify kernel walked completely
+                                  // [3] words flagged by the filter [4] tiles handed on for a complete walk
     uint32_t *first_end;          // FIRST kernels: per haystack earliest event end seen (init 0xffffffff)
     const uint32_t *mask;         // ac_verify_kernel: flagged-word bit planes written by ac_filter_kernel
     uint32_t n_spans;             // ac_verify_kernel: 512-byte spans in the stream
+    uint32_t dense_max;           // ac_verify_kernel: more flagged words than this in a 16 KiB tile: walk the tile
+    uint2 *runs;                  // ac_verify_kernel: per chunk {offset, count} of its run of events in `out`
+    uint32_t warm;                // ac_verify_kernel: warm-up bytes before a flagged word's end offsets (halo rounded up to W)
+    uint32_t want_end_state;      // ac_verify_kernel: also compute the state at the end of the stream
 };
 
 // ------------------------------------------------------------ finalize ----
@@ -122,25 +126,25 @@ constexpr unsigned long long ST_PREFIX = 2ull << 62;  // inclusive prefix publis
 constexpr unsigned long long ST_MASK = (1ull << 62) - 1;
 
 // Decoupled look-back over earlier tiles, 32 predecessors per step: publishes this
-// tile's event total, returns the number of events of all earlier tiles (plus
-// `prior`, the events of earlier launches of the same call) and publishes the
-// inclusive prefix.  The last tile also stores the grand total in counters[1].
+// tile's total in status[tile], returns the sum over all earlier tiles plus `prior`
+// and publishes the inclusive prefix.  Tiles must be handed out in ascending order
+// (atomic ticket) so that a tile only ever waits for tiles that already started.
 // Must be called by all 32 lanes of the warp that owns `tile`.
-__device__ __forceinline__ unsigned long long tile_lookback(const ScanArgs &a, uint32_t tile, uint32_t total,
-                                                            uint32_t prior, uint32_t lane)
+__device__ __forceinline__ unsigned long long lookback(unsigned long long *status, uint32_t tile, uint32_t total,
+                                                       uint32_t prior, uint32_t lane)
 {
     unsigned long long excl = prior;
     if (tile == 0) {
-        if (lane == 0) st_status(a.tile_status, ST_PREFIX | (excl + total));
+        if (lane == 0) st_status(status, ST_PREFIX | (excl + total));
     } else {
-        if (lane == 0) st_status(a.tile_status + tile, ST_AGG | total);
+        if (lane == 0) st_status(status + tile, ST_AGG | total);
         long long j = (long long)tile - 1 - lane;
         unsigned long long sum = 0;
         while (true) {
             unsigned long long v = ST_PREFIX;         // before tile 0: the events of earlier launches
             const bool virt = j < 0;
             if (!virt) {
-                do { v = ld_status(a.tile_status + j); } while ((v >> 62) == 0);
+                do { v = ld_status(status + j); } while ((v >> 62) == 0);
             }
             const bool is_prefix = (v >> 62) == 2;
             const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
@@ -154,8 +158,16 @@ __device__ __forceinline__ unsigned long long tile_lookback(const ScanArgs &a, u
             j -= 32;
         }
         excl = sum;
-        if (lane == 0) st_status(a.tile_status + tile, ST_PREFIX | (excl + total));
+        if (lane == 0) st_status(status + tile, ST_PREFIX | (excl + total));
     }
+    return excl;
+}
+
+// The scan kernels' use of it: event offsets; the last tile stores the grand total in counters[1].
+__device__ __forceinline__ unsigned long long tile_lookback(const ScanArgs &a, uint32_t tile, uint32_t total,
+                                                            uint32_t prior, uint32_t lane)
+{
+    const unsigned long long excl = lookback(a.tile_status, tile, total, prior, lane);
     if (lane == 0 && tile == a.n_tiles - 1) a.counters[1] = (uint32_t)(excl + total);
     return excl;
 }

@@ -60,7 +60,7 @@ class Stats(C.Structure):
                 ("chunk_bytes", C.c_uint32), ("halo_bytes", C.c_uint32), ("kernel_ms", C.c_float),
                 ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("ilp", C.c_uint32), ("filtered", C.c_uint32),
                 ("filter_ms", C.c_float), ("verify_ms", C.c_float), ("flagged_words", C.c_uint64),
-                ("dense_tiles", C.c_uint64)]
+                ("dense_tiles", C.c_uint64), ("reorder_ms", C.c_float), ("reserved_", C.c_uint32)]
 
 
 MATCH_CB = C.CFUNCTYPE(C.c_int, C.POINTER(AcMatch), C.c_void_p)

@@ -14,11 +14,11 @@ def run(name, aut, dev_buf, offsets, mode, reps=5):
         _, ne = aut.search_device(dev_buf.data_ptr(), offsets)
         st = aut.stats()
         if best is None or st.kernel_ms < best[0]:
-            best = (st.kernel_ms, st.filter_ms, st.verify_ms, st.flagged_words, st.dense_tiles, st.filtered, ne)
-    k, f, v, fl, dt, fi, ne = best
+            best = (st.kernel_ms, st.filter_ms, st.verify_ms, st.flagged_words, st.dense_tiles, st.filtered, ne, st.reorder_ms, 0)
+    k, f, v, fl, dt, fi, ne, c, wi = best
     n = dev_buf.numel()
     print(f"{name:28s} filter={mode:2d} used={fi} events={ne:9d} flagged={fl:10d} dense_tiles={dt:7d} "
-          f"kernel={k:8.3f} ms ({n/k/1e6:8.1f} GB/s)  filter={f:7.3f} ms ({(n/f/1e6) if f else 0:8.1f} GB/s) verify={v:7.3f} ms",
+          f"kernel={k:8.3f} ms ({n/k/1e6:8.1f} GB/s)  filter={f:7.3f} ms ({(n/f/1e6) if f else 0:8.1f} GB/s) reorder={c:6.3f} verify={v:6.3f} ms items={wi}",
           flush=True)
 
 
