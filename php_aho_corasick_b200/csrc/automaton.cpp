@@ -295,17 +295,16 @@ void HostTrie::build_filter(FlatAutomaton &flat) const {
         for (uint32_t r = 1; r <= W; ++r) {
             uint32_t lo, hi;
             gram(p, r, lo, hi);
-            const uint32_t i = filter_reduce(filter_mix1(lo, hi), flat.l1_bits);
-            flat.l1[i >> 5] |= 1u << (i & 31);
-            const uint32_t i2 = filter_reduce(filter_mix2(lo, hi), flat.l1_bits);
-            flat.l1[i2 >> 5] |= 1u << (i2 & 31);
+            const uint32_t t = filter_mix1(lo, hi);
+            const uint32_t i = filter_reduce(t, flat.l1_bits);
+            flat.l1[i >> 5] |= (1u << (i & 31)) | (1u << filter_bit2(t));
         }
     flat.n_grams = (uint64_t)patterns_.size() * W;
     uint64_t set = 0;
     for (uint32_t w : flat.l1) set += (uint64_t)__builtin_popcount(w);
     flat.l1_fill = (double)set / (double)flat.l1_bits;
 
-    // Level 1 is probed twice (two hashes, one bitmap): a random word passes with probability fill^2.
+    // Level 1 tests two bits of one word: a random haystack word passes with probability ~fill^2.
     // Level 2 (global memory) is only worth its latency when that is still not selective.
     double l2_min_fill = 0.15;
     if (const char *e = getenv("ACB200_L2_MIN_FILL")) l2_min_fill = atof(e);

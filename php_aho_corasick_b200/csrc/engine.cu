@@ -296,7 +296,7 @@ bool Engine::ensure_runs(size_t n)
     if (n <= runs_cap_) return true;
     cudaFree(d_runs_); d_runs_ = nullptr; runs_cap_ = 0;
     const size_t cap = std::max(n + n / 4, (size_t)256);
-    CU_OK(cudaMalloc(&d_runs_, cap * 2 * sizeof(uint32_t)));
+    CU_OK(cudaMalloc(&d_runs_, cap * 2 * sizeof(uint32_t)));      // {offset, count} per tile
     runs_cap_ = cap;
     return true;
 }
@@ -513,8 +513,8 @@ static void launch_filter_k(const FilterArgs &fa, bool l2, unsigned grid, cudaSt
 template <typename E, int W>
 static void launch_verify_k(const ScanArgs &a, bool range, unsigned grid, size_t smem, cudaStream_t st)
 {
-    if (range) ac_verify_kernel<E, true, W><<<grid, SCAN_THREADS, smem, st>>>(a);
-    else ac_verify_kernel<E, false, W><<<grid, SCAN_THREADS, smem, st>>>(a);
+    if (range) ac_verify_kernel<E, true, W><<<grid, VERIFY_THREADS, smem, st>>>(a);
+    else ac_verify_kernel<E, false, W><<<grid, VERIFY_THREADS, smem, st>>>(a);
 }
 
 // ahocorasick_match() through the gram prefilter: ac_filter_kernel streams the haystack and flags
@@ -526,7 +526,7 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     const uint32_t W = filter_w_;
     const uint32_t NB = 16 / W;
     const uint32_t n_spans = (uint32_t)(((uint64_t)total + SPAN_BYTES - 1) / SPAN_BYTES);
-    const uint32_t n_tiles = (n_spans + 31) / 32;      // 16 KiB tiles (statistics only)
+    const uint32_t n_tiles = (n_spans + 32 * VT_SUB - 1) / (32 * VT_SUB);      // 64 KiB warp tiles of the verify kernel
     stats.chunk_bytes = SPAN_BYTES;
     stats.filtered = 1;
     if (events_cap_ == 0 && !ensure_events(std::max<size_t>(1 << 16, total / 64))) return false;
@@ -535,15 +535,16 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     const uint32_t warm = (halo_ + W - 1) / W * W;
     // walking a whole tile costs ~(512 + halo) steps per lane, a flagged word (warm + W) steps on one lane
     const uint32_t dense_max = std::max<uint32_t>(32u, std::min<uint32_t>(VER_DENSE_MAX, 32u * (SPAN_BYTES + halo_) / (warm + W)));
-    const uint32_t n_chunks = (n_spans + CHUNK_SPANS - 1) / CHUNK_SPANS;
-    if (!ensure_runs(n_chunks)) return false;
+    const uint32_t n_runs = n_tiles * (VT_BATCHES / VT_LOCK);   // one run of events per lockstep group of a tile
+    if (!ensure_runs(n_runs)) return false;
 
     const int dyn_max = max_smem_optin_ - 2048;
-    size_t smem_budget = (size_t)dyn_max - VER_FIXED_SMEM;
+    const size_t row_bytes = (size_t)ncls_ * entry_bytes_;
+    size_t smem_budget = (size_t)dyn_max - VER_FIXED_SMEM - row_bytes - 16;  // one extra all-zero row
     if (tune_smem_bytes) smem_budget = std::min<size_t>(smem_budget, tune_smem_bytes);
     uint32_t win_lo = 0, win_rows = 0;
     window_for(smem_budget, &win_lo, &win_rows);
-    const size_t smem_bytes = VER_FIXED_SMEM + std::max<size_t>(16, (size_t)win_rows * ncls_ * entry_bytes_);
+    const size_t smem_bytes = VER_FIXED_SMEM + ((size_t)win_rows + 1) * row_bytes + 16;
 
     FilterArgs fa{};
     fa.text = (const uint8_t *)d_text;
@@ -588,13 +589,14 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
 
     const unsigned warps_per_cta = SCAN_THREADS / 32;
     const unsigned grid_f = std::min<uint32_t>((n_spans + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
-    const unsigned grid_v = std::min<uint32_t>(n_chunks, (uint32_t)n_sms_);
+    const unsigned grid_v = std::min<uint32_t>((n_tiles + VERIFY_THREADS / 32 - 1) / (VERIFY_THREADS / 32), (uint32_t)n_sms_);
 
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (!ensure_events_tmp(events_cap_)) return false;
         a.out = (uint2 *)d_events_tmp_;        // runs in completion order; ac_reorder_kernel writes d_events_
         a.capacity = (uint32_t)std::min<size_t>(events_cap_, 0xffffffffu);
         CU_OK(cudaMemsetAsync(d_counters_, 0, 32, st));
+        CU_OK(cudaMemsetAsync(d_runs_, 0, (size_t)n_runs * 2 * sizeof(uint32_t), st));
         CU_OK(cudaEventRecord(EV(ev_[0]), st));
         if (attempt == 0) {          // the bit planes survive a regrow of the event buffer
             if (W == 8) launch_filter_k<8>(fa, d_l2_ != nullptr, grid_f, st);
@@ -610,8 +612,8 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
             else launch_verify_k<uint32_t, 4>(a, range_map_, grid_v, smem_bytes, st);
         }
         CU_OK(cudaEventRecord(EV(ev_[5]), st));
-        ac_reorder_kernel<<<n_chunks, REORDER_THREADS, 0, st>>>((const uint2 *)d_runs_, (const uint2 *)d_events_tmp_,
-                                                                (uint2 *)d_events_, a.capacity);
+        ac_reorder_kernel<<<(n_runs + RUNSCAN_THREADS - 1) / RUNSCAN_THREADS, RUNSCAN_THREADS, 0, st>>>(
+            (const uint2 *)d_runs_, n_runs, (const uint2 *)d_events_tmp_, (uint2 *)d_events_, a.capacity);
         CU_OK(cudaGetLastError());
         CU_OK(cudaEventRecord(EV(ev_[1]), st));
         stats.kernel_launches += 2;

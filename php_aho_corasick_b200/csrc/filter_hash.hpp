@@ -18,7 +18,9 @@ namespace acb200 {
 constexpr uint32_t FILTER_L1_BYTES = 220u * 1024u;          // level-1 bitmap, lives in shared memory
 constexpr uint32_t FILTER_L1_BITS = FILTER_L1_BYTES * 8u;
 
-// level 1: bit index in [0, n_bits) — multiplicative hash, range-reduced with a high multiply
+// level 1 is a blocked Bloom filter with two bits per gram inside ONE 32-bit word (one shared-memory
+// load per haystack word): word = reduce(mix1) >> 5, first bit = reduce(mix1) & 31, second bit taken from
+// low-order bits of the same hash, which the high-multiply range reduction does not look at.
 ACB_HD uint32_t filter_mix1(uint32_t lo, uint32_t hi)
 {
     return lo * 0x9E3779B1u + hi * 0x85EBCA77u;
@@ -33,13 +35,7 @@ ACB_HD uint32_t filter_reduce(uint32_t t, uint32_t n_bits)
 #endif
 }
 
-// level 1, second probe (same bitmap, independent hash; only evaluated when the first probe hits)
-ACB_HD uint32_t filter_mix2(uint32_t lo, uint32_t hi)
-{
-    uint32_t t = lo * 0xC2B2AE3Du + hi * 0x27D4EB2Fu;
-    t ^= t >> 15;
-    return t * 0x2C1B3C6Du;
-}
+ACB_HD uint32_t filter_bit2(uint32_t t) { return (t >> 3) & 31u; }
 
 // level 2: third independent hash, top `log2_bits` bits index a 2^log2_bits-bit map in global memory
 ACB_HD uint32_t filter_mix3(uint32_t lo, uint32_t hi)

@@ -13,24 +13,27 @@
 //                     see FlatAutomaton) and writes one bit per word: "the W
 //                     end offsets after this word need a look".  No false
 //                     negatives by construction.
-//   ac_verify_kernel  a CTA takes a 512 KiB chunk of the stream at a time.  Its
-//                     warps turn the chunk's bit planes into a dense, ordered
-//                     list of work items in shared memory (ballot / popc /
-//                     prefix sums): one item per flagged word, or — for a
-//                     16 KiB tile with so many flagged words that walking all
-//                     of it is cheaper — one item per 512-byte span of the
-//                     tile.  Then one lane per item: for a flagged word the
-//                     lane walks the automaton from the root over the
-//                     (Lmax-1)-byte warm-up plus the W bytes after the word —
-//                     exactly the halo argument of ac_scan_kernel, so states
-//                     and events are those of an uninterrupted walk; a span
-//                     item is walked like an ac_scan_kernel slice.  The
-//                     chunk's events are written as one ordered run at an
-//                     offset taken from a global counter (no CTA ever waits
-//                     for another one).
-//   ac_reorder_kernel copies the runs into chunk order: the final event list
-//                     is ascending, as the callback contract requires.  The
-//                     worst case costs what the plain scan costs.
+//   ac_verify_kernel  a warp takes a 64 KiB tile of the stream at a time and needs
+//                     no other warp: its lanes turn the tile's bit planes into
+//                     an ordered list of work items (ballot / popc / prefix
+//                     sums) — one item per flagged word, or, when so many words
+//                     are flagged that walking all of the tile is cheaper, one
+//                     item per 512-byte span.  Then one lane per item, two
+//                     items per lane in lockstep (independent lookup chains
+//                     hide each other's latency): for a
+//                     flagged word the lane walks the automaton from the root
+//                     over the (Lmax-1)-byte warm-up plus the W bytes after the
+//                     word — exactly the halo argument of ac_scan_kernel, so
+//                     states and events are those of an uninterrupted walk; a
+//                     span item is walked like an ac_scan_kernel slice.  The
+//                     tile's events are written as one ordered run at an offset
+//                     taken from a global counter (no warp ever waits for
+//                     another one).
+//   ac_runs_scan_kernel / ac_reorder_kernel
+//                     prefix-sum the run lengths in tile order and copy the
+//                     runs there: the final event list is ascending, as the
+//                     callback contract requires.  The worst case costs what
+//                     the plain scan costs.
 //
 // Replaces the same reference loop as ac_scan_kernel
 // (src/multifast/ahocorasick.c:199-234); events are bit-identical.
@@ -43,14 +46,25 @@ namespace acb200 {
 
 constexpr uint32_t SPAN_BYTES = 512;       // one warp-wide 16-byte load; one verify lane
 constexpr int FILTER_UNROLL = 4;           // 16-byte loads in flight per thread
-constexpr uint32_t VER_DENSE_MAX = 128;    // flagged words per 16 KiB tile beyond which the whole tile is walked
+constexpr uint32_t VER_DENSE_MAX = 64;     // flagged words per 16 KiB tile beyond which the whole tile is walked
 constexpr uint32_t ITEM_SPAN = 0x80000000u;// work item: walk 512-byte span (item & ~ITEM_SPAN) completely
 constexpr uint32_t ITEM_NONE = 0xffffffffu;
-constexpr uint32_t CHUNK_SPANS = 32u * (SCAN_THREADS / 32);   // spans per CTA chunk: one 32-span tile per warp (512 KiB)
-constexpr int VER_ROUNDS = VER_DENSE_MAX / 32;                // batches of 32 items a warp may get per chunk
-constexpr uint32_t VER_LIST_CAP = (SCAN_THREADS / 32) * VER_DENSE_MAX;   // items per chunk
-constexpr uint32_t VER_FIXED_SMEM = VER_LIST_CAP * 4u + 2048u;           // item list + scan scratch
+constexpr int VERIFY_THREADS = 512;        // 16 warps: room for 128 registers per thread
+#ifndef ACB_VT_SUB
+#define ACB_VT_SUB 4
+#endif
+#ifndef ACB_VT_LOCK
+#define ACB_VT_LOCK 2
+#endif
+constexpr int VT_SUB = ACB_VT_SUB;         // 16 KiB sub-tiles per warp tile: a lane owns that many 512-byte spans
+constexpr int VT_LOCK = ACB_VT_LOCK;       // batches walked in lockstep
+constexpr int VT_BATCHES = VT_SUB * (int)VER_DENSE_MAX / 32;   // 8: batches of 32 items per warp tile at most
+constexpr uint32_t VT_LIST_CAP = VT_SUB * VER_DENSE_MAX;       // items per warp tile
+constexpr uint32_t VER_FIXED_SMEM = (VERIFY_THREADS / 32) * VT_LIST_CAP * 4u;   // per-warp item lists
+static_assert(VT_BATCHES % VT_LOCK == 0 && VT_SUB % VT_LOCK == 0, "lockstep groups must tile the batches and the sub-tiles");
+static_assert(VER_FIXED_SMEM % 16 == 0, "table window must stay 16-byte aligned");
 constexpr int REORDER_THREADS = 256;
+constexpr int RUNSCAN_THREADS = 1024;
 
 struct FilterArgs {
     const uint8_t *text;          // 16-byte aligned
@@ -84,75 +98,80 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const Filter
     __syncthreads();
     const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_bm);
 
-    const uint32_t n16 = a.total >> 4;                        // complete 16-byte chunks
-    const uint32_t tail_chunk = (a.total & 15u) ? n16 : 0xffffffffu;
+    // one flag per aligned word: both bits of the word's gram hash are set in the level-1 bitmap
+    auto test_word = [&](uint32_t lo, uint32_t hi) -> bool {
+        const uint32_t t = filter_mix1(lo, hi);
+        const uint32_t idx = filter_reduce(t, a.l1_bits);
+        uint32_t word;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(s_base + ((idx >> 5) << 2)));
+        bool p = ((word >> (idx & 31u)) & (word >> filter_bit2(t)) & 1u) != 0;
+        if (L2) {
+            uint32_t word3 = 0;
+            const uint32_t i3 = filter_mix3(lo, hi) >> a.l2_shift;
+            if (p) word3 = __ldg(a.l2 + (i3 >> 5));
+            p = (word3 >> (i3 & 31u)) & 1u;
+        }
+        return p;
+    };
+
+    const uint32_t n_full = a.total / SPAN_BYTES;             // spans that lie completely inside the stream
     const uint32_t n_warps = gridDim.x * (SCAN_THREADS / 32);
     const uint32_t warp = blockIdx.x * (SCAN_THREADS / 32) + (tid >> 5);
     uint32_t flagged = 0;
 
-    for (uint32_t g0 = warp; g0 < a.n_spans; g0 += n_warps * FILTER_UNROLL) {
+    for (uint32_t g0 = warp; g0 < n_full; g0 += n_warps * FILTER_UNROLL) {
         uint4 v[FILTER_UNROLL];
 #pragma unroll
         for (int u = 0; u < FILTER_UNROLL; ++u) {
             const uint32_t g = g0 + u * n_warps;
-            const uint32_t c = g * 32u + lane;
             v[u] = make_uint4(0, 0, 0, 0);
-            if (g < a.n_spans && c < n16) v[u] = ld_text16(a.text + (size_t)c * 16u);
+            if (g < n_full) v[u] = ld_text16(a.text + ((size_t)g * 32u + lane) * 16u);
         }
 #pragma unroll
         for (int u = 0; u < FILTER_UNROLL; ++u) {
             const uint32_t g = g0 + u * n_warps;
-            if (g >= a.n_spans) break;                        // warp-uniform
-            const uint32_t c = g * 32u + lane;
+            if (g >= n_full) break;                           // warp-uniform
             const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-            uint32_t planes[NB];
+            uint32_t mine = 0;
 #pragma unroll
             for (int j = 0; j < NB; ++j) {
-                const uint32_t lo = (W == 8) ? w[2 * j] : w[j];
-                const uint32_t hi = (W == 8) ? w[2 * j + 1] : 0u;
-                const uint32_t idx = filter_reduce(filter_mix1(lo, hi), a.l1_bits);
-                uint32_t word;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(s_base + ((idx >> 5) << 2)));
-                bool p = (word >> (idx & 31u)) & 1u;
-                {   // second probe of the same bitmap, only where the first one hit
-                    const uint32_t idx2 = filter_reduce(filter_mix2(lo, hi), a.l1_bits);
-                    uint32_t word2 = 0;
-                    if (p) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word2) : "r"(s_base + ((idx2 >> 5) << 2)));
-                    p = (word2 >> (idx2 & 31u)) & 1u;
-                }
-                if (L2) {
-                    uint32_t word3 = 0;
-                    const uint32_t i3 = filter_mix3(lo, hi) >> a.l2_shift;
-                    if (p) word3 = __ldg(a.l2 + (i3 >> 5));
-                    p = (word3 >> (i3 & 31u)) & 1u;
-                }
-                // the partial chunk at the very end is not read: its words are simply handed on
-                p = (c < n16) ? p : (c == tail_chunk);
-                planes[j] = __ballot_sync(0xffffffffu, p);
+                const bool p = (W == 8) ? test_word(w[2 * j], w[2 * j + 1]) : test_word(w[j], 0u);
+                const uint32_t plane = __ballot_sync(0xffffffffu, p);
+                if (lane == (uint32_t)j) mine = plane;
             }
-            uint32_t mine = planes[0];
-#pragma unroll
-            for (int j = 1; j < NB; ++j) if (lane == (uint32_t)j) mine = planes[j];
             if (lane < (uint32_t)NB) {
                 a.mask[(size_t)g * NB + lane] = mine;
                 flagged += __popc(mine);
             }
         }
     }
+
+    // The last, partial span: complete 16-byte chunks are tested, the partial chunk at the very end is not
+    // read at all — its words are simply handed on to verification.
+    if (n_full < a.n_spans && warp == (n_full % n_warps)) {
+        const uint32_t n16 = a.total >> 4;
+        const uint32_t c = n_full * 32u + lane;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (c < n16) v = ld_text16(a.text + (size_t)c * 16u);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const bool tail = (a.total & 15u) && c == n16;
+        uint32_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            bool p = (W == 8) ? test_word(w[2 * j], w[2 * j + 1]) : test_word(w[j], 0u);
+            p = (c < n16) ? p : tail;
+            const uint32_t plane = __ballot_sync(0xffffffffu, p);
+            if (lane == (uint32_t)j) mine = plane;
+        }
+        if (lane < (uint32_t)NB) {
+            a.mask[(size_t)n_full * NB + lane] = mine;
+            flagged += __popc(mine);
+        }
+    }
     if (lane < (uint32_t)NB && flagged) atomicAdd(&a.counters[3], flagged);
 }
 
 // ------------------------------------------------------------- verify -----
-
-template <typename SC>
-__device__ __forceinline__ uint32_t dfa_step(const SC &sc, uint32_t s, uint32_t b)
-{
-    if (s - sc.win_lo < sc.win_rows) {
-        const uint32_t e = sc.hot_next(s, b);
-        if (e) return e;
-    }
-    return sc.any_next(s, b);
-}
 
 // W aligned bytes of the stream as 32-bit words (second word unused for W = 4)
 template <int W>
@@ -172,45 +191,137 @@ __device__ __forceinline__ uint2 ld_group_guarded(const ScanArgs &a, uint32_t i)
     return make_uint2(w[0], w[1]);
 }
 
-__device__ __forceinline__ uint32_t pair_byte(const uint2 &v, int j)
+// true table entry from HBM/L2, only where the shared-memory window answered 0
+template <typename E> __device__ __forceinline__ void ldg_if_zero(uint32_t &e, const E *gtab, uint32_t s, uint32_t ncls, uint32_t c);
+template <> __device__ __forceinline__ void ldg_if_zero<uint16_t>(uint32_t &e, const uint16_t *gtab, uint32_t s, uint32_t ncls, uint32_t c)
 {
-    return (((j < 4) ? v.x : v.y) >> ((j & 3) * 8)) & 0xffu;
+    asm("{\n\t.reg .pred p;\n\t.reg .u32 t;\n\t.reg .u64 a;\n\t"
+                 "setp.eq.u32 p, %0, 0;\n\t"
+                 "@p mad.lo.u32 t, %2, %3, %4;\n\t"
+                 "@p mad.wide.u32 a, t, 2, %1;\n\t"
+                 "@p ld.global.nc.u16 %0, [a];\n\t}"
+                 : "+r"(e) : "l"(gtab), "r"(s), "r"(ncls), "r"(c));
+}
+template <> __device__ __forceinline__ void ldg_if_zero<uint32_t>(uint32_t &e, const uint32_t *gtab, uint32_t s, uint32_t ncls, uint32_t c)
+{
+    asm("{\n\t.reg .pred p;\n\t.reg .u32 t;\n\t.reg .u64 a;\n\t"
+                 "setp.eq.u32 p, %0, 0;\n\t"
+                 "@p mad.lo.u32 t, %2, %3, %4;\n\t"
+                 "@p mad.wide.u32 a, t, 4, %1;\n\t"
+                 "@p ld.global.nc.u32 %0, [a];\n\t}"
+                 : "+r"(e) : "l"(gtab), "r"(s), "r"(ncls), "r"(c));
 }
 
-// The W end offsets owned by flagged word k (bytes rs .. rs+W-1 with rs = W(k+1)): walk from the root over
-// the warm-up [ws, rs) and report the final states reached inside [rs, re).  Fast version: the window lies
-// inside one haystack and inside the stream.
-template <int W, bool EMIT, typename SC>
-__device__ __forceinline__ void walk_word_fast(const ScanArgs &a, SC &sc, uint32_t ws, uint32_t rs)
-{
-    uint32_t s = a.root;
-    uint2 cur = ld_group<W>(a.text, ws);
-    uint2 nxt = (ws + W <= rs) ? ld_group<W>(a.text, ws + W) : cur;
-    for (uint32_t i = ws; i < rs; i += W) {
-        uint2 nn = nxt;
-        if (i + 2u * W <= rs) nn = ld_group<W>(a.text, i + 2u * W);
-#pragma unroll
-        for (int j = 0; j < W; ++j) s = dfa_step(sc, s, pair_byte(cur, j));
-        cur = nxt; nxt = nn;
+// Branch-free automaton step for the verify kernel.  Row `win_rows` of the shared-memory window is all
+// zero, states outside the window are clamped onto it, and a zero entry means "ask the full table".
+template <typename E, bool RANGE>
+struct Stepper {
+    const E *gtab;
+    uint32_t s_tab;          // shared-window byte address of row win_lo
+    uint32_t s_cls;
+    uint32_t row_bytes, ncls, win_lo, win_rows, lo, n_used, final_bound, root;
+
+    __device__ __forceinline__ uint32_t step(uint32_t s, uint32_t b) const
+    {
+        uint32_t c;
+        if (RANGE) c = min(b - lo, n_used);
+        else asm("ld.shared.u8 %0, [%1];" : "=r"(c) : "r"(s_cls + b));
+        const uint32_t row = min(s - win_lo, win_rows);
+        uint32_t e;
+        if (sizeof(E) == 2) asm("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(s_tab + row * row_bytes + c * 2u));
+        else asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(s_tab + row * row_bytes + c * 4u));
+        ldg_if_zero<E>(e, gtab, s, ncls, c);
+        return e;
     }
+};
+
+// per-lane event record of one item
+struct ItemEvents { uint32_t cnt, e0p, e0s; };
+
+// The W end offsets owned by flagged word k are rs+1 .. rs+W with rs = W(k+1).  K such words are verified in
+// lockstep: each walk starts `warm` bytes before rs, is reset to the root where its haystack starts (w0[k], a
+// multiple of W inside [rs-warm, rs)), and reports the final states reached inside [rs, rs+W).  The caller
+// guarantees that every window [rs-warm, rs+W) lies inside the stream and that [w0, rs+W) lies inside one
+// haystack.  Unused slots simply repeat a valid walk and are ignored.
+template <int W, int K, typename ST>
+__device__ __forceinline__ void walk_words_lockstep(const ST &st, const uint8_t *text, uint32_t warm,
+                                                    const uint32_t (&rs)[K], const uint32_t (&w0)[K],
+                                                    ItemEvents (&ev)[K])
+{
+    uint32_t s[K];
+    uint2 cur[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        s[k] = st.root;
+        cur[k] = ld_group<W>(text, rs[k] - warm);
+    }
+    for (uint32_t off = warm; off > 0; off -= W) {          // this group starts at rs - off
+        uint2 nxt[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            nxt[k] = ld_group<W>(text, rs[k] - off + W);    // the next group (the last one is the report group)
+            if (rs[k] - off == w0[k]) s[k] = st.root;       // bytes before the haystack start do not count
+        }
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                s[k] = st.step(s[k], __byte_perm((j < 4) ? cur[k].x : cur[k].y, 0, 0x4440 | (j & 3)));
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) cur[k] = nxt[k];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) ev[k] = ItemEvents{0, 0, 0};
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-        s = dfa_step(sc, s, pair_byte(cur, j));
-        if (s < a.final_bound) sc.template hit<EMIT>(rs + j + 1u, s);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            s[k] = st.step(s[k], __byte_perm((j < 4) ? cur[k].x : cur[k].y, 0, 0x4440 | (j & 3)));
+            const bool f = s[k] < st.final_bound;
+            if (f && ev[k].cnt == 0) { ev[k].e0p = rs[k] + j + 1u; ev[k].e0s = s[k]; }
+            ev[k].cnt += f ? 1u : 0u;
+        }
     }
 }
 
-// General version: haystack starts inside the window reset the state, the window may be clipped at the
-// end of the stream, nothing is read past `readable`.  rs = 0xffffffff: report nothing (end-state walk).
-template <int W, bool EMIT, typename SC>
-__device__ __forceinline__ uint32_t walk_word_careful(const ScanArgs &a, SC &sc, uint32_t ws, uint32_t rs, uint32_t re)
+// Everything else, out of line (rare): a flagged word whose window contains a haystack start or is clipped
+// by the end of the stream, and span items (a 512-byte span of a densely flagged tile, walked like an
+// ac_scan_kernel slice).  rs == 0xffffffff: report nothing, return the end state in e0s (end-state walk).
+template <typename E, bool RANGE, int W, bool EMIT>
+__device__ __noinline__ ItemEvents walk_item_slow(const ScanArgs &a, uint32_t s_tab_addr, uint32_t s_cls_addr,
+                                                  uint32_t item, uint32_t ws, uint32_t rs, uint32_t re, uint32_t obase)
 {
+    Scanner<E, RANGE, false> sc;
+    sc.gtab = static_cast<const E *>(a.table); sc.text = a.text;
+    sc.ncls = a.ncls; sc.row_bytes = a.ncls * (uint32_t)sizeof(E);
+    sc.win_lo = a.win_lo; sc.win_rows = a.win_rows;
+    sc.s_tab = s_tab_addr - a.win_lo * sc.row_bytes;
+    sc.s_cls = s_cls_addr;
+    sc.lo = a.range_lo; sc.n_used = a.n_used;
+    sc.final_bound = a.final_bound; sc.readable = a.readable;
+    sc.out = a.out; sc.cap = a.capacity;
+    sc.found = false; sc.cnt = 0; sc.obase = obase;
+    sc.e0p = sc.e0s = sc.e1p = sc.e1s = 0;
+
+    if (item != ITEM_NONE && (item & ITEM_SPAN)) {
+        const uint32_t cs = (item & ~ITEM_SPAN) * SPAN_BYTES;
+        const uint32_t ce = min(cs + SPAN_BYTES, a.total);
+        const uint32_t h = find_haystack(a, cs);
+        const uint32_t hb = hay_begin(a, h);
+        uint32_t w0 = (cs - hb > a.halo) ? ((cs - a.halo) & ~15u) : hb;
+        if (w0 < hb) w0 = hb;
+        const uint32_t s_cs = sc.template walk<false, false>(a.root, w0, cs);
+        scan_slice<EMIT>(a, sc, s_cs, h, cs, ce);
+        return ItemEvents{sc.cnt, sc.e0p, sc.e0s};
+    }
+
     uint32_t h = find_haystack(a, ws);
     uint32_t nb = hay_end(a, h);
     uint32_t s = a.root;
     for (uint32_t i = ws; i < re; i += W) {
         const uint2 cur = ld_group_guarded<W>(a, i);
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < W; ++j) {
             const uint32_t ii = i + j;
             if (ii < re) {
@@ -218,277 +329,353 @@ __device__ __forceinline__ uint32_t walk_word_careful(const ScanArgs &a, SC &sc,
                     do { ++h; nb = hay_end(a, h); } while (nb == ii);
                     s = a.root;
                 }
-                s = dfa_step(sc, s, pair_byte(cur, j));
+                const uint32_t b = (((j < 4) ? cur.x : cur.y) >> ((j & 3) * 8)) & 0xffu;
+                if (s - sc.win_lo < sc.win_rows) {
+                    const uint32_t e = sc.hot_next(s, b);
+                    s = e ? e : sc.any_next(s, b);
+                } else {
+                    s = sc.any_next(s, b);
+                }
                 if (ii >= rs && s < a.final_bound) sc.template hit<EMIT>(ii + 1u, s);
             }
         }
     }
-    return s;
-}
-
-template <int W, bool EMIT, typename SC>
-__device__ __forceinline__ void walk_word(const ScanArgs &a, SC &sc, uint32_t k)
-{
-    const uint32_t rs = (k + 1u) * W;
-    if (rs >= a.total) return;                       // nothing ends after this word
-    const uint32_t re = min(rs + W, a.total);
-    const uint32_t ws = (rs > a.warm) ? rs - a.warm : 0u;
-    bool plain = (re == rs + W);
-    if (plain) {
-        const uint32_t h = find_haystack(a, ws);
-        plain = hay_end(a, h) >= re;
-    }
-    if (plain) walk_word_fast<W, EMIT>(a, sc, ws, rs);
-    else walk_word_careful<W, EMIT>(a, sc, ws, rs, re);
+    if (rs == 0xffffffffu) return ItemEvents{0, 0, s};
+    return ItemEvents{sc.cnt, sc.e0p, sc.e0s};
 }
 
 template <typename E, bool RANGE, int W>
-__global__ void __launch_bounds__(SCAN_THREADS, 1) ac_verify_kernel(const ScanArgs a)
+__global__ void __launch_bounds__(VERIFY_THREADS, 1) ac_verify_kernel(const __grid_constant__ ScanArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint8_t s_cls[256];
     constexpr int NB = 16 / W;
     constexpr uint32_t WORDS_PER_SPAN = 32u * NB;
-    constexpr int N_WARPS = SCAN_THREADS / 32;
-    constexpr int MAX_BATCHES = N_WARPS * VER_ROUNDS;
-
-    // dynamic shared memory: item list, scan scratch, then the table window
-    uint32_t *s_list = reinterpret_cast<uint32_t *>(smem_raw);
-    uint32_t *s_wcnt = s_list + VER_LIST_CAP;             // items per warp tile            [N_WARPS]
-    uint32_t *s_btot = s_wcnt + N_WARPS;                  // events per batch -> offsets    [MAX_BATCHES]
-    uint32_t *s_misc = s_btot + MAX_BATCHES;              // [0] offset of the chunk's run
-    E *s_tab = reinterpret_cast<E *>(smem_raw + VER_FIXED_SMEM);
-    static_assert((VER_LIST_CAP + N_WARPS + MAX_BATCHES + 4) * 4 <= VER_FIXED_SMEM, "scan scratch does not fit");
+    constexpr uint32_t TILE_SPANS = 32u * VT_SUB;
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
-    const uint32_t warp = tid >> 5;
+
+    // dynamic shared memory: per-warp item lists, then the table window
+    uint32_t *my_list = reinterpret_cast<uint32_t *>(smem_raw) + (tid >> 5) * VT_LIST_CAP;
+    E *s_tab = reinterpret_cast<E *>(smem_raw + VER_FIXED_SMEM);
     const E *gtab = static_cast<const E *>(a.table);
 
-    const uint32_t win_entries = a.win_rows * a.ncls;
-    const uint32_t win_first = a.win_lo * a.ncls;
-    for (uint32_t idx = tid; idx < win_entries; idx += SCAN_THREADS) {
-        uint32_t e = gtab[win_first + idx];
-        if (e - a.win_lo >= a.win_rows) e = 0;
-        s_tab[idx] = (E)e;
+    // window rows (targets outside the window replaced by 0) plus one all-zero row behind them
+    {
+        constexpr uint32_t PER = 16 / sizeof(E);           // entries per 16-byte load
+        const uint32_t win_entries = a.win_rows * a.ncls;
+        const uint32_t win_first = a.win_lo * a.ncls;
+        const uint32_t lead = min((PER - (win_first % PER)) % PER, win_entries);   // entries before the first aligned group
+        for (uint32_t idx = tid; idx < lead; idx += VERIFY_THREADS) {
+            uint32_t e = gtab[win_first + idx];
+            if (e - a.win_lo >= a.win_rows) e = 0;
+            s_tab[idx] = (E)e;
+        }
+        const uint32_t n_vec = (win_entries - lead) / PER;
+        const uint4 *src = reinterpret_cast<const uint4 *>(gtab + win_first + lead);
+        for (uint32_t v = tid; v < n_vec; v += VERIFY_THREADS) {
+            const uint4 q = __ldg(src + v);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (sizeof(E) == 2) {
+                    uint32_t lo = w[k] & 0xffffu, hi = w[k] >> 16;
+                    if (lo - a.win_lo >= a.win_rows) lo = 0;
+                    if (hi - a.win_lo >= a.win_rows) hi = 0;
+                    s_tab[lead + v * PER + 2 * k] = (E)lo;
+                    s_tab[lead + v * PER + 2 * k + 1] = (E)hi;
+                } else {
+                    uint32_t e = w[k];
+                    if (e - a.win_lo >= a.win_rows) e = 0;
+                    s_tab[lead + v * PER + k] = (E)e;
+                }
+            }
+        }
+        for (uint32_t idx = lead + n_vec * PER + tid; idx < win_entries + a.ncls; idx += VERIFY_THREADS) {
+            uint32_t e = 0;
+            if (idx < win_entries) {
+                e = gtab[win_first + idx];
+                if (e - a.win_lo >= a.win_rows) e = 0;
+            }
+            s_tab[idx] = (E)e;
+        }
     }
     if (tid < 256) s_cls[tid] = a.cls_map[tid];
-    __syncthreads();
+    __syncthreads();          // the only CTA-wide barrier: from here on warps run independently
 
-    Scanner<E, RANGE, false> sc;
-    sc.gtab = gtab; sc.text = a.text;
-    sc.ncls = a.ncls; sc.row_bytes = a.ncls * (uint32_t)sizeof(E);
-    sc.win_lo = a.win_lo; sc.win_rows = a.win_rows;
-    {
-        const uint32_t t0 = (uint32_t)__cvta_generic_to_shared(s_tab) - a.win_lo * sc.row_bytes;
-        const uint32_t c0 = (uint32_t)__cvta_generic_to_shared(s_cls);
-        asm volatile("mov.u32 %0, %1;" : "=r"(sc.s_tab) : "r"(t0));
-        asm volatile("mov.u32 %0, %1;" : "=r"(sc.s_cls) : "r"(c0));
-    }
-    sc.lo = a.range_lo; sc.n_used = a.n_used;
-    sc.final_bound = a.final_bound; sc.readable = a.readable;
-    sc.out = a.out; sc.cap = a.capacity;
-    sc.found = false;
+    Stepper<E, RANGE> st;
+    st.gtab = gtab;
+    st.row_bytes = a.ncls * (uint32_t)sizeof(E); st.ncls = a.ncls;
+    st.win_lo = a.win_lo; st.win_rows = a.win_rows;
+    st.lo = a.range_lo; st.n_used = a.n_used;
+    st.final_bound = a.final_bound; st.root = a.root;
+    const uint32_t s_tab_addr = (uint32_t)__cvta_generic_to_shared(s_tab);
+    const uint32_t s_cls_addr = (uint32_t)__cvta_generic_to_shared(s_cls);
+    asm volatile("mov.u32 %0, %1;" : "=r"(st.s_tab) : "r"(s_tab_addr));
+    asm volatile("mov.u32 %0, %1;" : "=r"(st.s_cls) : "r"(s_cls_addr));
 
-    const uint32_t n_chunks = (a.n_spans + CHUNK_SPANS - 1) / CHUNK_SPANS;
+    const uint32_t n_tiles = (a.n_spans + TILE_SPANS - 1) / TILE_SPANS;
+    const uint32_t n_warps = gridDim.x * (VERIFY_THREADS / 32);
+    const bool lockstep_ok = a.total >= a.warm + 2u * W;    // the stand-in walk of unused slots must be in bounds
     uint32_t dense_tiles = 0;
 
-    for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-        // ---- 1. flagged words of this warp's 32-span tile
-        const uint32_t span = chunk * CHUNK_SPANS + warp * 32u + lane;
-        const bool active = span < a.n_spans;
-        uint32_t planes[NB];
+    auto load_planes = [&](uint32_t tile, uint32_t (&pl)[VT_SUB][NB]) {
 #pragma unroll
-        for (int j = 0; j < NB; ++j) planes[j] = 0;
-        if (active) {
-            if (NB == 2) {
-                const uint2 m = __ldg(reinterpret_cast<const uint2 *>(a.mask) + span);
-                planes[0] = m.x; planes[1] = m.y;
-            } else {
-                const uint4 m = __ldg(reinterpret_cast<const uint4 *>(a.mask) + span);
-                planes[0] = m.x; planes[1] = m.y; planes[NB - 2] = m.z; planes[NB - 1] = m.w;
+        for (int q = 0; q < VT_SUB; ++q) {
+#pragma unroll
+            for (int j = 0; j < NB; ++j) pl[q][j] = 0;
+            const uint32_t span = tile * TILE_SPANS + q * 32u + lane;
+            if (tile < n_tiles && span < a.n_spans) {
+                if (NB == 2) {
+                    const uint2 m = __ldg(reinterpret_cast<const uint2 *>(a.mask) + span);
+                    pl[q][0] = m.x; pl[q][1] = m.y;
+                } else {
+                    const uint4 m = __ldg(reinterpret_cast<const uint4 *>(a.mask) + span);
+                    pl[q][0] = m.x; pl[q][1] = m.y; pl[q][NB - 2] = m.z; pl[q][NB - 1] = m.w;
+                }
             }
         }
-        uint32_t cnt = 0;
+    };
+
+    uint32_t tile = blockIdx.x * (VERIFY_THREADS / 32) + (tid >> 5);
+    uint32_t planes[VT_SUB][NB];
+    load_planes(tile, planes);
+    for (; tile < n_tiles; tile += n_warps) {
+        uint32_t next_planes[VT_SUB][NB];
+        load_planes(tile + n_warps, next_planes);      // in flight while this tile is verified
+
+        // ---- flagged words of the four sub-tiles, in stream order
+        uint32_t cnt[VT_SUB], incl[VT_SUB];
 #pragma unroll
-        for (int j = 0; j < NB; ++j) cnt += __popc(planes[j]);
-        uint32_t incl = cnt;
+        for (int q = 0; q < VT_SUB; ++q) {
+            cnt[q] = 0;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) cnt[q] += __popc(planes[q][j]);
+            incl[q] = cnt[q];
+        }
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
+#pragma unroll
+            for (int q = 0; q < VT_SUB; ++q) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl[q], d);
+                if (lane >= d) incl[q] += v;
+            }
         }
-        const uint32_t n_cand = __shfl_sync(0xffffffffu, incl, 31);
-        const bool dense = n_cand > a.dense_max;       // cheaper to walk the whole tile
-        const uint32_t n_act = __popc(__ballot_sync(0xffffffffu, active));
-        if (lane == 0) {
-            s_wcnt[warp] = dense ? n_act : n_cand;
+        uint32_t base[VT_SUB], n_cand = 0;
+        bool dense = false;
+#pragma unroll
+        for (int q = 0; q < VT_SUB; ++q) {
+            const uint32_t n_q = __shfl_sync(0xffffffffu, incl[q], 31);
+            base[q] = n_cand;
+            n_cand += n_q;
+            dense = dense || n_q > a.dense_max;        // cheaper to walk everything
+        }
+
+        if (n_cand) {                                   // warp-uniform
             if (dense) ++dense_tiles;
-        }
-        __syncthreads();
-
-        // ---- 2. ordered item list of the chunk
-        uint32_t n_items;
-        {
-            const uint32_t v = s_wcnt[lane];
-            uint32_t wincl = v;
+            else {
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, wincl, d);
-                if (lane >= d) wincl += t;
-            }
-            n_items = __shfl_sync(0xffffffffu, wincl, 31);
-            const uint32_t base = __shfl_sync(0xffffffffu, wincl - v, warp);
-            if (dense) {
-                if (active) s_list[base + lane] = ITEM_SPAN | span;
-            } else if (cnt) {
-                uint32_t at = base + incl - cnt;
-                uint32_t any = 0;
+                for (int q = 0; q < VT_SUB; ++q) {
+                    if (cnt[q]) {
+                        const uint32_t span = tile * TILE_SPANS + q * 32u + lane;
+                        uint32_t at = base[q] + incl[q] - cnt[q];
+                        uint32_t any = 0;
 #pragma unroll
-                for (int j = 0; j < NB; ++j) any |= planes[j];
-                while (any) {
-                    const uint32_t ch = __ffs(any) - 1;
-                    any &= any - 1;
+                        for (int j = 0; j < NB; ++j) any |= planes[q][j];
+                        while (any) {
+                            const uint32_t ch = __ffs(any) - 1;
+                            any &= any - 1;
 #pragma unroll
-                    for (int j = 0; j < NB; ++j)
-                        if ((planes[j] >> ch) & 1u) s_list[at++] = span * WORDS_PER_SPAN + ch * NB + j;
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- 3. one lane per item: count events (first one kept in registers)
-        const uint32_t n_batches = (n_items + 31u) >> 5;
-        uint32_t r_item[VER_ROUNDS], r_cnt[VER_ROUNDS], r_excl[VER_ROUNDS], r_e0p[VER_ROUNDS], r_e0s[VER_ROUNDS];
-#pragma unroll
-        for (int r = 0; r < VER_ROUNDS; ++r) {
-            r_item[r] = ITEM_NONE; r_cnt[r] = 0; r_excl[r] = 0; r_e0p[r] = 0; r_e0s[r] = 0;
-            const uint32_t b = warp + r * N_WARPS;
-            if (b < n_batches) {                       // warp-uniform
-                const uint32_t idx = b * 32u + lane;
-                const uint32_t item = (idx < n_items) ? s_list[idx] : ITEM_NONE;
-                sc.cnt = 0;
-                if (item == ITEM_NONE) {
-                } else if (item & ITEM_SPAN) {
-                    const uint32_t cs = (item & ~ITEM_SPAN) * SPAN_BYTES;
-                    const uint32_t ce = min(cs + SPAN_BYTES, a.total);
-                    const uint32_t h = find_haystack(a, cs);
-                    const uint32_t hb = hay_begin(a, h);
-                    uint32_t ws = (cs - hb > a.halo) ? ((cs - a.halo) & ~15u) : hb;
-                    if (ws < hb) ws = hb;
-                    const uint32_t s_cs = sc.template walk<false, false>(a.root, ws, cs);
-                    scan_slice<false>(a, sc, s_cs, h, cs, ce);
-                } else {
-                    walk_word<W, false>(a, sc, item);
+                            for (int j = 0; j < NB; ++j)
+                                if ((planes[q][j] >> ch) & 1u) my_list[at++] = span * WORDS_PER_SPAN + ch * NB + j;
+                        }
+                    }
                 }
                 __syncwarp();
-                uint32_t bincl = sc.cnt;
+            }
+
+            // ---- one lane per item, VT_LOCK batches at a time; every group of batches is one run of events
+            const uint32_t n_items = dense ? 32u * VT_SUB : n_cand;    // dense: batch q = sub-tile q, lane = span
+#pragma unroll 1
+            for (uint32_t g = 0; g * (32u * VT_LOCK) < n_items; ++g) {
+                uint32_t item[VT_LOCK];
+                ItemEvents res[VT_LOCK];
+#pragma unroll
+                for (int k = 0; k < VT_LOCK; ++k) res[k] = ItemEvents{0, 0, 0};
+
+                if (dense) {
+#pragma unroll 1
+                    for (int q = 0; q < VT_LOCK; ++q) {
+                        const uint32_t span = tile * TILE_SPANS + (g * VT_LOCK + q) * 32u + lane;
+                        const uint32_t it = (span < a.n_spans) ? (ITEM_SPAN | span) : ITEM_NONE;
+                        ItemEvents ev{0, 0, 0};
+                        if (it != ITEM_NONE)
+                            ev = walk_item_slow<E, RANGE, W, false>(a, s_tab_addr, s_cls_addr, it, 0u, 0u, 0u, 0u);
+#pragma unroll
+                        for (int k = 0; k < VT_LOCK; ++k) if (k == q) { res[k] = ev; item[k] = it; }
+                    }
+                } else {
+                    uint32_t rs[VT_LOCK], w0[VT_LOCK];
+                    bool plain[VT_LOCK], slow[VT_LOCK];
+                    uint32_t good_rs = 0, good_w0 = 0;
+                    bool have_good = false;
+#pragma unroll
+                    for (int k = 0; k < VT_LOCK; ++k) {
+                        const uint32_t idx = (g * VT_LOCK + k) * 32u + lane;
+                        item[k] = (idx < n_cand) ? my_list[idx] : ITEM_NONE;
+                        plain[k] = false; slow[k] = false; rs[k] = 0; w0[k] = 0;
+                        if (item[k] != ITEM_NONE) {
+                            rs[k] = (item[k] + 1u) * W;
+                            if (rs[k] < a.total) {         // else nothing ends after this word
+                                const uint32_t h = find_haystack(a, rs[k]);
+                                const uint32_t hb = hay_begin(a, h);
+                                w0[k] = (rs[k] >= a.warm && rs[k] - a.warm > hb) ? rs[k] - a.warm : hb;
+                                plain[k] = lockstep_ok && rs[k] >= a.warm && rs[k] + W <= a.total &&
+                                           hay_end(a, h) >= rs[k] + W && w0[k] < rs[k] &&
+                                           ((rs[k] - w0[k]) & (uint32_t)(W - 1)) == 0;
+                                slow[k] = !plain[k];
+                                if (plain[k]) { good_rs = rs[k]; good_w0 = w0[k]; have_good = true; }
+                            }
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, have_good)) {
+                        if (!have_good) { good_rs = a.warm; good_w0 = 0; }     // a harmless walk at the stream start
+#pragma unroll
+                        for (int k = 0; k < VT_LOCK; ++k)
+                            if (!plain[k]) { rs[k] = good_rs; w0[k] = good_w0; }
+                        ItemEvents ev[VT_LOCK];
+                        walk_words_lockstep<W, VT_LOCK>(st, a.text, a.warm, rs, w0, ev);
+#pragma unroll
+                        for (int k = 0; k < VT_LOCK; ++k) if (plain[k]) res[k] = ev[k];
+                    }
+                    // windows clipped by the stream ends or starting at an unaligned haystack start: out of line
+#pragma unroll 1
+                    for (int k = 0; k < VT_LOCK; ++k) {
+                        bool sl = false; uint32_t it = 0;
+#pragma unroll
+                        for (int kk = 0; kk < VT_LOCK; ++kk) if (kk == k) { sl = slow[kk]; it = item[kk]; }
+                        if (sl) {
+                            const uint32_t rs1 = (it + 1u) * W;
+                            const uint32_t ws1 = (rs1 > a.warm) ? rs1 - a.warm : 0u;
+                            const ItemEvents ev1 = walk_item_slow<E, RANGE, W, false>(a, s_tab_addr, s_cls_addr, it, ws1, rs1,
+                                                                                      min(rs1 + W, a.total), 0u);
+#pragma unroll
+                            for (int kk = 0; kk < VT_LOCK; ++kk) if (kk == k) res[kk] = ev1;
+                        }
+                    }
+                }
+                __syncwarp();
+
+                // ---- the group's run: offsets inside it, its place in the event buffer
+                uint32_t ri[VT_LOCK];
+#pragma unroll
+                for (int k = 0; k < VT_LOCK; ++k) ri[k] = res[k].cnt;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xffffffffu, bincl, d);
-                    if (lane >= d) bincl += t;
+#pragma unroll
+                    for (int k = 0; k < VT_LOCK; ++k) {
+                        const uint32_t v = __shfl_up_sync(0xffffffffu, ri[k], d);
+                        if (lane >= d) ri[k] += v;
+                    }
                 }
-                if (lane == 31) s_btot[b] = bincl;
-                r_item[r] = item; r_cnt[r] = sc.cnt; r_excl[r] = bincl - sc.cnt; r_e0p[r] = sc.e0p; r_e0s[r] = sc.e0s;
-            }
-        }
-        __syncthreads();
-
-        // ---- 4. batch offsets inside the chunk's run; the run's place in the event buffer
-        if (warp == 0) {
-            constexpr int PER = MAX_BATCHES / 32;
-            uint32_t v[PER];
-            uint32_t sum = 0;
+                uint32_t total = 0, boff[VT_LOCK];
 #pragma unroll
-            for (int k = 0; k < PER; ++k) {
-                const uint32_t b = lane * PER + k;
-                v[k] = (b < n_batches) ? s_btot[b] : 0u;
-                sum += v[k];
-            }
-            uint32_t sincl = sum;
+                for (int k = 0; k < VT_LOCK; ++k) {
+                    boff[k] = total;
+                    total += __shfl_sync(0xffffffffu, ri[k], 31);
+                }
+                if (total) {                            // warp-uniform
+                    uint32_t run_base = 0;
+                    if (lane == 0) {
+                        run_base = atomicAdd(&a.counters[1], total);
+                        a.runs[tile * (VT_BATCHES / VT_LOCK) + g] = make_uint2(run_base, total);
+                    }
+                    run_base = __shfl_sync(0xffffffffu, run_base, 0);
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, sincl, d);
-                if (lane >= d) sincl += t;
-            }
-            uint32_t run = sincl - sum;
-#pragma unroll
-            for (int k = 0; k < PER; ++k) {
-                const uint32_t b = lane * PER + k;
-                if (b < n_batches) s_btot[b] = run;
-                run += v[k];
-            }
-            if (lane == 31) {
-                const uint32_t base = sincl ? atomicAdd(&a.counters[1], sincl) : 0u;
-                a.runs[chunk] = make_uint2(base, sincl);
-                s_misc[0] = base;
-            }
-        }
-        __syncthreads();
-
-        // ---- 5. emit
-        const uint32_t run_base = s_misc[0];
-#pragma unroll
-        for (int r = 0; r < VER_ROUNDS; ++r) {
-            if (r_cnt[r]) {
-                const uint32_t b = warp + r * N_WARPS;
-                const uint32_t off = run_base + s_btot[b] + r_excl[r];
-                if (r_cnt[r] == 1) {
-                    if (off < a.capacity) a.out[off] = make_uint2(r_e0p[r], r_e0s[r]);
-                } else if (off < a.capacity) {
-                    sc.obase = off;
-                    sc.cnt = 0;
-                    const uint32_t item = r_item[r];
-                    if (item & ITEM_SPAN) {
-                        const uint32_t cs = (item & ~ITEM_SPAN) * SPAN_BYTES;
-                        const uint32_t ce = min(cs + SPAN_BYTES, a.total);
-                        const uint32_t h = find_haystack(a, cs);
-                        const uint32_t hb = hay_begin(a, h);
-                        uint32_t ws = (cs - hb > a.halo) ? ((cs - a.halo) & ~15u) : hb;
-                        if (ws < hb) ws = hb;
-                        const uint32_t s_cs = sc.template walk<false, false>(a.root, ws, cs);
-                        scan_slice<true>(a, sc, s_cs, h, cs, ce);
-                    } else {
-                        walk_word<W, true>(a, sc, item);
+                    for (int k = 0; k < VT_LOCK; ++k) {
+                        if (res[k].cnt) {
+                            const uint32_t off = run_base + boff[k] + ri[k] - res[k].cnt;
+                            if (res[k].cnt == 1) {
+                                if (off < a.capacity) a.out[off] = make_uint2(res[k].e0p, res[k].e0s);
+                            } else if (off < a.capacity) {
+                                uint32_t ws1 = 0, rs1 = 0, re1 = 0;
+                                if (!(item[k] & ITEM_SPAN)) {
+                                    rs1 = (item[k] + 1u) * W;
+                                    re1 = min(rs1 + W, a.total);
+                                    ws1 = (rs1 > a.warm) ? rs1 - a.warm : 0u;
+                                }
+                                walk_item_slow<E, RANGE, W, true>(a, s_tab_addr, s_cls_addr, item[k], ws1, rs1, re1, off);
+                            }
+                        }
                     }
                 }
             }
+            __syncwarp();                               // the list is rewritten for the next tile
         }
-        // the next chunk's first barrier orders these reads before the scratch is overwritten
+#pragma unroll
+        for (int q = 0; q < VT_SUB; ++q)
+#pragma unroll
+            for (int j = 0; j < NB; ++j) planes[q][j] = next_planes[q][j];
     }
     if (lane == 0 && dense_tiles) atomicAdd(&a.counters[4], dense_tiles);
 
     // state at the end of the stream (keep=1 continuation): the last Lmax bytes decide it
-    if (a.want_end_state && blockIdx.x == gridDim.x - 1 && tid == SCAN_THREADS - 1) {
+    if (a.want_end_state && blockIdx.x == gridDim.x - 1 && tid == VERIFY_THREADS - 1) {
         const uint32_t back = a.halo + 1u;
         const uint32_t ws = (a.total > back) ? ((a.total - back) & ~(uint32_t)(W - 1)) : 0u;
-        a.counters[2] = walk_word_careful<W, false>(a, sc, ws, 0xffffffffu, a.total);
+        a.counters[2] = walk_item_slow<E, RANGE, W, false>(a, s_tab_addr, s_cls_addr, ITEM_NONE, ws, 0xffffffffu, a.total, 0u).e0s;
     }
 }
 
 // ------------------------------------------------------------ reorder -----
 
-// One CTA per chunk: the run's final offset is the number of events of all earlier chunks.
-__global__ void __launch_bounds__(REORDER_THREADS) ac_reorder_kernel(const uint2 *__restrict__ runs,
+// One CTA per 1024 tiles, one thread per tile.  A run's final offset is the number of events of all
+// earlier tiles: the CTA sums the earlier blocks' run lengths (a coalesced read of at most n_tiles words
+// from L2), scans its own 1024 lengths, then its warps copy their 32 runs cooperatively.
+__global__ void __launch_bounds__(RUNSCAN_THREADS) ac_reorder_kernel(const uint2 *__restrict__ runs, uint32_t n_tiles,
                                                                       const uint2 *__restrict__ tmp,
                                                                       uint2 *__restrict__ out, uint32_t capacity)
 {
-    __shared__ uint32_t s_part[REORDER_THREADS / 32];
-    const uint32_t chunk = blockIdx.x;
-    const uint2 run = runs[chunk];
-    if (run.y == 0) return;                            // CTA-uniform
+    __shared__ uint32_t s_warp[RUNSCAN_THREADS / 32];
+    __shared__ uint32_t s_prev[RUNSCAN_THREADS / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t first = blockIdx.x * RUNSCAN_THREADS;
+
     uint32_t part = 0;
-    for (uint32_t j = threadIdx.x; j < chunk; j += REORDER_THREADS) part += runs[j].y;
+    for (uint32_t j = tid; j < first; j += RUNSCAN_THREADS) part += runs[j].y;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-    if ((threadIdx.x & 31u) == 0) s_part[threadIdx.x >> 5] = part;
-    __syncthreads();
-    uint32_t excl = 0;
+    if (lane == 0) s_prev[warp] = part;
+
+    const uint32_t tile = first + tid;
+    const uint2 run = (tile < n_tiles) ? runs[tile] : make_uint2(0u, 0u);
+    uint32_t incl = run.y;
 #pragma unroll
-    for (int w = 0; w < REORDER_THREADS / 32; ++w) excl += s_part[w];
-    for (uint32_t i = threadIdx.x; i < run.y; i += REORDER_THREADS) {
-        const unsigned long long src = (unsigned long long)run.x + i, dst = (unsigned long long)excl + i;
-        if (src < capacity && dst < capacity) out[dst] = tmp[src];
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+#pragma unroll
+    for (int w = 0; w < RUNSCAN_THREADS / 32; ++w) {
+        base += s_prev[w];
+        if ((uint32_t)w < warp) base += s_warp[w];
+    }
+    const uint32_t dst0 = base + incl - run.y;
+
+    const uint32_t busy = __ballot_sync(0xffffffffu, run.y != 0);
+    for (uint32_t m = busy; m; m &= m - 1) {
+        const int src_lane = __ffs(m) - 1;
+        const uint32_t src = __shfl_sync(0xffffffffu, run.x, src_lane);
+        const uint32_t cnt = __shfl_sync(0xffffffffu, run.y, src_lane);
+        const uint32_t dst = __shfl_sync(0xffffffffu, dst0, src_lane);
+        for (uint32_t i = lane; i < cnt; i += 32u) {
+            const unsigned long long s_i = (unsigned long long)src + i, d_i = (unsigned long long)dst + i;
+            if (s_i < capacity && d_i < capacity) out[d_i] = tmp[s_i];
+        }
     }
 }
 

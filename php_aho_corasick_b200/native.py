@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libacb200.so")
+LIB_PATH = os.environ.get("ACB200_LIB") or os.path.join(_HERE, "libacb200.so")
 _lib = None
 
 

@@ -8,7 +8,8 @@ from php_aho_corasick_b200.native import Automaton
 mib = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 mode = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-needles, hay, off = W.cfg2(n_hay=256, hay_len=8192, planted_per_hay=8)
+planted = int(sys.argv[4]) if len(sys.argv) > 4 else 8
+needles, hay, off = W.cfg2(n_hay=256, hay_len=8192, planted_per_hay=planted)
 a = Automaton(0); a.add_php_order(needles); a.finalize(); a.set_filter(mode)
 k = (mib << 20) // hay.size
 big = torch.from_numpy(hay).to("cuda:0").repeat(k)
