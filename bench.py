@@ -10,8 +10,9 @@ bound) to 131,072 haystacks = 1 GiB per GPU (SURVEY.md §8d "steady-state varian
 256 x 8 KiB batch is timed too and reported under config.literal_256x8KiB.
 
 * value      device-timed whole-job throughput, haystacks resident in HBM (CUDA events, max over ranks)
-* roofline   scan kernel only: 1 algorithmic HBM byte per haystack byte / kernel time (library's own
-             CUDA events on the launching stream), against MEASURED_PEAKS.json hbm_gbs
+* roofline   the device kernels of one step (prefilter + verify + reorder, or the full-walk scan kernel):
+             1 algorithmic HBM byte per haystack byte / their summed duration (library's own CUDA events on
+             the launching stream), against MEASURED_PEAKS.json hbm_gbs; per-kernel figures alongside
 * e2e        the C-ABI call ac_trie_search_flat() with a pinned HOST buffer: H2D copy, scan, D2H of
              the event list and the host replay through the callback, all inside the timed region
 * cpu_baseline / --impl reference   the reference's own ac_trie_search (oracle/_ref, compiled from
@@ -191,6 +192,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--hays-per-gpu", type=int, default=HAYS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-filter", action="store_true", help="force the full automaton walk (ac_scan_kernel)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":
@@ -217,6 +219,8 @@ def main():
     aut.finalize()
     finalize_s = time.time() - t0
     inf = aut.info()
+    if args.no_filter:
+        aut.set_filter(-1)
 
     reps = max(1, args.hays_per_gpu // BLOCK_HAYS)
     n_hays = reps * BLOCK_HAYS
@@ -229,7 +233,7 @@ def main():
     sm = ShardedMatcher(aut)
 
     def step_resident():
-        ev = sm.scan_local_device(resident, offsets, stream=stream)
+        ev = sm.scan_local_device(resident, offsets, stream=stream, uniform_len=HAY_LEN)
         if world > 1:
             gather_packed_events(ev.contiguous(), 0)
         return ev.shape[0], aut.stats()
@@ -250,10 +254,16 @@ def main():
     wall0 = time.time()
     e0.record()
     kernel_ms, launches = 0.0, 0
+    filter_ms = verify_ms = reorder_ms = 0.0
+    filtered_steps = 0
     for _ in range(args.steps):
         n_events, st = step_resident()
         kernel_ms += st.kernel_ms
         launches += st.kernel_launches
+        filter_ms += st.filter_ms
+        verify_ms += st.verify_ms
+        reorder_ms += st.reorder_ms
+        filtered_steps += st.filtered
     e1.record()
     sync()
     wall1 = time.time()
@@ -296,13 +306,15 @@ def main():
     small_s = (time.time() - t0) / 50
 
     # ---- max over ranks
-    t = torch.tensor([elapsed_ms, kernel_ms, e2e_s, float(launches)], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms, kernel_ms, e2e_s, float(launches), filter_ms, verify_ms, reorder_ms],
+                     dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         elapsed_ms, kernel_ms, e2e_s = float(tmax[0]), float(tmax[1]), float(tmax[2])
+        filter_ms, verify_ms, reorder_ms = float(tmax[4]), float(tmax[5]), float(tmax[6])
         launches = int(tsum[3])
     ms_per_step = elapsed_ms / args.steps
     value = world * nbytes / (ms_per_step * 1e-3) / 1e9
@@ -311,24 +323,42 @@ def main():
     achieved = nbytes / (k_ms * 1e-3) / 1e9
     e2e_val = world * nbytes / e2e_s / 1e9
 
+    filtered = filtered_steps == args.steps
+    if filtered:
+        per = {}
+        for name, ms in (("ac_filter_kernel", filter_ms), ("ac_verify_kernel", verify_ms), ("ac_reorder_kernel", reorder_ms)):
+            m = ms / args.steps
+            per[name] = {"ms": m, "GBps": nbytes / (m * 1e-3) / 1e9 if m else None,
+                         "frac_of_peak": nbytes / (m * 1e-3) / 1e9 / peak if m else None}
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ncu_traffic("cfg2_1GiB_filtered"), "peak_source": peak_src,
+                    "kernel": "ac_filter_kernel + ac_verify_kernel + ac_reorder_kernel (the device kernels of one step)",
+                    "kernel_ms": k_ms, "algorithmic_bytes_per_launch": nbytes, "per_kernel": per,
+                    "note": "1 HBM byte per haystack byte over the summed duration of the step's three kernels. "
+                            "ac_filter_kernel is the only one that streams the haystack (HBM-bound); "
+                            "ac_verify_kernel walks the automaton around ~2% of the words and is latency-bound "
+                            "(dependent shared-memory lookups, random 24-byte reads) — see DESIGN.md"}
+    else:
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ncu_traffic("cfg2_1GiB"), "peak_source": peak_src,
+                    "kernel": "ac_scan_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": nbytes,
+                    "note": "1 HBM byte per haystack byte; the kernel is bound by dependent shared-memory table "
+                            "lookups (bank-conflicted LDS), not by HBM — see DESIGN.md"}
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": dict(workload_config(world, nbytes),
+                       path="gram prefilter + verify" if filtered else "full automaton walk",
                        automaton={"states": int(inf.n_states), "classes": int(inf.n_classes),
+                                  "prefilter_word": int(inf.filter_word), "prefilter_l1_fill": float(inf.filter_l1_fill),
                                   "entry_bytes": int(inf.entry_bytes), "table_bytes": int(inf.table_bytes),
                                   "finalize_s": round(finalize_s, 4)},
                        events_per_step_per_gpu=int(n_events),
                        literal_256x8KiB={"bytes": BLOCK_HAYS * HAY_LEN, "call_us": small_s * 1e6,
                                          "kernel_us": small_kernel_ms / 50 * 1e3,
                                          "GBps": BLOCK_HAYS * HAY_LEN / small_s / 1e9}),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic("cfg2_1GiB"), "peak_source": peak_src,
-                     "kernel": "ac_scan_kernel", "kernel_ms": k_ms,
-                     "algorithmic_bytes_per_launch": nbytes,
-                     "note": "1 HBM byte per haystack byte; the kernel is bound by dependent shared-memory table "
-                             "lookups (bank-conflicted LDS), not by HBM — see DESIGN.md"},
+        "roofline": roofline,
         "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": int(nbytes),
                 "d2h_bytes_per_step": int(tally.events * 8 + 16), "ms_per_step": e2e_s * 1e3,
                 "h2d_ms": h2d_ms / e2e_steps, "d2h_ms": d2h_ms / e2e_steps, "steps": e2e_steps,

@@ -188,6 +188,12 @@ int acb200_search_device(AC_TRIE_t *thiz, const void *d_bytes,
                          void *stream, const void **d_events,
                          size_t *n_events);
 
+/* Same for a batch of n haystacks of EQUAL length hay_len laid end to end (no offsets array:
+ * nothing on the host is proportional to n).                                          */
+int acb200_search_device_uniform(AC_TRIE_t *thiz, const void *d_bytes, size_t n,
+                                 size_t hay_len, int first_only, void *stream,
+                                 const void **d_events, size_t *n_events);
+
 /* Copies up to max_events packed {uint32 end_in_buffer, uint32 state} records of the most recent
  * device-resident search into the caller's DEVICE buffer `d_dst` (async on `stream`, NULL = the
  * handle's stream).  Returns the number of records copied, or -1.                      */

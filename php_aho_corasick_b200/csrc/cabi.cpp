@@ -204,6 +204,17 @@ int acb200_search_device(AC_TRIE_t *t, const void *d_bytes, const uint64_t *offs
     return 0;
 }
 
+int acb200_search_device_uniform(AC_TRIE_t *t, const void *d_bytes, size_t n, size_t hay_len,
+                                 int first_only, void *stream, const void **d_events, size_t *n_events)
+{
+    if (t->open) { set_error("automaton is not finalized"); return -1; }
+    if (!t->device_ok) return -1;
+    if (!t->engine.scan_device_uniform(d_bytes, n, hay_len, first_only != 0, stream)) return -1;
+    if (d_events) *d_events = t->engine.device_events();
+    if (n_events) *n_events = t->engine.n_events();
+    return 0;
+}
+
 long acb200_copy_events(AC_TRIE_t *t, void *d_dst, size_t max_events, void *stream)
 {
     if (t->open || !t->device_ok) { set_error("automaton is not finalized"); return -1; }

@@ -58,9 +58,10 @@ void Engine::release()
     if (stream_) cudaStreamSynchronize(S(stream_));
     cudaFree(d_table_); cudaFree(d_cls_); cudaFree(d_text_); cudaFree(d_off_);
     cudaFree(d_first_); cudaFree(d_events_); cudaFree(d_tiles_); cudaFree(d_counters_);
-    cudaFree(d_l1_); cudaFree(d_l2_); cudaFree(d_mask_); cudaFree(d_runs_); cudaFree(d_events_tmp_);
-    d_l1_ = nullptr; d_l2_ = nullptr; d_mask_ = nullptr; mask_cap_ = 0; d_runs_ = nullptr; runs_cap_ = 0;
-    d_events_tmp_ = nullptr; events_tmp_cap_ = 0;
+    cudaFree(d_l1_); cudaFree(d_l2_); cudaFree(d_mask_);
+    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_);
+    d_l1_ = nullptr; d_l2_ = nullptr; d_mask_ = nullptr; mask_cap_ = 0;
+    d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; verify_tiles_cap_ = 0;
     if (h_counters_) cudaFreeHost(h_counters_);
     if (h_events_) cudaFreeHost(h_events_);
     if (h_stage_) cudaFreeHost(h_stage_);
@@ -211,14 +212,6 @@ bool Engine::build(const FlatAutomaton &f)
         CU_OK(cudaFuncSetAttribute(ac_filter_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
         CU_OK(cudaFuncSetAttribute(ac_filter_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
         CU_OK(cudaFuncSetAttribute(ac_filter_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
-        CU_OK(cudaFuncSetAttribute(ac_verify_kernel<uint16_t, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-        CU_OK(cudaFuncSetAttribute(ac_verify_kernel<uint16_t, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-        CU_OK(cudaFuncSetAttribute(ac_verify_kernel<uint32_t, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-        CU_OK(cudaFuncSetAttribute(ac_verify_kernel<uint32_t, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-        CU_OK(cudaFuncSetAttribute(ac_verify_kernel<uint16_t, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-        CU_OK(cudaFuncSetAttribute(ac_verify_kernel<uint16_t, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-        CU_OK(cudaFuncSetAttribute(ac_verify_kernel<uint32_t, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-        CU_OK(cudaFuncSetAttribute(ac_verify_kernel<uint32_t, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     }
     info.filter_word = (int32_t)filter_w_;
     info.min_pattern_len = f.min_pattern_len;
@@ -291,22 +284,18 @@ bool Engine::ensure_mask(size_t words)
     return true;
 }
 
-bool Engine::ensure_runs(size_t n)
+// scratch of the verify kernels, sized by the number of 16 KiB tiles
+bool Engine::ensure_verify_scratch(size_t n_tiles)
 {
-    if (n <= runs_cap_) return true;
-    cudaFree(d_runs_); d_runs_ = nullptr; runs_cap_ = 0;
-    const size_t cap = std::max(n + n / 4, (size_t)256);
-    CU_OK(cudaMalloc(&d_runs_, cap * 2 * sizeof(uint32_t)));      // {offset, count} per tile
-    runs_cap_ = cap;
-    return true;
-}
-
-bool Engine::ensure_events_tmp(size_t n)
-{
-    if (n <= events_tmp_cap_) return true;
-    cudaFree(d_events_tmp_); d_events_tmp_ = nullptr; events_tmp_cap_ = 0;
-    CU_OK(cudaMalloc(&d_events_tmp_, n * sizeof(PackedEvent)));
-    events_tmp_cap_ = n;
+    if (n_tiles <= verify_tiles_cap_) return true;
+    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_);
+    d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; verify_tiles_cap_ = 0;
+    const size_t cap = std::max(n_tiles + n_tiles / 4, (size_t)256);
+    CU_OK(cudaMalloc(&d_items_, cap * VER_DENSE_MAX * sizeof(uint32_t)));
+    CU_OK(cudaMalloc(&d_recs_, cap * VER_DENSE_MAX * 2 * sizeof(uint32_t)));
+    CU_OK(cudaMalloc(&d_desc_, cap * 2 * sizeof(uint32_t)));
+    CU_OK(cudaMalloc(&d_tile_len_, cap * sizeof(uint32_t)));
+    verify_tiles_cap_ = cap;
     return true;
 }
 
@@ -394,7 +383,7 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     // skips it for inputs too small to amortise a second launch and after a scan whose tiles were mostly
     // walked completely anyway.
     if (filter_w_ && tune_filter >= 0 && !first_only && (init_state == ROOT_STATE || init_state == root_)) {
-        const bool want = tune_filter > 0 || (total >= (1u << 20) && last_dense_frac_ < 0.5);
+        const bool want = tune_filter > 0 || (total >= (8u << 20) && last_dense_frac_ < 0.5);
         if (want) return launch_filtered(d_text, total, readable, n_hay, uniform_len, stream);
         last_dense_frac_ *= 0.5;      // re-probe the prefilter now and then
     }
@@ -511,14 +500,22 @@ static void launch_filter_k(const FilterArgs &fa, bool l2, unsigned grid, cudaSt
 }
 
 template <typename E, int W>
-static void launch_verify_k(const ScanArgs &a, bool range, unsigned grid, size_t smem, cudaStream_t st)
+static void launch_walk_k(const VerifyArgs &a, bool range, unsigned grid, cudaStream_t st)
 {
-    if (range) ac_verify_kernel<E, true, W><<<grid, VERIFY_THREADS, smem, st>>>(a);
-    else ac_verify_kernel<E, false, W><<<grid, VERIFY_THREADS, smem, st>>>(a);
+    if (range) ac_walk_kernel<E, true, W><<<grid, WALK_THREADS, 0, st>>>(a);
+    else ac_walk_kernel<E, false, W><<<grid, WALK_THREADS, 0, st>>>(a);
 }
 
-// ahocorasick_match() through the gram prefilter: ac_filter_kernel streams the haystack and flags
-// aligned words, ac_verify_kernel walks the automaton around the flagged words only.
+template <typename E, int W>
+static void launch_emit_k(const VerifyArgs &a, bool range, unsigned grid, cudaStream_t st)
+{
+    if (range) ac_emit_kernel<E, true, W><<<grid, EMIT_THREADS, 0, st>>>(a);
+    else ac_emit_kernel<E, false, W><<<grid, EMIT_THREADS, 0, st>>>(a);
+}
+
+// ahocorasick_match() through the gram prefilter: ac_filter_kernel streams the haystack and flags aligned
+// words; ac_collect_kernel / ac_walk_kernel / ac_tile_count_kernel / ac_emit_kernel walk the automaton
+// around the flagged words only and write the ordered event list.
 bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readable, size_t n_hay,
                              uint32_t uniform_len, void *stream)
 {
@@ -526,7 +523,7 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     const uint32_t W = filter_w_;
     const uint32_t NB = 16 / W;
     const uint32_t n_spans = (uint32_t)(((uint64_t)total + SPAN_BYTES - 1) / SPAN_BYTES);
-    const uint32_t n_tiles = (n_spans + 32 * VT_SUB - 1) / (32 * VT_SUB);      // 64 KiB warp tiles of the verify kernel
+    const uint32_t n_tiles = (n_spans + 31) / 32;      // 16 KiB tiles
     stats.chunk_bytes = SPAN_BYTES;
     stats.filtered = 1;
     if (events_cap_ == 0 && !ensure_events(std::max<size_t>(1 << 16, total / 64))) return false;
@@ -535,16 +532,7 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     const uint32_t warm = (halo_ + W - 1) / W * W;
     // walking a whole tile costs ~(512 + halo) steps per lane, a flagged word (warm + W) steps on one lane
     const uint32_t dense_max = std::max<uint32_t>(32u, std::min<uint32_t>(VER_DENSE_MAX, 32u * (SPAN_BYTES + halo_) / (warm + W)));
-    const uint32_t n_runs = n_tiles * (VT_BATCHES / VT_LOCK);   // one run of events per lockstep group of a tile
-    if (!ensure_runs(n_runs)) return false;
-
-    const int dyn_max = max_smem_optin_ - 2048;
-    const size_t row_bytes = (size_t)ncls_ * entry_bytes_;
-    size_t smem_budget = (size_t)dyn_max - VER_FIXED_SMEM - row_bytes - 16;  // one extra all-zero row
-    if (tune_smem_bytes) smem_budget = std::min<size_t>(smem_budget, tune_smem_bytes);
-    uint32_t win_lo = 0, win_rows = 0;
-    window_for(smem_budget, &win_lo, &win_rows);
-    const size_t smem_bytes = VER_FIXED_SMEM + ((size_t)win_rows + 1) * row_bytes + 16;
+    if (!ensure_verify_scratch(n_tiles)) return false;
 
     FilterArgs fa{};
     fa.text = (const uint8_t *)d_text;
@@ -555,7 +543,8 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     fa.n_spans = n_spans;
     fa.counters = d_counters_;
 
-    ScanArgs a{};
+    VerifyArgs va{};
+    ScanArgs &a = va.s;
     a.text = (const uint8_t *)d_text;
     a.hay_off = uniform_len ? nullptr : d_off_;
     a.n_hay = (uint32_t)n_hay;
@@ -572,31 +561,36 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     a.ncls = ncls_;
     a.final_bound = final_bound_;
     a.root = root_;
-    a.win_lo = win_lo;
-    a.win_rows = win_rows;
+    a.win_lo = final_bound_;
+    a.win_rows = 0;
     a.range_lo = range_lo_;
     a.n_used = n_used_;
     a.init_state = root_;
     a.tile_status = nullptr;
     a.counters = d_counters_;
     a.first_end = nullptr;
-    a.mask = d_mask_;
-    a.n_spans = n_spans;
-    a.dense_max = dense_max;
-    a.runs = (uint2 *)d_runs_;
-    a.warm = warm;
-    a.want_end_state = (n_hay == 1) ? 1u : 0u;
+    va.mask = d_mask_;
+    va.n_spans = n_spans;
+    va.n_tiles = n_tiles;
+    va.dense_max = dense_max;
+    va.warm = warm;
+    va.want_end_state = (n_hay == 1) ? 1u : 0u;
+    va.items = d_items_;
+    va.desc = (uint2 *)d_desc_;
+    va.recs = (uint2 *)d_recs_;
+    va.tile_len = d_tile_len_;
 
     const unsigned warps_per_cta = SCAN_THREADS / 32;
     const unsigned grid_f = std::min<uint32_t>((n_spans + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
-    const unsigned grid_v = std::min<uint32_t>((n_tiles + VERIFY_THREADS / 32 - 1) / (VERIFY_THREADS / 32), (uint32_t)n_sms_);
+    const unsigned tiles_per_cta = COLLECT_THREADS / 32;
+    const unsigned grid_c = std::min<uint32_t>((n_tiles + tiles_per_cta - 1) / tiles_per_cta, (uint32_t)n_sms_ * 8u);
+    const unsigned grid_w = (unsigned)n_sms_ * 8u;
+    const unsigned grid_e = (n_tiles + EMIT_THREADS - 1) / EMIT_THREADS;
 
     for (int attempt = 0; attempt < 2; ++attempt) {
-        if (!ensure_events_tmp(events_cap_)) return false;
-        a.out = (uint2 *)d_events_tmp_;        // runs in completion order; ac_reorder_kernel writes d_events_
+        a.out = (uint2 *)d_events_;
         a.capacity = (uint32_t)std::min<size_t>(events_cap_, 0xffffffffu);
         CU_OK(cudaMemsetAsync(d_counters_, 0, 32, st));
-        CU_OK(cudaMemsetAsync(d_runs_, 0, (size_t)n_runs * 2 * sizeof(uint32_t), st));
         CU_OK(cudaEventRecord(EV(ev_[0]), st));
         if (attempt == 0) {          // the bit planes survive a regrow of the event buffer
             if (W == 8) launch_filter_k<8>(fa, d_l2_ != nullptr, grid_f, st);
@@ -604,19 +598,27 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
             stats.kernel_launches += 1;
         }
         CU_OK(cudaEventRecord(EV(ev_[4]), st));
+        if (W == 8) ac_collect_kernel<8><<<grid_c, COLLECT_THREADS, 0, st>>>(va);
+        else ac_collect_kernel<4><<<grid_c, COLLECT_THREADS, 0, st>>>(va);
         if (entry_bytes_ == 2) {
-            if (W == 8) launch_verify_k<uint16_t, 8>(a, range_map_, grid_v, smem_bytes, st);
-            else launch_verify_k<uint16_t, 4>(a, range_map_, grid_v, smem_bytes, st);
+            if (W == 8) launch_walk_k<uint16_t, 8>(va, range_map_, grid_w, st);
+            else launch_walk_k<uint16_t, 4>(va, range_map_, grid_w, st);
         } else {
-            if (W == 8) launch_verify_k<uint32_t, 8>(a, range_map_, grid_v, smem_bytes, st);
-            else launch_verify_k<uint32_t, 4>(a, range_map_, grid_v, smem_bytes, st);
+            if (W == 8) launch_walk_k<uint32_t, 8>(va, range_map_, grid_w, st);
+            else launch_walk_k<uint32_t, 4>(va, range_map_, grid_w, st);
         }
         CU_OK(cudaEventRecord(EV(ev_[5]), st));
-        ac_reorder_kernel<<<(n_runs + RUNSCAN_THREADS - 1) / RUNSCAN_THREADS, RUNSCAN_THREADS, 0, st>>>(
-            (const uint2 *)d_runs_, n_runs, (const uint2 *)d_events_tmp_, (uint2 *)d_events_, a.capacity);
+        ac_tile_count_kernel<<<grid_c, COLLECT_THREADS, 0, st>>>(va);
+        if (entry_bytes_ == 2) {
+            if (W == 8) launch_emit_k<uint16_t, 8>(va, range_map_, grid_e, st);
+            else launch_emit_k<uint16_t, 4>(va, range_map_, grid_e, st);
+        } else {
+            if (W == 8) launch_emit_k<uint32_t, 8>(va, range_map_, grid_e, st);
+            else launch_emit_k<uint32_t, 4>(va, range_map_, grid_e, st);
+        }
         CU_OK(cudaGetLastError());
         CU_OK(cudaEventRecord(EV(ev_[1]), st));
-        stats.kernel_launches += 2;
+        stats.kernel_launches += 4;
         CU_OK(cudaMemcpyAsync(h_counters_, d_counters_, 32, cudaMemcpyDeviceToHost, st));
         CU_OK(cudaStreamSynchronize(st));
         float ms_f = 0, ms_v = 0, ms_r = 0;
@@ -663,6 +665,18 @@ bool Engine::scan_device(const void *d_bytes, const uint64_t *offsets, size_t n,
     if (!uniform_len && stream && S(stream) != S(stream_)) CU_OK(cudaStreamSynchronize(S(stream_)));
     stats.h2d_ms = 0; stats.d2h_ms = 0;
     return launch_scan(d_bytes, (uint32_t)total, (uint32_t)total, n, uniform_len, first_only, init_state, stream);
+}
+
+bool Engine::scan_device_uniform(const void *d_bytes, size_t n, size_t hay_len, bool first_only, void *stream)
+{
+    if (device_ < 0) { set_error("automaton has no device table (finalize failed?)"); return false; }
+    CU_OK(cudaSetDevice(device_));
+    const uint64_t total = (uint64_t)n * hay_len;
+    if (total >= 0xffffff00ull) { set_error("haystack stream exceeds 4 GiB per call"); return false; }
+    if (((uintptr_t)d_bytes & 15u) != 0) { set_error("device haystack pointer must be 16-byte aligned"); return false; }
+    stats.h2d_ms = 0; stats.d2h_ms = 0;
+    const uint32_t uniform_len = (n <= 1 || total == 0) ? (uint32_t)std::max<uint64_t>(total, 1) : (uint32_t)hay_len;
+    return launch_scan(d_bytes, (uint32_t)total, (uint32_t)total, std::max<size_t>(n, 1), uniform_len, first_only, ROOT_STATE, stream);
 }
 
 bool Engine::scan_host(const char *bytes, const uint64_t *offsets, size_t n, bool first_only,

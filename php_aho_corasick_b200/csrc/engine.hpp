@@ -37,6 +37,9 @@ public:
     bool scan_device(const void *d_bytes, const uint64_t *offsets, size_t n, bool first_only,
                      uint32_t init_state, void *stream);
 
+    // n haystacks of equal length laid end to end
+    bool scan_device_uniform(const void *d_bytes, size_t n, size_t hay_len, bool first_only, void *stream);
+
     bool copy_events_to(void *d_dst, size_t n, void *stream);
     const PackedEvent *host_events() const { return h_events_; }
     const void *device_events() const { return d_events_; }
@@ -56,8 +59,7 @@ private:
     bool ensure_offsets(size_t n);
     bool ensure_tiles(size_t n);
     bool ensure_mask(size_t words);
-    bool ensure_runs(size_t n);
-    bool ensure_events_tmp(size_t n);
+    bool ensure_verify_scratch(size_t n_tiles);
     bool launch_filtered(const void *d_text, uint32_t total, uint32_t readable, size_t n_hay, uint32_t uniform_len,
                          void *stream);
     void window_for(size_t smem_budget, uint32_t *win_lo, uint32_t *win_rows) const;
@@ -87,8 +89,11 @@ private:
     uint32_t filter_w_ = 0, l1_bits_ = 0, l2_log2_ = 0;
     uint32_t *d_l1_ = nullptr, *d_l2_ = nullptr;
     uint32_t *d_mask_ = nullptr;  size_t mask_cap_ = 0;
-    uint32_t *d_runs_ = nullptr;  size_t runs_cap_ = 0;      // per chunk {offset, count} of its run of events
-    void *d_events_tmp_ = nullptr; size_t events_tmp_cap_ = 0;  // runs in completion order
+    uint32_t *d_items_ = nullptr;   // work items of the verify kernels
+    uint32_t *d_recs_ = nullptr;    // per item {first event state, count << 16 | relative end}
+    uint32_t *d_desc_ = nullptr;    // per 16 KiB tile {offset into items, count}
+    uint32_t *d_tile_len_ = nullptr;// per tile: events
+    size_t verify_tiles_cap_ = 0;
     double last_dense_frac_ = 0.0; // tiles the verify kernel had to walk completely, previous filtered scan
 
     // scratch

@@ -13,27 +13,29 @@
 //                     see FlatAutomaton) and writes one bit per word: "the W
 //                     end offsets after this word need a look".  No false
 //                     negatives by construction.
-//   ac_verify_kernel  a warp takes a 64 KiB tile of the stream at a time and needs
-//                     no other warp: its lanes turn the tile's bit planes into
-//                     an ordered list of work items (ballot / popc / prefix
-//                     sums) — one item per flagged word, or, when so many words
-//                     are flagged that walking all of the tile is cheaper, one
-//                     item per 512-byte span.  Then one lane per item, two
-//                     items per lane in lockstep (independent lookup chains
-//                     hide each other's latency): for a
-//                     flagged word the lane walks the automaton from the root
-//                     over the (Lmax-1)-byte warm-up plus the W bytes after the
-//                     word — exactly the halo argument of ac_scan_kernel, so
-//                     states and events are those of an uninterrupted walk; a
-//                     span item is walked like an ac_scan_kernel slice.  The
-//                     tile's events are written as one ordered run at an offset
-//                     taken from a global counter (no warp ever waits for
-//                     another one).
-//   ac_runs_scan_kernel / ac_reorder_kernel
-//                     prefix-sum the run lengths in tile order and copy the
-//                     runs there: the final event list is ascending, as the
-//                     callback contract requires.  The worst case costs what
-//                     the plain scan costs.
+//   ac_collect_kernel turns the bit planes into work items, one warp per 16 KiB
+//                     tile (ballot / popc / prefix sums): one item per flagged
+//                     word, or — when so many words of a tile are flagged that
+//                     walking all of it is cheaper — one item per 512-byte
+//                     span.  A tile's items are appended to one global list at
+//                     an offset taken from a counter; {offset, count} per tile.
+//   ac_walk_kernel    one thread per item, no shared memory, as many warps per
+//                     SM as registers allow (the walk is a chain of dependent
+//                     lookups: only parallelism hides it).  For a flagged word
+//                     the thread walks the automaton from the root over the
+//                     (Lmax-1)-byte warm-up plus the W bytes after the word —
+//                     exactly the halo argument of ac_scan_kernel, so states
+//                     and events are those of an uninterrupted walk; the table
+//                     rows of the shallow states this touches live in L1.  A
+//                     span item is walked like an ac_scan_kernel slice.  Result
+//                     per item: event count + first event.
+//   ac_tile_count_kernel / ac_emit_kernel
+//                     sum the counts per tile, turn them into offsets (every
+//                     CTA adds up the lengths of all earlier tiles itself — no
+//                     CTA waits for another one) and write the events straight
+//                     to their final, ascending place, as the callback
+//                     contract requires.  The worst case costs about what the
+//                     plain scan costs.
 //
 // Replaces the same reference loop as ac_scan_kernel
 // (src/multifast/ahocorasick.c:199-234); events are bit-identical.
@@ -49,22 +51,9 @@ constexpr int FILTER_UNROLL = 4;           // 16-byte loads in flight per thread
 constexpr uint32_t VER_DENSE_MAX = 64;     // flagged words per 16 KiB tile beyond which the whole tile is walked
 constexpr uint32_t ITEM_SPAN = 0x80000000u;// work item: walk 512-byte span (item & ~ITEM_SPAN) completely
 constexpr uint32_t ITEM_NONE = 0xffffffffu;
-constexpr int VERIFY_THREADS = 512;        // 16 warps: room for 128 registers per thread
-#ifndef ACB_VT_SUB
-#define ACB_VT_SUB 4
-#endif
-#ifndef ACB_VT_LOCK
-#define ACB_VT_LOCK 2
-#endif
-constexpr int VT_SUB = ACB_VT_SUB;         // 16 KiB sub-tiles per warp tile: a lane owns that many 512-byte spans
-constexpr int VT_LOCK = ACB_VT_LOCK;       // batches walked in lockstep
-constexpr int VT_BATCHES = VT_SUB * (int)VER_DENSE_MAX / 32;   // 8: batches of 32 items per warp tile at most
-constexpr uint32_t VT_LIST_CAP = VT_SUB * VER_DENSE_MAX;       // items per warp tile
-constexpr uint32_t VER_FIXED_SMEM = (VERIFY_THREADS / 32) * VT_LIST_CAP * 4u;   // per-warp item lists
-static_assert(VT_BATCHES % VT_LOCK == 0 && VT_SUB % VT_LOCK == 0, "lockstep groups must tile the batches and the sub-tiles");
-static_assert(VER_FIXED_SMEM % 16 == 0, "table window must stay 16-byte aligned");
-constexpr int REORDER_THREADS = 256;
-constexpr int RUNSCAN_THREADS = 1024;
+constexpr int COLLECT_THREADS = 256;
+constexpr int WALK_THREADS = 256;
+constexpr int EMIT_THREADS = 1024;         // one thread per tile in the offset scan, one warp per 32 tiles when emitting
 
 struct FilterArgs {
     const uint8_t *text;          // 16-byte aligned
@@ -171,7 +160,88 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const Filter
     if (lane < (uint32_t)NB && flagged) atomicAdd(&a.counters[3], flagged);
 }
 
-// ------------------------------------------------------------- verify -----
+// ------------------------------------------------------------ collect -----
+
+struct VerifyArgs {
+    ScanArgs s;                   // stream, automaton, event buffer (win_rows = 0: no shared-memory window)
+    const uint32_t *mask;         // bit planes written by ac_filter_kernel
+    uint32_t n_spans;             // 512-byte spans in the stream
+    uint32_t n_tiles;             // 16 KiB tiles = ceil(n_spans / 32)
+    uint32_t dense_max;           // more flagged words than this in a tile: hand on the tile's spans instead
+    uint32_t warm;                // warm-up bytes before a flagged word's end offsets (halo rounded up to W)
+    uint32_t want_end_state;      // also compute the state at the end of the stream (counters[2])
+    uint32_t *items;              // work items, tile runs in completion order (capacity n_tiles * VER_DENSE_MAX)
+    uint2 *desc;                  // per tile {offset into items, count}
+    uint2 *recs;                  // per item {state of the first event, count << 16 | first end - item origin}
+    uint32_t *tile_len;           // per tile: events
+};
+
+template <int W>
+__global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __grid_constant__ VerifyArgs a)
+{
+    constexpr int NB = 16 / W;
+    constexpr uint32_t WORDS_PER_SPAN = 32u * NB;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_warps = gridDim.x * (COLLECT_THREADS / 32);
+    uint32_t dense_tiles = 0;
+
+    for (uint32_t tile = blockIdx.x * (COLLECT_THREADS / 32) + (threadIdx.x >> 5); tile < a.n_tiles; tile += n_warps) {
+        const uint32_t span = tile * 32u + lane;
+        const bool active = span < a.n_spans;
+        uint32_t planes[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) planes[j] = 0;
+        if (active) {
+            if (NB == 2) {
+                const uint2 m = __ldg(reinterpret_cast<const uint2 *>(a.mask) + span);
+                planes[0] = m.x; planes[1] = m.y;
+            } else {
+                const uint4 m = __ldg(reinterpret_cast<const uint4 *>(a.mask) + span);
+                planes[0] = m.x; planes[1] = m.y; planes[NB - 2] = m.z; planes[NB - 1] = m.w;
+            }
+        }
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) cnt += __popc(planes[j]);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const uint32_t n_cand = __shfl_sync(0xffffffffu, incl, 31);
+        const bool dense = n_cand > a.dense_max;       // cheaper to walk the whole tile
+        const uint32_t n_act = __popc(__ballot_sync(0xffffffffu, active));
+        const uint32_t n = dense ? n_act : n_cand;
+        uint32_t base = 0;
+        if (lane == 0) {
+            if (n) base = atomicAdd(&a.s.counters[5], n);
+            a.desc[tile] = make_uint2(base, n);
+        }
+        if (n == 0) continue;                           // warp-uniform
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (dense) {
+            ++dense_tiles;
+            if (active) a.items[base + lane] = ITEM_SPAN | span;
+        } else if (cnt) {
+            // flagged words of this lane's span in ascending stream order
+            uint32_t at = base + incl - cnt;
+            uint32_t any = 0;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) any |= planes[j];
+            while (any) {
+                const uint32_t ch = __ffs(any) - 1;
+                any &= any - 1;
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+                    if ((planes[j] >> ch) & 1u) a.items[at++] = span * WORDS_PER_SPAN + ch * NB + j;
+            }
+        }
+    }
+    if (lane == 0 && dense_tiles) atomicAdd(&a.s.counters[4], dense_tiles);
+}
+
+// --------------------------------------------------------------- walk -----
 
 // W aligned bytes of the stream as 32-bit words (second word unused for W = 4)
 template <int W>
@@ -191,112 +261,65 @@ __device__ __forceinline__ uint2 ld_group_guarded(const ScanArgs &a, uint32_t i)
     return make_uint2(w[0], w[1]);
 }
 
-// true table entry from HBM/L2, only where the shared-memory window answered 0
-template <typename E> __device__ __forceinline__ void ldg_if_zero(uint32_t &e, const E *gtab, uint32_t s, uint32_t ncls, uint32_t c);
-template <> __device__ __forceinline__ void ldg_if_zero<uint16_t>(uint32_t &e, const uint16_t *gtab, uint32_t s, uint32_t ncls, uint32_t c)
-{
-    asm("{\n\t.reg .pred p;\n\t.reg .u32 t;\n\t.reg .u64 a;\n\t"
-                 "setp.eq.u32 p, %0, 0;\n\t"
-                 "@p mad.lo.u32 t, %2, %3, %4;\n\t"
-                 "@p mad.wide.u32 a, t, 2, %1;\n\t"
-                 "@p ld.global.nc.u16 %0, [a];\n\t}"
-                 : "+r"(e) : "l"(gtab), "r"(s), "r"(ncls), "r"(c));
-}
-template <> __device__ __forceinline__ void ldg_if_zero<uint32_t>(uint32_t &e, const uint32_t *gtab, uint32_t s, uint32_t ncls, uint32_t c)
-{
-    asm("{\n\t.reg .pred p;\n\t.reg .u32 t;\n\t.reg .u64 a;\n\t"
-                 "setp.eq.u32 p, %0, 0;\n\t"
-                 "@p mad.lo.u32 t, %2, %3, %4;\n\t"
-                 "@p mad.wide.u32 a, t, 4, %1;\n\t"
-                 "@p ld.global.nc.u32 %0, [a];\n\t}"
-                 : "+r"(e) : "l"(gtab), "r"(s), "r"(ncls), "r"(c));
-}
-
-// Branch-free automaton step for the verify kernel.  Row `win_rows` of the shared-memory window is all
-// zero, states outside the window are clamped onto it, and a zero entry means "ask the full table".
+// One automaton step straight from the dense table: the rows of the shallow states a verification walk
+// visits stay in L1 (read-only path), deeper rows come from L2.
 template <typename E, bool RANGE>
 struct Stepper {
     const E *gtab;
-    uint32_t s_tab;          // shared-window byte address of row win_lo
-    uint32_t s_cls;
-    uint32_t row_bytes, ncls, win_lo, win_rows, lo, n_used, final_bound, root;
+    uint32_t s_cls;               // shared-window address of the 256-byte class map (unused when RANGE)
+    uint32_t ncls, lo, n_used, final_bound, root;
 
     __device__ __forceinline__ uint32_t step(uint32_t s, uint32_t b) const
     {
         uint32_t c;
         if (RANGE) c = min(b - lo, n_used);
         else asm("ld.shared.u8 %0, [%1];" : "=r"(c) : "r"(s_cls + b));
-        const uint32_t row = min(s - win_lo, win_rows);
-        uint32_t e;
-        if (sizeof(E) == 2) asm("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(s_tab + row * row_bytes + c * 2u));
-        else asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(s_tab + row * row_bytes + c * 4u));
-        ldg_if_zero<E>(e, gtab, s, ncls, c);
-        return e;
+        return (uint32_t)__ldg(gtab + (s * ncls + c));
     }
 };
 
-// per-lane event record of one item
+// per-item result
 struct ItemEvents { uint32_t cnt, e0p, e0s; };
 
-// The W end offsets owned by flagged word k are rs+1 .. rs+W with rs = W(k+1).  K such words are verified in
-// lockstep: each walk starts `warm` bytes before rs, is reset to the root where its haystack starts (w0[k], a
-// multiple of W inside [rs-warm, rs)), and reports the final states reached inside [rs, rs+W).  The caller
-// guarantees that every window [rs-warm, rs+W) lies inside the stream and that [w0, rs+W) lies inside one
-// haystack.  Unused slots simply repeat a valid walk and are ignored.
-template <int W, int K, typename ST>
-__device__ __forceinline__ void walk_words_lockstep(const ST &st, const uint8_t *text, uint32_t warm,
-                                                    const uint32_t (&rs)[K], const uint32_t (&w0)[K],
-                                                    ItemEvents (&ev)[K])
+// The W end offsets owned by flagged word k are rs+1 .. rs+W with rs = W(k+1): walk from the root over the
+// warm-up [w0, rs) — w0 a multiple of W, the whole window [w0, rs+W) inside one haystack and inside the
+// stream (the caller checked) — and report the final states reached inside [rs, rs+W).
+template <int W, typename ST>
+__device__ __forceinline__ ItemEvents walk_word_fast(const ST &st, const uint8_t *text, uint32_t w0, uint32_t rs)
 {
-    uint32_t s[K];
-    uint2 cur[K];
+    uint32_t s = st.root;
+    uint2 cur = ld_group<W>(text, w0);
+    for (uint32_t i = w0; i < rs; i += W) {
+        const uint2 nxt = ld_group<W>(text, i + W);        // the last one is the report group
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        s[k] = st.root;
-        cur[k] = ld_group<W>(text, rs[k] - warm);
+        for (int j = 0; j < W; ++j)
+            s = st.step(s, __byte_perm((j < 4) ? cur.x : cur.y, 0, 0x4440 | (j & 3)));
+        cur = nxt;
     }
-    for (uint32_t off = warm; off > 0; off -= W) {          // this group starts at rs - off
-        uint2 nxt[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            nxt[k] = ld_group<W>(text, rs[k] - off + W);    // the next group (the last one is the report group)
-            if (rs[k] - off == w0[k]) s[k] = st.root;       // bytes before the haystack start do not count
-        }
-#pragma unroll
-        for (int j = 0; j < W; ++j) {
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-                s[k] = st.step(s[k], __byte_perm((j < 4) ? cur[k].x : cur[k].y, 0, 0x4440 | (j & 3)));
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k) cur[k] = nxt[k];
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) ev[k] = ItemEvents{0, 0, 0};
+    ItemEvents ev{0, 0, 0};
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            s[k] = st.step(s[k], __byte_perm((j < 4) ? cur[k].x : cur[k].y, 0, 0x4440 | (j & 3)));
-            const bool f = s[k] < st.final_bound;
-            if (f && ev[k].cnt == 0) { ev[k].e0p = rs[k] + j + 1u; ev[k].e0s = s[k]; }
-            ev[k].cnt += f ? 1u : 0u;
-        }
+        s = st.step(s, __byte_perm((j < 4) ? cur.x : cur.y, 0, 0x4440 | (j & 3)));
+        const bool f = s < st.final_bound;
+        if (f && ev.cnt == 0) { ev.e0p = rs + j + 1u; ev.e0s = s; }
+        ev.cnt += f ? 1u : 0u;
     }
+    return ev;
 }
 
-// Everything else, out of line (rare): a flagged word whose window contains a haystack start or is clipped
-// by the end of the stream, and span items (a 512-byte span of a densely flagged tile, walked like an
-// ac_scan_kernel slice).  rs == 0xffffffff: report nothing, return the end state in e0s (end-state walk).
+// Everything else, out of line (rare): a flagged word whose window is clipped by the ends of the stream or
+// starts at an unaligned haystack start, and span items (a 512-byte span of a densely flagged tile, walked
+// like an ac_scan_kernel slice).  rs == 0xffffffff: report nothing, return the end state in e0s.
+// EMIT: events go to a.out[obase..).
 template <typename E, bool RANGE, int W, bool EMIT>
-__device__ __noinline__ ItemEvents walk_item_slow(const ScanArgs &a, uint32_t s_tab_addr, uint32_t s_cls_addr,
-                                                  uint32_t item, uint32_t ws, uint32_t rs, uint32_t re, uint32_t obase)
+__device__ __noinline__ ItemEvents walk_item_slow(const ScanArgs &a, uint32_t s_cls_addr, uint32_t item,
+                                                  uint32_t ws, uint32_t rs, uint32_t re, uint32_t obase)
 {
     Scanner<E, RANGE, false> sc;
     sc.gtab = static_cast<const E *>(a.table); sc.text = a.text;
     sc.ncls = a.ncls; sc.row_bytes = a.ncls * (uint32_t)sizeof(E);
-    sc.win_lo = a.win_lo; sc.win_rows = a.win_rows;
-    sc.s_tab = s_tab_addr - a.win_lo * sc.row_bytes;
+    sc.win_lo = a.win_lo; sc.win_rows = 0;               // no shared-memory window: every step reads the table
+    sc.s_tab = 0;
     sc.s_cls = s_cls_addr;
     sc.lo = a.range_lo; sc.n_used = a.n_used;
     sc.final_bound = a.final_bound; sc.readable = a.readable;
@@ -329,13 +352,7 @@ __device__ __noinline__ ItemEvents walk_item_slow(const ScanArgs &a, uint32_t s_
                     do { ++h; nb = hay_end(a, h); } while (nb == ii);
                     s = a.root;
                 }
-                const uint32_t b = (((j < 4) ? cur.x : cur.y) >> ((j & 3) * 8)) & 0xffu;
-                if (s - sc.win_lo < sc.win_rows) {
-                    const uint32_t e = sc.hot_next(s, b);
-                    s = e ? e : sc.any_next(s, b);
-                } else {
-                    s = sc.any_next(s, b);
-                }
+                s = sc.any_next(s, (((j < 4) ? cur.x : cur.y) >> ((j & 3) * 8)) & 0xffu);
                 if (ii >= rs && s < a.final_bound) sc.template hit<EMIT>(ii + 1u, s);
             }
         }
@@ -344,313 +361,102 @@ __device__ __noinline__ ItemEvents walk_item_slow(const ScanArgs &a, uint32_t s_
     return ItemEvents{sc.cnt, sc.e0p, sc.e0s};
 }
 
-template <typename E, bool RANGE, int W>
-__global__ void __launch_bounds__(VERIFY_THREADS, 1) ac_verify_kernel(const __grid_constant__ ScanArgs a)
+// origin of an item's end offsets: a record stores its first event's end relative to this
+template <int W>
+__device__ __forceinline__ uint32_t item_origin(uint32_t item)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    return (item & ITEM_SPAN) ? (item & ~ITEM_SPAN) * SPAN_BYTES : (item + 1u) * W;
+}
+
+template <typename E, bool RANGE, int W>
+__global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_constant__ VerifyArgs a)
+{
     __shared__ uint8_t s_cls[256];
-    constexpr int NB = 16 / W;
-    constexpr uint32_t WORDS_PER_SPAN = 32u * NB;
-    constexpr uint32_t TILE_SPANS = 32u * VT_SUB;
-
-    const uint32_t tid = threadIdx.x;
-    const uint32_t lane = tid & 31u;
-
-    // dynamic shared memory: per-warp item lists, then the table window
-    uint32_t *my_list = reinterpret_cast<uint32_t *>(smem_raw) + (tid >> 5) * VT_LIST_CAP;
-    E *s_tab = reinterpret_cast<E *>(smem_raw + VER_FIXED_SMEM);
-    const E *gtab = static_cast<const E *>(a.table);
-
-    // window rows (targets outside the window replaced by 0) plus one all-zero row behind them
-    {
-        constexpr uint32_t PER = 16 / sizeof(E);           // entries per 16-byte load
-        const uint32_t win_entries = a.win_rows * a.ncls;
-        const uint32_t win_first = a.win_lo * a.ncls;
-        const uint32_t lead = min((PER - (win_first % PER)) % PER, win_entries);   // entries before the first aligned group
-        for (uint32_t idx = tid; idx < lead; idx += VERIFY_THREADS) {
-            uint32_t e = gtab[win_first + idx];
-            if (e - a.win_lo >= a.win_rows) e = 0;
-            s_tab[idx] = (E)e;
-        }
-        const uint32_t n_vec = (win_entries - lead) / PER;
-        const uint4 *src = reinterpret_cast<const uint4 *>(gtab + win_first + lead);
-        for (uint32_t v = tid; v < n_vec; v += VERIFY_THREADS) {
-            const uint4 q = __ldg(src + v);
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (sizeof(E) == 2) {
-                    uint32_t lo = w[k] & 0xffffu, hi = w[k] >> 16;
-                    if (lo - a.win_lo >= a.win_rows) lo = 0;
-                    if (hi - a.win_lo >= a.win_rows) hi = 0;
-                    s_tab[lead + v * PER + 2 * k] = (E)lo;
-                    s_tab[lead + v * PER + 2 * k + 1] = (E)hi;
-                } else {
-                    uint32_t e = w[k];
-                    if (e - a.win_lo >= a.win_rows) e = 0;
-                    s_tab[lead + v * PER + k] = (E)e;
-                }
-            }
-        }
-        for (uint32_t idx = lead + n_vec * PER + tid; idx < win_entries + a.ncls; idx += VERIFY_THREADS) {
-            uint32_t e = 0;
-            if (idx < win_entries) {
-                e = gtab[win_first + idx];
-                if (e - a.win_lo >= a.win_rows) e = 0;
-            }
-            s_tab[idx] = (E)e;
-        }
-    }
-    if (tid < 256) s_cls[tid] = a.cls_map[tid];
-    __syncthreads();          // the only CTA-wide barrier: from here on warps run independently
+    if (threadIdx.x < 256) s_cls[threadIdx.x] = a.s.cls_map[threadIdx.x];
+    __syncthreads();
+    const uint32_t s_cls_addr = (uint32_t)__cvta_generic_to_shared(s_cls);
 
     Stepper<E, RANGE> st;
-    st.gtab = gtab;
-    st.row_bytes = a.ncls * (uint32_t)sizeof(E); st.ncls = a.ncls;
-    st.win_lo = a.win_lo; st.win_rows = a.win_rows;
-    st.lo = a.range_lo; st.n_used = a.n_used;
-    st.final_bound = a.final_bound; st.root = a.root;
-    const uint32_t s_tab_addr = (uint32_t)__cvta_generic_to_shared(s_tab);
-    const uint32_t s_cls_addr = (uint32_t)__cvta_generic_to_shared(s_cls);
-    asm volatile("mov.u32 %0, %1;" : "=r"(st.s_tab) : "r"(s_tab_addr));
-    asm volatile("mov.u32 %0, %1;" : "=r"(st.s_cls) : "r"(s_cls_addr));
+    st.gtab = static_cast<const E *>(a.s.table);
+    st.s_cls = s_cls_addr;
+    st.ncls = a.s.ncls; st.lo = a.s.range_lo; st.n_used = a.s.n_used;
+    st.final_bound = a.s.final_bound; st.root = a.s.root;
 
-    const uint32_t n_tiles = (a.n_spans + TILE_SPANS - 1) / TILE_SPANS;
-    const uint32_t n_warps = gridDim.x * (VERIFY_THREADS / 32);
-    const bool lockstep_ok = a.total >= a.warm + 2u * W;    // the stand-in walk of unused slots must be in bounds
-    uint32_t dense_tiles = 0;
-
-    auto load_planes = [&](uint32_t tile, uint32_t (&pl)[VT_SUB][NB]) {
-#pragma unroll
-        for (int q = 0; q < VT_SUB; ++q) {
-#pragma unroll
-            for (int j = 0; j < NB; ++j) pl[q][j] = 0;
-            const uint32_t span = tile * TILE_SPANS + q * 32u + lane;
-            if (tile < n_tiles && span < a.n_spans) {
-                if (NB == 2) {
-                    const uint2 m = __ldg(reinterpret_cast<const uint2 *>(a.mask) + span);
-                    pl[q][0] = m.x; pl[q][1] = m.y;
-                } else {
-                    const uint4 m = __ldg(reinterpret_cast<const uint4 *>(a.mask) + span);
-                    pl[q][0] = m.x; pl[q][1] = m.y; pl[q][NB - 2] = m.z; pl[q][NB - 1] = m.w;
-                }
+    const uint32_t n_items = a.s.counters[5];
+    const uint32_t n_threads = gridDim.x * WALK_THREADS;
+    for (uint32_t i = blockIdx.x * WALK_THREADS + threadIdx.x; i < n_items; i += n_threads) {
+        const uint32_t item = a.items[i];
+        ItemEvents ev{0, 0, 0};
+        if (item & ITEM_SPAN) {
+            ev = walk_item_slow<E, RANGE, W, false>(a.s, s_cls_addr, item, 0u, 0u, 0u, 0u);
+        } else {
+            const uint32_t rs = (item + 1u) * W;       // the W end offsets owned by word k are rs+1 .. rs+W
+            if (rs < a.s.total) {                      // else nothing ends after this word
+                const uint32_t re = min(rs + W, a.s.total);
+                const uint32_t ws = (rs > a.warm) ? rs - a.warm : 0u;
+                // a walk that would start before the haystack of byte rs starts at that haystack's
+                // first byte instead (the state there is the root by definition)
+                const uint32_t h = find_haystack(a.s, rs);
+                const uint32_t w0 = max(ws, hay_begin(a.s, h));
+                const bool plain = (re == rs + W) && hay_end(a.s, h) >= re &&
+                                   ((rs - w0) & (uint32_t)(W - 1)) == 0 && w0 < rs;
+                if (plain) ev = walk_word_fast<W>(st, a.s.text, w0, rs);
+                else ev = walk_item_slow<E, RANGE, W, false>(a.s, s_cls_addr, item, ws, rs, re, 0u);
             }
         }
-    };
-
-    uint32_t tile = blockIdx.x * (VERIFY_THREADS / 32) + (tid >> 5);
-    uint32_t planes[VT_SUB][NB];
-    load_planes(tile, planes);
-    for (; tile < n_tiles; tile += n_warps) {
-        uint32_t next_planes[VT_SUB][NB];
-        load_planes(tile + n_warps, next_planes);      // in flight while this tile is verified
-
-        // ---- flagged words of the four sub-tiles, in stream order
-        uint32_t cnt[VT_SUB], incl[VT_SUB];
-#pragma unroll
-        for (int q = 0; q < VT_SUB; ++q) {
-            cnt[q] = 0;
-#pragma unroll
-            for (int j = 0; j < NB; ++j) cnt[q] += __popc(planes[q][j]);
-            incl[q] = cnt[q];
-        }
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-            for (int q = 0; q < VT_SUB; ++q) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, incl[q], d);
-                if (lane >= d) incl[q] += v;
-            }
-        }
-        uint32_t base[VT_SUB], n_cand = 0;
-        bool dense = false;
-#pragma unroll
-        for (int q = 0; q < VT_SUB; ++q) {
-            const uint32_t n_q = __shfl_sync(0xffffffffu, incl[q], 31);
-            base[q] = n_cand;
-            n_cand += n_q;
-            dense = dense || n_q > a.dense_max;        // cheaper to walk everything
-        }
-
-        if (n_cand) {                                   // warp-uniform
-            if (dense) ++dense_tiles;
-            else {
-#pragma unroll
-                for (int q = 0; q < VT_SUB; ++q) {
-                    if (cnt[q]) {
-                        const uint32_t span = tile * TILE_SPANS + q * 32u + lane;
-                        uint32_t at = base[q] + incl[q] - cnt[q];
-                        uint32_t any = 0;
-#pragma unroll
-                        for (int j = 0; j < NB; ++j) any |= planes[q][j];
-                        while (any) {
-                            const uint32_t ch = __ffs(any) - 1;
-                            any &= any - 1;
-#pragma unroll
-                            for (int j = 0; j < NB; ++j)
-                                if ((planes[q][j] >> ch) & 1u) my_list[at++] = span * WORDS_PER_SPAN + ch * NB + j;
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-
-            // ---- one lane per item, VT_LOCK batches at a time; every group of batches is one run of events
-            const uint32_t n_items = dense ? 32u * VT_SUB : n_cand;    // dense: batch q = sub-tile q, lane = span
-#pragma unroll 1
-            for (uint32_t g = 0; g * (32u * VT_LOCK) < n_items; ++g) {
-                uint32_t item[VT_LOCK];
-                ItemEvents res[VT_LOCK];
-#pragma unroll
-                for (int k = 0; k < VT_LOCK; ++k) res[k] = ItemEvents{0, 0, 0};
-
-                if (dense) {
-#pragma unroll 1
-                    for (int q = 0; q < VT_LOCK; ++q) {
-                        const uint32_t span = tile * TILE_SPANS + (g * VT_LOCK + q) * 32u + lane;
-                        const uint32_t it = (span < a.n_spans) ? (ITEM_SPAN | span) : ITEM_NONE;
-                        ItemEvents ev{0, 0, 0};
-                        if (it != ITEM_NONE)
-                            ev = walk_item_slow<E, RANGE, W, false>(a, s_tab_addr, s_cls_addr, it, 0u, 0u, 0u, 0u);
-#pragma unroll
-                        for (int k = 0; k < VT_LOCK; ++k) if (k == q) { res[k] = ev; item[k] = it; }
-                    }
-                } else {
-                    uint32_t rs[VT_LOCK], w0[VT_LOCK];
-                    bool plain[VT_LOCK], slow[VT_LOCK];
-                    uint32_t good_rs = 0, good_w0 = 0;
-                    bool have_good = false;
-#pragma unroll
-                    for (int k = 0; k < VT_LOCK; ++k) {
-                        const uint32_t idx = (g * VT_LOCK + k) * 32u + lane;
-                        item[k] = (idx < n_cand) ? my_list[idx] : ITEM_NONE;
-                        plain[k] = false; slow[k] = false; rs[k] = 0; w0[k] = 0;
-                        if (item[k] != ITEM_NONE) {
-                            rs[k] = (item[k] + 1u) * W;
-                            if (rs[k] < a.total) {         // else nothing ends after this word
-                                const uint32_t h = find_haystack(a, rs[k]);
-                                const uint32_t hb = hay_begin(a, h);
-                                w0[k] = (rs[k] >= a.warm && rs[k] - a.warm > hb) ? rs[k] - a.warm : hb;
-                                plain[k] = lockstep_ok && rs[k] >= a.warm && rs[k] + W <= a.total &&
-                                           hay_end(a, h) >= rs[k] + W && w0[k] < rs[k] &&
-                                           ((rs[k] - w0[k]) & (uint32_t)(W - 1)) == 0;
-                                slow[k] = !plain[k];
-                                if (plain[k]) { good_rs = rs[k]; good_w0 = w0[k]; have_good = true; }
-                            }
-                        }
-                    }
-                    if (__any_sync(0xffffffffu, have_good)) {
-                        if (!have_good) { good_rs = a.warm; good_w0 = 0; }     // a harmless walk at the stream start
-#pragma unroll
-                        for (int k = 0; k < VT_LOCK; ++k)
-                            if (!plain[k]) { rs[k] = good_rs; w0[k] = good_w0; }
-                        ItemEvents ev[VT_LOCK];
-                        walk_words_lockstep<W, VT_LOCK>(st, a.text, a.warm, rs, w0, ev);
-#pragma unroll
-                        for (int k = 0; k < VT_LOCK; ++k) if (plain[k]) res[k] = ev[k];
-                    }
-                    // windows clipped by the stream ends or starting at an unaligned haystack start: out of line
-#pragma unroll 1
-                    for (int k = 0; k < VT_LOCK; ++k) {
-                        bool sl = false; uint32_t it = 0;
-#pragma unroll
-                        for (int kk = 0; kk < VT_LOCK; ++kk) if (kk == k) { sl = slow[kk]; it = item[kk]; }
-                        if (sl) {
-                            const uint32_t rs1 = (it + 1u) * W;
-                            const uint32_t ws1 = (rs1 > a.warm) ? rs1 - a.warm : 0u;
-                            const ItemEvents ev1 = walk_item_slow<E, RANGE, W, false>(a, s_tab_addr, s_cls_addr, it, ws1, rs1,
-                                                                                      min(rs1 + W, a.total), 0u);
-#pragma unroll
-                            for (int kk = 0; kk < VT_LOCK; ++kk) if (kk == k) res[kk] = ev1;
-                        }
-                    }
-                }
-                __syncwarp();
-
-                // ---- the group's run: offsets inside it, its place in the event buffer
-                uint32_t ri[VT_LOCK];
-#pragma unroll
-                for (int k = 0; k < VT_LOCK; ++k) ri[k] = res[k].cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-                    for (int k = 0; k < VT_LOCK; ++k) {
-                        const uint32_t v = __shfl_up_sync(0xffffffffu, ri[k], d);
-                        if (lane >= d) ri[k] += v;
-                    }
-                }
-                uint32_t total = 0, boff[VT_LOCK];
-#pragma unroll
-                for (int k = 0; k < VT_LOCK; ++k) {
-                    boff[k] = total;
-                    total += __shfl_sync(0xffffffffu, ri[k], 31);
-                }
-                if (total) {                            // warp-uniform
-                    uint32_t run_base = 0;
-                    if (lane == 0) {
-                        run_base = atomicAdd(&a.counters[1], total);
-                        a.runs[tile * (VT_BATCHES / VT_LOCK) + g] = make_uint2(run_base, total);
-                    }
-                    run_base = __shfl_sync(0xffffffffu, run_base, 0);
-#pragma unroll
-                    for (int k = 0; k < VT_LOCK; ++k) {
-                        if (res[k].cnt) {
-                            const uint32_t off = run_base + boff[k] + ri[k] - res[k].cnt;
-                            if (res[k].cnt == 1) {
-                                if (off < a.capacity) a.out[off] = make_uint2(res[k].e0p, res[k].e0s);
-                            } else if (off < a.capacity) {
-                                uint32_t ws1 = 0, rs1 = 0, re1 = 0;
-                                if (!(item[k] & ITEM_SPAN)) {
-                                    rs1 = (item[k] + 1u) * W;
-                                    re1 = min(rs1 + W, a.total);
-                                    ws1 = (rs1 > a.warm) ? rs1 - a.warm : 0u;
-                                }
-                                walk_item_slow<E, RANGE, W, true>(a, s_tab_addr, s_cls_addr, item[k], ws1, rs1, re1, off);
-                            }
-                        }
-                    }
-                }
-            }
-            __syncwarp();                               // the list is rewritten for the next tile
-        }
-#pragma unroll
-        for (int q = 0; q < VT_SUB; ++q)
-#pragma unroll
-            for (int j = 0; j < NB; ++j) planes[q][j] = next_planes[q][j];
+        const uint32_t rel = ev.cnt ? ev.e0p - item_origin<W>(item) : 0u;
+        a.recs[i] = make_uint2(ev.e0s, (min(ev.cnt, 0xffffu) << 16) | (rel & 0xffffu));
     }
-    if (lane == 0 && dense_tiles) atomicAdd(&a.counters[4], dense_tiles);
 
     // state at the end of the stream (keep=1 continuation): the last Lmax bytes decide it
-    if (a.want_end_state && blockIdx.x == gridDim.x - 1 && tid == VERIFY_THREADS - 1) {
-        const uint32_t back = a.halo + 1u;
-        const uint32_t ws = (a.total > back) ? ((a.total - back) & ~(uint32_t)(W - 1)) : 0u;
-        a.counters[2] = walk_item_slow<E, RANGE, W, false>(a, s_tab_addr, s_cls_addr, ITEM_NONE, ws, 0xffffffffu, a.total, 0u).e0s;
+    if (a.want_end_state && blockIdx.x == gridDim.x - 1 && threadIdx.x == WALK_THREADS - 1) {
+        const uint32_t back = a.s.halo + 1u;
+        const uint32_t ws = (a.s.total > back) ? ((a.s.total - back) & ~(uint32_t)(W - 1)) : 0u;
+        a.s.counters[2] = walk_item_slow<E, RANGE, W, false>(a.s, s_cls_addr, ITEM_NONE, ws, 0xffffffffu, a.s.total, 0u).e0s;
     }
 }
 
-// ------------------------------------------------------------ reorder -----
+// --------------------------------------------------------------- emit -----
 
-// One CTA per 1024 tiles, one thread per tile.  A run's final offset is the number of events of all
-// earlier tiles: the CTA sums the earlier blocks' run lengths (a coalesced read of at most n_tiles words
-// from L2), scans its own 1024 lengths, then its warps copy their 32 runs cooperatively.
-__global__ void __launch_bounds__(RUNSCAN_THREADS) ac_reorder_kernel(const uint2 *__restrict__ runs, uint32_t n_tiles,
-                                                                      const uint2 *__restrict__ tmp,
-                                                                      uint2 *__restrict__ out, uint32_t capacity)
+// events per tile: one warp per tile sums the counts of the tile's items
+__global__ void __launch_bounds__(COLLECT_THREADS) ac_tile_count_kernel(const __grid_constant__ VerifyArgs a)
 {
-    __shared__ uint32_t s_warp[RUNSCAN_THREADS / 32];
-    __shared__ uint32_t s_prev[RUNSCAN_THREADS / 32];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_warps = gridDim.x * (COLLECT_THREADS / 32);
+    for (uint32_t tile = blockIdx.x * (COLLECT_THREADS / 32) + (threadIdx.x >> 5); tile < a.n_tiles; tile += n_warps) {
+        const uint2 d = a.desc[tile];
+        uint32_t sum = 0;
+        for (uint32_t i = lane; i < d.y; i += 32u) sum += a.recs[d.x + i].y >> 16;
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, k);
+        if (lane == 0) a.tile_len[tile] = sum;
+    }
+}
+
+// One CTA per 1024 tiles.  A tile's first event goes to (events of all earlier tiles): the CTA adds up the
+// earlier blocks' tile lengths itself (a coalesced read of at most n_tiles words from L2), scans its own
+// 1024 lengths, then each warp writes the events of its 32 tiles in item order.
+template <typename E, bool RANGE, int W>
+__global__ void __launch_bounds__(EMIT_THREADS) ac_emit_kernel(const __grid_constant__ VerifyArgs a)
+{
+    __shared__ uint32_t s_warp[EMIT_THREADS / 32];
+    __shared__ uint32_t s_prev[EMIT_THREADS / 32];
+    __shared__ uint32_t s_off[EMIT_THREADS];
+    __shared__ uint8_t s_cls[256];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t first = blockIdx.x * RUNSCAN_THREADS;
+    const uint32_t first = blockIdx.x * EMIT_THREADS;
+    if (tid < 256) s_cls[tid] = a.s.cls_map[tid];
+    const uint32_t s_cls_addr = (uint32_t)__cvta_generic_to_shared(s_cls);
 
     uint32_t part = 0;
-    for (uint32_t j = tid; j < first; j += RUNSCAN_THREADS) part += runs[j].y;
+    for (uint32_t j = tid; j < first; j += EMIT_THREADS) part += a.tile_len[j];
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
     if (lane == 0) s_prev[warp] = part;
 
-    const uint32_t tile = first + tid;
-    const uint2 run = (tile < n_tiles) ? runs[tile] : make_uint2(0u, 0u);
-    uint32_t incl = run.y;
+    const uint32_t my_tile = first + tid;
+    const uint32_t len = (my_tile < a.n_tiles) ? a.tile_len[my_tile] : 0u;
+    uint32_t incl = len;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
@@ -660,21 +466,47 @@ __global__ void __launch_bounds__(RUNSCAN_THREADS) ac_reorder_kernel(const uint2
     __syncthreads();
     uint32_t base = 0;
 #pragma unroll
-    for (int w = 0; w < RUNSCAN_THREADS / 32; ++w) {
+    for (int w = 0; w < EMIT_THREADS / 32; ++w) {
         base += s_prev[w];
         if ((uint32_t)w < warp) base += s_warp[w];
     }
-    const uint32_t dst0 = base + incl - run.y;
+    s_off[tid] = base + incl - len;
+    if (my_tile == a.n_tiles - 1) a.s.counters[1] = base + incl;     // all events of the call
+    __syncwarp();
 
-    const uint32_t busy = __ballot_sync(0xffffffffu, run.y != 0);
+    const uint32_t busy = __ballot_sync(0xffffffffu, len != 0);
     for (uint32_t m = busy; m; m &= m - 1) {
-        const int src_lane = __ffs(m) - 1;
-        const uint32_t src = __shfl_sync(0xffffffffu, run.x, src_lane);
-        const uint32_t cnt = __shfl_sync(0xffffffffu, run.y, src_lane);
-        const uint32_t dst = __shfl_sync(0xffffffffu, dst0, src_lane);
-        for (uint32_t i = lane; i < cnt; i += 32u) {
-            const unsigned long long s_i = (unsigned long long)src + i, d_i = (unsigned long long)dst + i;
-            if (s_i < capacity && d_i < capacity) out[d_i] = tmp[s_i];
+        const uint32_t t = warp * 32u + (__ffs(m) - 1);
+        const uint2 d = a.desc[first + t];
+        uint32_t off = s_off[t];
+        for (uint32_t i0 = 0; i0 < d.y; i0 += 32u) {                 // warp-uniform
+            const uint32_t i = i0 + lane;
+            uint32_t item = ITEM_NONE, cnt = 0;
+            uint2 rec = make_uint2(0u, 0u);
+            if (i < d.y) {
+                rec = a.recs[d.x + i];
+                cnt = rec.y >> 16;
+                if (cnt) item = a.items[d.x + i];
+            }
+            uint32_t pincl = cnt;
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, pincl, k);
+                if (lane >= k) pincl += v;
+            }
+            const uint32_t o = off + pincl - cnt;
+            if (cnt == 1) {
+                if (o < a.s.capacity) a.s.out[o] = make_uint2(item_origin<W>(item) + (rec.y & 0xffffu), rec.x);
+            } else if (cnt > 1 && o < a.s.capacity) {
+                uint32_t ws = 0, rs = 0, re = 0;
+                if (!(item & ITEM_SPAN)) {
+                    rs = (item + 1u) * W;
+                    re = min(rs + W, a.s.total);
+                    ws = (rs > a.warm) ? rs - a.warm : 0u;
+                }
+                walk_item_slow<E, RANGE, W, true>(a.s, s_cls_addr, item, ws, rs, re, o);
+            }
+            off += __shfl_sync(0xffffffffu, pincl, 31);
         }
     }
 }

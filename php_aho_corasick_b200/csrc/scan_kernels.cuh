@@ -57,14 +57,8 @@ struct ScanArgs {
     uint32_t capacity;            // events that fit in `out`
     unsigned long long *tile_status;  // n_tiles words, zeroed before launch
     uint32_t *counters;           // [0] ticket (zeroed per launch) [1] running event total [2] end state
-                                  // [3] words flagged by the filter [4] tiles handed on for a complete walk
+                                  // [3] words flagged by the filter [4] tiles handed on for a complete walk [5] work items
     uint32_t *first_end;          // FIRST kernels: per haystack earliest event end seen (init 0xffffffff)
-    const uint32_t *mask;         // ac_verify_kernel: flagged-word bit planes written by ac_filter_kernel
-    uint32_t n_spans;             // ac_verify_kernel: 512-byte spans in the stream
-    uint32_t dense_max;           // ac_verify_kernel: more flagged words than this in a 16 KiB tile: walk the tile
-    uint2 *runs;                  // ac_verify_kernel: per chunk {offset, count} of its run of events in `out`
-    uint32_t warm;                // ac_verify_kernel: warm-up bytes before a flagged word's end offsets (halo rounded up to W)
-    uint32_t want_end_state;      // ac_verify_kernel: also compute the state at the end of the stream
 };
 
 // ------------------------------------------------------------ finalize ----

@@ -81,9 +81,14 @@ class ShardedMatcher:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._ev = None
 
-    def scan_local_device(self, dev_tensor: torch.Tensor, local_offsets, first_only=False, stream=0):
+    def scan_local_device(self, dev_tensor: torch.Tensor, local_offsets, first_only=False, stream=0, uniform_len=0):
         """Scans this rank's shard (uint8 CUDA tensor, haystacks end to end). -> int32 CUDA tensor [n,2]"""
-        _, n = self.aut.search_device(dev_tensor.data_ptr(), local_offsets, first_only=first_only, stream=stream)
+        if uniform_len:                          # equal-length batch: no offsets array on any side
+            n_hay = len(local_offsets) - 1
+            _, n = self.aut.search_device_uniform(dev_tensor.data_ptr(), n_hay, int(uniform_len),
+                                                  first_only=first_only, stream=stream)
+        else:
+            _, n = self.aut.search_device(dev_tensor.data_ptr(), local_offsets, first_only=first_only, stream=stream)
         if self._ev is None or self._ev.shape[0] < max(n, 1):
             self._ev = torch.empty((max(n, 1024), 2), dtype=torch.int32, device=dev_tensor.device)
         self.aut.copy_events(self._ev.data_ptr(), n, stream=stream)

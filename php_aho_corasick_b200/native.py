@@ -73,7 +73,7 @@ EXPORTS = [
     "acb200_state_patterns", "acb200_info", "acb200_last_stats", "acb200_last_error",
     "acb200_set_device", "acb200_device_count", "acb200_host_alloc", "acb200_host_free",
     "acb200_set_tuning", "acb200_version", "acb200_copy_events", "acb200_tally_cb", "acb200_tally_match_cb", "acb200_set_ilp",
-    "acb200_set_filter",
+    "acb200_set_filter", "acb200_search_device_uniform",
 ]
 
 
@@ -104,6 +104,9 @@ def lib() -> C.CDLL:
     L.acb200_search_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.acb200_search_device.restype = C.c_int
+    L.acb200_search_device_uniform.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p,
+                                               C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.acb200_search_device_uniform.restype = C.c_int
     L.acb200_state_patterns.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(AcPattern))]
     L.acb200_state_patterns.restype = C.c_size_t
     L.acb200_info.argtypes = [C.c_void_p, C.POINTER(Info)]
@@ -219,6 +222,16 @@ class Automaton:
         ne = C.c_size_t(0)
         rc = self.L.acb200_search_device(self.h, C.c_void_p(dev_ptr), off.ctypes.data, off.size - 1, int(first_only),
                                          C.c_void_p(stream), C.byref(out), C.byref(ne))
+        if rc != 0:
+            raise AcError(last_error())
+        return out.value, int(ne.value)
+
+    def search_device_uniform(self, dev_ptr: int, n_hay: int, hay_len: int, first_only: bool = False, stream: int = 0):
+        """n_hay haystacks of hay_len bytes each, end to end in HBM. -> (device pointer of packed events, n_events)"""
+        out = C.c_void_p(0)
+        ne = C.c_size_t(0)
+        rc = self.L.acb200_search_device_uniform(self.h, C.c_void_p(dev_ptr), int(n_hay), int(hay_len), int(first_only),
+                                                 C.c_void_p(stream), C.byref(out), C.byref(ne))
         if rc != 0:
             raise AcError(last_error())
         return out.value, int(ne.value)
