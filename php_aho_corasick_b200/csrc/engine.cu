@@ -294,7 +294,7 @@ bool Engine::ensure_verify_scratch(size_t n_tiles)
     CU_OK(cudaMalloc(&d_items_, cap * VER_DENSE_MAX * sizeof(uint32_t)));
     CU_OK(cudaMalloc(&d_recs_, cap * VER_DENSE_MAX * 2 * sizeof(uint32_t)));
     CU_OK(cudaMalloc(&d_desc_, cap * 2 * sizeof(uint32_t)));
-    CU_OK(cudaMalloc(&d_tile_len_, cap * sizeof(uint32_t)));
+    CU_OK(cudaMalloc(&d_tile_len_, 2 * cap * sizeof(uint32_t)));   // events per tile, then offsets per tile
     verify_tiles_cap_ = cap;
     return true;
 }
@@ -509,8 +509,8 @@ static void launch_walk_k(const VerifyArgs &a, bool range, unsigned grid, cudaSt
 template <typename E, int W>
 static void launch_emit_k(const VerifyArgs &a, bool range, unsigned grid, cudaStream_t st)
 {
-    if (range) ac_emit_kernel<E, true, W><<<grid, EMIT_THREADS, 0, st>>>(a);
-    else ac_emit_kernel<E, false, W><<<grid, EMIT_THREADS, 0, st>>>(a);
+    if (range) ac_emit_kernel<E, true, W><<<grid, COUNT_THREADS, 0, st>>>(a);
+    else ac_emit_kernel<E, false, W><<<grid, COUNT_THREADS, 0, st>>>(a);
 }
 
 // ahocorasick_match() through the gram prefilter: ac_filter_kernel streams the haystack and flags aligned
@@ -579,11 +579,13 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     va.desc = (uint2 *)d_desc_;
     va.recs = (uint2 *)d_recs_;
     va.tile_len = d_tile_len_;
+    va.tile_off = d_tile_len_ + verify_tiles_cap_;
 
     const unsigned warps_per_cta = SCAN_THREADS / 32;
     const unsigned grid_f = std::min<uint32_t>((n_spans + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
     const unsigned tiles_per_cta = COLLECT_THREADS / 32;
-    const unsigned grid_c = std::min<uint32_t>((n_tiles + tiles_per_cta - 1) / tiles_per_cta, (uint32_t)n_sms_ * 8u);
+    const unsigned grid_c = std::min<uint32_t>((n_tiles + tiles_per_cta - 1) / tiles_per_cta, (uint32_t)n_sms_ * 2u);
+    const unsigned grid_n = std::min<uint32_t>((n_tiles + COUNT_THREADS / 32 - 1) / (COUNT_THREADS / 32), (uint32_t)n_sms_ * 8u);
     const unsigned grid_w = (unsigned)n_sms_ * 8u;
     const unsigned grid_e = (n_tiles + EMIT_THREADS - 1) / EMIT_THREADS;
 
@@ -591,6 +593,7 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
         a.out = (uint2 *)d_events_;
         a.capacity = (uint32_t)std::min<size_t>(events_cap_, 0xffffffffu);
         CU_OK(cudaMemsetAsync(d_counters_, 0, 32, st));
+        CU_OK(cudaMemsetAsync(d_tile_len_, 0, (size_t)n_tiles * sizeof(uint32_t), st));   // the walk kernel adds to it
         CU_OK(cudaEventRecord(EV(ev_[0]), st));
         if (attempt == 0) {          // the bit planes survive a regrow of the event buffer
             if (W == 8) launch_filter_k<8>(fa, d_l2_ != nullptr, grid_f, st);
@@ -608,13 +611,13 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
             else launch_walk_k<uint32_t, 4>(va, range_map_, grid_w, st);
         }
         CU_OK(cudaEventRecord(EV(ev_[5]), st));
-        ac_tile_count_kernel<<<grid_c, COLLECT_THREADS, 0, st>>>(va);
+        ac_offsets_kernel<<<grid_e, EMIT_THREADS, 0, st>>>(va);
         if (entry_bytes_ == 2) {
-            if (W == 8) launch_emit_k<uint16_t, 8>(va, range_map_, grid_e, st);
-            else launch_emit_k<uint16_t, 4>(va, range_map_, grid_e, st);
+            if (W == 8) launch_emit_k<uint16_t, 8>(va, range_map_, grid_n, st);
+            else launch_emit_k<uint16_t, 4>(va, range_map_, grid_n, st);
         } else {
-            if (W == 8) launch_emit_k<uint32_t, 8>(va, range_map_, grid_e, st);
-            else launch_emit_k<uint32_t, 4>(va, range_map_, grid_e, st);
+            if (W == 8) launch_emit_k<uint32_t, 8>(va, range_map_, grid_n, st);
+            else launch_emit_k<uint32_t, 4>(va, range_map_, grid_n, st);
         }
         CU_OK(cudaGetLastError());
         CU_OK(cudaEventRecord(EV(ev_[1]), st));

@@ -51,9 +51,14 @@ constexpr int FILTER_UNROLL = 4;           // 16-byte loads in flight per thread
 constexpr uint32_t VER_DENSE_MAX = 64;     // flagged words per 16 KiB tile beyond which the whole tile is walked
 constexpr uint32_t ITEM_SPAN = 0x80000000u;// work item: walk 512-byte span (item & ~ITEM_SPAN) completely
 constexpr uint32_t ITEM_NONE = 0xffffffffu;
-constexpr int COLLECT_THREADS = 256;
+constexpr int COLLECT_THREADS = 1024;      // 32 tiles per CTA iteration share one atomic (same-address atomics serialise)
+constexpr int COUNT_THREADS = 256;
 constexpr int WALK_THREADS = 256;
-constexpr int EMIT_THREADS = 1024;         // one thread per tile in the offset scan, one warp per 32 tiles when emitting
+#ifndef ACB_WALK_ILP
+#define ACB_WALK_ILP 1
+#endif
+constexpr int WALK_ILP = ACB_WALK_ILP;      // items a walk thread verifies in lockstep
+constexpr int EMIT_THREADS = 256;          // one thread per tile in the offset scan, one warp per 32 tiles when emitting
 
 struct FilterArgs {
     const uint8_t *text;          // 16-byte aligned
@@ -173,7 +178,8 @@ struct VerifyArgs {
     uint32_t *items;              // work items, tile runs in completion order (capacity n_tiles * VER_DENSE_MAX)
     uint2 *desc;                  // per tile {offset into items, count}
     uint2 *recs;                  // per item {state of the first event, count << 16 | first end - item origin}
-    uint32_t *tile_len;           // per tile: events
+    uint32_t *tile_len;           // per tile: events (zeroed before the launch; the walk kernel adds to it)
+    uint32_t *tile_off;           // per tile: offset of its first event in the event buffer
 };
 
 template <int W>
@@ -181,25 +187,35 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
 {
     constexpr int NB = 16 / W;
     constexpr uint32_t WORDS_PER_SPAN = 32u * NB;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n_warps = gridDim.x * (COLLECT_THREADS / 32);
+    constexpr int N_WARPS = COLLECT_THREADS / 32;
+    __shared__ uint32_t s_n[N_WARPS];
+    __shared__ uint32_t s_base;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t dense_tiles = 0;
 
-    for (uint32_t tile = blockIdx.x * (COLLECT_THREADS / 32) + (threadIdx.x >> 5); tile < a.n_tiles; tile += n_warps) {
-        const uint32_t span = tile * 32u + lane;
-        const bool active = span < a.n_spans;
-        uint32_t planes[NB];
+    auto load_planes = [&](uint32_t tile, uint32_t (&pl)[NB]) {
 #pragma unroll
-        for (int j = 0; j < NB; ++j) planes[j] = 0;
-        if (active) {
+        for (int j = 0; j < NB; ++j) pl[j] = 0;
+        const uint32_t span = tile * 32u + lane;
+        if (tile < a.n_tiles && span < a.n_spans) {
             if (NB == 2) {
                 const uint2 m = __ldg(reinterpret_cast<const uint2 *>(a.mask) + span);
-                planes[0] = m.x; planes[1] = m.y;
+                pl[0] = m.x; pl[1] = m.y;
             } else {
                 const uint4 m = __ldg(reinterpret_cast<const uint4 *>(a.mask) + span);
-                planes[0] = m.x; planes[1] = m.y; planes[NB - 2] = m.z; planes[NB - 1] = m.w;
+                pl[0] = m.x; pl[1] = m.y; pl[NB - 2] = m.z; pl[NB - 1] = m.w;
             }
         }
+    };
+
+    // a CTA iteration takes 32 consecutive tiles, one per warp; the loop bound is CTA-uniform
+    uint32_t planes[NB], next_planes[NB];
+    load_planes(blockIdx.x * N_WARPS + warp, planes);
+    for (uint32_t tile0 = blockIdx.x * N_WARPS; tile0 < a.n_tiles; tile0 += gridDim.x * N_WARPS) {
+        const uint32_t tile = tile0 + warp;
+        load_planes(tile + gridDim.x * N_WARPS, next_planes);      // in flight while this tile is compacted
+        const uint32_t span = tile * 32u + lane;
+        const bool active = tile < a.n_tiles && span < a.n_spans;
         uint32_t cnt = 0;
 #pragma unroll
         for (int j = 0; j < NB; ++j) cnt += __popc(planes[j]);
@@ -213,14 +229,23 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
         const bool dense = n_cand > a.dense_max;       // cheaper to walk the whole tile
         const uint32_t n_act = __popc(__ballot_sync(0xffffffffu, active));
         const uint32_t n = dense ? n_act : n_cand;
-        uint32_t base = 0;
-        if (lane == 0) {
-            if (n) base = atomicAdd(&a.s.counters[5], n);
-            a.desc[tile] = make_uint2(base, n);
+        if (lane == 0) s_n[warp] = n;
+        __syncthreads();
+        // every warp scans the 32 counts; one atomic per CTA iteration reserves the items of all 32 tiles
+        const uint32_t v = s_n[lane];
+        uint32_t wincl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, wincl, d);
+            if (lane >= d) wincl += u;
         }
-        if (n == 0) continue;                           // warp-uniform
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (dense) {
+        const uint32_t cta_total = __shfl_sync(0xffffffffu, wincl, 31);
+        if (threadIdx.x == 0) s_base = cta_total ? atomicAdd(&a.s.counters[5], cta_total) : 0u;
+        __syncthreads();
+        const uint32_t base = s_base + __shfl_sync(0xffffffffu, wincl - v, warp);
+        if (lane == 0 && tile < a.n_tiles) a.desc[tile] = make_uint2(base, n);
+        if (n == 0) {
+        } else if (dense) {
             ++dense_tiles;
             if (active) a.items[base + lane] = ITEM_SPAN | span;
         } else if (cnt) {
@@ -237,6 +262,8 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
                     if ((planes[j] >> ch) & 1u) a.items[at++] = span * WORDS_PER_SPAN + ch * NB + j;
             }
         }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) planes[j] = next_planes[j];
     }
     if (lane == 0 && dense_tiles) atomicAdd(&a.s.counters[4], dense_tiles);
 }
@@ -281,30 +308,57 @@ struct Stepper {
 // per-item result
 struct ItemEvents { uint32_t cnt, e0p, e0s; };
 
-// The W end offsets owned by flagged word k are rs+1 .. rs+W with rs = W(k+1): walk from the root over the
-// warm-up [w0, rs) — w0 a multiple of W, the whole window [w0, rs+W) inside one haystack and inside the
-// stream (the caller checked) — and report the final states reached inside [rs, rs+W).
-template <int W, typename ST>
-__device__ __forceinline__ ItemEvents walk_word_fast(const ST &st, const uint8_t *text, uint32_t w0, uint32_t rs)
+// The W end offsets owned by flagged word k are rs+1 .. rs+W with rs = W(k+1).  K such words are verified in
+// lockstep (independent lookup chains hide each other's latency): each walk starts `warm` bytes before rs,
+// is reset to the root where its haystack starts (w0[k], a multiple of W inside [rs-warm, rs)), and reports
+// the final states reached inside [rs, rs+W).  The caller guarantees that every window [rs-warm, rs+W)
+// lies inside the stream and that [w0, rs+W) lies inside one haystack.
+template <int W, int K, typename ST>
+__device__ __forceinline__ void walk_words_lockstep(const ST &st, const uint8_t *text, uint32_t warm,
+                                                    const uint32_t (&rs)[K], const uint32_t (&w0)[K],
+                                                    ItemEvents (&ev)[K])
 {
-    uint32_t s = st.root;
-    uint2 cur = ld_group<W>(text, w0);
-    for (uint32_t i = w0; i < rs; i += W) {
-        const uint2 nxt = ld_group<W>(text, i + W);        // the last one is the report group
+    // four groups in flight per walk: a 24-byte window costs ONE memory latency, not three
+    uint32_t s[K];
+    uint2 cur[K], n1[K], n2[K], n3[K];
 #pragma unroll
-        for (int j = 0; j < W; ++j)
-            s = st.step(s, __byte_perm((j < 4) ? cur.x : cur.y, 0, 0x4440 | (j & 3)));
-        cur = nxt;
+    for (int k = 0; k < K; ++k) {
+        s[k] = st.root;
+        const uint32_t g0 = rs[k] - warm;                    // last group (the report group) starts at rs
+        cur[k] = ld_group<W>(text, g0);
+        n1[k] = ld_group<W>(text, min(g0 + W, rs[k]));
+        n2[k] = ld_group<W>(text, min(g0 + 2u * W, rs[k]));
+        n3[k] = ld_group<W>(text, min(g0 + 3u * W, rs[k]));
     }
-    ItemEvents ev{0, 0, 0};
+    for (uint32_t off = warm; off > 0; off -= W) {          // this group starts at rs - off
+        uint2 n4[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            n4[k] = n3[k];
+            if (off >= 4u * W) n4[k] = ld_group<W>(text, rs[k] - off + 4u * W);
+            if (rs[k] - off == w0[k]) s[k] = st.root;       // bytes before the haystack start do not count
+        }
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                s[k] = st.step(s[k], __byte_perm((j < 4) ? cur[k].x : cur[k].y, 0, 0x4440 | (j & 3)));
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) { cur[k] = n1[k]; n1[k] = n2[k]; n2[k] = n3[k]; n3[k] = n4[k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) ev[k] = ItemEvents{0, 0, 0};
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-        s = st.step(s, __byte_perm((j < 4) ? cur.x : cur.y, 0, 0x4440 | (j & 3)));
-        const bool f = s < st.final_bound;
-        if (f && ev.cnt == 0) { ev.e0p = rs + j + 1u; ev.e0s = s; }
-        ev.cnt += f ? 1u : 0u;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            s[k] = st.step(s[k], __byte_perm((j < 4) ? cur[k].x : cur[k].y, 0, 0x4440 | (j & 3)));
+            const bool f = s[k] < st.final_bound;
+            if (f && ev[k].cnt == 0) { ev[k].e0p = rs[k] + j + 1u; ev[k].e0s = s[k]; }
+            ev[k].cnt += f ? 1u : 0u;
+        }
     }
-    return ev;
 }
 
 // Everything else, out of line (rare): a flagged word whose window is clipped by the ends of the stream or
@@ -368,6 +422,13 @@ __device__ __forceinline__ uint32_t item_origin(uint32_t item)
     return (item & ITEM_SPAN) ? (item & ~ITEM_SPAN) * SPAN_BYTES : (item + 1u) * W;
 }
 
+// 16 KiB tile an item lies in
+template <int W>
+__device__ __forceinline__ uint32_t item_tile(uint32_t item)
+{
+    return (item & ITEM_SPAN) ? (item & ~ITEM_SPAN) >> 5 : item / (32u * (16u / W) * 32u);
+}
+
 template <typename E, bool RANGE, int W>
 __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_constant__ VerifyArgs a)
 {
@@ -384,28 +445,61 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
 
     const uint32_t n_items = a.s.counters[5];
     const uint32_t n_threads = gridDim.x * WALK_THREADS;
-    for (uint32_t i = blockIdx.x * WALK_THREADS + threadIdx.x; i < n_items; i += n_threads) {
-        const uint32_t item = a.items[i];
-        ItemEvents ev{0, 0, 0};
-        if (item & ITEM_SPAN) {
-            ev = walk_item_slow<E, RANGE, W, false>(a.s, s_cls_addr, item, 0u, 0u, 0u, 0u);
+    constexpr int K = WALK_ILP;
+    // a thread takes K consecutive items and walks them in lockstep
+    for (uint32_t i0 = (blockIdx.x * WALK_THREADS + threadIdx.x) * K; i0 < n_items; i0 += n_threads * K) {
+        uint32_t item[K], rs[K], w0[K];
+        bool lock[K];
+        bool all_lock = true;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            item[k] = (i0 + k < n_items) ? a.items[i0 + k] : ITEM_NONE;
+            rs[k] = 0; w0[k] = 0; lock[k] = false;
+            if (item[k] != ITEM_NONE && !(item[k] & ITEM_SPAN)) {
+                rs[k] = (item[k] + 1u) * W;            // the W end offsets owned by word k are rs+1 .. rs+W
+                if (rs[k] >= a.warm && rs[k] + W <= a.s.total) {
+                    // a walk that would start before the haystack of byte rs starts at that haystack's
+                    // first byte instead (the state there is the root by definition)
+                    const uint32_t h = find_haystack(a.s, rs[k]);
+                    w0[k] = max(rs[k] - a.warm, hay_begin(a.s, h));
+                    lock[k] = hay_end(a.s, h) >= rs[k] + W && ((rs[k] - w0[k]) & (uint32_t)(W - 1)) == 0 && w0[k] < rs[k];
+                }
+            }
+            all_lock = all_lock && lock[k];
+        }
+        ItemEvents ev[K];
+        if (all_lock) {
+            walk_words_lockstep<W, K>(st, a.s.text, a.warm, rs, w0, ev);
         } else {
-            const uint32_t rs = (item + 1u) * W;       // the W end offsets owned by word k are rs+1 .. rs+W
-            if (rs < a.s.total) {                      // else nothing ends after this word
-                const uint32_t re = min(rs + W, a.s.total);
-                const uint32_t ws = (rs > a.warm) ? rs - a.warm : 0u;
-                // a walk that would start before the haystack of byte rs starts at that haystack's
-                // first byte instead (the state there is the root by definition)
-                const uint32_t h = find_haystack(a.s, rs);
-                const uint32_t w0 = max(ws, hay_begin(a.s, h));
-                const bool plain = (re == rs + W) && hay_end(a.s, h) >= re &&
-                                   ((rs - w0) & (uint32_t)(W - 1)) == 0 && w0 < rs;
-                if (plain) ev = walk_word_fast<W>(st, a.s.text, w0, rs);
-                else ev = walk_item_slow<E, RANGE, W, false>(a.s, s_cls_addr, item, ws, rs, re, 0u);
+#pragma unroll 1
+            for (int k = 0; k < K; ++k) {
+                uint32_t it = ITEM_NONE, r1 = 0, w1 = 0; bool lk = false;
+#pragma unroll
+                for (int kk = 0; kk < K; ++kk) if (kk == k) { it = item[kk]; r1 = rs[kk]; w1 = w0[kk]; lk = lock[kk]; }
+                ItemEvents e1{0, 0, 0};
+                if (lk) {
+                    const uint32_t r_[1] = {r1}, w_[1] = {w1};
+                    ItemEvents e_[1];
+                    walk_words_lockstep<W, 1>(st, a.s.text, a.warm, r_, w_, e_);
+                    e1 = e_[0];
+                } else if (it != ITEM_NONE) {
+                    if (it & ITEM_SPAN) e1 = walk_item_slow<E, RANGE, W, false>(a.s, s_cls_addr, it, 0u, 0u, 0u, 0u);
+                    else if (r1 < a.s.total)           // else nothing ends after this word
+                        e1 = walk_item_slow<E, RANGE, W, false>(a.s, s_cls_addr, it, (r1 > a.warm) ? r1 - a.warm : 0u, r1,
+                                                                min(r1 + W, a.s.total), 0u);
+                }
+#pragma unroll
+                for (int kk = 0; kk < K; ++kk) if (kk == k) ev[kk] = e1;
             }
         }
-        const uint32_t rel = ev.cnt ? ev.e0p - item_origin<W>(item) : 0u;
-        a.recs[i] = make_uint2(ev.e0s, (min(ev.cnt, 0xffffu) << 16) | (rel & 0xffffu));
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (i0 + k < n_items) {
+                const uint32_t rel = ev[k].cnt ? ev[k].e0p - item_origin<W>(item[k]) : 0u;
+                a.recs[i0 + k] = make_uint2(ev[k].e0s, (min(ev[k].cnt, 0xffffu) << 16) | (rel & 0xffffu));
+                if (ev[k].cnt) atomicAdd(&a.tile_len[item_tile<W>(item[k])], ev[k].cnt);   // events per tile, for the offsets
+            }
+        }
     }
 
     // state at the end of the stream (keep=1 continuation): the last Lmax bytes decide it
@@ -418,44 +512,23 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
 
 // --------------------------------------------------------------- emit -----
 
-// events per tile: one warp per tile sums the counts of the tile's items
-__global__ void __launch_bounds__(COLLECT_THREADS) ac_tile_count_kernel(const __grid_constant__ VerifyArgs a)
-{
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n_warps = gridDim.x * (COLLECT_THREADS / 32);
-    for (uint32_t tile = blockIdx.x * (COLLECT_THREADS / 32) + (threadIdx.x >> 5); tile < a.n_tiles; tile += n_warps) {
-        const uint2 d = a.desc[tile];
-        uint32_t sum = 0;
-        for (uint32_t i = lane; i < d.y; i += 32u) sum += a.recs[d.x + i].y >> 16;
-#pragma unroll
-        for (int k = 16; k > 0; k >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, k);
-        if (lane == 0) a.tile_len[tile] = sum;
-    }
-}
-
-// One CTA per 1024 tiles.  A tile's first event goes to (events of all earlier tiles): the CTA adds up the
-// earlier blocks' tile lengths itself (a coalesced read of at most n_tiles words from L2), scans its own
-// 1024 lengths, then each warp writes the events of its 32 tiles in item order.
-template <typename E, bool RANGE, int W>
-__global__ void __launch_bounds__(EMIT_THREADS) ac_emit_kernel(const __grid_constant__ VerifyArgs a)
+// Exclusive prefix sum of the events per tile.  One CTA per 256 tiles: it adds up the lengths of all earlier
+// tiles itself (a coalesced read of at most n_tiles words from L2 — no CTA waits for another one) and scans
+// its own 256 tile lengths.  tile_len -> tile_off.
+__global__ void __launch_bounds__(EMIT_THREADS) ac_offsets_kernel(const __grid_constant__ VerifyArgs a)
 {
     __shared__ uint32_t s_warp[EMIT_THREADS / 32];
     __shared__ uint32_t s_prev[EMIT_THREADS / 32];
-    __shared__ uint32_t s_off[EMIT_THREADS];
-    __shared__ uint8_t s_cls[256];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t first = blockIdx.x * EMIT_THREADS;
-    if (tid < 256) s_cls[tid] = a.s.cls_map[tid];
-    const uint32_t s_cls_addr = (uint32_t)__cvta_generic_to_shared(s_cls);
 
     uint32_t part = 0;
-    for (uint32_t j = tid; j < first; j += EMIT_THREADS) part += a.tile_len[j];
+    for (uint32_t j = tid; j < blockIdx.x * EMIT_THREADS; j += EMIT_THREADS) part += a.tile_len[j];
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
     if (lane == 0) s_prev[warp] = part;
 
-    const uint32_t my_tile = first + tid;
-    const uint32_t len = (my_tile < a.n_tiles) ? a.tile_len[my_tile] : 0u;
+    const uint32_t tile = blockIdx.x * EMIT_THREADS + tid;
+    const uint32_t len = (tile < a.n_tiles) ? a.tile_len[tile] : 0u;
     uint32_t incl = len;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -470,15 +543,24 @@ __global__ void __launch_bounds__(EMIT_THREADS) ac_emit_kernel(const __grid_cons
         base += s_prev[w];
         if ((uint32_t)w < warp) base += s_warp[w];
     }
-    s_off[tid] = base + incl - len;
-    if (my_tile == a.n_tiles - 1) a.s.counters[1] = base + incl;     // all events of the call
-    __syncwarp();
+    if (tile < a.n_tiles) a.tile_off[tile] = base + incl - len;
+    if (tile == a.n_tiles - 1) a.s.counters[1] = base + incl;        // all events of the call
+}
 
-    const uint32_t busy = __ballot_sync(0xffffffffu, len != 0);
-    for (uint32_t m = busy; m; m &= m - 1) {
-        const uint32_t t = warp * 32u + (__ffs(m) - 1);
-        const uint2 d = a.desc[first + t];
-        uint32_t off = s_off[t];
+// One warp per tile with events: write them to their final place, in item order.
+template <typename E, bool RANGE, int W>
+__global__ void __launch_bounds__(COUNT_THREADS) ac_emit_kernel(const __grid_constant__ VerifyArgs a)
+{
+    __shared__ uint8_t s_cls[256];
+    const uint32_t lane = threadIdx.x & 31u;
+    if (threadIdx.x < 256) s_cls[threadIdx.x] = a.s.cls_map[threadIdx.x];
+    __syncthreads();
+    const uint32_t s_cls_addr = (uint32_t)__cvta_generic_to_shared(s_cls);
+    const uint32_t n_warps = gridDim.x * (COUNT_THREADS / 32);
+
+    for (uint32_t tile = blockIdx.x * (COUNT_THREADS / 32) + (threadIdx.x >> 5); tile < a.n_tiles; tile += n_warps) {
+        const uint2 d = a.desc[tile];
+        uint32_t off = a.tile_off[tile];
         for (uint32_t i0 = 0; i0 < d.y; i0 += 32u) {                 // warp-uniform
             const uint32_t i = i0 + lane;
             uint32_t item = ITEM_NONE, cnt = 0;
@@ -488,6 +570,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) ac_emit_kernel(const __grid_cons
                 cnt = rec.y >> 16;
                 if (cnt) item = a.items[d.x + i];
             }
+            if (!__any_sync(0xffffffffu, cnt != 0)) continue;
             uint32_t pincl = cnt;
 #pragma unroll
             for (int k = 1; k < 32; k <<= 1) {
