@@ -294,7 +294,7 @@ bool Engine::ensure_verify_scratch(size_t n_tiles)
     CU_OK(cudaMalloc(&d_items_, cap * VER_DENSE_MAX * sizeof(uint32_t)));
     CU_OK(cudaMalloc(&d_recs_, cap * VER_DENSE_MAX * 2 * sizeof(uint32_t)));
     CU_OK(cudaMalloc(&d_desc_, cap * 2 * sizeof(uint32_t)));
-    CU_OK(cudaMalloc(&d_tile_len_, 2 * cap * sizeof(uint32_t)));   // events per tile, then offsets per tile
+    CU_OK(cudaMalloc(&d_tile_len_, (2 * cap + cap / EMIT_THREADS + 16) * sizeof(uint32_t)));   // events per tile, offsets per tile, block sums
     verify_tiles_cap_ = cap;
     return true;
 }
@@ -580,6 +580,7 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     va.recs = (uint2 *)d_recs_;
     va.tile_len = d_tile_len_;
     va.tile_off = d_tile_len_ + verify_tiles_cap_;
+    va.block_sum = d_tile_len_ + 2 * verify_tiles_cap_;
 
     const unsigned warps_per_cta = SCAN_THREADS / 32;
     const unsigned grid_f = std::min<uint32_t>((n_spans + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
@@ -593,7 +594,8 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
         a.out = (uint2 *)d_events_;
         a.capacity = (uint32_t)std::min<size_t>(events_cap_, 0xffffffffu);
         CU_OK(cudaMemsetAsync(d_counters_, 0, 32, st));
-        CU_OK(cudaMemsetAsync(d_tile_len_, 0, (size_t)n_tiles * sizeof(uint32_t), st));   // the walk kernel adds to it
+        CU_OK(cudaMemsetAsync(d_tile_len_, 0, (size_t)n_tiles * sizeof(uint32_t), st));   // the walk kernel adds to both
+        CU_OK(cudaMemsetAsync(va.block_sum, 0, (size_t)((n_tiles + EMIT_THREADS - 1) / EMIT_THREADS) * sizeof(uint32_t), st));
         CU_OK(cudaEventRecord(EV(ev_[0]), st));
         if (attempt == 0) {          // the bit planes survive a regrow of the event buffer
             if (W == 8) launch_filter_k<8>(fa, d_l2_ != nullptr, grid_f, st);

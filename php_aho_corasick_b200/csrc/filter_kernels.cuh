@@ -47,7 +47,7 @@
 namespace acb200 {
 
 constexpr uint32_t SPAN_BYTES = 512;       // one warp-wide 16-byte load; one verify lane
-constexpr int FILTER_UNROLL = 4;           // 16-byte loads in flight per thread
+constexpr int FILTER_UNROLL = 6;           // 16-byte loads in flight per thread
 constexpr uint32_t VER_DENSE_MAX = 64;     // flagged words per 16 KiB tile beyond which the whole tile is walked
 constexpr uint32_t ITEM_SPAN = 0x80000000u;// work item: walk 512-byte span (item & ~ITEM_SPAN) completely
 constexpr uint32_t ITEM_NONE = 0xffffffffu;
@@ -180,6 +180,7 @@ struct VerifyArgs {
     uint2 *recs;                  // per item {state of the first event, count << 16 | first end - item origin}
     uint32_t *tile_len;           // per tile: events (zeroed before the launch; the walk kernel adds to it)
     uint32_t *tile_off;           // per tile: offset of its first event in the event buffer
+    uint32_t *block_sum;          // per EMIT_THREADS tiles: events (zeroed before the launch)
 };
 
 template <int W>
@@ -500,6 +501,26 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
                 if (ev[k].cnt) atomicAdd(&a.tile_len[item_tile<W>(item[k])], ev[k].cnt);   // events per tile, for the offsets
             }
         }
+        // events per block of EMIT_THREADS tiles: the items of a warp almost always lie in one block, so one
+        // atomic per warp (same-address atomics serialise)
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const bool has = (i0 + k < n_items) && ev[k].cnt;
+            const uint32_t blk = has ? item_tile<W>(item[k]) / EMIT_THREADS : 0xffffffffu;
+            const uint32_t act = __activemask();
+            const uint32_t voters = __ballot_sync(act, has);
+            if (voters) {
+                const uint32_t lead_blk = __shfl_sync(act, blk, __ffs(voters) - 1);
+                if (__all_sync(act, !has || blk == lead_blk)) {
+                    uint32_t sum = has ? ev[k].cnt : 0u;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(act, sum, d);
+                    if ((threadIdx.x & 31u) == (uint32_t)(__ffs(act) - 1)) atomicAdd(&a.block_sum[lead_blk], sum);
+                } else if (has) {
+                    atomicAdd(&a.block_sum[blk], ev[k].cnt);
+                }
+            }
+        }
     }
 
     // state at the end of the stream (keep=1 continuation): the last Lmax bytes decide it
@@ -512,9 +533,8 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
 
 // --------------------------------------------------------------- emit -----
 
-// Exclusive prefix sum of the events per tile.  One CTA per 256 tiles: it adds up the lengths of all earlier
-// tiles itself (a coalesced read of at most n_tiles words from L2 — no CTA waits for another one) and scans
-// its own 256 tile lengths.  tile_len -> tile_off.
+// Exclusive prefix sum of the events per tile.  One CTA per 256 tiles: it adds up the earlier blocks' sums
+// itself (no CTA waits for another one) and scans its own 256 tile lengths.  tile_len -> tile_off.
 __global__ void __launch_bounds__(EMIT_THREADS) ac_offsets_kernel(const __grid_constant__ VerifyArgs a)
 {
     __shared__ uint32_t s_warp[EMIT_THREADS / 32];
@@ -522,7 +542,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) ac_offsets_kernel(const __grid_c
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
     uint32_t part = 0;
-    for (uint32_t j = tid; j < blockIdx.x * EMIT_THREADS; j += EMIT_THREADS) part += a.tile_len[j];
+    for (uint32_t j = tid; j < blockIdx.x; j += EMIT_THREADS) part += a.block_sum[j];
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
     if (lane == 0) s_prev[warp] = part;
@@ -559,6 +579,7 @@ __global__ void __launch_bounds__(COUNT_THREADS) ac_emit_kernel(const __grid_con
     const uint32_t n_warps = gridDim.x * (COUNT_THREADS / 32);
 
     for (uint32_t tile = blockIdx.x * (COUNT_THREADS / 32) + (threadIdx.x >> 5); tile < a.n_tiles; tile += n_warps) {
+        if (a.tile_len[tile] == 0) continue;                          // warp-uniform: nothing ends in this tile
         const uint2 d = a.desc[tile];
         uint32_t off = a.tile_off[tile];
         for (uint32_t i0 = 0; i0 < d.y; i0 += 32u) {                 // warp-uniform
