@@ -326,18 +326,21 @@ def main():
     filtered = filtered_steps == args.steps
     if filtered:
         per = {}
-        for name, ms in (("ac_filter_kernel", filter_ms), ("ac_verify_kernel", verify_ms), ("ac_reorder_kernel", reorder_ms)):
+        for name, ms in (("ac_filter_kernel", filter_ms), ("ac_collect_kernel + ac_walk_kernel", verify_ms),
+                         ("ac_offsets_kernel + ac_emit_kernel", reorder_ms)):
             m = ms / args.steps
             per[name] = {"ms": m, "GBps": nbytes / (m * 1e-3) / 1e9 if m else None,
                          "frac_of_peak": nbytes / (m * 1e-3) / 1e9 / peak if m else None}
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": ncu_traffic("cfg2_1GiB_filtered"), "peak_source": peak_src,
-                    "kernel": "ac_filter_kernel + ac_verify_kernel + ac_reorder_kernel (the device kernels of one step)",
+                    "kernel": "ac_filter_kernel + ac_collect_kernel + ac_walk_kernel + ac_offsets_kernel + ac_emit_kernel "
+                              "(the device kernels of one step)",
                     "kernel_ms": k_ms, "algorithmic_bytes_per_launch": nbytes, "per_kernel": per,
-                    "note": "1 HBM byte per haystack byte over the summed duration of the step's three kernels. "
-                            "ac_filter_kernel is the only one that streams the haystack (HBM-bound); "
-                            "ac_verify_kernel walks the automaton around ~2% of the words and is latency-bound "
-                            "(dependent shared-memory lookups, random 24-byte reads) — see DESIGN.md"}
+                    "note": "1 HBM byte per haystack byte over the summed duration of the step's five kernels. "
+                            "ac_filter_kernel is the only one that streams the haystack (HBM-bound, per_kernel "
+                            "shows its own fraction); ac_walk_kernel walks the automaton around the ~2% of the "
+                            "words the filter flags and is latency-bound (dependent table lookups, random 24-byte "
+                            "reads) — see DESIGN.md"}
     else:
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": ncu_traffic("cfg2_1GiB"), "peak_source": peak_src,

@@ -140,12 +140,72 @@ static int replay_batch(ac_trie *t, const uint64_t *offsets, size_t n, int first
     return 0;
 }
 
+// Large batches are cut into slabs at haystack boundaries and pipelined: while slab i is scanned on the
+// device and its events are replayed through the callback on the host, slab i+1 is already crossing PCIe.
+static constexpr uint64_t SLAB_BYTES = 64ull << 20;
+
+static int search_flat_pipelined(ac_trie *t, const char *bytes, const uint64_t *offsets, size_t n,
+                                 int first_only, ACB200_BATCH_CALLBACK_f callback, void *user)
+{
+    // slab s covers haystacks [cut[s], cut[s+1])
+    std::vector<size_t> cut{0};
+    for (size_t h = 0; h < n;) {
+        size_t e = h;
+        while (e < n && offsets[e + 1] - offsets[h] <= SLAB_BYTES) ++e;
+        if (e == h) e = h + 1;                   // a single haystack larger than a slab travels alone
+        if (offsets[e] - offsets[h] >= 0xffffff00ull) { set_error("haystack exceeds 4 GiB"); return -1; }
+        cut.push_back(e);
+        h = e;
+    }
+    const size_t n_slabs = cut.size() - 1;
+    Engine &eng = t->engine;
+    ACB200_STATS_t sum{};
+    std::vector<uint64_t> rel;
+    auto upload = [&](size_t s) {
+        const uint64_t b0 = offsets[cut[s]], b1 = offsets[cut[s + 1]];
+        return eng.slab_upload_async((int)(s & 1), bytes + b0, (size_t)(b1 - b0));
+    };
+    if (!upload(0)) return -1;
+    for (size_t s = 0; s < n_slabs; ++s) {
+        if (s + 1 < n_slabs && !upload(s + 1)) return -1;
+        const size_t h0 = cut[s], h1 = cut[s + 1];
+        rel.resize(h1 - h0 + 1);
+        for (size_t i = 0; i <= h1 - h0; ++i) rel[i] = offsets[h0 + i] - offsets[h0];
+        if (!eng.scan_slab((int)(s & 1), rel.data(), h1 - h0, first_only != 0)) return -1;
+        sum.bytes += eng.stats.bytes; sum.events += eng.stats.events; sum.kernel_launches += eng.stats.kernel_launches;
+        sum.kernel_ms += eng.stats.kernel_ms; sum.filter_ms += eng.stats.filter_ms; sum.verify_ms += eng.stats.verify_ms;
+        sum.reorder_ms += eng.stats.reorder_ms; sum.d2h_ms += eng.stats.d2h_ms; sum.h2d_ms += eng.slab_h2d_ms((int)(s & 1));
+        sum.flagged_words += eng.stats.flagged_words; sum.dense_tiles += eng.stats.dense_tiles;
+        sum.chunk_bytes = eng.stats.chunk_bytes; sum.halo_bytes = eng.stats.halo_bytes; sum.ilp = eng.stats.ilp;
+        sum.filtered = eng.stats.filtered;
+        // replay this slab's events; haystack indices are those of the whole batch
+        const PackedEvent *ev = eng.host_events();
+        const size_t ne = eng.n_events();
+        size_t h = 0, stopped = (size_t)-1;
+        for (size_t i = 0; i < ne; ++i) {
+            const uint64_t end = ev[i].end;
+            while (h < h1 - h0 && end > rel[h + 1]) ++h;
+            if (h == stopped) continue;
+            const AC_PATTERN_t *pats;
+            AC_MATCH_t m;
+            m.size = patterns_of(t, ev[i].state, &pats);
+            m.patterns = const_cast<AC_PATTERN_t *>(pats);
+            m.position = (size_t)(end - rel[h]);
+            const int r = callback(h0 + h, &m, user);
+            if (r || first_only) stopped = h;
+        }
+    }
+    eng.stats = sum;
+    return 0;
+}
+
 int ac_trie_search_flat(AC_TRIE_t *t, const char *bytes, const uint64_t *offsets, size_t n,
                         int first_only, ACB200_BATCH_CALLBACK_f callback, void *user)
 {
     if (t->open) { set_error("automaton is not finalized"); return -1; }
     if (!t->device_ok) return -1;
     if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return -1; }
+    if (n > 1 && offsets[n] > 2 * SLAB_BYTES) return search_flat_pipelined(t, bytes, offsets, n, first_only, callback, user);
     if (!t->engine.scan_host(bytes, offsets, n, first_only != 0, ROOT_STATE)) return -1;
     return replay_batch(t, offsets, n, first_only, callback, user);
 }

@@ -66,6 +66,9 @@ void Engine::release()
     if (h_events_) cudaFreeHost(h_events_);
     if (h_stage_) cudaFreeHost(h_stage_);
     for (auto &e : ev_) if (e) { cudaEventDestroy(EV(e)); e = nullptr; }
+    for (auto &e : ev_slab_) if (e) { cudaEventDestroy(EV(e)); e = nullptr; }
+    for (int b = 0; b < 2; ++b) { cudaFree(d_slab_[b]); d_slab_[b] = nullptr; slab_cap_[b] = 0; }
+    if (copy_stream_) { cudaStreamDestroy(S(copy_stream_)); copy_stream_ = nullptr; }
     if (stream_) cudaStreamDestroy(S(stream_));
     d_table_ = nullptr; d_cls_ = nullptr; d_text_ = nullptr; d_off_ = nullptr; d_first_ = nullptr;
     d_events_ = nullptr; d_tiles_ = nullptr; d_counters_ = nullptr;
@@ -682,6 +685,62 @@ bool Engine::scan_device_uniform(const void *d_bytes, size_t n, size_t hay_len, 
     stats.h2d_ms = 0; stats.d2h_ms = 0;
     const uint32_t uniform_len = (n <= 1 || total == 0) ? (uint32_t)std::max<uint64_t>(total, 1) : (uint32_t)hay_len;
     return launch_scan(d_bytes, (uint32_t)total, (uint32_t)total, std::max<size_t>(n, 1), uniform_len, first_only, ROOT_STATE, stream);
+}
+
+bool Engine::slab_upload_async(int buf, const char *bytes, size_t n_bytes)
+{
+    if (device_ < 0) { set_error("automaton has no device table (finalize failed?)"); return false; }
+    CU_OK(cudaSetDevice(device_));
+    if (!copy_stream_) {
+        cudaStream_t cs;
+        CU_OK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        copy_stream_ = cs;
+        for (auto &e : ev_slab_) { cudaEvent_t x; CU_OK(cudaEventCreate(&x)); e = x; }
+    }
+    if (n_bytes + 64 > slab_cap_[buf]) {
+        cudaFree(d_slab_[buf]); d_slab_[buf] = nullptr; slab_cap_[buf] = 0;
+        const size_t cap = n_bytes + n_bytes / 8 + 4096;
+        CU_OK(cudaMalloc(&d_slab_[buf], cap));
+        slab_cap_[buf] = cap;
+    }
+    CU_OK(cudaEventRecord(EV(ev_slab_[2 * buf]), S(copy_stream_)));
+    if (n_bytes) CU_OK(cudaMemcpyAsync(d_slab_[buf], bytes, n_bytes, cudaMemcpyHostToDevice, S(copy_stream_)));
+    CU_OK(cudaEventRecord(EV(ev_slab_[2 * buf + 1]), S(copy_stream_)));
+    return true;
+}
+
+float Engine::slab_h2d_ms(int buf)
+{
+    float ms = 0;
+    if (ev_slab_[2 * buf] && cudaEventElapsedTime(&ms, EV(ev_slab_[2 * buf]), EV(ev_slab_[2 * buf + 1])) != cudaSuccess) ms = 0;
+    return ms;
+}
+
+// Scans the slab uploaded into buffer `buf` (offsets are relative to the slab) and brings its events to
+// host_events().  Returns after the events have arrived; the other buffer's upload keeps running meanwhile.
+bool Engine::scan_slab(int buf, const uint64_t *offsets, size_t n, bool first_only)
+{
+    CU_OK(cudaSetDevice(device_));
+    cudaStream_t st = S(stream_);
+    const uint64_t total = offsets[n];
+    if (total >= 0xffffff00ull) { set_error("haystack stream exceeds 4 GiB per call"); return false; }
+    uint32_t uniform_len = 0;
+    if (!upload_offsets(offsets, n, &uniform_len)) return false;
+    CU_OK(cudaStreamWaitEvent(st, EV(ev_slab_[2 * buf + 1]), 0));
+    if (!launch_scan(d_slab_[buf], (uint32_t)total, (uint32_t)std::min<uint64_t>(slab_cap_[buf], 0xffffffffu), n, uniform_len,
+                     first_only, ROOT_STATE, nullptr)) return false;
+    stats.d2h_ms = 0;
+    if (n_events_) {
+        if (!ensure_host_events(n_events_)) return false;
+        CU_OK(cudaEventRecord(EV(ev_[2]), st));
+        CU_OK(cudaMemcpyAsync(h_events_, d_events_, n_events_ * sizeof(PackedEvent), cudaMemcpyDeviceToHost, st));
+        CU_OK(cudaEventRecord(EV(ev_[3]), st));
+        CU_OK(cudaStreamSynchronize(st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, EV(ev_[2]), EV(ev_[3]));
+        stats.d2h_ms = ms;
+    }
+    return true;
 }
 
 bool Engine::scan_host(const char *bytes, const uint64_t *offsets, size_t n, bool first_only,

@@ -33,6 +33,11 @@ public:
     // host_events() sorted by stream offset; returns false on error.
     bool scan_host(const char *bytes, const uint64_t *offsets, size_t n, bool first_only,
                    uint32_t init_state);
+    // Pipelined variant for large batches: the caller cuts the batch into slabs at haystack boundaries,
+    // uploads slab i+1 (slab_upload_async) while slab i is scanned (scan_slab) and replayed on the host.
+    bool slab_upload_async(int buf, const char *bytes, size_t n_bytes);
+    bool scan_slab(int buf, const uint64_t *offsets, size_t n, bool first_only);
+    float slab_h2d_ms(int buf);
     // Same for a stream already resident in device memory; events stay on the device.
     bool scan_device(const void *d_bytes, const uint64_t *offsets, size_t n, bool first_only,
                      uint32_t init_state, void *stream);
@@ -106,6 +111,9 @@ private:
     uint32_t *h_counters_ = nullptr;          // pinned
     PackedEvent *h_events_ = nullptr; size_t h_events_cap_ = 0;   // pinned
     uint8_t *h_stage_ = nullptr;  size_t stage_cap_ = 0;          // pinned staging for pageable input
+    uint8_t *d_slab_[2] = {nullptr, nullptr}; size_t slab_cap_[2] = {0, 0};   // double-buffered haystack slabs
+    void *copy_stream_ = nullptr;                                  // cudaStream_t of the slab uploads
+    void *ev_slab_[4] = {nullptr, nullptr, nullptr, nullptr};     // per buffer: upload started / finished
     std::vector<uint32_t> off32_;
 
     double last_density_ = 0.0;    // events per byte of the previous scan (kernel choice)

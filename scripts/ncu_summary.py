@@ -4,7 +4,10 @@ import csv, subprocess, sys, io
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, vals = rows[0], rows[2]
+hdr = rows[0]
+units = dict(zip(hdr, rows[1]))
+which = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # n-th profiled kernel of the report
+vals = rows[2 + which]
 m = dict(zip(hdr, vals))
 def g(k):
     try: return float(m[k].replace(",", ""))
@@ -21,7 +24,7 @@ for k in ["dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput
           "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts.sum",
           "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum",
           "smsp__cycles_active.avg", "sm__cycles_elapsed.max"]:
-    if k in m: print(f"  {k} = {m[k]}")
+    if k in m: print(f"  {k} = {m[k]} {units.get(k, '')}")
 st = []
 for h, v in m.items():
     if "average_warps_issue_stalled" in h and h.endswith("per_issue_active.ratio") and "not_issued" not in h:

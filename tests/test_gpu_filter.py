@@ -174,3 +174,39 @@ def test_device_resident_stream_with_odd_length_is_not_read_past_its_end():
     assert int(got[-1, 0]) == hay.size
     ev = a.search_events(hay, off)
     assert np.array_equal(got[:, 0].astype(np.uint64), ev["end"]) and np.array_equal(got[:, 1], ev["state"])
+
+
+def test_pipelined_flat_search_equals_monolithic_batch_search():
+    """ac_trie_search_flat cuts batches above 128 MiB into 64 MiB slabs (upload of slab i+1 overlaps scan and
+    replay of slab i); the callback sequence must be the one of the single-launch path."""
+    import ctypes as C
+    from php_aho_corasick_b200 import native
+    needles, hay, off = W.cfg2(n_hay=256, hay_len=8192, planted_per_hay=8)
+    reps = 72                                           # 144 MiB, haystack lengths varied below
+    flat = np.tile(hay, reps)
+    n = reps * 256
+    lens = np.full(n, 8192, dtype=np.uint64)
+    lens[::7] -= 3                                      # ragged: slab cuts fall on unaligned offsets
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lens)
+    flat = np.ascontiguousarray(flat[: int(offsets[-1])])
+    a = build([needles], 0)
+    t_pipe = a.search_flat_tally(flat.ctypes.data, offsets)
+    assert a.stats().bytes == flat.size and a.stats().kernel_launches >= 3 * 5
+    # monolithic reference: ac_trie_search_batch gathers the texts and scans them in one launch
+    texts = (native.AcText * n)()
+    base = flat.ctypes.data
+    for i in range(n):
+        texts[i].astring = base + int(offsets[i])
+        texts[i].length = int(lens[i])
+    t_mono = native.Tally()
+    cb = C.cast(a.L.acb200_tally_cb, native.BATCH_CB)
+    rc = a.L.ac_trie_search_batch(a.h, texts, n, 0, cb, C.cast(C.byref(t_mono), C.c_void_p))
+    assert rc == 0
+    assert (t_pipe.events, t_pipe.hits, t_pipe.hash) == (t_mono.events, t_mono.hits, t_mono.hash)
+    assert t_pipe.events > n * 5
+    # findAll=false through both paths
+    t1 = a.search_flat_tally(flat.ctypes.data, offsets, first_only=True)
+    t2 = native.Tally()
+    rc = a.L.ac_trie_search_batch(a.h, texts, n, 1, cb, C.cast(C.byref(t2), C.c_void_p))
+    assert rc == 0 and (t1.events, t1.hash) == (t2.events, t2.hash) and t1.events == n
