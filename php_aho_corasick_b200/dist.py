@@ -29,24 +29,67 @@ def shard_ranges(offsets, world: int):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+class EventGatherer:
+    """Variable-length gather of packed event lists with persistent buffers: ONE all_gather per call.
+
+    Every rank sends `cap + 1` rows: row 0 carries its event count, rows 1.. its events.  `cap` is the same on
+    all ranks by construction (it only changes as a deterministic function of the gathered counts, which every
+    rank sees), so no size exchange is needed in the steady state; a call whose counts exceed `cap` grows it and
+    gathers again.  The tensors returned on `dst` are views into the receive buffer, valid until the next call."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.cap = 0
+        self.send = None
+        self.recv = None
+
+    def _ensure(self, cap, world, like):
+        if self.send is None or self.send.shape[0] != cap + 1 or self.send.device != like.device or self.send.dtype != like.dtype:
+            self.send = torch.zeros((cap + 1, 2), dtype=like.dtype, device=like.device)
+            self.recv = torch.zeros((world, cap + 1, 2), dtype=like.dtype, device=like.device)
+            self.cap = cap
+
+    @staticmethod
+    def _grow(n):
+        cap = 1024
+        while cap < n + n // 4:
+            cap *= 2
+        return cap
+
+    def gather(self, local: torch.Tensor, dst: int = 0):
+        world = dist.get_world_size(self.group)
+        n = int(local.shape[0])
+        if self.cap == 0:                        # first call: agree on a capacity
+            n_local = torch.tensor([n], dtype=torch.int64, device=local.device)
+            sizes = [torch.zeros_like(n_local) for _ in range(world)]
+            dist.all_gather(sizes, n_local, group=self.group)
+            self._ensure(self._grow(max(int(s.item()) for s in sizes)), world, local)
+        while True:
+            self._ensure(self.cap, world, local)
+            self.send[0, 0] = n
+            m = min(n, self.cap)
+            if m:
+                self.send[1:1 + m].copy_(local[:m])
+            dist.all_gather([self.recv[r] for r in range(world)], self.send, group=self.group)
+            sizes = [int(x) for x in self.recv[:, 0, 0].cpu().tolist()]
+            if max(sizes) <= self.cap:
+                break
+            self._ensure(self._grow(max(sizes)), world, local)     # same decision on every rank
+        if dist.get_rank(self.group) != dst:
+            return None
+        return [self.recv[r, 1:1 + sizes[r]] for r in range(world)]
+
+
+_gatherers = {}
+
+
 def gather_packed_events(local: torch.Tensor, dst: int = 0, group=None):
     """local: int32/uint32-as-int32 tensor [n, 2] = {end offset in this rank's stream, state}.
-    Returns on `dst` the list of per-rank tensors (rank order), elsewhere None.
-    Variable lengths are handled by a size all_gather followed by a padded all_gather."""
-    world = dist.get_world_size(group)
-    n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
-    sizes = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(sizes, n_local, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    cap = max(1, max(sizes))
-    padded = torch.zeros((cap, 2), dtype=local.dtype, device=local.device)
-    if local.shape[0]:
-        padded[: local.shape[0]] = local
-    bufs = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(bufs, padded, group=group)
-    if dist.get_rank(group) != dst:
-        return None
-    return [bufs[r][: sizes[r]] for r in range(world)]
+    Returns on `dst` the list of per-rank tensors (rank order; views valid until the next call), elsewhere None."""
+    g = _gatherers.get(id(group))
+    if g is None:
+        g = _gatherers[id(group)] = EventGatherer(group)
+    return g.gather(local, dst)
 
 
 def globalize(per_rank_events, ranges, offsets):

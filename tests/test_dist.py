@@ -53,6 +53,11 @@ def _worker(rank, world, port, q):
     got = gather_packed_events(local if rank == 0 else torch.zeros((0, 2), dtype=torch.int32), 0)
     if rank == 0:
         q.put(sum(int(g.shape[0]) for g in got))
+    # third round: rank 1 outgrows the agreed capacity -> every rank regrows and the gather is repeated
+    big = torch.arange(2 * 5000, dtype=torch.int32).reshape(5000, 2)
+    got = gather_packed_events(local if rank == 0 else big, 0)
+    if rank == 0:
+        q.put((int(got[0].shape[0]), int(got[1].shape[0]), got[1][-1].tolist(), got[0].tolist() == local.tolist()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -66,6 +71,7 @@ def test_gloo_two_rank_gather_and_globalize():
         p.start()
     ranges, tidx, end, state = q.get(timeout=120)
     n_second = q.get(timeout=120)
+    third = q.get(timeout=120)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -75,3 +81,4 @@ def test_gloo_two_rank_gather_and_globalize():
     assert end == [5, 100, 1, 150, 50, 1, 80]
     assert state == [7, 9, 3, 4, 11, 12, 13]
     assert n_second == 4
+    assert third == (4, 5000, [9998, 9999], True)
