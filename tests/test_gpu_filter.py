@@ -210,3 +210,48 @@ def test_pipelined_flat_search_equals_monolithic_batch_search():
     t2 = native.Tally()
     rc = a.L.ac_trie_search_batch(a.h, texts, n, 1, cb, C.cast(C.byref(t2), C.c_void_p))
     assert rc == 0 and (t1.events, t1.hash) == (t2.events, t2.hash) and t1.events == n
+
+
+def test_full_size_config2_device_resident_filter_equals_full_walk_and_planted_count():
+    """BASELINE config 2 at the size bench.py runs (1 GiB, 131,072 x 8 KiB): the two device paths must produce the
+    same event array; every haystack is a copy of one of 256 distinct ones, so the event total is 512 x the
+    oracle's total for the 256-haystack block."""
+    torch = pytest.importorskip("torch")
+    needles, hay, off = W.cfg2()
+    exp_block = sum(e[2] for e in oracle_hits([needles], split(hay, off)))
+    reps = 512
+    big = torch.from_numpy(hay).cuda().repeat(reps)
+    a = build([needles], 1)
+    _, n1 = a.search_device_uniform(big.data_ptr(), 256 * reps, 8192)
+    assert a.stats().filtered == 1 and a.stats().bytes == 1 << 30
+    assert n1 == exp_block * reps
+    ev1 = torch.empty((n1, 2), dtype=torch.int32, device="cuda")
+    a.copy_events(ev1.data_ptr(), n1)
+    a.set_filter(-1)
+    _, n2 = a.search_device_uniform(big.data_ptr(), 256 * reps, 8192)
+    assert a.stats().filtered == 0 and n2 == n1
+    ev2 = torch.empty((n2, 2), dtype=torch.int32, device="cuda")
+    a.copy_events(ev2.data_ptr(), n2)
+    torch.cuda.synchronize()
+    assert torch.equal(ev1, ev2)
+    # ascending end offsets (viewed as unsigned), and periodic with the block: event i+k == event i + 2 MiB
+    ends = ev1[:, 0].to(torch.int64) & 0xFFFFFFFF
+    assert bool((ends[1:] > ends[:-1]).all())
+    assert torch.equal(ends[exp_block:], ends[:-exp_block] + hay.size)
+    assert torch.equal(ev1[exp_block:, 1], ev1[:-exp_block, 1])
+
+
+def test_config4_shape_reduced_through_the_pipelined_batch_call():
+    """BASELINE config 4 shape (64 KiB haystacks, config-2 dictionary) at 8,192 haystacks = 512 MiB through
+    ac_trie_search_flat (eight pipelined slabs): totals against the oracle on a sample of haystacks."""
+    needles, hay, off = W.cfg2(n_hay=64, hay_len=65536, planted_per_hay=16, seed=44)
+    reps = 128
+    flat = np.tile(hay, reps)
+    offsets = W.offsets_uniform(64 * reps, 65536)
+    a = build([needles], 0)
+    t = a.search_flat_tally(flat.ctypes.data, offsets)
+    st = a.stats()
+    assert st.bytes == flat.size and st.filtered == 1
+    exp = oracle_hits([needles], split(hay, off))
+    assert t.events == reps * sum(e[2] for e in exp)
+    assert t.hits == reps * sum(len(e[0]) for e in exp)
