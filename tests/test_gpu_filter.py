@@ -255,3 +255,61 @@ def test_config4_shape_reduced_through_the_pipelined_batch_call():
     exp = oracle_hits([needles], split(hay, off))
     assert t.events == reps * sum(e[2] for e in exp)
     assert t.hits == reps * sum(len(e[0]) for e in exp)
+
+
+def test_full_size_config5_adversarial_closed_form_on_the_device():
+    """BASELINE config 5 at full size: a^1..a^4096 submitted (a^1..a^1024 accepted) over 256 MiB of 'a' — one event
+    per byte; event i ends at i+1 and reports min(i+1, 1024) patterns.  Checked on the device (2 GiB of events)."""
+    torch = pytest.importorskip("torch")
+    n = 256 << 20
+    pats = [b"a" * (i + 1) for i in range(4096)]
+    a = build([pats], 0)
+    assert a.info().n_patterns == 1024 and a.info().filter_word == 0      # shortest pattern is 1 byte: full walk only
+    text = torch.full((n,), ord("a"), dtype=torch.uint8, device="cuda")
+    ptr, ne = a.search_device(text.data_ptr(), np.array([0, n], dtype=np.uint64))
+    assert ne == n and a.stats().filtered == 0
+    ev = torch.empty((ne, 2), dtype=torch.int32, device="cuda")
+    a.copy_events(ev.data_ptr(), ne)
+    torch.cuda.synchronize()
+    ends = ev[:, 0].to(torch.int64) & 0xFFFFFFFF
+    assert torch.equal(ends, torch.arange(1, n + 1, device="cuda", dtype=torch.int64))
+    del ends
+    # state of event i reports min(i+1, 1024) patterns: 1024 distinct states, the deepest one from offset 1024 on
+    states = ev[:, 1]
+    head = states[:1024].cpu().numpy().astype(np.uint32)
+    sizes = [len(a.state_patterns(int(s))) for s in head]
+    assert sizes == list(range(1, 1025))
+    assert bool((states[1024:] == states[1023]).all())
+    events, hits = W.cfg5_expected(n)
+    assert events == ne and hits == sum(sizes) + (n - 1024) * 1024
+
+
+def test_full_size_config3_signatures_filter_equals_full_walk():
+    """BASELINE config 3: 100,000 binary signatures of 8..64 bytes (3.45 M states, 3.5 GB table) over a 1 GiB
+    binary haystack with one planted signature per MiB: both device paths give the same events, every planted
+    signature is found."""
+    torch = pytest.importorskip("torch")
+    pats, hay, off = W.cfg3()
+    a = build([pats], 1)
+    inf = a.info()
+    assert inf.n_states > 3_000_000 and inf.filter_word == 4 and inf.filter_l2_log2 > 0
+    text = torch.from_numpy(hay).cuda()
+    _, n1 = a.search_device(text.data_ptr(), off)
+    assert a.stats().filtered == 1
+    ev1 = torch.empty((n1, 2), dtype=torch.int32, device="cuda")
+    a.copy_events(ev1.data_ptr(), n1)
+    a.set_filter(-1)
+    _, n2 = a.search_device(text.data_ptr(), off)
+    assert a.stats().filtered == 0
+    ev2 = torch.empty((n2, 2), dtype=torch.int32, device="cuda")
+    a.copy_events(ev2.data_ptr(), n2)
+    torch.cuda.synchronize()
+    assert n1 == n2 and torch.equal(ev1, ev2)
+    assert n1 >= 1000                                   # 1,024 planted (a few may overwrite each other)
+    # every event really is a signature ending there (host check of all of them)
+    e = ev1.cpu().numpy().view(np.uint32)
+    for end, state in e[:: max(1, len(e) // 200)]:
+        lst = a.state_patterns(int(state))
+        assert lst, state
+        o, l = lst[0]
+        assert hay[int(end) - l:int(end)].tobytes() == pats[o]
