@@ -233,9 +233,10 @@ def main():
     sm = ShardedMatcher(aut)
 
     def step_resident():
-        ev = sm.scan_local_device(resident, offsets, stream=stream, uniform_len=HAY_LEN)
         if world > 1:
-            gather_packed_events(ev.contiguous(), 0)
+            n, _ = sm.scan_and_gather(resident, offsets, 0, stream=stream, uniform_len=HAY_LEN)
+            return n, aut.stats()
+        ev = sm.scan_local_device(resident, offsets, stream=stream, uniform_len=HAY_LEN)
         return ev.shape[0], aut.stats()
 
     def sync():

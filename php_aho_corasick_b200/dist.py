@@ -56,25 +56,35 @@ class EventGatherer:
             cap *= 2
         return cap
 
-    def gather(self, local: torch.Tensor, dst: int = 0):
+    def gather(self, local, dst: int = 0, n: int | None = None, fill=None, like: torch.Tensor | None = None):
+        """local: [n, 2] tensor of this rank's events — or, to save a device copy, `n` plus `fill(rows)`, a callable
+        that writes the first len(rows) events into the given rows of the send buffer (`like` gives device/dtype)."""
         world = dist.get_world_size(self.group)
-        n = int(local.shape[0])
+        if local is not None:
+            n = int(local.shape[0])
+            like = local
         if self.cap == 0:                        # first call: agree on a capacity
-            n_local = torch.tensor([n], dtype=torch.int64, device=local.device)
+            n_local = torch.tensor([n], dtype=torch.int64, device=like.device)
             sizes = [torch.zeros_like(n_local) for _ in range(world)]
             dist.all_gather(sizes, n_local, group=self.group)
-            self._ensure(self._grow(max(int(s.item()) for s in sizes)), world, local)
+            self._ensure(self._grow(max(int(s.item()) for s in sizes)), world, like)
         while True:
-            self._ensure(self.cap, world, local)
-            self.send[0, 0] = n
+            self._ensure(self.cap, world, like)
+            self.send[0].fill_(n)                # row 0 = the count (a fill kernel, no host-to-device copy)
             m = min(n, self.cap)
             if m:
-                self.send[1:1 + m].copy_(local[:m])
-            dist.all_gather([self.recv[r] for r in range(world)], self.send, group=self.group)
+                if fill is not None:
+                    fill(self.send[1:1 + m])
+                else:
+                    self.send[1:1 + m].copy_(local[:m])
+            try:
+                dist.all_gather_into_tensor(self.recv.view(world * (self.cap + 1), 2), self.send, group=self.group)
+            except (RuntimeError, NotImplementedError, AttributeError):
+                dist.all_gather([self.recv[r] for r in range(world)], self.send, group=self.group)
             sizes = [int(x) for x in self.recv[:, 0, 0].cpu().tolist()]
             if max(sizes) <= self.cap:
                 break
-            self._ensure(self._grow(max(sizes)), world, local)     # same decision on every rank
+            self._ensure(self._grow(max(sizes)), world, like)      # same decision on every rank
         if dist.get_rank(self.group) != dst:
             return None
         return [self.recv[r, 1:1 + sizes[r]] for r in range(world)]
@@ -123,6 +133,7 @@ class ShardedMatcher:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._ev = None
+        self._gatherer = None
 
     def scan_local_device(self, dev_tensor: torch.Tensor, local_offsets, first_only=False, stream=0, uniform_len=0):
         """Scans this rank's shard (uint8 CUDA tensor, haystacks end to end). -> int32 CUDA tensor [n,2]"""
@@ -136,6 +147,20 @@ class ShardedMatcher:
             self._ev = torch.empty((max(n, 1024), 2), dtype=torch.int32, device=dev_tensor.device)
         self.aut.copy_events(self._ev.data_ptr(), n, stream=stream)
         return self._ev[:n]
+
+    def scan_and_gather(self, dev_tensor: torch.Tensor, local_offsets, dst: int = 0, stream=0, uniform_len=0):
+        """Scans this rank's shard and gathers every rank's packed events on `dst` (list in rank order, views valid
+        until the next call; None elsewhere).  The events go from the library's buffer straight into the send buffer."""
+        if uniform_len:
+            _, n = self.aut.search_device_uniform(dev_tensor.data_ptr(), len(local_offsets) - 1, int(uniform_len), stream=stream)
+        else:
+            _, n = self.aut.search_device(dev_tensor.data_ptr(), local_offsets, stream=stream)
+        if self._gatherer is None:
+            self._gatherer = EventGatherer(self.group)
+        like = torch.empty((0, 2), dtype=torch.int32, device=dev_tensor.device)
+        got = self._gatherer.gather(None, dst, n=n, like=like,
+                                    fill=lambda rows: self.aut.copy_events(rows.data_ptr(), rows.shape[0], stream=stream))
+        return n, got
 
     def match(self, flat: np.ndarray, offsets, first_only=False):
         """flat: host uint8 array of the whole batch; offsets uint64[n+1]."""
