@@ -284,6 +284,10 @@ int acb200_set_ilp(AC_TRIE_t *thiz, int ilp);
  * Results are identical either way.                                                     */
 int acb200_set_filter(AC_TRIE_t *thiz, int mode);
 
+/* Parts a prefiltered scan is cut into (the filter of part p+1 overlaps the verification of part p on a
+ * second stream): 0 = automatic (currently 1: overlapping did not pay on B200), 1..8 = fixed. */
+int acb200_set_parts(AC_TRIE_t *thiz, unsigned parts);
+
 const char *acb200_version(void);
 
 #ifdef __cplusplus

@@ -352,6 +352,12 @@ int acb200_set_filter(AC_TRIE_t *t, int mode)
     return 0;
 }
 
+int acb200_set_parts(AC_TRIE_t *t, unsigned parts)
+{
+    t->engine.tune_parts = parts;
+    return 0;
+}
+
 void ac_trie_release(AC_TRIE_t *t)
 {
     delete t;

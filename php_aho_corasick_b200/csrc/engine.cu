@@ -69,6 +69,8 @@ void Engine::release()
     for (auto &e : ev_slab_) if (e) { cudaEventDestroy(EV(e)); e = nullptr; }
     for (int b = 0; b < 2; ++b) { cudaFree(d_slab_[b]); d_slab_[b] = nullptr; slab_cap_[b] = 0; }
     if (copy_stream_) { cudaStreamDestroy(S(copy_stream_)); copy_stream_ = nullptr; }
+    for (auto &e : ev_part_) if (e) { cudaEventDestroy(EV(e)); e = nullptr; }
+    if (verify_stream_) { cudaStreamDestroy(S(verify_stream_)); verify_stream_ = nullptr; }
     if (stream_) cudaStreamDestroy(S(stream_));
     d_table_ = nullptr; d_cls_ = nullptr; d_text_ = nullptr; d_off_ = nullptr; d_first_ = nullptr;
     d_events_ = nullptr; d_tiles_ = nullptr; d_counters_ = nullptr;
@@ -585,35 +587,70 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     va.tile_off = d_tile_len_ + verify_tiles_cap_;
     va.block_sum = d_tile_len_ + 2 * verify_tiles_cap_;
 
+    // A stream can be cut into parts: while ac_filter_kernel streams part p+1, the collect and walk kernels of
+    // part p run on a second stream; offsets and emit run once, after everything.  Measured on B200 this does
+    // NOT pay (1 GiB: 0.42 ms in one part, 0.45 / 0.58 / 0.59 ms in 2 / 4 / 8): resident walk CTAs delay the
+    // next filter launch's 1,024-thread, 220 KB CTAs.  One part unless asked otherwise (acb200_set_parts).
+    const uint32_t n_parts = tune_parts ? std::min<uint32_t>(tune_parts, 8u) : 1u;
+    const uint32_t part_tiles = ((n_tiles + n_parts - 1) / n_parts + 31u) & ~31u;
+    cudaStream_t st2 = st;
+    if (n_parts > 1) {
+        if (!verify_stream_) {
+            cudaStream_t vs;
+            CU_OK(cudaStreamCreateWithFlags(&vs, cudaStreamNonBlocking));
+            verify_stream_ = vs;
+            for (auto &e : ev_part_) { cudaEvent_t x; CU_OK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming)); e = x; }
+        }
+        st2 = S(verify_stream_);
+    }
     const unsigned warps_per_cta = SCAN_THREADS / 32;
-    const unsigned grid_f = std::min<uint32_t>((n_spans + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
     const unsigned tiles_per_cta = COLLECT_THREADS / 32;
-    const unsigned grid_c = std::min<uint32_t>((n_tiles + tiles_per_cta - 1) / tiles_per_cta, (uint32_t)n_sms_ * 2u);
-    const unsigned grid_n = std::min<uint32_t>((n_tiles + COUNT_THREADS / 32 - 1) / (COUNT_THREADS / 32), (uint32_t)n_sms_ * 8u);
     const unsigned grid_w = (unsigned)n_sms_ * 8u;
     const unsigned grid_e = (n_tiles + EMIT_THREADS - 1) / EMIT_THREADS;
+    const unsigned grid_n = std::min<uint32_t>((n_tiles + COUNT_THREADS / 32 - 1) / (COUNT_THREADS / 32), (uint32_t)n_sms_ * 8u);
 
     for (int attempt = 0; attempt < 2; ++attempt) {
         a.out = (uint2 *)d_events_;
         a.capacity = (uint32_t)std::min<size_t>(events_cap_, 0xffffffffu);
-        CU_OK(cudaMemsetAsync(d_counters_, 0, 32, st));
+        CU_OK(cudaMemsetAsync(d_counters_, 0, 64, st));
         CU_OK(cudaMemsetAsync(d_tile_len_, 0, (size_t)n_tiles * sizeof(uint32_t), st));   // the walk kernel adds to both
         CU_OK(cudaMemsetAsync(va.block_sum, 0, (size_t)((n_tiles + EMIT_THREADS - 1) / EMIT_THREADS) * sizeof(uint32_t), st));
         CU_OK(cudaEventRecord(EV(ev_[0]), st));
-        if (attempt == 0) {          // the bit planes survive a regrow of the event buffer
-            if (W == 8) launch_filter_k<8>(fa, d_l2_ != nullptr, grid_f, st);
-            else launch_filter_k<4>(fa, d_l2_ != nullptr, grid_f, st);
-            stats.kernel_launches += 1;
+        for (uint32_t p = 0; p < n_parts; ++p) {
+            const uint32_t t0 = std::min(p * part_tiles, n_tiles), t1 = std::min(t0 + part_tiles, n_tiles);
+            if (t0 == t1) continue;
+            if (attempt == 0) {      // the bit planes survive a regrow of the event buffer
+                fa.span_begin = t0 * 32u;
+                fa.span_end = std::min(t1 * 32u, n_spans);
+                const unsigned grid_f = std::min<uint32_t>((fa.span_end - fa.span_begin + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
+                if (W == 8) launch_filter_k<8>(fa, d_l2_ != nullptr, grid_f, st);
+                else launch_filter_k<4>(fa, d_l2_ != nullptr, grid_f, st);
+                stats.kernel_launches += 1;
+            }
+            if (p == n_parts - 1) CU_OK(cudaEventRecord(EV(ev_[4]), st));      // the last filter launch is done
+            if (n_parts > 1) {
+                CU_OK(cudaEventRecord(EV(ev_part_[p]), st));
+                CU_OK(cudaStreamWaitEvent(st2, EV(ev_part_[p]), 0));
+            }
+            va.tile_begin = t0; va.tile_end = t1;
+            va.item_base = t0 * VER_DENSE_MAX;
+            va.counter_slot = 8u + p;
+            va.want_end_state = (n_hay == 1 && p == n_parts - 1) ? 1u : 0u;
+            const unsigned grid_c = std::min<uint32_t>((t1 - t0 + tiles_per_cta - 1) / tiles_per_cta, (uint32_t)n_sms_ * 2u);
+            if (W == 8) ac_collect_kernel<8><<<grid_c, COLLECT_THREADS, 0, st2>>>(va);
+            else ac_collect_kernel<4><<<grid_c, COLLECT_THREADS, 0, st2>>>(va);
+            if (entry_bytes_ == 2) {
+                if (W == 8) launch_walk_k<uint16_t, 8>(va, range_map_, grid_w, st2);
+                else launch_walk_k<uint16_t, 4>(va, range_map_, grid_w, st2);
+            } else {
+                if (W == 8) launch_walk_k<uint32_t, 8>(va, range_map_, grid_w, st2);
+                else launch_walk_k<uint32_t, 4>(va, range_map_, grid_w, st2);
+            }
+            stats.kernel_launches += 2;
         }
-        CU_OK(cudaEventRecord(EV(ev_[4]), st));
-        if (W == 8) ac_collect_kernel<8><<<grid_c, COLLECT_THREADS, 0, st>>>(va);
-        else ac_collect_kernel<4><<<grid_c, COLLECT_THREADS, 0, st>>>(va);
-        if (entry_bytes_ == 2) {
-            if (W == 8) launch_walk_k<uint16_t, 8>(va, range_map_, grid_w, st);
-            else launch_walk_k<uint16_t, 4>(va, range_map_, grid_w, st);
-        } else {
-            if (W == 8) launch_walk_k<uint32_t, 8>(va, range_map_, grid_w, st);
-            else launch_walk_k<uint32_t, 4>(va, range_map_, grid_w, st);
+        if (n_parts > 1) {
+            CU_OK(cudaEventRecord(EV(ev_part_[8]), st2));
+            CU_OK(cudaStreamWaitEvent(st, EV(ev_part_[8]), 0));
         }
         CU_OK(cudaEventRecord(EV(ev_[5]), st));
         ac_offsets_kernel<<<grid_e, EMIT_THREADS, 0, st>>>(va);
@@ -626,7 +663,7 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
         }
         CU_OK(cudaGetLastError());
         CU_OK(cudaEventRecord(EV(ev_[1]), st));
-        stats.kernel_launches += 4;
+        stats.kernel_launches += 2;
         CU_OK(cudaMemcpyAsync(h_counters_, d_counters_, 32, cudaMemcpyDeviceToHost, st));
         CU_OK(cudaStreamSynchronize(st));
         float ms_f = 0, ms_v = 0, ms_r = 0;

@@ -57,6 +57,7 @@ public:
     uint32_t tune_smem_bytes = 0;
     int tune_ilp = 0;              // 0 auto, 1 one slice per lane, 4 four slices per lane
     int tune_filter = 0;           // 0 auto, 1 always use the gram prefilter when the dictionary allows, -1 never
+    uint32_t tune_parts = 0;       // 0 auto; parts a filtered scan is cut into (filter of part p+1 overlaps verification of part p)
 
 private:
     bool ensure_text(size_t bytes);
@@ -113,6 +114,8 @@ private:
     uint8_t *h_stage_ = nullptr;  size_t stage_cap_ = 0;          // pinned staging for pageable input
     uint8_t *d_slab_[2] = {nullptr, nullptr}; size_t slab_cap_[2] = {0, 0};   // double-buffered haystack slabs
     void *copy_stream_ = nullptr;                                  // cudaStream_t of the slab uploads
+    void *verify_stream_ = nullptr;                                // cudaStream_t of the collect / walk kernels of a multi-part scan
+    void *ev_part_[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void *ev_slab_[4] = {nullptr, nullptr, nullptr, nullptr};     // per buffer: upload started / finished
     std::vector<uint32_t> off32_;
 

@@ -69,6 +69,7 @@ struct FilterArgs {
     uint32_t l2_shift;            // 32 - log2(bits of level 2)
     uint32_t *mask;               // n_spans x (16/W) words: plane j bit c <=> word (c*(16/W) + j) of the span
     uint32_t n_spans;             // ceil(total / 512)
+    uint32_t span_begin, span_end;// this launch filters spans [span_begin, span_end)
     uint32_t *counters;           // [3] += flagged words
 };
 
@@ -108,12 +109,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const Filter
         return p;
     };
 
-    const uint32_t n_full = a.total / SPAN_BYTES;             // spans that lie completely inside the stream
+    const uint32_t n_full_all = a.total / SPAN_BYTES;         // spans that lie completely inside the stream
+    const uint32_t n_full = min(n_full_all, a.span_end);
     const uint32_t n_warps = gridDim.x * (SCAN_THREADS / 32);
     const uint32_t warp = blockIdx.x * (SCAN_THREADS / 32) + (tid >> 5);
     uint32_t flagged = 0;
 
-    for (uint32_t g0 = warp; g0 < n_full; g0 += n_warps * FILTER_UNROLL) {
+    for (uint32_t g0 = a.span_begin + warp; g0 < n_full; g0 += n_warps * FILTER_UNROLL) {
         uint4 v[FILTER_UNROLL];
 #pragma unroll
         for (int u = 0; u < FILTER_UNROLL; ++u) {
@@ -142,7 +144,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const Filter
 
     // The last, partial span: complete 16-byte chunks are tested, the partial chunk at the very end is not
     // read at all — its words are simply handed on to verification.
-    if (n_full < a.n_spans && warp == (n_full % n_warps)) {
+    if (n_full_all < a.n_spans && n_full_all >= a.span_begin && n_full_all < a.span_end && warp == (n_full_all % n_warps)) {
+        const uint32_t n_full = n_full_all;
         const uint32_t n16 = a.total >> 4;
         const uint32_t c = n_full * 32u + lane;
         uint4 v = make_uint4(0, 0, 0, 0);
@@ -172,6 +175,9 @@ struct VerifyArgs {
     const uint32_t *mask;         // bit planes written by ac_filter_kernel
     uint32_t n_spans;             // 512-byte spans in the stream
     uint32_t n_tiles;             // 16 KiB tiles = ceil(n_spans / 32)
+    uint32_t tile_begin, tile_end;// collect / walk launches work on the tiles [tile_begin, tile_end) of one part
+    uint32_t item_base;           // that part's region of items / recs starts here
+    uint32_t counter_slot;        // counters[counter_slot] = items of the part
     uint32_t dense_max;           // more flagged words than this in a tile: hand on the tile's spans instead
     uint32_t warm;                // warm-up bytes before a flagged word's end offsets (halo rounded up to W)
     uint32_t want_end_state;      // also compute the state at the end of the stream (counters[2])
@@ -198,7 +204,7 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
 #pragma unroll
         for (int j = 0; j < NB; ++j) pl[j] = 0;
         const uint32_t span = tile * 32u + lane;
-        if (tile < a.n_tiles && span < a.n_spans) {
+        if (tile < a.tile_end && span < a.n_spans) {
             if (NB == 2) {
                 const uint2 m = __ldg(reinterpret_cast<const uint2 *>(a.mask) + span);
                 pl[0] = m.x; pl[1] = m.y;
@@ -211,12 +217,12 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
 
     // a CTA iteration takes 32 consecutive tiles, one per warp; the loop bound is CTA-uniform
     uint32_t planes[NB], next_planes[NB];
-    load_planes(blockIdx.x * N_WARPS + warp, planes);
-    for (uint32_t tile0 = blockIdx.x * N_WARPS; tile0 < a.n_tiles; tile0 += gridDim.x * N_WARPS) {
+    load_planes(a.tile_begin + blockIdx.x * N_WARPS + warp, planes);
+    for (uint32_t tile0 = a.tile_begin + blockIdx.x * N_WARPS; tile0 < a.tile_end; tile0 += gridDim.x * N_WARPS) {
         const uint32_t tile = tile0 + warp;
         load_planes(tile + gridDim.x * N_WARPS, next_planes);      // in flight while this tile is compacted
         const uint32_t span = tile * 32u + lane;
-        const bool active = tile < a.n_tiles && span < a.n_spans;
+        const bool active = tile < a.tile_end && span < a.n_spans;
         uint32_t cnt = 0;
 #pragma unroll
         for (int j = 0; j < NB; ++j) cnt += __popc(planes[j]);
@@ -241,10 +247,10 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
             if (lane >= d) wincl += u;
         }
         const uint32_t cta_total = __shfl_sync(0xffffffffu, wincl, 31);
-        if (threadIdx.x == 0) s_base = cta_total ? atomicAdd(&a.s.counters[5], cta_total) : 0u;
+        if (threadIdx.x == 0) s_base = a.item_base + (cta_total ? atomicAdd(&a.s.counters[a.counter_slot], cta_total) : 0u);
         __syncthreads();
         const uint32_t base = s_base + __shfl_sync(0xffffffffu, wincl - v, warp);
-        if (lane == 0 && tile < a.n_tiles) a.desc[tile] = make_uint2(base, n);
+        if (lane == 0 && tile < a.tile_end) a.desc[tile] = make_uint2(base, n);
         if (n == 0) {
         } else if (dense) {
             ++dense_tiles;
@@ -444,7 +450,7 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
     st.ncls = a.s.ncls; st.lo = a.s.range_lo; st.n_used = a.s.n_used;
     st.final_bound = a.s.final_bound; st.root = a.s.root;
 
-    const uint32_t n_items = a.s.counters[5];
+    const uint32_t n_items = a.s.counters[a.counter_slot];
     const uint32_t n_threads = gridDim.x * WALK_THREADS;
     constexpr int K = WALK_ILP;
     // a thread takes K consecutive items and walks them in lockstep
@@ -454,7 +460,7 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
         bool all_lock = true;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            item[k] = (i0 + k < n_items) ? a.items[i0 + k] : ITEM_NONE;
+            item[k] = (i0 + k < n_items) ? a.items[a.item_base + i0 + k] : ITEM_NONE;
             rs[k] = 0; w0[k] = 0; lock[k] = false;
             if (item[k] != ITEM_NONE && !(item[k] & ITEM_SPAN)) {
                 rs[k] = (item[k] + 1u) * W;            // the W end offsets owned by word k are rs+1 .. rs+W
@@ -497,7 +503,7 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
         for (int k = 0; k < K; ++k) {
             if (i0 + k < n_items) {
                 const uint32_t rel = ev[k].cnt ? ev[k].e0p - item_origin<W>(item[k]) : 0u;
-                a.recs[i0 + k] = make_uint2(ev[k].e0s, (min(ev[k].cnt, 0xffffu) << 16) | (rel & 0xffffu));
+                a.recs[a.item_base + i0 + k] = make_uint2(ev[k].e0s, (min(ev[k].cnt, 0xffffu) << 16) | (rel & 0xffffu));
                 if (ev[k].cnt) atomicAdd(&a.tile_len[item_tile<W>(item[k])], ev[k].cnt);   // events per tile, for the offsets
             }
         }

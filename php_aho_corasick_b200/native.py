@@ -73,7 +73,7 @@ EXPORTS = [
     "acb200_state_patterns", "acb200_info", "acb200_last_stats", "acb200_last_error",
     "acb200_set_device", "acb200_device_count", "acb200_host_alloc", "acb200_host_free",
     "acb200_set_tuning", "acb200_version", "acb200_copy_events", "acb200_tally_cb", "acb200_tally_match_cb", "acb200_set_ilp",
-    "acb200_set_filter", "acb200_search_device_uniform",
+    "acb200_set_filter", "acb200_search_device_uniform", "acb200_set_parts",
 ]
 
 
@@ -122,6 +122,7 @@ def lib() -> C.CDLL:
     L.acb200_version.restype = C.c_char_p
     L.acb200_set_ilp.argtypes = [C.c_void_p, C.c_int]
     L.acb200_set_filter.argtypes = [C.c_void_p, C.c_int]
+    L.acb200_set_parts.argtypes = [C.c_void_p, C.c_uint]
     L.acb200_copy_events.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.acb200_copy_events.restype = C.c_long
     _lib = L
@@ -190,6 +191,10 @@ class Automaton:
         self.L.acb200_set_tuning(self.h, int(chunk_bytes), int(smem_table_bytes))
         if ilp is not None:
             self.L.acb200_set_ilp(self.h, int(ilp))
+
+    def set_parts(self, parts: int) -> None:
+        """parts a prefiltered scan is cut into (0 automatic)"""
+        self.L.acb200_set_parts(self.h, int(parts))
 
     def set_filter(self, mode: int) -> None:
         """0 automatic, 1 prefilter whenever the dictionary allows, -1 always the full automaton walk"""

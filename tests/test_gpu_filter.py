@@ -85,6 +85,22 @@ def test_random_dictionaries_both_word_sizes_ragged_batches(seed):
         a.release()
 
 
+@pytest.mark.parametrize("parts", [2, 5, 8])
+def test_multi_part_scans_on_two_streams_give_the_same_events(parts):
+    needles, hay, off = W.cfg2(n_hay=512, hay_len=8192, planted_per_hay=8, seed=12)
+    a = build([needles], 1)
+    ev1 = a.search_events(hay, off)
+    a.set_parts(parts)
+    ev2 = a.search_events(hay, off)
+    assert 3 * 2 + 2 <= a.stats().kernel_launches <= 3 * parts + 2      # parts are rounded to 32 tiles; empty ones are skipped
+    assert np.array_equal(ev1, ev2)
+    one = np.array([0, hay.size], dtype=np.uint64)      # one haystack: the end state is computed by the last part
+    rc, got = a.search_callback(hay[:100_000].tobytes())
+    a.set_parts(1)
+    rc1, got1 = a.search_callback(hay[:100_000].tobytes())
+    assert got == got1
+
+
 def test_every_word_flagged_falls_back_to_whole_tile_walks():
     # nested patterns over one repeated byte: every aligned word is a pattern word, every offset an event
     pats = [b"a" * n for n in range(16, 41)]
