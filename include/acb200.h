@@ -194,6 +194,29 @@ int acb200_search_device_uniform(AC_TRIE_t *thiz, const void *d_bytes, size_t n,
                                  size_t hay_len, int first_only, void *stream,
                                  const void **d_events, size_t *n_events);
 
+/* One reported pattern occurrence, as the reference's callback would have recorded it
+ * (src/php_ahocorasick.c:555-584): haystack index, exclusive end offset inside the haystack
+ * ("pos"), start offset ("start_postion" = pos - length) and the pattern's index in acceptance
+ * order (acb200_pattern() returns its AC_PATTERN_t: id, aux, bytes).                       */
+typedef struct acb200_hit
+{
+    uint32_t text_idx;
+    uint32_t end;
+    uint32_t start;
+    uint32_t pattern;
+} ACB200_HIT_t;
+
+/* Hit-level search: the events are expanded to hits ON THE DEVICE (every pattern of every event,
+ * longest first inside an event, events in ascending order) and only the hit columns come back.
+ * Fills up to `cap` hits and stores the total in *n_hits (which may exceed cap).  findAll only.
+ * Inputs as ac_trie_search_flat.  Returns 0 / -1.                                           */
+int acb200_search_hits(AC_TRIE_t *thiz, const char *bytes, const uint64_t *offsets, size_t n,
+                       ACB200_HIT_t *hits, size_t cap, size_t *n_hits);
+
+/* Accepted pattern number `index` (acceptance order = the order of successful ac_trie_add calls);
+ * NULL if out of range or not finalized.                                                     */
+const AC_PATTERN_t *acb200_pattern(const AC_TRIE_t *thiz, size_t index);
+
 /* Copies up to max_events packed {uint32 end_in_buffer, uint32 state} records of the most recent
  * device-resident search into the caller's DEVICE buffer `d_dst` (async on `stream`, NULL = the
  * handle's stream).  Returns the number of records copied, or -1.                      */
@@ -254,8 +277,8 @@ typedef struct acb200_stats
     float verify_ms;          /* device time of the verify kernel (0 if unused) */
     uint64_t flagged_words;   /* aligned words the prefilter handed to verification */
     uint64_t dense_tiles;     /* 16 KiB tiles handed to verification as whole spans */
-    float reorder_ms;         /* device time of the run reorder kernel (0 if unused) */
-    uint32_t reserved_;
+    float reorder_ms;         /* device time of the offsets + emit kernels (0 if unused) */
+    float expand_ms;          /* device time of the hit expansion kernels (acb200_search_hits) */
 } ACB200_STATS_t;
 int acb200_last_stats(const AC_TRIE_t *thiz, ACB200_STATS_t *out);
 

@@ -260,11 +260,13 @@ void HostTrie::flatten(FlatAutomaton &flat) {
         flat.out_off[i + 1] = flat.out_off[i] + cnt;
     }
     flat.out_pat.resize(flat.out_off[n_final]);
+    flat.out_idx.resize(flat.out_off[n_final]);
+    flat.accepted = patterns_;
     for (uint32_t i = 0; i < n_final; ++i) {
         uint64_t o = flat.out_off[i];
         uint32_t v = old_of_final[i];
-        if (own_[v] >= 0) flat.out_pat[o++] = patterns_[own_[v]];
-        for (uint32_t d = dlink[v]; d != NONE; d = dlink[d]) flat.out_pat[o++] = patterns_[own_[d]];
+        if (own_[v] >= 0) { flat.out_idx[o] = (uint32_t)own_[v]; flat.out_pat[o++] = patterns_[own_[v]]; }
+        for (uint32_t d = dlink[v]; d != NONE; d = dlink[d]) { flat.out_idx[o] = (uint32_t)own_[d]; flat.out_pat[o++] = patterns_[own_[d]]; }
     }
 
     build_filter(flat);

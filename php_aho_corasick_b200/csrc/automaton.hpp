@@ -61,6 +61,8 @@ struct FlatAutomaton {
     // output lists for final states (index: state - 1), longest pattern first
     std::vector<uint64_t> out_off;
     std::vector<AC_PATTERN_t> out_pat;
+    std::vector<uint32_t> out_idx;         // same order as out_pat: index of the pattern in acceptance order
+    std::vector<AC_PATTERN_t> accepted;    // accepted patterns in acceptance order (what out_idx indexes)
 
     // Gram prefilter (filter_kernels.cuh).  With every accepted pattern at least 2W bytes long
     // (W = 8 or 4), a match that ends at stream offset p contains the aligned W-byte word k with

@@ -252,6 +252,25 @@ int acb200_search_events(AC_TRIE_t *t, const char *bytes, const uint64_t *offset
     return 0;
 }
 
+int acb200_search_hits(AC_TRIE_t *t, const char *bytes, const uint64_t *offsets, size_t n,
+                       ACB200_HIT_t *hits, size_t cap, size_t *n_hits)
+{
+    if (t->open) { set_error("automaton is not finalized"); return -1; }
+    if (!t->device_ok) return -1;
+    if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return -1; }
+    if (!t->engine.scan_host(bytes, offsets, n, false, ROOT_STATE)) return -1;
+    size_t total = 0;
+    if (!t->engine.expand_hits_to_host(n, hits, cap, &total)) return -1;
+    if (n_hits) *n_hits = total;
+    return 0;
+}
+
+const AC_PATTERN_t *acb200_pattern(const AC_TRIE_t *t, size_t index)
+{
+    if (t->open || index >= t->flat.accepted.size()) return nullptr;
+    return &t->flat.accepted[index];
+}
+
 int acb200_search_device(AC_TRIE_t *t, const void *d_bytes, const uint64_t *offsets, size_t n,
                          int first_only, void *stream, const void **d_events, size_t *n_events)
 {

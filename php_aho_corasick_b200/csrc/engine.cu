@@ -59,6 +59,9 @@ void Engine::release()
     cudaFree(d_table_); cudaFree(d_cls_); cudaFree(d_text_); cudaFree(d_off_);
     cudaFree(d_first_); cudaFree(d_events_); cudaFree(d_tiles_); cudaFree(d_counters_);
     cudaFree(d_l1_); cudaFree(d_l2_); cudaFree(d_mask_);
+    cudaFree(d_out_off_); cudaFree(d_out_idx_); cudaFree(d_pat_len_); cudaFree(d_hit_sums_); cudaFree(d_hits_); cudaFree(d_hit_total_);
+    d_out_off_ = nullptr; d_out_idx_ = nullptr; d_pat_len_ = nullptr; d_hit_sums_ = nullptr; d_hits_ = nullptr; d_hit_total_ = nullptr;
+    hit_sums_cap_ = 0; hits_cap_ = 0;
     cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_);
     d_l1_ = nullptr; d_l2_ = nullptr; d_mask_ = nullptr; mask_cap_ = 0;
     d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; verify_tiles_cap_ = 0;
@@ -202,6 +205,22 @@ bool Engine::build(const FlatAutomaton &f)
     CU_OK(cudaFuncSetAttribute(ac_scan_kernel_x4<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     CU_OK(cudaFuncSetAttribute(ac_scan_kernel_x4<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     CU_OK(cudaFuncSetAttribute(ac_scan_kernel_x4<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+
+    // output lists for the device-side hit expansion
+    {
+        std::vector<uint32_t> off32(f.out_off.size());
+        for (size_t i = 0; i < f.out_off.size(); ++i) off32[i] = (uint32_t)f.out_off[i];
+        std::vector<uint32_t> len32(f.accepted.size());
+        for (size_t i = 0; i < f.accepted.size(); ++i) len32[i] = (uint32_t)f.accepted[i].ptext.length;
+        CU_OK(cudaMalloc(&d_out_off_, std::max<size_t>(1, off32.size()) * sizeof(uint32_t)));
+        CU_OK(cudaMalloc(&d_out_idx_, std::max<size_t>(1, f.out_idx.size()) * sizeof(uint32_t)));
+        CU_OK(cudaMalloc(&d_pat_len_, std::max<size_t>(1, len32.size()) * sizeof(uint32_t)));
+        CU_OK(cudaMalloc(&d_hit_total_, sizeof(unsigned long long)));
+        CU_OK(cudaMemcpyAsync(d_out_off_, off32.data(), off32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        if (!f.out_idx.empty()) CU_OK(cudaMemcpyAsync(d_out_idx_, f.out_idx.data(), f.out_idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        if (!len32.empty()) CU_OK(cudaMemcpyAsync(d_pat_len_, len32.data(), len32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CU_OK(cudaStreamSynchronize(st));
+    }
 
     // gram prefilter tables
     filter_w_ = f.filter_w; l1_bits_ = f.l1_bits; l2_log2_ = f.l2_log2;
@@ -381,7 +400,7 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     stats.bytes = total; stats.events = 0; stats.kernel_launches = 0; stats.kernel_ms = 0;
     stats.halo_bytes = halo_;
     stats.filtered = 0; stats.filter_ms = 0; stats.verify_ms = 0; stats.flagged_words = 0; stats.dense_tiles = 0;
-    stats.reorder_ms = 0; stats.reserved_ = 0;
+    stats.reorder_ms = 0; stats.expand_ms = 0;
     if (total == 0) { stats.chunk_bytes = 0; return true; }
 
     // Gram prefilter: needs an eligible dictionary and a walk that starts at the root.  Automatic mode
@@ -689,6 +708,59 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     return false;
 }
 
+bool Engine::expand_hits_to_host(size_t n_hay, ACB200_HIT_t *hits, size_t cap, size_t *n_hits)
+{
+    CU_OK(cudaSetDevice(device_));
+    cudaStream_t st = S(stream_);
+    *n_hits = 0;
+    stats.expand_ms = 0;
+    if (n_events_ == 0) return true;
+    const uint32_t n_blocks = (uint32_t)((n_events_ + HIT_THREADS - 1) / HIT_THREADS);
+    if (n_blocks > hit_sums_cap_) {
+        cudaFree(d_hit_sums_); d_hit_sums_ = nullptr; hit_sums_cap_ = 0;
+        CU_OK(cudaMalloc(&d_hit_sums_, (size_t)(n_blocks + n_blocks / 4 + 64) * sizeof(uint32_t)));
+        hit_sums_cap_ = n_blocks + n_blocks / 4 + 64;
+    }
+    HitArgs ha{};
+    ha.events = (const uint2 *)d_events_;
+    ha.n_events = (uint32_t)n_events_;
+    ha.out_off = d_out_off_; ha.out_idx = d_out_idx_; ha.pat_len = d_pat_len_;
+    ha.hay_off = last_uniform_len_ ? nullptr : d_off_;
+    ha.n_hay = (uint32_t)n_hay; ha.uniform_len = last_uniform_len_;
+    ha.block_sum = d_hit_sums_;
+    ha.total = d_hit_total_;
+    unsigned long long total = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        ha.hits = (uint4 *)d_hits_;
+        ha.capacity = hits_cap_;
+        CU_OK(cudaEventRecord(EV(ev_[2]), st));
+        ac_hit_count_kernel<<<n_blocks, HIT_THREADS, 0, st>>>(ha);
+        ac_hit_write_kernel<<<n_blocks, HIT_THREADS, 0, st>>>(ha);
+        CU_OK(cudaGetLastError());
+        CU_OK(cudaEventRecord(EV(ev_[3]), st));
+        CU_OK(cudaMemcpyAsync(&total, d_hit_total_, sizeof(total), cudaMemcpyDeviceToHost, st));
+        CU_OK(cudaStreamSynchronize(st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, EV(ev_[2]), EV(ev_[3]));
+        stats.expand_ms += ms;
+        stats.kernel_launches += 2;
+        if (total <= hits_cap_) break;
+        // hit buffer too small: grow to what the caller can take (plus the exact need if that is smaller)
+        const size_t want = (size_t)std::min<unsigned long long>(total, std::max<unsigned long long>(cap, 1));
+        if (want <= hits_cap_) break;            // the caller's buffer is the limit: a truncated expansion is enough
+        cudaFree(d_hits_); d_hits_ = nullptr; hits_cap_ = 0;
+        CU_OK(cudaMalloc(&d_hits_, want * sizeof(ACB200_HIT_t)));
+        hits_cap_ = want;
+    }
+    *n_hits = (size_t)total;
+    const size_t n_copy = (size_t)std::min<unsigned long long>(std::min<unsigned long long>(total, cap), hits_cap_);
+    if (n_copy) {
+        CU_OK(cudaMemcpyAsync(hits, d_hits_, n_copy * sizeof(ACB200_HIT_t), cudaMemcpyDeviceToHost, st));
+        CU_OK(cudaStreamSynchronize(st));
+    }
+    return true;
+}
+
 bool Engine::copy_events_to(void *d_dst, size_t n, void *stream)
 {
     CU_OK(cudaSetDevice(device_));
@@ -791,6 +863,7 @@ bool Engine::scan_host(const char *bytes, const uint64_t *offsets, size_t n, boo
     if (!ensure_text(total + 64)) return false;
     uint32_t uniform_len = 0;
     if (!upload_offsets(offsets, n, &uniform_len)) return false;
+    last_uniform_len_ = uniform_len;
     CU_OK(cudaEventRecord(EV(ev_[2]), st));
     if (total) CU_OK(cudaMemcpyAsync(d_text_, bytes, total, cudaMemcpyHostToDevice, st));
     CU_OK(cudaEventRecord(EV(ev_[3]), st));

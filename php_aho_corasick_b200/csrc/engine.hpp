@@ -46,6 +46,9 @@ public:
     bool scan_device_uniform(const void *d_bytes, size_t n, size_t hay_len, bool first_only, void *stream);
 
     bool copy_events_to(void *d_dst, size_t n, void *stream);
+    // Expands the events of the most recent scan_host() into hits on the device and copies up to `cap` of them
+    // to `hits` (host).  *n_hits receives the total.
+    bool expand_hits_to_host(size_t n_hay, ACB200_HIT_t *hits, size_t cap, size_t *n_hits);
     const PackedEvent *host_events() const { return h_events_; }
     const void *device_events() const { return d_events_; }
     size_t n_events() const { return n_events_; }
@@ -93,6 +96,12 @@ private:
 
     // gram prefilter
     uint32_t filter_w_ = 0, l1_bits_ = 0, l2_log2_ = 0;
+    // output lists on the device (hit expansion)
+    uint32_t *d_out_off_ = nullptr, *d_out_idx_ = nullptr, *d_pat_len_ = nullptr;
+    uint32_t *d_hit_sums_ = nullptr; size_t hit_sums_cap_ = 0;
+    void *d_hits_ = nullptr; size_t hits_cap_ = 0;
+    unsigned long long *d_hit_total_ = nullptr;
+    uint32_t last_uniform_len_ = 0;            // batch shape of the most recent scan (hit expansion needs it)
     uint32_t *d_l1_ = nullptr, *d_l2_ = nullptr;
     uint32_t *d_mask_ = nullptr;  size_t mask_cap_ = 0;
     uint32_t *d_items_ = nullptr;   // work items of the verify kernels

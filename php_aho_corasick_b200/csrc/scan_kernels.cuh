@@ -475,4 +475,105 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_kernel(const ScanArgs
     }
 }
 
+// ------------------------------------------------------- hit expansion ----
+//
+// The reference's callback turns every event into one record per reported pattern
+// (src/php_ahocorasick.c:555-584: pos, start = pos - length, the pattern's identity).
+// On the device: events -> hits {haystack index, end offset inside it, start offset,
+// pattern index in acceptance order}, longest pattern first inside an event, events in order.
+
+struct HitArgs {
+    const uint2 *events;          // {end offset in the stream, state}, ascending
+    uint32_t n_events;
+    const uint32_t *out_off;      // per reporting state s: patterns out_idx[out_off[s-1] .. out_off[s])
+    const uint32_t *out_idx;      // pattern index in acceptance order
+    const uint32_t *pat_len;      // per accepted pattern: length
+    const uint32_t *hay_off;      // haystack offsets (or nullptr with uniform_len)
+    uint32_t n_hay, uniform_len;
+    uint32_t *block_sum;          // per HIT_THREADS events: hits
+    uint4 *hits;                  // out: {text_idx, end, start, pattern}
+    unsigned long long capacity;
+    unsigned long long *total;    // out: number of hits
+};
+
+constexpr int HIT_THREADS = 256;
+
+// hits per block of HIT_THREADS events
+__global__ void __launch_bounds__(HIT_THREADS) ac_hit_count_kernel(const HitArgs a)
+{
+    __shared__ uint32_t s_warp[HIT_THREADS / 32];
+    const uint32_t i = blockIdx.x * HIT_THREADS + threadIdx.x;
+    uint32_t c = 0;
+    if (i < a.n_events) {
+        const uint32_t s = a.events[i].y;
+        c = a.out_off[s] - a.out_off[s - 1];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31u) == 0) s_warp[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < HIT_THREADS / 32; ++w) t += s_warp[w];
+        a.block_sum[blockIdx.x] = t;
+    }
+}
+
+// every CTA adds up the earlier blocks' sums itself, scans its own events' counts and writes their hits
+__global__ void __launch_bounds__(HIT_THREADS) ac_hit_write_kernel(const HitArgs a)
+{
+    __shared__ unsigned long long s_prev[HIT_THREADS / 32];
+    __shared__ uint32_t s_warp[HIT_THREADS / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    unsigned long long part = 0;
+    for (uint32_t j = tid; j < blockIdx.x; j += HIT_THREADS) part += a.block_sum[j];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (lane == 0) s_prev[warp] = part;
+
+    const uint32_t i = blockIdx.x * HIT_THREADS + tid;
+    uint32_t end = 0, s = 0, b = 0, c = 0;
+    if (i < a.n_events) {
+        const uint2 e = a.events[i];
+        end = e.x; s = e.y;
+        b = a.out_off[s - 1];
+        c = a.out_off[s] - b;
+    }
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned long long base = 0;
+#pragma unroll
+    for (int w = 0; w < HIT_THREADS / 32; ++w) {
+        base += s_prev[w];
+        if ((uint32_t)w < warp) base += s_warp[w];
+    }
+    unsigned long long o = base + incl - c;
+    if (i == a.n_events - 1) *a.total = o + c;
+    if (c == 0) return;
+    // haystack of this event: the one that contains byte end-1
+    uint32_t h, hb;
+    if (a.uniform_len) { h = (end - 1u) / a.uniform_len; hb = h * a.uniform_len; }
+    else {
+        uint32_t lo = 0, hi = a.n_hay;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(a.hay_off + mid) <= end - 1u) lo = mid; else hi = mid;
+        }
+        h = lo; hb = __ldg(a.hay_off + h);
+    }
+    const uint32_t pos = end - hb;
+    for (uint32_t k = 0; k < c; ++k, ++o) {
+        if (o >= a.capacity) break;
+        const uint32_t pid = __ldg(a.out_idx + b + k);
+        a.hits[o] = make_uint4(h, pos, pos - __ldg(a.pat_len + pid), pid);
+    }
+}
+
 } // namespace acb200

@@ -39,6 +39,7 @@ class Event(C.Structure):
     _fields_ = [("end", C.c_uint64), ("state", C.c_uint32), ("text_idx", C.c_uint32)]
 
 
+HIT_DTYPE = np.dtype([("text_idx", np.uint32), ("end", np.uint32), ("start", np.uint32), ("pattern", np.uint32)])
 EVENT_DTYPE = np.dtype([("end", np.uint64), ("state", np.uint32), ("text_idx", np.uint32)])
 PACKED_EVENT_DTYPE = np.dtype([("end", np.uint32), ("state", np.uint32)])
 
@@ -60,7 +61,7 @@ class Stats(C.Structure):
                 ("chunk_bytes", C.c_uint32), ("halo_bytes", C.c_uint32), ("kernel_ms", C.c_float),
                 ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("ilp", C.c_uint32), ("filtered", C.c_uint32),
                 ("filter_ms", C.c_float), ("verify_ms", C.c_float), ("flagged_words", C.c_uint64),
-                ("dense_tiles", C.c_uint64), ("reorder_ms", C.c_float), ("reserved_", C.c_uint32)]
+                ("dense_tiles", C.c_uint64), ("reorder_ms", C.c_float), ("expand_ms", C.c_float)]
 
 
 MATCH_CB = C.CFUNCTYPE(C.c_int, C.POINTER(AcMatch), C.c_void_p)
@@ -73,7 +74,7 @@ EXPORTS = [
     "acb200_state_patterns", "acb200_info", "acb200_last_stats", "acb200_last_error",
     "acb200_set_device", "acb200_device_count", "acb200_host_alloc", "acb200_host_free",
     "acb200_set_tuning", "acb200_version", "acb200_copy_events", "acb200_tally_cb", "acb200_tally_match_cb", "acb200_set_ilp",
-    "acb200_set_filter", "acb200_search_device_uniform", "acb200_set_parts",
+    "acb200_set_filter", "acb200_search_device_uniform", "acb200_set_parts", "acb200_search_hits", "acb200_pattern",
 ]
 
 
@@ -123,6 +124,10 @@ def lib() -> C.CDLL:
     L.acb200_set_ilp.argtypes = [C.c_void_p, C.c_int]
     L.acb200_set_filter.argtypes = [C.c_void_p, C.c_int]
     L.acb200_set_parts.argtypes = [C.c_void_p, C.c_uint]
+    L.acb200_search_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.acb200_search_hits.restype = C.c_int
+    L.acb200_pattern.argtypes = [C.c_void_p, C.c_size_t]
+    L.acb200_pattern.restype = C.POINTER(AcPattern)
     L.acb200_copy_events.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.acb200_copy_events.restype = C.c_long
     _lib = L
@@ -219,6 +224,30 @@ class Automaton:
             if ne.value <= cap:
                 return ev[:ne.value]
             cap = int(ne.value)
+
+    def search_hits(self, flat, offsets=None) -> np.ndarray:
+        """Hit-level search with device-side expansion -> structured array (text_idx, end, start, pattern);
+        `pattern` indexes the accepted patterns (see pattern_ordinal)."""
+        buf = _as_u8(flat)
+        if offsets is None:
+            offsets = np.array([0, buf.size], dtype=np.uint64)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        cap = 1 << 12
+        while True:
+            hits = np.empty(cap, dtype=HIT_DTYPE)
+            nh = C.c_size_t(0)
+            rc = self.L.acb200_search_hits(self.h, buf.ctypes.data if buf.size else None, off.ctypes.data, off.size - 1,
+                                           hits.ctypes.data, cap, C.byref(nh))
+            if rc != 0:
+                raise AcError(last_error())
+            if nh.value <= cap:
+                return hits[:nh.value]
+            cap = int(nh.value)
+
+    def pattern_ordinal(self, index: int) -> int:
+        """add() ordinal of accepted pattern `index` (this binding stores ordinal+1 in aux)"""
+        p = self.L.acb200_pattern(self.h, int(index))
+        return int(p.contents.aux) - 1 if p else -1
 
     def search_device(self, dev_ptr: int, offsets, first_only: bool = False, stream: int = 0):
         """Haystack stream already in HBM. -> (device pointer of packed events, n_events)"""
