@@ -217,6 +217,16 @@ int acb200_search_hits(AC_TRIE_t *thiz, const char *bytes, const uint64_t *offse
  * NULL if out of range or not finalized.                                                     */
 const AC_PATTERN_t *acb200_pattern(const AC_TRIE_t *thiz, size_t index);
 
+/* Writes the finalized automaton (flat description, output lists, prefilter tables, accepted patterns with
+ * their ids; aux pointers are stored as opaque integers) to `path`.  The reference has no counterpart: a trie
+ * cannot be serialised, so every request pays init + finalize again.  Returns 0 / -1.              */
+int acb200_save(const AC_TRIE_t *thiz, const char *path);
+
+/* Loads such a file: a finalized automaton, ready to search (only the device part of finalize is replayed).
+ * Returns NULL on a missing / corrupt file (acb200_last_error()); like after ac_trie_finalize, a handle whose
+ * device setup failed is returned but unusable (acb200_info().device < 0).                           */
+AC_TRIE_t *acb200_load(const char *path);
+
 /* Copies up to max_events packed {uint32 end_in_buffer, uint32 state} records of the most recent
  * device-resident search into the caller's DEVICE buffer `d_dst` (async on `stream`, NULL = the
  * handle's stream).  Returns the number of records copied, or -1.                      */

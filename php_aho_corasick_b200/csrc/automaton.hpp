@@ -81,6 +81,10 @@ struct FlatAutomaton {
     double l1_fill = 0.0;              // fraction of level-1 bits set
 };
 
+// blob.cpp: position-independent dump of a finalized automaton
+bool save_flat(const FlatAutomaton &flat, const char *path, std::string &err);
+bool load_flat(FlatAutomaton &flat, std::deque<std::string> &arena, const char *path, std::string &err);
+
 class HostTrie {
 public:
     HostTrie();

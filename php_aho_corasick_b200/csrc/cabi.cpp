@@ -30,6 +30,7 @@ struct ac_trie {
     size_t base_position = 0;  // keep=1 continuation (reference: base_position)
     std::vector<char> gather;  // batch gather buffer
     std::vector<uint64_t> gather_off;
+    std::deque<std::string> blob_arena;   // pattern bytes / string ids of an automaton loaded from a blob
 };
 
 static inline size_t patterns_of(const ac_trie *t, uint32_t state, const AC_PATTERN_t **p)
@@ -88,12 +89,29 @@ void ac_trie_finalize(AC_TRIE_t *t)
     t->engine.info.n_patterns = t->trie.n_patterns();
     t->engine.info.finalized = 1;
     t->trie.release_build_memory();
-    // the expansion inputs are only needed once
-    std::vector<uint32_t>().swap(t->flat.bfs_order);
-    std::vector<uint32_t>().swap(t->flat.fail);
-    std::vector<uint32_t>().swap(t->flat.edge_src);
-    std::vector<uint32_t>().swap(t->flat.edge_dst);
-    std::vector<uint16_t>().swap(t->flat.edge_cls);
+    // the expansion inputs (a few words per state) stay: acb200_save() writes them
+}
+
+int acb200_save(const AC_TRIE_t *t, const char *path)
+{
+    if (t->open) { set_error("automaton is not finalized"); return -1; }
+    std::string err;
+    if (!save_flat(t->flat, path, err)) { set_error(err); return -1; }
+    return 0;
+}
+
+AC_TRIE_t *acb200_load(const char *path)
+{
+    ac_trie *t = new (std::nothrow) ac_trie();
+    if (!t) { set_error("out of memory"); return nullptr; }
+    std::string err;
+    if (!load_flat(t->flat, t->blob_arena, path, err)) { set_error(err); delete t; return nullptr; }
+    t->open = false;
+    set_error("");
+    t->device_ok = t->engine.build(t->flat);
+    t->engine.info.n_patterns = t->flat.accepted.size();
+    t->engine.info.finalized = 1;
+    return t;
 }
 
 int ac_trie_search(AC_TRIE_t *t, AC_TEXT_t *text, int keep, AC_MATCH_CALBACK_f callback, void *user)
@@ -336,7 +354,7 @@ int acb200_info(const AC_TRIE_t *t, ACB200_INFO_t *out)
 {
     if (!out) return -1;
     *out = t->engine.info;
-    out->n_patterns = t->open ? t->trie.n_patterns() : t->engine.info.n_patterns;
+    out->n_patterns = t->open ? t->trie.n_patterns() : t->flat.accepted.size();
     out->finalized = t->open ? 0 : 1;
     if (t->open || !t->device_ok) {
         out->n_states = t->open ? t->trie.n_nodes() : t->flat.n_states;

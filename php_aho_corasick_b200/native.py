@@ -74,7 +74,7 @@ EXPORTS = [
     "acb200_state_patterns", "acb200_info", "acb200_last_stats", "acb200_last_error",
     "acb200_set_device", "acb200_device_count", "acb200_host_alloc", "acb200_host_free",
     "acb200_set_tuning", "acb200_version", "acb200_copy_events", "acb200_tally_cb", "acb200_tally_match_cb", "acb200_set_ilp",
-    "acb200_set_filter", "acb200_search_device_uniform", "acb200_set_parts", "acb200_search_hits", "acb200_pattern",
+    "acb200_set_filter", "acb200_search_device_uniform", "acb200_set_parts", "acb200_search_hits", "acb200_pattern", "acb200_save", "acb200_load",
 ]
 
 
@@ -128,6 +128,10 @@ def lib() -> C.CDLL:
     L.acb200_search_hits.restype = C.c_int
     L.acb200_pattern.argtypes = [C.c_void_p, C.c_size_t]
     L.acb200_pattern.restype = C.POINTER(AcPattern)
+    L.acb200_save.argtypes = [C.c_void_p, C.c_char_p]
+    L.acb200_save.restype = C.c_int
+    L.acb200_load.argtypes = [C.c_char_p]
+    L.acb200_load.restype = C.c_void_p
     L.acb200_copy_events.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.acb200_copy_events.restype = C.c_long
     _lib = L
@@ -196,6 +200,25 @@ class Automaton:
         self.L.acb200_set_tuning(self.h, int(chunk_bytes), int(smem_table_bytes))
         if ilp is not None:
             self.L.acb200_set_ilp(self.h, int(ilp))
+
+    def save(self, path: str) -> None:
+        if self.L.acb200_save(self.h, os.fsencode(path)) != 0:
+            raise AcError(last_error())
+
+    @classmethod
+    def load(cls, path: str, device: int | None = None, require_device: bool = True) -> "Automaton":
+        self = cls.__new__(cls)
+        self.L = lib()
+        if device is not None:
+            self.L.acb200_set_device(int(device))
+        self.h = self.L.acb200_load(os.fsencode(path))
+        self.n_added = 0
+        self._keep = []
+        if not self.h:
+            raise AcError(last_error())
+        if require_device and self.info().device < 0:
+            raise AcError("load did not reach the GPU: " + last_error())
+        return self
 
     def set_parts(self, parts: int) -> None:
         """parts a prefiltered scan is cut into (0 automatic)"""

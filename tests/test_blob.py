@@ -1,0 +1,74 @@
+"""Save / load of a finalized automaton (acb200_save / acb200_load).  The CPU half checks the file
+round trip (flat description, output lists, pattern ids); the GPU half that a loaded automaton matches like the original."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from php_aho_corasick_b200 import native, workloads as W
+from php_aho_corasick_b200.native import Automaton
+
+
+def _finalize_anyhow(a):
+    a.L.ac_trie_finalize(a.h)          # no GPU here: the host part of finalize still runs
+
+
+def test_blob_round_trip_on_the_host(tmp_path):
+    pats = [b"alfa", b"beta", b"gamma", b"lfa", b"a", b"\x00\xff\x80", b"alfabet"]
+    a = Automaton()
+    a.add_php_order(pats)
+    _finalize_anyhow(a)
+    path = str(tmp_path / "dict.acb")
+    a.save(path)
+    b = Automaton.load(path, require_device=False)
+    ia, ib = a.info(), b.info()
+    assert (ia.n_patterns, ia.n_states, ib.finalized) == (ib.n_patterns, ib.n_states, 1) and ib.n_patterns == len(pats)
+    for state in range(1, 12):
+        assert a.state_patterns(state) == b.state_patterns(state)
+    # ids and bytes survive (this binding adds numeric ids)
+    for i in range(len(pats)):
+        pa, pb = a.L.acb200_pattern(a.h, i).contents, b.L.acb200_pattern(b.h, i).contents
+        assert C.string_at(pa.ptext.astring, pa.ptext.length) == C.string_at(pb.ptext.astring, pb.ptext.length)
+        assert (pa.id.type, pa.id.u.number, pa.aux) == (pb.id.type, pb.id.u.number, pb.aux)
+    assert b.add(b"zzz") == 4                       # a loaded automaton is closed (ACERR_TRIE_CLOSED)
+
+
+def test_blob_rejects_garbage_and_unfinalized(tmp_path):
+    a = Automaton()
+    a.add(b"abc")
+    with pytest.raises(native.AcError):
+        a.save(str(tmp_path / "x.acb"))             # not finalized
+    bad = tmp_path / "bad.acb"
+    bad.write_bytes(b"ACB200v1" + os.urandom(100))
+    with pytest.raises(native.AcError):
+        Automaton.load(str(bad), require_device=False)
+    with pytest.raises(native.AcError):
+        Automaton.load(str(tmp_path / "missing.acb"), require_device=False)
+    _finalize_anyhow(a)
+    good = tmp_path / "good.acb"
+    a.save(str(good))
+    data = good.read_bytes()
+    (tmp_path / "cut.acb").write_bytes(data[: len(data) // 2])
+    with pytest.raises(native.AcError):
+        Automaton.load(str(tmp_path / "cut.acb"), require_device=False)
+
+
+@pytest.mark.gpu
+def test_loaded_automaton_matches_like_the_original(tmp_path):
+    needles, hay, off = W.cfg2(n_hay=64, hay_len=8192, planted_per_hay=8, seed=3)
+    a = Automaton()
+    a.add_php_order(needles)
+    a.finalize()
+    path = str(tmp_path / "cfg2.acb")
+    a.save(path)
+    b = Automaton.load(path)
+    for mode in (1, -1):
+        a.set_filter(mode); b.set_filter(mode)
+        assert np.array_equal(a.search_events(hay, off), b.search_events(hay, off))
+    ha, hb = a.search_hits(hay, off), b.search_hits(hay, off)
+    assert np.array_equal(ha, hb) and len(ha) >= 64 * 7
+    assert [a.pattern_ordinal(i) for i in range(50)] == [b.pattern_ordinal(i) for i in range(50)]
+    rc, got = b.search_callback(hay[:20000].tobytes())
+    rc2, got2 = a.search_callback(hay[:20000].tobytes())
+    assert (rc, got) == (rc2, got2) and got
