@@ -263,6 +263,7 @@ bool Engine::ensure_text(size_t bytes)
     cudaFree(d_text_); d_text_ = nullptr; text_cap_ = 0;
     const size_t cap = std::max(bytes + bytes / 4, (size_t)1 << 20);
     CU_OK(cudaMalloc(&d_text_, cap));
+    CU_OK(cudaMemset(d_text_, 0, cap));      // the scan prefetches 16-byte groups past the end of the stream (never used)
     text_cap_ = cap;
     return true;
 }
@@ -810,6 +811,7 @@ bool Engine::slab_upload_async(int buf, const char *bytes, size_t n_bytes)
         cudaFree(d_slab_[buf]); d_slab_[buf] = nullptr; slab_cap_[buf] = 0;
         const size_t cap = n_bytes + n_bytes / 8 + 4096;
         CU_OK(cudaMalloc(&d_slab_[buf], cap));
+        CU_OK(cudaMemset(d_slab_[buf], 0, cap));
         slab_cap_[buf] = cap;
     }
     CU_OK(cudaEventRecord(EV(ev_slab_[2 * buf]), S(copy_stream_)));
