@@ -181,6 +181,48 @@ template <> __device__ __forceinline__ uint32_t lds_entry<uint32_t>(uint32_t add
     return v;
 }
 
+// Stages the window rows of the dense table into shared memory with 16-byte loads; entries whose target
+// lies outside the window become 0.  Called by all threads of the CTA (n_threads of them).
+template <typename E>
+__device__ __forceinline__ void stage_window(E *s_tab, const E *gtab, uint32_t win_lo, uint32_t win_rows, uint32_t ncls,
+                                             uint32_t tid, uint32_t n_threads)
+{
+    constexpr uint32_t PER = 16 / sizeof(E);               // entries per 16-byte load
+    const uint32_t win_entries = win_rows * ncls;
+    const uint32_t win_first = win_lo * ncls;
+    const uint32_t lead = min((PER - (win_first % PER)) % PER, win_entries);   // entries before the first aligned group
+    for (uint32_t idx = tid; idx < lead; idx += n_threads) {
+        uint32_t e = gtab[win_first + idx];
+        if (e - win_lo >= win_rows) e = 0;
+        s_tab[idx] = (E)e;
+    }
+    const uint32_t n_vec = (win_entries - lead) / PER;
+    const uint4 *src = reinterpret_cast<const uint4 *>(gtab + win_first + lead);
+    for (uint32_t v = tid; v < n_vec; v += n_threads) {
+        const uint4 q = __ldg(src + v);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (sizeof(E) == 2) {
+                uint32_t lo = w[k] & 0xffffu, hi = w[k] >> 16;
+                if (lo - win_lo >= win_rows) lo = 0;
+                if (hi - win_lo >= win_rows) hi = 0;
+                s_tab[lead + v * PER + 2 * k] = (E)lo;
+                s_tab[lead + v * PER + 2 * k + 1] = (E)hi;
+            } else {
+                uint32_t e = w[k];
+                if (e - win_lo >= win_rows) e = 0;
+                s_tab[lead + v * PER + k] = (E)e;
+            }
+        }
+    }
+    for (uint32_t idx = lead + n_vec * PER + tid; idx < win_entries; idx += n_threads) {
+        uint32_t e = gtab[win_first + idx];
+        if (e - win_lo >= win_rows) e = 0;
+        s_tab[idx] = (E)e;
+    }
+}
+
 // Per-thread walker.
 //
 // Shared memory holds the rows of a contiguous window of state ids around
@@ -383,13 +425,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_kernel(const ScanArgs
     const E *gtab = static_cast<const E *>(a.table);
 
     // window rows, with targets outside the window replaced by 0
-    const uint32_t win_entries = a.win_rows * a.ncls;
-    const uint32_t win_first = a.win_lo * a.ncls;
-    for (uint32_t idx = tid; idx < win_entries; idx += SCAN_THREADS) {
-        uint32_t e = gtab[win_first + idx];
-        if (e - a.win_lo >= a.win_rows) e = 0;
-        s_tab[idx] = (E)e;
-    }
+    stage_window<E>(s_tab, gtab, a.win_lo, a.win_rows, a.ncls, tid, SCAN_THREADS);
     if (tid < 256) s_cls[tid] = a.cls_map[tid];
     __syncthreads();      // the only CTA-wide barrier: from here on warps run independently
 
