@@ -407,7 +407,10 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     // Gram prefilter: needs an eligible dictionary and a walk that starts at the root.  Automatic mode
     // skips it for inputs too small to amortise a second launch and after a scan whose tiles were mostly
     // walked completely anyway.
-    if (filter_w_ && tune_filter >= 0 && !first_only && (init_state == ROOT_STATE || init_state == root_)) {
+    // findAll=false may use it too while events are sparse: the prefilter path returns every event and the host
+    // keeps the first one per haystack; with dense events the FIRST kernel's early exit wins.
+    if (filter_w_ && tune_filter >= 0 && (init_state == ROOT_STATE || init_state == root_) &&
+        (!first_only || last_density_ < 1.0 / 2048)) {
         const bool want = tune_filter > 0 || (total >= (8u << 20) && last_dense_frac_ < 0.5);
         if (want) return launch_filtered(d_text, total, readable, n_hay, uniform_len, stream);
         last_dense_frac_ *= 0.5;      // re-probe the prefilter now and then

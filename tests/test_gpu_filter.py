@@ -101,6 +101,21 @@ def test_multi_part_scans_on_two_streams_give_the_same_events(parts):
     assert got == got1
 
 
+def test_find_first_through_the_prefilter_equals_the_first_only_kernel():
+    needles, hay, off = W.cfg2(n_hay=300, hay_len=8192, planted_per_hay=3, seed=31)
+    hay = hay.copy()
+    hay.reshape(300, 8192)[::5] = ord("z")              # every fifth haystack has no hit at all
+    exp = oracle_hits([needles], split(hay, off), first_only=True)
+    a = build([needles], 1)
+    ev = a.search_events(hay, off, first_only=True)
+    assert a.stats().filtered == 1
+    assert_same(a, ev, 300, exp)
+    a.set_filter(-1)
+    ev2 = a.search_events(hay, off, first_only=True)
+    assert a.stats().filtered == 0 and np.array_equal(ev, ev2)
+    assert 200 <= len(ev) <= 240
+
+
 def test_every_word_flagged_falls_back_to_whole_tile_walks():
     # nested patterns over one repeated byte: every aligned word is a pattern word, every offset an event
     pats = [b"a" * n for n in range(16, 41)]
