@@ -284,24 +284,28 @@ void HostTrie::build_filter(FlatAutomaton &flat) const {
     const uint32_t W = (min_len >= 16) ? 8u : (min_len >= 8) ? 4u : 0u;
     if (!W) return;
 
-    auto gram = [&](const AC_PATTERN_t &p, uint32_t r, uint32_t &lo, uint32_t &hi) {
+    // the word at distance r from the pattern's end plus the byte after it (r >= 1: still inside the pattern)
+    auto gram = [&](const AC_PATTERN_t &p, uint32_t r, uint32_t &lo, uint32_t &hi, uint32_t &nb) {
         const uint8_t *b = (const uint8_t *)p.ptext.astring + (p.ptext.length - W - r);
         lo = hi = 0;
         memcpy(&lo, b, 4);
         if (W == 8) memcpy(&hi, b + 4, 4);
+        nb = b[W];
     };
     flat.filter_w = W;
     flat.l1_bits = FILTER_L1_BITS;
     flat.l1.assign(FILTER_L1_BITS / 32, 0);
     for (const AC_PATTERN_t &p : patterns_)
         for (uint32_t r = 1; r <= W; ++r) {
-            uint32_t lo, hi;
-            gram(p, r, lo, hi);
-            const uint32_t t = filter_mix1(lo, hi);
-            const uint32_t i = filter_reduce(t, flat.l1_bits);
-            flat.l1[i >> 5] |= (1u << (i & 31)) | (1u << filter_bit2(t));
+            uint32_t lo, hi, nb;
+            gram(p, r, lo, hi, nb);
+            for (uint32_t next : {nb, FILTER_NEXT_UNKNOWN}) {
+                const uint32_t t = filter_mix1(lo, hi, next);
+                const uint32_t i = filter_l1_index(t, next == FILTER_NEXT_UNKNOWN);
+                flat.l1[i >> 5] |= (1u << (i & 31)) | (1u << filter_bit2(t));
+            }
         }
-    flat.n_grams = (uint64_t)patterns_.size() * W;
+    flat.n_grams = (uint64_t)patterns_.size() * W * 2;
     uint64_t set = 0;
     for (uint32_t w : flat.l1) set += (uint64_t)__builtin_popcount(w);
     flat.l1_fill = (double)set / (double)flat.l1_bits;
@@ -317,10 +321,12 @@ void HostTrie::build_filter(FlatAutomaton &flat) const {
         flat.l2.assign((size_t)1 << (lg - 5), 0);
         for (const AC_PATTERN_t &p : patterns_)
             for (uint32_t r = 1; r <= W; ++r) {
-                uint32_t lo, hi;
-                gram(p, r, lo, hi);
-                const uint32_t i = filter_mix3(lo, hi) >> (32 - lg);
-                flat.l2[i >> 5] |= 1u << (i & 31);
+                uint32_t lo, hi, nb;
+                gram(p, r, lo, hi, nb);
+                for (uint32_t next : {nb, FILTER_NEXT_UNKNOWN}) {
+                    const uint32_t i = filter_mix3(lo, hi, next) >> (32 - lg);
+                    flat.l2[i >> 5] |= 1u << (i & 31);
+                }
             }
     }
 }

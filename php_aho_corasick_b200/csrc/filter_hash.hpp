@@ -19,11 +19,13 @@ constexpr uint32_t FILTER_L1_BYTES = 220u * 1024u;          // level-1 bitmap, l
 constexpr uint32_t FILTER_L1_BITS = FILTER_L1_BYTES * 8u;
 
 // level 1 is a blocked Bloom filter with two bits per gram inside ONE 32-bit word (one shared-memory
-// load per haystack word): word = reduce(mix1) >> 5, first bit = reduce(mix1) & 31, second bit taken from
+// load per haystack word): word = reduce(mix1) >> 5, first bit = reduce(mix1) & 31, the second one taken from
 // low-order bits of the same hash, which the high-multiply range reduction does not look at.
-ACB_HD uint32_t filter_mix1(uint32_t lo, uint32_t hi)
+// A gram is the aligned word plus the byte that follows it: an occurrence that "belongs" to the word ends
+// at least one byte after it, so that byte is part of the occurrence too (one more byte of selectivity).
+ACB_HD uint32_t filter_mix1(uint32_t lo, uint32_t hi, uint32_t next_byte)
 {
-    return lo * 0x9E3779B1u + hi * 0x85EBCA77u;
+    return lo * 0x9E3779B1u + hi * 0x85EBCA77u + next_byte * 0x7FEB352Du;
 }
 
 ACB_HD uint32_t filter_reduce(uint32_t t, uint32_t n_bits)
@@ -37,10 +39,24 @@ ACB_HD uint32_t filter_reduce(uint32_t t, uint32_t n_bits)
 
 ACB_HD uint32_t filter_bit2(uint32_t t) { return (t >> 3) & 31u; }
 
-// level 2: third independent hash, top `log2_bits` bits index a 2^log2_bits-bit map in global memory
-ACB_HD uint32_t filter_mix3(uint32_t lo, uint32_t hi)
+// "next byte unknown" (the last word of a 512-byte span, whose successor belongs to another warp): every gram
+// is entered a second time with this value, so such a word is tested on its W bytes alone.  These entries
+// live in their own eighth of the bitmap (only one word in 64 or 128 looks there), the others in the rest.
+constexpr uint32_t FILTER_NEXT_UNKNOWN = 0x100u;
+constexpr uint32_t FILTER_L1_UNKNOWN_BITS = FILTER_L1_BITS / 8u;
+constexpr uint32_t FILTER_L1_KNOWN_BITS = FILTER_L1_BITS - FILTER_L1_UNKNOWN_BITS;
+
+// bit index of a gram hash in level 1
+ACB_HD uint32_t filter_l1_index(uint32_t t, bool next_unknown)
 {
-    uint32_t t = (lo ^ 0x5bd1e995u) * 0x165667B1u + (hi ^ 0x7feb352du) * 0xD3A2646Du;
+    return next_unknown ? FILTER_L1_KNOWN_BITS + filter_reduce(t, FILTER_L1_UNKNOWN_BITS)
+                        : filter_reduce(t, FILTER_L1_KNOWN_BITS);
+}
+
+// level 2: third independent hash, top `log2_bits` bits index a 2^log2_bits-bit map in global memory
+ACB_HD uint32_t filter_mix3(uint32_t lo, uint32_t hi, uint32_t next_byte)
+{
+    uint32_t t = (lo ^ 0x5bd1e995u) * 0x165667B1u + (hi ^ 0x7feb352du) * 0xD3A2646Du + next_byte * 0x9E3779B1u;
     t ^= t >> 16;
     return t * 0x846CA68Bu;
 }

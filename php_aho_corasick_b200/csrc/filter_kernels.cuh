@@ -93,16 +93,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const Filter
     __syncthreads();
     const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_bm);
 
-    // one flag per aligned word: both bits of the word's gram hash are set in the level-1 bitmap
-    auto test_word = [&](uint32_t lo, uint32_t hi) -> bool {
-        const uint32_t t = filter_mix1(lo, hi);
-        const uint32_t idx = filter_reduce(t, a.l1_bits);
+    // one flag per aligned word: both bits of the gram hash (the word + the byte after it) are set in level 1
+    auto test_word = [&](uint32_t lo, uint32_t hi, uint32_t nb, bool maybe_unknown) -> bool {
+        const uint32_t t = filter_mix1(lo, hi, nb);
+        const uint32_t idx = maybe_unknown ? filter_l1_index(t, nb == FILTER_NEXT_UNKNOWN) : filter_l1_index(t, false);
         uint32_t word;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(s_base + ((idx >> 5) << 2)));
         bool p = ((word >> (idx & 31u)) & (word >> filter_bit2(t)) & 1u) != 0;
         if (L2) {
             uint32_t word3 = 0;
-            const uint32_t i3 = filter_mix3(lo, hi) >> a.l2_shift;
+            const uint32_t i3 = filter_mix3(lo, hi, nb) >> a.l2_shift;
             if (p) word3 = __ldg(a.l2 + (i3 >> 5));
             p = (word3 >> (i3 & 31u)) & 1u;
         }
@@ -128,10 +128,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const Filter
             const uint32_t g = g0 + u * n_warps;
             if (g >= n_full) break;                           // warp-uniform
             const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            // byte after the lane's last word: the next lane's first byte; lane 31 does not know it
+            uint32_t after = __shfl_down_sync(0xffffffffu, w[0], 1) & 0xffu;
+            if (lane == 31u) after = FILTER_NEXT_UNKNOWN;
             uint32_t mine = 0;
 #pragma unroll
             for (int j = 0; j < NB; ++j) {
-                const bool p = (W == 8) ? test_word(w[2 * j], w[2 * j + 1]) : test_word(w[j], 0u);
+                const uint32_t nb = (j == NB - 1) ? after : (((W == 8) ? w[2] : w[j + 1]) & 0xffu);
+                const bool p = (W == 8) ? test_word(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test_word(w[j], 0u, nb, j == NB - 1);
                 const uint32_t plane = __ballot_sync(0xffffffffu, p);
                 if (lane == (uint32_t)j) mine = plane;
             }
@@ -152,10 +156,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const Filter
         if (c < n16) v = ld_text16(a.text + (size_t)c * 16u);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
         const bool tail = (a.total & 15u) && c == n16;
+        uint32_t after = __shfl_down_sync(0xffffffffu, w[0], 1) & 0xffu;
+        if (lane == 31u || c + 1u >= n16) after = FILTER_NEXT_UNKNOWN;      // the next chunk is not in this warp's registers
         uint32_t mine = 0;
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
-            bool p = (W == 8) ? test_word(w[2 * j], w[2 * j + 1]) : test_word(w[j], 0u);
+            const uint32_t nb = (j == NB - 1) ? after : (((W == 8) ? w[2] : w[j + 1]) & 0xffu);
+            bool p = (W == 8) ? test_word(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test_word(w[j], 0u, nb, j == NB - 1);
             p = (c < n16) ? p : tail;
             const uint32_t plane = __ballot_sync(0xffffffffu, p);
             if (lane == (uint32_t)j) mine = plane;
