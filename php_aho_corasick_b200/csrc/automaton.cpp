@@ -312,7 +312,7 @@ void HostTrie::build_filter(FlatAutomaton &flat) const {
 
     // Level 1 tests two bits of one word: a random haystack word passes with probability ~fill^2.
     // Level 2 (global memory) is only worth its latency when that is still not selective.
-    double l2_min_fill = 0.15;
+    double l2_min_fill = 0.10;
     if (const char *e = getenv("ACB200_L2_MIN_FILL")) l2_min_fill = atof(e);
     if (flat.l1_fill > l2_min_fill) {
         uint32_t lg = 23;                                   // at least 1 MiB: ~256 bits per gram, capped at 128 MiB

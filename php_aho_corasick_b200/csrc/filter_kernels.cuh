@@ -396,8 +396,12 @@ __device__ __noinline__ ItemEvents walk_item_slow(const ScanArgs &a, uint32_t s_
     sc.e0p = sc.e0s = sc.e1p = sc.e1s = 0;
 
     if (item != ITEM_NONE && (item & ITEM_SPAN)) {
-        const uint32_t cs = (item & ~ITEM_SPAN) * SPAN_BYTES;
+        // A span item stands for the WORDS of its span, and word k owns the end offsets W(k+1)+1 .. W(k+2): the
+        // bytes to report are the span's shifted by W.  (Reporting the span's own bytes would duplicate the
+        // ends owned by the last word of a sparse tile before it and lose those after a dense tile.)
+        const uint32_t cs = min((item & ~ITEM_SPAN) * SPAN_BYTES + W, a.total);
         const uint32_t ce = min(cs + SPAN_BYTES, a.total);
+        if (cs >= ce) return ItemEvents{0, 0, 0};
         const uint32_t h = find_haystack(a, cs);
         const uint32_t hb = hay_begin(a, h);
         uint32_t w0 = (cs - hb > a.halo) ? ((cs - a.halo) & ~15u) : hb;

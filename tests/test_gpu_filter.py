@@ -128,6 +128,36 @@ def test_every_word_flagged_falls_back_to_whole_tile_walks():
     assert_same(a, ev, 1, oracle_hits([pats], [hay]))
 
 
+@pytest.mark.parametrize("word", [8, 4])
+def test_dense_and_sparse_tiles_side_by_side_own_every_end_offset_exactly_once(word):
+    """A densely flagged 16 KiB tile is walked as whole spans, its neighbours word by word.  The end offsets right
+    behind a tile boundary belong to the last word of the tile before it — they must be reported exactly once
+    whichever way the two tiles are handled."""
+    rng = np.random.default_rng(17)
+    L = 2 * word
+    filler = bytes(range(0x30, 0x61)) + bytes(range(0x62, 0x7b))       # no 'a': random text stays sparsely flagged
+    pats = [b"a" * n for n in range(L, L + 6)] + [rand_bytes(rng, L + 3, filler).tobytes() for _ in range(20)]
+    n_tiles = 12
+    hay = rand_bytes(rng, n_tiles * 16384, filler)
+    for t in (1, 2, 5, 8, 9, 10):                      # dense tiles, some adjacent, some isolated
+        hay[t * 16384:(t + 1) * 16384] = ord("a")
+    # needles that end 1..word bytes behind every tile boundary, and ones that straddle it further
+    p0 = np.frombuffer(pats[-1], dtype=np.uint8)
+    for t in range(1, n_tiles):
+        for k, d in enumerate((1, word, word + 1, 3 * word)):
+            if (t + k) % 2 == 0:
+                end = t * 16384 + d
+                hay[end - p0.size:end] = p0
+    a = build([pats], 1)
+    ev = a.search_events(hay)
+    st = a.stats()
+    assert st.filtered == 1 and 0 < st.dense_tiles < n_tiles
+    assert a.info().filter_word == word
+    assert_same(a, ev, 1, oracle_hits([pats], [hay]))
+    a.set_filter(-1)
+    assert np.array_equal(ev, a.search_events(hay))
+
+
 def test_event_bursts_from_few_flagged_words_stay_ordered():
     # few flagged words per 16 KiB tile, but each yields a run of events (lanes with more than two re-walk and emit)
     rng = np.random.default_rng(9)
