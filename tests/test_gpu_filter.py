@@ -374,3 +374,45 @@ def test_full_size_config3_signatures_filter_equals_full_walk():
         assert lst, state
         o, l = lst[0]
         assert hay[int(end) - l:int(end)].tobytes() == pats[o]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_randomised_mixtures_of_dense_and_sparse_regions(seed):
+    """Haystacks stitched from random filler, long runs of a repeated pattern byte / pattern prefix, and pattern
+    copies at random offsets; ragged batches.  Prefilter path vs oracle vs full walk."""
+    rng = np.random.default_rng(1000 + seed)
+    pyr = random.Random(seed)
+    for trial in range(5):
+        word = pyr.choice([4, 8])
+        L = 2 * word
+        alphabet = pyr.choice([b"ab", b"abcd", bytes(range(256)), bytes(range(0x30, 0x7b))])
+        pats = [rand_bytes(rng, pyr.randint(L, L + 40), alphabet).tobytes() for _ in range(pyr.choice([3, 30, 300]))]
+        rep = bytes([alphabet[0]])
+        pats += [rep * n for n in range(L, L + pyr.choice([1, 5, 30]))]          # nested runs of one byte
+        hays = []
+        for _ in range(pyr.randint(1, 6)):
+            parts = []
+            for _ in range(pyr.randint(1, 8)):
+                kind = pyr.choice(["fill", "fill", "run", "prefix", "pats"])
+                n = pyr.choice([0, 5, 100, 3000, 20000, 70000])
+                if kind == "fill":
+                    parts.append(rand_bytes(rng, n, alphabet))
+                elif kind == "run":
+                    parts.append(np.full(n, alphabet[0], dtype=np.uint8))
+                elif kind == "prefix":
+                    p = np.frombuffer(pyr.choice(pats), dtype=np.uint8)
+                    parts.append(np.tile(p[: max(1, p.size - 1)], n // max(1, p.size - 1) + 1)[:n])
+                else:
+                    parts.append(np.concatenate([np.frombuffer(pyr.choice(pats), dtype=np.uint8) for _ in range(1 + n // 500)]))
+            hays.append(np.concatenate(parts) if parts else np.zeros(0, np.uint8))
+        lens = [h.size for h in hays]
+        flat = np.concatenate(hays) if sum(lens) else np.zeros(0, np.uint8)
+        off = np.zeros(len(lens) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(lens)
+        exp = oracle_hits([pats], hays)
+        a = build([pats], 1)
+        ev = a.search_events(flat, off)
+        assert_same(a, ev, len(lens), exp)
+        a.set_filter(-1)
+        assert np.array_equal(ev, a.search_events(flat, off)), (seed, trial)
+        a.release()
