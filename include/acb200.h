@@ -317,6 +317,13 @@ int acb200_set_ilp(AC_TRIE_t *thiz, int ilp);
  * Results are identical either way.                                                     */
 int acb200_set_filter(AC_TRIE_t *thiz, int mode);
 
+/* Diagnostic: the prefilter's decision for one aligned word, evaluated on the HOST from the tables finalize
+ * built (the same hashes the filter kernel uses).  `word` = the W bytes little-endian (W from
+ * acb200_info().filter_word; upper bytes zero for W = 4), `next_byte` = the byte after the word, or 0x100 for
+ * "unknown".  Returns 1 if the word would be handed to verification, 0 if not, -1 if the dictionary has no
+ * prefilter.  Not a matching path: tests use it to check that no occurrence can be filtered away.        */
+int acb200_filter_probe(const AC_TRIE_t *thiz, uint64_t word, unsigned next_byte);
+
 /* Parts a prefiltered scan is cut into (the filter of part p+1 overlaps the verification of part p on a
  * second stream): 0 = automatic (currently 1: overlapping did not pay on B200), 1..8 = fixed. */
 int acb200_set_parts(AC_TRIE_t *thiz, unsigned parts);

@@ -17,6 +17,7 @@
 #include "acb200.h"
 #include "automaton.hpp"
 #include "engine.hpp"
+#include "filter_hash.hpp"
 
 using namespace acb200;
 
@@ -360,6 +361,16 @@ int acb200_info(const AC_TRIE_t *t, ACB200_INFO_t *out)
         out->n_states = t->open ? t->trie.n_nodes() : t->flat.n_states;
         out->device = -1;
     }
+    if (!t->open) {                              // host facts of a finalized automaton hold with or without a device
+        out->n_classes = t->flat.n_classes;
+        out->max_pattern_len = t->flat.max_pattern_len;
+        out->final_bound = t->flat.final_bound;
+        out->root = t->flat.root;
+        out->filter_word = (int32_t)t->flat.filter_w;
+        out->min_pattern_len = t->flat.min_pattern_len;
+        out->filter_l1_fill = (float)t->flat.l1_fill;
+        out->filter_l2_log2 = t->flat.l2_log2;
+    }
     return 0;
 }
 
@@ -387,6 +398,22 @@ int acb200_set_filter(AC_TRIE_t *t, int mode)
 {
     t->engine.tune_filter = mode;
     return 0;
+}
+
+int acb200_filter_probe(const AC_TRIE_t *t, uint64_t word, unsigned next_byte)
+{
+    const FlatAutomaton &f = t->flat;
+    if (t->open || f.filter_w == 0) return -1;
+    const uint32_t lo = (uint32_t)word, hi = (f.filter_w == 8) ? (uint32_t)(word >> 32) : 0u;
+    const uint32_t tt = filter_mix1(lo, hi, next_byte);
+    const uint32_t i = filter_l1_index(tt, next_byte == FILTER_NEXT_UNKNOWN);
+    const uint32_t w = f.l1[i >> 5];
+    if (!((w >> (i & 31)) & (w >> filter_bit2(tt)) & 1u)) return 0;
+    if (f.l2_log2) {
+        const uint32_t i3 = filter_mix3(lo, hi, next_byte) >> (32 - f.l2_log2);
+        if (!((f.l2[i3 >> 5] >> (i3 & 31)) & 1u)) return 0;
+    }
+    return 1;
 }
 
 int acb200_set_parts(AC_TRIE_t *t, unsigned parts)

@@ -74,7 +74,7 @@ EXPORTS = [
     "acb200_state_patterns", "acb200_info", "acb200_last_stats", "acb200_last_error",
     "acb200_set_device", "acb200_device_count", "acb200_host_alloc", "acb200_host_free",
     "acb200_set_tuning", "acb200_version", "acb200_copy_events", "acb200_tally_cb", "acb200_tally_match_cb", "acb200_set_ilp",
-    "acb200_set_filter", "acb200_search_device_uniform", "acb200_set_parts", "acb200_search_hits", "acb200_pattern", "acb200_save", "acb200_load",
+    "acb200_set_filter", "acb200_search_device_uniform", "acb200_set_parts", "acb200_search_hits", "acb200_pattern", "acb200_save", "acb200_load", "acb200_filter_probe",
 ]
 
 
@@ -128,6 +128,8 @@ def lib() -> C.CDLL:
     L.acb200_search_hits.restype = C.c_int
     L.acb200_pattern.argtypes = [C.c_void_p, C.c_size_t]
     L.acb200_pattern.restype = C.POINTER(AcPattern)
+    L.acb200_filter_probe.argtypes = [C.c_void_p, C.c_uint64, C.c_uint]
+    L.acb200_filter_probe.restype = C.c_int
     L.acb200_save.argtypes = [C.c_void_p, C.c_char_p]
     L.acb200_save.restype = C.c_int
     L.acb200_load.argtypes = [C.c_char_p]
@@ -219,6 +221,10 @@ class Automaton:
         if require_device and self.info().device < 0:
             raise AcError("load did not reach the GPU: " + last_error())
         return self
+
+    def filter_probe(self, word: int, next_byte: int) -> int:
+        """host-side evaluation of the prefilter decision for one aligned word (diagnostic, see acb200.h)"""
+        return int(self.L.acb200_filter_probe(self.h, int(word), int(next_byte)))
 
     def set_parts(self, parts: int) -> None:
         """parts a prefiltered scan is cut into (0 automatic)"""
