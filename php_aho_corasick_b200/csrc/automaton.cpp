@@ -301,8 +301,7 @@ void HostTrie::build_filter(FlatAutomaton &flat) const {
             gram(p, r, lo, hi, nb);
             for (uint32_t next : {nb, FILTER_NEXT_UNKNOWN}) {
                 const uint32_t t = filter_mix1(lo, hi, next);
-                const uint32_t i = filter_l1_index(t, next == FILTER_NEXT_UNKNOWN);
-                flat.l1[i >> 5] |= (1u << (i & 31)) | (1u << filter_bit2(t));
+                flat.l1[filter_l1_word(t, next == FILTER_NEXT_UNKNOWN)] |= (1u << filter_bit1(t)) | (1u << filter_bit2(t));
             }
         }
     flat.n_grams = (uint64_t)patterns_.size() * W * 2;

@@ -37,21 +37,23 @@ ACB_HD uint32_t filter_reduce(uint32_t t, uint32_t n_bits)
 #endif
 }
 
-ACB_HD uint32_t filter_bit2(uint32_t t) { return (t >> 3) & 31u; }
-
 // "next byte unknown" (the last word of a 512-byte span, whose successor belongs to another warp): every gram
 // is entered a second time with this value, so such a word is tested on its W bytes alone.  These entries
 // live in their own eighth of the bitmap (only one word in 64 or 128 looks there), the others in the rest.
 constexpr uint32_t FILTER_NEXT_UNKNOWN = 0x100u;
-constexpr uint32_t FILTER_L1_UNKNOWN_BITS = FILTER_L1_BITS / 8u;
-constexpr uint32_t FILTER_L1_KNOWN_BITS = FILTER_L1_BITS - FILTER_L1_UNKNOWN_BITS;
+constexpr uint32_t FILTER_L1_WORDS = FILTER_L1_BITS / 32u;
+constexpr uint32_t FILTER_L1_UNKNOWN_WORDS = FILTER_L1_WORDS / 8u;
+constexpr uint32_t FILTER_L1_KNOWN_WORDS = FILTER_L1_WORDS - FILTER_L1_UNKNOWN_WORDS;
 
-// bit index of a gram hash in level 1
-ACB_HD uint32_t filter_l1_index(uint32_t t, bool next_unknown)
+// 32-bit word of level 1 a gram hash selects (high multiply: looks at the high-order bits of the hash) ...
+ACB_HD uint32_t filter_l1_word(uint32_t t, bool next_unknown)
 {
-    return next_unknown ? FILTER_L1_KNOWN_BITS + filter_reduce(t, FILTER_L1_UNKNOWN_BITS)
-                        : filter_reduce(t, FILTER_L1_KNOWN_BITS);
+    return next_unknown ? FILTER_L1_KNOWN_WORDS + filter_reduce(t, FILTER_L1_UNKNOWN_WORDS)
+                        : filter_reduce(t, FILTER_L1_KNOWN_WORDS);
 }
+// ... and the two bits inside it (low-order bits of the hash, which the word index does not look at)
+ACB_HD uint32_t filter_bit1(uint32_t t) { return t & 31u; }
+ACB_HD uint32_t filter_bit2(uint32_t t) { return (t >> 5) & 31u; }
 
 // level 2: third independent hash, top `log2_bits` bits index a 2^log2_bits-bit map in global memory
 ACB_HD uint32_t filter_mix3(uint32_t lo, uint32_t hi, uint32_t next_byte)

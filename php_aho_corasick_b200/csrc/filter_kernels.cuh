@@ -96,10 +96,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const Filter
     // one flag per aligned word: both bits of the gram hash (the word + the byte after it) are set in level 1
     auto test_word = [&](uint32_t lo, uint32_t hi, uint32_t nb, bool maybe_unknown) -> bool {
         const uint32_t t = filter_mix1(lo, hi, nb);
-        const uint32_t idx = maybe_unknown ? filter_l1_index(t, nb == FILTER_NEXT_UNKNOWN) : filter_l1_index(t, false);
+        const uint32_t widx = maybe_unknown ? filter_l1_word(t, nb == FILTER_NEXT_UNKNOWN) : filter_l1_word(t, false);
         uint32_t word;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(s_base + ((idx >> 5) << 2)));
-        bool p = ((word >> (idx & 31u)) & (word >> filter_bit2(t)) & 1u) != 0;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(s_base + widx * 4u));
+        bool p = ((word >> filter_bit1(t)) & (word >> filter_bit2(t)) & 1u) != 0;
         if (L2) {
             uint32_t word3 = 0;
             const uint32_t i3 = filter_mix3(lo, hi, nb) >> a.l2_shift;
