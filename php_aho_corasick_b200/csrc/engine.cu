@@ -319,7 +319,8 @@ bool Engine::ensure_verify_scratch(size_t n_tiles)
     CU_OK(cudaMalloc(&d_items_, cap * VER_DENSE_MAX * sizeof(uint32_t)));
     CU_OK(cudaMalloc(&d_recs_, cap * VER_DENSE_MAX * 2 * sizeof(uint32_t)));
     CU_OK(cudaMalloc(&d_desc_, cap * 2 * sizeof(uint32_t)));
-    CU_OK(cudaMalloc(&d_tile_len_, (2 * cap + cap / EMIT_THREADS + 16) * sizeof(uint32_t)));   // events per tile, offsets per tile, block sums
+    // one block: [16 counters | block sums | events per tile | offsets per tile] — the first three are zeroed by ONE memset
+    CU_OK(cudaMalloc(&d_tile_len_, (16 + (cap / EMIT_THREADS + 16) + 2 * cap) * sizeof(uint32_t)));
     verify_tiles_cap_ = cap;
     return true;
 }
@@ -569,7 +570,10 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     fa.l2 = d_l2_; fa.l2_shift = l2_log2_ ? 32 - l2_log2_ : 0;
     fa.mask = d_mask_;
     fa.n_spans = n_spans;
-    fa.counters = d_counters_;
+    uint32_t *const vcounters = d_tile_len_;                              // counters of the prefilter path
+    uint32_t *const vblock_sum = d_tile_len_ + 16;
+    uint32_t *const vtile_len = vblock_sum + (verify_tiles_cap_ / EMIT_THREADS + 16);
+    fa.counters = vcounters;
 
     VerifyArgs va{};
     ScanArgs &a = va.s;
@@ -595,7 +599,7 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     a.n_used = n_used_;
     a.init_state = root_;
     a.tile_status = nullptr;
-    a.counters = d_counters_;
+    a.counters = vcounters;
     a.first_end = nullptr;
     va.mask = d_mask_;
     va.n_spans = n_spans;
@@ -606,9 +610,9 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     va.items = d_items_;
     va.desc = (uint2 *)d_desc_;
     va.recs = (uint2 *)d_recs_;
-    va.tile_len = d_tile_len_;
-    va.tile_off = d_tile_len_ + verify_tiles_cap_;
-    va.block_sum = d_tile_len_ + 2 * verify_tiles_cap_;
+    va.tile_len = vtile_len;
+    va.tile_off = vtile_len + verify_tiles_cap_;
+    va.block_sum = vblock_sum;
 
     // A stream can be cut into parts: while ac_filter_kernel streams part p+1, the collect and walk kernels of
     // part p run on a second stream; offsets and emit run once, after everything.  Measured on B200 this does
@@ -635,9 +639,8 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     for (int attempt = 0; attempt < 2; ++attempt) {
         a.out = (uint2 *)d_events_;
         a.capacity = (uint32_t)std::min<size_t>(events_cap_, 0xffffffffu);
-        CU_OK(cudaMemsetAsync(d_counters_, 0, 64, st));
-        CU_OK(cudaMemsetAsync(d_tile_len_, 0, (size_t)n_tiles * sizeof(uint32_t), st));   // the walk kernel adds to both
-        CU_OK(cudaMemsetAsync(va.block_sum, 0, (size_t)((n_tiles + EMIT_THREADS - 1) / EMIT_THREADS) * sizeof(uint32_t), st));
+        // counters, block sums and events per tile (the walk kernel adds to both) are adjacent: one memset
+        CU_OK(cudaMemsetAsync(vcounters, 0, (size_t)((vtile_len - vcounters) + n_tiles) * sizeof(uint32_t), st));
         CU_OK(cudaEventRecord(EV(ev_[0]), st));
         for (uint32_t p = 0; p < n_parts; ++p) {
             const uint32_t t0 = std::min(p * part_tiles, n_tiles), t1 = std::min(t0 + part_tiles, n_tiles);
@@ -687,7 +690,7 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
         CU_OK(cudaGetLastError());
         CU_OK(cudaEventRecord(EV(ev_[1]), st));
         stats.kernel_launches += 2;
-        CU_OK(cudaMemcpyAsync(h_counters_, d_counters_, 32, cudaMemcpyDeviceToHost, st));
+        CU_OK(cudaMemcpyAsync(h_counters_, vcounters, 32, cudaMemcpyDeviceToHost, st));
         CU_OK(cudaStreamSynchronize(st));
         float ms_f = 0, ms_v = 0, ms_r = 0;
         cudaEventElapsedTime(&ms_f, EV(ev_[0]), EV(ev_[4]));
