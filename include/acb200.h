@@ -268,6 +268,8 @@ typedef struct acb200_info
     float filter_l1_fill;     /* fraction of level-1 prefilter bits set      */
     uint32_t filter_l2_log2;  /* log2(bits) of the level-2 bitmap, 0 = none  */
     uint32_t reserved_;
+    uint32_t direct_keys;      /* distinct grams in the exact gram table (0 = no table)                  */
+    uint32_t direct_walk_keys; /* of those, grams that cannot be decided by one comparison (are walked)  */
 } ACB200_INFO_t;
 int acb200_info(const AC_TRIE_t *thiz, ACB200_INFO_t *out);
 
@@ -289,6 +291,7 @@ typedef struct acb200_stats
     uint64_t dense_tiles;     /* 16 KiB tiles handed to verification as whole spans */
     float reorder_ms;         /* device time of the offsets + emit kernels (0 if unused) */
     float expand_ms;          /* device time of the hit expansion kernels (acb200_search_hits) */
+    uint32_t fused;           /* 1: filter, item lists and window staging in one pass (ac_filter_collect_kernel) */
 } ACB200_STATS_t;
 int acb200_last_stats(const AC_TRIE_t *thiz, ACB200_STATS_t *out);
 
@@ -323,6 +326,23 @@ int acb200_set_filter(AC_TRIE_t *thiz, int mode);
  * "unknown".  Returns 1 if the word would be handed to verification, 0 if not, -1 if the dictionary has no
  * prefilter.  Not a matching path: tests use it to check that no occurrence can be filtered away.        */
 int acb200_filter_probe(const AC_TRIE_t *thiz, uint64_t word, unsigned next_byte);
+
+/* Direct verification of flagged words (gram_table.hpp): a flagged word whose (word, next byte) belongs to exactly
+ * one (pattern, alignment) is decided by comparing the haystack with that pattern instead of walking the
+ * automaton.  0 = automatic (currently 1), 1 = inside ac_walk_kernel, 2 = fused pass (ac_filter_collect_kernel
+ * filters, builds the item lists and stages the windows; opt-in, measured slower so far), -1 = off (every flagged
+ * word is walked).  Results are identical in every mode. */
+int acb200_set_direct(AC_TRIE_t *thiz, int mode);
+
+/* Diagnostic: the direct verification of the aligned word `word_index` (bytes [W*word_index, W*word_index + W) of
+ * the stream `bytes`) evaluated on the HOST with the code the kernels run; the haystack that contains the W end
+ * offsets after the word starts at stream offset `hay_begin` (bytes before it belong to another haystack).
+ * Returns 0 = nothing ends at those offsets, 1 = exactly one event (*end = its exclusive end offset in the
+ * stream, *state = the automaton state the event carries), 2 = undecided (the kernel walks the automaton),
+ * -1 = not applicable (no table, or the window [W*(word_index+1) - warm, W*(word_index+2)) does not lie inside
+ * the stream).  Not a matching path: tests check the table construction against the CPU oracle with it. */
+int acb200_direct_probe(const AC_TRIE_t *thiz, const char *bytes, size_t length, size_t hay_begin, size_t word_index,
+                        uint32_t *end, uint32_t *state);
 
 /* Parts a prefiltered scan is cut into (the filter of part p+1 overlaps the verification of part p on a
  * second stream): 0 = automatic (currently 1: overlapping did not pay on B200), 1..8 = fixed. */

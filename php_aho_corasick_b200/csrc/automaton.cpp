@@ -270,6 +270,7 @@ void HostTrie::flatten(FlatAutomaton &flat) {
     }
 
     build_filter(flat);
+    build_gram_table(flat);
 }
 
 // Gram prefilter tables (see FlatAutomaton).  Every ACCEPTED pattern contributes the W words that can be
@@ -327,6 +328,90 @@ void HostTrie::build_filter(FlatAutomaton &flat) const {
                     flat.l2[i >> 5] |= 1u << (i & 31);
                 }
             }
+    }
+}
+
+// Exact gram table (gram_table.hpp), derived from the flat description alone so that a loaded blob gets it too.
+void build_gram_table(FlatAutomaton &flat) {
+    flat.gt_log2 = 0; flat.gt_slots.clear(); flat.gt_pat.clear(); flat.gt_keys = 0; flat.gt_walk_keys = 0;
+    const uint32_t W = flat.filter_w;
+    const size_t np = flat.accepted.size();
+    if ((W != 4 && W != 8) || np == 0 || np * W > (1ull << 27)) return;
+    if (getenv("ACB200_NO_GRAM_TABLE")) return;
+    // (a loaded blob is only structurally validated: make sure of what is indexed below)
+    for (const AC_PATTERN_t &p : flat.accepted)
+        if (p.ptext.length < 2 * W || p.ptext.length > AC_PATTRN_MAX_LENGTH) return;
+    if (flat.level_off.empty() || flat.level_off.back() > flat.bfs_order.size() || flat.fail.size() < flat.n_rows ||
+        flat.out_off.size() < flat.final_bound) return;
+    for (size_t d = 0; d + 1 < flat.level_off.size(); ++d)
+        if (flat.level_off[d] > flat.level_off[d + 1]) return;
+
+    // depth of every state from the breadth-first order; states some other state fails to
+    std::vector<uint32_t> depth(flat.n_rows, 0);
+    for (size_t d = 0; d + 1 < flat.level_off.size(); ++d)
+        for (uint32_t i = flat.level_off[d]; i < flat.level_off[d + 1]; ++i) depth[flat.bfs_order[i]] = (uint32_t)d;
+    std::vector<uint8_t> fail_target(flat.n_rows, 0);
+    for (uint32_t s : flat.bfs_order)
+        if (s != flat.root) fail_target[flat.fail[s]] = 1;
+
+    // the state of each pattern's own node: the final state whose longest output is the pattern at full depth
+    std::vector<uint32_t> pat_state(np, 0);
+    for (uint32_t s = 1; s < flat.final_bound; ++s) {
+        const uint64_t o = flat.out_off[s - 1];
+        if (o == flat.out_off[s]) continue;
+        const uint32_t pi = flat.out_idx[o];
+        if (flat.accepted[pi].ptext.length == depth[s]) pat_state[pi] = s;
+    }
+
+    // pattern store
+    std::vector<uint32_t> pat_ref(np, 0);
+    for (size_t pi = 0; pi < np; ++pi) {
+        const size_t len = flat.accepted[pi].ptext.length;
+        const size_t padded = (len + W - 1) / W * W;
+        const size_t at = flat.gt_pat.size();
+        flat.gt_pat.resize(at + padded / 4 + 2, 0);               // bytes, state id, one word of padding (8-byte records)
+        memcpy((uint8_t *)(flat.gt_pat.data() + at) + (padded - len), flat.accepted[pi].ptext.astring, len);
+        pat_ref[pi] = (uint32_t)(at + padded / 4);
+        flat.gt_pat[pat_ref[pi]] = pat_state[pi];
+    }
+
+    uint32_t lg = 10;
+    while ((1ull << lg) < 2ull * np * W) ++lg;
+    flat.gt_log2 = lg;
+    flat.gt_slots.assign((size_t)1 << lg, GramSlot{0, 0, 0, 0, {0, 0, 0, 0}});
+    const uint32_t mask = (1u << lg) - 1u;
+    for (size_t pi = 0; pi < np; ++pi) {
+        const AC_PATTERN_t &p = flat.accepted[pi];
+        const uint32_t len = (uint32_t)p.ptext.length;
+        // a pattern without a node of its own (cannot happen) or whose node is a failure target: walk
+        const bool walk = pat_state[pi] == 0 || fail_target[pat_state[pi]];
+        for (uint32_t r = 1; r <= W; ++r) {
+            const uint8_t *b = (const uint8_t *)p.ptext.astring + (len - W - r);
+            uint32_t lo = 0, hi = 0;
+            memcpy(&lo, b, 4);
+            if (W == 8) memcpy(&hi, b + 4, 4);
+            const uint32_t nb = b[W];
+            uint32_t i = gram_home(lo, hi, nb, lg);
+            while (true) {
+                GramSlot &s = flat.gt_slots[i];
+                if (!(s.meta & GRAM_USED)) {
+                    const bool inl = len <= 16;
+                    s = GramSlot{lo, hi, gram_meta(len, r, nb) | (walk ? GRAM_WALK : 0u) | (inl ? GRAM_INLINE : 0u),
+                                 inl ? pat_state[pi] : pat_ref[pi], {0, 0, 0, 0}};
+                    const uint32_t nt = std::min<uint32_t>(len, 16u);
+                    memcpy((uint8_t *)s.tail + (16 - nt), (const uint8_t *)p.ptext.astring + (len - nt), nt);
+                    ++flat.gt_keys;
+                    if (walk) ++flat.gt_walk_keys;
+                    break;
+                }
+                if (s.key_lo == lo && s.key_hi == hi && gram_meta_next(s.meta) == nb) {
+                    // a second (pattern, r) under one key: more than one candidate
+                    if (!(s.meta & GRAM_WALK)) { s.meta |= GRAM_WALK; ++flat.gt_walk_keys; }
+                    break;
+                }
+                i = (i + 1u) & mask;
+            }
+        }
     }
 }
 

@@ -15,6 +15,7 @@
 #include <deque>
 
 #include "acb200.h"
+#include "gram_table.hpp"
 
 namespace acb200 {
 
@@ -79,7 +80,17 @@ struct FlatAutomaton {
     std::vector<uint32_t> l2;
     uint64_t n_grams = 0;
     double l1_fill = 0.0;              // fraction of level-1 bits set
+
+    // Exact gram table (gram_table.hpp): decides most flagged words with one comparison instead of a walk.
+    // Derived from the fields above by build_gram_table(); not part of the blob.
+    uint32_t gt_log2 = 0;              // 2^gt_log2 slots; 0: no table
+    std::vector<GramSlot> gt_slots;
+    std::vector<uint32_t> gt_pat;      // per pattern: its bytes, zero-padded in FRONT to a multiple of W, then its state id
+    uint64_t gt_keys = 0, gt_walk_keys = 0;
 };
+
+// Fills the gt_* fields from the rest of `flat` (needs filter_w, accepted, out lists, fail, bfs order).
+void build_gram_table(FlatAutomaton &flat);
 
 // blob.cpp: position-independent dump of a finalized automaton
 bool save_flat(const FlatAutomaton &flat, const char *path, std::string &err);

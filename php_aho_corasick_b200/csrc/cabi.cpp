@@ -107,6 +107,7 @@ AC_TRIE_t *acb200_load(const char *path)
     if (!t) { set_error("out of memory"); return nullptr; }
     std::string err;
     if (!load_flat(t->flat, t->blob_arena, path, err)) { set_error(err); delete t; return nullptr; }
+    build_gram_table(t->flat);
     t->open = false;
     set_error("");
     t->device_ok = t->engine.build(t->flat);
@@ -370,6 +371,8 @@ int acb200_info(const AC_TRIE_t *t, ACB200_INFO_t *out)
         out->min_pattern_len = t->flat.min_pattern_len;
         out->filter_l1_fill = (float)t->flat.l1_fill;
         out->filter_l2_log2 = t->flat.l2_log2;
+        out->direct_keys = (uint32_t)t->flat.gt_keys;
+        out->direct_walk_keys = (uint32_t)t->flat.gt_walk_keys;
     }
     return 0;
 }
@@ -413,6 +416,39 @@ int acb200_filter_probe(const AC_TRIE_t *t, uint64_t word, unsigned next_byte)
         if (!((f.l2[i3 >> 5] >> (i3 & 31)) & 1u)) return 0;
     }
     return 1;
+}
+
+int acb200_set_direct(AC_TRIE_t *t, int mode)
+{
+    t->engine.tune_direct = mode;
+    return 0;
+}
+
+int acb200_direct_probe(const AC_TRIE_t *t, const char *bytes, size_t length, size_t hay_begin, size_t word_index, uint32_t *end, uint32_t *state)
+{
+    const FlatAutomaton &f = t->flat;
+    if (t->open || f.filter_w == 0 || f.gt_log2 == 0) return -1;
+    const uint32_t W = f.filter_w;
+    const uint32_t warm = (f.max_pattern_len - 1 + W - 1) / W * W;
+    const uint64_t rs = (uint64_t)(word_index + 1) * W;
+    if (rs < warm || rs + W > length || rs + W > 0xffffffffull) return -1;     // window clipped by the stream: the kernel walks
+    const uint32_t hb = (uint32_t)std::min<uint64_t>(hay_begin, rs);
+    const uint8_t *text = (const uint8_t *)bytes;
+    auto slot = [&](uint32_t i) { return f.gt_slots[i]; };
+    auto st = [&](uint32_t i) { return f.gt_pat[i]; };
+    uint32_t e = 0, s = 0;
+    int v;
+    if (W == 8) {
+        auto txt = [&](uint32_t i) { uint64_t c; memcpy(&c, text + i, 8); return c; };
+        auto pat = [&](uint32_t i) { uint64_t c; memcpy(&c, f.gt_pat.data() + i, 8); return c; };
+        v = (int)gram_verify<8>((uint32_t)rs, warm, hb, f.gt_log2, txt, slot, pat, st, &e, &s);
+    } else {
+        auto txt = [&](uint32_t i) { uint32_t c; memcpy(&c, text + i, 4); return c; };
+        auto pat = [&](uint32_t i) { return f.gt_pat[i]; };
+        v = (int)gram_verify<4>((uint32_t)rs, warm, hb, f.gt_log2, txt, slot, pat, st, &e, &s);
+    }
+    if (v == GRAM_EVENT) { if (end) *end = e; if (state) *state = s; }
+    return v;
 }
 
 int acb200_set_parts(AC_TRIE_t *t, unsigned parts)

@@ -59,10 +59,12 @@ void Engine::release()
     cudaFree(d_table_); cudaFree(d_cls_); cudaFree(d_text_); cudaFree(d_off_);
     cudaFree(d_first_); cudaFree(d_events_); cudaFree(d_tiles_); cudaFree(d_counters_);
     cudaFree(d_l1_); cudaFree(d_l2_); cudaFree(d_mask_);
+    cudaFree(d_gt_slots_); cudaFree(d_gt_pat_); d_gt_slots_ = nullptr; d_gt_pat_ = nullptr; gt_log2_ = 0;
     cudaFree(d_out_off_); cudaFree(d_out_idx_); cudaFree(d_pat_len_); cudaFree(d_hit_sums_); cudaFree(d_hits_); cudaFree(d_hit_total_);
     d_out_off_ = nullptr; d_out_idx_ = nullptr; d_pat_len_ = nullptr; d_hit_sums_ = nullptr; d_hits_ = nullptr; d_hit_total_ = nullptr;
     hit_sums_cap_ = 0; hits_cap_ = 0;
-    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_);
+    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_); cudaFree(d_stage_);
+    d_stage_ = nullptr; stage_tiles_cap_ = 0;
     d_l1_ = nullptr; d_l2_ = nullptr; d_mask_ = nullptr; mask_cap_ = 0;
     d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; verify_tiles_cap_ = 0;
     if (h_counters_) cudaFreeHost(h_counters_);
@@ -231,11 +233,22 @@ bool Engine::build(const FlatAutomaton &f)
             CU_OK(cudaMalloc(&d_l2_, f.l2.size() * sizeof(uint32_t)));
             CU_OK(cudaMemcpyAsync(d_l2_, f.l2.data(), f.l2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         }
+        if (f.gt_log2 && !f.gt_slots.empty() && !f.gt_pat.empty()) {
+            CU_OK(cudaMalloc(&d_gt_slots_, f.gt_slots.size() * sizeof(GramSlot)));
+            CU_OK(cudaMemcpyAsync(d_gt_slots_, f.gt_slots.data(), f.gt_slots.size() * sizeof(GramSlot), cudaMemcpyHostToDevice, st));
+            CU_OK(cudaMalloc(&d_gt_pat_, f.gt_pat.size() * sizeof(uint32_t)));
+            CU_OK(cudaMemcpyAsync(d_gt_pat_, f.gt_pat.data(), f.gt_pat.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            gt_log2_ = f.gt_log2;
+        }
         CU_OK(cudaStreamSynchronize(st));
         CU_OK(cudaFuncSetAttribute(ac_filter_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
         CU_OK(cudaFuncSetAttribute(ac_filter_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
         CU_OK(cudaFuncSetAttribute(ac_filter_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
         CU_OK(cudaFuncSetAttribute(ac_filter_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
+        CU_OK((cudaFuncSetAttribute(ac_filter_collect_kernel<8, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
+        CU_OK((cudaFuncSetAttribute(ac_filter_collect_kernel<8, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
+        CU_OK((cudaFuncSetAttribute(ac_filter_collect_kernel<4, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
+        CU_OK((cudaFuncSetAttribute(ac_filter_collect_kernel<4, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
     }
     info.filter_word = (int32_t)filter_w_;
     info.min_pattern_len = f.min_pattern_len;
@@ -313,8 +326,8 @@ bool Engine::ensure_mask(size_t words)
 bool Engine::ensure_verify_scratch(size_t n_tiles)
 {
     if (n_tiles <= verify_tiles_cap_) return true;
-    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_);
-    d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; verify_tiles_cap_ = 0;
+    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_); cudaFree(d_stage_);
+    d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; d_stage_ = nullptr; stage_tiles_cap_ = 0; verify_tiles_cap_ = 0;
     const size_t cap = std::max(n_tiles + n_tiles / 4, (size_t)256);
     CU_OK(cudaMalloc(&d_items_, cap * VER_DENSE_MAX * sizeof(uint32_t)));
     CU_OK(cudaMalloc(&d_recs_, cap * VER_DENSE_MAX * 2 * sizeof(uint32_t)));
@@ -402,7 +415,7 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     stats.bytes = total; stats.events = 0; stats.kernel_launches = 0; stats.kernel_ms = 0;
     stats.halo_bytes = halo_;
     stats.filtered = 0; stats.filter_ms = 0; stats.verify_ms = 0; stats.flagged_words = 0; stats.dense_tiles = 0;
-    stats.reorder_ms = 0; stats.expand_ms = 0;
+    stats.reorder_ms = 0; stats.expand_ms = 0; stats.fused = 0;
     if (total == 0) { stats.chunk_bytes = 0; return true; }
 
     // Gram prefilter: needs an eligible dictionary and a walk that starts at the root.  Automatic mode
@@ -528,6 +541,14 @@ static void launch_filter_k(const FilterArgs &fa, bool l2, unsigned grid, cudaSt
     else ac_filter_kernel<W, false><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa);
 }
 
+template <int W>
+static void launch_fused_k(const FilterArgs &fa, const VerifyArgs &a, bool l2, unsigned grid, cudaStream_t st)
+{
+    // six 512-byte loads in flight per warp: 4, 6 and 8 measured the same on B200
+    if (l2) ac_filter_collect_kernel<W, true, 6><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa, a);
+    else ac_filter_collect_kernel<W, false, 6><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa, a);
+}
+
 template <typename E, int W>
 static void launch_walk_k(const VerifyArgs &a, bool range, unsigned grid, cudaStream_t st)
 {
@@ -607,6 +628,12 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     va.dense_max = dense_max;
     va.warm = warm;
     va.want_end_state = (n_hay == 1) ? 1u : 0u;
+    const bool direct = gt_log2_ && tune_direct >= 0;
+    va.gt_slots = direct ? (const uint4 *)d_gt_slots_ : nullptr;
+    va.gt_pat = d_gt_pat_;
+    va.gt_log2 = direct ? gt_log2_ : 0u;
+    va.stage = nullptr;
+    va.partial_span = (total % SPAN_BYTES) ? total / SPAN_BYTES : 0xffffffffu;
     va.items = d_items_;
     va.desc = (uint2 *)d_desc_;
     va.recs = (uint2 *)d_recs_;
@@ -630,6 +657,19 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
         }
         st2 = S(verify_stream_);
     }
+    // tune_direct: 0 / 1 filter, collect and walk kernels, flagged words settled by one comparison inside ac_walk_kernel
+    // where the gram table allows (the default: best measured); -1 every flagged word walked; 2 the fused path: ONE
+    // pass filters the haystack, builds the item lists and stages every flagged word's window
+    // (ac_filter_collect_kernel), ac_walk_kernel settles the items from the staged windows.  Measured on B200
+    // (1 GiB config 2, 1.57 M flagged words) the fused pass takes 0.256 ms against 0.205 + 0.017 ms for filter +
+    // collect, and the slot-indexed walk 0.22 ms against 0.105 ms: opt-in until that kernel is rebuilt.
+    const bool fused = direct && tune_direct == 2 && n_parts == 1;
+    stats.fused = fused ? 1u : 0u;
+    if (fused && stage_tiles_cap_ < verify_tiles_cap_) {
+        cudaFree(d_stage_); d_stage_ = nullptr; stage_tiles_cap_ = 0;
+        CU_OK(cudaMalloc(&d_stage_, verify_tiles_cap_ * VER_DENSE_MAX * (size_t)STAGE_BYTES));
+        stage_tiles_cap_ = verify_tiles_cap_;
+    }
     const unsigned warps_per_cta = SCAN_THREADS / 32;
     const unsigned tiles_per_cta = COLLECT_THREADS / 32;
     const unsigned grid_w = (unsigned)n_sms_ * 8u;
@@ -640,8 +680,33 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
         a.out = (uint2 *)d_events_;
         a.capacity = (uint32_t)std::min<size_t>(events_cap_, 0xffffffffu);
         // counters, block sums and events per tile (the walk kernel adds to both) are adjacent: one memset
-        CU_OK(cudaMemsetAsync(vcounters, 0, (size_t)((vtile_len - vcounters) + n_tiles) * sizeof(uint32_t), st));
+        if (!fused || attempt == 0)
+            CU_OK(cudaMemsetAsync(vcounters, 0, (size_t)((vtile_len - vcounters) + n_tiles) * sizeof(uint32_t), st));
         CU_OK(cudaEventRecord(EV(ev_[0]), st));
+        if (fused) {
+            // (after a regrow of the event buffer the items, records and per-tile counts are still valid: only
+            // the offsets + emit kernels run again)
+            if (attempt == 0) {
+                va.tile_begin = 0; va.tile_end = n_tiles;
+                va.item_base = 0;
+                va.counter_slot = 8u;
+                va.stage = (uint4 *)d_stage_;
+                const unsigned grid_f = std::min<uint32_t>((n_tiles + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
+                if (W == 8) launch_fused_k<8>(fa, va, d_l2_ != nullptr, grid_f, st);
+                else launch_fused_k<4>(fa, va, d_l2_ != nullptr, grid_f, st);
+            }
+            CU_OK(cudaEventRecord(EV(ev_[4]), st));
+            if (attempt == 0) {
+                if (entry_bytes_ == 2) {
+                    if (W == 8) launch_walk_k<uint16_t, 8>(va, range_map_, grid_w, st);
+                    else launch_walk_k<uint16_t, 4>(va, range_map_, grid_w, st);
+                } else {
+                    if (W == 8) launch_walk_k<uint32_t, 8>(va, range_map_, grid_w, st);
+                    else launch_walk_k<uint32_t, 4>(va, range_map_, grid_w, st);
+                }
+                stats.kernel_launches += 2;
+            }
+        } else
         for (uint32_t p = 0; p < n_parts; ++p) {
             const uint32_t t0 = std::min(p * part_tiles, n_tiles), t1 = std::min(t0 + part_tiles, n_tiles);
             if (t0 == t1) continue;

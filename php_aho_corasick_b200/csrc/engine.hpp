@@ -60,6 +60,8 @@ public:
     uint32_t tune_smem_bytes = 0;
     int tune_ilp = 0;              // 0 auto, 1 one slice per lane, 4 four slices per lane
     int tune_filter = 0;           // 0 auto, 1 always use the gram prefilter when the dictionary allows, -1 never
+    int tune_direct = 0;           // 0 auto (= 1), 1 direct verification of flagged words inside the walk kernel, 2 fused
+                                   // filter + collect pass that stages the windows (opt-in), -1 every flagged word is walked
     uint32_t tune_parts = 0;       // 0 auto; parts a filtered scan is cut into (filter of part p+1 overlaps verification of part p)
 
 private:
@@ -103,7 +105,12 @@ private:
     unsigned long long *d_hit_total_ = nullptr;
     uint32_t last_uniform_len_ = 0;            // batch shape of the most recent scan (hit expansion needs it)
     uint32_t *d_l1_ = nullptr, *d_l2_ = nullptr;
+    void *d_gt_slots_ = nullptr;    // exact gram table (gram_table.hpp)
+    uint32_t *d_gt_pat_ = nullptr;
+    uint32_t gt_log2_ = 0;
     uint32_t *d_mask_ = nullptr;  size_t mask_cap_ = 0;
+    void *d_stage_ = nullptr;       // fused path: per item slot the 48 bytes around the flagged word (allocated on first use)
+    size_t stage_tiles_cap_ = 0;
     uint32_t *d_items_ = nullptr;   // work items of the verify kernels
     uint32_t *d_recs_ = nullptr;    // per item {first event state, count << 16 | relative end}
     uint32_t *d_desc_ = nullptr;    // per 16 KiB tile {offset into items, count}

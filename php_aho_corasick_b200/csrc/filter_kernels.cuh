@@ -43,6 +43,7 @@
 
 #include "scan_kernels.cuh"
 #include "filter_hash.hpp"
+#include "gram_table.hpp"
 
 namespace acb200 {
 
@@ -188,6 +189,12 @@ struct VerifyArgs {
     uint32_t dense_max;           // more flagged words than this in a tile: hand on the tile's spans instead
     uint32_t warm;                // warm-up bytes before a flagged word's end offsets (halo rounded up to W)
     uint32_t want_end_state;      // also compute the state at the end of the stream (counters[2])
+    const uint4 *gt_slots;        // exact gram table (gram_table.hpp) or nullptr
+    const uint32_t *gt_pat;       // its pattern store
+    uint32_t gt_log2;             // 2^gt_log2 slots; 0: every flagged word is walked
+    uint4 *stage;                 // fused path: per item slot the three 16-byte chunks around the flagged word (ac_filter_collect_kernel
+                                  // writes, ac_walk_kernel reads); nullptr: items are a dense list and windows come from the haystack
+    uint32_t partial_span;        // index of the stream's last, partial span (never staged) or 0xffffffff
     uint32_t *items;              // work items, tile runs in completion order (capacity n_tiles * VER_DENSE_MAX)
     uint2 *desc;                  // per tile {offset into items, count}
     uint2 *recs;                  // per item {state of the first event, count << 16 | first end - item origin}
@@ -433,6 +440,64 @@ __device__ __noinline__ ItemEvents walk_item_slow(const ScanArgs &a, uint32_t s_
     return ItemEvents{sc.cnt, sc.e0p, sc.e0s};
 }
 
+// Direct verification of the flagged word before rs (gram_table.hpp): one table probe and one comparison of the
+// haystack with the only pattern that can end in the word's window.  false: the automaton has to be walked.
+template <int W, typename LT>
+__device__ __forceinline__ bool verify_word_direct(const VerifyArgs &a, uint32_t rs, uint32_t hay_begin, LT load_text, ItemEvents &ev)
+{
+    typedef typename GramChunk<W>::type chunk_t;
+    const uint4 *slots = a.gt_slots;
+    const uint32_t *pat = a.gt_pat;
+    auto load_slot = [slots](uint32_t i) -> GramSlot {
+        const uint4 v = __ldg(slots + 2u * i), t = __ldg(slots + 2u * i + 1u);      // one 32-byte sector
+        return GramSlot{v.x, v.y, v.z, v.w, {t.x, t.y, t.z, t.w}};
+    };
+    auto load_pat = [pat](uint32_t i) -> chunk_t {
+        if (W == 8) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(pat + i));
+            return (chunk_t)(((uint64_t)v.y << 32) | v.x);
+        }
+        return (chunk_t)__ldg(pat + i);
+    };
+    auto load_state = [pat](uint32_t i) -> uint32_t { return __ldg(pat + i); };
+    uint32_t end = 0, state = 0;
+    const GramVerdict v = gram_verify<W>(rs, a.warm, hay_begin, a.gt_log2, load_text, load_slot, load_pat, load_state, &end, &state);
+    if (v == GRAM_NEEDS_WALK) return false;
+    ev = (v == GRAM_EVENT) ? ItemEvents{1u, end, state} : ItemEvents{0u, 0u, 0u};
+    return true;
+}
+
+template <int W>
+__device__ __forceinline__ typename GramChunk<W>::type group_chunk(uint2 g)
+{
+    typedef typename GramChunk<W>::type chunk_t;
+    return (W == 8) ? (chunk_t)(((uint64_t)g.y << 32) | g.x) : (chunk_t)g.x;
+}
+
+// ... with every group read from the haystack in memory
+template <int W>
+__device__ __forceinline__ bool verify_word_direct(const VerifyArgs &a, uint32_t rs, uint32_t hay_begin, ItemEvents &ev)
+{
+    const uint8_t *text = a.s.text;
+    return verify_word_direct<W>(a, rs, hay_begin, [text](uint32_t i) { return group_chunk<W>(ld_group<W>(text, i)); }, ev);
+}
+
+constexpr uint32_t STAGE_BYTES = 48;       // per work item: the three 16-byte chunks around the flagged word
+
+// window of the flagged word `item` inside its 48-byte stage record: [rs - 2W, rs + W) starts at this byte
+template <int W>
+__device__ __forceinline__ uint32_t stage_window_offset(uint32_t item) { return 16u + W * (item % (16u / W)) - W; }
+
+// Is the record complete?  The neighbours of a span's first / last word sit in another warp-load, and the partial
+// span at the end of the stream is not staged at all.
+template <int W>
+__device__ __forceinline__ bool stage_complete(uint32_t item, uint32_t partial_span)
+{
+    constexpr uint32_t NB = 16u / W;
+    const uint32_t in_span = item % (32u * NB);
+    return in_span != 0u && in_span != 32u * NB - 1u && item / (32u * NB) != partial_span;
+}
+
 // origin of an item's end offsets: a record stores its first event's end relative to this
 template <int W>
 __device__ __forceinline__ uint32_t item_origin(uint32_t item)
@@ -461,17 +526,21 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
     st.ncls = a.s.ncls; st.lo = a.s.range_lo; st.n_used = a.s.n_used;
     st.final_bound = a.s.final_bound; st.root = a.s.root;
 
-    const uint32_t n_items = a.s.counters[a.counter_slot];
+    // fused path: item slots (VER_DENSE_MAX per tile, the first desc[tile].y in use); else the dense list ac_collect_kernel made
+    const uint32_t n_items = a.stage ? a.n_tiles * VER_DENSE_MAX : a.s.counters[a.counter_slot];
     const uint32_t n_threads = gridDim.x * WALK_THREADS;
     constexpr int K = WALK_ILP;
     // a thread takes K consecutive items and walks them in lockstep
     for (uint32_t i0 = (blockIdx.x * WALK_THREADS + threadIdx.x) * K; i0 < n_items; i0 += n_threads * K) {
-        uint32_t item[K], rs[K], w0[K];
-        bool lock[K];
+        uint32_t item[K], rs[K], w0[K], slot[K];
+        bool lock[K], valid[K];
         bool all_lock = true;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            item[k] = (i0 + k < n_items) ? a.items[a.item_base + i0 + k] : ITEM_NONE;
+            slot[k] = a.item_base + i0 + k;
+            valid[k] = i0 + k < n_items;
+            if (a.stage && valid[k]) valid[k] = (slot[k] % VER_DENSE_MAX) < a.desc[slot[k] / VER_DENSE_MAX].y;
+            item[k] = valid[k] ? a.items[slot[k]] : ITEM_NONE;
             rs[k] = 0; w0[k] = 0; lock[k] = false;
             if (item[k] != ITEM_NONE && !(item[k] & ITEM_SPAN)) {
                 rs[k] = (item[k] + 1u) * W;            // the W end offsets owned by word k are rs+1 .. rs+W
@@ -486,7 +555,27 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
             all_lock = all_lock && lock[k];
         }
         ItemEvents ev[K];
-        if (all_lock) {
+        // most flagged words are settled by one comparison against the only pattern their gram belongs to
+        bool all_direct = a.gt_log2 != 0;
+        if (all_direct) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (!(all_direct && lock[k])) { all_direct = false; break; }
+                if (a.stage && stage_complete<W>(item[k], a.partial_span)) {
+                    // the window [rs - 2W, rs + W) was copied next to the item while the filter had it in registers
+                    const uint8_t *rec = reinterpret_cast<const uint8_t *>(a.stage) + (size_t)slot[k] * STAGE_BYTES + stage_window_offset<W>(item[k]);
+                    const uint2 g0 = ld_group<W>(rec, 0), g1 = ld_group<W>(rec, W), g2 = ld_group<W>(rec, 2 * W);
+                    const uint8_t *text = a.s.text;
+                    const uint32_t r = rs[k];
+                    all_direct = verify_word_direct<W>(a, r, w0[k], [=](uint32_t i) {
+                        return group_chunk<W>((i == r) ? g2 : (i == r - W) ? g1 : (i == r - 2u * W) ? g0 : ld_group<W>(text, i)); }, ev[k]);
+                } else {
+                    all_direct = verify_word_direct<W>(a, rs[k], w0[k], ev[k]);
+                }
+            }
+        }
+        if (all_direct) {
+        } else if (all_lock) {
             walk_words_lockstep<W, K>(st, a.s.text, a.warm, rs, w0, ev);
         } else {
 #pragma unroll 1
@@ -512,9 +601,9 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            if (i0 + k < n_items) {
+            if (valid[k]) {
                 const uint32_t rel = ev[k].cnt ? ev[k].e0p - item_origin<W>(item[k]) : 0u;
-                a.recs[a.item_base + i0 + k] = make_uint2(ev[k].e0s, (min(ev[k].cnt, 0xffffu) << 16) | (rel & 0xffffu));
+                a.recs[slot[k]] = make_uint2(ev[k].e0s, (min(ev[k].cnt, 0xffffu) << 16) | (rel & 0xffffu));
                 if (ev[k].cnt) atomicAdd(&a.tile_len[item_tile<W>(item[k])], ev[k].cnt);   // events per tile, for the offsets
             }
         }
@@ -522,7 +611,7 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
         // atomic per warp (same-address atomics serialise)
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const bool has = (i0 + k < n_items) && ev[k].cnt;
+            const bool has = valid[k] && ev[k].cnt;
             const uint32_t blk = has ? item_tile<W>(item[k]) / EMIT_THREADS : 0xffffffffu;
             const uint32_t act = __activemask();
             const uint32_t voters = __ballot_sync(act, has);
@@ -546,6 +635,165 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
         const uint32_t ws = (a.s.total > back) ? ((a.s.total - back) & ~(uint32_t)(W - 1)) : 0u;
         a.s.counters[2] = walk_item_slow<E, RANGE, W, false>(a.s, s_cls_addr, ITEM_NONE, ws, 0xffffffffu, a.s.total, 0u).e0s;
     }
+}
+
+// ------------------------------------------------------- fused filter -----
+
+// ac_filter_kernel + ac_collect_kernel in ONE pass, one warp per 16 KiB tile and no CTA-wide barrier after the
+// bitmap is staged: a warp streams its tile (FUSED_UNROLL 512-byte loads in flight), keeps the flag bits of span
+// l in lane l and turns them into the tile's ordered item list (a tile owns VER_DENSE_MAX slots: no atomics).
+// While a flagged word's 16-byte chunk and its two neighbours are still in registers they are copied to the
+// item's stage record, so that ac_walk_kernel finds the word's verification window in a dense, sequentially
+// written buffer instead of re-reading the haystack around every flagged word (one random DRAM access per item,
+// which is what bounds it).  No bit planes are written.
+template <int W, bool L2, int FUSED_UNROLL>
+__global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_collect_kernel(const FilterArgs fa, const __grid_constant__ VerifyArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *s_bm = reinterpret_cast<uint32_t *>(smem_raw);
+    constexpr int NB = 16 / W;
+    constexpr uint32_t WORDS_PER_SPAN = 32u * NB;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(fa.l1);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_bm);
+        const uint32_t n4 = fa.l1_bits >> 7;
+        for (uint32_t i = tid; i < n4; i += SCAN_THREADS) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_bm);
+
+    auto test_word = [&](uint32_t lo, uint32_t hi, uint32_t nb, bool maybe_unknown) -> bool {
+        const uint32_t t = filter_mix1(lo, hi, nb);
+        const uint32_t widx = maybe_unknown ? filter_l1_word(t, nb == FILTER_NEXT_UNKNOWN) : filter_l1_word(t, false);
+        uint32_t word;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(s_base + widx * 4u));
+        bool p = ((word >> filter_bit1(t)) & (word >> filter_bit2(t)) & 1u) != 0;
+        if (L2) {
+            uint32_t word3 = 0;
+            const uint32_t i3 = filter_mix3(lo, hi, nb) >> fa.l2_shift;
+            if (p) word3 = __ldg(fa.l2 + (i3 >> 5));
+            p = (word3 >> (i3 & 31u)) & 1u;
+        }
+        return p;
+    };
+    // flag bits of one 16-byte chunk per lane: plane j bit c <=> word j of lane c
+    auto test_chunk = [&](const uint4 &v, bool chunk_known, bool next_known, bool force, uint32_t (&plane)[NB]) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t after = __shfl_down_sync(0xffffffffu, w[0], 1) & 0xffu;
+        if (lane == 31u || !next_known) after = FILTER_NEXT_UNKNOWN;     // the next chunk is not in this warp's registers
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const uint32_t nb = (j == NB - 1) ? after : (((W == 8) ? w[2] : w[j + 1]) & 0xffu);
+            bool p = (W == 8) ? test_word(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test_word(w[j], 0u, nb, j == NB - 1);
+            p = chunk_known ? p : force;
+            plane[j] = __ballot_sync(0xffffffffu, p);
+        }
+    };
+
+    const uint32_t n_full_all = fa.total / SPAN_BYTES;       // spans that lie completely inside the stream
+    const uint32_t n_warps = gridDim.x * (SCAN_THREADS / 32);
+    uint32_t flagged = 0, dense_tiles = 0;
+
+    for (uint32_t tile = blockIdx.x * (SCAN_THREADS / 32) + (tid >> 5); tile < a.n_tiles; tile += n_warps) {
+        const uint32_t span0 = tile * 32u;
+        const uint32_t base = tile * VER_DENSE_MAX;
+        const uint32_t n_here = min(32u, n_full_all > span0 ? n_full_all - span0 : 0u);   // complete spans of this tile
+        uint32_t pl[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) pl[j] = 0;
+        uint32_t n_arr = 0;                                   // flagged words of the tile so far (warp-uniform) = next item slot
+
+        for (uint32_t s0 = 0; s0 < n_here; s0 += FUSED_UNROLL) {
+            uint4 v[FUSED_UNROLL];
+#pragma unroll
+            for (int u = 0; u < FUSED_UNROLL; ++u) {
+                v[u] = make_uint4(0, 0, 0, 0);
+                if (s0 + u < n_here) v[u] = ld_text16(fa.text + ((size_t)(span0 + s0 + u) * 32u + lane) * 16u);
+            }
+#pragma unroll
+            for (int u = 0; u < FUSED_UNROLL; ++u) {
+                if (s0 + u >= n_here) break;                  // warp-uniform
+                uint32_t plane[NB];
+                test_chunk(v[u], true, true, false, plane);
+                uint32_t m = 0;
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    if (lane == s0 + u) pl[j] = plane[j];
+                    m |= plane[j];
+                }
+                // stage the chunks around every flagged word, in ascending stream order = item order (warp-uniform loop)
+                while (m) {
+                    const uint32_t ch = __ffs(m) - 1;
+                    m &= m - 1;
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        if (!((plane[j] >> ch) & 1u)) continue;
+                        const uint32_t rel = lane + 1u - ch;  // lanes ch-1, ch, ch+1 hold parts 0, 1, 2 of the record
+                        if (n_arr < VER_DENSE_MAX && rel < 3u)
+                            a.stage[(size_t)(base + n_arr) * 3u + rel] = v[u];
+                        ++n_arr;
+                    }
+                }
+            }
+        }
+        // The last, partial span of the stream: complete 16-byte chunks are tested, the partial chunk at the very
+        // end is not read at all — its words are simply handed on to verification (nothing staged: they are walked).
+        if (n_full_all < a.n_spans && n_full_all >= span0 && n_full_all < span0 + 32u) {
+            const uint32_t n16 = fa.total >> 4;
+            const uint32_t c = n_full_all * 32u + lane;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (c < n16) v = ld_text16(fa.text + (size_t)c * 16u);
+            const bool tail = (fa.total & 15u) && c == n16;
+            uint32_t plane[NB];
+            test_chunk(v, c < n16, c + 1u < n16, tail, plane);
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+                if (lane == n_full_all - span0) pl[j] = plane[j];
+        }
+
+        // ---- the tile's ordered item list (what ac_collect_kernel does, warp-local)
+        const uint32_t span = span0 + lane;
+        const bool active = span < a.n_spans;
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) cnt += __popc(pl[j]);
+        flagged += cnt;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const uint32_t n_cand = __shfl_sync(0xffffffffu, incl, 31);
+        const bool dense = n_cand > a.dense_max;            // cheaper to walk the whole tile
+        const uint32_t n_act = __popc(__ballot_sync(0xffffffffu, active));
+        const uint32_t n = dense ? n_act : n_cand;
+        if (lane == 0) a.desc[tile] = make_uint2(base, n);
+        if (n == 0) continue;                                 // warp-uniform
+        if (dense) {
+            if (lane == 0) ++dense_tiles;
+            if (active) a.items[base + lane] = ITEM_SPAN | span;
+        } else if (cnt) {
+            uint32_t at = base + incl - cnt;
+            uint32_t any = 0;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) any |= pl[j];
+            while (any) {
+                const uint32_t ch = __ffs(any) - 1;
+                any &= any - 1;
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+                    if ((pl[j] >> ch) & 1u) a.items[at++] = span * WORDS_PER_SPAN + ch * NB + j;
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) flagged += __shfl_xor_sync(0xffffffffu, flagged, d);
+    if (lane == 0 && flagged) atomicAdd(&a.s.counters[3], flagged);
+    if (lane == 0 && dense_tiles) atomicAdd(&a.s.counters[4], dense_tiles);
 }
 
 // --------------------------------------------------------------- emit -----

@@ -53,7 +53,8 @@ class Info(C.Structure):
                 ("entry_bytes", C.c_uint32), ("max_pattern_len", C.c_uint32), ("final_bound", C.c_uint32),
                 ("root", C.c_uint32), ("table_bytes", C.c_uint64), ("device", C.c_int32),
                 ("finalized", C.c_int32), ("filter_word", C.c_int32), ("min_pattern_len", C.c_uint32),
-                ("filter_l1_fill", C.c_float), ("filter_l2_log2", C.c_uint32), ("reserved_", C.c_uint32)]
+                ("filter_l1_fill", C.c_float), ("filter_l2_log2", C.c_uint32), ("reserved_", C.c_uint32),
+                ("direct_keys", C.c_uint32), ("direct_walk_keys", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -61,7 +62,8 @@ class Stats(C.Structure):
                 ("chunk_bytes", C.c_uint32), ("halo_bytes", C.c_uint32), ("kernel_ms", C.c_float),
                 ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("ilp", C.c_uint32), ("filtered", C.c_uint32),
                 ("filter_ms", C.c_float), ("verify_ms", C.c_float), ("flagged_words", C.c_uint64),
-                ("dense_tiles", C.c_uint64), ("reorder_ms", C.c_float), ("expand_ms", C.c_float)]
+                ("dense_tiles", C.c_uint64), ("reorder_ms", C.c_float), ("expand_ms", C.c_float),
+                ("fused", C.c_uint32)]
 
 
 MATCH_CB = C.CFUNCTYPE(C.c_int, C.POINTER(AcMatch), C.c_void_p)
@@ -75,6 +77,7 @@ EXPORTS = [
     "acb200_set_device", "acb200_device_count", "acb200_host_alloc", "acb200_host_free",
     "acb200_set_tuning", "acb200_version", "acb200_copy_events", "acb200_tally_cb", "acb200_tally_match_cb", "acb200_set_ilp",
     "acb200_set_filter", "acb200_search_device_uniform", "acb200_set_parts", "acb200_search_hits", "acb200_pattern", "acb200_save", "acb200_load", "acb200_filter_probe",
+    "acb200_set_direct", "acb200_direct_probe",
 ]
 
 
@@ -130,6 +133,9 @@ def lib() -> C.CDLL:
     L.acb200_pattern.restype = C.POINTER(AcPattern)
     L.acb200_filter_probe.argtypes = [C.c_void_p, C.c_uint64, C.c_uint]
     L.acb200_filter_probe.restype = C.c_int
+    L.acb200_set_direct.argtypes = [C.c_void_p, C.c_int]
+    L.acb200_direct_probe.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.acb200_direct_probe.restype = C.c_int
     L.acb200_save.argtypes = [C.c_void_p, C.c_char_p]
     L.acb200_save.restype = C.c_int
     L.acb200_load.argtypes = [C.c_char_p]
@@ -225,6 +231,17 @@ class Automaton:
     def filter_probe(self, word: int, next_byte: int) -> int:
         """host-side evaluation of the prefilter decision for one aligned word (diagnostic, see acb200.h)"""
         return int(self.L.acb200_filter_probe(self.h, int(word), int(next_byte)))
+
+    def set_direct(self, mode: int) -> None:
+        """0 automatic (= 1), 1 flagged words settled by one comparison inside the walk kernel, 2 fused filter + collect
+        pass with staged windows (opt-in), -1 every flagged word is walked"""
+        self.L.acb200_set_direct(self.h, int(mode))
+
+    def direct_probe(self, text: bytes, word_index: int, hay_begin: int = 0):
+        """host-side evaluation of the direct verification of one aligned word -> (verdict, end, state)"""
+        e, s = C.c_uint32(0), C.c_uint32(0)
+        v = int(self.L.acb200_direct_probe(self.h, text, len(text), int(hay_begin), int(word_index), C.byref(e), C.byref(s)))
+        return v, int(e.value), int(s.value)
 
     def set_parts(self, parts: int) -> None:
         """parts a prefiltered scan is cut into (0 automatic)"""

@@ -35,7 +35,7 @@ def test_cfg2_planted_filtered_equals_oracle_and_full_walk():
     assert inf.filter_word == 8 and inf.min_pattern_len == 16
     ev = a.search_events(hay, off)
     st = a.stats()
-    assert st.filtered == 1 and st.kernel_launches == 5 and 0 < st.flagged_words < hay.size // 8 // 10
+    assert st.filtered == 1 and st.fused == 0 and st.kernel_launches == 5 and 0 < st.flagged_words < hay.size // 8 // 10
     assert_same(a, ev, 256, exp)
     a.set_filter(-1)
     ev_full = a.search_events(hay, off)
@@ -82,6 +82,11 @@ def test_random_dictionaries_both_word_sizes_ragged_batches(seed):
         assert_same(a, ev, len(lens), exp)
         a.set_filter(-1)
         assert np.array_equal(ev, a.search_events(flat, off)), (seed, trial)
+        if flat.size:                                   # the opt-in fused filter + collect pass with staged windows
+            a.set_filter(1)
+            a.set_direct(2)
+            assert np.array_equal(ev, a.search_events(flat, off)), (seed, trial)
+            assert a.stats().fused == 1
         a.release()
 
 
@@ -416,3 +421,62 @@ def test_randomised_mixtures_of_dense_and_sparse_regions(seed):
         a.set_filter(-1)
         assert np.array_equal(ev, a.search_events(flat, off)), (seed, trial)
         a.release()
+
+
+def test_direct_verification_equals_walking_every_flagged_word():
+    """gram_table.hpp: flagged words settled by one comparison inside ac_walk_kernel (default) vs from windows staged by
+    the fused filter + collect pass (set_direct(2), ac_filter_collect_kernel) vs every flagged word walked
+    (set_direct(-1)) vs the full automaton walk — raw events (end offset AND state id) must be identical."""
+    rng = np.random.default_rng(77)
+    pyr = random.Random(77)
+    cases = []
+    needles, hay, off = W.cfg2(n_hay=1024, hay_len=8192, planted_per_hay=8, seed=21)
+    cases.append((needles, hay, off))
+    # nested / overlapping patterns: shared grams and failure-target nodes must fall back to the walk
+    nested = [b"0123456789abcdef", b"xx0123456789abcdef", b"456789abcdefghij", b"Q0123456789abcdefZZ",
+              b"aaaaaaaaaaaaaaaa", b"aaaaaaaaaaaaaaaaaaaa", b"hello, world....", b"say hello, world....!"]
+    lens = [5, 300, 0, 16, 17, 70001, 4096, 9_000_000]
+    hays = [rand_bytes(rng, n, b"abcdefx0123456789") for n in lens]
+    for h in hays:
+        for _ in range(h.size // 500):
+            p = np.frombuffer(pyr.choice(nested), dtype=np.uint8)
+            if h.size >= p.size:
+                at = pyr.randint(0, h.size - p.size)
+                h[at:at + p.size] = p
+    hays[-1][5000:5100] = ord("a")
+    o = np.zeros(len(lens) + 1, dtype=np.uint64); o[1:] = np.cumsum(lens)
+    cases.append((nested, np.concatenate(hays), o))
+    # W = 4, binary patterns of 8..64 bytes (config-3 shape): comparisons of up to 16 chunks
+    sigs = [rand_bytes(rng, pyr.randint(8, 64), bytes(range(256))).tobytes() for _ in range(3000)]
+    big = rand_bytes(rng, 12_000_000, bytes(range(256)))
+    for i in range(4000):
+        p = np.frombuffer(sigs[i % len(sigs)], dtype=np.uint8)
+        at = pyr.randint(0, big.size - p.size)
+        big[at:at + p.size] = p
+    big[:len(sigs[0])] = np.frombuffer(sigs[0], dtype=np.uint8)
+    big[big.size - len(sigs[1]):] = np.frombuffer(sigs[1], dtype=np.uint8)
+    lens3 = [3_000_000, 1, 4_999_999, 4_000_000]
+    o3 = np.zeros(5, dtype=np.uint64); o3[1:] = np.cumsum(lens3)
+    cases.append((sigs, big, o3))
+    for pats, flat, offs in cases:
+        a = build([pats], 1)
+        inf = a.info()
+        assert inf.direct_keys > 0
+        ev = a.search_events(flat, offs)
+        st = a.stats()
+        assert st.filtered == 1 and st.fused == 0 and st.kernel_launches == 5 and len(ev) > 100
+        for mode in (2, -1):
+            a.set_direct(mode)
+            ev_walk = a.search_events(flat, offs)
+            st = a.stats()
+            assert st.filtered == 1 and st.fused == (1 if mode == 2 else 0) and st.kernel_launches == (4 if mode == 2 else 5)
+            assert np.array_equal(ev, ev_walk), mode
+        a.set_filter(-1)
+        ev_full = a.search_events(flat, offs)
+        assert a.stats().filtered == 0
+        assert np.array_equal(ev, ev_full)
+        a.release()
+    # and against the oracle on the nested case
+    pats, flat, offs = cases[1]
+    a = build([pats], 1)
+    assert_same(a, a.search_events(flat, offs), len(offs) - 1, oracle_hits([pats], split(flat, offs)))
