@@ -340,9 +340,9 @@ def main():
                     "kernel_ms": k_ms, "algorithmic_bytes_per_launch": nbytes, "per_kernel": per,
                     "note": "1 HBM byte per haystack byte over the summed duration of the step's five kernels. "
                             "ac_filter_kernel is the only one that streams the haystack (HBM-bound, per_kernel "
-                            "shows its own fraction); ac_walk_kernel walks the automaton around the ~2% of the "
-                            "words the filter flags and is latency-bound (dependent table lookups, random 24-byte "
-                            "reads) — see DESIGN.md"}
+                            "shows its own fraction); ac_walk_kernel settles the ~1.2% of the words the filter flags "
+                            "(one comparison with the only candidate pattern, else an automaton walk) and is bound by "
+                            "the random 24-byte DRAM read per flagged word — see DESIGN.md"}
     else:
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": ncu_traffic("cfg2_1GiB"), "peak_source": peak_src,
@@ -357,6 +357,7 @@ def main():
                        path="gram prefilter + verify" if filtered else "full automaton walk",
                        automaton={"states": int(inf.n_states), "classes": int(inf.n_classes),
                                   "prefilter_word": int(inf.filter_word), "prefilter_l1_fill": float(inf.filter_l1_fill),
+                                  "direct_keys": int(inf.direct_keys), "direct_walk_keys": int(inf.direct_walk_keys),
                                   "entry_bytes": int(inf.entry_bytes), "table_bytes": int(inf.table_bytes),
                                   "finalize_s": round(finalize_s, 4)},
                        events_per_step_per_gpu=int(n_events),

@@ -63,8 +63,8 @@ void Engine::release()
     cudaFree(d_out_off_); cudaFree(d_out_idx_); cudaFree(d_pat_len_); cudaFree(d_hit_sums_); cudaFree(d_hits_); cudaFree(d_hit_total_);
     d_out_off_ = nullptr; d_out_idx_ = nullptr; d_pat_len_ = nullptr; d_hit_sums_ = nullptr; d_hits_ = nullptr; d_hit_total_ = nullptr;
     hit_sums_cap_ = 0; hits_cap_ = 0;
-    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_); cudaFree(d_stage_);
-    d_stage_ = nullptr; stage_tiles_cap_ = 0;
+    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_); cudaFree(d_stage_); cudaFree(d_todo_);
+    d_stage_ = nullptr; d_todo_ = nullptr; stage_tiles_cap_ = 0;
     d_l1_ = nullptr; d_l2_ = nullptr; d_mask_ = nullptr; mask_cap_ = 0;
     d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; verify_tiles_cap_ = 0;
     if (h_counters_) cudaFreeHost(h_counters_);
@@ -326,10 +326,11 @@ bool Engine::ensure_mask(size_t words)
 bool Engine::ensure_verify_scratch(size_t n_tiles)
 {
     if (n_tiles <= verify_tiles_cap_) return true;
-    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_); cudaFree(d_stage_);
-    d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; d_stage_ = nullptr; stage_tiles_cap_ = 0; verify_tiles_cap_ = 0;
+    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_); cudaFree(d_stage_); cudaFree(d_todo_);
+    d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; d_stage_ = nullptr; d_todo_ = nullptr; stage_tiles_cap_ = 0; verify_tiles_cap_ = 0;
     const size_t cap = std::max(n_tiles + n_tiles / 4, (size_t)256);
     CU_OK(cudaMalloc(&d_items_, cap * VER_DENSE_MAX * sizeof(uint32_t)));
+    CU_OK(cudaMemset(d_items_, 0, cap * VER_DENSE_MAX * sizeof(uint32_t)));     // ac_settle_kernel loads a tile's unused slots too
     CU_OK(cudaMalloc(&d_recs_, cap * VER_DENSE_MAX * 2 * sizeof(uint32_t)));
     CU_OK(cudaMalloc(&d_desc_, cap * 2 * sizeof(uint32_t)));
     // one block: [16 counters | block sums | events per tile | offsets per tile] — the first three are zeroed by ONE memset
@@ -633,6 +634,7 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     va.gt_pat = d_gt_pat_;
     va.gt_log2 = direct ? gt_log2_ : 0u;
     va.stage = nullptr;
+    va.todo = nullptr;
     va.partial_span = (total % SPAN_BYTES) ? total / SPAN_BYTES : 0xffffffffu;
     va.items = d_items_;
     va.desc = (uint2 *)d_desc_;
@@ -667,7 +669,10 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     stats.fused = fused ? 1u : 0u;
     if (fused && stage_tiles_cap_ < verify_tiles_cap_) {
         cudaFree(d_stage_); d_stage_ = nullptr; stage_tiles_cap_ = 0;
+        cudaFree(d_todo_); d_todo_ = nullptr;
         CU_OK(cudaMalloc(&d_stage_, verify_tiles_cap_ * VER_DENSE_MAX * (size_t)STAGE_BYTES));
+        CU_OK(cudaMemset(d_stage_, 0, verify_tiles_cap_ * VER_DENSE_MAX * (size_t)STAGE_BYTES));   // unused slots are read (and ignored)
+        CU_OK(cudaMalloc(&d_todo_, verify_tiles_cap_ * VER_DENSE_MAX * sizeof(uint32_t)));
         stage_tiles_cap_ = verify_tiles_cap_;
     }
     const unsigned warps_per_cta = SCAN_THREADS / 32;
@@ -697,6 +702,10 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
             }
             CU_OK(cudaEventRecord(EV(ev_[4]), st));
             if (attempt == 0) {
+                va.todo = d_todo_;
+                const unsigned grid_s = (n_tiles + SETTLE_THREADS / 32 - 1) / (SETTLE_THREADS / 32);
+                if (W == 8) ac_settle_kernel<8><<<grid_s, SETTLE_THREADS, 0, st>>>(va);
+                else ac_settle_kernel<4><<<grid_s, SETTLE_THREADS, 0, st>>>(va);
                 if (entry_bytes_ == 2) {
                     if (W == 8) launch_walk_k<uint16_t, 8>(va, range_map_, grid_w, st);
                     else launch_walk_k<uint16_t, 4>(va, range_map_, grid_w, st);
@@ -704,7 +713,7 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
                     if (W == 8) launch_walk_k<uint32_t, 8>(va, range_map_, grid_w, st);
                     else launch_walk_k<uint32_t, 4>(va, range_map_, grid_w, st);
                 }
-                stats.kernel_launches += 2;
+                stats.kernel_launches += 3;
             }
         } else
         for (uint32_t p = 0; p < n_parts; ++p) {

@@ -110,6 +110,7 @@ private:
     uint32_t gt_log2_ = 0;
     uint32_t *d_mask_ = nullptr;  size_t mask_cap_ = 0;
     void *d_stage_ = nullptr;       // fused path: per item slot the 48 bytes around the flagged word (allocated on first use)
+    uint32_t *d_todo_ = nullptr;    // fused path: slots of the items left to ac_walk_kernel
     size_t stage_tiles_cap_ = 0;
     uint32_t *d_items_ = nullptr;   // work items of the verify kernels
     uint32_t *d_recs_ = nullptr;    // per item {first event state, count << 16 | relative end}

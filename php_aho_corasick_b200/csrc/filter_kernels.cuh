@@ -193,7 +193,9 @@ struct VerifyArgs {
     const uint32_t *gt_pat;       // its pattern store
     uint32_t gt_log2;             // 2^gt_log2 slots; 0: every flagged word is walked
     uint4 *stage;                 // fused path: per item slot the three 16-byte chunks around the flagged word (ac_filter_collect_kernel
-                                  // writes, ac_walk_kernel reads); nullptr: items are a dense list and windows come from the haystack
+                                  // writes, ac_settle_kernel reads)
+    uint32_t *todo;               // fused path: slots of the items ac_settle_kernel left to ac_walk_kernel (count in
+                                  // counters[counter_slot]); nullptr: ac_walk_kernel takes the dense list of ac_collect_kernel
     uint32_t partial_span;        // index of the stream's last, partial span (never staged) or 0xffffffff
     uint32_t *items;              // work items, tile runs in completion order (capacity n_tiles * VER_DENSE_MAX)
     uint2 *desc;                  // per tile {offset into items, count}
@@ -484,20 +486,6 @@ __device__ __forceinline__ bool verify_word_direct(const VerifyArgs &a, uint32_t
 
 constexpr uint32_t STAGE_BYTES = 48;       // per work item: the three 16-byte chunks around the flagged word
 
-// window of the flagged word `item` inside its 48-byte stage record: [rs - 2W, rs + W) starts at this byte
-template <int W>
-__device__ __forceinline__ uint32_t stage_window_offset(uint32_t item) { return 16u + W * (item % (16u / W)) - W; }
-
-// Is the record complete?  The neighbours of a span's first / last word sit in another warp-load, and the partial
-// span at the end of the stream is not staged at all.
-template <int W>
-__device__ __forceinline__ bool stage_complete(uint32_t item, uint32_t partial_span)
-{
-    constexpr uint32_t NB = 16u / W;
-    const uint32_t in_span = item % (32u * NB);
-    return in_span != 0u && in_span != 32u * NB - 1u && item / (32u * NB) != partial_span;
-}
-
 // origin of an item's end offsets: a record stores its first event's end relative to this
 template <int W>
 __device__ __forceinline__ uint32_t item_origin(uint32_t item)
@@ -526,8 +514,8 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
     st.ncls = a.s.ncls; st.lo = a.s.range_lo; st.n_used = a.s.n_used;
     st.final_bound = a.s.final_bound; st.root = a.s.root;
 
-    // fused path: item slots (VER_DENSE_MAX per tile, the first desc[tile].y in use); else the dense list ac_collect_kernel made
-    const uint32_t n_items = a.stage ? a.n_tiles * VER_DENSE_MAX : a.s.counters[a.counter_slot];
+    // the dense list ac_collect_kernel made, or (fused path) the todo list of ac_settle_kernel
+    const uint32_t n_items = a.s.counters[a.counter_slot];
     const uint32_t n_threads = gridDim.x * WALK_THREADS;
     constexpr int K = WALK_ILP;
     // a thread takes K consecutive items and walks them in lockstep
@@ -539,7 +527,7 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
         for (int k = 0; k < K; ++k) {
             slot[k] = a.item_base + i0 + k;
             valid[k] = i0 + k < n_items;
-            if (a.stage && valid[k]) valid[k] = (slot[k] % VER_DENSE_MAX) < a.desc[slot[k] / VER_DENSE_MAX].y;
+            if (a.todo && valid[k]) slot[k] = a.todo[i0 + k];
             item[k] = valid[k] ? a.items[slot[k]] : ITEM_NONE;
             rs[k] = 0; w0[k] = 0; lock[k] = false;
             if (item[k] != ITEM_NONE && !(item[k] & ITEM_SPAN)) {
@@ -559,20 +547,8 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
         bool all_direct = a.gt_log2 != 0;
         if (all_direct) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                if (!(all_direct && lock[k])) { all_direct = false; break; }
-                if (a.stage && stage_complete<W>(item[k], a.partial_span)) {
-                    // the window [rs - 2W, rs + W) was copied next to the item while the filter had it in registers
-                    const uint8_t *rec = reinterpret_cast<const uint8_t *>(a.stage) + (size_t)slot[k] * STAGE_BYTES + stage_window_offset<W>(item[k]);
-                    const uint2 g0 = ld_group<W>(rec, 0), g1 = ld_group<W>(rec, W), g2 = ld_group<W>(rec, 2 * W);
-                    const uint8_t *text = a.s.text;
-                    const uint32_t r = rs[k];
-                    all_direct = verify_word_direct<W>(a, r, w0[k], [=](uint32_t i) {
-                        return group_chunk<W>((i == r) ? g2 : (i == r - W) ? g1 : (i == r - 2u * W) ? g0 : ld_group<W>(text, i)); }, ev[k]);
-                } else {
-                    all_direct = verify_word_direct<W>(a, rs[k], w0[k], ev[k]);
-                }
-            }
+            for (int k = 0; k < K; ++k)
+                all_direct = all_direct && lock[k] && verify_word_direct<W>(a, rs[k], w0[k], ev[k]);
         }
         if (all_direct) {
         } else if (all_lock) {
@@ -794,6 +770,81 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_collect_kernel(cons
     for (int d = 16; d > 0; d >>= 1) flagged += __shfl_xor_sync(0xffffffffu, flagged, d);
     if (lane == 0 && flagged) atomicAdd(&a.s.counters[3], flagged);
     if (lane == 0 && dense_tiles) atomicAdd(&a.s.counters[4], dense_tiles);
+}
+
+// Fused path, second kernel: one warp per tile settles the tile's items from their staged windows — one probe of
+// the gram table and one comparison each (gram_table.hpp), no haystack access for patterns of up to 2W bytes.
+// Every load whose address depends only on (tile, lane) is issued before anything is looked at, so a tile costs
+// two dependent memory round trips.  Items that need the automaton (shared grams, failure-target patterns,
+// windows clipped by the ends of the stream or straddling a haystack end, spans of densely flagged tiles) are
+// appended to `todo` for ac_walk_kernel.  Writes the records, the events per tile and per block of tiles.
+constexpr int SETTLE_THREADS = 256;
+
+template <int W>
+__global__ void __launch_bounds__(SETTLE_THREADS) ac_settle_kernel(const __grid_constant__ VerifyArgs a)
+{
+    constexpr uint32_t NB = 16u / W;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t tile = blockIdx.x * (SETTLE_THREADS / 32) + (threadIdx.x >> 5);
+    if (tile >= a.n_tiles) return;
+    const uint2 d = __ldg(a.desc + tile);                     // {tile * VER_DENSE_MAX, items}
+    uint32_t tile_events = 0;
+    for (uint32_t i0 = 0; i0 < VER_DENSE_MAX; i0 += 32u) {    // the second half is rare
+        if (i0 && i0 >= d.y) break;                           // warp-uniform
+        const uint32_t slot = tile * VER_DENSE_MAX + i0 + lane;
+        const uint32_t item = __ldg(a.items + slot);
+        // bytes [8, 40) of the 48-byte record hold the window [rs - 2W, rs + W) of every word of the middle chunk
+        const uint2 *rec = reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(a.stage) + (size_t)slot * STAGE_BYTES + 8u);
+        const uint2 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), r3 = __ldg(rec + 3);
+        const bool have = i0 + lane < d.y;
+        bool undecided = false;
+        ItemEvents ev{0u, 0u, 0u};
+        if (have) {
+            undecided = true;
+            const uint32_t rs = (item + 1u) * W;             // the W end offsets owned by the word are rs+1 .. rs+W
+            if (!(item & ITEM_SPAN) && a.gt_log2 && rs >= a.warm && rs + W <= a.s.total && item / (32u * NB) != a.partial_span) {
+                const uint32_t h = find_haystack(a.s, rs);
+                if (hay_end(a.s, h) >= rs + W) {             // a window clipped by the haystack START is fine: the candidate must fit
+                    uint2 g0, g1, g2;
+                    const uint32_t j = item % NB;
+                    if (W == 8) {
+                        g0 = j ? r1 : r0; g1 = j ? r2 : r1; g2 = j ? r3 : r2;
+                    } else {                                  // 32-bit groups at record bytes 12 + 4j, 16 + 4j, 20 + 4j
+                        const uint32_t w[6] = {r0.y, r1.x, r1.y, r2.x, r2.y, r3.x};
+                        g0 = make_uint2(j == 0 ? w[0] : j == 1 ? w[1] : j == 2 ? w[2] : w[3], 0u);
+                        g1 = make_uint2(j == 0 ? w[1] : j == 1 ? w[2] : j == 2 ? w[3] : w[4], 0u);
+                        g2 = make_uint2(j == 0 ? w[2] : j == 1 ? w[3] : j == 2 ? w[4] : w[5], 0u);
+                    }
+                    // the neighbours of a span's first / last word were not in the filter's registers: from the haystack
+                    const uint32_t in_span = item % (32u * NB);
+                    const uint8_t *text = a.s.text;
+                    if (in_span == 0u) g0 = ld_group<W>(text, rs - 2u * W);
+                    if (in_span == 32u * NB - 1u) g2 = ld_group<W>(text, rs);
+                    undecided = !verify_word_direct<W>(a, rs, hay_begin(a.s, h), [=](uint32_t i) {
+                        return group_chunk<W>((i == rs) ? g2 : (i == rs - W) ? g1 : (i == rs - 2u * W) ? g0 : ld_group<W>(text, i)); }, ev);
+                }
+            }
+            if (!undecided) {
+                const uint32_t rel = ev.cnt ? ev.e0p - rs : 0u;
+                a.recs[slot] = make_uint2(ev.e0s, (ev.cnt << 16) | (rel & 0xffffu));
+            }
+        }
+        const uint32_t um = __ballot_sync(0xffffffffu, undecided);
+        if (um) {
+            uint32_t t0 = 0;
+            if (lane == 0) t0 = atomicAdd(&a.s.counters[a.counter_slot], (uint32_t)__popc(um));
+            t0 = __shfl_sync(0xffffffffu, t0, 0);
+            if (undecided) a.todo[t0 + __popc(um & ((1u << lane) - 1u))] = slot;
+        }
+        uint32_t sum = ev.cnt;
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, k);
+        tile_events += sum;
+    }
+    if (tile_events && lane == 0) {
+        a.tile_len[tile] = tile_events;                       // ac_walk_kernel adds the events of the todo items
+        atomicAdd(&a.block_sum[tile / EMIT_THREADS], tile_events);
+    }
 }
 
 // --------------------------------------------------------------- emit -----

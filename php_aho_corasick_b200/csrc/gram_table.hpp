@@ -72,54 +72,64 @@ template <int W, typename LT, typename LS, typename LP, typename LST>
 ACB_HD GramVerdict gram_verify(uint32_t rs, uint32_t warm, uint32_t hay_begin, uint32_t log2_slots, LT load_text, LS load_slot,
                                LP load_pat, LST load_state, uint32_t *end, uint32_t *state)
 {
+    // Written for SIMT execution: one probe loop, then straight-line code with a single exit — lanes of a warp that
+    // reach different verdicts stay converged (early returns fragment the warp and multiply the instruction count).
     typedef typename GramChunk<W>::type chunk_t;
     constexpr uint32_t WORDS = W / 4;
+    constexpr uint32_t TAIL_CHUNKS = 16 / W;
     const chunk_t word = load_text(rs - W);
-    chunk_t hi_grp = load_text(rs);
+    const chunk_t next = load_text(rs);
     const chunk_t prev = load_text(rs - 2u * W);      // always inside the warm-up: every pattern is at least 2W long
     const uint32_t lo = (uint32_t)word, hi = (W == 8) ? (uint32_t)((uint64_t)word >> 32) : 0u;
-    const uint32_t nb = (uint32_t)hi_grp & 0xffu;
+    const uint32_t nb = (uint32_t)next & 0xffu;
     const uint32_t mask = (1u << log2_slots) - 1u;
     uint32_t i = gram_home(lo, hi, nb, log2_slots);
-    GramSlot s;
-    while (true) {
-        s = load_slot(i);
-        if (!(s.meta & GRAM_USED)) return GRAM_NOTHING;                  // no pattern owns this gram
-        if (s.key_lo == lo && s.key_hi == hi && gram_meta_next(s.meta) == nb) break;
+    GramSlot s = load_slot(i);
+    while ((s.meta & GRAM_USED) && !(s.key_lo == lo && s.key_hi == hi && gram_meta_next(s.meta) == nb)) {
         i = (i + 1u) & mask;
+        s = load_slot(i);
     }
-    if (s.meta & GRAM_WALK) return GRAM_NEEDS_WALK;
-    const uint32_t r = gram_meta_r(s.meta), len = gram_meta_len(s.meta);
-    if (rs + r < hay_begin + len) return GRAM_NOTHING;                   // the only candidate starts before its haystack
-    const uint32_t n_chunks = (len + W - 1) / W;
-    constexpr uint32_t TAIL_CHUNKS = 16 / W;
+    const bool found = (s.meta & GRAM_USED) != 0;                        // else: no pattern owns this gram
+    const bool walk = found && (s.meta & GRAM_WALK) != 0;
+    const uint32_t r = found ? gram_meta_r(s.meta) : (uint32_t)W, len = gram_meta_len(s.meta);
+    // a candidate that starts before its haystack is no occurrence
+    bool ok = found && !walk && rs + r >= hay_begin + len;
     // chunk j (from the end) of the candidate = haystack bytes [rs + r - W(j+1), rs + r - Wj): the top W-r bytes of
-    // the group at b = rs - W(j+1) and the low r bytes of the group after it
-    chunk_t lo_grp = word;
-    for (uint32_t j = 0; j < n_chunks; ++j) {
-        if (j) {
+    // the group at rs - W(j+1) and the low r bytes of the group after it.  Chunks 0 and 1 always exist and are full.
+    const uint32_t sh = 8u * (r & (uint32_t)(W - 1)), back_sh = 8u * ((uint32_t)W - (r & (uint32_t)(W - 1))) & (8u * W - 1u);
+    const chunk_t have0 = (r == (uint32_t)W) ? next : (chunk_t)((word >> sh) | (next << back_sh));
+    const chunk_t have1 = (r == (uint32_t)W) ? word : (chunk_t)((prev >> sh) | (word << back_sh));
+    chunk_t want0, want1;
+    if (W == 8) {
+        want0 = (chunk_t)(((uint64_t)s.tail[3] << 32) | s.tail[2]);
+        want1 = (chunk_t)(((uint64_t)s.tail[1] << 32) | s.tail[0]);
+    } else {
+        want0 = (chunk_t)s.tail[3];
+        want1 = (chunk_t)s.tail[2];
+    }
+    ok = ok && have0 == want0 && have1 == want1;
+    const uint32_t n_chunks = (len + W - 1) / W;
+    if (ok && n_chunks > 2u) {                                           // patterns longer than 2W: the rest, chunk by chunk
+        chunk_t hi_grp = prev, lo_grp = prev;
+        for (uint32_t j = 2; ok && j < n_chunks; ++j) {
             hi_grp = lo_grp;
             const uint32_t back = W * (j + 1u);
-            // bytes before the warm-up are never part of the candidate
-            lo_grp = (j == 1u) ? prev : (back <= warm) ? load_text(rs - back) : (chunk_t)0;
+            lo_grp = (back <= warm) ? load_text(rs - back) : (chunk_t)0; // bytes before the warm-up are never part of the candidate
+            chunk_t have = (r == (uint32_t)W) ? hi_grp : (chunk_t)((lo_grp >> sh) | (hi_grp << back_sh));
+            if (j == n_chunks - 1u) {
+                const uint32_t valid = len - W * j;                      // bytes of the pattern in its first chunk
+                if (valid < (uint32_t)W) have &= ~(chunk_t)0 << (8u * (W - valid));
+            }
+            chunk_t want;
+            if (j < TAIL_CHUNKS) want = (chunk_t)((j == 2u) ? s.tail[1] : s.tail[0]);       // W = 4 only
+            else want = load_pat(s.ref - WORDS * (j + 1u));
+            ok = have == want;
         }
-        chunk_t have = (r == (uint32_t)W) ? hi_grp : (chunk_t)((lo_grp >> (8u * r)) | (hi_grp << (8u * (W - r))));
-        if (j == n_chunks - 1u) {
-            const uint32_t valid = len - W * j;                          // bytes of the pattern in its first chunk
-            if (valid < (uint32_t)W) have &= ~(chunk_t)0 << (8u * (W - valid));
-        }
-        chunk_t want;
-        if (j < TAIL_CHUNKS) {                                            // chunk j from the end of the 16-byte tail
-            if (W == 8) want = (j == 0u) ? (chunk_t)(((uint64_t)s.tail[3] << 32) | s.tail[2]) : (chunk_t)(((uint64_t)s.tail[1] << 32) | s.tail[0]);
-            else want = (chunk_t)((j == 0u) ? s.tail[3] : (j == 1u) ? s.tail[2] : (j == 2u) ? s.tail[1] : s.tail[0]);
-        } else {
-            want = load_pat(s.ref - WORDS * (j + 1u));
-        }
-        if (have != want) return GRAM_NOTHING;
     }
     *end = rs + r;
-    *state = (s.meta & GRAM_INLINE) ? s.ref : load_state(s.ref);
-    return GRAM_EVENT;
+    *state = 0;
+    if (ok) *state = (s.meta & GRAM_INLINE) ? s.ref : load_state(s.ref);
+    return walk ? GRAM_NEEDS_WALK : ok ? GRAM_EVENT : GRAM_NOTHING;
 }
 
 } // namespace acb200

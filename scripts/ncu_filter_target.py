@@ -12,6 +12,7 @@ planted = int(sys.argv[4]) if len(sys.argv) > 4 else 8
 needles, hay, off = W.cfg2(n_hay=256, hay_len=8192, planted_per_hay=planted)
 a = Automaton(0); a.add_php_order(needles); a.finalize(); a.set_filter(mode)
 if len(sys.argv) > 5: a.set_parts(int(sys.argv[5]))
+if len(sys.argv) > 6: a.set_direct(int(sys.argv[6]))
 k = (mib << 20) // hay.size
 big = torch.from_numpy(hay).to("cuda:0").repeat(k)
 boff = W.offsets_uniform(k * 256, 8192)

@@ -469,7 +469,7 @@ def test_direct_verification_equals_walking_every_flagged_word():
             a.set_direct(mode)
             ev_walk = a.search_events(flat, offs)
             st = a.stats()
-            assert st.filtered == 1 and st.fused == (1 if mode == 2 else 0) and st.kernel_launches == (4 if mode == 2 else 5)
+            assert st.filtered == 1 and st.fused == (1 if mode == 2 else 0) and st.kernel_launches == 5
             assert np.array_equal(ev, ev_walk), mode
         a.set_filter(-1)
         ev_full = a.search_events(flat, offs)
