@@ -363,7 +363,12 @@ void build_gram_table(FlatAutomaton &flat) {
         if (flat.accepted[pi].ptext.length == depth[s]) pat_state[pi] = s;
     }
 
-    // pattern store
+    // pattern store (indexed with 32 bits)
+    {
+        uint64_t words = 0;
+        for (const AC_PATTERN_t &p : flat.accepted) words += (p.ptext.length + W - 1) / W * W / 4 + 2;
+        if (words >= 0x7fffffffull) return;
+    }
     std::vector<uint32_t> pat_ref(np, 0);
     for (size_t pi = 0; pi < np; ++pi) {
         const size_t len = flat.accepted[pi].ptext.length;

@@ -894,18 +894,32 @@ __global__ void __launch_bounds__(COUNT_THREADS) ac_emit_kernel(const __grid_con
     const uint32_t s_cls_addr = (uint32_t)__cvta_generic_to_shared(s_cls);
     const uint32_t n_warps = gridDim.x * (COUNT_THREADS / 32);
 
-    for (uint32_t tile = blockIdx.x * (COUNT_THREADS / 32) + (threadIdx.x >> 5); tile < a.n_tiles; tile += n_warps) {
-        if (a.tile_len[tile] == 0) continue;                          // warp-uniform: nothing ends in this tile
-        const uint2 d = a.desc[tile];
-        uint32_t off = a.tile_off[tile];
-        for (uint32_t i0 = 0; i0 < d.y; i0 += 32u) {                 // warp-uniform
+    // The kernel is a chain of dependent loads per tile (events of the tile -> descriptor + offset -> records -> items).
+    // A warp looks two tiles ahead for the event count and one tile ahead for descriptor + offset (only where the
+    // count says something ends there), and fetches the records and items of a round together.
+    auto load_len = [&](uint32_t t) -> uint32_t { return (t < a.n_tiles) ? a.tile_len[t] : 0u; };
+    auto load_header = [&](uint32_t t, uint32_t len, uint2 &d, uint32_t &off) {
+        d = make_uint2(0u, 0u); off = 0;
+        if (len) { d = a.desc[t]; off = a.tile_off[t]; }
+    };
+    uint32_t tile = blockIdx.x * (COUNT_THREADS / 32) + (threadIdx.x >> 5);
+    uint32_t len = load_len(tile), next_len = load_len(tile + n_warps), off;
+    uint2 d;
+    load_header(tile, len, d, off);
+    for (; tile < a.n_tiles; tile += n_warps) {
+        const uint32_t next2_len = load_len(tile + 2u * n_warps);
+        uint32_t next_off;
+        uint2 next_d;
+        load_header(tile + n_warps, next_len, next_d, next_off);
+        const uint32_t n_items = len ? d.y : 0u;                      // warp-uniform; 0: nothing ends in this tile
+        for (uint32_t i0 = 0; i0 < n_items; i0 += 32u) {             // warp-uniform
             const uint32_t i = i0 + lane;
             uint32_t item = ITEM_NONE, cnt = 0;
             uint2 rec = make_uint2(0u, 0u);
-            if (i < d.y) {
+            if (i < n_items) {
                 rec = a.recs[d.x + i];
+                item = a.items[d.x + i];
                 cnt = rec.y >> 16;
-                if (cnt) item = a.items[d.x + i];
             }
             if (!__any_sync(0xffffffffu, cnt != 0)) continue;
             uint32_t pincl = cnt;
@@ -928,6 +942,7 @@ __global__ void __launch_bounds__(COUNT_THREADS) ac_emit_kernel(const __grid_con
             }
             off += __shfl_sync(0xffffffffu, pincl, 31);
         }
+        len = next_len; d = next_d; off = next_off; next_len = next2_len;
     }
 }
 
