@@ -34,6 +34,34 @@ def test_blob_round_trip_on_the_host(tmp_path):
     assert b.add(b"zzz") == 4                       # a loaded automaton is closed (ACERR_TRIE_CLOSED)
 
 
+def test_loaded_blob_rebuilds_the_gram_table(tmp_path):
+    """The exact gram table (direct verification of flagged words) is derived from the flat description: a loaded
+    automaton must have the same table — same verdict, end and state for every word of a text."""
+    import random
+    rng = random.Random(11)
+    pats = [bytes(rng.choice(b"abcdef") for _ in range(rng.choice([16, 17, 24, 40]))) for _ in range(200)]
+    pats += [b"x" + pats[0], pats[1][4:] + b"yyyy"]            # a failure-target pattern and an overlapping one
+    a = Automaton()
+    a.add_php_order(pats)
+    _finalize_anyhow(a)
+    path = str(tmp_path / "grams.acb")
+    a.save(path)
+    b = Automaton.load(path, require_device=False)
+    ia, ib = a.info(), b.info()
+    assert ia.direct_keys > 0 and (ia.direct_keys, ia.direct_walk_keys, ia.filter_word) == (ib.direct_keys, ib.direct_walk_keys, ib.filter_word)
+    text = bytearray(rng.choice(b"abcdef") for _ in range(4000))
+    for i in range(60):
+        p = pats[rng.randrange(len(pats))]
+        at = rng.randint(0, len(text) - len(p))
+        text[at:at + len(p)] = p
+    for at in (100, 1003, 2501):                               # the failure-target pattern: its words must be "undecided"
+        text[at:at + len(pats[0])] = pats[0]
+    text = bytes(text)
+    verdicts = [a.direct_probe(text, k) for k in range(len(text) // 8)]
+    assert verdicts == [b.direct_probe(text, k) for k in range(len(text) // 8)]
+    assert sum(1 for v in verdicts if v[0] == 1) >= 20 and any(v[0] == 2 for v in verdicts)
+
+
 def test_blob_rejects_garbage_and_unfinalized(tmp_path):
     a = Automaton()
     a.add(b"abc")
