@@ -194,6 +194,19 @@ int acb200_search_device_uniform(AC_TRIE_t *thiz, const void *d_bytes, size_t n,
                                  size_t hay_len, int first_only, void *stream,
                                  const void **d_events, size_t *n_events);
 
+/* Asynchronous variant for callers that chain more device work behind the scan on `stream` (the multi-GPU event
+ * gather sends the rows on without a host round trip): returns after the kernels are enqueued, waits for nothing.
+ * `d_rows` is a DEVICE buffer of 1 + max_events 8-byte rows: row 0 receives {uint32 event count, uint32 densely
+ * flagged tiles}, rows 1.. the first max_events packed events in ascending order (a count above max_events means
+ * the caller has to repeat the call with more rows).  Only the prefilter path supports this: -1 (and an error
+ * text) if the dictionary, the batch size or the automatic density rule would choose the full walk — use the
+ * synchronous call then.  `stream` = NULL means the legacy default stream here (the kernels must be ordered with
+ * the caller's work, so the library's private stream is never used).  After the caller has waited for `stream`, acb200_async_finish(count) completes the
+ * statistics of acb200_last_stats(); the library's own event buffer is not touched.                      */
+int acb200_search_device_uniform_async(AC_TRIE_t *thiz, const void *d_bytes, size_t n, size_t hay_len,
+                                       void *d_rows, size_t max_events, void *stream);
+int acb200_async_finish(AC_TRIE_t *thiz, size_t n_events);
+
 /* One reported pattern occurrence, as the reference's callback would have recorded it
  * (src/php_ahocorasick.c:555-584): haystack index, exclusive end offset inside the haystack
  * ("pos"), start offset ("start_postion" = pos - length) and the pattern's index in acceptance

@@ -314,6 +314,21 @@ int acb200_search_device_uniform(AC_TRIE_t *t, const void *d_bytes, size_t n, si
     return 0;
 }
 
+int acb200_search_device_uniform_async(AC_TRIE_t *t, const void *d_bytes, size_t n, size_t hay_len, void *d_rows,
+                                       size_t max_events, void *stream)
+{
+    if (t->open) { set_error("automaton is not finalized"); return -1; }
+    if (!t->device_ok) return -1;
+    return t->engine.scan_device_uniform_async(d_bytes, n, hay_len, d_rows, max_events, stream) ? 0 : -1;
+}
+
+int acb200_async_finish(AC_TRIE_t *t, size_t n_events)
+{
+    if (t->open || !t->device_ok) return -1;
+    t->engine.async_finish(n_events);
+    return 0;
+}
+
 long acb200_copy_events(AC_TRIE_t *t, void *d_dst, size_t max_events, void *stream)
 {
     if (t->open || !t->device_ok) { set_error("automaton is not finalized"); return -1; }

@@ -431,6 +431,7 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
         last_dense_frac_ *= 0.5;      // re-probe the prefilter now and then
     }
 
+    if (async_rows_) { set_error("asynchronous search needs the prefilter path (dictionary, batch size or density rule it out)"); return false; }
     const uint32_t chunk = pick_chunk(total);
     const uint32_t n_chunks = (uint32_t)(((uint64_t)total + chunk - 1) / chunk);
     stats.chunk_bytes = chunk;
@@ -684,9 +685,14 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     const unsigned grid_e = (n_tiles + EMIT_THREADS - 1) / EMIT_THREADS;
     const unsigned grid_n = std::min<uint32_t>((n_tiles + COUNT_THREADS / 32 - 1) / (COUNT_THREADS / 32), (uint32_t)n_sms_ * 8u);
 
+    const bool async = async_rows_ != nullptr;
     for (int attempt = 0; attempt < 2; ++attempt) {
         a.out = (uint2 *)d_events_;
         a.capacity = (uint32_t)std::min<size_t>(events_cap_, 0xffffffffu);
+        if (async) {                 // events go straight into the caller's rows; what does not fit is counted, not written
+            a.out = (uint2 *)async_rows_ + 1;
+            a.capacity = (uint32_t)std::min<size_t>(async_cap_, 0xffffffffu);
+        }
         // counters, block sums and events per tile (the walk kernel adds to both) are adjacent: one memset
         if (!fused || attempt == 0)
             CU_OK(cudaMemsetAsync(vcounters, 0, (size_t)((vtile_len - vcounters) + n_tiles) * sizeof(uint32_t), st));
@@ -767,6 +773,14 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
         CU_OK(cudaGetLastError());
         CU_OK(cudaEventRecord(EV(ev_[1]), st));
         stats.kernel_launches += 2;
+        if (async) {
+            // row 0 = {event count, dense tiles}; the caller waits (after its own work on the stream) and calls async_finish()
+            CU_OK(cudaMemcpyAsync(async_rows_, vcounters + 1, 4, cudaMemcpyDeviceToDevice, st));
+            CU_OK(cudaMemcpyAsync((uint32_t *)async_rows_ + 1, vcounters + 4, 4, cudaMemcpyDeviceToDevice, st));
+            async_pending_ = true;
+            async_tiles_ = n_tiles;
+            return true;
+        }
         CU_OK(cudaMemcpyAsync(h_counters_, vcounters, 32, cudaMemcpyDeviceToHost, st));
         CU_OK(cudaStreamSynchronize(st));
         float ms_f = 0, ms_v = 0, ms_r = 0;
@@ -878,6 +892,43 @@ bool Engine::scan_device_uniform(const void *d_bytes, size_t n, size_t hay_len, 
     stats.h2d_ms = 0; stats.d2h_ms = 0;
     const uint32_t uniform_len = (n <= 1 || total == 0) ? (uint32_t)std::max<uint64_t>(total, 1) : (uint32_t)hay_len;
     return launch_scan(d_bytes, (uint32_t)total, (uint32_t)total, std::max<size_t>(n, 1), uniform_len, first_only, ROOT_STATE, stream);
+}
+
+bool Engine::scan_device_uniform_async(const void *d_bytes, size_t n, size_t hay_len, void *d_rows, size_t max_events, void *stream)
+{
+    if (device_ < 0) { set_error("automaton has no device table (finalize failed?)"); return false; }
+    CU_OK(cudaSetDevice(device_));
+    const uint64_t total = (uint64_t)n * hay_len;
+    if (total == 0 || total >= 0xffffff00ull) { set_error("asynchronous search: empty batch or stream beyond 4 GiB"); return false; }
+    if (((uintptr_t)d_bytes & 15u) != 0 || ((uintptr_t)d_rows & 7u) != 0) { set_error("device pointers must be 16-byte (haystack) / 8-byte (rows) aligned"); return false; }
+    stats.h2d_ms = 0; stats.d2h_ms = 0;
+    const uint32_t uniform_len = (n <= 1) ? (uint32_t)total : (uint32_t)hay_len;
+    async_rows_ = d_rows; async_cap_ = max_events; async_pending_ = false;
+    // The point of this call is ordering with the caller's later work on ITS stream: a NULL handle here means the
+    // legacy default stream itself (the synchronous calls read NULL as "the library's own stream").
+    if (!stream) stream = (void *)cudaStreamLegacy;
+    const bool ok = launch_scan(d_bytes, (uint32_t)total, (uint32_t)total, std::max<size_t>(n, 1), uniform_len, false, ROOT_STATE, stream);
+    async_rows_ = nullptr; async_cap_ = 0;
+    return ok && async_pending_;
+}
+
+// The caller has waited for the stream: times from the recorded events, counts from what it read in row 0.
+void Engine::async_finish(size_t n_events)
+{
+    if (!async_pending_) return;
+    async_pending_ = false;
+    cudaSetDevice(device_);
+    float ms_f = 0, ms_v = 0, ms_r = 0;
+    if (cudaEventElapsedTime(&ms_f, EV(ev_[0]), EV(ev_[4])) != cudaSuccess) ms_f = 0;
+    if (cudaEventElapsedTime(&ms_v, EV(ev_[4]), EV(ev_[5])) != cudaSuccess) ms_v = 0;
+    if (cudaEventElapsedTime(&ms_r, EV(ev_[5]), EV(ev_[1])) != cudaSuccess) ms_r = 0;
+    cudaGetLastError();
+    stats.filter_ms = ms_f; stats.verify_ms = ms_v; stats.reorder_ms = ms_r;
+    stats.kernel_ms = ms_f + ms_v + ms_r;
+    stats.events = n_events;
+    n_events_ = 0;                           // the events live in the caller's rows, not in the library's buffer
+    last_density_ = stats.bytes ? (double)n_events / (double)stats.bytes : 0.0;
+    stats.ilp = 1;
 }
 
 bool Engine::slab_upload_async(int buf, const char *bytes, size_t n_bytes)

@@ -45,6 +45,12 @@ public:
     // n haystacks of equal length laid end to end
     bool scan_device_uniform(const void *d_bytes, size_t n, size_t hay_len, bool first_only, void *stream);
 
+    // Asynchronous variant of scan_device_uniform for callers that chain more device work behind the scan (the
+    // multi-GPU event gather): nothing is waited for.  Row 0 of d_rows (8-byte rows) receives the event count,
+    // rows 1 .. max_events the first max_events events.  Only the prefilter path can do this (false + error
+    // otherwise: use the synchronous call); async_finish() completes the bookkeeping once the caller has waited.
+    bool scan_device_uniform_async(const void *d_bytes, size_t n, size_t hay_len, void *d_rows, size_t max_events, void *stream);
+    void async_finish(size_t n_events);
     bool copy_events_to(void *d_dst, size_t n, void *stream);
     // Expands the events of the most recent scan_host() into hits on the device and copies up to `cap` of them
     // to `hits` (host).  *n_hits receives the total.
@@ -136,6 +142,10 @@ private:
     void *ev_slab_[4] = {nullptr, nullptr, nullptr, nullptr};     // per buffer: upload started / finished
     std::vector<uint32_t> off32_;
 
+    void *async_rows_ = nullptr;   // set while scan_device_uniform_async runs launch_scan
+    size_t async_cap_ = 0;
+    bool async_pending_ = false;
+    uint32_t async_tiles_ = 0;
     double last_density_ = 0.0;    // events per byte of the previous scan (kernel choice)
     size_t n_events_ = 0;
     uint32_t end_state_ = 0;

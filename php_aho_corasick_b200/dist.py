@@ -56,6 +56,25 @@ class EventGatherer:
     def _rows_for(max_count):
         return max(1023, (max_count + max_count // 8 + 4095) // 4096 * 4096 - 1)
 
+    def exchange(self, rows: int, world: int):
+        """all_gather of the first rows + 1 rows of the send buffer (row 0 = this rank's count, already in place);
+        -> every rank's count (one host wait); agrees on the rows of the next call."""
+        out = self.recv[: world * (rows + 1)]
+        try:
+            dist.all_gather_into_tensor(out, self.send[: rows + 1], group=self.group)
+        except (RuntimeError, NotImplementedError, AttributeError):
+            dist.all_gather([out[r * (rows + 1):(r + 1) * (rows + 1)] for r in range(world)], self.send[: rows + 1],
+                            group=self.group)
+        sizes = [int(x) & 0xFFFFFFFF for x in out.view(world, rows + 1, 2)[:, 0, 0].cpu().tolist()]
+        self.rows = self._rows_for(max(sizes))
+        return sizes
+
+    def views(self, rows: int, world: int, sizes, dst: int):
+        if dist.get_rank(self.group) != dst:
+            return None
+        got = self.recv[: world * (rows + 1)].view(world, rows + 1, 2)
+        return [got[r, 1:1 + sizes[r]] for r in range(world)]
+
     def gather(self, local, dst: int = 0, n: int | None = None, fill=None, like: torch.Tensor | None = None):
         """local: [n, 2] tensor of this rank's events — or, to save a device copy, `n` plus `fill(rows)`, a callable
         that writes the first len(rows) events into the given rows of the send buffer (`like` gives device/dtype)."""
@@ -138,6 +157,7 @@ class ShardedMatcher:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._ev = None
         self._gatherer = None
+        self._like = None
 
     def scan_local_device(self, dev_tensor: torch.Tensor, local_offsets, first_only=False, stream=0, uniform_len=0):
         """Scans this rank's shard (uint8 CUDA tensor, haystacks end to end). -> int32 CUDA tensor [n,2]"""
@@ -154,13 +174,34 @@ class ShardedMatcher:
 
     def scan_and_gather(self, dev_tensor: torch.Tensor, local_offsets, dst: int = 0, stream=0, uniform_len=0):
         """Scans this rank's shard and gathers every rank's packed events on `dst` (list in rank order, views valid
-        until the next call; None elsewhere).  The events go from the library's buffer straight into the send buffer."""
+        until the next call; None elsewhere).  The events go from the library's buffer straight into the send buffer.
+
+        Equal-length batches after the first call take the chained form: the library enqueues its kernels with the
+        send buffer as their output (row 0 = the count) and returns at once, the all_gather is enqueued behind them,
+        and the one host wait of the step is the read of the gathered counts — no host round trip between scan and
+        collective.  If a rank's events outgrow the agreed rows, every rank sees it in the counts and repeats."""
+        if self._gatherer is None:
+            self._gatherer = EventGatherer(self.group)
+        g = self._gatherer
+        if uniform_len and g.rows and dev_tensor.is_cuda:
+            n_hay = len(local_offsets) - 1
+            while True:
+                rows = g.rows
+                if self._like is None:
+                    self._like = torch.empty((0, 2), dtype=torch.int32, device=dev_tensor.device)
+                g._ensure(rows, self.world, self._like)
+                if not self.aut.search_device_uniform_async(dev_tensor.data_ptr(), n_hay, int(uniform_len),
+                                                            g.send.data_ptr(), rows, stream=stream):
+                    break                                    # this batch needs the synchronous call (full walk)
+                sizes = g.exchange(rows, self.world)         # all_gather + the host wait
+                n = sizes[self.rank]
+                self.aut.async_finish(n)
+                if max(sizes) <= rows:
+                    return n, g.views(rows, self.world, sizes, dst)
         if uniform_len:
             _, n = self.aut.search_device_uniform(dev_tensor.data_ptr(), len(local_offsets) - 1, int(uniform_len), stream=stream)
         else:
             _, n = self.aut.search_device(dev_tensor.data_ptr(), local_offsets, stream=stream)
-        if self._gatherer is None:
-            self._gatherer = EventGatherer(self.group)
         like = torch.empty((0, 2), dtype=torch.int32, device=dev_tensor.device)
         got = self._gatherer.gather(None, dst, n=n, like=like,
                                     fill=lambda rows: self.aut.copy_events(rows.data_ptr(), rows.shape[0], stream=stream))

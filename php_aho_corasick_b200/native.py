@@ -77,7 +77,7 @@ EXPORTS = [
     "acb200_set_device", "acb200_device_count", "acb200_host_alloc", "acb200_host_free",
     "acb200_set_tuning", "acb200_version", "acb200_copy_events", "acb200_tally_cb", "acb200_tally_match_cb", "acb200_set_ilp",
     "acb200_set_filter", "acb200_search_device_uniform", "acb200_set_parts", "acb200_search_hits", "acb200_pattern", "acb200_save", "acb200_load", "acb200_filter_probe",
-    "acb200_set_direct", "acb200_direct_probe",
+    "acb200_set_direct", "acb200_direct_probe", "acb200_search_device_uniform_async", "acb200_async_finish",
 ]
 
 
@@ -133,6 +133,10 @@ def lib() -> C.CDLL:
     L.acb200_pattern.restype = C.POINTER(AcPattern)
     L.acb200_filter_probe.argtypes = [C.c_void_p, C.c_uint64, C.c_uint]
     L.acb200_filter_probe.restype = C.c_int
+    L.acb200_search_device_uniform_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.acb200_search_device_uniform_async.restype = C.c_int
+    L.acb200_async_finish.argtypes = [C.c_void_p, C.c_size_t]
+    L.acb200_async_finish.restype = C.c_int
     L.acb200_set_direct.argtypes = [C.c_void_p, C.c_int]
     L.acb200_direct_probe.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.acb200_direct_probe.restype = C.c_int
@@ -315,6 +319,15 @@ class Automaton:
         if rc != 0:
             raise AcError(last_error())
         return out.value, int(ne.value)
+
+    def search_device_uniform_async(self, dev_ptr: int, n_hay: int, hay_len: int, rows_ptr: int, max_events: int, stream: int = 0) -> bool:
+        """Enqueues the scan and returns at once: row 0 of the device buffer at rows_ptr receives the event count, rows 1..
+        the events.  False if only the synchronous call can serve this batch (see acb200.h)."""
+        return self.L.acb200_search_device_uniform_async(self.h, C.c_void_p(dev_ptr), int(n_hay), int(hay_len),
+                                                         C.c_void_p(rows_ptr), int(max_events), C.c_void_p(stream)) == 0
+
+    def async_finish(self, n_events: int) -> None:
+        self.L.acb200_async_finish(self.h, int(n_events))
 
     def search_flat_tally(self, host_ptr: int, offsets, first_only: bool = False) -> Tally:
         """ac_trie_search_flat() on a HOST buffer (e.g. pinned) with the library's tally callback:

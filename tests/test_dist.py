@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from php_aho_corasick_b200.dist import gather_packed_events, globalize, shard_ranges
+from php_aho_corasick_b200.dist import EventGatherer, gather_packed_events, globalize, shard_ranges
 
 
 def test_shard_ranges_cover_and_balance():
@@ -82,3 +82,68 @@ def test_gloo_two_rank_gather_and_globalize():
     assert state == [7, 9, 3, 4, 11, 12, 13]
     assert n_second == 4
     assert third == (4, 5000, [9998, 9999], True)
+
+
+def _chained_worker(rank, world, port, q):
+    """The chained scan -> gather step (ShardedMatcher.scan_and_gather, equal-length batches): the library writes
+    {count, events} straight into the send buffer and EventGatherer.exchange() sends it on.  Here a stand-in writes
+    the rows; rank 1 takes the synchronous gather() in the second step (a rank whose batch needs the full walk),
+    and outgrows the agreed rows in the third — all ranks must stay in step."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = EventGatherer()
+    like = torch.zeros((0, 2), dtype=torch.int32)
+
+    def library_writes(events, rows):                    # what acb200_search_device_uniform_async does with d_rows
+        g._ensure(rows, world, like)
+        g.send[0, 0] = events.shape[0]
+        m = min(events.shape[0], rows)
+        g.send[1:1 + m] = events[:m]
+
+    def chained(events):
+        while True:
+            rows = g.rows
+            library_writes(events, rows)
+            sizes = g.exchange(rows, world)
+            if max(sizes) <= rows:
+                return sizes, g.views(rows, world, sizes, 0)
+
+    mine = torch.arange(2 * (10 + rank), dtype=torch.int32).reshape(-1, 2) + 1000 * rank
+    got = g.gather(mine, 0)                              # first step: the synchronous form agrees on the rows
+    assert g.rows >= 1023
+    out = []
+    sizes, got = chained(mine)                           # second step: every rank chained
+    out.append((sizes, None if got is None else [x.tolist() for x in got]))
+    if rank == 0:                                        # third step: rank 0 chained, rank 1 synchronous
+        sizes, got = chained(mine)
+        out.append((sizes, [x.tolist() for x in got]))
+    else:
+        assert g.gather(mine, 0) is None
+    big = torch.arange(2 * 3000, dtype=torch.int32).reshape(3000, 2)
+    sizes, got = chained(big if rank == 1 else mine)     # fourth step: rank 1 outgrows the rows -> both repeat
+    out.append((sizes, None if got is None else (int(got[0].shape[0]), int(got[1].shape[0]), got[1][-1].tolist())))
+    q.put((rank, out, mine.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_chained_scan_and_gather_protocol():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_chained_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict()
+    for _ in range(2):
+        rank, out, mine = q.get(timeout=120)
+        res[rank] = (out, mine)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    out0, mine0 = res[0]
+    out1, mine1 = res[1]
+    assert out0[0] == ([10, 11], [mine0, mine1]) and out1[0] == ([10, 11], None)
+    assert out0[1] == ([10, 11], [mine0, mine1])
+    assert out0[2] == ([10, 3000], (10, 3000, [5998, 5999])) and out1[1] == ([10, 3000], None)

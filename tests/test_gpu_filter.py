@@ -480,3 +480,40 @@ def test_direct_verification_equals_walking_every_flagged_word():
     pats, flat, offs = cases[1]
     a = build([pats], 1)
     assert_same(a, a.search_events(flat, offs), len(offs) - 1, oracle_hits([pats], split(flat, offs)))
+
+
+def test_asynchronous_device_search_fills_the_callers_rows():
+    """acb200_search_device_uniform_async: nothing is waited for inside the call, row 0 of the caller's device buffer
+    receives the count, the rows after it the events of the synchronous call; too few rows -> the count says so and
+    only the first rows are written; batches the prefilter cannot take are refused (the caller uses the synchronous
+    call)."""
+    import torch
+    needles, hay, off = W.cfg2(n_hay=2048, hay_len=8192, planted_per_hay=8, seed=33)      # 16 MiB
+    a = build([needles], 0)
+    dev = torch.from_numpy(hay).to("cuda:0")
+    stream = torch.cuda.current_stream().cuda_stream
+    ptr, n = a.search_device_uniform(dev.data_ptr(), 2048, 8192, stream=stream)
+    assert a.stats().filtered == 1 and n > 10000
+    ref = torch.empty((n, 2), dtype=torch.int32, device="cuda:0")
+    assert a.copy_events(ref.data_ptr(), n, stream=stream) == n
+    torch.cuda.synchronize()
+    for rows in (n + 100, n, n // 2):
+        buf = torch.full((rows + 1, 2), -1, dtype=torch.int32, device="cuda:0")
+        assert a.search_device_uniform_async(dev.data_ptr(), 2048, 8192, buf.data_ptr(), rows, stream=stream)
+        got = buf.cpu()                                         # ordered by the STREAM alone (torch's current stream): no device-wide wait
+        assert int(got[0, 0]) == n                              # the full count, also when the rows were too few
+        a.async_finish(n)
+        st = a.stats()
+        assert st.events == n and st.kernel_ms > 0 and st.filtered == 1
+        m = min(n, rows)
+        assert torch.equal(got[1:1 + m], ref[:m].cpu())
+        assert bool((got[1 + m:] == -1).all())                  # nothing written behind the rows that fit
+    # a small batch goes to the full walk in automatic mode: no asynchronous form
+    small = dev[: 64 * 8192]
+    buf = torch.zeros((1025, 2), dtype=torch.int32, device="cuda:0")
+    assert not a.search_device_uniform_async(small.data_ptr(), 64, 8192, buf.data_ptr(), 1024, stream=stream)
+    a.set_filter(1)                                              # forced prefilter: served
+    assert a.search_device_uniform_async(small.data_ptr(), 64, 8192, buf.data_ptr(), 1024, stream=stream)
+    torch.cuda.synchronize()
+    _, n_small = a.search_device_uniform(small.data_ptr(), 64, 8192, stream=stream)
+    assert int(buf[0, 0].cpu()) == n_small
