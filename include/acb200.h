@@ -205,7 +205,7 @@ int acb200_search_device_uniform(AC_TRIE_t *thiz, const void *d_bytes, size_t n,
  * statistics of acb200_last_stats(); the library's own event buffer is not touched.                      */
 int acb200_search_device_uniform_async(AC_TRIE_t *thiz, const void *d_bytes, size_t n, size_t hay_len,
                                        void *d_rows, size_t max_events, void *stream);
-int acb200_async_finish(AC_TRIE_t *thiz, size_t n_events);
+int acb200_async_finish(AC_TRIE_t *thiz, size_t n_events, size_t dense_tiles);
 
 /* One reported pattern occurrence, as the reference's callback would have recorded it
  * (src/php_ahocorasick.c:555-584): haystack index, exclusive end offset inside the haystack

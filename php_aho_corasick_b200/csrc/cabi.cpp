@@ -322,10 +322,10 @@ int acb200_search_device_uniform_async(AC_TRIE_t *t, const void *d_bytes, size_t
     return t->engine.scan_device_uniform_async(d_bytes, n, hay_len, d_rows, max_events, stream) ? 0 : -1;
 }
 
-int acb200_async_finish(AC_TRIE_t *t, size_t n_events)
+int acb200_async_finish(AC_TRIE_t *t, size_t n_events, size_t dense_tiles)
 {
     if (t->open || !t->device_ok) return -1;
-    t->engine.async_finish(n_events);
+    t->engine.async_finish(n_events, dense_tiles);
     return 0;
 }
 

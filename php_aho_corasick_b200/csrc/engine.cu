@@ -913,7 +913,7 @@ bool Engine::scan_device_uniform_async(const void *d_bytes, size_t n, size_t hay
 }
 
 // The caller has waited for the stream: times from the recorded events, counts from what it read in row 0.
-void Engine::async_finish(size_t n_events)
+void Engine::async_finish(size_t n_events, size_t dense_tiles)
 {
     if (!async_pending_) return;
     async_pending_ = false;
@@ -928,6 +928,8 @@ void Engine::async_finish(size_t n_events)
     stats.events = n_events;
     n_events_ = 0;                           // the events live in the caller's rows, not in the library's buffer
     last_density_ = stats.bytes ? (double)n_events / (double)stats.bytes : 0.0;
+    stats.dense_tiles = dense_tiles;
+    if (async_tiles_) last_dense_frac_ = (double)dense_tiles / (double)async_tiles_;      // feeds the automatic kernel choice
     stats.ilp = 1;
 }
 

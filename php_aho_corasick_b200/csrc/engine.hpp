@@ -50,7 +50,7 @@ public:
     // rows 1 .. max_events the first max_events events.  Only the prefilter path can do this (false + error
     // otherwise: use the synchronous call); async_finish() completes the bookkeeping once the caller has waited.
     bool scan_device_uniform_async(const void *d_bytes, size_t n, size_t hay_len, void *d_rows, size_t max_events, void *stream);
-    void async_finish(size_t n_events);
+    void async_finish(size_t n_events, size_t dense_tiles);
     bool copy_events_to(void *d_dst, size_t n, void *stream);
     // Expands the events of the most recent scan_host() into hits on the device and copies up to `cap` of them
     // to `hits` (host).  *n_hits receives the total.

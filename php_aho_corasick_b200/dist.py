@@ -45,6 +45,7 @@ class EventGatherer:
         self.rows = 0            # event rows per rank in the collective (agreed)
         self.send = None
         self.recv = None
+        self.row0_extra = []
 
     def _ensure(self, rows, world, like):
         if self.send is None or self.send.shape[0] < rows + 1 or self.send.device != like.device or self.send.dtype != like.dtype:
@@ -65,7 +66,9 @@ class EventGatherer:
         except (RuntimeError, NotImplementedError, AttributeError):
             dist.all_gather([out[r * (rows + 1):(r + 1) * (rows + 1)] for r in range(world)], self.send[: rows + 1],
                             group=self.group)
-        sizes = [int(x) & 0xFFFFFFFF for x in out.view(world, rows + 1, 2)[:, 0, 0].cpu().tolist()]
+        row0 = out.view(world, rows + 1, 2)[:, 0, :].cpu().tolist()      # the one host wait of the step
+        sizes = [int(r[0]) & 0xFFFFFFFF for r in row0]
+        self.row0_extra = [int(r[1]) & 0xFFFFFFFF for r in row0]           # second word of row 0 (the library: dense tiles)
         self.rows = self._rows_for(max(sizes))
         return sizes
 
@@ -195,7 +198,7 @@ class ShardedMatcher:
                     break                                    # this batch needs the synchronous call (full walk)
                 sizes = g.exchange(rows, self.world)         # all_gather + the host wait
                 n = sizes[self.rank]
-                self.aut.async_finish(n)
+                self.aut.async_finish(n, g.row0_extra[self.rank])
                 if max(sizes) <= rows:
                     return n, g.views(rows, self.world, sizes, dst)
         if uniform_len:

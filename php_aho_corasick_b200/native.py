@@ -135,7 +135,7 @@ def lib() -> C.CDLL:
     L.acb200_filter_probe.restype = C.c_int
     L.acb200_search_device_uniform_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
     L.acb200_search_device_uniform_async.restype = C.c_int
-    L.acb200_async_finish.argtypes = [C.c_void_p, C.c_size_t]
+    L.acb200_async_finish.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t]
     L.acb200_async_finish.restype = C.c_int
     L.acb200_set_direct.argtypes = [C.c_void_p, C.c_int]
     L.acb200_direct_probe.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -326,8 +326,9 @@ class Automaton:
         return self.L.acb200_search_device_uniform_async(self.h, C.c_void_p(dev_ptr), int(n_hay), int(hay_len),
                                                          C.c_void_p(rows_ptr), int(max_events), C.c_void_p(stream)) == 0
 
-    def async_finish(self, n_events: int) -> None:
-        self.L.acb200_async_finish(self.h, int(n_events))
+    def async_finish(self, n_events: int, dense_tiles: int = 0) -> None:
+        """after the caller has waited for the stream: the two values it read from row 0"""
+        self.L.acb200_async_finish(self.h, int(n_events), int(dense_tiles))
 
     def search_flat_tally(self, host_ptr: int, offsets, first_only: bool = False) -> Tally:
         """ac_trie_search_flat() on a HOST buffer (e.g. pinned) with the library's tally callback:

@@ -24,7 +24,7 @@ for mode in ("sync", "async", "sync", "async"):
     e1.record()
     if mode == "async":
         n2 = int(buf[0, 0].cpu())                     # stream-ordered read, no device-wide wait before it
-        a.async_finish(n2)
+        a.async_finish(n2, int(buf[0, 1].cpu()))
     torch.cuda.synchronize()
     st = a.stats()
     print(f"{mode:5s} events={n2} wall(cuda events)={e0.elapsed_time(e1):.3f} ms  kernel={st.kernel_ms:.3f} filter={st.filter_ms:.3f} verify={st.verify_ms:.3f} reorder={st.reorder_ms:.3f}", flush=True)

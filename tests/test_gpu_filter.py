@@ -502,7 +502,7 @@ def test_asynchronous_device_search_fills_the_callers_rows():
         assert a.search_device_uniform_async(dev.data_ptr(), 2048, 8192, buf.data_ptr(), rows, stream=stream)
         got = buf.cpu()                                         # ordered by the STREAM alone (torch's current stream): no device-wide wait
         assert int(got[0, 0]) == n                              # the full count, also when the rows were too few
-        a.async_finish(n)
+        a.async_finish(n, int(got[0, 1]))
         st = a.stats()
         assert st.events == n and st.kernel_ms > 0 and st.filtered == 1
         m = min(n, rows)
