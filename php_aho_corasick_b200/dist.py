@@ -13,6 +13,8 @@ import torch.distributed as dist
 
 from .native import EVENT_DTYPE
 
+LEGACY_STREAM = 1        # cudaStreamLegacy: the explicit handle of the default stream torch uses (its cuda_stream is 0)
+
 
 def shard_ranges(offsets, world: int):
     """Contiguous haystack blocks [h0, h1) per rank, balanced by bytes. offsets: uint64[n+1]."""
@@ -172,7 +174,8 @@ class ShardedMatcher:
             _, n = self.aut.search_device(dev_tensor.data_ptr(), local_offsets, first_only=first_only, stream=stream)
         if self._ev is None or self._ev.shape[0] < max(n, 1):
             self._ev = torch.empty((max(n, 1024), 2), dtype=torch.int32, device=dev_tensor.device)
-        self.aut.copy_events(self._ev.data_ptr(), n, stream=stream)
+        # (a NULL handle would mean the library's private stream: the copy has to be ordered with the caller's stream)
+        self.aut.copy_events(self._ev.data_ptr(), n, stream=stream or LEGACY_STREAM)
         return self._ev[:n]
 
     def scan_and_gather(self, dev_tensor: torch.Tensor, local_offsets, dst: int = 0, stream=0, uniform_len=0):
@@ -207,7 +210,7 @@ class ShardedMatcher:
             _, n = self.aut.search_device(dev_tensor.data_ptr(), local_offsets, stream=stream)
         like = torch.empty((0, 2), dtype=torch.int32, device=dev_tensor.device)
         got = self._gatherer.gather(None, dst, n=n, like=like,
-                                    fill=lambda rows: self.aut.copy_events(rows.data_ptr(), rows.shape[0], stream=stream))
+                                    fill=lambda rows: self.aut.copy_events(rows.data_ptr(), rows.shape[0], stream=stream or LEGACY_STREAM))
         return n, got
 
     def match(self, flat: np.ndarray, offsets, first_only=False):

@@ -517,3 +517,41 @@ def test_asynchronous_device_search_fills_the_callers_rows():
     torch.cuda.synchronize()
     _, n_small = a.search_device_uniform(small.data_ptr(), 64, 8192, stream=stream)
     assert int(buf[0, 0].cpu()) == n_small
+
+
+def test_sharded_matcher_chained_step_on_one_rank():
+    """dist.ShardedMatcher on a one-rank NCCL group: the first scan_and_gather step is synchronous (it agrees on the
+    rows), the following ones chain scan -> all_gather on the stream; the gathered rows must be the events of the
+    plain call, and match() must return what search_events returns."""
+    import os
+    import socket
+    import torch
+    import torch.distributed as dist
+    from php_aho_corasick_b200.dist import ShardedMatcher
+    needles, hay, off = W.cfg2(n_hay=2048, hay_len=8192, planted_per_hay=8, seed=44)      # 16 MiB: prefilter in automatic mode
+    a = build([needles], 0)
+    ref = a.search_events(hay, off)
+    stream_end = ref["end"].astype(np.int64) + ref["text_idx"].astype(np.int64) * 8192
+    created = False
+    if not dist.is_initialized():
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        torch.cuda.set_device(0)
+        dist.init_process_group("nccl", rank=0, world_size=1)
+        created = True
+    try:
+        dev = torch.from_numpy(hay).to("cuda:0")
+        stream = torch.cuda.current_stream().cuda_stream
+        sm = ShardedMatcher(a)
+        for step in range(3):
+            n, got = sm.scan_and_gather(dev, off, 0, stream=stream, uniform_len=8192)
+            assert n == len(ref) and len(got) == 1 and got[0].shape[0] == n, step
+            ev = got[0].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+            assert np.array_equal(ev[:, 0], stream_end) and np.array_equal(ev[:, 1], ref["state"].astype(np.int64)), step
+            st = a.stats()
+            assert st.filtered == 1 and st.events == n and st.kernel_ms > 0
+        assert np.array_equal(sm.match(hay, off), ref)
+    finally:
+        if created:
+            dist.destroy_process_group()
