@@ -82,6 +82,32 @@ def test_direct_verdicts_match_the_oracle(seed):
     check_text(a, pats, bytes(text), expect_mostly_direct=len(alphabet) > 3)
 
 
+@pytest.mark.parametrize("W", [4, 8])
+def test_edge_lengths_duplicates_and_high_bytes(W):
+    """Lengths at the limits (exactly 2W, 2W+1, the tail/store boundary at 16/17 bytes, the reference's maximum of
+    1024), a duplicate inside one call (the later array entry wins) and bytes >= 0x80 / NUL."""
+    rng = random.Random(4242 + W)
+    alphabet = bytes([0x00, 0x7f, 0x80, 0xff, 0x41, 0x42])
+    lens = [2 * W, 2 * W + 1, 15 if W == 4 else 23, 16, 17, 24, 31, 32, 33, 64, 100, 1023, 1024]
+    pats = [bytes(rng.choice(alphabet) for _ in range(L)) for L in lens if L >= 2 * W]
+    pats.append(pats[3])                                     # duplicate value: ordinal of the LAST entry is reported
+    a = build_host(pats)
+    assert a.info().filter_word == W
+    text = bytearray(rng.choice(alphabet) for _ in range(9000))
+    at = 40
+    for p in pats:                                           # every pattern once, at a different alignment each
+        text[at:at + len(p)] = p
+        at += len(p) + 37 + (at % 5)
+        if at + 1100 > len(text):
+            at = 3
+    for _ in range(40):
+        p = pats[rng.randrange(6)]
+        pos = rng.randint(0, len(text) - len(p))
+        text[pos:pos + len(p)] = p
+    counts = check_text(a, pats, bytes(text), expect_mostly_direct=False)
+    assert counts[1] >= 20, counts
+
+
 def test_nested_and_overlapping_patterns_fall_back_to_the_walk():
     # suffix-nested patterns share grams; a pattern that is the suffix of a longer pattern's PREFIX is a failure
     # target (the walk may sit on a deeper node when it ends) — both must come back as "undecided", never wrong
