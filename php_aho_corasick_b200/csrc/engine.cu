@@ -489,7 +489,12 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     a.first_end = d_first_;
     if (win_rows == 0 && x4) { set_error("internal: x4 kernel chosen without a window"); return false; }
     const unsigned warps_per_cta = (x4 ? X4_THREADS : SCAN_THREADS) / 32;
-    const unsigned grid = std::min<uint32_t>((n_tiles + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
+    // Tiles are handed out by ticket, so any grid is correct.  One CTA per 32 tiles (a tile per warp) left most SMs idle
+    // for mid-size inputs and long patterns (config 5: 256 MiB = 1,024 tiles of 256 KiB -> 32 of 148 SMs): spread
+    // the tiles over the SMs instead, at least four per CTA so that a CTA's table staging is shared by some work.
+    // (Changed after this round's last GPU run: correctness does not depend on it, its effect is not measured yet.)
+    const unsigned grid = std::min<uint32_t>(std::max<uint32_t>((n_tiles + warps_per_cta - 1) / warps_per_cta, (n_tiles + 3u) / 4u),
+                                             (uint32_t)n_sms_);
 
     for (int attempt = 0; attempt < 2; ++attempt) {
         a.out = (uint2 *)d_events_;
