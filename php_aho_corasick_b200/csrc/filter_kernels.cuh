@@ -76,6 +76,36 @@ struct FilterArgs {
 
 // ------------------------------------------------------------- filter -----
 
+// Stages the level-1 bitmap in shared memory (all threads of the CTA) and returns its shared-window address.
+__device__ __forceinline__ uint32_t stage_bitmap(const FilterArgs &a, uint32_t *s_bm, uint32_t tid)
+{
+    const uint4 *src = reinterpret_cast<const uint4 *>(a.l1);
+    uint4 *dst = reinterpret_cast<uint4 *>(s_bm);
+    const uint32_t n4 = a.l1_bits >> 7;
+    for (uint32_t i = tid; i < n4; i += SCAN_THREADS) dst[i] = __ldg(src + i);
+    __syncthreads();
+    return (uint32_t)__cvta_generic_to_shared(s_bm);
+}
+
+// One flag per aligned word: both bits of the gram hash (the word + the byte after it) are set in level 1
+// (and, with L2, the bit of the independent hash in the level-2 bitmap in HBM/L2).
+template <bool L2>
+__device__ __forceinline__ bool test_word(const FilterArgs &a, uint32_t s_base, uint32_t lo, uint32_t hi, uint32_t nb, bool maybe_unknown)
+{
+    const uint32_t t = filter_mix1(lo, hi, nb);
+    const uint32_t widx = maybe_unknown ? filter_l1_word(t, nb == FILTER_NEXT_UNKNOWN) : filter_l1_word(t, false);
+    uint32_t word;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(s_base + widx * 4u));
+    bool p = ((word >> filter_bit1(t)) & (word >> filter_bit2(t)) & 1u) != 0;
+    if (L2) {
+        uint32_t word3 = 0;
+        const uint32_t i3 = filter_mix3(lo, hi, nb) >> a.l2_shift;
+        if (p) word3 = __ldg(a.l2 + (i3 >> 5));
+        p = (word3 >> (i3 & 31u)) & 1u;
+    }
+    return p;
+}
+
 template <int W, bool L2>
 __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const FilterArgs a)
 {
@@ -85,29 +115,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const Filter
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.l1);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_bm);
-        const uint32_t n4 = a.l1_bits >> 7;
-        for (uint32_t i = tid; i < n4; i += SCAN_THREADS) dst[i] = __ldg(src + i);
-    }
-    __syncthreads();
-    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_bm);
-
-    // one flag per aligned word: both bits of the gram hash (the word + the byte after it) are set in level 1
-    auto test_word = [&](uint32_t lo, uint32_t hi, uint32_t nb, bool maybe_unknown) -> bool {
-        const uint32_t t = filter_mix1(lo, hi, nb);
-        const uint32_t widx = maybe_unknown ? filter_l1_word(t, nb == FILTER_NEXT_UNKNOWN) : filter_l1_word(t, false);
-        uint32_t word;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(s_base + widx * 4u));
-        bool p = ((word >> filter_bit1(t)) & (word >> filter_bit2(t)) & 1u) != 0;
-        if (L2) {
-            uint32_t word3 = 0;
-            const uint32_t i3 = filter_mix3(lo, hi, nb) >> a.l2_shift;
-            if (p) word3 = __ldg(a.l2 + (i3 >> 5));
-            p = (word3 >> (i3 & 31u)) & 1u;
-        }
-        return p;
+    const uint32_t s_base = stage_bitmap(a, s_bm, tid);
+    auto test = [&](uint32_t lo, uint32_t hi, uint32_t nb, bool maybe_unknown) -> bool {
+        return test_word<L2>(a, s_base, lo, hi, nb, maybe_unknown);
     };
 
     const uint32_t n_full_all = a.total / SPAN_BYTES;         // spans that lie completely inside the stream
@@ -136,7 +146,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const Filter
 #pragma unroll
             for (int j = 0; j < NB; ++j) {
                 const uint32_t nb = (j == NB - 1) ? after : (((W == 8) ? w[2] : w[j + 1]) & 0xffu);
-                const bool p = (W == 8) ? test_word(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test_word(w[j], 0u, nb, j == NB - 1);
+                const bool p = (W == 8) ? test(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test(w[j], 0u, nb, j == NB - 1);
                 const uint32_t plane = __ballot_sync(0xffffffffu, p);
                 if (lane == (uint32_t)j) mine = plane;
             }
@@ -163,7 +173,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const Filter
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
             const uint32_t nb = (j == NB - 1) ? after : (((W == 8) ? w[2] : w[j + 1]) & 0xffu);
-            bool p = (W == 8) ? test_word(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test_word(w[j], 0u, nb, j == NB - 1);
+            bool p = (W == 8) ? test(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test(w[j], 0u, nb, j == NB - 1);
             p = (c < n16) ? p : tail;
             const uint32_t plane = __ballot_sync(0xffffffffu, p);
             if (lane == (uint32_t)j) mine = plane;
@@ -632,28 +642,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_collect_kernel(cons
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(fa.l1);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_bm);
-        const uint32_t n4 = fa.l1_bits >> 7;
-        for (uint32_t i = tid; i < n4; i += SCAN_THREADS) dst[i] = __ldg(src + i);
-    }
-    __syncthreads();
-    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_bm);
-
-    auto test_word = [&](uint32_t lo, uint32_t hi, uint32_t nb, bool maybe_unknown) -> bool {
-        const uint32_t t = filter_mix1(lo, hi, nb);
-        const uint32_t widx = maybe_unknown ? filter_l1_word(t, nb == FILTER_NEXT_UNKNOWN) : filter_l1_word(t, false);
-        uint32_t word;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(s_base + widx * 4u));
-        bool p = ((word >> filter_bit1(t)) & (word >> filter_bit2(t)) & 1u) != 0;
-        if (L2) {
-            uint32_t word3 = 0;
-            const uint32_t i3 = filter_mix3(lo, hi, nb) >> fa.l2_shift;
-            if (p) word3 = __ldg(fa.l2 + (i3 >> 5));
-            p = (word3 >> (i3 & 31u)) & 1u;
-        }
-        return p;
+    const uint32_t s_base = stage_bitmap(fa, s_bm, tid);
+    auto test = [&](uint32_t lo, uint32_t hi, uint32_t nb, bool maybe_unknown) -> bool {
+        return test_word<L2>(fa, s_base, lo, hi, nb, maybe_unknown);
     };
     // flag bits of one 16-byte chunk per lane: plane j bit c <=> word j of lane c
     auto test_chunk = [&](const uint4 &v, bool chunk_known, bool next_known, bool force, uint32_t (&plane)[NB]) {
@@ -663,7 +654,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_collect_kernel(cons
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
             const uint32_t nb = (j == NB - 1) ? after : (((W == 8) ? w[2] : w[j + 1]) & 0xffu);
-            bool p = (W == 8) ? test_word(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test_word(w[j], 0u, nb, j == NB - 1);
+            bool p = (W == 8) ? test(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test(w[j], 0u, nb, j == NB - 1);
             p = chunk_known ? p : force;
             plane[j] = __ballot_sync(0xffffffffu, p);
         }
