@@ -1,6 +1,6 @@
 // gram_table.hpp — exact table of the prefilter grams and the direct verification of a flagged word,
 // shared by the host (table construction at finalize, acb200_direct_probe) and the device
-// (ac_filter_collect_kernel, ac_walk_kernel).
+// (ac_walk_kernel; ac_settle_kernel on the opt-in fused path).
 //
 // The prefilter (filter_kernels.cuh) flags an aligned W-byte haystack word k when (word, byte after it) MAY be
 // the gram pattern[L-W-r, L-r] + pattern[L-r] of some accepted pattern, r = 1..W.  Walking the automaton over
