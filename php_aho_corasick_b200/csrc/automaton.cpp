@@ -337,7 +337,6 @@ void build_gram_table(FlatAutomaton &flat) {
     const uint32_t W = flat.filter_w;
     const size_t np = flat.accepted.size();
     if ((W != 4 && W != 8) || np == 0 || np * W > (1ull << 27)) return;
-    if (getenv("ACB200_NO_GRAM_TABLE")) return;
     // (a loaded blob is only structurally validated: make sure of what is indexed below)
     for (const AC_PATTERN_t &p : flat.accepted)
         if (p.ptext.length < 2 * W || p.ptext.length > AC_PATTRN_MAX_LENGTH) return;

@@ -1,5 +1,7 @@
-"""GPU parity of the gram-prefilter path (ac_filter_kernel + ac_verify_kernel) against the CPU oracle and
-against the full automaton walk (ac_scan_kernel): same events, same order, through the C-ABI."""
+"""GPU parity of the gram-prefilter path (ac_filter_kernel, ac_collect_kernel, ac_walk_kernel with the direct
+verification of gram_table.hpp, ac_offsets_kernel, ac_emit_kernel; the opt-in fused ac_filter_collect_kernel +
+ac_settle_kernel; the asynchronous device call and the chained multi-GPU step) against the CPU oracle and against
+the full automaton walk (ac_scan_kernel): same events, same order, through the C-ABI."""
 import random
 
 import numpy as np
