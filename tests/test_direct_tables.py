@@ -190,3 +190,32 @@ def test_no_table_without_prefilter():
     b = build_host([b"abc", b"abcdefghijklmnopq"])
     assert b.info().direct_keys == 0
     assert b.direct_probe(b"x" * 64, 3)[0] == -1
+
+
+def test_property_random_dictionaries_with_heavy_overlap():
+    """hypothesis: tiny alphabets and patterns cut from one another (shared grams, suffix / prefix nesting, failure
+    targets everywhere) — whatever the table decides directly must be what the oracle reports."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.integers(0, 2 ** 32 - 1), st.sampled_from([4, 8]), st.sampled_from([b"ab", b"abc", b"\x00\xff"]))
+    def run(seed, W, alphabet):
+        rng = random.Random(seed)
+        base = bytes(rng.choice(alphabet) for _ in range(120))
+        pats = []
+        for _ in range(rng.randint(1, 12)):                  # substrings of one text: maximal overlap between patterns
+            L = rng.randint(2 * W, 2 * W + rng.choice([0, 1, 5, 20]))
+            at = rng.randint(0, len(base) - L)
+            pats.append(base[at:at + L])
+        a = build_host(pats)
+        if a.info().filter_word != W:                        # (W = 8 needs every pattern >= 16 bytes: true by construction)
+            assert W == 4 and min(len(p) for p in pats) >= 16
+        text = bytearray(rng.choice(alphabet) for _ in range(600))
+        for _ in range(8):
+            at = rng.randint(0, len(text) - len(base))
+            cut = rng.randint(20, len(base))
+            text[at:at + cut] = base[:cut]
+        check_text(a, pats, bytes(text), expect_mostly_direct=False)
+        a.release()
+
+    run()
