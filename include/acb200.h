@@ -296,7 +296,7 @@ typedef struct acb200_stats
     uint32_t halo_bytes;      /* overlap re-read before each slice           */
     float kernel_ms;          /* device time of the scan kernel(s)           */
     float h2d_ms, d2h_ms;     /* copies, 0 for the device-resident entry     */
-    uint32_t ilp;             /* slices walked in lockstep per lane (1 or 4) */
+    uint32_t devices;         /* GPUs that took part in the call (acb200_set_devices) */
     uint32_t filtered;        /* 1: gram prefilter + verify kernels, 0: full automaton walk */
     float filter_ms;          /* device time of the prefilter kernel (0 if unused) */
     float verify_ms;          /* device time of the verify kernel (0 if unused) */
@@ -304,7 +304,6 @@ typedef struct acb200_stats
     uint64_t dense_tiles;     /* 16 KiB tiles handed to verification as whole spans */
     float reorder_ms;         /* device time of the offsets + emit kernels (0 if unused) */
     float expand_ms;          /* device time of the hit expansion kernels (acb200_search_hits) */
-    uint32_t fused;           /* 1: filter, item lists and window staging in one pass (ac_filter_collect_kernel) */
 } ACB200_STATS_t;
 int acb200_last_stats(const AC_TRIE_t *thiz, ACB200_STATS_t *out);
 
@@ -325,9 +324,6 @@ void acb200_host_free(void *p);
 int acb200_set_tuning(AC_TRIE_t *thiz, uint32_t chunk_bytes,
                       uint32_t smem_table_bytes);
 
-/* Slices per lane: 0 = automatic, 1 or 4 force a kernel variant (benchmarks, tests). */
-int acb200_set_ilp(AC_TRIE_t *thiz, int ilp);
-
 /* Gram prefilter (dictionaries whose accepted patterns are all >= 8 bytes): 0 = automatic,
  * 1 = use it whenever the dictionary allows, -1 = never (always walk the full automaton).
  * Results are identical either way.                                                     */
@@ -342,9 +338,8 @@ int acb200_filter_probe(const AC_TRIE_t *thiz, uint64_t word, unsigned next_byte
 
 /* Direct verification of flagged words (gram_table.hpp): a flagged word whose (word, next byte) belongs to exactly
  * one (pattern, alignment) is decided by comparing the haystack with that pattern instead of walking the
- * automaton.  0 = automatic (currently 1), 1 = inside ac_walk_kernel, 2 = fused pass (ac_filter_collect_kernel
- * filters, builds the item lists and stages the windows; opt-in, measured slower so far), -1 = off (every flagged
- * word is walked).  Results are identical in every mode. */
+ * automaton.  0 = automatic (currently 1), 1 = on, -1 = off (every flagged word is walked).  Results are
+ * identical in every mode. */
 int acb200_set_direct(AC_TRIE_t *thiz, int mode);
 
 /* Diagnostic: the direct verification of the aligned word `word_index` (bytes [W*word_index, W*word_index + W) of
@@ -356,10 +351,6 @@ int acb200_set_direct(AC_TRIE_t *thiz, int mode);
  * the stream).  Not a matching path: tests check the table construction against the CPU oracle with it. */
 int acb200_direct_probe(const AC_TRIE_t *thiz, const char *bytes, size_t length, size_t hay_begin, size_t word_index,
                         uint32_t *end, uint32_t *state);
-
-/* Parts a prefiltered scan is cut into (the filter of part p+1 overlaps the verification of part p on a
- * second stream): 0 = automatic (currently 1: overlapping did not pay on B200), 1..8 = fixed. */
-int acb200_set_parts(AC_TRIE_t *thiz, unsigned parts);
 
 const char *acb200_version(void);
 

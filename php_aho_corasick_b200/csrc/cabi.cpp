@@ -196,7 +196,7 @@ static int search_flat_pipelined(ac_trie *t, const char *bytes, const uint64_t *
         sum.kernel_ms += eng.stats.kernel_ms; sum.filter_ms += eng.stats.filter_ms; sum.verify_ms += eng.stats.verify_ms;
         sum.reorder_ms += eng.stats.reorder_ms; sum.d2h_ms += eng.stats.d2h_ms; sum.h2d_ms += eng.slab_h2d_ms((int)(s & 1));
         sum.flagged_words += eng.stats.flagged_words; sum.dense_tiles += eng.stats.dense_tiles;
-        sum.chunk_bytes = eng.stats.chunk_bytes; sum.halo_bytes = eng.stats.halo_bytes; sum.ilp = eng.stats.ilp;
+        sum.chunk_bytes = eng.stats.chunk_bytes; sum.halo_bytes = eng.stats.halo_bytes;
         sum.filtered = eng.stats.filtered;
         // replay this slab's events; haystack indices are those of the whole batch
         const PackedEvent *ev = eng.host_events();
@@ -406,12 +406,6 @@ int acb200_set_tuning(AC_TRIE_t *t, uint32_t chunk_bytes, uint32_t smem_table_by
     return 0;
 }
 
-int acb200_set_ilp(AC_TRIE_t *t, int ilp)
-{
-    t->engine.tune_ilp = ilp;
-    return 0;
-}
-
 int acb200_set_filter(AC_TRIE_t *t, int mode)
 {
     t->engine.tune_filter = mode;
@@ -464,12 +458,6 @@ int acb200_direct_probe(const AC_TRIE_t *t, const char *bytes, size_t length, si
     }
     if (v == GRAM_EVENT) { if (end) *end = e; if (state) *state = s; }
     return v;
-}
-
-int acb200_set_parts(AC_TRIE_t *t, unsigned parts)
-{
-    t->engine.tune_parts = parts;
-    return 0;
 }
 
 void ac_trie_release(AC_TRIE_t *t)

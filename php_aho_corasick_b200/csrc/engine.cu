@@ -1,7 +1,6 @@
 // engine.cu — see engine.hpp.
 #include "engine.hpp"
 #include "scan_kernels.cuh"
-#include "scan_kernel_x4.cuh"
 #include "filter_kernels.cuh"
 
 #include <algorithm>
@@ -63,8 +62,7 @@ void Engine::release()
     cudaFree(d_out_off_); cudaFree(d_out_idx_); cudaFree(d_pat_len_); cudaFree(d_hit_sums_); cudaFree(d_hits_); cudaFree(d_hit_total_);
     d_out_off_ = nullptr; d_out_idx_ = nullptr; d_pat_len_ = nullptr; d_hit_sums_ = nullptr; d_hits_ = nullptr; d_hit_total_ = nullptr;
     hit_sums_cap_ = 0; hits_cap_ = 0;
-    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_); cudaFree(d_stage_); cudaFree(d_todo_);
-    d_stage_ = nullptr; d_todo_ = nullptr; stage_tiles_cap_ = 0;
+    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_);
     d_l1_ = nullptr; d_l2_ = nullptr; d_mask_ = nullptr; mask_cap_ = 0;
     d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; verify_tiles_cap_ = 0;
     if (h_counters_) cudaFreeHost(h_counters_);
@@ -74,8 +72,6 @@ void Engine::release()
     for (auto &e : ev_slab_) if (e) { cudaEventDestroy(EV(e)); e = nullptr; }
     for (int b = 0; b < 2; ++b) { cudaFree(d_slab_[b]); d_slab_[b] = nullptr; slab_cap_[b] = 0; }
     if (copy_stream_) { cudaStreamDestroy(S(copy_stream_)); copy_stream_ = nullptr; }
-    for (auto &e : ev_part_) if (e) { cudaEventDestroy(EV(e)); e = nullptr; }
-    if (verify_stream_) { cudaStreamDestroy(S(verify_stream_)); verify_stream_ = nullptr; }
     if (stream_) cudaStreamDestroy(S(stream_));
     d_table_ = nullptr; d_cls_ = nullptr; d_text_ = nullptr; d_off_ = nullptr; d_first_ = nullptr;
     d_events_ = nullptr; d_tiles_ = nullptr; d_counters_ = nullptr;
@@ -203,10 +199,6 @@ bool Engine::build(const FlatAutomaton &f)
     CU_OK((set_smem_attr<uint32_t, true, true>(dyn)));
     CU_OK((set_smem_attr<uint32_t, false, false>(dyn)));
     CU_OK((set_smem_attr<uint32_t, false, true>(dyn)));
-    CU_OK(cudaFuncSetAttribute(ac_scan_kernel_x4<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-    CU_OK(cudaFuncSetAttribute(ac_scan_kernel_x4<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-    CU_OK(cudaFuncSetAttribute(ac_scan_kernel_x4<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-    CU_OK(cudaFuncSetAttribute(ac_scan_kernel_x4<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
 
     // output lists for the device-side hit expansion
     {
@@ -245,10 +237,6 @@ bool Engine::build(const FlatAutomaton &f)
         CU_OK(cudaFuncSetAttribute(ac_filter_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
         CU_OK(cudaFuncSetAttribute(ac_filter_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
         CU_OK(cudaFuncSetAttribute(ac_filter_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
-        CU_OK((cudaFuncSetAttribute(ac_filter_collect_kernel<8, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
-        CU_OK((cudaFuncSetAttribute(ac_filter_collect_kernel<8, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
-        CU_OK((cudaFuncSetAttribute(ac_filter_collect_kernel<4, false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
-        CU_OK((cudaFuncSetAttribute(ac_filter_collect_kernel<4, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
     }
     info.filter_word = (int32_t)filter_w_;
     info.min_pattern_len = f.min_pattern_len;
@@ -326,11 +314,10 @@ bool Engine::ensure_mask(size_t words)
 bool Engine::ensure_verify_scratch(size_t n_tiles)
 {
     if (n_tiles <= verify_tiles_cap_) return true;
-    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_); cudaFree(d_stage_); cudaFree(d_todo_);
-    d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; d_stage_ = nullptr; d_todo_ = nullptr; stage_tiles_cap_ = 0; verify_tiles_cap_ = 0;
+    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_);
+    d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; verify_tiles_cap_ = 0;
     const size_t cap = std::max(n_tiles + n_tiles / 4, (size_t)256);
     CU_OK(cudaMalloc(&d_items_, cap * VER_DENSE_MAX * sizeof(uint32_t)));
-    CU_OK(cudaMemset(d_items_, 0, cap * VER_DENSE_MAX * sizeof(uint32_t)));     // ac_settle_kernel loads a tile's unused slots too
     CU_OK(cudaMalloc(&d_recs_, cap * VER_DENSE_MAX * 2 * sizeof(uint32_t)));
     CU_OK(cudaMalloc(&d_desc_, cap * 2 * sizeof(uint32_t)));
     // one block: [16 counters | block sums | events per tile | offsets per tile] — the first three are zeroed by ONE memset
@@ -416,7 +403,7 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     stats.bytes = total; stats.events = 0; stats.kernel_launches = 0; stats.kernel_ms = 0;
     stats.halo_bytes = halo_;
     stats.filtered = 0; stats.filter_ms = 0; stats.verify_ms = 0; stats.flagged_words = 0; stats.dense_tiles = 0;
-    stats.reorder_ms = 0; stats.expand_ms = 0; stats.fused = 0;
+    stats.reorder_ms = 0; stats.expand_ms = 0;
     if (total == 0) { stats.chunk_bytes = 0; return true; }
 
     // Gram prefilter: needs an eligible dictionary and a walk that starts at the root.  Automatic mode
@@ -453,12 +440,7 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     const size_t row_bytes = (size_t)ncls_ * entry_bytes_;
     const size_t smem_bytes = std::max<size_t>(16, (size_t)win_rows * row_bytes);
 
-    // ac_scan_kernel_x4 (four slices per lane in lockstep) is opt-in for now: with text arriving through
-    // strided 16-byte loads the L1TEX pipe, not lookup latency, is the limit, and measured on B200 it is
-    // no faster than one slice per lane (940 vs 968 GB/s) and much slower when events are dense.
-    const bool x4 = (tune_ilp == 4) && !first_only && win_rows > 0;
-    const uint32_t per_tile = x4 ? 32u * X4 : 32u;
-    const uint32_t n_tiles = (n_chunks + per_tile - 1) / per_tile;
+    const uint32_t n_tiles = (n_chunks + 31u) / 32u;
 
     if (!ensure_tiles(n_tiles)) return false;
 
@@ -487,8 +469,7 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     a.tile_status = d_tiles_;
     a.counters = d_counters_;
     a.first_end = d_first_;
-    if (win_rows == 0 && x4) { set_error("internal: x4 kernel chosen without a window"); return false; }
-    const unsigned warps_per_cta = (x4 ? X4_THREADS : SCAN_THREADS) / 32;
+    const unsigned warps_per_cta = SCAN_THREADS / 32;
     // Tiles are handed out by ticket, so any grid is correct.  One CTA per 32 tiles (a tile per warp) left most SMs idle
     // for mid-size inputs and long patterns (config 5: 256 MiB = 1,024 tiles of 256 KiB -> 32 of 148 SMs): spread
     // the tiles over the SMs instead, at least four per CTA so that a CTA's table staging is shared by some work.
@@ -503,15 +484,7 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
         CU_OK(cudaMemsetAsync(d_counters_, 0, 32, st));
         if (first_only) CU_OK(cudaMemsetAsync(d_first_, 0xff, n_hay * sizeof(uint32_t), st));
         CU_OK(cudaEventRecord(EV(ev_[0]), st));
-        if (x4) {
-            if (entry_bytes_ == 2) {
-                if (range_map_) ac_scan_kernel_x4<uint16_t, true><<<grid, X4_THREADS, smem_bytes, st>>>(a);
-                else ac_scan_kernel_x4<uint16_t, false><<<grid, X4_THREADS, smem_bytes, st>>>(a);
-            } else {
-                if (range_map_) ac_scan_kernel_x4<uint32_t, true><<<grid, X4_THREADS, smem_bytes, st>>>(a);
-                else ac_scan_kernel_x4<uint32_t, false><<<grid, X4_THREADS, smem_bytes, st>>>(a);
-            }
-        } else if (entry_bytes_ == 2) {
+        if (entry_bytes_ == 2) {
             if (range_map_) { if (first_only) launch_kernel<uint16_t, true, true>(a, grid, smem_bytes, st); else launch_kernel<uint16_t, true, false>(a, grid, smem_bytes, st); }
             else            { if (first_only) launch_kernel<uint16_t, false, true>(a, grid, smem_bytes, st); else launch_kernel<uint16_t, false, false>(a, grid, smem_bytes, st); }
         } else {
@@ -531,7 +504,6 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
         if (found <= events_cap_) {
             n_events_ = found; stats.events = found;
             last_density_ = (double)found / (double)total;
-            stats.ilp = x4 ? 4 : 1;
             return true;
         }
         // event buffer too small: grow to the exact need and scan again
@@ -546,14 +518,6 @@ static void launch_filter_k(const FilterArgs &fa, bool l2, unsigned grid, cudaSt
 {
     if (l2) ac_filter_kernel<W, true><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa);
     else ac_filter_kernel<W, false><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa);
-}
-
-template <int W>
-static void launch_fused_k(const FilterArgs &fa, const VerifyArgs &a, bool l2, unsigned grid, cudaStream_t st)
-{
-    // six 512-byte loads in flight per warp: 4, 6 and 8 measured the same on B200
-    if (l2) ac_filter_collect_kernel<W, true, 6><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa, a);
-    else ac_filter_collect_kernel<W, false, 6><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa, a);
 }
 
 template <typename E, int W>
@@ -639,9 +603,6 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     va.gt_slots = direct ? (const uint4 *)d_gt_slots_ : nullptr;
     va.gt_pat = d_gt_pat_;
     va.gt_log2 = direct ? gt_log2_ : 0u;
-    va.stage = nullptr;
-    va.todo = nullptr;
-    va.partial_span = (total % SPAN_BYTES) ? total / SPAN_BYTES : 0xffffffffu;
     va.items = d_items_;
     va.desc = (uint2 *)d_desc_;
     va.recs = (uint2 *)d_recs_;
@@ -649,38 +610,8 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     va.tile_off = vtile_len + verify_tiles_cap_;
     va.block_sum = vblock_sum;
 
-    // A stream can be cut into parts: while ac_filter_kernel streams part p+1, the collect and walk kernels of
-    // part p run on a second stream; offsets and emit run once, after everything.  Measured on B200 this does
-    // NOT pay (1 GiB: 0.42 ms in one part, 0.45 / 0.58 / 0.59 ms in 2 / 4 / 8): resident walk CTAs delay the
-    // next filter launch's 1,024-thread, 220 KB CTAs.  One part unless asked otherwise (acb200_set_parts).
-    const uint32_t n_parts = tune_parts ? std::min<uint32_t>(tune_parts, 8u) : 1u;
-    const uint32_t part_tiles = ((n_tiles + n_parts - 1) / n_parts + 31u) & ~31u;
-    cudaStream_t st2 = st;
-    if (n_parts > 1) {
-        if (!verify_stream_) {
-            cudaStream_t vs;
-            CU_OK(cudaStreamCreateWithFlags(&vs, cudaStreamNonBlocking));
-            verify_stream_ = vs;
-            for (auto &e : ev_part_) { cudaEvent_t x; CU_OK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming)); e = x; }
-        }
-        st2 = S(verify_stream_);
-    }
-    // tune_direct: 0 / 1 filter, collect and walk kernels, flagged words settled by one comparison inside ac_walk_kernel
-    // where the gram table allows (the default: best measured); -1 every flagged word walked; 2 the fused path: ONE
-    // pass filters the haystack, builds the item lists and stages every flagged word's window
-    // (ac_filter_collect_kernel), ac_walk_kernel settles the items from the staged windows.  Measured on B200
-    // (1 GiB config 2, 1.57 M flagged words) the fused pass takes 0.256 ms against 0.205 + 0.017 ms for filter +
-    // collect, and the slot-indexed walk 0.22 ms against 0.105 ms: opt-in until that kernel is rebuilt.
-    const bool fused = direct && tune_direct == 2 && n_parts == 1;
-    stats.fused = fused ? 1u : 0u;
-    if (fused && stage_tiles_cap_ < verify_tiles_cap_) {
-        cudaFree(d_stage_); d_stage_ = nullptr; stage_tiles_cap_ = 0;
-        cudaFree(d_todo_); d_todo_ = nullptr;
-        CU_OK(cudaMalloc(&d_stage_, verify_tiles_cap_ * VER_DENSE_MAX * (size_t)STAGE_BYTES));
-        CU_OK(cudaMemset(d_stage_, 0, verify_tiles_cap_ * VER_DENSE_MAX * (size_t)STAGE_BYTES));   // unused slots are read (and ignored)
-        CU_OK(cudaMalloc(&d_todo_, verify_tiles_cap_ * VER_DENSE_MAX * sizeof(uint32_t)));
-        stage_tiles_cap_ = verify_tiles_cap_;
-    }
+    // tune_direct: 0 / 1 flagged words are settled by one comparison inside ac_walk_kernel where the gram table allows;
+    // -1 every flagged word is walked.
     const unsigned warps_per_cta = SCAN_THREADS / 32;
     const unsigned tiles_per_cta = COLLECT_THREADS / 32;
     // grid-stride kernels, measured on B200: 8 / 12 / 16 / 24 / 40 CTAs per SM for the walk give 0.108 / 0.106 / 0.102 /
@@ -699,72 +630,32 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
             a.capacity = (uint32_t)std::min<size_t>(async_cap_, 0xffffffffu);
         }
         // counters, block sums and events per tile (the walk kernel adds to both) are adjacent: one memset
-        if (!fused || attempt == 0)
-            CU_OK(cudaMemsetAsync(vcounters, 0, (size_t)((vtile_len - vcounters) + n_tiles) * sizeof(uint32_t), st));
+        CU_OK(cudaMemsetAsync(vcounters, 0, (size_t)((vtile_len - vcounters) + n_tiles) * sizeof(uint32_t), st));
         CU_OK(cudaEventRecord(EV(ev_[0]), st));
-        if (fused) {
-            // (after a regrow of the event buffer the items, records and per-tile counts are still valid: only
-            // the offsets + emit kernels run again)
-            if (attempt == 0) {
-                va.tile_begin = 0; va.tile_end = n_tiles;
-                va.item_base = 0;
-                va.counter_slot = 8u;
-                va.stage = (uint4 *)d_stage_;
-                const unsigned grid_f = std::min<uint32_t>((n_tiles + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
-                if (W == 8) launch_fused_k<8>(fa, va, d_l2_ != nullptr, grid_f, st);
-                else launch_fused_k<4>(fa, va, d_l2_ != nullptr, grid_f, st);
-            }
-            CU_OK(cudaEventRecord(EV(ev_[4]), st));
-            if (attempt == 0) {
-                va.todo = d_todo_;
-                const unsigned grid_s = (n_tiles + SETTLE_THREADS / 32 - 1) / (SETTLE_THREADS / 32);
-                if (W == 8) ac_settle_kernel<8><<<grid_s, SETTLE_THREADS, 0, st>>>(va);
-                else ac_settle_kernel<4><<<grid_s, SETTLE_THREADS, 0, st>>>(va);
-                if (entry_bytes_ == 2) {
-                    if (W == 8) launch_walk_k<uint16_t, 8>(va, range_map_, grid_w, st);
-                    else launch_walk_k<uint16_t, 4>(va, range_map_, grid_w, st);
-                } else {
-                    if (W == 8) launch_walk_k<uint32_t, 8>(va, range_map_, grid_w, st);
-                    else launch_walk_k<uint32_t, 4>(va, range_map_, grid_w, st);
-                }
-                stats.kernel_launches += 3;
-            }
-        } else
-        for (uint32_t p = 0; p < n_parts; ++p) {
-            const uint32_t t0 = std::min(p * part_tiles, n_tiles), t1 = std::min(t0 + part_tiles, n_tiles);
-            if (t0 == t1) continue;
-            if (attempt == 0) {      // the bit planes survive a regrow of the event buffer
-                fa.span_begin = t0 * 32u;
-                fa.span_end = std::min(t1 * 32u, n_spans);
-                const unsigned grid_f = std::min<uint32_t>((fa.span_end - fa.span_begin + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
-                if (W == 8) launch_filter_k<8>(fa, d_l2_ != nullptr, grid_f, st);
-                else launch_filter_k<4>(fa, d_l2_ != nullptr, grid_f, st);
-                stats.kernel_launches += 1;
-            }
-            if (p == n_parts - 1) CU_OK(cudaEventRecord(EV(ev_[4]), st));      // the last filter launch is done
-            if (n_parts > 1) {
-                CU_OK(cudaEventRecord(EV(ev_part_[p]), st));
-                CU_OK(cudaStreamWaitEvent(st2, EV(ev_part_[p]), 0));
-            }
-            va.tile_begin = t0; va.tile_end = t1;
-            va.item_base = t0 * VER_DENSE_MAX;
-            va.counter_slot = 8u + p;
-            va.want_end_state = (n_hay == 1 && p == n_parts - 1) ? 1u : 0u;
-            const unsigned grid_c = std::min<uint32_t>((t1 - t0 + tiles_per_cta - 1) / tiles_per_cta, (uint32_t)n_sms_ * 2u);
-            if (W == 8) ac_collect_kernel<8><<<grid_c, COLLECT_THREADS, 0, st2>>>(va);
-            else ac_collect_kernel<4><<<grid_c, COLLECT_THREADS, 0, st2>>>(va);
+        if (attempt == 0) {      // the bit planes survive a regrow of the event buffer
+            fa.span_begin = 0;
+            fa.span_end = n_spans;
+            const unsigned grid_f = std::min<uint32_t>((n_spans + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
+            if (W == 8) launch_filter_k<8>(fa, d_l2_ != nullptr, grid_f, st);
+            else launch_filter_k<4>(fa, d_l2_ != nullptr, grid_f, st);
+            stats.kernel_launches += 1;
+        }
+        CU_OK(cudaEventRecord(EV(ev_[4]), st));
+        va.tile_begin = 0; va.tile_end = n_tiles;
+        va.item_base = 0;
+        va.counter_slot = 8u;
+        {
+            const unsigned grid_c = std::min<uint32_t>((n_tiles + tiles_per_cta - 1) / tiles_per_cta, (uint32_t)n_sms_ * 2u);
+            if (W == 8) ac_collect_kernel<8><<<grid_c, COLLECT_THREADS, 0, st>>>(va);
+            else ac_collect_kernel<4><<<grid_c, COLLECT_THREADS, 0, st>>>(va);
             if (entry_bytes_ == 2) {
-                if (W == 8) launch_walk_k<uint16_t, 8>(va, range_map_, grid_w, st2);
-                else launch_walk_k<uint16_t, 4>(va, range_map_, grid_w, st2);
+                if (W == 8) launch_walk_k<uint16_t, 8>(va, range_map_, grid_w, st);
+                else launch_walk_k<uint16_t, 4>(va, range_map_, grid_w, st);
             } else {
-                if (W == 8) launch_walk_k<uint32_t, 8>(va, range_map_, grid_w, st2);
-                else launch_walk_k<uint32_t, 4>(va, range_map_, grid_w, st2);
+                if (W == 8) launch_walk_k<uint32_t, 8>(va, range_map_, grid_w, st);
+                else launch_walk_k<uint32_t, 4>(va, range_map_, grid_w, st);
             }
             stats.kernel_launches += 2;
-        }
-        if (n_parts > 1) {
-            CU_OK(cudaEventRecord(EV(ev_part_[8]), st2));
-            CU_OK(cudaStreamWaitEvent(st, EV(ev_part_[8]), 0));
         }
         CU_OK(cudaEventRecord(EV(ev_[5]), st));
         ac_offsets_kernel<<<grid_e, EMIT_THREADS, 0, st>>>(va);
@@ -802,7 +693,6 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
             n_events_ = found; stats.events = found;
             last_density_ = (double)found / (double)total;
             last_dense_frac_ = (double)stats.dense_tiles / (double)n_tiles;
-            stats.ilp = 1;
             return true;
         }
         if (!ensure_events(found + found / 16 + 1024)) return false;
@@ -935,7 +825,6 @@ void Engine::async_finish(size_t n_events, size_t dense_tiles)
     last_density_ = stats.bytes ? (double)n_events / (double)stats.bytes : 0.0;
     stats.dense_tiles = dense_tiles;
     if (async_tiles_) last_dense_frac_ = (double)dense_tiles / (double)async_tiles_;      // feeds the automatic kernel choice
-    stats.ilp = 1;
 }
 
 bool Engine::slab_upload_async(int buf, const char *bytes, size_t n_bytes)

@@ -64,11 +64,9 @@ public:
     ACB200_INFO_t info{};
     uint32_t tune_chunk = 0;
     uint32_t tune_smem_bytes = 0;
-    int tune_ilp = 0;              // 0 auto, 1 one slice per lane, 4 four slices per lane
     int tune_filter = 0;           // 0 auto, 1 always use the gram prefilter when the dictionary allows, -1 never
-    int tune_direct = 0;           // 0 auto (= 1), 1 direct verification of flagged words inside the walk kernel, 2 fused
-                                   // filter + collect pass that stages the windows (opt-in), -1 every flagged word is walked
-    uint32_t tune_parts = 0;       // 0 auto; parts a filtered scan is cut into (filter of part p+1 overlaps verification of part p)
+    int tune_direct = 0;           // 0 auto (= 1), 1 direct verification of flagged words inside the walk kernel,
+                                   // -1 every flagged word is walked
 
 private:
     bool ensure_text(size_t bytes);
@@ -115,9 +113,6 @@ private:
     uint32_t *d_gt_pat_ = nullptr;
     uint32_t gt_log2_ = 0;
     uint32_t *d_mask_ = nullptr;  size_t mask_cap_ = 0;
-    void *d_stage_ = nullptr;       // fused path: per item slot the 48 bytes around the flagged word (allocated on first use)
-    uint32_t *d_todo_ = nullptr;    // fused path: slots of the items left to ac_walk_kernel
-    size_t stage_tiles_cap_ = 0;
     uint32_t *d_items_ = nullptr;   // work items of the verify kernels
     uint32_t *d_recs_ = nullptr;    // per item {first event state, count << 16 | relative end}
     uint32_t *d_desc_ = nullptr;    // per 16 KiB tile {offset into items, count}
@@ -137,8 +132,6 @@ private:
     uint8_t *h_stage_ = nullptr;  size_t stage_cap_ = 0;          // pinned staging for pageable input
     uint8_t *d_slab_[2] = {nullptr, nullptr}; size_t slab_cap_[2] = {0, 0};   // double-buffered haystack slabs
     void *copy_stream_ = nullptr;                                  // cudaStream_t of the slab uploads
-    void *verify_stream_ = nullptr;                                // cudaStream_t of the collect / walk kernels of a multi-part scan
-    void *ev_part_[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void *ev_slab_[4] = {nullptr, nullptr, nullptr, nullptr};     // per buffer: upload started / finished
     std::vector<uint32_t> off32_;
 

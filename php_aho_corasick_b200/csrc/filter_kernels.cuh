@@ -202,11 +202,6 @@ struct VerifyArgs {
     const uint4 *gt_slots;        // exact gram table (gram_table.hpp) or nullptr
     const uint32_t *gt_pat;       // its pattern store
     uint32_t gt_log2;             // 2^gt_log2 slots; 0: every flagged word is walked
-    uint4 *stage;                 // fused path: per item slot the three 16-byte chunks around the flagged word (ac_filter_collect_kernel
-                                  // writes, ac_settle_kernel reads)
-    uint32_t *todo;               // fused path: slots of the items ac_settle_kernel left to ac_walk_kernel (count in
-                                  // counters[counter_slot]); nullptr: ac_walk_kernel takes the dense list of ac_collect_kernel
-    uint32_t partial_span;        // index of the stream's last, partial span (never staged) or 0xffffffff
     uint32_t *items;              // work items, tile runs in completion order (capacity n_tiles * VER_DENSE_MAX)
     uint2 *desc;                  // per tile {offset into items, count}
     uint2 *recs;                  // per item {state of the first event, count << 16 | first end - item origin}
@@ -494,8 +489,6 @@ __device__ __forceinline__ bool verify_word_direct(const VerifyArgs &a, uint32_t
     return verify_word_direct<W>(a, rs, hay_begin, [text](uint32_t i) { return group_chunk<W>(ld_group<W>(text, i)); }, ev);
 }
 
-constexpr uint32_t STAGE_BYTES = 48;       // per work item: the three 16-byte chunks around the flagged word
-
 // origin of an item's end offsets: a record stores its first event's end relative to this
 template <int W>
 __device__ __forceinline__ uint32_t item_origin(uint32_t item)
@@ -524,7 +517,7 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
     st.ncls = a.s.ncls; st.lo = a.s.range_lo; st.n_used = a.s.n_used;
     st.final_bound = a.s.final_bound; st.root = a.s.root;
 
-    // the dense list ac_collect_kernel made, or (fused path) the todo list of ac_settle_kernel
+    // the dense list ac_collect_kernel made
     const uint32_t n_items = a.s.counters[a.counter_slot];
     const uint32_t n_threads = gridDim.x * WALK_THREADS;
     constexpr int K = WALK_ILP;
@@ -537,7 +530,6 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
         for (int k = 0; k < K; ++k) {
             slot[k] = a.item_base + i0 + k;
             valid[k] = i0 + k < n_items;
-            if (a.todo && valid[k]) slot[k] = a.todo[i0 + k];
             item[k] = valid[k] ? a.items[slot[k]] : ITEM_NONE;
             rs[k] = 0; w0[k] = 0; lock[k] = false;
             if (item[k] != ITEM_NONE && !(item[k] & ITEM_SPAN)) {
@@ -620,221 +612,6 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
         const uint32_t back = a.s.halo + 1u;
         const uint32_t ws = (a.s.total > back) ? ((a.s.total - back) & ~(uint32_t)(W - 1)) : 0u;
         a.s.counters[2] = walk_item_slow<E, RANGE, W, false>(a.s, s_cls_addr, ITEM_NONE, ws, 0xffffffffu, a.s.total, 0u).e0s;
-    }
-}
-
-// ------------------------------------------------------- fused filter -----
-
-// ac_filter_kernel + ac_collect_kernel in ONE pass, one warp per 16 KiB tile and no CTA-wide barrier after the
-// bitmap is staged: a warp streams its tile (FUSED_UNROLL 512-byte loads in flight), keeps the flag bits of span
-// l in lane l and turns them into the tile's ordered item list (a tile owns VER_DENSE_MAX slots: no atomics).
-// While a flagged word's 16-byte chunk and its two neighbours are still in registers they are copied to the
-// item's stage record, so that ac_walk_kernel finds the word's verification window in a dense, sequentially
-// written buffer instead of re-reading the haystack around every flagged word (one random DRAM access per item,
-// which is what bounds it).  No bit planes are written.
-template <int W, bool L2, int FUSED_UNROLL>
-__global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_collect_kernel(const FilterArgs fa, const __grid_constant__ VerifyArgs a)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *s_bm = reinterpret_cast<uint32_t *>(smem_raw);
-    constexpr int NB = 16 / W;
-    constexpr uint32_t WORDS_PER_SPAN = 32u * NB;
-
-    const uint32_t tid = threadIdx.x;
-    const uint32_t lane = tid & 31u;
-    const uint32_t s_base = stage_bitmap(fa, s_bm, tid);
-    auto test = [&](uint32_t lo, uint32_t hi, uint32_t nb, bool maybe_unknown) -> bool {
-        return test_word<L2>(fa, s_base, lo, hi, nb, maybe_unknown);
-    };
-    // flag bits of one 16-byte chunk per lane: plane j bit c <=> word j of lane c
-    auto test_chunk = [&](const uint4 &v, bool chunk_known, bool next_known, bool force, uint32_t (&plane)[NB]) {
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        uint32_t after = __shfl_down_sync(0xffffffffu, w[0], 1) & 0xffu;
-        if (lane == 31u || !next_known) after = FILTER_NEXT_UNKNOWN;     // the next chunk is not in this warp's registers
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            const uint32_t nb = (j == NB - 1) ? after : (((W == 8) ? w[2] : w[j + 1]) & 0xffu);
-            bool p = (W == 8) ? test(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test(w[j], 0u, nb, j == NB - 1);
-            p = chunk_known ? p : force;
-            plane[j] = __ballot_sync(0xffffffffu, p);
-        }
-    };
-
-    const uint32_t n_full_all = fa.total / SPAN_BYTES;       // spans that lie completely inside the stream
-    const uint32_t n_warps = gridDim.x * (SCAN_THREADS / 32);
-    uint32_t flagged = 0, dense_tiles = 0;
-
-    for (uint32_t tile = blockIdx.x * (SCAN_THREADS / 32) + (tid >> 5); tile < a.n_tiles; tile += n_warps) {
-        const uint32_t span0 = tile * 32u;
-        const uint32_t base = tile * VER_DENSE_MAX;
-        const uint32_t n_here = min(32u, n_full_all > span0 ? n_full_all - span0 : 0u);   // complete spans of this tile
-        uint32_t pl[NB];
-#pragma unroll
-        for (int j = 0; j < NB; ++j) pl[j] = 0;
-        uint32_t n_arr = 0;                                   // flagged words of the tile so far (warp-uniform) = next item slot
-
-        for (uint32_t s0 = 0; s0 < n_here; s0 += FUSED_UNROLL) {
-            uint4 v[FUSED_UNROLL];
-#pragma unroll
-            for (int u = 0; u < FUSED_UNROLL; ++u) {
-                v[u] = make_uint4(0, 0, 0, 0);
-                if (s0 + u < n_here) v[u] = ld_text16(fa.text + ((size_t)(span0 + s0 + u) * 32u + lane) * 16u);
-            }
-#pragma unroll
-            for (int u = 0; u < FUSED_UNROLL; ++u) {
-                if (s0 + u >= n_here) break;                  // warp-uniform
-                uint32_t plane[NB];
-                test_chunk(v[u], true, true, false, plane);
-                uint32_t m = 0;
-#pragma unroll
-                for (int j = 0; j < NB; ++j) {
-                    if (lane == s0 + u) pl[j] = plane[j];
-                    m |= plane[j];
-                }
-                // stage the chunks around every flagged word, in ascending stream order = item order (warp-uniform loop)
-                while (m) {
-                    const uint32_t ch = __ffs(m) - 1;
-                    m &= m - 1;
-#pragma unroll
-                    for (int j = 0; j < NB; ++j) {
-                        if (!((plane[j] >> ch) & 1u)) continue;
-                        const uint32_t rel = lane + 1u - ch;  // lanes ch-1, ch, ch+1 hold parts 0, 1, 2 of the record
-                        if (n_arr < VER_DENSE_MAX && rel < 3u)
-                            a.stage[(size_t)(base + n_arr) * 3u + rel] = v[u];
-                        ++n_arr;
-                    }
-                }
-            }
-        }
-        // The last, partial span of the stream: complete 16-byte chunks are tested, the partial chunk at the very
-        // end is not read at all — its words are simply handed on to verification (nothing staged: they are walked).
-        if (n_full_all < a.n_spans && n_full_all >= span0 && n_full_all < span0 + 32u) {
-            const uint32_t n16 = fa.total >> 4;
-            const uint32_t c = n_full_all * 32u + lane;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (c < n16) v = ld_text16(fa.text + (size_t)c * 16u);
-            const bool tail = (fa.total & 15u) && c == n16;
-            uint32_t plane[NB];
-            test_chunk(v, c < n16, c + 1u < n16, tail, plane);
-#pragma unroll
-            for (int j = 0; j < NB; ++j)
-                if (lane == n_full_all - span0) pl[j] = plane[j];
-        }
-
-        // ---- the tile's ordered item list (what ac_collect_kernel does, warp-local)
-        const uint32_t span = span0 + lane;
-        const bool active = span < a.n_spans;
-        uint32_t cnt = 0;
-#pragma unroll
-        for (int j = 0; j < NB; ++j) cnt += __popc(pl[j]);
-        flagged += cnt;
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        const uint32_t n_cand = __shfl_sync(0xffffffffu, incl, 31);
-        const bool dense = n_cand > a.dense_max;            // cheaper to walk the whole tile
-        const uint32_t n_act = __popc(__ballot_sync(0xffffffffu, active));
-        const uint32_t n = dense ? n_act : n_cand;
-        if (lane == 0) a.desc[tile] = make_uint2(base, n);
-        if (n == 0) continue;                                 // warp-uniform
-        if (dense) {
-            if (lane == 0) ++dense_tiles;
-            if (active) a.items[base + lane] = ITEM_SPAN | span;
-        } else if (cnt) {
-            uint32_t at = base + incl - cnt;
-            uint32_t any = 0;
-#pragma unroll
-            for (int j = 0; j < NB; ++j) any |= pl[j];
-            while (any) {
-                const uint32_t ch = __ffs(any) - 1;
-                any &= any - 1;
-#pragma unroll
-                for (int j = 0; j < NB; ++j)
-                    if ((pl[j] >> ch) & 1u) a.items[at++] = span * WORDS_PER_SPAN + ch * NB + j;
-            }
-        }
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) flagged += __shfl_xor_sync(0xffffffffu, flagged, d);
-    if (lane == 0 && flagged) atomicAdd(&a.s.counters[3], flagged);
-    if (lane == 0 && dense_tiles) atomicAdd(&a.s.counters[4], dense_tiles);
-}
-
-// Fused path, second kernel: one warp per tile settles the tile's items from their staged windows — one probe of
-// the gram table and one comparison each (gram_table.hpp), no haystack access for patterns of up to 2W bytes.
-// Every load whose address depends only on (tile, lane) is issued before anything is looked at, so a tile costs
-// two dependent memory round trips.  Items that need the automaton (shared grams, failure-target patterns,
-// windows clipped by the ends of the stream or straddling a haystack end, spans of densely flagged tiles) are
-// appended to `todo` for ac_walk_kernel.  Writes the records, the events per tile and per block of tiles.
-constexpr int SETTLE_THREADS = 256;
-
-template <int W>
-__global__ void __launch_bounds__(SETTLE_THREADS) ac_settle_kernel(const __grid_constant__ VerifyArgs a)
-{
-    constexpr uint32_t NB = 16u / W;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t tile = blockIdx.x * (SETTLE_THREADS / 32) + (threadIdx.x >> 5);
-    if (tile >= a.n_tiles) return;
-    const uint2 d = __ldg(a.desc + tile);                     // {tile * VER_DENSE_MAX, items}
-    uint32_t tile_events = 0;
-    for (uint32_t i0 = 0; i0 < VER_DENSE_MAX; i0 += 32u) {    // the second half is rare
-        if (i0 && i0 >= d.y) break;                           // warp-uniform
-        const uint32_t slot = tile * VER_DENSE_MAX + i0 + lane;
-        const uint32_t item = __ldg(a.items + slot);
-        // bytes [8, 40) of the 48-byte record hold the window [rs - 2W, rs + W) of every word of the middle chunk
-        const uint2 *rec = reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(a.stage) + (size_t)slot * STAGE_BYTES + 8u);
-        const uint2 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), r3 = __ldg(rec + 3);
-        const bool have = i0 + lane < d.y;
-        bool undecided = false;
-        ItemEvents ev{0u, 0u, 0u};
-        if (have) {
-            undecided = true;
-            const uint32_t rs = (item + 1u) * W;             // the W end offsets owned by the word are rs+1 .. rs+W
-            if (!(item & ITEM_SPAN) && a.gt_log2 && rs >= a.warm && rs + W <= a.s.total && item / (32u * NB) != a.partial_span) {
-                const uint32_t h = find_haystack(a.s, rs);
-                if (hay_end(a.s, h) >= rs + W) {             // a window clipped by the haystack START is fine: the candidate must fit
-                    uint2 g0, g1, g2;
-                    const uint32_t j = item % NB;
-                    if (W == 8) {
-                        g0 = j ? r1 : r0; g1 = j ? r2 : r1; g2 = j ? r3 : r2;
-                    } else {                                  // 32-bit groups at record bytes 12 + 4j, 16 + 4j, 20 + 4j
-                        const uint32_t w[6] = {r0.y, r1.x, r1.y, r2.x, r2.y, r3.x};
-                        g0 = make_uint2(j == 0 ? w[0] : j == 1 ? w[1] : j == 2 ? w[2] : w[3], 0u);
-                        g1 = make_uint2(j == 0 ? w[1] : j == 1 ? w[2] : j == 2 ? w[3] : w[4], 0u);
-                        g2 = make_uint2(j == 0 ? w[2] : j == 1 ? w[3] : j == 2 ? w[4] : w[5], 0u);
-                    }
-                    // the neighbours of a span's first / last word were not in the filter's registers: from the haystack
-                    const uint32_t in_span = item % (32u * NB);
-                    const uint8_t *text = a.s.text;
-                    if (in_span == 0u) g0 = ld_group<W>(text, rs - 2u * W);
-                    if (in_span == 32u * NB - 1u) g2 = ld_group<W>(text, rs);
-                    undecided = !verify_word_direct<W>(a, rs, hay_begin(a.s, h), [=](uint32_t i) {
-                        return group_chunk<W>((i == rs) ? g2 : (i == rs - W) ? g1 : (i == rs - 2u * W) ? g0 : ld_group<W>(text, i)); }, ev);
-                }
-            }
-            if (!undecided) {
-                const uint32_t rel = ev.cnt ? ev.e0p - rs : 0u;
-                a.recs[slot] = make_uint2(ev.e0s, (ev.cnt << 16) | (rel & 0xffffu));
-            }
-        }
-        const uint32_t um = __ballot_sync(0xffffffffu, undecided);
-        if (um) {
-            uint32_t t0 = 0;
-            if (lane == 0) t0 = atomicAdd(&a.s.counters[a.counter_slot], (uint32_t)__popc(um));
-            t0 = __shfl_sync(0xffffffffu, t0, 0);
-            if (undecided) a.todo[t0 + __popc(um & ((1u << lane) - 1u))] = slot;
-        }
-        uint32_t sum = ev.cnt;
-#pragma unroll
-        for (int k = 16; k > 0; k >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, k);
-        tile_events += sum;
-    }
-    if (tile_events && lane == 0) {
-        a.tile_len[tile] = tile_events;                       // ac_walk_kernel adds the events of the todo items
-        atomicAdd(&a.block_sum[tile / EMIT_THREADS], tile_events);
     }
 }
 

@@ -60,10 +60,9 @@ class Info(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("bytes", C.c_uint64), ("events", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("chunk_bytes", C.c_uint32), ("halo_bytes", C.c_uint32), ("kernel_ms", C.c_float),
-                ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("ilp", C.c_uint32), ("filtered", C.c_uint32),
+                ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("devices", C.c_uint32), ("filtered", C.c_uint32),
                 ("filter_ms", C.c_float), ("verify_ms", C.c_float), ("flagged_words", C.c_uint64),
-                ("dense_tiles", C.c_uint64), ("reorder_ms", C.c_float), ("expand_ms", C.c_float),
-                ("fused", C.c_uint32)]
+                ("dense_tiles", C.c_uint64), ("reorder_ms", C.c_float), ("expand_ms", C.c_float)]
 
 
 MATCH_CB = C.CFUNCTYPE(C.c_int, C.POINTER(AcMatch), C.c_void_p)
@@ -75,8 +74,8 @@ EXPORTS = [
     "ac_trie_search_batch", "ac_trie_search_flat", "acb200_search_events", "acb200_search_device",
     "acb200_state_patterns", "acb200_info", "acb200_last_stats", "acb200_last_error",
     "acb200_set_device", "acb200_device_count", "acb200_host_alloc", "acb200_host_free",
-    "acb200_set_tuning", "acb200_version", "acb200_copy_events", "acb200_tally_cb", "acb200_tally_match_cb", "acb200_set_ilp",
-    "acb200_set_filter", "acb200_search_device_uniform", "acb200_set_parts", "acb200_search_hits", "acb200_pattern", "acb200_save", "acb200_load", "acb200_filter_probe",
+    "acb200_set_tuning", "acb200_version", "acb200_copy_events", "acb200_tally_cb", "acb200_tally_match_cb",
+    "acb200_set_filter", "acb200_search_device_uniform", "acb200_search_hits", "acb200_pattern", "acb200_save", "acb200_load", "acb200_filter_probe",
     "acb200_set_direct", "acb200_direct_probe", "acb200_search_device_uniform_async", "acb200_async_finish",
 ]
 
@@ -124,9 +123,7 @@ def lib() -> C.CDLL:
     L.acb200_host_free.restype = None
     L.acb200_set_tuning.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
     L.acb200_version.restype = C.c_char_p
-    L.acb200_set_ilp.argtypes = [C.c_void_p, C.c_int]
     L.acb200_set_filter.argtypes = [C.c_void_p, C.c_int]
-    L.acb200_set_parts.argtypes = [C.c_void_p, C.c_uint]
     L.acb200_search_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.acb200_search_hits.restype = C.c_int
     L.acb200_pattern.argtypes = [C.c_void_p, C.c_size_t]
@@ -208,10 +205,8 @@ class Automaton:
         if inf.device < 0:
             raise AcError("finalize did not reach the GPU: " + last_error())
 
-    def set_tuning(self, chunk_bytes: int = 0, smem_table_bytes: int = 0, ilp: int | None = None) -> None:
+    def set_tuning(self, chunk_bytes: int = 0, smem_table_bytes: int = 0) -> None:
         self.L.acb200_set_tuning(self.h, int(chunk_bytes), int(smem_table_bytes))
-        if ilp is not None:
-            self.L.acb200_set_ilp(self.h, int(ilp))
 
     def save(self, path: str) -> None:
         if self.L.acb200_save(self.h, os.fsencode(path)) != 0:
@@ -237,8 +232,7 @@ class Automaton:
         return int(self.L.acb200_filter_probe(self.h, int(word), int(next_byte)))
 
     def set_direct(self, mode: int) -> None:
-        """0 automatic (= 1), 1 flagged words settled by one comparison inside the walk kernel, 2 fused filter + collect
-        pass with staged windows (opt-in), -1 every flagged word is walked"""
+        """0 automatic (= 1), 1 flagged words settled by one comparison inside the walk kernel, -1 every flagged word is walked"""
         self.L.acb200_set_direct(self.h, int(mode))
 
     def direct_probe(self, text: bytes, word_index: int, hay_begin: int = 0):
@@ -246,10 +240,6 @@ class Automaton:
         e, s = C.c_uint32(0), C.c_uint32(0)
         v = int(self.L.acb200_direct_probe(self.h, text, len(text), int(hay_begin), int(word_index), C.byref(e), C.byref(s)))
         return v, int(e.value), int(s.value)
-
-    def set_parts(self, parts: int) -> None:
-        """parts a prefiltered scan is cut into (0 automatic)"""
-        self.L.acb200_set_parts(self.h, int(parts))
 
     def set_filter(self, mode: int) -> None:
         """0 automatic, 1 prefilter whenever the dictionary allows, -1 always the full automaton walk"""

@@ -1,6 +1,6 @@
 """GPU parity of the gram-prefilter path (ac_filter_kernel, ac_collect_kernel, ac_walk_kernel with the direct
-verification of gram_table.hpp, ac_offsets_kernel, ac_emit_kernel; the opt-in fused ac_filter_collect_kernel +
-ac_settle_kernel; the asynchronous device call and the chained multi-GPU step) against the CPU oracle and against
+verification of gram_table.hpp, ac_offsets_kernel, ac_emit_kernel; the asynchronous device call and the chained
+multi-GPU step) against the CPU oracle and against
 the full automaton walk (ac_scan_kernel): same events, same order, through the C-ABI."""
 import random
 
@@ -37,7 +37,7 @@ def test_cfg2_planted_filtered_equals_oracle_and_full_walk():
     assert inf.filter_word == 8 and inf.min_pattern_len == 16
     ev = a.search_events(hay, off)
     st = a.stats()
-    assert st.filtered == 1 and st.fused == 0 and st.kernel_launches == 5 and 0 < st.flagged_words < hay.size // 8 // 10
+    assert st.filtered == 1 and st.kernel_launches == 5 and 0 < st.flagged_words < hay.size // 8 // 10
     assert_same(a, ev, 256, exp)
     a.set_filter(-1)
     ev_full = a.search_events(hay, off)
@@ -84,28 +84,7 @@ def test_random_dictionaries_both_word_sizes_ragged_batches(seed):
         assert_same(a, ev, len(lens), exp)
         a.set_filter(-1)
         assert np.array_equal(ev, a.search_events(flat, off)), (seed, trial)
-        if flat.size:                                   # the opt-in fused filter + collect pass with staged windows
-            a.set_filter(1)
-            a.set_direct(2)
-            assert np.array_equal(ev, a.search_events(flat, off)), (seed, trial)
-            assert a.stats().fused == 1
         a.release()
-
-
-@pytest.mark.parametrize("parts", [2, 5, 8])
-def test_multi_part_scans_on_two_streams_give_the_same_events(parts):
-    needles, hay, off = W.cfg2(n_hay=512, hay_len=8192, planted_per_hay=8, seed=12)
-    a = build([needles], 1)
-    ev1 = a.search_events(hay, off)
-    a.set_parts(parts)
-    ev2 = a.search_events(hay, off)
-    assert 3 * 2 + 2 <= a.stats().kernel_launches <= 3 * parts + 2      # parts are rounded to 32 tiles; empty ones are skipped
-    assert np.array_equal(ev1, ev2)
-    one = np.array([0, hay.size], dtype=np.uint64)      # one haystack: the end state is computed by the last part
-    rc, got = a.search_callback(hay[:100_000].tobytes())
-    a.set_parts(1)
-    rc1, got1 = a.search_callback(hay[:100_000].tobytes())
-    assert got == got1
 
 
 def test_find_first_through_the_prefilter_equals_the_first_only_kernel():
@@ -426,9 +405,8 @@ def test_randomised_mixtures_of_dense_and_sparse_regions(seed):
 
 
 def test_direct_verification_equals_walking_every_flagged_word():
-    """gram_table.hpp: flagged words settled by one comparison inside ac_walk_kernel (default) vs from windows staged by
-    the fused filter + collect pass (set_direct(2), ac_filter_collect_kernel) vs every flagged word walked
-    (set_direct(-1)) vs the full automaton walk — raw events (end offset AND state id) must be identical."""
+    """gram_table.hpp: flagged words settled by one comparison inside ac_walk_kernel (default) vs every flagged word
+    walked (set_direct(-1)) vs the full automaton walk — raw events (end offset AND state id) must be identical."""
     rng = np.random.default_rng(77)
     pyr = random.Random(77)
     cases = []
@@ -466,13 +444,12 @@ def test_direct_verification_equals_walking_every_flagged_word():
         assert inf.direct_keys > 0
         ev = a.search_events(flat, offs)
         st = a.stats()
-        assert st.filtered == 1 and st.fused == 0 and st.kernel_launches == 5 and len(ev) > 100
-        for mode in (2, -1):
-            a.set_direct(mode)
-            ev_walk = a.search_events(flat, offs)
-            st = a.stats()
-            assert st.filtered == 1 and st.fused == (1 if mode == 2 else 0) and st.kernel_launches == 5
-            assert np.array_equal(ev, ev_walk), mode
+        assert st.filtered == 1 and st.kernel_launches == 5 and len(ev) > 100
+        a.set_direct(-1)
+        ev_walk = a.search_events(flat, offs)
+        st = a.stats()
+        assert st.filtered == 1 and st.kernel_launches == 5
+        assert np.array_equal(ev, ev_walk)
         a.set_filter(-1)
         ev_full = a.search_events(flat, offs)
         assert a.stats().filtered == 0

@@ -69,25 +69,21 @@ def test_cfg2_benchmark_shape_planted():
     assert st.kernel_launches >= 1 and st.bytes == hay.size
 
 
-@pytest.mark.parametrize("ilp", [1, 4])
 @pytest.mark.parametrize("chunk,smem", [(16, 0), (48, 4096), (256, 0), (1024, 512), (4096, 0)])
-def test_slice_and_table_placement_do_not_change_results(chunk, smem, ilp):
+def test_slice_and_table_placement_do_not_change_results(chunk, smem):
     needles, hay, off = W.cfg2(n_hay=16, hay_len=3000, n_needles=300, planted_per_hay=6, seed=11)
     a = build([needles])
-    a.set_tuning(chunk, smem, ilp)
+    a.set_tuning(chunk, smem)
     ev = a.search_events(hay, off)
     assert_same(a, ev, 16, oracle_hits([needles], split(hay, off)))
 
 
-@pytest.mark.parametrize("ilp", [1, 4])
 @pytest.mark.parametrize("planted", [0, 1, 8])
-def test_lockstep_kernel_on_uniform_batches(ilp, planted):
+def test_full_walk_on_uniform_batches(planted):
     # 2,048-needle dictionary (deep states fall out of the shared-memory window), 64 x 8 KiB + one long haystack
     needles, hay, off = W.cfg2(n_hay=64, hay_len=8192, planted_per_hay=planted, seed=77)
     a = build([needles])
-    a.set_tuning(0, 0, ilp)
     ev = a.search_events(hay, off)
-    assert a.stats().ilp == ilp
     assert_same(a, ev, 64, oracle_hits([needles], split(hay, off)))
     one = np.array([0, hay.size], dtype=np.uint64)          # the same bytes as ONE haystack: matches may straddle
     ev = a.search_events(hay, one)
@@ -103,8 +99,8 @@ def test_ragged_batch_with_empty_haystacks():
     off = np.zeros(len(lens) + 1, dtype=np.uint64)
     off[1:] = np.cumsum(lens)
     a = build([needles])
-    for chunk, ilp in ((0, 1), (16, 4), (64, 1), (32, 4)):
-        a.set_tuning(chunk, 0, ilp)
+    for chunk in (0, 16, 64, 32):
+        a.set_tuning(chunk, 0)
         ev = a.search_events(flat, off)
         assert_same(a, ev, len(lens), oracle_hits([needles], hays))
         ev1 = a.search_events(flat, off, first_only=True)
