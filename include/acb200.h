@@ -141,8 +141,10 @@ void ac_trie_release(AC_TRIE_t *thiz);
  * Non-zero return stops the search of THAT haystack only.                   */
 typedef int (*ACB200_BATCH_CALLBACK_f)(size_t text_idx, AC_MATCH_t *, void *);
 
-/* Searches n independent haystacks in one device launch; every haystack
+/* Searches n independent haystacks in one call; every haystack
  * starts at the root at offset 0 (the keep=0 rule of php_ahocorasick.c:745).
+ * Large batches are gathered slab by slab into pinned staging memory and
+ * pipelined over every GPU of the handle (acb200_set_devices).
  * first_only!=0 reports only the first event of each haystack
  * (php_ahocorasick.c:588 — findAll=false).  Callbacks arrive ordered by
  * (text_idx, position).  Returns 0, or -1 on error.                         */
@@ -258,6 +260,13 @@ typedef struct acb200_tally
 int acb200_tally_cb(size_t text_idx, AC_MATCH_t *m, void *tally);
 int acb200_tally_match_cb(AC_MATCH_t *m, void *tally);
 
+/* Per-haystack digest of an event list (as returned by acb200_search_events): counts[h] = events of haystack h,
+ * hashes[h] = fold over its events, in order, of (position, number of patterns, first and last pattern's aux) —
+ * the value a caller of the reference gets by folding the same fields inside its AC_MATCH_CALBACK_f, so two
+ * implementations can be compared haystack by haystack without keeping every hit.  Returns 0 / -1.          */
+int acb200_event_digest(const AC_TRIE_t *thiz, const ACB200_EVENT_t *events, size_t n_events, size_t n_texts,
+                        uint64_t *counts, uint64_t *hashes);
+
 /* Patterns reported by automaton state `state` (longest first); returns the
  * count and stores a library-owned array in *patterns (NULL if none).       */
 size_t acb200_state_patterns(const AC_TRIE_t *thiz, uint32_t state,
@@ -311,10 +320,37 @@ int acb200_last_stats(const AC_TRIE_t *thiz, ACB200_STATS_t *out);
  * The reference's void/ignored returns leave no room for CUDA errors.       */
 const char *acb200_last_error(void);
 
-/* Device selection for automata finalized afterwards by this thread
+/* Primary device of automata CREATED afterwards by this thread
  * (default: env ACB200_DEVICE, else the current CUDA device).               */
 int acb200_set_device(int device);
 int acb200_device_count(void);
+
+/* The GPUs one host call may use.  After finalize (or acb200_load) the automaton lives on its primary device
+ * (acb200_set_device at create time); this call replicates it onto the other listed devices — the expanded
+ * table is copied from the primary's HBM over NVLink — and from then on ac_trie_search, ac_trie_search_batch,
+ * ac_trie_search_flat and acb200_search_events cut large inputs into slabs spread over all of them, balanced by
+ * bytes, one pinned double-buffered H2D pipeline per GPU, events returned in the same global order as on one
+ * GPU.  A cut may fall inside a haystack (the slab then carries the Lmax-1 bytes before it), so ONE large
+ * haystack is spread as well.  The list replaces any earlier one; the primary device always takes part, and an
+ * ordinal listed k times gets k pipelines (its own scratch and streams each).
+ * Environment ACB200_DEVICES=all|0,1,... does the same at finalize for callers that cannot make this call
+ * (the PHP extension).  Returns 0 / -1.                                                                      */
+int acb200_set_devices(AC_TRIE_t *thiz, const int *devices, size_t n);
+
+/* Bytes per slab of the host pipeline (0 = default 64 MiB).  Tests use small slabs to force cuts. */
+int acb200_set_slab_bytes(AC_TRIE_t *thiz, uint64_t bytes);
+
+/* Diagnostic: the slab plan of a call (csrc/shard.hpp) evaluated on the host — no GPU involved.  Slab i reports
+ * the events that end in stream bytes (begin, end], travels with `halo` bytes in front, runs on device slot
+ * `device_slot` and touches the haystacks [first_text, end_text).                                            */
+typedef struct acb200_slab
+{
+    uint64_t begin, end;
+    uint32_t halo, device_slot;
+    uint64_t first_text, end_text;
+} ACB200_SLAB_t;
+int acb200_plan_slabs(const uint64_t *offsets, size_t n, uint32_t halo_max, int n_devices, uint64_t slab_bytes,
+                      ACB200_SLAB_t *out, size_t cap, size_t *n_slabs);
 
 /* Pinned host memory for haystacks (optional; pageable memory works too).   */
 void *acb200_host_alloc(size_t bytes);

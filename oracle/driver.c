@@ -139,23 +139,48 @@ void drv_release(drv_t *d)
 /* ---------------------------------------------------------------------- *
  * CPU baseline timing: `threads` workers, each with a PRIVATE trie replica
  * (the reference trie carries mutable search state,
- * src/multifast/ahocorasick.h:49-65), each taking a contiguous block of
- * haystacks.  Only the searches are timed (finalize excluded).  Returns the
- * wall-clock seconds of the slowest repetition-best; *events = events seen
- * in one pass.
+ * src/multifast/ahocorasick.h:49-65) that it builds and finalizes itself
+ * (side by side: the reference's finalize takes 16 s for 100 k signatures).
+ * A batch is split into contiguous blocks of haystacks; ONE large haystack
+ * is split into disjoint byte slices, each walked from the root over the
+ * `halo` = Lmax-1 bytes before it, events counted only when they end inside
+ * the slice (SURVEY.md 8d "CPU baseline").  Only the searches are timed
+ * (finalize excluded).  Returns the wall-clock seconds of the best
+ * repetition; *events = events seen in one pass.  With hay_events /
+ * hay_hash (n_hay entries each, batches only) every haystack's event count
+ * and order-sensitive hash (the fold of on_match) are stored as well.
  * ---------------------------------------------------------------------- */
 typedef struct work {
     drv_t *d;
+    const char *pat_flat; const uint64_t *pat_off; size_t n_pat;
     const char *text; const uint64_t *hay_off; size_t h0, h1;
+    uint64_t b0, b1, skip;          /* slice mode: bytes [b0, b1) of haystack 0, events ending at <= skip ignored */
+    int slice_mode;
     uint64_t events;
+    uint64_t *hay_events, *hay_hash;
     pthread_barrier_t *start, *stop;
     int reps;
 } work_t;
 
+typedef struct tally { uint64_t events, hash, skip; } tally_t;
+
 static int on_count(AC_MATCH_t *m, void *param)
 {
-    (void)m;
-    (*(uint64_t *)param)++;
+    tally_t *t = (tally_t *)param;
+    if ((uint64_t)m->position > t->skip) t->events++;
+    return 0;
+}
+
+static int on_digest(AC_MATCH_t *m, void *param)
+{
+    tally_t *t = (tally_t *)param;
+    t->events++;
+    t->hash = fold(t->hash, (uint64_t)m->position);
+    t->hash = fold(t->hash, (uint64_t)m->size);
+    if (m->size) {
+        t->hash = fold(t->hash, (uint64_t)(uintptr_t)m->patterns[0].aux);
+        t->hash = fold(t->hash, (uint64_t)(uintptr_t)m->patterns[m->size - 1].aux);
+    }
     return 0;
 }
 
@@ -164,42 +189,66 @@ static void *worker(void *arg)
     work_t *w = (work_t *)arg;
     int r;
     size_t h;
+    w->d = drv_create();
+    drv_add_php_order(w->d, w->pat_flat, w->pat_off, w->n_pat);
+    drv_finalize(w->d);
     for (r = 0; r < w->reps; r++) {
         pthread_barrier_wait(w->start);
         w->events = 0;
+        if (w->slice_mode) {
+            tally_t t = {0, 0, w->skip};
+            AC_TEXT_t x;
+            x.astring = w->text + (w->b0 - w->skip);
+            x.length = (size_t)(w->b1 - w->b0 + w->skip);
+            ac_trie_search(w->d->trie, &x, 0, on_count, &t);
+            w->events = t.events;
+        } else
         for (h = w->h0; h < w->h1; h++) {
-            AC_TEXT_t t;
-            t.astring = w->text + w->hay_off[h];
-            t.length = (size_t)(w->hay_off[h + 1] - w->hay_off[h]);
-            ac_trie_search(w->d->trie, &t, 0, on_count, &w->events);
+            tally_t t = {0, 0, 0};
+            AC_TEXT_t x;
+            x.astring = w->text + w->hay_off[h];
+            x.length = (size_t)(w->hay_off[h + 1] - w->hay_off[h]);
+            ac_trie_search(w->d->trie, &x, 0, w->hay_hash ? on_digest : on_count, &t);
+            w->events += t.events;
+            if (w->hay_events) w->hay_events[h] = t.events;
+            if (w->hay_hash) w->hay_hash[h] = t.hash;
         }
         pthread_barrier_wait(w->stop);
     }
     return NULL;
 }
 
-double drv_bench(const char *pat_flat, const uint64_t *pat_off, size_t n_pat,
-                 const char *text, const uint64_t *hay_off, size_t n_hay,
-                 int threads, int reps, uint64_t *events)
+double drv_bench2(const char *pat_flat, const uint64_t *pat_off, size_t n_pat,
+                  const char *text, const uint64_t *hay_off, size_t n_hay,
+                  int threads, int reps, uint64_t halo, uint64_t *events,
+                  uint64_t *hay_events, uint64_t *hay_hash)
 {
     pthread_t *th;
     work_t *w;
     pthread_barrier_t start, stop;
     double best = 1e30;
     int i, r;
+    const int slice_mode = (n_hay == 1 && threads > 1);
     if (threads < 1) threads = 1;
-    if ((size_t)threads > n_hay && n_hay) threads = (int)n_hay;
+    if (!slice_mode && (size_t)threads > n_hay && n_hay) threads = (int)n_hay;
     th = (pthread_t *)calloc(threads, sizeof(pthread_t));
     w = (work_t *)calloc(threads, sizeof(work_t));
     pthread_barrier_init(&start, NULL, threads + 1);
     pthread_barrier_init(&stop, NULL, threads + 1);
     for (i = 0; i < threads; i++) {
-        w[i].d = drv_create();
-        drv_add_php_order(w[i].d, pat_flat, pat_off, n_pat);
-        drv_finalize(w[i].d);
+        w[i].pat_flat = pat_flat; w[i].pat_off = pat_off; w[i].n_pat = n_pat;
         w[i].text = text; w[i].hay_off = hay_off;
         w[i].h0 = n_hay * (size_t)i / threads;
         w[i].h1 = n_hay * (size_t)(i + 1) / threads;
+        w[i].slice_mode = slice_mode;
+        if (slice_mode) {
+            const uint64_t total = hay_off[1] - hay_off[0];
+            w[i].b0 = hay_off[0] + total * (uint64_t)i / threads;
+            w[i].b1 = hay_off[0] + total * (uint64_t)(i + 1) / threads;
+            w[i].skip = (w[i].b0 - hay_off[0] < halo) ? w[i].b0 - hay_off[0] : halo;
+        }
+        w[i].hay_events = slice_mode ? NULL : hay_events;
+        w[i].hay_hash = slice_mode ? NULL : hay_hash;
         w[i].start = &start; w[i].stop = &stop; w[i].reps = reps;
         pthread_create(&th[i], NULL, worker, &w[i]);
     }
@@ -223,4 +272,11 @@ double drv_bench(const char *pat_flat, const uint64_t *pat_off, size_t n_pat,
     pthread_barrier_destroy(&stop);
     free(th); free(w);
     return best;
+}
+
+double drv_bench(const char *pat_flat, const uint64_t *pat_off, size_t n_pat,
+                 const char *text, const uint64_t *hay_off, size_t n_hay,
+                 int threads, int reps, uint64_t *events)
+{
+    return drv_bench2(pat_flat, pat_off, n_pat, text, hay_off, n_hay, threads, reps, 0, events, NULL, NULL);
 }

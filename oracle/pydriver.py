@@ -55,6 +55,9 @@ def _load(kind: str) -> C.CDLL:
     lib.drv_bench.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
                               C.c_int, C.c_int, C.POINTER(C.c_uint64)]
     lib.drv_bench.restype = C.c_double
+    lib.drv_bench2.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                               C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]
+    lib.drv_bench2.restype = C.c_double
     _LIBS[kind] = lib
     return lib
 
@@ -136,3 +139,23 @@ def bench(kind: str, patterns, haystacks_flat: np.ndarray, hay_off: np.ndarray, 
     sec = lib.drv_bench(pflat, poff.ctypes.data, len(poff) - 1, hay.ctypes.data, off.ctypes.data,
                         len(off) - 1, int(threads), int(reps), C.byref(ev))
     return float(sec), int(ev.value)
+
+
+def bench_digest(kind: str, patterns, haystacks_flat: np.ndarray, hay_off: np.ndarray, threads: int, reps: int = 1,
+                 halo: int = 0, digest: bool = True):
+    """drv_bench2: like bench(); ONE haystack is cut into per-thread slices with a `halo`-byte warm-up (halo = Lmax-1);
+    for batches `digest` also returns every haystack's event count and order-sensitive event hash.
+    -> (seconds, events, counts[u64] | None, hashes[u64] | None)"""
+    lib = _load(kind)
+    pflat, poff = flatten(list(patterns))
+    ev = C.c_uint64(0)
+    hay = np.ascontiguousarray(haystacks_flat, dtype=np.uint8)
+    off = np.ascontiguousarray(hay_off, dtype=np.uint64)
+    n = len(off) - 1
+    want = digest and n > 1
+    counts = np.zeros(n, dtype=np.uint64) if want else None
+    hashes = np.zeros(n, dtype=np.uint64) if want else None
+    sec = lib.drv_bench2(pflat, poff.ctypes.data, len(poff) - 1, hay.ctypes.data, off.ctypes.data, n, int(threads),
+                         int(reps), int(halo), C.byref(ev), counts.ctypes.data if want else None,
+                         hashes.ctypes.data if want else None)
+    return float(sec), int(ev.value), counts, hashes

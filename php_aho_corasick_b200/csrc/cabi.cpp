@@ -7,9 +7,15 @@
 // as the reference's loop would have called it
 // (src/multifast/ahocorasick.c:214-233).
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime_api.h>
@@ -18,20 +24,24 @@
 #include "automaton.hpp"
 #include "engine.hpp"
 #include "filter_hash.hpp"
+#include "shard.hpp"
 
 using namespace acb200;
 
 struct ac_trie {
     HostTrie trie;
     FlatAutomaton flat;
-    Engine engine;
+    Engine engine;             // the automaton on its primary device
+    std::vector<std::unique_ptr<Engine>> replicas;   // the same automaton on further GPUs (acb200_set_devices)
+    int device = 0;            // primary device, fixed when the handle is created
     bool open = true;          // patterns may still be added (reference: trie_open)
     bool device_ok = false;    // finalize reached the device
     uint32_t last_state = ROOT_STATE;   // keep=1 continuation (reference: last_node)
     size_t base_position = 0;  // keep=1 continuation (reference: base_position)
-    std::vector<char> gather;  // batch gather buffer
     std::vector<uint64_t> gather_off;
     std::deque<std::string> blob_arena;   // pattern bytes / string ids of an automaton loaded from a blob
+    ACB200_STATS_t stats{};    // statistics of the most recent search (summed over slabs and devices)
+    uint64_t slab_bytes = 64ull << 20;
 };
 
 static inline size_t patterns_of(const ac_trie *t, uint32_t state, const AC_PATTERN_t **p)
@@ -41,6 +51,315 @@ static inline size_t patterns_of(const ac_trie *t, uint32_t state, const AC_PATT
     const uint64_t b = t->flat.out_off[i], e = t->flat.out_off[i + 1];
     if (p) *p = t->flat.out_pat.data() + b;
     return (size_t)(e - b);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Replicas: the same finalized automaton on further GPUs of the box, so that ONE host call (one PHP process, one
+// thread — src/php_ahocorasick.c:664-746) can spread its haystacks over all of them.
+// ------------------------------------------------------------------------------------------------------------
+
+static int set_devices(ac_trie *t, const int *devices, size_t n)
+{
+    if (t->open || !t->device_ok) { set_error("automaton is not finalized"); return -1; }
+    // the primary always takes part; every further entry of the list is one more pipeline (an ordinal listed
+    // twice gets two: two pipelines on one GPU are legal, and how a one-GPU box tests this path)
+    std::vector<int> want(devices, devices + n);
+    auto self = std::find(want.begin(), want.end(), t->device);
+    if (self != want.end()) want.erase(self);
+    t->replicas.clear();
+    std::vector<std::unique_ptr<Engine>> built(want.size());
+    std::vector<std::string> errs(want.size());
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < want.size(); ++i)       // one thread per replica: the builds run side by side
+        th.emplace_back([&, i] {
+            std::unique_ptr<Engine> e(new (std::nothrow) Engine());
+            if (e && e->build(t->flat, want[i], &t->engine)) {
+                e->info.n_patterns = t->engine.info.n_patterns;
+                e->info.finalized = 1;
+                built[i] = std::move(e);
+            } else errs[i] = get_error();
+        });
+    for (auto &x : th) x.join();
+    cudaSetDevice(t->device);
+    int rc = 0;
+    for (size_t i = 0; i < want.size(); ++i) {
+        if (built[i]) t->replicas.push_back(std::move(built[i]));
+        else { set_error("replica on device " + std::to_string(want[i]) + ": " + errs[i]); rc = -1; }
+    }
+    return rc;
+}
+
+// ACB200_DEVICES=all | 0,1,2,...  — the knob a PHP deployment has (there is no INI entry in the reference either,
+// src/php_ahocorasick.c:92-95); unset: one GPU.
+static void replicate_from_env(ac_trie *t)
+{
+    const char *e = getenv("ACB200_DEVICES");
+    if (!e || !*e) return;
+    std::vector<int> devs;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return;
+    if (!strcmp(e, "all")) { for (int d = 0; d < n; ++d) devs.push_back(d); }
+    else {
+        for (const char *p = e; *p;) {
+            char *end = nullptr;
+            const long d = strtol(p, &end, 10);
+            if (end == p) break;
+            if (d >= 0 && d < n) devs.push_back((int)d);
+            p = (*end == ',') ? end + 1 : end;
+        }
+    }
+    const std::string keep = get_error();
+    if (set_devices(t, devs.data(), devs.size()) == 0) set_error(keep);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// One host call = slabs spread over the devices (shard.hpp), one worker thread per device running a double-
+// buffered pipeline (gather into pinned staging -> H2D -> kernels -> D2H of the compact events), the calling
+// thread replaying the events through the callback in global order while the workers run ahead.
+// ------------------------------------------------------------------------------------------------------------
+
+namespace {
+
+struct HaySource {
+    const char *flat = nullptr;          // haystacks laid end to end ...
+    const AC_TEXT_t *texts = nullptr;    // ... or scattered (ac_trie_search_batch: PHP strings)
+    const uint64_t *off = nullptr;       // n + 1 stream offsets
+    size_t n = 0;
+    bool pinned = false;                 // flat buffer is page-locked: slabs are DMA'd straight from it
+
+    // stream bytes [b, e) -> dst; h = a haystack that starts at or before b
+    void copy(char *dst, uint64_t b, uint64_t e, size_t h) const
+    {
+        if (flat) { memcpy(dst, flat + b, (size_t)(e - b)); return; }
+        while (h + 1 <= n && off[h + 1] <= b) ++h;
+        while (b < e) {
+            const uint64_t he = std::min(off[h + 1], e);
+            if (he > b) { memcpy(dst, texts[h].astring + (b - off[h]), (size_t)(he - b)); dst += he - b; b = he; }
+            ++h;
+        }
+    }
+};
+
+struct SlabResult {
+    std::vector<PackedEvent> ev;
+    ACB200_STATS_t st{};
+    uint32_t end_state = 0;
+    bool ready = false, ok = true;
+    std::string err;
+};
+
+struct ShardRun {
+    std::mutex m;
+    std::condition_variable cv;
+    std::vector<SlabResult> res;
+    std::atomic<bool> abort{false};
+};
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// The gather of one slab into pinned staging, cut over a few helper threads (one core copies ~10 GB/s, PCIe
+// takes 55).
+void gather_slab(const HaySource &src, char *dst, const SlabPlan &p, int helpers)
+{
+    const uint64_t b = p.b0 - p.halo, e = p.b1;
+    const uint64_t len = e - b;
+    if (helpers <= 1 || len < (8u << 20)) { src.copy(dst, b, e, p.h_first); return; }
+    std::vector<std::thread> th;
+    const uint64_t part = (len + helpers - 1) / helpers;
+    for (int k = 1; k < helpers; ++k) {
+        const uint64_t pb = b + part * k, pe = std::min(e, pb + part);
+        if (pb >= pe) break;
+        th.emplace_back([&src, dst, b, pb, pe, &p] { src.copy(dst + (pb - b), pb, pe, p.h_first); });
+    }
+    src.copy(dst, b, std::min(e, b + part), p.h_first);
+    for (auto &x : th) x.join();
+}
+
+void add_stats(ACB200_STATS_t &sum, const ACB200_STATS_t &s)
+{
+    sum.bytes += s.bytes; sum.events += s.events; sum.kernel_launches += s.kernel_launches;
+    sum.kernel_ms += s.kernel_ms; sum.filter_ms += s.filter_ms; sum.verify_ms += s.verify_ms;
+    sum.reorder_ms += s.reorder_ms; sum.d2h_ms += s.d2h_ms; sum.h2d_ms += s.h2d_ms;
+    sum.flagged_words += s.flagged_words; sum.dense_tiles += s.dense_tiles;
+    sum.chunk_bytes = s.chunk_bytes; sum.halo_bytes = s.halo_bytes; sum.filtered = s.filtered;
+}
+
+void shard_worker(Engine *eng, const HaySource &src, const std::vector<SlabPlan> &plans, const std::vector<size_t> &mine,
+                  bool first_only, uint32_t init_state, int helpers, ShardRun &run)
+{
+    std::vector<uint64_t> rel;
+    auto fail = [&](size_t from) {
+        const std::string err = get_error();
+        std::lock_guard<std::mutex> g(run.m);
+        for (size_t k = from; k < mine.size(); ++k) { run.res[mine[k]].ok = false; run.res[mine[k]].err = err; run.res[mine[k]].ready = true; }
+        run.cv.notify_all();
+    };
+    auto prepare = [&](size_t k) -> bool {
+        const SlabPlan &p = plans[mine[k]];
+        const size_t n_bytes = (size_t)(p.halo + (p.b1 - p.b0));
+        const int buf = (int)(k & 1);
+        const char *from;
+        if (src.pinned) from = src.flat + (p.b0 - p.halo);
+        else {
+            char *stage = eng->slab_staging(buf, n_bytes);
+            if (!stage) return false;
+            gather_slab(src, stage, p, helpers);
+            from = stage;
+        }
+        return eng->slab_upload_async(buf, from, n_bytes);
+    };
+    if (mine.empty()) return;
+    if (!prepare(0)) { fail(0); return; }
+    for (size_t k = 0; k < mine.size(); ++k) {
+        if (run.abort.load(std::memory_order_relaxed)) { set_error("search stopped"); fail(k); return; }
+        if (k + 1 < mine.size() && !prepare(k + 1)) { fail(k); return; }
+        const SlabPlan &p = plans[mine[k]];
+        slab_rel_offsets(p, src.off, rel);
+        // findAll=false on the device keeps one event per haystack piece; a piece that starts with a halo could
+        // lose its first real event to one inside the halo, so such a slab reports everything and the host picks
+        const bool fo = first_only && p.halo == 0;
+        const uint32_t init = (mine[k] == 0) ? init_state : ROOT_STATE;
+        if (!eng->scan_slab((int)(k & 1), rel.data(), p.h_end - p.h_first, fo, init)) { fail(k); return; }
+        SlabResult r;
+        r.ev.assign(eng->host_events(), eng->host_events() + eng->n_events());
+        r.st = eng->stats;
+        r.st.h2d_ms = eng->slab_h2d_ms((int)(k & 1));
+        r.end_state = eng->end_state();
+        r.ready = true;
+        {
+            std::lock_guard<std::mutex> g(run.m);
+            run.res[mine[k]] = std::move(r);
+        }
+        run.cv.notify_all();
+    }
+}
+
+// below this many bytes a further GPU costs more than it brings (16 MiB with the default 64 MiB slabs)
+inline uint64_t min_bytes_per_device(const ac_trie *t) { return std::max<uint64_t>(1, t->slab_bytes / 4); }
+
+// sink(text_idx, position, state) -> non-zero = stop (that haystack, or with stop_all the whole search).
+// Returns 0, 1 (stopped, stop_all only) or -1.
+template <class Sink>
+int sharded_search(ac_trie *t, const HaySource &src, bool first_only, uint32_t init_state, bool stop_all,
+                   uint32_t *end_state, Sink &&sink)
+{
+    const uint64_t total = src.off[src.n];
+    std::vector<Engine *> engines{&t->engine};
+    for (auto &r : t->replicas) engines.push_back(r.get());
+    const int n_dev = (int)std::min<uint64_t>(engines.size(), std::max<uint64_t>(1, total / min_bytes_per_device(t)));
+    const uint32_t halo_max = t->flat.max_pattern_len ? t->flat.max_pattern_len - 1 : 0;
+    const std::vector<SlabPlan> plans = plan_slabs(src.off, src.n, halo_max, n_dev, t->slab_bytes);
+    ACB200_STATS_t sum{};
+    sum.devices = (uint32_t)n_dev;
+    if (end_state) *end_state = (init_state == ROOT_STATE) ? t->flat.root : init_state;
+    if (plans.empty()) { t->stats = sum; return 0; }
+
+    ShardRun run;
+    run.res.resize(plans.size());
+    std::vector<std::vector<size_t>> mine(n_dev);
+    for (size_t i = 0; i < plans.size(); ++i) mine[plans[i].device_slot].push_back(i);
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int helpers = src.pinned ? 1 : (int)std::max(1u, std::min(4u, hw / (2u * (unsigned)n_dev)));
+    std::vector<std::thread> workers;
+    for (int d = 0; d < n_dev; ++d)
+        workers.emplace_back(shard_worker, engines[d], std::cref(src), std::cref(plans), std::cref(mine[d]), first_only,
+                             init_state, helpers, std::ref(run));
+
+    int rc = 0;
+    size_t h = 0, stopped = (size_t)-1;
+    std::vector<ACB200_STATS_t> per_dev(n_dev);
+    for (size_t i = 0; i < plans.size() && rc == 0; ++i) {
+        {
+            std::unique_lock<std::mutex> g(run.m);
+            run.cv.wait(g, [&] { return run.res[i].ready; });
+        }
+        SlabResult &r = run.res[i];
+        if (!r.ok) { set_error(r.err); rc = -1; break; }
+        const SlabPlan &p = plans[i];
+        add_stats(per_dev[p.device_slot], r.st);
+        if (end_state) *end_state = r.end_state;
+        h = std::max(h, p.h_first);
+        const uint64_t base = p.b0 - p.halo;
+        for (const PackedEvent &e : r.ev) {
+            if (e.end <= p.halo) continue;                   // ends inside the halo: the slab before reported it
+            const uint64_t g = base + e.end;
+            while (g > src.off[h + 1]) ++h;
+            if (h == stopped) continue;
+            const int s = sink(h, (uint64_t)(g - src.off[h]), e.state);
+            if (s && stop_all) { rc = 1; break; }
+            if (s || first_only) stopped = h;
+        }
+        std::vector<PackedEvent>().swap(r.ev);
+    }
+    if (rc != 0) run.abort.store(true);
+    for (auto &w : workers) w.join();
+    cudaSetDevice(t->device);
+    // devices work side by side: the call's device time is that of the slowest one
+    for (int d = 0; d < n_dev; ++d) {
+        const ACB200_STATS_t &s = per_dev[d];
+        sum.bytes += s.bytes; sum.events += s.events; sum.kernel_launches += s.kernel_launches;
+        sum.flagged_words += s.flagged_words; sum.dense_tiles += s.dense_tiles;
+        sum.kernel_ms = std::max(sum.kernel_ms, s.kernel_ms); sum.filter_ms = std::max(sum.filter_ms, s.filter_ms);
+        sum.verify_ms = std::max(sum.verify_ms, s.verify_ms); sum.reorder_ms = std::max(sum.reorder_ms, s.reorder_ms);
+        sum.h2d_ms = std::max(sum.h2d_ms, s.h2d_ms); sum.d2h_ms = std::max(sum.d2h_ms, s.d2h_ms);
+        if (s.bytes) { sum.chunk_bytes = s.chunk_bytes; sum.halo_bytes = s.halo_bytes; sum.filtered = s.filtered; }
+    }
+    t->stats = sum;
+    return rc;
+}
+
+// Inputs of up to half a slab (32 MiB by default) skip the slab machinery: one copy, one launch, no threads.
+inline bool takes_direct_path(const ac_trie *t, uint64_t total)
+{
+    return total <= t->slab_bytes / 2;
+}
+
+} // namespace
+
+// Events of a direct (single launch) scan -> sink, in (text_idx, position) order
+template <class Sink>
+static void replay_direct(ac_trie *t, const uint64_t *offsets, size_t n, int first_only, Sink &&sink)
+{
+    const PackedEvent *ev = t->engine.host_events();
+    const size_t ne = t->engine.n_events();
+    size_t h = 0;
+    size_t stopped = (size_t)-1;                 // haystack whose callback asked to stop
+    for (size_t i = 0; i < ne; ++i) {
+        const uint64_t end = ev[i].end;
+        while (h < n && end > offsets[h + 1]) ++h;
+        if (h == stopped) continue;
+        const int r = sink(h, (uint64_t)(end - offsets[h]), ev[i].state);
+        if (r || first_only) stopped = h;
+    }
+}
+
+template <class Sink>
+static int search_source(ac_trie *t, HaySource &src, int first_only, Sink &&sink)
+{
+    if (t->open) { set_error("automaton is not finalized"); return -1; }
+    if (!t->device_ok) return -1;
+    const uint64_t total = src.off[src.n];
+    if (takes_direct_path(t, total)) {
+        const char *bytes = src.flat;
+        if (!bytes && total) {                   // scattered haystacks: gathered straight into pinned staging
+            char *stage = t->engine.slab_staging(0, (size_t)total);
+            if (!stage) return -1;
+            src.copy(stage, 0, total, 0);
+            bytes = stage;
+        }
+        if (!t->engine.scan_host(bytes, src.off, src.n, first_only != 0, ROOT_STATE)) return -1;
+        t->stats = t->engine.stats; t->stats.devices = 1;
+        replay_direct(t, src.off, src.n, first_only, sink);
+        return 0;
+    }
+    src.pinned = src.flat && is_pinned(src.flat);
+    return sharded_search(t, src, first_only != 0, ROOT_STATE, false, nullptr, sink) < 0 ? -1 : 0;
 }
 
 extern "C" {
@@ -71,7 +390,9 @@ void acb200_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 AC_TRIE_t *ac_trie_create(void)
 {
-    return new (std::nothrow) ac_trie();
+    ac_trie *t = new (std::nothrow) ac_trie();
+    if (t) t->device = preferred_device();       // the device is a property of the handle, not of whoever finalizes it
+    return t;
 }
 
 AC_STATUS_t ac_trie_add(AC_TRIE_t *t, AC_PATTERN_t *patt, int copy)
@@ -86,10 +407,11 @@ void ac_trie_finalize(AC_TRIE_t *t)
     t->trie.flatten(t->flat);
     t->open = false;                             // src/multifast/ahocorasick.c:154
     set_error("");
-    t->device_ok = t->engine.build(t->flat);
+    t->device_ok = t->engine.build(t->flat, t->device);
     t->engine.info.n_patterns = t->trie.n_patterns();
     t->engine.info.finalized = 1;
     t->trie.release_build_memory();
+    if (t->device_ok) replicate_from_env(t);
     // the expansion inputs (a few words per state) stay: acb200_save() writes them
 }
 
@@ -105,14 +427,16 @@ AC_TRIE_t *acb200_load(const char *path)
 {
     ac_trie *t = new (std::nothrow) ac_trie();
     if (!t) { set_error("out of memory"); return nullptr; }
+    t->device = preferred_device();
     std::string err;
     if (!load_flat(t->flat, t->blob_arena, path, err)) { set_error(err); delete t; return nullptr; }
     build_gram_table(t->flat);
     t->open = false;
     set_error("");
-    t->device_ok = t->engine.build(t->flat);
+    t->device_ok = t->engine.build(t->flat, t->device);
     t->engine.info.n_patterns = t->flat.accepted.size();
     t->engine.info.finalized = 1;
+    if (t->device_ok) replicate_from_env(t);
     return t;
 }
 
@@ -122,153 +446,111 @@ int ac_trie_search(AC_TRIE_t *t, AC_TEXT_t *text, int keep, AC_MATCH_CALBACK_f c
     if (!t->device_ok) return -1;
     if (!keep) { t->last_state = ROOT_STATE; t->base_position = 0; }   // ac_trie_reset, ahocorasick.c:330-335
     const uint64_t offs[2] = {0, (uint64_t)text->length};
-    if (!t->engine.scan_host(text->astring, offs, 1, false, t->last_state)) return -1;
-    const PackedEvent *ev = t->engine.host_events();
-    const size_t n = t->engine.n_events();
-    for (size_t i = 0; i < n; ++i) {
+    const size_t base = t->base_position;
+    auto fire = [&](uint64_t position, uint32_t state) -> int {
         const AC_PATTERN_t *pats;
         AC_MATCH_t m;
-        m.size = patterns_of(t, ev[i].state, &pats);
+        m.size = patterns_of(t, state, &pats);
         m.patterns = const_cast<AC_PATTERN_t *>(pats);
-        m.position = (size_t)ev[i].end + t->base_position;
-        if (callback(&m, user)) return 1;        // state is not saved on a stop (ahocorasick.c:226-232)
-    }
-    t->last_state = t->engine.end_state();       // ahocorasick.c:236-238
-    t->base_position += text->length;
-    return 0;
-}
-
-static int replay_batch(ac_trie *t, const uint64_t *offsets, size_t n, int first_only,
-                        ACB200_BATCH_CALLBACK_f callback, void *user)
-{
-    const PackedEvent *ev = t->engine.host_events();
-    const size_t ne = t->engine.n_events();
-    size_t h = 0;
-    size_t stopped = (size_t)-1;                 // haystack whose callback asked to stop
-    for (size_t i = 0; i < ne; ++i) {
-        const uint64_t end = ev[i].end;
-        while (h < n && end > offsets[h + 1]) ++h;
-        if (h == stopped) continue;
-        const AC_PATTERN_t *pats;
-        AC_MATCH_t m;
-        m.size = patterns_of(t, ev[i].state, &pats);
-        m.patterns = const_cast<AC_PATTERN_t *>(pats);
-        m.position = (size_t)(end - offsets[h]);
-        const int r = callback(h, &m, user);
-        if (r || first_only) stopped = h;
-    }
-    return 0;
-}
-
-// Large batches are cut into slabs at haystack boundaries and pipelined: while slab i is scanned on the
-// device and its events are replayed through the callback on the host, slab i+1 is already crossing PCIe.
-static constexpr uint64_t SLAB_BYTES = 64ull << 20;
-
-static int search_flat_pipelined(ac_trie *t, const char *bytes, const uint64_t *offsets, size_t n,
-                                 int first_only, ACB200_BATCH_CALLBACK_f callback, void *user)
-{
-    // slab s covers haystacks [cut[s], cut[s+1])
-    std::vector<size_t> cut{0};
-    for (size_t h = 0; h < n;) {
-        size_t e = h;
-        while (e < n && offsets[e + 1] - offsets[h] <= SLAB_BYTES) ++e;
-        if (e == h) e = h + 1;                   // a single haystack larger than a slab travels alone
-        if (offsets[e] - offsets[h] >= 0xffffff00ull) { set_error("haystack exceeds 4 GiB"); return -1; }
-        cut.push_back(e);
-        h = e;
-    }
-    const size_t n_slabs = cut.size() - 1;
-    Engine &eng = t->engine;
-    ACB200_STATS_t sum{};
-    std::vector<uint64_t> rel;
-    auto upload = [&](size_t s) {
-        const uint64_t b0 = offsets[cut[s]], b1 = offsets[cut[s + 1]];
-        return eng.slab_upload_async((int)(s & 1), bytes + b0, (size_t)(b1 - b0));
+        m.position = (size_t)position + base;
+        return callback(&m, user);
     };
-    if (!upload(0)) return -1;
-    for (size_t s = 0; s < n_slabs; ++s) {
-        if (s + 1 < n_slabs && !upload(s + 1)) return -1;
-        const size_t h0 = cut[s], h1 = cut[s + 1];
-        rel.resize(h1 - h0 + 1);
-        for (size_t i = 0; i <= h1 - h0; ++i) rel[i] = offsets[h0 + i] - offsets[h0];
-        if (!eng.scan_slab((int)(s & 1), rel.data(), h1 - h0, first_only != 0)) return -1;
-        sum.bytes += eng.stats.bytes; sum.events += eng.stats.events; sum.kernel_launches += eng.stats.kernel_launches;
-        sum.kernel_ms += eng.stats.kernel_ms; sum.filter_ms += eng.stats.filter_ms; sum.verify_ms += eng.stats.verify_ms;
-        sum.reorder_ms += eng.stats.reorder_ms; sum.d2h_ms += eng.stats.d2h_ms; sum.h2d_ms += eng.slab_h2d_ms((int)(s & 1));
-        sum.flagged_words += eng.stats.flagged_words; sum.dense_tiles += eng.stats.dense_tiles;
-        sum.chunk_bytes = eng.stats.chunk_bytes; sum.halo_bytes = eng.stats.halo_bytes;
-        sum.filtered = eng.stats.filtered;
-        // replay this slab's events; haystack indices are those of the whole batch
-        const PackedEvent *ev = eng.host_events();
-        const size_t ne = eng.n_events();
-        size_t h = 0, stopped = (size_t)-1;
-        for (size_t i = 0; i < ne; ++i) {
-            const uint64_t end = ev[i].end;
-            while (h < h1 - h0 && end > rel[h + 1]) ++h;
-            if (h == stopped) continue;
-            const AC_PATTERN_t *pats;
-            AC_MATCH_t m;
-            m.size = patterns_of(t, ev[i].state, &pats);
-            m.patterns = const_cast<AC_PATTERN_t *>(pats);
-            m.position = (size_t)(end - rel[h]);
-            const int r = callback(h0 + h, &m, user);
-            if (r || first_only) stopped = h;
-        }
+    uint32_t end_state;
+    if (takes_direct_path(t, offs[1])) {
+        if (!t->engine.scan_host(text->astring, offs, 1, false, t->last_state)) return -1;
+        t->stats = t->engine.stats; t->stats.devices = 1;
+        const PackedEvent *ev = t->engine.host_events();
+        const size_t n = t->engine.n_events();
+        for (size_t i = 0; i < n; ++i)
+            if (fire(ev[i].end, ev[i].state)) return 1;      // state is not saved on a stop (ahocorasick.c:226-232)
+        end_state = t->engine.end_state();
+    } else {
+        // a long text: slabs with a halo, over every GPU of the handle; a text of any size_t length is scanned
+        HaySource src;
+        src.flat = text->astring; src.off = offs; src.n = 1; src.pinned = is_pinned(text->astring);
+        const int rc = sharded_search(t, src, false, t->last_state, true, &end_state,
+                                      [&](size_t, uint64_t position, uint32_t state) { return fire(position, state); });
+        if (rc != 0) return rc;
     }
-    eng.stats = sum;
+    t->last_state = end_state;                   // ahocorasick.c:236-238
+    t->base_position += text->length;
     return 0;
 }
 
 int ac_trie_search_flat(AC_TRIE_t *t, const char *bytes, const uint64_t *offsets, size_t n,
                         int first_only, ACB200_BATCH_CALLBACK_f callback, void *user)
 {
-    if (t->open) { set_error("automaton is not finalized"); return -1; }
-    if (!t->device_ok) return -1;
     if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return -1; }
-    if (n > 1 && offsets[n] > 2 * SLAB_BYTES) return search_flat_pipelined(t, bytes, offsets, n, first_only, callback, user);
-    if (!t->engine.scan_host(bytes, offsets, n, first_only != 0, ROOT_STATE)) return -1;
-    return replay_batch(t, offsets, n, first_only, callback, user);
+    HaySource src;
+    src.flat = bytes ? bytes : ""; src.off = offsets; src.n = n;
+    return search_source(t, src, first_only, [&](size_t h, uint64_t position, uint32_t state) {
+        const AC_PATTERN_t *pats;
+        AC_MATCH_t m;
+        m.size = patterns_of(t, state, &pats);
+        m.patterns = const_cast<AC_PATTERN_t *>(pats);
+        m.position = (size_t)position;
+        return callback(h, &m, user);
+    });
 }
 
 int ac_trie_search_batch(AC_TRIE_t *t, const AC_TEXT_t *texts, size_t n, int first_only,
                          ACB200_BATCH_CALLBACK_f callback, void *user)
 {
-    if (t->open) { set_error("automaton is not finalized"); return -1; }
-    if (!t->device_ok) return -1;
     t->gather_off.resize(n + 1);
     uint64_t total = 0;
     for (size_t i = 0; i < n; ++i) { t->gather_off[i] = total; total += texts[i].length; }
     t->gather_off[n] = total;
-    if (t->gather.size() < total) t->gather.resize(total);
-    for (size_t i = 0; i < n; ++i)
-        if (texts[i].length) memcpy(t->gather.data() + t->gather_off[i], texts[i].astring, texts[i].length);
-    if (!t->engine.scan_host(t->gather.data(), t->gather_off.data(), n, first_only != 0, ROOT_STATE)) return -1;
-    return replay_batch(t, t->gather_off.data(), n, first_only, callback, user);
+    HaySource src;
+    src.texts = texts; src.off = t->gather_off.data(); src.n = n;
+    return search_source(t, src, first_only, [&](size_t h, uint64_t position, uint32_t state) {
+        const AC_PATTERN_t *pats;
+        AC_MATCH_t m;
+        m.size = patterns_of(t, state, &pats);
+        m.patterns = const_cast<AC_PATTERN_t *>(pats);
+        m.position = (size_t)position;
+        return callback(h, &m, user);
+    });
 }
 
 int acb200_search_events(AC_TRIE_t *t, const char *bytes, const uint64_t *offsets, size_t n,
                          int first_only, ACB200_EVENT_t *events, size_t cap, size_t *n_events)
 {
-    if (t->open) { set_error("automaton is not finalized"); return -1; }
-    if (!t->device_ok) return -1;
     if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return -1; }
-    if (!t->engine.scan_host(bytes, offsets, n, first_only != 0, ROOT_STATE)) return -1;
-    const PackedEvent *ev = t->engine.host_events();
-    const size_t ne = t->engine.n_events();
-    size_t h = 0, w = 0;
-    size_t last_h = (size_t)-1;
-    for (size_t i = 0; i < ne; ++i) {
-        const uint64_t end = ev[i].end;
-        while (h < n && end > offsets[h + 1]) ++h;
-        if (first_only) { if (h == last_h) continue; last_h = h; }
+    HaySource src;
+    src.flat = bytes ? bytes : ""; src.off = offsets; src.n = n;
+    size_t w = 0;
+    const int rc = search_source(t, src, first_only, [&](size_t h, uint64_t position, uint32_t state) {
         if (w < cap) {
-            events[w].end = end - offsets[h];
-            events[w].state = ev[i].state;
+            events[w].end = position;
+            events[w].state = state;
             events[w].text_idx = (uint32_t)h;
         }
         ++w;
-    }
+        return 0;
+    });
     if (n_events) *n_events = w;
+    return rc;
+}
+
+int acb200_set_devices(AC_TRIE_t *t, const int *devices, size_t n) { return set_devices(t, devices, n); }
+
+int acb200_set_slab_bytes(AC_TRIE_t *t, uint64_t bytes)
+{
+    if (bytes && (bytes < 4096 || bytes > (1ull << 31))) { set_error("slab size must lie in [4 KiB, 2 GiB]"); return -1; }
+    t->slab_bytes = bytes ? bytes : (64ull << 20);
+    return 0;
+}
+
+int acb200_plan_slabs(const uint64_t *offsets, size_t n, uint32_t halo_max, int n_devices, uint64_t slab_bytes,
+                      ACB200_SLAB_t *out, size_t cap, size_t *n_slabs)
+{
+    const std::vector<SlabPlan> plans = plan_slabs(offsets, n, halo_max, n_devices, slab_bytes ? slab_bytes : (64ull << 20));
+    for (size_t i = 0; i < plans.size() && i < cap; ++i) {
+        out[i].begin = plans[i].b0; out[i].end = plans[i].b1; out[i].halo = plans[i].halo;
+        out[i].device_slot = (uint32_t)plans[i].device_slot;
+        out[i].first_text = plans[i].h_first; out[i].end_text = plans[i].h_end;
+    }
+    if (n_slabs) *n_slabs = plans.size();
     return 0;
 }
 
@@ -280,7 +562,9 @@ int acb200_search_hits(AC_TRIE_t *t, const char *bytes, const uint64_t *offsets,
     if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return -1; }
     if (!t->engine.scan_host(bytes, offsets, n, false, ROOT_STATE)) return -1;
     size_t total = 0;
-    if (!t->engine.expand_hits_to_host(n, hits, cap, &total)) return -1;
+    const bool ok = t->engine.expand_hits_to_host(n, hits, cap, &total);
+    t->stats = t->engine.stats; t->stats.devices = 1;
+    if (!ok) return -1;
     if (n_hits) *n_hits = total;
     return 0;
 }
@@ -297,7 +581,9 @@ int acb200_search_device(AC_TRIE_t *t, const void *d_bytes, const uint64_t *offs
     if (t->open) { set_error("automaton is not finalized"); return -1; }
     if (!t->device_ok) return -1;
     if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return -1; }
-    if (!t->engine.scan_device(d_bytes, offsets, n, first_only != 0, ROOT_STATE, stream)) return -1;
+    const bool ok = t->engine.scan_device(d_bytes, offsets, n, first_only != 0, ROOT_STATE, stream);
+    t->stats = t->engine.stats; t->stats.devices = 1;
+    if (!ok) return -1;
     if (d_events) *d_events = t->engine.device_events();
     if (n_events) *n_events = t->engine.n_events();
     return 0;
@@ -308,7 +594,9 @@ int acb200_search_device_uniform(AC_TRIE_t *t, const void *d_bytes, size_t n, si
 {
     if (t->open) { set_error("automaton is not finalized"); return -1; }
     if (!t->device_ok) return -1;
-    if (!t->engine.scan_device_uniform(d_bytes, n, hay_len, first_only != 0, stream)) return -1;
+    const bool ok = t->engine.scan_device_uniform(d_bytes, n, hay_len, first_only != 0, stream);
+    t->stats = t->engine.stats; t->stats.devices = 1;
+    if (!ok) return -1;
     if (d_events) *d_events = t->engine.device_events();
     if (n_events) *n_events = t->engine.n_events();
     return 0;
@@ -326,6 +614,7 @@ int acb200_async_finish(AC_TRIE_t *t, size_t n_events, size_t dense_tiles)
 {
     if (t->open || !t->device_ok) return -1;
     t->engine.async_finish(n_events, dense_tiles);
+    t->stats = t->engine.stats; t->stats.devices = 1;
     return 0;
 }
 
@@ -361,6 +650,28 @@ int acb200_tally_cb(size_t text_idx, AC_MATCH_t *m, void *tally)
 
 int acb200_tally_match_cb(AC_MATCH_t *m, void *tally) { return acb200_tally_cb(0, m, tally); }
 
+int acb200_event_digest(const AC_TRIE_t *t, const ACB200_EVENT_t *events, size_t n_events, size_t n_texts,
+                        uint64_t *counts, uint64_t *hashes)
+{
+    if (t->open) { set_error("automaton is not finalized"); return -1; }
+    for (size_t h = 0; h < n_texts; ++h) { counts[h] = 0; hashes[h] = 0; }
+    for (size_t i = 0; i < n_events; ++i) {
+        const ACB200_EVENT_t &e = events[i];
+        if (e.text_idx >= n_texts) { set_error("event names a haystack outside the batch"); return -1; }
+        const AC_PATTERN_t *pats;
+        const size_t size = patterns_of(t, e.state, &pats);
+        uint64_t h = tally_fold(hashes[e.text_idx], e.end);
+        h = tally_fold(h, (uint64_t)size);
+        if (size) {
+            h = tally_fold(h, (uint64_t)(uintptr_t)pats[0].aux);
+            h = tally_fold(h, (uint64_t)(uintptr_t)pats[size - 1].aux);
+        }
+        hashes[e.text_idx] = h;
+        counts[e.text_idx]++;
+    }
+    return 0;
+}
+
 size_t acb200_state_patterns(const AC_TRIE_t *t, uint32_t state, const AC_PATTERN_t **patterns)
 {
     if (t->open) { if (patterns) *patterns = nullptr; return 0; }
@@ -395,7 +706,7 @@ int acb200_info(const AC_TRIE_t *t, ACB200_INFO_t *out)
 int acb200_last_stats(const AC_TRIE_t *t, ACB200_STATS_t *out)
 {
     if (!out) return -1;
-    *out = t->engine.stats;
+    *out = t->stats;
     return 0;
 }
 

@@ -67,7 +67,7 @@ void Engine::release()
     d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; verify_tiles_cap_ = 0;
     if (h_counters_) cudaFreeHost(h_counters_);
     if (h_events_) cudaFreeHost(h_events_);
-    if (h_stage_) cudaFreeHost(h_stage_);
+    for (int b = 0; b < 2; ++b) { if (h_slab_[b]) cudaFreeHost(h_slab_[b]); h_slab_[b] = nullptr; h_slab_cap_[b] = 0; }
     for (auto &e : ev_) if (e) { cudaEventDestroy(EV(e)); e = nullptr; }
     for (auto &e : ev_slab_) if (e) { cudaEventDestroy(EV(e)); e = nullptr; }
     for (int b = 0; b < 2; ++b) { cudaFree(d_slab_[b]); d_slab_[b] = nullptr; slab_cap_[b] = 0; }
@@ -75,7 +75,7 @@ void Engine::release()
     if (stream_) cudaStreamDestroy(S(stream_));
     d_table_ = nullptr; d_cls_ = nullptr; d_text_ = nullptr; d_off_ = nullptr; d_first_ = nullptr;
     d_events_ = nullptr; d_tiles_ = nullptr; d_counters_ = nullptr;
-    h_counters_ = nullptr; h_events_ = nullptr; h_stage_ = nullptr; stream_ = nullptr;
+    h_counters_ = nullptr; h_events_ = nullptr; stream_ = nullptr;
     device_ = -1;
 }
 
@@ -102,14 +102,16 @@ static bool expand_table(E *table, const FlatAutomaton &f, cudaStream_t st, uint
         if (ok && (e = cudaMalloc(&d_dst, sizeof(uint32_t) * ne)) != cudaSuccess) fail_with("cudaMalloc(edge_dst)", e);
         if (ok && (e = cudaMalloc(&d_cls, sizeof(uint16_t) * ne)) != cudaSuccess) fail_with("cudaMalloc(edge_cls)", e);
     }
+    auto upload = [&](void *dst, const void *src, size_t bytes, const char *what) {
+        if (!ok || !bytes) return;
+        if ((e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) fail_with(what, e);
+    };
+    upload(d_order, f.bfs_order.data(), sizeof(uint32_t) * N, "upload(order)");
+    upload(d_fail, f.fail.data(), sizeof(uint32_t) * NR, "upload(fail)");
+    upload(d_src, f.edge_src.data(), sizeof(uint32_t) * ne, "upload(edge_src)");
+    upload(d_dst, f.edge_dst.data(), sizeof(uint32_t) * ne, "upload(edge_dst)");
+    upload(d_cls, f.edge_cls.data(), sizeof(uint16_t) * ne, "upload(edge_cls)");
     if (ok) {
-        cudaMemcpyAsync(d_order, f.bfs_order.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(d_fail, f.fail.data(), sizeof(uint32_t) * NR, cudaMemcpyHostToDevice, st);
-        if (ne) {
-            cudaMemcpyAsync(d_src, f.edge_src.data(), sizeof(uint32_t) * ne, cudaMemcpyHostToDevice, st);
-            cudaMemcpyAsync(d_dst, f.edge_dst.data(), sizeof(uint32_t) * ne, cudaMemcpyHostToDevice, st);
-            cudaMemcpyAsync(d_cls, f.edge_cls.data(), sizeof(uint16_t) * ne, cudaMemcpyHostToDevice, st);
-        }
         const size_t n_levels = f.level_off.size() - 1;
         for (size_t d = 0; d < n_levels; ++d) {
             const uint32_t lb = f.level_off[d], le = f.level_off[d + 1];
@@ -140,7 +142,7 @@ static cudaError_t set_smem_attr(int bytes)
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
-bool Engine::build(const FlatAutomaton &f)
+bool Engine::build(const FlatAutomaton &f, int dev, const Engine *table_src)
 {
     int n_dev = 0;
     cudaError_t ce = cudaGetDeviceCount(&n_dev);
@@ -148,7 +150,6 @@ bool Engine::build(const FlatAutomaton &f)
         set_error(std::string("no CUDA device available: ") + cudaGetErrorString(ce));
         return false;
     }
-    int dev = preferred_device();
     if (dev < 0 || dev >= n_dev) { set_error("ACB200 device ordinal out of range"); return false; }
     CU_OK(cudaSetDevice(dev));
     device_ = dev;
@@ -186,8 +187,17 @@ bool Engine::build(const FlatAutomaton &f)
     CU_OK(cudaMallocHost(&h_counters_, 64));
 
     uint64_t launches = 0;
-    bool ok = (entry_bytes_ == 2) ? expand_table<uint16_t>((uint16_t *)d_table_, f, st, &launches)
-                                  : expand_table<uint32_t>((uint32_t *)d_table_, f, st, &launches);
+    bool ok = false;
+    if (table_src && table_src->device_ >= 0 && table_src->d_table_ && table_src->table_entries_ == table_entries_ &&
+        table_src->entry_bytes_ == entry_bytes_) {
+        // a replica: the expanded table comes from the primary's HBM over NVLink instead of being expanded again
+        ok = cudaMemcpyPeerAsync(d_table_, dev, table_src->d_table_, table_src->device_, table_bytes, st) == cudaSuccess &&
+             cudaStreamSynchronize(st) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+    }
+    if (!ok)
+        ok = (entry_bytes_ == 2) ? expand_table<uint16_t>((uint16_t *)d_table_, f, st, &launches)
+                                 : expand_table<uint32_t>((uint32_t *)d_table_, f, st, &launches);
     if (!ok) return false;
 
     const int dyn = max_smem_optin_ - 2048;   // static shared memory of the kernel + slack
@@ -358,7 +368,7 @@ bool Engine::upload_offsets(const uint64_t *offsets, size_t n, uint32_t *uniform
 
 uint32_t Engine::pick_chunk(uint64_t total) const
 {
-    if (tune_chunk) return std::max(16u, (tune_chunk + 15u) & ~15u);
+    if (tune_chunk) return std::min(1u << 20, std::max(16u, (tune_chunk + 15u) & ~15u));
     auto up16 = [](uint64_t v) -> uint64_t { return (v + 15) & ~(uint64_t)15; };
     // Steady state: 512-byte slices measured best on B200 (adjacent lanes stay within a few DRAM
     // pages, the (Lmax-1)-byte halo re-read stays below ~12%); long patterns need longer slices.
@@ -768,7 +778,7 @@ bool Engine::scan_device(const void *d_bytes, const uint64_t *offsets, size_t n,
     if (device_ < 0) { set_error("automaton has no device table (finalize failed?)"); return false; }
     CU_OK(cudaSetDevice(device_));
     const uint64_t total = offsets[n];
-    if (total >= 0xffffff00ull) { set_error("haystack stream exceeds 4 GiB per call"); return false; }
+    if (total >= MAX_STREAM_BYTES) { set_error("haystack stream exceeds 4 GiB per call"); return false; }
     if (((uintptr_t)d_bytes & 15u) != 0) { set_error("device haystack pointer must be 16-byte aligned"); return false; }
     uint32_t uniform_len = 0;
     if (!upload_offsets(offsets, n, &uniform_len)) return false;
@@ -782,7 +792,7 @@ bool Engine::scan_device_uniform(const void *d_bytes, size_t n, size_t hay_len, 
     if (device_ < 0) { set_error("automaton has no device table (finalize failed?)"); return false; }
     CU_OK(cudaSetDevice(device_));
     const uint64_t total = (uint64_t)n * hay_len;
-    if (total >= 0xffffff00ull) { set_error("haystack stream exceeds 4 GiB per call"); return false; }
+    if (total >= MAX_STREAM_BYTES) { set_error("haystack stream exceeds 4 GiB per call"); return false; }
     if (((uintptr_t)d_bytes & 15u) != 0) { set_error("device haystack pointer must be 16-byte aligned"); return false; }
     stats.h2d_ms = 0; stats.d2h_ms = 0;
     const uint32_t uniform_len = (n <= 1 || total == 0) ? (uint32_t)std::max<uint64_t>(total, 1) : (uint32_t)hay_len;
@@ -794,7 +804,7 @@ bool Engine::scan_device_uniform_async(const void *d_bytes, size_t n, size_t hay
     if (device_ < 0) { set_error("automaton has no device table (finalize failed?)"); return false; }
     CU_OK(cudaSetDevice(device_));
     const uint64_t total = (uint64_t)n * hay_len;
-    if (total == 0 || total >= 0xffffff00ull) { set_error("asynchronous search: empty batch or stream beyond 4 GiB"); return false; }
+    if (total == 0 || total >= MAX_STREAM_BYTES) { set_error("asynchronous search: empty batch or stream beyond 4 GiB"); return false; }
     if (((uintptr_t)d_bytes & 15u) != 0 || ((uintptr_t)d_rows & 7u) != 0) { set_error("device pointers must be 16-byte (haystack) / 8-byte (rows) aligned"); return false; }
     stats.h2d_ms = 0; stats.d2h_ms = 0;
     const uint32_t uniform_len = (n <= 1) ? (uint32_t)total : (uint32_t)hay_len;
@@ -825,6 +835,22 @@ void Engine::async_finish(size_t n_events, size_t dense_tiles)
     last_density_ = stats.bytes ? (double)n_events / (double)stats.bytes : 0.0;
     stats.dense_tiles = dense_tiles;
     if (async_tiles_) last_dense_frac_ = (double)dense_tiles / (double)async_tiles_;      // feeds the automatic kernel choice
+}
+
+// Pinned staging memory of slab buffer `buf` for callers whose haystacks are pageable or scattered (the gather
+// of ac_trie_search_batch): fill it, then slab_upload_async(buf, <this pointer>, n).
+char *Engine::slab_staging(int buf, size_t n_bytes)
+{
+    if (device_ < 0) { set_error("automaton has no device table (finalize failed?)"); return nullptr; }
+    if (cudaSetDevice(device_) != cudaSuccess) { set_error("cudaSetDevice failed"); return nullptr; }
+    if (n_bytes > h_slab_cap_[buf]) {
+        if (h_slab_[buf]) cudaFreeHost(h_slab_[buf]);
+        h_slab_[buf] = nullptr; h_slab_cap_[buf] = 0;
+        const size_t cap = n_bytes + n_bytes / 8 + 4096;
+        if (cudaMallocHost(&h_slab_[buf], cap) != cudaSuccess) { set_error("cudaMallocHost(slab staging) failed"); return nullptr; }
+        h_slab_cap_[buf] = cap;
+    }
+    return (char *)h_slab_[buf];
 }
 
 bool Engine::slab_upload_async(int buf, const char *bytes, size_t n_bytes)
@@ -859,17 +885,18 @@ float Engine::slab_h2d_ms(int buf)
 
 // Scans the slab uploaded into buffer `buf` (offsets are relative to the slab) and brings its events to
 // host_events().  Returns after the events have arrived; the other buffer's upload keeps running meanwhile.
-bool Engine::scan_slab(int buf, const uint64_t *offsets, size_t n, bool first_only)
+bool Engine::scan_slab(int buf, const uint64_t *offsets, size_t n, bool first_only, uint32_t init_state)
 {
     CU_OK(cudaSetDevice(device_));
     cudaStream_t st = S(stream_);
     const uint64_t total = offsets[n];
-    if (total >= 0xffffff00ull) { set_error("haystack stream exceeds 4 GiB per call"); return false; }
+    if (total >= MAX_STREAM_BYTES) { set_error("haystack stream exceeds 4 GiB per call"); return false; }
     uint32_t uniform_len = 0;
     if (!upload_offsets(offsets, n, &uniform_len)) return false;
     CU_OK(cudaStreamWaitEvent(st, EV(ev_slab_[2 * buf + 1]), 0));
     if (!launch_scan(d_slab_[buf], (uint32_t)total, (uint32_t)std::min<uint64_t>(slab_cap_[buf], 0xffffffffu), n, uniform_len,
-                     first_only, ROOT_STATE, nullptr)) return false;
+                     first_only, init_state, nullptr)) return false;
+    last_uniform_len_ = uniform_len;
     stats.d2h_ms = 0;
     if (n_events_) {
         if (!ensure_host_events(n_events_)) return false;
@@ -891,7 +918,7 @@ bool Engine::scan_host(const char *bytes, const uint64_t *offsets, size_t n, boo
     CU_OK(cudaSetDevice(device_));
     cudaStream_t st = S(stream_);
     const uint64_t total = offsets[n];
-    if (total >= 0xffffff00ull) { set_error("haystack stream exceeds 4 GiB per call"); return false; }
+    if (total >= MAX_STREAM_BYTES) { set_error("haystack stream exceeds 4 GiB per call"); return false; }
     if (!ensure_text(total + 64)) return false;
     uint32_t uniform_len = 0;
     if (!upload_offsets(offsets, n, &uniform_len)) return false;

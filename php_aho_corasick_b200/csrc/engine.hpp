@@ -15,6 +15,9 @@ namespace acb200 {
 
 struct PackedEvent { uint32_t end; uint32_t state; };   // as written by the kernel
 constexpr uint32_t ROOT_STATE = 0xffffffffu;            // init_state value meaning "start at the root"
+// One launch addresses its stream with 32-bit offsets; the bound leaves room for slice ends (offset + slice
+// length, slice <= 1 MiB) to stay below 2^32.  Host callers never see it: their streams are cut into slabs.
+constexpr uint64_t MAX_STREAM_BYTES = 0xffe00000ull;
 
 void set_error(const std::string &msg);
 const char *get_error();
@@ -26,8 +29,10 @@ public:
     Engine();
     ~Engine();
 
-    // Uploads `flat` and expands the dense table on the device. false on error.
-    bool build(const FlatAutomaton &flat);
+    // Uploads `flat` to CUDA device `device` and expands the dense table there; a replica (table_src != nullptr)
+    // copies the expanded table from the primary's HBM instead (peer copy over NVLink).  false on error.
+    bool build(const FlatAutomaton &flat, int device, const Engine *table_src = nullptr);
+    int device() const { return device_; }
 
     // Scans a flat haystack stream that lives in HOST memory.  Events are left in
     // host_events() sorted by stream offset; returns false on error.
@@ -35,8 +40,10 @@ public:
                    uint32_t init_state);
     // Pipelined variant for large batches: the caller cuts the batch into slabs at haystack boundaries,
     // uploads slab i+1 (slab_upload_async) while slab i is scanned (scan_slab) and replayed on the host.
+    // `bytes` is page-locked memory: the caller's own (acb200_host_alloc) or slab_staging(buf, n).
+    char *slab_staging(int buf, size_t n_bytes);
     bool slab_upload_async(int buf, const char *bytes, size_t n_bytes);
-    bool scan_slab(int buf, const uint64_t *offsets, size_t n, bool first_only);
+    bool scan_slab(int buf, const uint64_t *offsets, size_t n, bool first_only, uint32_t init_state = ROOT_STATE);
     float slab_h2d_ms(int buf);
     // Same for a stream already resident in device memory; events stay on the device.
     bool scan_device(const void *d_bytes, const uint64_t *offsets, size_t n, bool first_only,
@@ -129,7 +136,7 @@ private:
     uint32_t *d_counters_ = nullptr;
     uint32_t *h_counters_ = nullptr;          // pinned
     PackedEvent *h_events_ = nullptr; size_t h_events_cap_ = 0;   // pinned
-    uint8_t *h_stage_ = nullptr;  size_t stage_cap_ = 0;          // pinned staging for pageable input
+    void *h_slab_[2] = {nullptr, nullptr}; size_t h_slab_cap_[2] = {0, 0};   // pinned staging of the slabs (pageable / scattered input)
     uint8_t *d_slab_[2] = {nullptr, nullptr}; size_t slab_cap_[2] = {0, 0};   // double-buffered haystack slabs
     void *copy_stream_ = nullptr;                                  // cudaStream_t of the slab uploads
     void *ev_slab_[4] = {nullptr, nullptr, nullptr, nullptr};     // per buffer: upload started / finished

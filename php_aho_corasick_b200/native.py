@@ -44,6 +44,11 @@ EVENT_DTYPE = np.dtype([("end", np.uint64), ("state", np.uint32), ("text_idx", n
 PACKED_EVENT_DTYPE = np.dtype([("end", np.uint32), ("state", np.uint32)])
 
 
+class Slab(C.Structure):
+    _fields_ = [("begin", C.c_uint64), ("end", C.c_uint64), ("halo", C.c_uint32), ("device_slot", C.c_uint32),
+                ("first_text", C.c_uint64), ("end_text", C.c_uint64)]
+
+
 class Tally(C.Structure):
     _fields_ = [("events", C.c_uint64), ("hits", C.c_uint64), ("hash", C.c_uint64)]
 
@@ -77,6 +82,7 @@ EXPORTS = [
     "acb200_set_tuning", "acb200_version", "acb200_copy_events", "acb200_tally_cb", "acb200_tally_match_cb",
     "acb200_set_filter", "acb200_search_device_uniform", "acb200_search_hits", "acb200_pattern", "acb200_save", "acb200_load", "acb200_filter_probe",
     "acb200_set_direct", "acb200_direct_probe", "acb200_search_device_uniform_async", "acb200_async_finish",
+    "acb200_set_devices", "acb200_set_slab_bytes", "acb200_plan_slabs", "acb200_event_digest",
 ]
 
 
@@ -141,6 +147,15 @@ def lib() -> C.CDLL:
     L.acb200_save.restype = C.c_int
     L.acb200_load.argtypes = [C.c_char_p]
     L.acb200_load.restype = C.c_void_p
+    L.acb200_set_devices.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_size_t]
+    L.acb200_set_devices.restype = C.c_int
+    L.acb200_set_slab_bytes.argtypes = [C.c_void_p, C.c_uint64]
+    L.acb200_set_slab_bytes.restype = C.c_int
+    L.acb200_plan_slabs.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_int, C.c_uint64, C.POINTER(Slab), C.c_size_t,
+                                    C.POINTER(C.c_size_t)]
+    L.acb200_plan_slabs.restype = C.c_int
+    L.acb200_event_digest.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
+    L.acb200_event_digest.restype = C.c_int
     L.acb200_copy_events.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.acb200_copy_events.restype = C.c_long
     _lib = L
@@ -159,6 +174,18 @@ def _as_u8(buf) -> np.ndarray:
     if isinstance(buf, (bytes, bytearray, memoryview)):
         return np.frombuffer(bytes(buf), dtype=np.uint8)
     return np.ascontiguousarray(buf, dtype=np.uint8).reshape(-1)
+
+
+def plan_slabs(offsets, halo_max: int, n_devices: int, slab_bytes: int = 0):
+    """the slab plan of a host call (csrc/shard.hpp), evaluated on the host -> list of dicts"""
+    L = lib()
+    off = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = C.c_size_t(0)
+    L.acb200_plan_slabs(off.ctypes.data, off.size - 1, int(halo_max), int(n_devices), int(slab_bytes), None, 0, C.byref(n))
+    arr = (Slab * max(1, n.value))()
+    L.acb200_plan_slabs(off.ctypes.data, off.size - 1, int(halo_max), int(n_devices), int(slab_bytes), arr, n.value, C.byref(n))
+    return [{"begin": int(x.begin), "end": int(x.end), "halo": int(x.halo), "device_slot": int(x.device_slot),
+             "first_text": int(x.first_text), "end_text": int(x.end_text)} for x in arr[: n.value]]
 
 
 class Automaton:
@@ -240,6 +267,16 @@ class Automaton:
         e, s = C.c_uint32(0), C.c_uint32(0)
         v = int(self.L.acb200_direct_probe(self.h, text, len(text), int(hay_begin), int(word_index), C.byref(e), C.byref(s)))
         return v, int(e.value), int(s.value)
+
+    def set_devices(self, devices) -> None:
+        """GPUs one host call may use (the automaton is replicated onto them; see acb200.h)"""
+        arr = (C.c_int * max(1, len(devices)))(*[int(d) for d in devices])
+        if self.L.acb200_set_devices(self.h, arr, len(devices)) != 0:
+            raise AcError(last_error())
+
+    def set_slab_bytes(self, nbytes: int) -> None:
+        if self.L.acb200_set_slab_bytes(self.h, int(nbytes)) != 0:
+            raise AcError(last_error())
 
     def set_filter(self, mode: int) -> None:
         """0 automatic, 1 prefilter whenever the dictionary allows, -1 always the full automaton walk"""
@@ -331,6 +368,34 @@ class Automaton:
         if rc != 0:
             raise AcError(last_error())
         return t
+
+    def search_batch_tally(self, haystacks, first_only: bool = False) -> Tally:
+        """ac_trie_search_batch() over separately allocated host strings (what the PHP extension holds) with the
+        library's tally callback.  `haystacks`: list of bytes / uint8 arrays (kept alive by the caller)."""
+        n = len(haystacks)
+        texts = (AcText * max(1, n))()
+        keep = []
+        for i, h in enumerate(haystacks):
+            a = _as_u8(h)
+            keep.append(a)
+            texts[i].astring = a.ctypes.data if a.size else None
+            texts[i].length = a.size
+        t = Tally()
+        cb = C.cast(self.L.acb200_tally_cb, BATCH_CB)
+        rc = self.L.ac_trie_search_batch(self.h, texts, n, int(first_only), cb, C.cast(C.byref(t), C.c_void_p))
+        if rc != 0:
+            raise AcError(last_error())
+        return t
+
+    def event_digest(self, events: np.ndarray, n_texts: int):
+        """per-haystack (event count, order-sensitive event hash) of an event list -> (counts[u64], hashes[u64])"""
+        ev = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        counts = np.zeros(n_texts, dtype=np.uint64)
+        hashes = np.zeros(n_texts, dtype=np.uint64)
+        if self.L.acb200_event_digest(self.h, ev.ctypes.data if ev.size else None, ev.size, int(n_texts),
+                                      counts.ctypes.data, hashes.ctypes.data) != 0:
+            raise AcError(last_error())
+        return counts, hashes
 
     def copy_events(self, dev_ptr: int, max_events: int, stream: int = 0) -> int:
         n = self.L.acb200_copy_events(self.h, C.c_void_p(dev_ptr), int(max_events), C.c_void_p(stream))

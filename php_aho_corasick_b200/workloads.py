@@ -27,7 +27,11 @@ CFG1_HAYSTACK = b"alFABETA gamma zetaomegaalfa!"
 
 def _alphabet_bytes(rng, n, alphabet: bytes) -> np.ndarray:
     lut = np.frombuffer(alphabet, dtype=np.uint8)
-    return lut[rng.integers(0, len(alphabet), size=n, dtype=np.uint8)]
+    idx = rng.integers(0, len(alphabet), size=n, dtype=np.uint8)
+    if len(alphabet) > 1 and bytes(range(alphabet[0], alphabet[0] + len(alphabet))) == alphabet:
+        idx += np.uint8(alphabet[0])          # a contiguous alphabet needs no table (same bytes, 25x cheaper)
+        return idx
+    return lut[idx]
 
 
 def offsets_uniform(n: int, length: int) -> np.ndarray:
@@ -53,6 +57,51 @@ def cfg2(n_hay: int = 256, hay_len: int = 8192, n_needles: int = 2048, needle_le
             hay[np.arange(n_hay)[:, None], idx] = needles_arr[which[:, j]]
     needles = [needles_arr[i].tobytes() for i in range(n_needles)]
     return needles, hay.reshape(-1), offsets_uniform(n_hay, hay_len)
+
+
+def cfg2_needles(n_needles: int = 2048, needle_len: int = 16, alphabet: bytes = b"abcdef", seed: int = SEED):
+    """the dictionary of cfg2() alone -> (needles: list[bytes], needles_arr: uint8[n_needles, needle_len])"""
+    rng = np.random.default_rng(seed)
+    arr = _alphabet_bytes(rng, n_needles * needle_len, alphabet).reshape(n_needles, needle_len)
+    return [arr[i].tobytes() for i in range(n_needles)], arr
+
+
+def cfg2_stream(stream_seed: int, first_block: int, n_blocks: int, block_hays: int = 256, hay_len: int = 8192,
+                planted_per_hay: int = 8, alphabet: bytes = b"abcdef", seed: int = SEED):
+    """config 2 at steady state as a stream of independent 256-haystack blocks: block b of stream `stream_seed`
+    (one stream per GPU rank) is seeded by (seed, stream_seed, b) alone, so any range of blocks can be
+    regenerated anywhere — the GPU arm, the CPU reference arm's bounded sample, the parity check — and all
+    see the same bytes.  Every block is distinct (nothing is tiled).  The dictionary is cfg2_needles(seed).
+    -> uint8[n_blocks * block_hays * hay_len]"""
+    _, needles_arr = cfg2_needles(alphabet=alphabet, seed=seed)
+    n_needles, needle_len = needles_arr.shape
+    out = np.empty((n_blocks * block_hays, hay_len), dtype=np.uint8)
+    cols = np.arange(needle_len)
+    rows = np.arange(block_hays)[:, None]
+
+    def make(b):
+        rng = np.random.default_rng([seed & 0xFFFFFFFF, stream_seed, first_block + b])
+        hay = _alphabet_bytes(rng, block_hays * hay_len, alphabet).reshape(block_hays, hay_len)
+        k = planted_per_hay
+        if k and hay_len >= needle_len:
+            which = rng.integers(0, n_needles, size=(block_hays, k))
+            pos = rng.integers(0, hay_len - needle_len + 1, size=(block_hays, k))
+            pos[:, 0] = 0
+            if k > 1:
+                pos[:, 1] = hay_len - needle_len
+            for j in range(k):
+                hay[rows, pos[:, j][:, None] + cols[None, :]] = needles_arr[which[:, j]]
+        out[b * block_hays:(b + 1) * block_hays] = hay
+
+    if n_blocks >= 8:                      # numpy's generators release the GIL: blocks are independent
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+        with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as pool:
+            list(pool.map(make, range(n_blocks)))
+    else:
+        for b in range(n_blocks):
+            make(b)
+    return out.reshape(-1)
 
 
 def cfg3(n_patterns: int = 100_000, min_len: int = 8, max_len: int = 64, hay_bytes: int = 1 << 30,
