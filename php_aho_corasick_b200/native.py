@@ -369,9 +369,9 @@ class Automaton:
             raise AcError(last_error())
         return t
 
-    def search_batch_tally(self, haystacks, first_only: bool = False) -> Tally:
-        """ac_trie_search_batch() over separately allocated host strings (what the PHP extension holds) with the
-        library's tally callback.  `haystacks`: list of bytes / uint8 arrays (kept alive by the caller)."""
+    @staticmethod
+    def make_texts(haystacks):
+        """list of bytes / uint8 arrays -> (AC_TEXT_t array, n, the arrays that own the bytes)"""
         n = len(haystacks)
         texts = (AcText * max(1, n))()
         keep = []
@@ -380,6 +380,12 @@ class Automaton:
             keep.append(a)
             texts[i].astring = a.ctypes.data if a.size else None
             texts[i].length = a.size
+        return texts, n, keep
+
+    def search_batch_tally(self, haystacks=None, first_only: bool = False, texts=None) -> Tally:
+        """ac_trie_search_batch() over separately allocated host strings (what the PHP extension holds) with the
+        library's tally callback.  `haystacks`: list of bytes / uint8 arrays, or `texts` = make_texts(...) built once."""
+        texts, n, _keep = texts if texts is not None else self.make_texts(haystacks)
         t = Tally()
         cb = C.cast(self.L.acb200_tally_cb, BATCH_CB)
         rc = self.L.ac_trie_search_batch(self.h, texts, n, int(first_only), cb, C.cast(C.byref(t), C.c_void_p))

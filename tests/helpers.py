@@ -3,13 +3,24 @@ from __future__ import annotations
 
 import numpy as np
 
+from oracle import pydriver
 from oracle.pydriver import Driver
 
 
-def oracle_hits(patterns_calls, haystacks, first_only=False, kind="oracle"):
+def checker_kind(patterns_calls):
+    """The reference's own compiled code (oracle/_ref) wherever its finalize is cheap — it is quadratic in the depth
+    per node and quartic on nested chains — else the C restatement, which tests/test_oracle.py pins to it."""
+    if not pydriver.available("reference"):
+        return "oracle"
+    n = sum(len(c) for c in patterns_calls)
+    longest = max((len(p) for c in patterns_calls for p in c), default=0)
+    return "reference" if n <= 5000 and longest <= 128 else "oracle"
+
+
+def oracle_hits(patterns_calls, haystacks, first_only=False, kind=None):
     """patterns_calls: list of pattern lists, one per init()/add_patterns() call.
     -> list per haystack of (pos[], ordinal[], n_events, hash)"""
-    d = Driver(kind)
+    d = Driver(kind or checker_kind(patterns_calls))
     for call in patterns_calls:
         d.add_php_order(call)
     d.finalize()
