@@ -243,10 +243,14 @@ bool Engine::build(const FlatAutomaton &f, int dev, const Engine *table_src)
             gt_log2_ = f.gt_log2;
         }
         CU_OK(cudaStreamSynchronize(st));
-        CU_OK(cudaFuncSetAttribute(ac_filter_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
-        CU_OK(cudaFuncSetAttribute(ac_filter_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
-        CU_OK(cudaFuncSetAttribute(ac_filter_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
-        CU_OK(cudaFuncSetAttribute(ac_filter_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
+        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
+        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
+        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
+        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
+        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
+        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
+        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
+        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
     }
     info.filter_word = (int32_t)filter_w_;
     info.min_pattern_len = f.min_pattern_len;
@@ -524,10 +528,15 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
 }
 
 template <int W>
-static void launch_filter_k(const FilterArgs &fa, bool l2, unsigned grid, cudaStream_t st)
+static void launch_filter_k(const FilterArgs &fa, const VerifyArgs &va, bool l2, bool verify, unsigned grid, cudaStream_t st)
 {
-    if (l2) ac_filter_kernel<W, true><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa);
-    else ac_filter_kernel<W, false><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa);
+    if (l2) {
+        if (verify) ac_filter_verify_kernel<W, true, true><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa, va);
+        else ac_filter_verify_kernel<W, true, false><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa, va);
+    } else {
+        if (verify) ac_filter_verify_kernel<W, false, true><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa, va);
+        else ac_filter_verify_kernel<W, false, false><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa, va);
+    }
 }
 
 template <typename E, int W>
@@ -558,7 +567,11 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     stats.chunk_bytes = SPAN_BYTES;
     stats.filtered = 1;
     if (events_cap_ == 0 && !ensure_events(std::max<size_t>(1 << 16, total / 64))) return false;
-    if (!ensure_mask((size_t)n_spans * NB)) return false;
+    // bit planes, then per span: settled-event count (1 word) and SPAN_CAP event slots (8 bytes each)
+    const size_t span_words = (size_t)n_spans * (NB + 1 + 2 * SPAN_CAP);
+    if (!ensure_mask(span_words + 4)) return false;
+    uint32_t *const d_span_cnt = d_mask_ + (size_t)n_spans * NB;
+    uint2 *const d_span_out = (uint2 *)(d_mask_ + (((size_t)n_spans * (NB + 1) + 1) & ~(size_t)1));
 
     const uint32_t warm = (halo_ + W - 1) / W * W;
     // walking a whole tile costs ~(512 + halo) steps per lane, a flagged word (warm + W) steps on one lane
@@ -613,6 +626,8 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     va.gt_slots = direct ? (const uint4 *)d_gt_slots_ : nullptr;
     va.gt_pat = d_gt_pat_;
     va.gt_log2 = direct ? gt_log2_ : 0u;
+    va.span_cnt = d_span_cnt;
+    va.span_out = d_span_out;
     va.items = d_items_;
     va.desc = (uint2 *)d_desc_;
     va.recs = (uint2 *)d_recs_;
@@ -646,8 +661,11 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
             fa.span_begin = 0;
             fa.span_end = n_spans;
             const unsigned grid_f = std::min<uint32_t>((n_spans + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
-            if (W == 8) launch_filter_k<8>(fa, d_l2_ != nullptr, grid_f, st);
-            else launch_filter_k<4>(fa, d_l2_ != nullptr, grid_f, st);
+            // flagged words are settled inside the filter pass where one comparison decides them and the batch is one
+            // haystack or equal-length haystacks (no offset search inside the streaming loop)
+            const bool verify = direct && uniform_len != 0 && tune_direct != 2;
+            if (W == 8) launch_filter_k<8>(fa, va, d_l2_ != nullptr, verify, grid_f, st);
+            else launch_filter_k<4>(fa, va, d_l2_ != nullptr, verify, grid_f, st);
             stats.kernel_launches += 1;
         }
         CU_OK(cudaEventRecord(EV(ev_[4]), st));

@@ -249,6 +249,14 @@ struct Scanner {
     // EMIT mode
     uint2 *out;
     uint32_t obase, cap;
+    uint2 pend;              // event at an even output index, waiting to be stored together with its successor
+    bool have_pend;
+
+    __device__ __forceinline__ void flush_pending()
+    {
+        if (have_pend) { out[obase + cnt - 1u] = pend; have_pend = false; }
+    }
+
     bool found;   // FIRST: an event was taken in the current haystack segment
 
     __device__ __forceinline__ uint32_t cls(uint32_t b) const
@@ -283,8 +291,20 @@ struct Scanner {
             found = true;
         }
         if (EMIT) {
+            // Dense slices: every lane writes into its own region, so a warp store touches 32 different sectors and
+            // what it costs is store wavefronts, not bytes.  Two events go out as ONE 16-byte store (the event at an
+            // even index waits in registers for its successor; flush_pending() writes a last odd one).
             const uint32_t o = obase + cnt;
-            if (o < cap) out[o] = make_uint2(pos, s);
+            if (o < cap) {
+                if ((reinterpret_cast<uintptr_t>(out + o) & 15u) == 0u) { pend = make_uint2(pos, s); have_pend = true; }
+                else if (have_pend) {
+                    *reinterpret_cast<uint4 *>(out + (o - 1u)) = make_uint4(pend.x, pend.y, pos, s);
+                    have_pend = false;
+                } else out[o] = make_uint2(pos, s);
+            } else if (have_pend) {                    // the buffer ends between the two: the waiting one goes out alone
+                out[o - 1u] = pend;
+                have_pend = false;
+            }
         } else {
             if (cnt == 0) { e0p = pos; e0s = s; }
             else if (cnt == 1) { e1p = pos; e1s = s; }
@@ -504,7 +524,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_kernel(const ScanArgs
                 // dense slice: walk it again from the saved entry state and write in place
                 sc.obase = off;
                 sc.cnt = 0;
+                sc.have_pend = false;
                 scan_slice<true>(a, sc, s_cs, h, cs, ce);
+                sc.flush_pending();
             }
         }
         __syncwarp();
