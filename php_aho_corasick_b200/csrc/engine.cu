@@ -243,14 +243,14 @@ bool Engine::build(const FlatAutomaton &f, int dev, const Engine *table_src)
             gt_log2_ = f.gt_log2;
         }
         CU_OK(cudaStreamSynchronize(st));
-        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
-        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
-        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
-        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
-        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
-        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
-        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
-        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES)));
+        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_L1_BYTES + VQ_BYTES))));
+        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_L1_BYTES + VQ_BYTES))));
+        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_L1_BYTES + VQ_BYTES))));
+        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_L1_BYTES + VQ_BYTES))));
+        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_L1_BYTES + VQ_BYTES))));
+        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_L1_BYTES + VQ_BYTES))));
+        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_L1_BYTES + VQ_BYTES))));
+        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_L1_BYTES + VQ_BYTES))));
     }
     info.filter_word = (int32_t)filter_w_;
     info.min_pattern_len = f.min_pattern_len;
@@ -334,8 +334,9 @@ bool Engine::ensure_verify_scratch(size_t n_tiles)
     CU_OK(cudaMalloc(&d_items_, cap * VER_DENSE_MAX * sizeof(uint32_t)));
     CU_OK(cudaMalloc(&d_recs_, cap * VER_DENSE_MAX * 2 * sizeof(uint32_t)));
     CU_OK(cudaMalloc(&d_desc_, cap * 2 * sizeof(uint32_t)));
-    // one block: [16 counters | block sums | events per tile | offsets per tile] — the first three are zeroed by ONE memset
-    CU_OK(cudaMalloc(&d_tile_len_, (16 + (cap / EMIT_THREADS + 16) + 2 * cap) * sizeof(uint32_t)));
+    // one block: [16 counters | block sums | events per tile | slow marks per tile | offsets per tile] — all but the
+    // last are zeroed by ONE memset
+    CU_OK(cudaMalloc(&d_tile_len_, (16 + (cap / EMIT_THREADS + 16) + 3 * cap) * sizeof(uint32_t)));
     verify_tiles_cap_ = cap;
     return true;
 }
@@ -531,11 +532,11 @@ template <int W>
 static void launch_filter_k(const FilterArgs &fa, const VerifyArgs &va, bool l2, bool verify, unsigned grid, cudaStream_t st)
 {
     if (l2) {
-        if (verify) ac_filter_verify_kernel<W, true, true><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa, va);
-        else ac_filter_verify_kernel<W, true, false><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa, va);
+        if (verify) ac_filter_verify_kernel<W, true, true><<<grid, SCAN_THREADS, FILTER_L1_BYTES + VQ_BYTES, st>>>(fa, va);
+        else ac_filter_verify_kernel<W, true, false><<<grid, SCAN_THREADS, FILTER_L1_BYTES + VQ_BYTES, st>>>(fa, va);
     } else {
-        if (verify) ac_filter_verify_kernel<W, false, true><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa, va);
-        else ac_filter_verify_kernel<W, false, false><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa, va);
+        if (verify) ac_filter_verify_kernel<W, false, true><<<grid, SCAN_THREADS, FILTER_L1_BYTES + VQ_BYTES, st>>>(fa, va);
+        else ac_filter_verify_kernel<W, false, false><<<grid, SCAN_THREADS, FILTER_L1_BYTES + VQ_BYTES, st>>>(fa, va);
     }
 }
 
@@ -632,7 +633,8 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     va.desc = (uint2 *)d_desc_;
     va.recs = (uint2 *)d_recs_;
     va.tile_len = vtile_len;
-    va.tile_off = vtile_len + verify_tiles_cap_;
+    va.tile_slow = vtile_len + verify_tiles_cap_;
+    va.tile_off = vtile_len + 2 * verify_tiles_cap_;
     va.block_sum = vblock_sum;
 
     // tune_direct: 0 / 1 flagged words are settled by one comparison inside ac_walk_kernel where the gram table allows;
@@ -655,9 +657,9 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
             a.capacity = (uint32_t)std::min<size_t>(async_cap_, 0xffffffffu);
         }
         // counters, block sums and events per tile (the walk kernel adds to both) are adjacent: one memset
-        CU_OK(cudaMemsetAsync(vcounters, 0, (size_t)((vtile_len - vcounters) + n_tiles) * sizeof(uint32_t), st));
+        CU_OK(cudaMemsetAsync(vcounters, 0, (size_t)((vtile_len - vcounters) + verify_tiles_cap_ + n_tiles) * sizeof(uint32_t), st));
         CU_OK(cudaEventRecord(EV(ev_[0]), st));
-        if (attempt == 0) {      // the bit planes survive a regrow of the event buffer
+        {                        // (a regrow of the event buffer repeats the whole step: the filter pass counts events too)
             fa.span_begin = 0;
             fa.span_end = n_spans;
             const unsigned grid_f = std::min<uint32_t>((n_spans + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
@@ -715,7 +717,7 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
         stats.kernel_ms += ms_f + ms_v + ms_r;
         const size_t found = h_counters_[1];
         end_state_ = h_counters_[2];
-        if (attempt == 0) stats.flagged_words = h_counters_[3];
+        stats.flagged_words = h_counters_[3];
         stats.dense_tiles = h_counters_[4];
         if (found <= events_cap_) {
             n_events_ = found; stats.events = found;

@@ -52,7 +52,7 @@ constexpr int FILTER_UNROLL = 6;           // 16-byte loads in flight per thread
 constexpr uint32_t VER_DENSE_MAX = 64;     // flagged words per 16 KiB tile beyond which the whole tile is walked
 constexpr uint32_t ITEM_SPAN = 0x80000000u;// work item: walk 512-byte span (item & ~ITEM_SPAN) completely
 constexpr uint32_t ITEM_NONE = 0xffffffffu;
-constexpr uint32_t SPAN_CAP = 4;           // events of one span the filter pass can settle itself
+constexpr uint32_t SPAN_CAP = 4;           // flagged words of one span the filter pass settles itself
 constexpr uint32_t SPAN_SLOW = 0x80000000u;// span_cnt: this span (hence its tile) goes through collect / walk / emit
 constexpr uint32_t DESC_FAST = 0xffffffffu;// desc[tile].x: every span of the tile was settled by the filter pass
 constexpr int COLLECT_THREADS = 1024;      // 32 tiles per CTA iteration share one atomic (same-address atomics serialise)
@@ -125,8 +125,9 @@ struct VerifyArgs {
     const uint4 *gt_slots;        // exact gram table (gram_table.hpp) or nullptr
     const uint32_t *gt_pat;       // its pattern store
     uint32_t gt_log2;             // 2^gt_log2 slots; 0: every flagged word is walked
-    uint32_t *span_cnt;           // per 512-byte span, written by ac_filter_verify_kernel: events it settled itself, or SPAN_SLOW
-    uint2 *span_out;              // per span SPAN_CAP event slots {end offset, state}: the settled events, in order
+    uint32_t *span_cnt;           // per 512-byte span, written by ac_filter_verify_kernel: its flagged words (<= SPAN_CAP), or SPAN_SLOW
+    uint2 *span_out;              // per span SPAN_CAP slots, one per flagged word in stream order: {end offset, state}, state 0 = no event
+    uint32_t *tile_slow;          // per tile (zeroed before the launch): non-zero = the filter pass could not settle all of it
     uint32_t *items;              // work items, tile runs in completion order (capacity n_tiles * VER_DENSE_MAX)
     uint2 *desc;                  // per tile {offset into items, count}
     uint2 *recs;                  // per item {state of the first event, count << 16 | first end - item origin}
@@ -142,12 +143,11 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
     constexpr uint32_t WORDS_PER_SPAN = 32u * NB;
     constexpr int N_WARPS = COLLECT_THREADS / 32;
     __shared__ uint32_t s_n[N_WARPS];
-    __shared__ uint32_t s_ev[N_WARPS];
     __shared__ uint32_t s_base;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t dense_tiles = 0;
 
-    // planes of the tile's 32 spans + what ac_filter_verify_kernel settled of them (cnt)
+    // planes of the tile's 32 spans + their span_cnt (flagged words the filter pass queued, or SPAN_SLOW)
     auto load_planes = [&](uint32_t tile, uint32_t (&pl)[NB], uint32_t &cnt) {
 #pragma unroll
         for (int j = 0; j < NB; ++j) pl[j] = 0;
@@ -173,15 +173,21 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
         load_planes(tile + gridDim.x * N_WARPS, next_planes, next_settled);      // in flight while this tile is compacted
         const uint32_t span = tile * 32u + lane;
         const bool active = tile < a.tile_end && span < a.n_spans;
-        // A tile whose spans were all settled by the filter pass needs no items: its events already sit in span_out.
-        // One slow span sends the WHOLE tile through the items (what the filter pass settled of it is ignored).
-        const bool fast = !__any_sync(0xffffffffu, (settled & SPAN_SLOW) != 0);
-        uint32_t fast_events = fast ? settled : 0u;
+        // A tile the filter pass settled completely needs no items: its events already sit in span_out and are
+        // counted.  Anything it could not settle (or a densely flagged tile) sends the WHOLE tile through the items;
+        // what the filter pass counted for it is taken back first.
+        uint32_t n_flagged = settled & ~SPAN_SLOW;
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) fast_events += __shfl_xor_sync(0xffffffffu, fast_events, d);
+        for (int d = 16; d > 0; d >>= 1) n_flagged += __shfl_xor_sync(0xffffffffu, n_flagged, d);
+        uint32_t slow_mark = 0;
+        if (lane == 0 && tile < a.tile_end) slow_mark = __ldg(a.tile_slow + tile);
+        const bool fast = !__any_sync(0xffffffffu, (settled & SPAN_SLOW) != 0 || slow_mark != 0) && n_flagged <= a.dense_max;
         if (fast) {
 #pragma unroll
             for (int j = 0; j < NB; ++j) planes[j] = 0;
+        } else if (lane == 0 && tile < a.tile_end) {
+            const uint32_t counted = a.tile_len[tile];
+            if (counted) { a.tile_len[tile] = 0; atomicSub(&a.block_sum[tile / EMIT_THREADS], counted); }
         }
         uint32_t cnt = 0;
 #pragma unroll
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
         const bool dense = n_cand > a.dense_max;       // cheaper to walk the whole tile
         const uint32_t n_act = __popc(__ballot_sync(0xffffffffu, active));
         const uint32_t n = dense ? n_act : n_cand;
-        if (lane == 0) { s_n[warp] = n; s_ev[warp] = fast_events; }
+        if (lane == 0) s_n[warp] = n;
         __syncthreads();
         // every warp scans the 32 counts; one atomic per CTA iteration reserves the items of all 32 tiles
         const uint32_t v = s_n[lane];
@@ -208,17 +214,10 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
         }
         const uint32_t cta_total = __shfl_sync(0xffffffffu, wincl, 31);
         if (threadIdx.x == 0) s_base = a.item_base + (cta_total ? atomicAdd(&a.s.counters[a.counter_slot], cta_total) : 0u);
-        if (warp == 1) {          // the settled events of this iteration's 32 tiles (one block of EMIT_THREADS tiles): one atomic
-            uint32_t e = s_ev[lane];
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) e += __shfl_xor_sync(0xffffffffu, e, d);
-            if (lane == 0 && e) atomicAdd(&a.block_sum[tile0 / EMIT_THREADS], e);
-        }
         __syncthreads();
         const uint32_t base = s_base + __shfl_sync(0xffffffffu, wincl - v, warp);
         if (lane == 0 && tile < a.tile_end) {
-            a.desc[tile] = fast ? make_uint2(DESC_FAST, fast_events) : make_uint2(base, n);
-            if (fast && fast_events) a.tile_len[tile] = fast_events;
+            a.desc[tile] = fast ? make_uint2(DESC_FAST, n_flagged) : make_uint2(base, n);
         }
         if (n == 0) {
         } else if (dense) {
@@ -568,118 +567,61 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
 
 // ------------------------------------------------------ filter + verify ---
 
-// ac_filter_kernel with the verification folded in.  A warp that has just tested the 64 (W = 8) or 128 (W = 4)
-// words of a 512-byte span still holds the span in its registers: lane c has chunk c, the word before and after a
-// flagged word are its own or one shuffle away.  So the lanes with a flagged word settle it on the spot — one
-// probe of the exact gram table (gram_table.hpp, L2-resident) and one comparison, no second pass over the
-// haystack, no random DRAM read per flagged word — and write the span's events, in order, to its SPAN_CAP slots;
-// span_cnt[span] says how many.  What cannot be settled that way (a key several patterns share, a window cut by a
-// haystack or stream end, ragged batches, more than SPAN_CAP events, densely flagged tiles) marks the span
-// SPAN_SLOW: its tile takes the collect / walk path below, exactly as before.  The bit planes are written
-// regardless (that path reads them).
+// The filter pass with the verification folded in.
 //
-// The haystack arrives through a rotating register pipeline: the load of span i + U is issued the moment span
-// i's registers are free, so U - 1 loads stay in flight while a span is tested and verified.
-template <int W, bool VERIFY, typename TEST>
-__device__ __forceinline__ uint32_t filter_verify_span(const FilterArgs &fa, const VerifyArgs &a, TEST test, const uint4 &v, uint32_t g,
-                                                       uint32_t lane)
+// A warp streams 512-byte spans (U loads in flight), tests every aligned word against the bitmap and ballots the
+// flag bits into the span's bit planes — and instead of leaving every flagged word to a later kernel (one random
+// DRAM read each, long after the span has left the caches), it puts the word on a small queue of its own in shared
+// memory.  Whenever 32 words have gathered, the warp settles them together, one per lane: the three groups around
+// the word come from L2 (the warp read them microseconds ago), one probe of the exact gram table (gram_table.hpp)
+// and one comparison decide it.  The round is issued right after the next U loads, so its two round trips to L2
+// hide behind their trip to HBM.  Result per flagged word: its slot span_out[span * SPAN_CAP + rank of the word
+// among the span's flagged words] = the event, or state 0 for "nothing ends here"; span_cnt[span] = flagged
+// words of the span; events are counted per tile and per block of tiles (tile_len, block_sum) as ac_walk_kernel
+// does.  What cannot be settled that way — a key several patterns share, a window cut by a haystack or stream end,
+// ragged batches, more than SPAN_CAP flagged words in a span — marks the tile in tile_slow: ac_collect_kernel
+// takes the count back and sends the whole tile through the items / ac_walk_kernel as before.  The bit planes are
+// written regardless (that path reads them).
+constexpr uint32_t VQ_SLOTS = 48;          // queue entries per warp (a flush leaves < 32, a span adds <= SPAN_CAP)
+constexpr uint32_t VQ_BYTES = (SCAN_THREADS / 32) * VQ_SLOTS * 4;
+constexpr uint32_t VQ_RANK_SHIFT = 30;     // entry = word index | rank << 30 (word index < 2^30: streams stay below 4 GiB)
+
+// settles up to 32 queued words, one per lane (called by the whole warp)
+template <int W>
+__device__ __noinline__ void verify_round(const VerifyArgs &a, uint32_t entry, bool have)
 {
-    constexpr int NB = 16 / W;
-    typedef typename GramChunk<W>::type chunk_t;
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    // byte after the lane's last word: the next lane's first byte; lane 31 does not know it
-    const uint32_t next_w0 = __shfl_down_sync(0xffffffffu, w[0], 1);
-    const uint32_t after = (lane == 31u) ? FILTER_NEXT_UNKNOWN : (next_w0 & 0xffu);
-    bool p[NB];
-    uint32_t plane[NB];
-    uint32_t m = 0, mine = 0;
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-        const uint32_t nb = (j == NB - 1) ? after : (((W == 8) ? w[2] : w[j + 1]) & 0xffu);
-        p[j] = (W == 8) ? test(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test(w[j], 0u, nb, j == NB - 1);
-        plane[j] = __ballot_sync(0xffffffffu, p[j]);
-        m |= plane[j];
-        if (lane == (uint32_t)j) mine = plane[j];
-    }
-    uint32_t cnt = 0;                                   // warp-uniform: what span_cnt[g] becomes
-    if (m) {                                            // warp-uniform
-        if (!VERIFY) cnt = SPAN_SLOW;
-        else {
-            // the word before the lane's first one and the word after its last one
-            uint32_t pm_lo, pm_hi = 0, nx_lo = next_w0, nx_hi = 0;
-            if (W == 8) {
-                pm_lo = __shfl_up_sync(0xffffffffu, w[2], 1);
-                pm_hi = __shfl_up_sync(0xffffffffu, w[3], 1);
-                nx_hi = __shfl_down_sync(0xffffffffu, w[1], 1);
-            } else {
-                pm_lo = __shfl_up_sync(0xffffffffu, w[3], 1);
-            }
-            bool slow = false;
-            uint32_t ev_end[NB], ev_state[NB];
-            bool ev_has[NB];
-#pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                ev_has[j] = false; ev_end[j] = 0; ev_state[j] = 0;
-                if (p[j]) {
-                    const uint32_t k = g * (32u * NB) + lane * NB + j;          // word index in the stream
-                    const uint32_t rs = (k + 1u) * W;                           // it owns the end offsets rs+1 .. rs+W
-                    bool can = rs >= a.warm && rs + W <= a.s.total;
-                    uint32_t w0 = 0;
-                    if (can) {
-                        // (equal-length batches and single haystacks only: no search through an offset array here)
-                        const uint32_t h = rs / a.s.uniform_len;
-                        const uint32_t hb = h * a.s.uniform_len;
-                        w0 = max(rs - a.warm, hb);
-                        can = hb + a.s.uniform_len >= rs + W && ((rs - w0) & (uint32_t)(W - 1)) == 0 && w0 < rs;
-                    }
-                    if (!can) slow = true;
-                    else {
-                        chunk_t c_prev, c_word, c_next;
-                        const uint8_t *text = a.s.text;
-                        if (W == 8) {
-                            const uint64_t A = ((uint64_t)w[1] << 32) | w[0], B = ((uint64_t)w[3] << 32) | w[2];
-                            const uint64_t P = ((uint64_t)pm_hi << 32) | pm_lo, N = ((uint64_t)nx_hi << 32) | nx_lo;
-                            c_prev = (chunk_t)(j == 0 ? P : A); c_word = (chunk_t)(j == 0 ? A : B); c_next = (chunk_t)(j == 0 ? B : N);
-                        } else {
-                            c_prev = (chunk_t)(j == 0 ? pm_lo : w[(j + 3) & 3]); c_word = (chunk_t)w[j]; c_next = (chunk_t)(j == NB - 1 ? nx_lo : w[(j + 1) & 3]);
-                        }
-                        // the neighbours of the span's first / last word are in another warp's registers
-                        if (lane == 0u && j == 0) c_prev = group_chunk<W>(ld_group<W>(text, rs - 2u * W));
-                        if (lane == 31u && j == NB - 1) c_next = group_chunk<W>(ld_group<W>(text, rs));
-                        ItemEvents ev{0u, 0u, 0u};
-                        const bool settled = verify_word_direct<W>(a, rs, w0, [=](uint32_t i) -> chunk_t {
-                            return (i == rs) ? c_next : (i == rs - W) ? c_word : (i == rs - 2u * W) ? c_prev
-                                                                                                   : group_chunk<W>(ld_group<W>(text, i)); }, ev);
-                        if (!settled) slow = true;
-                        else if (ev.cnt) { ev_has[j] = true; ev_end[j] = ev.e0p; ev_state[j] = ev.e0s; }
-                    }
-                }
-            }
-            if (__any_sync(0xffffffffu, slow)) cnt = SPAN_SLOW;
-            else {
-                // events in stream order = by lane, then by word inside the lane
-                uint32_t em[NB], n = 0, before = 0;
-#pragma unroll
-                for (int j = 0; j < NB; ++j) {
-                    em[j] = __ballot_sync(0xffffffffu, ev_has[j]);
-                    n += __popc(em[j]);
-                    before += __popc(em[j] & ((1u << lane) - 1u));
-                }
-                if (n > SPAN_CAP) cnt = SPAN_SLOW;
-                else {
-                    cnt = n;
-#pragma unroll
-                    for (int j = 0; j < NB; ++j) {
-                        if (ev_has[j]) a.span_out[(size_t)g * SPAN_CAP + before] = make_uint2(ev_end[j], ev_state[j]);
-                        before += ev_has[j] ? 1u : 0u;
-                    }
-                }
-            }
+    constexpr uint32_t NB = 16u / W;
+    ItemEvents ev{0u, 0u, 0u};
+    bool slow = false;
+    uint32_t span = 0, rank = 0;
+    if (have) {
+        const uint32_t k = entry & ((1u << VQ_RANK_SHIFT) - 1u);
+        rank = entry >> VQ_RANK_SHIFT;
+        span = k / (32u * NB);
+        const uint32_t rs = (k + 1u) * W;                    // the word owns the end offsets rs+1 .. rs+W
+        bool can = rs >= a.warm && rs + W <= a.s.total;
+        uint32_t w0 = 0;
+        if (can) {
+            // (equal-length batches and single haystacks only: no search through an offset array here)
+            const uint32_t hb = rs / a.s.uniform_len * a.s.uniform_len;
+            w0 = max(rs - a.warm, hb);
+            can = hb + a.s.uniform_len >= rs + W && ((rs - w0) & (uint32_t)(W - 1)) == 0 && w0 < rs;
         }
+        slow = !can || !verify_word_direct<W>(a, rs, w0, ev);
+        if (slow) a.tile_slow[span >> 5] = 1u;
+        else a.span_out[(size_t)span * SPAN_CAP + rank] = ev.cnt ? make_uint2(ev.e0p, ev.e0s) : make_uint2(0u, 0u);
     }
-    if (lane < (uint32_t)NB) fa.mask[(size_t)g * NB + lane] = mine;
-    else if (lane == (uint32_t)NB) a.span_cnt[g] = cnt;
-    return (lane < (uint32_t)NB) ? (uint32_t)__popc(mine) : 0u;
+    // events per tile and per block of EMIT_THREADS tiles (one atomic per warp where the lanes agree on the block)
+    const bool has = have && !slow && ev.cnt;
+    if (has) atomicAdd(&a.tile_len[span >> 5], 1u);
+    const uint32_t blk = has ? (span >> 5) / EMIT_THREADS : 0xffffffffu;
+    const uint32_t voters = __ballot_sync(0xffffffffu, has);
+    if (voters) {
+        const uint32_t lead_blk = __shfl_sync(0xffffffffu, blk, __ffs(voters) - 1);
+        if (__all_sync(0xffffffffu, !has || blk == lead_blk)) {
+            if ((threadIdx.x & 31u) == 0u) atomicAdd(&a.block_sum[lead_blk], (uint32_t)__popc(voters));
+        } else if (has) atomicAdd(&a.block_sum[blk], 1u);
+    }
 }
 
 template <int W, bool L2, bool VERIFY>
@@ -693,8 +635,24 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_verify_kernel(const
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const uint32_t s_base = stage_bitmap(fa, s_bm, tid);
+    // this warp's queue of flagged words (shared-window byte address)
+    const uint32_t q_base = s_base + FILTER_L1_BYTES + (tid >> 5) * (VQ_SLOTS * 4u);
+    uint32_t qn = 0;                                          // queued words (warp-uniform)
     auto test = [&](uint32_t lo, uint32_t hi, uint32_t nb, bool maybe_unknown) -> bool {
         return test_word<L2>(fa, s_base, lo, hi, nb, maybe_unknown);
+    };
+    auto flush = [&]() {                                      // settles the first 32 queued words (or all, if fewer)
+        uint32_t entry = 0;
+        const bool have = lane < qn;
+        if (have) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(entry) : "r"(q_base + lane * 4u));
+        uint32_t moved = 0;                                   // what is left moves to the front
+        const bool more = lane + 32u < qn;
+        if (more) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(moved) : "r"(q_base + (lane + 32u) * 4u));
+        __syncwarp();
+        if (more) asm volatile("st.shared.u32 [%0], %1;" :: "r"(q_base + lane * 4u), "r"(moved));
+        qn = qn > 32u ? qn - 32u : 0u;
+        __syncwarp();
+        verify_round<W>(a, entry, have);
     };
 
     const uint32_t n_full_all = fa.total / SPAN_BYTES;        // spans that lie completely inside the stream
@@ -703,26 +661,63 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_verify_kernel(const
     const uint32_t warp = blockIdx.x * (SCAN_THREADS / 32) + (tid >> 5);
     uint32_t flagged = 0;
 
-    uint4 v[U];
-    uint32_t g_load = fa.span_begin + warp;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        v[u] = make_uint4(0, 0, 0, 0);
-        if (g_load < n_full) v[u] = ld_text16(fa.text + ((size_t)g_load * 32u + lane) * 16u);
-        g_load += n_warps;
-    }
-    uint32_t g = fa.span_begin + warp;
-    while (g < n_full) {
+    for (uint32_t g0 = fa.span_begin + warp; g0 < n_full; g0 += n_warps * U) {
+        uint4 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
+            const uint32_t g = g0 + u * n_warps;
+            v[u] = make_uint4(0, 0, 0, 0);
+            if (g < n_full) v[u] = ld_text16(fa.text + ((size_t)g * 32u + lane) * 16u);
+        }
+        if (VERIFY && qn >= 32u) flush();                     // its L2 round trips hide behind the loads just issued
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t g = g0 + u * n_warps;
             if (g >= n_full) break;                           // warp-uniform
-            const uint4 cur = v[u];
-            if (g_load < n_full) v[u] = ld_text16(fa.text + ((size_t)g_load * 32u + lane) * 16u);
-            g_load += n_warps;
-            flagged += filter_verify_span<W, VERIFY>(fa, a, test, cur, g, lane);
-            g += n_warps;
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            // byte after the lane's last word: the next lane's first byte; lane 31 does not know it
+            uint32_t after = __shfl_down_sync(0xffffffffu, w[0], 1) & 0xffu;
+            if (lane == 31u) after = FILTER_NEXT_UNKNOWN;
+            uint32_t mine = 0, n_flag = 0;
+            bool p[NB];
+            uint32_t plane[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const uint32_t nb = (j == NB - 1) ? after : (((W == 8) ? w[2] : w[j + 1]) & 0xffu);
+                p[j] = (W == 8) ? test(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test(w[j], 0u, nb, j == NB - 1);
+                plane[j] = __ballot_sync(0xffffffffu, p[j]);
+                n_flag += __popc(plane[j]);
+                if (lane == (uint32_t)j) mine = plane[j];
+            }
+            uint32_t cnt = n_flag;                            // what span_cnt[g] becomes
+            if (n_flag) {                                     // warp-uniform
+                if (!VERIFY || n_flag > SPAN_CAP) {
+                    cnt = SPAN_SLOW;
+                    if (lane == 0u) a.tile_slow[g >> 5] = 1u;
+                } else {
+                    // queue the flagged words in stream order: by lane, then by word inside the lane
+                    uint32_t rank = 0;
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) rank += __popc(plane[j] & ((1u << lane) - 1u));
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        if (p[j]) {
+                            const uint32_t k = g * (32u * NB) + lane * NB + j;
+                            asm volatile("st.shared.u32 [%0], %1;" :: "r"(q_base + (qn + rank) * 4u), "r"(k | (rank << VQ_RANK_SHIFT)));
+                            ++rank;
+                        }
+                    }
+                    qn += n_flag;
+                    __syncwarp();
+                }
+            }
+            if (lane < (uint32_t)NB) fa.mask[(size_t)g * NB + lane] = mine;
+            else if (lane == (uint32_t)NB) a.span_cnt[g] = cnt;
+            if (lane < (uint32_t)NB) flagged += __popc(mine);
+            if (VERIFY && qn >= VQ_SLOTS - SPAN_CAP) flush();      // (only with many flagged words per span)
         }
     }
+    while (VERIFY && qn) flush();
 
     // The last, partial span: complete 16-byte chunks are tested, the partial chunk at the very end is not
     // read at all — its words are simply handed on to verification (always through the collect / walk path).
@@ -748,7 +743,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_verify_kernel(const
         if (lane < (uint32_t)NB) {
             fa.mask[(size_t)n_full_all * NB + lane] = mine;
             flagged += __popc(mine);
-        } else if (lane == (uint32_t)NB) a.span_cnt[n_full_all] = m ? SPAN_SLOW : 0u;
+        } else if (lane == (uint32_t)NB) {
+            a.span_cnt[n_full_all] = m ? SPAN_SLOW : 0u;
+            if (m) a.tile_slow[n_full_all >> 5] = 1u;
+        }
     }
     if (lane < (uint32_t)NB && flagged) atomicAdd(&fa.counters[3], flagged);
 }
@@ -818,9 +816,18 @@ __global__ void __launch_bounds__(COUNT_THREADS) ac_emit_kernel(const __grid_con
         uint2 next_d;
         load_header(tile + n_warps, next_len, next_d, next_off);
         if (len && d.x == DESC_FAST) {
-            // every span of the tile was settled by the filter pass: lane l copies the events of span l
+            // the filter pass settled every flagged word of the tile: lane l copies the events of span l (a slot whose
+            // state is 0 belongs to a flagged word at which nothing ends)
             const uint32_t span = tile * 32u + lane;
-            const uint32_t c = (span < a.n_spans) ? a.span_cnt[span] : 0u;
+            const uint32_t nf = (span < a.n_spans) ? a.span_cnt[span] : 0u;
+            uint2 slot[SPAN_CAP];
+            uint32_t c = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < SPAN_CAP; ++k) {
+                slot[k] = make_uint2(0u, 0u);
+                if (k < nf) slot[k] = a.span_out[(size_t)span * SPAN_CAP + k];
+                c += slot[k].y ? 1u : 0u;
+            }
             uint32_t pincl = c;
 #pragma unroll
             for (int k = 1; k < 32; k <<= 1) {
@@ -828,8 +835,13 @@ __global__ void __launch_bounds__(COUNT_THREADS) ac_emit_kernel(const __grid_con
                 if (lane >= k) pincl += v;
             }
             uint32_t o = off + pincl - c;
-            for (uint32_t k = 0; k < c; ++k, ++o)
-                if (o < a.s.capacity) a.s.out[o] = a.span_out[(size_t)span * SPAN_CAP + k];
+#pragma unroll
+            for (uint32_t k = 0; k < SPAN_CAP; ++k) {
+                if (slot[k].y) {
+                    if (o < a.s.capacity) a.s.out[o] = slot[k];
+                    ++o;
+                }
+            }
         }
         const uint32_t n_items = (len && d.x != DESC_FAST) ? d.y : 0u;   // warp-uniform; 0: nothing left to do for this tile
         for (uint32_t i0 = 0; i0 < n_items; i0 += 32u) {             // warp-uniform

@@ -366,27 +366,54 @@ struct Scanner {
     // Walks bytes [i, end) of one haystack from state s.  REPORT: record every
     // reporting state (EMIT: straight into the output, else count + keep 2).
     // Text arrives through a three-deep register pipeline of 16-byte loads.
+    // The second walk of a dense slice, which writes its events in place.  Deliberately compact (one byte per
+    // iteration, nothing unrolled): this pass is bound by its stores, and a second unrolled copy of the 16-step
+    // switch would push the count pass's hot loop out of the instruction cache.
+    __device__ __forceinline__ uint32_t walk_emit(uint32_t s, uint32_t i, uint32_t end)
+    {
+#pragma unroll 1
+        while (i < end) {
+            uint32_t w, n = 1;
+            if ((i & 3u) == 0u && i + 4u <= end) { w = __ldg(reinterpret_cast<const uint32_t *>(text + i)); n = 4; }
+            else w = __ldg(text + i);
+#pragma unroll 1
+            for (uint32_t j = 0; j < n; ++j, ++i) {
+                const uint32_t b = (w >> (8u * j)) & 0xffu;
+                uint32_t e = 0;
+                if (s - win_lo < win_rows) e = hot_next(s, b);
+                if (e == 0) e = any_next(s, b);              // outside the window, or leaving it: the true entry
+                s = e;
+                if (s < final_bound) hit<true>(i + 1u, s);
+                if (FIRST && found) return s;
+            }
+        }
+        return s;
+    }
+
     template <bool REPORT, bool EMIT>
     __device__ __forceinline__ uint32_t walk(uint32_t s, uint32_t i, uint32_t end)
     {
-        while (i < end && (i & 15u)) { s = byte_step<REPORT, EMIT>(s, i); ++i; }
-        if (i + 16 <= end) {
-            uint4 v0 = ld_text16(text + i);
-            uint4 v1 = v0, v2 = v0;
-            if (i + 32 <= readable) v1 = ld_text16(text + i + 16);
-            if (i + 48 <= readable) v2 = ld_text16(text + i + 32);
-            while (true) {
-                uint4 v3 = v2;
-                if (i + 64 <= readable) v3 = ld_text16(text + i + 48);
-                s = walk_group<REPORT, EMIT>(s, v0, i);
-                i += 16;
-                if (REPORT && FIRST && found) return s;
-                if (i + 16 > end) break;
-                v0 = v1; v1 = v2; v2 = v3;
+        if constexpr (EMIT) return walk_emit(s, i, end);
+        else {
+            while (i < end && (i & 15u)) { s = byte_step<REPORT, EMIT>(s, i); ++i; }
+            if (i + 16 <= end) {
+                uint4 v0 = ld_text16(text + i);
+                uint4 v1 = v0, v2 = v0;
+                if (i + 32 <= readable) v1 = ld_text16(text + i + 16);
+                if (i + 48 <= readable) v2 = ld_text16(text + i + 32);
+                while (true) {
+                    uint4 v3 = v2;
+                    if (i + 64 <= readable) v3 = ld_text16(text + i + 48);
+                    s = walk_group<REPORT, EMIT>(s, v0, i);
+                    i += 16;
+                    if (REPORT && FIRST && found) return s;
+                    if (i + 16 > end) break;
+                    v0 = v1; v1 = v2; v2 = v3;
+                }
             }
+            while (i < end) { s = byte_step<REPORT, EMIT>(s, i); ++i; }
+            return s;
         }
-        while (i < end) { s = byte_step<REPORT, EMIT>(s, i); ++i; }
-        return s;
     }
 };
 
