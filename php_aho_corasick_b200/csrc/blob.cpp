@@ -5,6 +5,7 @@
 // description ac_trie_finalize() produces — breadth-first order, failure links, trie edges, output lists,
 // prefilter bitmaps, accepted patterns — is position independent, so it is written as is; loading replays
 // only the device part of finalize (table expansion + uploads).
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -121,18 +122,50 @@ bool load_flat(FlatAutomaton &fl, std::deque<std::string> &arena, const char *pa
         p.aux = (void *)(uintptr_t)aux;
     }
     fclose(f);
-    // structural checks before anything is indexed
+    // Structural checks before anything is indexed: a corrupt or truncated-then-padded file must fail to load, not
+    // corrupt host or device memory or silently drop matches.
+    auto ascending = [](const auto &v) {
+        for (size_t i = 1; i < v.size(); ++i) if (v[i] < v[i - 1]) return false;
+        return true;
+    };
     bool sane = r.ok && fl.n_rows == fl.n_states + 1 && fl.bfs_order.size() == fl.n_states && fl.fail.size() == (size_t)fl.n_rows &&
                 fl.edge_src.size() == fl.edge_dst.size() && fl.edge_src.size() == fl.edge_cls.size() &&
-                fl.level_off.size() == fl.level_edge_off.size() && !fl.level_off.empty() &&
-                fl.out_off.size() == (size_t)fl.final_bound && fl.root == fl.final_bound && fl.n_classes >= 1 && fl.n_classes <= 256 &&
-                (fl.out_off.empty() || fl.out_off.back() == fl.out_idx.size()) &&
-                (fl.filter_w == 0 || (fl.l1_bits && fl.l1.size() == fl.l1_bits / 32));
+                fl.level_off.size() == fl.level_edge_off.size() && fl.level_off.size() >= 2 &&
+                fl.out_off.size() == (size_t)fl.final_bound && fl.root == fl.final_bound && fl.root >= 1 && fl.root < fl.n_rows &&
+                fl.n_classes >= 1 && fl.n_classes <= 256 && fl.n_used_bytes <= 256 &&
+                (uint64_t)fl.n_rows * fl.n_classes < (1ull << 32);
+    // breadth-first levels partition the states and the edges
+    sane = sane && fl.level_off.front() == 0 && fl.level_off.back() == fl.n_states && ascending(fl.level_off) &&
+           fl.level_edge_off.front() == 0 && fl.level_edge_off.back() == fl.edge_src.size() && ascending(fl.level_edge_off);
+    // output lists: non-decreasing offsets that end at the list's length, every final state reports something
+    sane = sane && !fl.out_off.empty() && fl.out_off.front() == 0 && fl.out_off.back() == fl.out_idx.size() && ascending(fl.out_off);
+    for (size_t i = 0; sane && i + 1 < fl.out_off.size(); ++i) sane = fl.out_off[i + 1] > fl.out_off[i];
     for (size_t i = 0; sane && i < fl.out_idx.size(); ++i) sane = fl.out_idx[i] < np;
     for (size_t i = 0; sane && i < fl.bfs_order.size(); ++i) sane = fl.bfs_order[i] >= 1 && fl.bfs_order[i] < fl.n_rows;
     for (size_t i = 0; sane && i < fl.fail.size(); ++i) sane = fl.fail[i] < fl.n_rows;
     for (size_t i = 0; sane && i < fl.edge_src.size(); ++i)
-        sane = fl.edge_src[i] < fl.n_rows && fl.edge_dst[i] < fl.n_rows && fl.edge_cls[i] < fl.n_classes;
+        sane = fl.edge_src[i] >= 1 && fl.edge_src[i] < fl.n_rows && fl.edge_dst[i] >= 1 && fl.edge_dst[i] < fl.n_rows &&
+               fl.edge_cls[i] < fl.n_classes;
+    for (int b = 0; sane && b < 256; ++b) sane = fl.cls_map[b] < fl.n_classes;
+    // pattern lengths are recomputed, never trusted: a wrong Lmax shrinks the halo and drops matches, a wrong
+    // minimum breaks the prefilter's ">= 2W bytes" premise
+    uint32_t lmax = 0, lmin = 0;
+    for (size_t i = 0; sane && i < fl.accepted.size(); ++i) {
+        const size_t L = fl.accepted[i].ptext.length;
+        sane = L >= 1 && L <= AC_PATTRN_MAX_LENGTH;
+        lmax = std::max<uint32_t>(lmax, (uint32_t)L);
+        lmin = lmin ? std::min<uint32_t>(lmin, (uint32_t)L) : (uint32_t)L;
+    }
+    sane = sane && fl.max_pattern_len == lmax && fl.min_pattern_len == lmin;
+    // prefilter tables: the word size the kernels are built for, the bitmap size they stage, a level 2 of the size its
+    // hash addresses
+    sane = sane && (fl.filter_w == 0 || fl.filter_w == 4 || fl.filter_w == 8);
+    if (sane && fl.filter_w) {
+        sane = lmin >= 2 * fl.filter_w && fl.l1_bits == FILTER_L1_BITS && fl.l1.size() == FILTER_L1_BITS / 32 &&
+               (fl.l2_log2 == 0 ? fl.l2.empty() : (fl.l2_log2 >= 23 && fl.l2_log2 <= 30 && fl.l2.size() == ((size_t)1 << (fl.l2_log2 - 5))));
+    } else if (sane) {
+        sane = fl.l1.empty() && fl.l2.empty() && fl.l2_log2 == 0;
+    }
     if (!sane) { err = "truncated or corrupt blob"; return false; }
     fl.out_pat.resize(fl.out_idx.size());
     for (size_t i = 0; i < fl.out_idx.size(); ++i) fl.out_pat[i] = fl.accepted[fl.out_idx[i]];

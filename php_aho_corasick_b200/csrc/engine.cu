@@ -62,7 +62,7 @@ void Engine::release()
     cudaFree(d_out_off_); cudaFree(d_out_idx_); cudaFree(d_pat_len_); cudaFree(d_hit_sums_); cudaFree(d_hits_); cudaFree(d_hit_total_);
     d_out_off_ = nullptr; d_out_idx_ = nullptr; d_pat_len_ = nullptr; d_hit_sums_ = nullptr; d_hits_ = nullptr; d_hit_total_ = nullptr;
     hit_sums_cap_ = 0; hits_cap_ = 0;
-    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_);
+    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_); cudaFree(d_tile_ev_); d_tile_ev_ = nullptr;
     d_l1_ = nullptr; d_l2_ = nullptr; d_mask_ = nullptr; mask_cap_ = 0;
     d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; verify_tiles_cap_ = 0;
     if (h_counters_) cudaFreeHost(h_counters_);
@@ -328,12 +328,13 @@ bool Engine::ensure_mask(size_t words)
 bool Engine::ensure_verify_scratch(size_t n_tiles)
 {
     if (n_tiles <= verify_tiles_cap_) return true;
-    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_);
-    d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; verify_tiles_cap_ = 0;
+    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_); cudaFree(d_tile_ev_);
+    d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; d_tile_ev_ = nullptr; verify_tiles_cap_ = 0;
     const size_t cap = std::max(n_tiles + n_tiles / 4, (size_t)256);
     CU_OK(cudaMalloc(&d_items_, cap * VER_DENSE_MAX * sizeof(uint32_t)));
     CU_OK(cudaMalloc(&d_recs_, cap * VER_DENSE_MAX * 2 * sizeof(uint32_t)));
     CU_OK(cudaMalloc(&d_desc_, cap * 2 * sizeof(uint32_t)));
+    CU_OK(cudaMalloc(&d_tile_ev_, cap * TILE_CAP * 2 * sizeof(uint32_t)));
     // one block: [16 counters | block sums | events per tile | slow marks per tile | offsets per tile] — all but the
     // last are zeroed by ONE memset
     CU_OK(cudaMalloc(&d_tile_len_, (16 + (cap / EMIT_THREADS + 16) + 3 * cap) * sizeof(uint32_t)));
@@ -568,11 +569,7 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     stats.chunk_bytes = SPAN_BYTES;
     stats.filtered = 1;
     if (events_cap_ == 0 && !ensure_events(std::max<size_t>(1 << 16, total / 64))) return false;
-    // bit planes, then per span: settled-event count (1 word) and SPAN_CAP event slots (8 bytes each)
-    const size_t span_words = (size_t)n_spans * (NB + 1 + 2 * SPAN_CAP);
-    if (!ensure_mask(span_words + 4)) return false;
-    uint32_t *const d_span_cnt = d_mask_ + (size_t)n_spans * NB;
-    uint2 *const d_span_out = (uint2 *)(d_mask_ + (((size_t)n_spans * (NB + 1) + 1) & ~(size_t)1));
+    if (!ensure_mask((size_t)n_spans * NB)) return false;
 
     const uint32_t warm = (halo_ + W - 1) / W * W;
     // walking a whole tile costs ~(512 + halo) steps per lane, a flagged word (warm + W) steps on one lane
@@ -627,8 +624,10 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     va.gt_slots = direct ? (const uint4 *)d_gt_slots_ : nullptr;
     va.gt_pat = d_gt_pat_;
     va.gt_log2 = direct ? gt_log2_ : 0u;
-    va.span_cnt = d_span_cnt;
-    va.span_out = d_span_out;
+    va.tile_ev = (uint2 *)d_tile_ev_;
+    // flagged words are settled inside the filter pass where one comparison decides them and the batch is one haystack
+    // or equal-length haystacks (no offset search inside the streaming loop)
+    va.settled = (direct && uniform_len != 0 && tune_direct != 2) ? 1u : 0u;
     va.items = d_items_;
     va.desc = (uint2 *)d_desc_;
     va.recs = (uint2 *)d_recs_;
@@ -665,7 +664,7 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
             const unsigned grid_f = std::min<uint32_t>((n_spans + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
             // flagged words are settled inside the filter pass where one comparison decides them and the batch is one
             // haystack or equal-length haystacks (no offset search inside the streaming loop)
-            const bool verify = direct && uniform_len != 0 && tune_direct != 2;
+            const bool verify = va.settled != 0;
             if (W == 8) launch_filter_k<8>(fa, va, d_l2_ != nullptr, verify, grid_f, st);
             else launch_filter_k<4>(fa, va, d_l2_ != nullptr, verify, grid_f, st);
             stats.kernel_launches += 1;

@@ -52,8 +52,8 @@ constexpr int FILTER_UNROLL = 6;           // 16-byte loads in flight per thread
 constexpr uint32_t VER_DENSE_MAX = 64;     // flagged words per 16 KiB tile beyond which the whole tile is walked
 constexpr uint32_t ITEM_SPAN = 0x80000000u;// work item: walk 512-byte span (item & ~ITEM_SPAN) completely
 constexpr uint32_t ITEM_NONE = 0xffffffffu;
-constexpr uint32_t SPAN_CAP = 4;           // flagged words of one span the filter pass settles itself
-constexpr uint32_t SPAN_SLOW = 0x80000000u;// span_cnt: this span (hence its tile) goes through collect / walk / emit
+constexpr uint32_t SPAN_CAP = 4;           // flagged words of one span the filter pass queues (more: the tile takes the slow path)
+constexpr uint32_t TILE_CAP = 64;          // events of one 16 KiB tile the filter pass can store (more: slow path)
 constexpr uint32_t DESC_FAST = 0xffffffffu;// desc[tile].x: every span of the tile was settled by the filter pass
 constexpr int COLLECT_THREADS = 1024;      // 32 tiles per CTA iteration share one atomic (same-address atomics serialise)
 constexpr int COUNT_THREADS = 256;
@@ -125,8 +125,8 @@ struct VerifyArgs {
     const uint4 *gt_slots;        // exact gram table (gram_table.hpp) or nullptr
     const uint32_t *gt_pat;       // its pattern store
     uint32_t gt_log2;             // 2^gt_log2 slots; 0: every flagged word is walked
-    uint32_t *span_cnt;           // per 512-byte span, written by ac_filter_verify_kernel: its flagged words (<= SPAN_CAP), or SPAN_SLOW
-    uint2 *span_out;              // per span SPAN_CAP slots, one per flagged word in stream order: {end offset, state}, state 0 = no event
+    uint32_t settled;             // 1: ac_filter_verify_kernel settled flagged words itself (tile_ev / tile_slow are meaningful)
+    uint2 *tile_ev;               // per tile TILE_CAP slots {end offset, state}: the events the filter pass settled, unordered
     uint32_t *tile_slow;          // per tile (zeroed before the launch): non-zero = the filter pass could not settle all of it
     uint32_t *items;              // work items, tile runs in completion order (capacity n_tiles * VER_DENSE_MAX)
     uint2 *desc;                  // per tile {offset into items, count}
@@ -147,14 +147,11 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t dense_tiles = 0;
 
-    // planes of the tile's 32 spans + their span_cnt (flagged words the filter pass queued, or SPAN_SLOW)
-    auto load_planes = [&](uint32_t tile, uint32_t (&pl)[NB], uint32_t &cnt) {
+    auto load_planes = [&](uint32_t tile, uint32_t (&pl)[NB]) {
 #pragma unroll
         for (int j = 0; j < NB; ++j) pl[j] = 0;
-        cnt = 0;
         const uint32_t span = tile * 32u + lane;
         if (tile < a.tile_end && span < a.n_spans) {
-            cnt = __ldg(a.span_cnt + span);
             if (NB == 2) {
                 const uint2 m = __ldg(reinterpret_cast<const uint2 *>(a.mask) + span);
                 pl[0] = m.x; pl[1] = m.y;
@@ -166,28 +163,32 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
     };
 
     // a CTA iteration takes 32 consecutive tiles, one per warp; the loop bound is CTA-uniform
-    uint32_t planes[NB], next_planes[NB], settled, next_settled;
-    load_planes(a.tile_begin + blockIdx.x * N_WARPS + warp, planes, settled);
+    uint32_t planes[NB], next_planes[NB];
+    load_planes(a.tile_begin + blockIdx.x * N_WARPS + warp, planes);
     for (uint32_t tile0 = a.tile_begin + blockIdx.x * N_WARPS; tile0 < a.tile_end; tile0 += gridDim.x * N_WARPS) {
         const uint32_t tile = tile0 + warp;
-        load_planes(tile + gridDim.x * N_WARPS, next_planes, next_settled);      // in flight while this tile is compacted
+        load_planes(tile + gridDim.x * N_WARPS, next_planes);      // in flight while this tile is compacted
         const uint32_t span = tile * 32u + lane;
         const bool active = tile < a.tile_end && span < a.n_spans;
-        // A tile the filter pass settled completely needs no items: its events already sit in span_out and are
+        // A tile the filter pass settled completely needs no items: its events already sit in tile_ev and are
         // counted.  Anything it could not settle (or a densely flagged tile) sends the WHOLE tile through the items;
         // what the filter pass counted for it is taken back first.
-        uint32_t n_flagged = settled & ~SPAN_SLOW;
+        uint32_t n_flagged = 0;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) n_flagged += __popc(planes[j]);
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) n_flagged += __shfl_xor_sync(0xffffffffu, n_flagged, d);
-        uint32_t slow_mark = 0;
-        if (lane == 0 && tile < a.tile_end) slow_mark = __ldg(a.tile_slow + tile);
-        const bool fast = !__any_sync(0xffffffffu, (settled & SPAN_SLOW) != 0 || slow_mark != 0) && n_flagged <= a.dense_max;
+        uint32_t fast_word = 0;                            // lane 0 decides, everyone follows
+        if (a.settled && lane == 0 && tile < a.tile_end) {
+            const uint32_t counted = a.tile_len[tile];
+            const bool ok = __ldg(a.tile_slow + tile) == 0u && counted <= TILE_CAP && n_flagged <= a.dense_max;
+            if (!ok && counted) { a.tile_len[tile] = 0; atomicSub(&a.block_sum[tile / EMIT_THREADS], counted); }
+            fast_word = ok ? 1u : 0u;
+        }
+        const bool fast = a.settled && (tile >= a.tile_end || __shfl_sync(0xffffffffu, fast_word, 0) != 0u);
         if (fast) {
 #pragma unroll
             for (int j = 0; j < NB; ++j) planes[j] = 0;
-        } else if (lane == 0 && tile < a.tile_end) {
-            const uint32_t counted = a.tile_len[tile];
-            if (counted) { a.tile_len[tile] = 0; atomicSub(&a.block_sum[tile / EMIT_THREADS], counted); }
         }
         uint32_t cnt = 0;
 #pragma unroll
@@ -239,7 +240,6 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
         }
 #pragma unroll
         for (int j = 0; j < NB; ++j) planes[j] = next_planes[j];
-        settled = next_settled;
     }
     if (lane == 0 && dense_tiles) atomicAdd(&a.s.counters[4], dense_tiles);
 }
@@ -341,7 +341,7 @@ __device__ __forceinline__ void walk_words_lockstep(const ST &st, const uint8_t 
 // starts at an unaligned haystack start, and span items (a 512-byte span of a densely flagged tile, walked
 // like an ac_scan_kernel slice).  rs == 0xffffffff: report nothing, return the end state in e0s.
 // EMIT: events go to a.out[obase..).
-template <typename E, bool RANGE, int W, bool EMIT>
+template <typename E, bool RANGE, int W, int EMIT>
 __device__ __noinline__ ItemEvents walk_item_slow(const ScanArgs &a, uint32_t s_cls_addr, uint32_t item,
                                                   uint32_t ws, uint32_t rs, uint32_t re, uint32_t obase)
 {
@@ -370,7 +370,6 @@ __device__ __noinline__ ItemEvents walk_item_slow(const ScanArgs &a, uint32_t s_
         if (w0 < hb) w0 = hb;
         const uint32_t s_cs = sc.template walk<false, false>(a.root, w0, cs);
         scan_slice<EMIT>(a, sc, s_cs, h, cs, ce);
-        if (EMIT) sc.flush_pending();
         return ItemEvents{sc.cnt, sc.e0p, sc.e0s};
     }
 
@@ -392,7 +391,6 @@ __device__ __noinline__ ItemEvents walk_item_slow(const ScanArgs &a, uint32_t s_
             }
         }
     }
-    if (EMIT) sc.flush_pending();
     if (rs == 0xffffffffu) return ItemEvents{0, 0, s};
     return ItemEvents{sc.cnt, sc.e0p, sc.e0s};
 }
@@ -518,9 +516,9 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
                     walk_words_lockstep<W, 1>(st, a.s.text, a.warm, r_, w_, e_);
                     e1 = e_[0];
                 } else if (it != ITEM_NONE) {
-                    if (it & ITEM_SPAN) e1 = walk_item_slow<E, RANGE, W, false>(a.s, s_cls_addr, it, 0u, 0u, 0u, 0u);
+                    if (it & ITEM_SPAN) e1 = walk_item_slow<E, RANGE, W, 0>(a.s, s_cls_addr, it, 0u, 0u, 0u, 0u);
                     else if (r1 < a.s.total)           // else nothing ends after this word
-                        e1 = walk_item_slow<E, RANGE, W, false>(a.s, s_cls_addr, it, (r1 > a.warm) ? r1 - a.warm : 0u, r1,
+                        e1 = walk_item_slow<E, RANGE, W, 0>(a.s, s_cls_addr, it, (r1 > a.warm) ? r1 - a.warm : 0u, r1,
                                                                 min(r1 + W, a.s.total), 0u);
                 }
 #pragma unroll
@@ -561,7 +559,7 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
     if (a.want_end_state && blockIdx.x == gridDim.x - 1 && threadIdx.x == WALK_THREADS - 1) {
         const uint32_t back = a.s.halo + 1u;
         const uint32_t ws = (a.s.total > back) ? ((a.s.total - back) & ~(uint32_t)(W - 1)) : 0u;
-        a.s.counters[2] = walk_item_slow<E, RANGE, W, false>(a.s, s_cls_addr, ITEM_NONE, ws, 0xffffffffu, a.s.total, 0u).e0s;
+        a.s.counters[2] = walk_item_slow<E, RANGE, W, 0>(a.s, s_cls_addr, ITEM_NONE, ws, 0xffffffffu, a.s.total, 0u).e0s;
     }
 }
 
@@ -574,30 +572,28 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
 // DRAM read each, long after the span has left the caches), it puts the word on a small queue of its own in shared
 // memory.  Whenever 32 words have gathered, the warp settles them together, one per lane: the three groups around
 // the word come from L2 (the warp read them microseconds ago), one probe of the exact gram table (gram_table.hpp)
-// and one comparison decide it.  The round is issued right after the next U loads, so its two round trips to L2
-// hide behind their trip to HBM.  Result per flagged word: its slot span_out[span * SPAN_CAP + rank of the word
-// among the span's flagged words] = the event, or state 0 for "nothing ends here"; span_cnt[span] = flagged
-// words of the span; events are counted per tile and per block of tiles (tile_len, block_sum) as ac_walk_kernel
-// does.  What cannot be settled that way — a key several patterns share, a window cut by a haystack or stream end,
-// ragged batches, more than SPAN_CAP flagged words in a span — marks the tile in tile_slow: ac_collect_kernel
-// takes the count back and sends the whole tile through the items / ac_walk_kernel as before.  The bit planes are
-// written regardless (that path reads them).
-constexpr uint32_t VQ_SLOTS = 48;          // queue entries per warp (a flush leaves < 32, a span adds <= SPAN_CAP)
+// and one comparison decide it; the SM's other warps keep streaming meanwhile.  An event goes to the next free
+// slot of its 16 KiB tile (tile_ev, TILE_CAP slots, claimed through tile_len — ac_emit_kernel puts a tile's few
+// events in order) and is counted for its block of tiles (block_sum) as ac_walk_kernel does.  What cannot be
+// settled that way — a key several patterns share, a window cut by a haystack or stream end, more than SPAN_CAP
+// flagged words in one span — marks the tile in tile_slow: ac_collect_kernel takes its count back and sends the
+// whole tile through the items / ac_walk_kernel as before.  The bit planes are written regardless.
+//
+// The streaming loop issues ~60 instructions per 512-byte span and is as much bound by that as by HBM (ncu: issue
+// slots 55 % busy at 0.80 of the copy bandwidth; 40 % more instructions measured 28 % more time), so everything
+// the verification adds sits behind the warp-uniform "any word flagged" branch or in the rounds.
+constexpr uint32_t VQ_SLOTS = 56;          // queue entries per warp: < 32 after a flush + FILTER_UNROLL spans x SPAN_CAP
 constexpr uint32_t VQ_BYTES = (SCAN_THREADS / 32) * VQ_SLOTS * 4;
-constexpr uint32_t VQ_RANK_SHIFT = 30;     // entry = word index | rank << 30 (word index < 2^30: streams stay below 4 GiB)
 
-// settles up to 32 queued words, one per lane (called by the whole warp)
+// settles up to 32 queued words (their indices in the stream), one per lane; called by the whole warp
 template <int W>
-__device__ __noinline__ void verify_round(const VerifyArgs &a, uint32_t entry, bool have)
+__device__ __noinline__ void verify_round(const VerifyArgs &a, uint32_t k, bool have)
 {
     constexpr uint32_t NB = 16u / W;
     ItemEvents ev{0u, 0u, 0u};
     bool slow = false;
-    uint32_t span = 0, rank = 0;
+    const uint32_t tile = k / (32u * NB * 32u);
     if (have) {
-        const uint32_t k = entry & ((1u << VQ_RANK_SHIFT) - 1u);
-        rank = entry >> VQ_RANK_SHIFT;
-        span = k / (32u * NB);
         const uint32_t rs = (k + 1u) * W;                    // the word owns the end offsets rs+1 .. rs+W
         bool can = rs >= a.warm && rs + W <= a.s.total;
         uint32_t w0 = 0;
@@ -608,13 +604,15 @@ __device__ __noinline__ void verify_round(const VerifyArgs &a, uint32_t entry, b
             can = hb + a.s.uniform_len >= rs + W && ((rs - w0) & (uint32_t)(W - 1)) == 0 && w0 < rs;
         }
         slow = !can || !verify_word_direct<W>(a, rs, w0, ev);
-        if (slow) a.tile_slow[span >> 5] = 1u;
-        else a.span_out[(size_t)span * SPAN_CAP + rank] = ev.cnt ? make_uint2(ev.e0p, ev.e0s) : make_uint2(0u, 0u);
+        if (slow) a.tile_slow[tile] = 1u;
     }
-    // events per tile and per block of EMIT_THREADS tiles (one atomic per warp where the lanes agree on the block)
     const bool has = have && !slow && ev.cnt;
-    if (has) atomicAdd(&a.tile_len[span >> 5], 1u);
-    const uint32_t blk = has ? (span >> 5) / EMIT_THREADS : 0xffffffffu;
+    if (has) {
+        const uint32_t slot = atomicAdd(&a.tile_len[tile], 1u);
+        if (slot < TILE_CAP) a.tile_ev[(size_t)tile * TILE_CAP + slot] = make_uint2(ev.e0p, ev.e0s);
+    }
+    // events per block of EMIT_THREADS tiles (one atomic per warp where the lanes agree on the block)
+    const uint32_t blk = has ? tile / EMIT_THREADS : 0xffffffffu;
     const uint32_t voters = __ballot_sync(0xffffffffu, has);
     if (voters) {
         const uint32_t lead_blk = __shfl_sync(0xffffffffu, blk, __ffs(voters) - 1);
@@ -634,6 +632,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_verify_kernel(const
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
+    const uint32_t lanes_below = (1u << lane) - 1u;
     const uint32_t s_base = stage_bitmap(fa, s_bm, tid);
     // this warp's queue of flagged words (shared-window byte address)
     const uint32_t q_base = s_base + FILTER_L1_BYTES + (tid >> 5) * (VQ_SLOTS * 4u);
@@ -642,17 +641,15 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_verify_kernel(const
         return test_word<L2>(fa, s_base, lo, hi, nb, maybe_unknown);
     };
     auto flush = [&]() {                                      // settles the first 32 queued words (or all, if fewer)
-        uint32_t entry = 0;
-        const bool have = lane < qn;
-        if (have) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(entry) : "r"(q_base + lane * 4u));
-        uint32_t moved = 0;                                   // what is left moves to the front
-        const bool more = lane + 32u < qn;
+        __syncwarp();
+        uint32_t k = 0, moved = 0;
+        const bool have = lane < qn, more = lane + 32u < qn;
+        if (have) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(k) : "r"(q_base + lane * 4u));
         if (more) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(moved) : "r"(q_base + (lane + 32u) * 4u));
         __syncwarp();
-        if (more) asm volatile("st.shared.u32 [%0], %1;" :: "r"(q_base + lane * 4u), "r"(moved));
+        if (more) asm volatile("st.shared.u32 [%0], %1;" :: "r"(q_base + lane * 4u), "r"(moved));     // the rest moves to the front
         qn = qn > 32u ? qn - 32u : 0u;
-        __syncwarp();
-        verify_round<W>(a, entry, have);
+        verify_round<W>(a, k, have);
     };
 
     const uint32_t n_full_all = fa.total / SPAN_BYTES;        // spans that lie completely inside the stream
@@ -662,6 +659,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_verify_kernel(const
     uint32_t flagged = 0;
 
     for (uint32_t g0 = fa.span_begin + warp; g0 < n_full; g0 += n_warps * U) {
+        // (the round sits where nothing of the streaming loop is live: a call in the middle of it spills the spans in
+        // flight to local memory on every iteration — measured 2x slower)
+        if (VERIFY && qn >= 32u) flush();
         uint4 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -669,7 +669,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_verify_kernel(const
             v[u] = make_uint4(0, 0, 0, 0);
             if (g < n_full) v[u] = ld_text16(fa.text + ((size_t)g * 32u + lane) * 16u);
         }
-        if (VERIFY && qn >= 32u) flush();                     // its L2 round trips hide behind the loads just issued
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t g = g0 + u * n_warps;
@@ -678,7 +677,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_verify_kernel(const
             // byte after the lane's last word: the next lane's first byte; lane 31 does not know it
             uint32_t after = __shfl_down_sync(0xffffffffu, w[0], 1) & 0xffu;
             if (lane == 31u) after = FILTER_NEXT_UNKNOWN;
-            uint32_t mine = 0, n_flag = 0;
+            uint32_t mine = 0, any = 0;
             bool p[NB];
             uint32_t plane[NB];
 #pragma unroll
@@ -686,35 +685,31 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_verify_kernel(const
                 const uint32_t nb = (j == NB - 1) ? after : (((W == 8) ? w[2] : w[j + 1]) & 0xffu);
                 p[j] = (W == 8) ? test(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test(w[j], 0u, nb, j == NB - 1);
                 plane[j] = __ballot_sync(0xffffffffu, p[j]);
-                n_flag += __popc(plane[j]);
+                any |= plane[j];
                 if (lane == (uint32_t)j) mine = plane[j];
             }
-            uint32_t cnt = n_flag;                            // what span_cnt[g] becomes
-            if (n_flag) {                                     // warp-uniform
-                if (!VERIFY || n_flag > SPAN_CAP) {
-                    cnt = SPAN_SLOW;
+            if (lane < (uint32_t)NB) {
+                fa.mask[(size_t)g * NB + lane] = mine;
+                flagged += __popc(mine);
+            }
+            if (VERIFY && any) {                              // warp-uniform
+                // queue the flagged words in stream order: by lane, then by word inside the lane
+                uint32_t n_flag = 0, at = qn;
+#pragma unroll
+                for (int j = 0; j < NB; ++j) { n_flag += __popc(plane[j]); at += __popc(plane[j] & lanes_below); }
+                if (n_flag > SPAN_CAP) {
                     if (lane == 0u) a.tile_slow[g >> 5] = 1u;
                 } else {
-                    // queue the flagged words in stream order: by lane, then by word inside the lane
-                    uint32_t rank = 0;
-#pragma unroll
-                    for (int j = 0; j < NB; ++j) rank += __popc(plane[j] & ((1u << lane) - 1u));
 #pragma unroll
                     for (int j = 0; j < NB; ++j) {
                         if (p[j]) {
-                            const uint32_t k = g * (32u * NB) + lane * NB + j;
-                            asm volatile("st.shared.u32 [%0], %1;" :: "r"(q_base + (qn + rank) * 4u), "r"(k | (rank << VQ_RANK_SHIFT)));
-                            ++rank;
+                            asm volatile("st.shared.u32 [%0], %1;" :: "r"(q_base + at * 4u), "r"(g * (32u * NB) + lane * NB + j));
+                            ++at;
                         }
                     }
                     qn += n_flag;
-                    __syncwarp();
                 }
             }
-            if (lane < (uint32_t)NB) fa.mask[(size_t)g * NB + lane] = mine;
-            else if (lane == (uint32_t)NB) a.span_cnt[g] = cnt;
-            if (lane < (uint32_t)NB) flagged += __popc(mine);
-            if (VERIFY && qn >= VQ_SLOTS - SPAN_CAP) flush();      // (only with many flagged words per span)
         }
     }
     while (VERIFY && qn) flush();
@@ -730,23 +725,21 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_verify_kernel(const
         const bool tail = (fa.total & 15u) && c == n16;
         uint32_t after = __shfl_down_sync(0xffffffffu, w[0], 1) & 0xffu;
         if (lane == 31u || c + 1u >= n16) after = FILTER_NEXT_UNKNOWN;      // the next chunk is not in this warp's registers
-        uint32_t mine = 0, m = 0;
+        uint32_t mine = 0, any = 0;
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
             const uint32_t nb = (j == NB - 1) ? after : (((W == 8) ? w[2] : w[j + 1]) & 0xffu);
             bool p = (W == 8) ? test(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test(w[j], 0u, nb, j == NB - 1);
             p = (c < n16) ? p : tail;
             const uint32_t plane = __ballot_sync(0xffffffffu, p);
-            m |= plane;
+            any |= plane;
             if (lane == (uint32_t)j) mine = plane;
         }
         if (lane < (uint32_t)NB) {
             fa.mask[(size_t)n_full_all * NB + lane] = mine;
             flagged += __popc(mine);
-        } else if (lane == (uint32_t)NB) {
-            a.span_cnt[n_full_all] = m ? SPAN_SLOW : 0u;
-            if (m) a.tile_slow[n_full_all >> 5] = 1u;
         }
+        if (VERIFY && any && lane == 0u) a.tile_slow[n_full_all >> 5] = 1u;
     }
     if (lane < (uint32_t)NB && flagged) atomicAdd(&fa.counters[3], flagged);
 }
@@ -816,32 +809,25 @@ __global__ void __launch_bounds__(COUNT_THREADS) ac_emit_kernel(const __grid_con
         uint2 next_d;
         load_header(tile + n_warps, next_len, next_d, next_off);
         if (len && d.x == DESC_FAST) {
-            // the filter pass settled every flagged word of the tile: lane l copies the events of span l (a slot whose
-            // state is 0 belongs to a flagged word at which nothing ends)
-            const uint32_t span = tile * 32u + lane;
-            const uint32_t nf = (span < a.n_spans) ? a.span_cnt[span] : 0u;
-            uint2 slot[SPAN_CAP];
-            uint32_t c = 0;
-#pragma unroll
-            for (uint32_t k = 0; k < SPAN_CAP; ++k) {
-                slot[k] = make_uint2(0u, 0u);
-                if (k < nf) slot[k] = a.span_out[(size_t)span * SPAN_CAP + k];
-                c += slot[k].y ? 1u : 0u;
+            // the filter pass settled the whole tile: its len <= TILE_CAP events sit in tile_ev in the order the rounds
+            // finished — every lane takes two, ranks them by end offset (distinct) and writes them in place
+            const uint2 *ev = a.tile_ev + (size_t)tile * TILE_CAP;
+            uint2 e0 = make_uint2(0xffffffffu, 0u), e1 = make_uint2(0xffffffffu, 0u);
+            if (lane < len) e0 = ev[lane];
+            if (lane + 32u < len) e1 = ev[lane + 32u];
+            uint32_t r0 = 0, r1 = 0;
+            for (uint32_t i = 0; i < min(len, 32u); ++i) {                // warp-uniform
+                const uint32_t x = __shfl_sync(0xffffffffu, e0.x, i);
+                r0 += x < e0.x ? 1u : 0u;
+                r1 += x < e1.x ? 1u : 0u;
             }
-            uint32_t pincl = c;
-#pragma unroll
-            for (int k = 1; k < 32; k <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, pincl, k);
-                if (lane >= k) pincl += v;
+            for (uint32_t i = 32; i < len; ++i) {
+                const uint32_t x = __shfl_sync(0xffffffffu, e1.x, i - 32u);
+                r0 += x < e0.x ? 1u : 0u;
+                r1 += x < e1.x ? 1u : 0u;
             }
-            uint32_t o = off + pincl - c;
-#pragma unroll
-            for (uint32_t k = 0; k < SPAN_CAP; ++k) {
-                if (slot[k].y) {
-                    if (o < a.s.capacity) a.s.out[o] = slot[k];
-                    ++o;
-                }
-            }
+            if (lane < len && off + r0 < a.s.capacity) a.s.out[off + r0] = e0;
+            if (lane + 32u < len && off + r1 < a.s.capacity) a.s.out[off + r1] = e1;
         }
         const uint32_t n_items = (len && d.x != DESC_FAST) ? d.y : 0u;   // warp-uniform; 0: nothing left to do for this tile
         for (uint32_t i0 = 0; i0 < n_items; i0 += 32u) {             // warp-uniform
@@ -870,7 +856,7 @@ __global__ void __launch_bounds__(COUNT_THREADS) ac_emit_kernel(const __grid_con
                     re = min(rs + W, a.s.total);
                     ws = (rs > a.warm) ? rs - a.warm : 0u;
                 }
-                walk_item_slow<E, RANGE, W, true>(a.s, s_cls_addr, item, ws, rs, re, o);
+                walk_item_slow<E, RANGE, W, 1>(a.s, s_cls_addr, item, ws, rs, re, o);
             }
             off += __shfl_sync(0xffffffffu, pincl, 31);
         }

@@ -30,6 +30,7 @@ namespace acb200 {
 
 constexpr int SCAN_THREADS = 1024;       // one persistent CTA per SM
 constexpr int EXPAND_THREADS = 256;
+constexpr uint32_t DENSE_PAIRED_MIN = 64; // events in one slice beyond which its second walk pairs them into 16-byte stores
 
 struct ScanArgs {
     const uint8_t *text;          // flat haystack bytes, 16-byte aligned, >=32 readable bytes past `total`
@@ -283,17 +284,18 @@ struct Scanner {
         return (uint32_t)__ldg(gtab + (s * ncls + cls(b)));
     }
 
-    template <bool EMIT>
+    // EMIT: 0 = count (and keep the first two events), 1 = write in place, 2 = write in place, two events per store
+    template <int EMIT>
     __device__ __forceinline__ void hit(uint32_t pos, uint32_t s)
     {
         if (FIRST) {
             if (found) return;
             found = true;
         }
-        if (EMIT) {
-            // Dense slices: every lane writes into its own region, so a warp store touches 32 different sectors and
-            // what it costs is store wavefronts, not bytes.  Two events go out as ONE 16-byte store (the event at an
-            // even index waits in registers for its successor; flush_pending() writes a last odd one).
+        if (EMIT == 2) {
+            // Very dense slices: every lane writes into its own region, so a warp store touches 32 different sectors
+            // and what it costs is store wavefronts, not bytes.  Two events go out as ONE 16-byte store (the event at a
+            // 16-byte aligned slot waits in registers for its successor; flush_pending() writes a last odd one).
             const uint32_t o = obase + cnt;
             if (o < cap) {
                 if ((reinterpret_cast<uintptr_t>(out + o) & 15u) == 0u) { pend = make_uint2(pos, s); have_pend = true; }
@@ -305,6 +307,9 @@ struct Scanner {
                 out[o - 1u] = pend;
                 have_pend = false;
             }
+        } else if (EMIT == 1) {
+            const uint32_t o = obase + cnt;
+            if (o < cap) out[o] = make_uint2(pos, s);
         } else {
             if (cnt == 0) { e0p = pos; e0s = s; }
             else if (cnt == 1) { e1p = pos; e1s = s; }
@@ -312,7 +317,7 @@ struct Scanner {
         ++cnt;
     }
 
-    template <bool REPORT, bool EMIT>
+    template <bool REPORT, int EMIT>
     __device__ __forceinline__ uint32_t byte_step(uint32_t s, uint32_t i)
     {
         s = any_next(s, text[i]);
@@ -331,7 +336,7 @@ struct Scanner {
     // careful path (true entry from the full table) and the fast path is
     // re-entered — through the switch, at the right byte — as soon as the state
     // is back inside.
-    template <bool REPORT, bool EMIT>
+    template <bool REPORT, int EMIT>
     __device__ __forceinline__ uint32_t walk_group(uint32_t s, const uint4 &v, uint32_t i)
     {
 #define ACB_STEP(J, W)                                                                          \
@@ -366,9 +371,11 @@ struct Scanner {
     // Walks bytes [i, end) of one haystack from state s.  REPORT: record every
     // reporting state (EMIT: straight into the output, else count + keep 2).
     // Text arrives through a three-deep register pipeline of 16-byte loads.
-    // The second walk of a dense slice, which writes its events in place.  Deliberately compact (one byte per
-    // iteration, nothing unrolled): this pass is bound by its stores, and a second unrolled copy of the 16-step
-    // switch would push the count pass's hot loop out of the instruction cache.
+    // The second walk of a VERY dense slice (EMIT == 2), which writes its events in place two per store.  Deliberately
+    // compact (one byte per iteration, nothing unrolled): this pass is bound by its stores, and a third unrolled
+    // copy of the 16-step switch would push the count pass's hot loop out of the instruction cache.  Slices with a
+    // handful of events take the unrolled walk (EMIT == 1): one warp in three re-walks a slice at one event per
+    // KiB, and the compact loop costs 4x the instructions per byte (measured: +36 % instructions, +18 % time).
     __device__ __forceinline__ uint32_t walk_emit(uint32_t s, uint32_t i, uint32_t end)
     {
 #pragma unroll 1
@@ -383,17 +390,17 @@ struct Scanner {
                 if (s - win_lo < win_rows) e = hot_next(s, b);
                 if (e == 0) e = any_next(s, b);              // outside the window, or leaving it: the true entry
                 s = e;
-                if (s < final_bound) hit<true>(i + 1u, s);
+                if (s < final_bound) hit<2>(i + 1u, s);
                 if (FIRST && found) return s;
             }
         }
         return s;
     }
 
-    template <bool REPORT, bool EMIT>
+    template <bool REPORT, int EMIT>
     __device__ __forceinline__ uint32_t walk(uint32_t s, uint32_t i, uint32_t end)
     {
-        if constexpr (EMIT) return walk_emit(s, i, end);
+        if constexpr (EMIT == 2) return walk_emit(s, i, end);
         else {
             while (i < end && (i & 15u)) { s = byte_step<REPORT, EMIT>(s, i); ++i; }
             if (i + 16 <= end) {
@@ -440,7 +447,7 @@ __device__ __forceinline__ uint32_t hay_end(const ScanArgs &a, uint32_t h)
 }
 
 // Scans slice [cs, ce).  `s` must be the state at cs, `h` the haystack at cs.
-template <bool EMIT, typename SC>
+template <int EMIT, typename SC>
 __device__ __forceinline__ uint32_t scan_slice(const ScanArgs &a, SC &sc, uint32_t s, uint32_t h,
                                                uint32_t cs, uint32_t ce)
 {
@@ -520,7 +527,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_kernel(const ScanArgs
                 uint32_t s = (ws == hb && h == 0) ? a.init_state : a.root;
                 s = sc.template walk<false, false>(s, ws, cs);
                 s_cs = s;
-                s = scan_slice<false>(a, sc, s, h, cs, ce);
+                s = scan_slice<0>(a, sc, s, h, cs, ce);
                 if (ce == a.total) a.counters[2] = s;
                 if (FIRST && sc.cnt) {
                     // publish the earliest event of the slice's first reporting haystack
@@ -549,11 +556,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_kernel(const ScanArgs
                 if (sc.cnt == 2 && off + 1 < a.capacity) a.out[off + 1] = make_uint2(sc.e1p, sc.e1s);
             } else if (off < a.capacity) {
                 // dense slice: walk it again from the saved entry state and write in place
+                const bool very_dense = sc.cnt > DENSE_PAIRED_MIN;
                 sc.obase = off;
                 sc.cnt = 0;
                 sc.have_pend = false;
-                scan_slice<true>(a, sc, s_cs, h, cs, ce);
-                sc.flush_pending();
+                if (very_dense) { scan_slice<2>(a, sc, s_cs, h, cs, ce); sc.flush_pending(); }
+                else scan_slice<1>(a, sc, s_cs, h, cs, ce);
             }
         }
         __syncwarp();

@@ -82,6 +82,78 @@ def test_blob_rejects_garbage_and_unfinalized(tmp_path):
         Automaton.load(str(tmp_path / "cut.acb"), require_device=False)
 
 
+def _blob_layout(data: bytes):
+    """file offsets of the blob's fields (csrc/blob.cpp save_flat) -> dict name -> (offset, element size, count)"""
+    import struct
+    pos = 8
+    out = {}
+    for name in ("n_states", "n_rows", "n_classes", "final_bound", "root", "max_pattern_len", "n_used_bytes"):
+        out[name] = (pos, 4, 1); pos += 4
+    out["cls_map"] = (pos, 1, 256); pos += 256
+    out["range_map"] = (pos, 4, 1); pos += 4
+    out["range_lo"] = (pos, 4, 1); pos += 4
+    for name, size in (("bfs_order", 4), ("level_off", 4), ("fail", 4), ("edge_src", 4), ("edge_dst", 4), ("edge_cls", 2),
+                       ("level_edge_off", 4), ("out_off", 8), ("out_idx", 4)):
+        (n,) = struct.unpack_from("<Q", data, pos)
+        out[name] = (pos + 8, size, n); pos += 8 + size * n
+    for name in ("min_pattern_len", "filter_w", "l1_bits"):
+        out[name] = (pos, 4, 1); pos += 4
+    (n,) = struct.unpack_from("<Q", data, pos)
+    out["l1"] = (pos + 8, 4, n); pos += 8 + 4 * n
+    out["l2_log2"] = (pos, 4, 1); pos += 4
+    return out
+
+
+def test_blob_with_corrupt_fields_fails_to_load(tmp_path):
+    """Every index, offset and size the loader (or the kernels after it) would trust is validated: a file with one
+    field changed must be refused, not loaded into memory corruption or silently wrong matches."""
+    import random
+    import struct
+    rng = random.Random(5)
+    pats = [bytes(rng.choice(b"abcdef") for _ in range(rng.choice([16, 20, 33]))) for _ in range(50)]
+    a = Automaton()
+    a.add_php_order(pats)
+    _finalize_anyhow(a)
+    good = tmp_path / "good.acb"
+    a.save(str(good))
+    data = good.read_bytes()
+    lay = _blob_layout(data)
+    assert Automaton.load(str(good), require_device=False).info().n_patterns == len(pats)
+
+    def patched(name, index, value):
+        off, size, n = lay[name]
+        assert index < n
+        b = bytearray(data)
+        struct.pack_into({1: "<B", 2: "<H", 4: "<I", 8: "<Q"}[size], b, off + size * index, value)
+        return bytes(b)
+
+    n_out = lay["out_off"][2]
+    cases = {
+        "max_pattern_len too small (halo would shrink)": patched("max_pattern_len", 0, 8),
+        "min_pattern_len wrong": patched("min_pattern_len", 0, 40),
+        "filter word size the kernels do not have": patched("filter_w", 0, 6),
+        "level-1 bitmap of another size": patched("l1_bits", 0, 1 << 16),
+        "level 2 announced but absent": patched("l2_log2", 0, 24),
+        "out_off decreasing": patched("out_off", n_out // 2, 0),
+        "out_off beyond out_idx": patched("out_off", n_out - 1, 1 << 40),
+        "out_idx names a missing pattern": patched("out_idx", 3, 1 << 20),
+        "level_off not ascending": patched("level_off", 2, 0),
+        "level_edge_off beyond the edges": patched("level_edge_off", lay["level_edge_off"][2] - 1, 1 << 30),
+        "edge into row 0": patched("edge_dst", 5, 0),
+        "edge class beyond the table": patched("edge_cls", 5, 200),
+        "failure link beyond the table": patched("fail", 7, 1 << 30),
+        "byte class beyond the table": patched("cls_map", 0x61, 250),
+        "root outside the table": patched("root", 0, 1 << 30),
+        "rows x classes beyond 2^32": patched("n_classes", 0, 1 << 31),
+    }
+    for what, blob in cases.items():
+        path = tmp_path / "bad.acb"
+        path.write_bytes(blob)
+        with pytest.raises(native.AcError):
+            Automaton.load(str(path), require_device=False)
+            pytest.fail(what)
+
+
 @pytest.mark.gpu
 def test_loaded_automaton_matches_like_the_original(tmp_path):
     needles, hay, off = W.cfg2(n_hay=64, hay_len=8192, planted_per_hay=8, seed=3)
