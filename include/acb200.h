@@ -374,9 +374,8 @@ int acb200_filter_probe(const AC_TRIE_t *thiz, uint64_t word, unsigned next_byte
 
 /* Direct verification of flagged words (gram_table.hpp): a flagged word whose (word, next byte) belongs to exactly
  * one (pattern, alignment) is decided by comparing the haystack with that pattern instead of walking the
- * automaton.  0 = automatic (currently 1), 1 = inside the filter pass, while the word is still in the warp's
- * registers (batches of one or of equal-length haystacks; others as 2), 2 = in the walk kernel, -1 = off (every
- * flagged word is walked).  Results are identical in every mode. */
+ * automaton.  0 = automatic (currently 1), 1 = on, -1 = off (every flagged word is walked).  Results are
+ * identical in every mode. */
 int acb200_set_direct(AC_TRIE_t *thiz, int mode);
 
 /* Diagnostic: the direct verification of the aligned word `word_index` (bytes [W*word_index, W*word_index + W) of

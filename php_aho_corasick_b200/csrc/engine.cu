@@ -62,7 +62,7 @@ void Engine::release()
     cudaFree(d_out_off_); cudaFree(d_out_idx_); cudaFree(d_pat_len_); cudaFree(d_hit_sums_); cudaFree(d_hits_); cudaFree(d_hit_total_);
     d_out_off_ = nullptr; d_out_idx_ = nullptr; d_pat_len_ = nullptr; d_hit_sums_ = nullptr; d_hits_ = nullptr; d_hit_total_ = nullptr;
     hit_sums_cap_ = 0; hits_cap_ = 0;
-    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_); cudaFree(d_tile_ev_); d_tile_ev_ = nullptr;
+    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_);
     d_l1_ = nullptr; d_l2_ = nullptr; d_mask_ = nullptr; mask_cap_ = 0;
     d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; verify_tiles_cap_ = 0;
     if (h_counters_) cudaFreeHost(h_counters_);
@@ -243,14 +243,10 @@ bool Engine::build(const FlatAutomaton &f, int dev, const Engine *table_src)
             gt_log2_ = f.gt_log2;
         }
         CU_OK(cudaStreamSynchronize(st));
-        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_L1_BYTES + VQ_BYTES))));
-        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_L1_BYTES + VQ_BYTES))));
-        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_L1_BYTES + VQ_BYTES))));
-        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_L1_BYTES + VQ_BYTES))));
-        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_L1_BYTES + VQ_BYTES))));
-        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_L1_BYTES + VQ_BYTES))));
-        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_L1_BYTES + VQ_BYTES))));
-        CU_OK((cudaFuncSetAttribute(ac_filter_verify_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FILTER_L1_BYTES + VQ_BYTES))));
+        CU_OK(cudaFuncSetAttribute(ac_filter_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
+        CU_OK(cudaFuncSetAttribute(ac_filter_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
+        CU_OK(cudaFuncSetAttribute(ac_filter_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
+        CU_OK(cudaFuncSetAttribute(ac_filter_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FILTER_L1_BYTES));
     }
     info.filter_word = (int32_t)filter_w_;
     info.min_pattern_len = f.min_pattern_len;
@@ -328,16 +324,14 @@ bool Engine::ensure_mask(size_t words)
 bool Engine::ensure_verify_scratch(size_t n_tiles)
 {
     if (n_tiles <= verify_tiles_cap_) return true;
-    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_); cudaFree(d_tile_ev_);
-    d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; d_tile_ev_ = nullptr; verify_tiles_cap_ = 0;
+    cudaFree(d_items_); cudaFree(d_recs_); cudaFree(d_desc_); cudaFree(d_tile_len_);
+    d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; verify_tiles_cap_ = 0;
     const size_t cap = std::max(n_tiles + n_tiles / 4, (size_t)256);
     CU_OK(cudaMalloc(&d_items_, cap * VER_DENSE_MAX * sizeof(uint32_t)));
     CU_OK(cudaMalloc(&d_recs_, cap * VER_DENSE_MAX * 2 * sizeof(uint32_t)));
     CU_OK(cudaMalloc(&d_desc_, cap * 2 * sizeof(uint32_t)));
-    CU_OK(cudaMalloc(&d_tile_ev_, cap * TILE_CAP * 2 * sizeof(uint32_t)));
-    // one block: [16 counters | block sums | events per tile | slow marks per tile | offsets per tile] — all but the
-    // last are zeroed by ONE memset
-    CU_OK(cudaMalloc(&d_tile_len_, (16 + (cap / EMIT_THREADS + 16) + 3 * cap) * sizeof(uint32_t)));
+    // one block: [16 counters | block sums | events per tile | offsets per tile] — the first three are zeroed by ONE memset
+    CU_OK(cudaMalloc(&d_tile_len_, (16 + (cap / EMIT_THREADS + 16) + 2 * cap) * sizeof(uint32_t)));
     verify_tiles_cap_ = cap;
     return true;
 }
@@ -381,7 +375,9 @@ uint32_t Engine::pick_chunk(uint64_t total) const
     const uint64_t ideal = std::max<uint64_t>(512, up16(8ull * (halo_ + 1)));
     // Small inputs: shorter slices so that every warp of every SM still gets a tile, but never so
     // short that the halo dominates.
-    const uint64_t floor_ = std::max<uint64_t>(64, up16(4ull * halo_));
+    // (2x the halo: measured on the adversarial shape — Lmax 1024, every byte an event — 2 KiB slices give 129 GB/s,
+    // 4 KiB 96, 8 KiB 62: with long patterns the walk needs the lanes more than it minds re-reading the halo)
+    const uint64_t floor_ = std::max<uint64_t>(64, up16(2ull * halo_));
     const uint64_t want = (uint64_t)n_sms_ * SCAN_THREADS;
     uint64_t c = ideal;
     if (total / ideal < want) c = std::max(floor_, up16(total / std::max<uint64_t>(want, 1)));
@@ -530,15 +526,10 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
 }
 
 template <int W>
-static void launch_filter_k(const FilterArgs &fa, const VerifyArgs &va, bool l2, bool verify, unsigned grid, cudaStream_t st)
+static void launch_filter_k(const FilterArgs &fa, bool l2, unsigned grid, cudaStream_t st)
 {
-    if (l2) {
-        if (verify) ac_filter_verify_kernel<W, true, true><<<grid, SCAN_THREADS, FILTER_L1_BYTES + VQ_BYTES, st>>>(fa, va);
-        else ac_filter_verify_kernel<W, true, false><<<grid, SCAN_THREADS, FILTER_L1_BYTES + VQ_BYTES, st>>>(fa, va);
-    } else {
-        if (verify) ac_filter_verify_kernel<W, false, true><<<grid, SCAN_THREADS, FILTER_L1_BYTES + VQ_BYTES, st>>>(fa, va);
-        else ac_filter_verify_kernel<W, false, false><<<grid, SCAN_THREADS, FILTER_L1_BYTES + VQ_BYTES, st>>>(fa, va);
-    }
+    if (l2) ac_filter_kernel<W, true><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa);
+    else ac_filter_kernel<W, false><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa);
 }
 
 template <typename E, int W>
@@ -624,16 +615,11 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     va.gt_slots = direct ? (const uint4 *)d_gt_slots_ : nullptr;
     va.gt_pat = d_gt_pat_;
     va.gt_log2 = direct ? gt_log2_ : 0u;
-    va.tile_ev = (uint2 *)d_tile_ev_;
-    // flagged words are settled inside the filter pass where one comparison decides them and the batch is one haystack
-    // or equal-length haystacks (no offset search inside the streaming loop)
-    va.settled = (direct && uniform_len != 0 && tune_direct != 2) ? 1u : 0u;
     va.items = d_items_;
     va.desc = (uint2 *)d_desc_;
     va.recs = (uint2 *)d_recs_;
     va.tile_len = vtile_len;
-    va.tile_slow = vtile_len + verify_tiles_cap_;
-    va.tile_off = vtile_len + 2 * verify_tiles_cap_;
+    va.tile_off = vtile_len + verify_tiles_cap_;
     va.block_sum = vblock_sum;
 
     // tune_direct: 0 / 1 flagged words are settled by one comparison inside ac_walk_kernel where the gram table allows;
@@ -656,17 +642,14 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
             a.capacity = (uint32_t)std::min<size_t>(async_cap_, 0xffffffffu);
         }
         // counters, block sums and events per tile (the walk kernel adds to both) are adjacent: one memset
-        CU_OK(cudaMemsetAsync(vcounters, 0, (size_t)((vtile_len - vcounters) + verify_tiles_cap_ + n_tiles) * sizeof(uint32_t), st));
+        CU_OK(cudaMemsetAsync(vcounters, 0, (size_t)((vtile_len - vcounters) + n_tiles) * sizeof(uint32_t), st));
         CU_OK(cudaEventRecord(EV(ev_[0]), st));
-        {                        // (a regrow of the event buffer repeats the whole step: the filter pass counts events too)
+        if (attempt == 0) {      // the bit planes survive a regrow of the event buffer
             fa.span_begin = 0;
             fa.span_end = n_spans;
             const unsigned grid_f = std::min<uint32_t>((n_spans + warps_per_cta - 1) / warps_per_cta, (uint32_t)n_sms_);
-            // flagged words are settled inside the filter pass where one comparison decides them and the batch is one
-            // haystack or equal-length haystacks (no offset search inside the streaming loop)
-            const bool verify = va.settled != 0;
-            if (W == 8) launch_filter_k<8>(fa, va, d_l2_ != nullptr, verify, grid_f, st);
-            else launch_filter_k<4>(fa, va, d_l2_ != nullptr, verify, grid_f, st);
+            if (W == 8) launch_filter_k<8>(fa, d_l2_ != nullptr, grid_f, st);
+            else launch_filter_k<4>(fa, d_l2_ != nullptr, grid_f, st);
             stats.kernel_launches += 1;
         }
         CU_OK(cudaEventRecord(EV(ev_[4]), st));
@@ -716,7 +699,7 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
         stats.kernel_ms += ms_f + ms_v + ms_r;
         const size_t found = h_counters_[1];
         end_state_ = h_counters_[2];
-        stats.flagged_words = h_counters_[3];
+        if (attempt == 0) stats.flagged_words = h_counters_[3];
         stats.dense_tiles = h_counters_[4];
         if (found <= events_cap_) {
             n_events_ = found; stats.events = found;

@@ -123,7 +123,6 @@ private:
     uint32_t *d_items_ = nullptr;   // work items of the verify kernels
     uint32_t *d_recs_ = nullptr;    // per item {first event state, count << 16 | relative end}
     uint32_t *d_desc_ = nullptr;    // per 16 KiB tile {offset into items, count}
-    uint32_t *d_tile_ev_ = nullptr; // per tile TILE_CAP event slots filled by the filter pass itself
     uint32_t *d_tile_len_ = nullptr;// per tile: events
     size_t verify_tiles_cap_ = 0;
     double last_dense_frac_ = 0.0; // tiles the verify kernel had to walk completely, previous filtered scan

@@ -52,9 +52,6 @@ constexpr int FILTER_UNROLL = 6;           // 16-byte loads in flight per thread
 constexpr uint32_t VER_DENSE_MAX = 64;     // flagged words per 16 KiB tile beyond which the whole tile is walked
 constexpr uint32_t ITEM_SPAN = 0x80000000u;// work item: walk 512-byte span (item & ~ITEM_SPAN) completely
 constexpr uint32_t ITEM_NONE = 0xffffffffu;
-constexpr uint32_t SPAN_CAP = 4;           // flagged words of one span the filter pass queues (more: the tile takes the slow path)
-constexpr uint32_t TILE_CAP = 64;          // events of one 16 KiB tile the filter pass can store (more: slow path)
-constexpr uint32_t DESC_FAST = 0xffffffffu;// desc[tile].x: every span of the tile was settled by the filter pass
 constexpr int COLLECT_THREADS = 1024;      // 32 tiles per CTA iteration share one atomic (same-address atomics serialise)
 constexpr int COUNT_THREADS = 256;
 constexpr int WALK_THREADS = 256;
@@ -109,6 +106,86 @@ __device__ __forceinline__ bool test_word(const FilterArgs &a, uint32_t s_base, 
     return p;
 }
 
+template <int W, bool L2>
+__global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const FilterArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *s_bm = reinterpret_cast<uint32_t *>(smem_raw);
+    constexpr int NB = 16 / W;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    const uint32_t s_base = stage_bitmap(a, s_bm, tid);
+    auto test = [&](uint32_t lo, uint32_t hi, uint32_t nb, bool maybe_unknown) -> bool {
+        return test_word<L2>(a, s_base, lo, hi, nb, maybe_unknown);
+    };
+
+    const uint32_t n_full_all = a.total / SPAN_BYTES;         // spans that lie completely inside the stream
+    const uint32_t n_full = min(n_full_all, a.span_end);
+    const uint32_t n_warps = gridDim.x * (SCAN_THREADS / 32);
+    const uint32_t warp = blockIdx.x * (SCAN_THREADS / 32) + (tid >> 5);
+    uint32_t flagged = 0;
+
+    for (uint32_t g0 = a.span_begin + warp; g0 < n_full; g0 += n_warps * FILTER_UNROLL) {
+        uint4 v[FILTER_UNROLL];
+#pragma unroll
+        for (int u = 0; u < FILTER_UNROLL; ++u) {
+            const uint32_t g = g0 + u * n_warps;
+            v[u] = make_uint4(0, 0, 0, 0);
+            if (g < n_full) v[u] = ld_text16(a.text + ((size_t)g * 32u + lane) * 16u);
+        }
+#pragma unroll
+        for (int u = 0; u < FILTER_UNROLL; ++u) {
+            const uint32_t g = g0 + u * n_warps;
+            if (g >= n_full) break;                           // warp-uniform
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            // byte after the lane's last word: the next lane's first byte; lane 31 does not know it
+            uint32_t after = __shfl_down_sync(0xffffffffu, w[0], 1) & 0xffu;
+            if (lane == 31u) after = FILTER_NEXT_UNKNOWN;
+            uint32_t mine = 0;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const uint32_t nb = (j == NB - 1) ? after : (((W == 8) ? w[2] : w[j + 1]) & 0xffu);
+                const bool p = (W == 8) ? test(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test(w[j], 0u, nb, j == NB - 1);
+                const uint32_t plane = __ballot_sync(0xffffffffu, p);
+                if (lane == (uint32_t)j) mine = plane;
+            }
+            if (lane < (uint32_t)NB) {
+                a.mask[(size_t)g * NB + lane] = mine;
+                flagged += __popc(mine);
+            }
+        }
+    }
+
+    // The last, partial span: complete 16-byte chunks are tested, the partial chunk at the very end is not
+    // read at all — its words are simply handed on to verification.
+    if (n_full_all < a.n_spans && n_full_all >= a.span_begin && n_full_all < a.span_end && warp == (n_full_all % n_warps)) {
+        const uint32_t n_full = n_full_all;
+        const uint32_t n16 = a.total >> 4;
+        const uint32_t c = n_full * 32u + lane;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (c < n16) v = ld_text16(a.text + (size_t)c * 16u);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const bool tail = (a.total & 15u) && c == n16;
+        uint32_t after = __shfl_down_sync(0xffffffffu, w[0], 1) & 0xffu;
+        if (lane == 31u || c + 1u >= n16) after = FILTER_NEXT_UNKNOWN;      // the next chunk is not in this warp's registers
+        uint32_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const uint32_t nb = (j == NB - 1) ? after : (((W == 8) ? w[2] : w[j + 1]) & 0xffu);
+            bool p = (W == 8) ? test(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test(w[j], 0u, nb, j == NB - 1);
+            p = (c < n16) ? p : tail;
+            const uint32_t plane = __ballot_sync(0xffffffffu, p);
+            if (lane == (uint32_t)j) mine = plane;
+        }
+        if (lane < (uint32_t)NB) {
+            a.mask[(size_t)n_full * NB + lane] = mine;
+            flagged += __popc(mine);
+        }
+    }
+    if (lane < (uint32_t)NB && flagged) atomicAdd(&a.counters[3], flagged);
+}
+
 // ------------------------------------------------------------ collect -----
 
 struct VerifyArgs {
@@ -125,9 +202,6 @@ struct VerifyArgs {
     const uint4 *gt_slots;        // exact gram table (gram_table.hpp) or nullptr
     const uint32_t *gt_pat;       // its pattern store
     uint32_t gt_log2;             // 2^gt_log2 slots; 0: every flagged word is walked
-    uint32_t settled;             // 1: ac_filter_verify_kernel settled flagged words itself (tile_ev / tile_slow are meaningful)
-    uint2 *tile_ev;               // per tile TILE_CAP slots {end offset, state}: the events the filter pass settled, unordered
-    uint32_t *tile_slow;          // per tile (zeroed before the launch): non-zero = the filter pass could not settle all of it
     uint32_t *items;              // work items, tile runs in completion order (capacity n_tiles * VER_DENSE_MAX)
     uint2 *desc;                  // per tile {offset into items, count}
     uint2 *recs;                  // per item {state of the first event, count << 16 | first end - item origin}
@@ -170,26 +244,6 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
         load_planes(tile + gridDim.x * N_WARPS, next_planes);      // in flight while this tile is compacted
         const uint32_t span = tile * 32u + lane;
         const bool active = tile < a.tile_end && span < a.n_spans;
-        // A tile the filter pass settled completely needs no items: its events already sit in tile_ev and are
-        // counted.  Anything it could not settle (or a densely flagged tile) sends the WHOLE tile through the items;
-        // what the filter pass counted for it is taken back first.
-        uint32_t n_flagged = 0;
-#pragma unroll
-        for (int j = 0; j < NB; ++j) n_flagged += __popc(planes[j]);
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) n_flagged += __shfl_xor_sync(0xffffffffu, n_flagged, d);
-        uint32_t fast_word = 0;                            // lane 0 decides, everyone follows
-        if (a.settled && lane == 0 && tile < a.tile_end) {
-            const uint32_t counted = a.tile_len[tile];
-            const bool ok = __ldg(a.tile_slow + tile) == 0u && counted <= TILE_CAP && n_flagged <= a.dense_max;
-            if (!ok && counted) { a.tile_len[tile] = 0; atomicSub(&a.block_sum[tile / EMIT_THREADS], counted); }
-            fast_word = ok ? 1u : 0u;
-        }
-        const bool fast = a.settled && (tile >= a.tile_end || __shfl_sync(0xffffffffu, fast_word, 0) != 0u);
-        if (fast) {
-#pragma unroll
-            for (int j = 0; j < NB; ++j) planes[j] = 0;
-        }
         uint32_t cnt = 0;
 #pragma unroll
         for (int j = 0; j < NB; ++j) cnt += __popc(planes[j]);
@@ -217,9 +271,7 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
         if (threadIdx.x == 0) s_base = a.item_base + (cta_total ? atomicAdd(&a.s.counters[a.counter_slot], cta_total) : 0u);
         __syncthreads();
         const uint32_t base = s_base + __shfl_sync(0xffffffffu, wincl - v, warp);
-        if (lane == 0 && tile < a.tile_end) {
-            a.desc[tile] = fast ? make_uint2(DESC_FAST, n_flagged) : make_uint2(base, n);
-        }
+        if (lane == 0 && tile < a.tile_end) a.desc[tile] = make_uint2(base, n);
         if (n == 0) {
         } else if (dense) {
             ++dense_tiles;
@@ -563,187 +615,6 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
     }
 }
 
-// ------------------------------------------------------ filter + verify ---
-
-// The filter pass with the verification folded in.
-//
-// A warp streams 512-byte spans (U loads in flight), tests every aligned word against the bitmap and ballots the
-// flag bits into the span's bit planes — and instead of leaving every flagged word to a later kernel (one random
-// DRAM read each, long after the span has left the caches), it puts the word on a small queue of its own in shared
-// memory.  Whenever 32 words have gathered, the warp settles them together, one per lane: the three groups around
-// the word come from L2 (the warp read them microseconds ago), one probe of the exact gram table (gram_table.hpp)
-// and one comparison decide it; the SM's other warps keep streaming meanwhile.  An event goes to the next free
-// slot of its 16 KiB tile (tile_ev, TILE_CAP slots, claimed through tile_len — ac_emit_kernel puts a tile's few
-// events in order) and is counted for its block of tiles (block_sum) as ac_walk_kernel does.  What cannot be
-// settled that way — a key several patterns share, a window cut by a haystack or stream end, more than SPAN_CAP
-// flagged words in one span — marks the tile in tile_slow: ac_collect_kernel takes its count back and sends the
-// whole tile through the items / ac_walk_kernel as before.  The bit planes are written regardless.
-//
-// The streaming loop issues ~60 instructions per 512-byte span and is as much bound by that as by HBM (ncu: issue
-// slots 55 % busy at 0.80 of the copy bandwidth; 40 % more instructions measured 28 % more time), so everything
-// the verification adds sits behind the warp-uniform "any word flagged" branch or in the rounds.
-constexpr uint32_t VQ_SLOTS = 56;          // queue entries per warp: < 32 after a flush + FILTER_UNROLL spans x SPAN_CAP
-constexpr uint32_t VQ_BYTES = (SCAN_THREADS / 32) * VQ_SLOTS * 4;
-
-// settles up to 32 queued words (their indices in the stream), one per lane; called by the whole warp
-template <int W>
-__device__ __noinline__ void verify_round(const VerifyArgs &a, uint32_t k, bool have)
-{
-    constexpr uint32_t NB = 16u / W;
-    ItemEvents ev{0u, 0u, 0u};
-    bool slow = false;
-    const uint32_t tile = k / (32u * NB * 32u);
-    if (have) {
-        const uint32_t rs = (k + 1u) * W;                    // the word owns the end offsets rs+1 .. rs+W
-        bool can = rs >= a.warm && rs + W <= a.s.total;
-        uint32_t w0 = 0;
-        if (can) {
-            // (equal-length batches and single haystacks only: no search through an offset array here)
-            const uint32_t hb = rs / a.s.uniform_len * a.s.uniform_len;
-            w0 = max(rs - a.warm, hb);
-            can = hb + a.s.uniform_len >= rs + W && ((rs - w0) & (uint32_t)(W - 1)) == 0 && w0 < rs;
-        }
-        slow = !can || !verify_word_direct<W>(a, rs, w0, ev);
-        if (slow) a.tile_slow[tile] = 1u;
-    }
-    const bool has = have && !slow && ev.cnt;
-    if (has) {
-        const uint32_t slot = atomicAdd(&a.tile_len[tile], 1u);
-        if (slot < TILE_CAP) a.tile_ev[(size_t)tile * TILE_CAP + slot] = make_uint2(ev.e0p, ev.e0s);
-    }
-    // events per block of EMIT_THREADS tiles (one atomic per warp where the lanes agree on the block)
-    const uint32_t blk = has ? tile / EMIT_THREADS : 0xffffffffu;
-    const uint32_t voters = __ballot_sync(0xffffffffu, has);
-    if (voters) {
-        const uint32_t lead_blk = __shfl_sync(0xffffffffu, blk, __ffs(voters) - 1);
-        if (__all_sync(0xffffffffu, !has || blk == lead_blk)) {
-            if ((threadIdx.x & 31u) == 0u) atomicAdd(&a.block_sum[lead_blk], (uint32_t)__popc(voters));
-        } else if (has) atomicAdd(&a.block_sum[blk], 1u);
-    }
-}
-
-template <int W, bool L2, bool VERIFY>
-__global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_verify_kernel(const FilterArgs fa, const __grid_constant__ VerifyArgs a)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *s_bm = reinterpret_cast<uint32_t *>(smem_raw);
-    constexpr int NB = 16 / W;
-    constexpr int U = FILTER_UNROLL;
-
-    const uint32_t tid = threadIdx.x;
-    const uint32_t lane = tid & 31u;
-    const uint32_t lanes_below = (1u << lane) - 1u;
-    const uint32_t s_base = stage_bitmap(fa, s_bm, tid);
-    // this warp's queue of flagged words (shared-window byte address)
-    const uint32_t q_base = s_base + FILTER_L1_BYTES + (tid >> 5) * (VQ_SLOTS * 4u);
-    uint32_t qn = 0;                                          // queued words (warp-uniform)
-    auto test = [&](uint32_t lo, uint32_t hi, uint32_t nb, bool maybe_unknown) -> bool {
-        return test_word<L2>(fa, s_base, lo, hi, nb, maybe_unknown);
-    };
-    auto flush = [&]() {                                      // settles the first 32 queued words (or all, if fewer)
-        __syncwarp();
-        uint32_t k = 0, moved = 0;
-        const bool have = lane < qn, more = lane + 32u < qn;
-        if (have) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(k) : "r"(q_base + lane * 4u));
-        if (more) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(moved) : "r"(q_base + (lane + 32u) * 4u));
-        __syncwarp();
-        if (more) asm volatile("st.shared.u32 [%0], %1;" :: "r"(q_base + lane * 4u), "r"(moved));     // the rest moves to the front
-        qn = qn > 32u ? qn - 32u : 0u;
-        verify_round<W>(a, k, have);
-    };
-
-    const uint32_t n_full_all = fa.total / SPAN_BYTES;        // spans that lie completely inside the stream
-    const uint32_t n_full = min(n_full_all, fa.span_end);
-    const uint32_t n_warps = gridDim.x * (SCAN_THREADS / 32);
-    const uint32_t warp = blockIdx.x * (SCAN_THREADS / 32) + (tid >> 5);
-    uint32_t flagged = 0;
-
-    for (uint32_t g0 = fa.span_begin + warp; g0 < n_full; g0 += n_warps * U) {
-        // (the round sits where nothing of the streaming loop is live: a call in the middle of it spills the spans in
-        // flight to local memory on every iteration — measured 2x slower)
-        if (VERIFY && qn >= 32u) flush();
-        uint4 v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t g = g0 + u * n_warps;
-            v[u] = make_uint4(0, 0, 0, 0);
-            if (g < n_full) v[u] = ld_text16(fa.text + ((size_t)g * 32u + lane) * 16u);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t g = g0 + u * n_warps;
-            if (g >= n_full) break;                           // warp-uniform
-            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-            // byte after the lane's last word: the next lane's first byte; lane 31 does not know it
-            uint32_t after = __shfl_down_sync(0xffffffffu, w[0], 1) & 0xffu;
-            if (lane == 31u) after = FILTER_NEXT_UNKNOWN;
-            uint32_t mine = 0, any = 0;
-            bool p[NB];
-            uint32_t plane[NB];
-#pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                const uint32_t nb = (j == NB - 1) ? after : (((W == 8) ? w[2] : w[j + 1]) & 0xffu);
-                p[j] = (W == 8) ? test(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test(w[j], 0u, nb, j == NB - 1);
-                plane[j] = __ballot_sync(0xffffffffu, p[j]);
-                any |= plane[j];
-                if (lane == (uint32_t)j) mine = plane[j];
-            }
-            if (lane < (uint32_t)NB) {
-                fa.mask[(size_t)g * NB + lane] = mine;
-                flagged += __popc(mine);
-            }
-            if (VERIFY && any) {                              // warp-uniform
-                // queue the flagged words in stream order: by lane, then by word inside the lane
-                uint32_t n_flag = 0, at = qn;
-#pragma unroll
-                for (int j = 0; j < NB; ++j) { n_flag += __popc(plane[j]); at += __popc(plane[j] & lanes_below); }
-                if (n_flag > SPAN_CAP) {
-                    if (lane == 0u) a.tile_slow[g >> 5] = 1u;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < NB; ++j) {
-                        if (p[j]) {
-                            asm volatile("st.shared.u32 [%0], %1;" :: "r"(q_base + at * 4u), "r"(g * (32u * NB) + lane * NB + j));
-                            ++at;
-                        }
-                    }
-                    qn += n_flag;
-                }
-            }
-        }
-    }
-    while (VERIFY && qn) flush();
-
-    // The last, partial span: complete 16-byte chunks are tested, the partial chunk at the very end is not
-    // read at all — its words are simply handed on to verification (always through the collect / walk path).
-    if (n_full_all < fa.n_spans && n_full_all >= fa.span_begin && n_full_all < fa.span_end && warp == (n_full_all % n_warps)) {
-        const uint32_t n16 = fa.total >> 4;
-        const uint32_t c = n_full_all * 32u + lane;
-        uint4 t = make_uint4(0, 0, 0, 0);
-        if (c < n16) t = ld_text16(fa.text + (size_t)c * 16u);
-        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-        const bool tail = (fa.total & 15u) && c == n16;
-        uint32_t after = __shfl_down_sync(0xffffffffu, w[0], 1) & 0xffu;
-        if (lane == 31u || c + 1u >= n16) after = FILTER_NEXT_UNKNOWN;      // the next chunk is not in this warp's registers
-        uint32_t mine = 0, any = 0;
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-            const uint32_t nb = (j == NB - 1) ? after : (((W == 8) ? w[2] : w[j + 1]) & 0xffu);
-            bool p = (W == 8) ? test(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test(w[j], 0u, nb, j == NB - 1);
-            p = (c < n16) ? p : tail;
-            const uint32_t plane = __ballot_sync(0xffffffffu, p);
-            any |= plane;
-            if (lane == (uint32_t)j) mine = plane;
-        }
-        if (lane < (uint32_t)NB) {
-            fa.mask[(size_t)n_full_all * NB + lane] = mine;
-            flagged += __popc(mine);
-        }
-        if (VERIFY && any && lane == 0u) a.tile_slow[n_full_all >> 5] = 1u;
-    }
-    if (lane < (uint32_t)NB && flagged) atomicAdd(&fa.counters[3], flagged);
-}
-
 // --------------------------------------------------------------- emit -----
 
 // Exclusive prefix sum of the events per tile.  One CTA per 256 tiles: it adds up the earlier blocks' sums
@@ -808,28 +679,7 @@ __global__ void __launch_bounds__(COUNT_THREADS) ac_emit_kernel(const __grid_con
         uint32_t next_off;
         uint2 next_d;
         load_header(tile + n_warps, next_len, next_d, next_off);
-        if (len && d.x == DESC_FAST) {
-            // the filter pass settled the whole tile: its len <= TILE_CAP events sit in tile_ev in the order the rounds
-            // finished — every lane takes two, ranks them by end offset (distinct) and writes them in place
-            const uint2 *ev = a.tile_ev + (size_t)tile * TILE_CAP;
-            uint2 e0 = make_uint2(0xffffffffu, 0u), e1 = make_uint2(0xffffffffu, 0u);
-            if (lane < len) e0 = ev[lane];
-            if (lane + 32u < len) e1 = ev[lane + 32u];
-            uint32_t r0 = 0, r1 = 0;
-            for (uint32_t i = 0; i < min(len, 32u); ++i) {                // warp-uniform
-                const uint32_t x = __shfl_sync(0xffffffffu, e0.x, i);
-                r0 += x < e0.x ? 1u : 0u;
-                r1 += x < e1.x ? 1u : 0u;
-            }
-            for (uint32_t i = 32; i < len; ++i) {
-                const uint32_t x = __shfl_sync(0xffffffffu, e1.x, i - 32u);
-                r0 += x < e0.x ? 1u : 0u;
-                r1 += x < e1.x ? 1u : 0u;
-            }
-            if (lane < len && off + r0 < a.s.capacity) a.s.out[off + r0] = e0;
-            if (lane + 32u < len && off + r1 < a.s.capacity) a.s.out[off + r1] = e1;
-        }
-        const uint32_t n_items = (len && d.x != DESC_FAST) ? d.y : 0u;   // warp-uniform; 0: nothing left to do for this tile
+        const uint32_t n_items = len ? d.y : 0u;                      // warp-uniform; 0: nothing ends in this tile
         for (uint32_t i0 = 0; i0 < n_items; i0 += 32u) {             // warp-uniform
             const uint32_t i = i0 + lane;
             uint32_t item = ITEM_NONE, cnt = 0;

@@ -60,71 +60,77 @@ void throw_aho(aho_diag_t *d, const char *fmt, ...)
     va_end(ap);
 }
 
-bool key_is(const aho_entry_t &e, const char *name)   // COMPAT_STR_EQUALS_CI
+// The fields a pattern array may carry (keys are matched case-insensitively; an element without a string key is
+// the value).  Rules observed from the reference (src/php_ahocorasick.c:195-336): unknown key -> warning, the call
+// fails; id must be an integer and key / value strings, else AhoException; a value is mandatory; key and id exclude
+// each other; ignoreCase is accepted with a deprecation warning and has no effect.
+enum Field { FIELD_NONE, FIELD_KEY, FIELD_VALUE, FIELD_IGNORECASE, FIELD_ID, FIELD_AUX };
+
+Field field_of(const aho_entry_t &e)
 {
-    return e.key_len == strlen(name) && strncasecmp(e.key, name, e.key_len) == 0;
+    static const struct { const char *name; Field f; } table[] = {
+        {"key", FIELD_KEY}, {"value", FIELD_VALUE}, {"ignoreCase", FIELD_IGNORECASE}, {"id", FIELD_ID}, {"aux", FIELD_AUX}};
+    if (!e.key) return FIELD_VALUE;
+    for (const auto &t : table)
+        if (e.key_len == strlen(t.name) && strncasecmp(e.key, t.name, e.key_len) == 0) return t.f;
+    return FIELD_NONE;
 }
 
-// php_ahocorasick_process_pattern, src/php_ahocorasick.c:195-336
+// one element of the pattern array -> record; 0 on success
 int process_pattern(long pidx, PatternRec &p, const aho_array_t *sub, aho_diag_t *diag)
 {
+    bool seen[6] = {false, false, false, false, false, false};
     int rc = 0;
-    unsigned long all_keys = 0;
-    bool has_exception = false;
-    for (size_t k = 0; k < sub->n; ++k) {
-        if (rc != 0 || has_exception) break;
+    for (size_t k = 0; k < sub->n && rc == 0; ++k) {
         const aho_entry_t &e = sub->entries[k];
-        unsigned long found = 0;
-        if (!e.key) found |= 2;                           // bare element => value (:230-231)
-        else if (key_is(e, "key")) found |= 1;
-        else if (key_is(e, "value")) found |= 2;
-        else if (key_is(e, "ignoreCase")) found |= 4;
-        else if (key_is(e, "id")) found |= 8;
-        else if (key_is(e, "aux")) found |= 0x10;
-        else {
+        const Field f = field_of(e);
+        seen[f] = true;
+        switch (f) {
+        case FIELD_NONE:
             warn(diag, "Invalid structure (unrecognized sub-array key)! Only allowed are: {key, id, value, aux, "
                        "ignoreCase}. Cannot initialize. Pattern index: %ld", pidx);
             rc = -2;
             break;
-        }
-        all_keys |= found;
-        if (found & 0x8) {
+        case FIELD_ID:
             if (e.val.type != AHO_T_LONG) {
                 throw_aho(diag, "Invalid type of pattern ID given (long required), type: %s, pattern index: %ld",
                           type_str(e.val.type), pidx);
-                has_exception = true; rc = -5;
+                rc = -5;
                 break;
             }
             p.key_id = e.val.lval;
             p.key_type = AC_PATTID_TYPE_NUMBER;
-        }
-        if (found & 0x10) { p.has_aux = true; p.aux_opaque = e.val.opaque; }
-        if (found & 0x3) {
+            break;
+        case FIELD_AUX:
+            p.has_aux = true;
+            p.aux_opaque = e.val.opaque;
+            break;
+        case FIELD_KEY:
+        case FIELD_VALUE: {
             if (e.val.type != AHO_T_STRING) {
                 throw_aho(diag, "Pattern %s has to be a string, type: %s, pattern index: %ld",
-                          found == 0x1 ? "key" : "value", type_str(e.val.type), pidx);
-                has_exception = true; rc = -5;
+                          f == FIELD_KEY ? "key" : "value", type_str(e.val.type), pidx);
+                rc = -5;
                 break;
             }
-            if (found == 0x1) {
-                p.key.assign(e.val.sval ? e.val.sval : "", e.val.slen);
-                p.key_opaque = e.val.opaque; p.has_key = true;
-                p.key_type = AC_PATTID_TYPE_STRING;
-            } else {
-                p.value.assign(e.val.sval ? e.val.sval : "", e.val.slen);
-                p.value_opaque = e.val.opaque; p.has_value = true;
-            }
+            std::string &dst = (f == FIELD_KEY) ? p.key : p.value;
+            dst.assign(e.val.sval ? e.val.sval : "", e.val.slen);
+            if (f == FIELD_KEY) { p.key_opaque = e.val.opaque; p.has_key = true; p.key_type = AC_PATTID_TYPE_STRING; }
+            else { p.value_opaque = e.val.opaque; p.has_value = true; }
+            break;
+        }
+        case FIELD_IGNORECASE:
+            break;
         }
     }
     if (rc == 0 && !p.has_value) {
         warn(diag, "No value was specified for pattern index: %ld", pidx);
         rc = -2;
-    }
-    if (rc == 0 && (all_keys & 0x1) && (all_keys & 0x8)) {
+    } else if (rc == 0 && seen[FIELD_KEY] && seen[FIELD_ID]) {
         warn(diag, "Pattern can have either numeric or string identifier, not both! Pattern index: %ld", pidx);
         rc = -3;
     }
-    if (all_keys & 0x4)
+    if (seen[FIELD_IGNORECASE])
         warn(diag, "ignoreCase attribute is deprecated and is ignored. Pattern index: %ld", pidx);
     return rc;
 }

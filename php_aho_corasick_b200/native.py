@@ -259,8 +259,7 @@ class Automaton:
         return int(self.L.acb200_filter_probe(self.h, int(word), int(next_byte)))
 
     def set_direct(self, mode: int) -> None:
-        """0 automatic (= 1), 1 flagged words settled by one comparison inside the filter pass, 2 inside the walk kernel,
-        -1 every flagged word is walked"""
+        """0 automatic (= 1), 1 flagged words settled by one comparison inside the walk kernel, -1 every flagged word is walked"""
         self.L.acb200_set_direct(self.h, int(mode))
 
     def direct_probe(self, text: bytes, word_index: int, hay_begin: int = 0):

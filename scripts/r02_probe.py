@@ -34,7 +34,7 @@ def main():
             n_h = n_blocks * 256
             scan = lambda: a.search_device_uniform(d.data_ptr(), n_h, 8192)[1]
             if "cfg2" in which:
-                for mode in (1, 2, -1):
+                for mode in (1, -1):
                     a.set_direct(mode)
                     split(f"cfg2 1 GiB planted={planted} direct={mode}", a, scan)
                 a.set_direct(0)
@@ -53,7 +53,7 @@ def main():
         pats, hay, off = W.cfg3(hay_bytes=256 << 20)
         a = Automaton(0); a.add_php_order(pats); a.finalize()
         d = torch.from_numpy(hay).to(dev)
-        for mode in (1, 2):
+        for mode in (1,):
             a.set_direct(mode)
             split(f"cfg3 256 MiB direct={mode}", a, lambda: a.search_device(d.data_ptr(), off)[1])
         del d

@@ -405,9 +405,8 @@ def test_randomised_mixtures_of_dense_and_sparse_regions(seed):
 
 
 def test_direct_verification_equals_walking_every_flagged_word():
-    """gram_table.hpp: flagged words settled by one comparison inside the filter pass itself (default,
-    ac_filter_verify_kernel) vs inside ac_walk_kernel (set_direct(2)) vs every flagged word walked (set_direct(-1)) vs
-    the full automaton walk — raw events (end offset AND state id) must be identical."""
+    """gram_table.hpp: flagged words settled by one comparison inside ac_walk_kernel (default) vs every flagged word
+    walked (set_direct(-1)) vs the full automaton walk — raw events (end offset AND state id) must be identical."""
     rng = np.random.default_rng(77)
     pyr = random.Random(77)
     cases = []
@@ -446,12 +445,11 @@ def test_direct_verification_equals_walking_every_flagged_word():
         ev = a.search_events(flat, offs)
         st = a.stats()
         assert st.filtered == 1 and st.kernel_launches == 5 and len(ev) > 100
-        for mode in (2, -1):                 # settled inside the walk kernel only / every flagged word walked
-            a.set_direct(mode)
-            ev_walk = a.search_events(flat, offs)
-            st = a.stats()
-            assert st.filtered == 1 and st.kernel_launches == 5
-            assert np.array_equal(ev, ev_walk), mode
+        a.set_direct(-1)
+        ev_walk = a.search_events(flat, offs)
+        st = a.stats()
+        assert st.filtered == 1 and st.kernel_launches == 5
+        assert np.array_equal(ev, ev_walk)
         a.set_filter(-1)
         ev_full = a.search_events(flat, offs)
         assert a.stats().filtered == 0
