@@ -560,7 +560,7 @@ int acb200_search_hits(AC_TRIE_t *t, const char *bytes, const uint64_t *offsets,
     if (t->open) { set_error("automaton is not finalized"); return -1; }
     if (!t->device_ok) return -1;
     if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return -1; }
-    if (!t->engine.scan_host(bytes, offsets, n, false, ROOT_STATE)) return -1;
+    if (!t->engine.scan_host(bytes, offsets, n, false, ROOT_STATE, true)) return -1;
     size_t total = 0;
     const bool ok = t->engine.expand_hits_to_host(n, hits, cap, &total);
     t->stats = t->engine.stats; t->stats.devices = 1;

@@ -67,6 +67,8 @@ void Engine::release()
     d_items_ = nullptr; d_recs_ = nullptr; d_desc_ = nullptr; d_tile_len_ = nullptr; verify_tiles_cap_ = 0;
     if (h_counters_) cudaFreeHost(h_counters_);
     if (h_events_) cudaFreeHost(h_events_);
+    if (h_small_) cudaFreeHost(h_small_);
+    h_small_ = nullptr; last_host_events_ = nullptr;
     for (int b = 0; b < 2; ++b) { if (h_slab_[b]) cudaFreeHost(h_slab_[b]); h_slab_[b] = nullptr; h_slab_cap_[b] = 0; }
     for (auto &e : ev_) if (e) { cudaEventDestroy(EV(e)); e = nullptr; }
     for (auto &e : ev_slab_) if (e) { cudaEventDestroy(EV(e)); e = nullptr; }
@@ -292,6 +294,8 @@ bool Engine::ensure_host_events(size_t n)
 {
     if (n <= h_events_cap_) return true;
     if (h_events_) cudaFreeHost(h_events_);
+    if (h_small_) cudaFreeHost(h_small_);
+    h_small_ = nullptr; last_host_events_ = nullptr;
     h_events_ = nullptr; h_events_cap_ = 0;
     const size_t cap = std::max(n + n / 4, (size_t)4096);
     CU_OK(cudaMallocHost(&h_events_, cap * sizeof(PackedEvent)));
@@ -577,7 +581,6 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     uint32_t *const vcounters = d_tile_len_;                              // counters of the prefilter path
     uint32_t *const vblock_sum = d_tile_len_ + 16;
     uint32_t *const vtile_len = vblock_sum + (verify_tiles_cap_ / EMIT_THREADS + 16);
-    fa.counters = vcounters;
 
     VerifyArgs va{};
     ScanArgs &a = va.s;
@@ -903,6 +906,7 @@ bool Engine::scan_slab(int buf, const uint64_t *offsets, size_t n, bool first_on
     if (n_events_) {
         if (!ensure_host_events(n_events_)) return false;
         CU_OK(cudaEventRecord(EV(ev_[2]), st));
+        last_host_events_ = h_events_;
         CU_OK(cudaMemcpyAsync(h_events_, d_events_, n_events_ * sizeof(PackedEvent), cudaMemcpyDeviceToHost, st));
         CU_OK(cudaEventRecord(EV(ev_[3]), st));
         CU_OK(cudaStreamSynchronize(st));
@@ -913,13 +917,63 @@ bool Engine::scan_slab(int buf, const uint64_t *offsets, size_t n, bool first_on
     return true;
 }
 
+// One short text: host-to-device copy from pinned staging, ONE launch of a one-CTA kernel that writes the ordered
+// events, their count and the end state into mapped host memory, one wait.
+bool Engine::scan_small(const char *bytes, uint32_t total, uint32_t init_state)
+{
+    cudaStream_t st = S(stream_);
+    constexpr size_t HDR = 64, EV_BYTES = (size_t)SMALL_TEXT_BYTES * sizeof(PackedEvent);
+    if (!h_small_) {
+        CU_OK(cudaHostAlloc(&h_small_, HDR + EV_BYTES + SMALL_TEXT_BYTES, cudaHostAllocMapped));
+        if (!ensure_text(SMALL_TEXT_BYTES + 64)) return false;
+    }
+    uint32_t *hdr = reinterpret_cast<uint32_t *>(h_small_);
+    PackedEvent *ev = reinterpret_cast<PackedEvent *>(h_small_ + HDR);
+    uint8_t *stage = h_small_ + HDR + EV_BYTES;
+    memcpy(stage, bytes, total);
+    CU_OK(cudaMemcpyAsync(d_text_, stage, total, cudaMemcpyHostToDevice, st));
+    const uint32_t want = (total + 15u) / 16u;
+    const uint32_t threads = std::min<uint32_t>(SMALL_THREADS, (want + 31u) & ~31u);
+    SmallArgs a{};
+    a.text = d_text_; a.total = total; a.readable = (uint32_t)std::min<size_t>(text_cap_, 0xffffffffu);
+    a.chunk = (((total + threads - 1) / threads) + 15u) & ~15u;
+    a.halo = halo_;
+    a.table = d_table_; a.cls_map = d_cls_; a.ncls = ncls_; a.final_bound = final_bound_; a.root = root_;
+    a.range_lo = range_lo_; a.n_used = n_used_;
+    a.init_state = (init_state == ROOT_STATE) ? root_ : init_state;
+    a.out = reinterpret_cast<uint2 *>(ev); a.capacity = SMALL_TEXT_BYTES;      // at most one event per byte
+    a.hdr = hdr;
+    hdr[1] = a.init_state;
+    if (entry_bytes_ == 2) {
+        if (range_map_) ac_small_kernel<uint16_t, true><<<1, threads, 0, st>>>(a);
+        else ac_small_kernel<uint16_t, false><<<1, threads, 0, st>>>(a);
+    } else {
+        if (range_map_) ac_small_kernel<uint32_t, true><<<1, threads, 0, st>>>(a);
+        else ac_small_kernel<uint32_t, false><<<1, threads, 0, st>>>(a);
+    }
+    CU_OK(cudaGetLastError());
+    CU_OK(cudaStreamSynchronize(st));
+    n_events_ = hdr[0];
+    end_state_ = hdr[1];
+    last_host_events_ = ev;
+    last_uniform_len_ = total;
+    stats = ACB200_STATS_t{};
+    stats.bytes = total; stats.events = n_events_; stats.kernel_launches = 1;
+    stats.chunk_bytes = a.chunk; stats.halo_bytes = halo_;
+    last_density_ = (double)n_events_ / (double)total;
+    return true;
+}
+
 bool Engine::scan_host(const char *bytes, const uint64_t *offsets, size_t n, bool first_only,
-                       uint32_t init_state)
+                       uint32_t init_state, bool events_stay_on_device)
 {
     if (device_ < 0) { set_error("automaton has no device table (finalize failed?)"); return false; }
     CU_OK(cudaSetDevice(device_));
     cudaStream_t st = S(stream_);
     const uint64_t total = offsets[n];
+    // (events of a findAll=false call are cut to the first one by the caller; tune_chunk forces the general path)
+    if (n == 1 && total > 0 && total <= SMALL_TEXT_BYTES && !events_stay_on_device && !tune_chunk && !tune_smem_bytes && tune_filter <= 0)
+        return scan_small(bytes, (uint32_t)total, init_state);
     if (total >= MAX_STREAM_BYTES) { set_error("haystack stream exceeds 4 GiB per call"); return false; }
     if (!ensure_text(total + 64)) return false;
     uint32_t uniform_len = 0;
@@ -936,6 +990,7 @@ bool Engine::scan_host(const char *bytes, const uint64_t *offsets, size_t n, boo
     if (n_events_) {
         if (!ensure_host_events(n_events_)) return false;
         CU_OK(cudaEventRecord(EV(ev_[2]), st));
+        last_host_events_ = h_events_;
         CU_OK(cudaMemcpyAsync(h_events_, d_events_, n_events_ * sizeof(PackedEvent), cudaMemcpyDeviceToHost, st));
         CU_OK(cudaEventRecord(EV(ev_[3]), st));
         CU_OK(cudaStreamSynchronize(st));

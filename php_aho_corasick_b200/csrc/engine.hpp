@@ -36,8 +36,9 @@ public:
 
     // Scans a flat haystack stream that lives in HOST memory.  Events are left in
     // host_events() sorted by stream offset; returns false on error.
+    // (events_stay_on_device: the caller goes on with the device copy of the events — expand_hits_to_host())
     bool scan_host(const char *bytes, const uint64_t *offsets, size_t n, bool first_only,
-                   uint32_t init_state);
+                   uint32_t init_state, bool events_stay_on_device = false);
     // Pipelined variant for large batches: the caller cuts the batch into slabs at haystack boundaries,
     // uploads slab i+1 (slab_upload_async) while slab i is scanned (scan_slab) and replayed on the host.
     // `bytes` is page-locked memory: the caller's own (acb200_host_alloc) or slab_staging(buf, n).
@@ -62,7 +63,7 @@ public:
     // Expands the events of the most recent scan_host() into hits on the device and copies up to `cap` of them
     // to `hits` (host).  *n_hits receives the total.
     bool expand_hits_to_host(size_t n_hay, ACB200_HIT_t *hits, size_t cap, size_t *n_hits);
-    const PackedEvent *host_events() const { return h_events_; }
+    const PackedEvent *host_events() const { return last_host_events_; }
     const void *device_events() const { return d_events_; }
     size_t n_events() const { return n_events_; }
     uint32_t end_state() const { return end_state_; }
@@ -86,6 +87,7 @@ private:
                          void *stream);
     void window_for(size_t smem_budget, uint32_t *win_lo, uint32_t *win_rows) const;
     bool ensure_host_events(size_t n);
+    bool scan_small(const char *bytes, uint32_t total, uint32_t init_state);
     bool upload_offsets(const uint64_t *offsets, size_t n, uint32_t *uniform_len);
     bool launch_scan(const void *d_text, uint32_t total, uint32_t readable, size_t n_hay, uint32_t uniform_len,
                      bool first_only, uint32_t init_state, void *stream);
@@ -136,6 +138,8 @@ private:
     uint32_t *d_counters_ = nullptr;
     uint32_t *h_counters_ = nullptr;          // pinned
     PackedEvent *h_events_ = nullptr; size_t h_events_cap_ = 0;   // pinned
+    const PackedEvent *last_host_events_ = nullptr;               // where the most recent host-side scan left its events
+    uint8_t *h_small_ = nullptr;                                   // pinned + mapped: [64-byte header | events | text staging] of the one-CTA path
     void *h_slab_[2] = {nullptr, nullptr}; size_t h_slab_cap_[2] = {0, 0};   // pinned staging of the slabs (pageable / scattered input)
     uint8_t *d_slab_[2] = {nullptr, nullptr}; size_t slab_cap_[2] = {0, 0};   // double-buffered haystack slabs
     void *copy_stream_ = nullptr;                                  // cudaStream_t of the slab uploads

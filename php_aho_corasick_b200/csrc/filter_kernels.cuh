@@ -71,7 +71,6 @@ struct FilterArgs {
     uint32_t *mask;               // n_spans x (16/W) words: plane j bit c <=> word (c*(16/W) + j) of the span
     uint32_t n_spans;             // ceil(total / 512)
     uint32_t span_begin, span_end;// this launch filters spans [span_begin, span_end)
-    uint32_t *counters;           // [3] += flagged words
 };
 
 // ------------------------------------------------------------- filter -----
@@ -89,14 +88,20 @@ __device__ __forceinline__ uint32_t stage_bitmap(const FilterArgs &a, uint32_t *
 
 // One flag per aligned word: both bits of the gram hash (the word + the byte after it) are set in level 1
 // (and, with L2, the bit of the independent hash in the level-2 bitmap in HBM/L2).
+//
+// The streaming loop issues ~60 instructions per 512-byte span and is as much bound by that as by HBM (ncu: issue
+// slots 55 % busy at 0.80 of the copy bandwidth; a variant with 40 % more instructions took 28 % longer), so the
+// test is written instruction by instruction: `region` / `n_words` select the part of the bitmap (per-lane
+// constants for the span's last word, whose successor only lanes 0..30 know), the two bit positions are taken
+// with wrap-around funnel shifts (no masking of the shift amounts).
 template <bool L2>
-__device__ __forceinline__ bool test_word(const FilterArgs &a, uint32_t s_base, uint32_t lo, uint32_t hi, uint32_t nb, bool maybe_unknown)
+__device__ __forceinline__ bool test_word_at(const FilterArgs &a, uint32_t region, uint32_t n_words, uint32_t lo, uint32_t hi, uint32_t nb)
 {
     const uint32_t t = filter_mix1(lo, hi, nb);
-    const uint32_t widx = maybe_unknown ? filter_l1_word(t, nb == FILTER_NEXT_UNKNOWN) : filter_l1_word(t, false);
     uint32_t word;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(s_base + widx * 4u));
-    bool p = ((word >> filter_bit1(t)) & (word >> filter_bit2(t)) & 1u) != 0;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(region + __umulhi(t, n_words) * 4u));
+    // bit (t & 31) and bit ((t >> 5) & 31) — filter_bit1 / filter_bit2
+    bool p = (__funnelshift_r(word, word, t) & __funnelshift_r(word, word, t >> 5) & 1u) != 0;
     if (L2) {
         uint32_t word3 = 0;
         const uint32_t i3 = filter_mix3(lo, hi, nb) >> a.l2_shift;
@@ -106,55 +111,75 @@ __device__ __forceinline__ bool test_word(const FilterArgs &a, uint32_t s_base, 
     return p;
 }
 
+template <bool L2>
+__device__ __forceinline__ bool test_word(const FilterArgs &a, uint32_t s_base, uint32_t lo, uint32_t hi, uint32_t nb, bool maybe_unknown)
+{
+    const bool unknown = maybe_unknown && nb == FILTER_NEXT_UNKNOWN;
+    return test_word_at<L2>(a, s_base + (unknown ? FILTER_L1_KNOWN_WORDS * 4u : 0u), unknown ? FILTER_L1_UNKNOWN_WORDS : FILTER_L1_KNOWN_WORDS,
+                            lo, hi, nb);
+}
+
 template <int W, bool L2>
 __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const FilterArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *s_bm = reinterpret_cast<uint32_t *>(smem_raw);
     constexpr int NB = 16 / W;
+    constexpr int U = FILTER_UNROLL;
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const uint32_t s_base = stage_bitmap(a, s_bm, tid);
+    // the span's last word of lane 31 is tested on its W bytes alone, in the bitmap's "next byte unknown" part
+    const uint32_t last_region = s_base + (lane == 31u ? FILTER_L1_KNOWN_WORDS * 4u : 0u);
+    const uint32_t last_words = lane == 31u ? FILTER_L1_UNKNOWN_WORDS : FILTER_L1_KNOWN_WORDS;
     auto test = [&](uint32_t lo, uint32_t hi, uint32_t nb, bool maybe_unknown) -> bool {
         return test_word<L2>(a, s_base, lo, hi, nb, maybe_unknown);
+    };
+    // planes of one complete span whose 16-byte chunks are in v (one per lane)
+    auto span_planes = [&](const uint4 &v) -> uint32_t {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        // byte after the lane's last word: the next lane's first byte; lane 31 does not know it
+        uint32_t after = __shfl_down_sync(0xffffffffu, w[0], 1) & 0xffu;
+        if (lane == 31u) after = FILTER_NEXT_UNKNOWN;
+        uint32_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            bool p;
+            if (j == NB - 1) p = (W == 8) ? test_word_at<L2>(a, last_region, last_words, w[2], w[3], after)
+                                          : test_word_at<L2>(a, last_region, last_words, w[3], 0u, after);
+            else p = (W == 8) ? test_word_at<L2>(a, s_base, FILTER_L1_KNOWN_WORDS, w[0], w[1], w[2] & 0xffu)
+                              : test_word_at<L2>(a, s_base, FILTER_L1_KNOWN_WORDS, w[j], 0u, w[j + 1] & 0xffu);
+            const uint32_t plane = __ballot_sync(0xffffffffu, p);
+            if (lane == (uint32_t)j) mine = plane;
+        }
+        return mine;
     };
 
     const uint32_t n_full_all = a.total / SPAN_BYTES;         // spans that lie completely inside the stream
     const uint32_t n_full = min(n_full_all, a.span_end);
     const uint32_t n_warps = gridDim.x * (SCAN_THREADS / 32);
     const uint32_t warp = blockIdx.x * (SCAN_THREADS / 32) + (tid >> 5);
-    uint32_t flagged = 0;
 
-    for (uint32_t g0 = a.span_begin + warp; g0 < n_full; g0 += n_warps * FILTER_UNROLL) {
-        uint4 v[FILTER_UNROLL];
+    // full rounds: U spans per warp, no bounds checks inside
+    uint32_t g0 = a.span_begin + warp;
+    const uint8_t *src = a.text + ((size_t)g0 * 32u + lane) * 16u;
+    const size_t span_stride = (size_t)n_warps * SPAN_BYTES;
+    for (; (uint64_t)g0 + (uint64_t)(U - 1) * n_warps < n_full; g0 += n_warps * U, src += span_stride * U) {
+        uint4 v[U];
 #pragma unroll
-        for (int u = 0; u < FILTER_UNROLL; ++u) {
-            const uint32_t g = g0 + u * n_warps;
-            v[u] = make_uint4(0, 0, 0, 0);
-            if (g < n_full) v[u] = ld_text16(a.text + ((size_t)g * 32u + lane) * 16u);
+        for (int u = 0; u < U; ++u) v[u] = ld_text16(src + span_stride * u);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t mine = span_planes(v[u]);
+            if (lane < (uint32_t)NB) a.mask[(size_t)(g0 + u * n_warps) * NB + lane] = mine;
         }
-#pragma unroll
-        for (int u = 0; u < FILTER_UNROLL; ++u) {
-            const uint32_t g = g0 + u * n_warps;
-            if (g >= n_full) break;                           // warp-uniform
-            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-            // byte after the lane's last word: the next lane's first byte; lane 31 does not know it
-            uint32_t after = __shfl_down_sync(0xffffffffu, w[0], 1) & 0xffu;
-            if (lane == 31u) after = FILTER_NEXT_UNKNOWN;
-            uint32_t mine = 0;
-#pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                const uint32_t nb = (j == NB - 1) ? after : (((W == 8) ? w[2] : w[j + 1]) & 0xffu);
-                const bool p = (W == 8) ? test(w[2 * j], w[2 * j + 1], nb, j == NB - 1) : test(w[j], 0u, nb, j == NB - 1);
-                const uint32_t plane = __ballot_sync(0xffffffffu, p);
-                if (lane == (uint32_t)j) mine = plane;
-            }
-            if (lane < (uint32_t)NB) {
-                a.mask[(size_t)g * NB + lane] = mine;
-                flagged += __popc(mine);
-            }
-        }
+    }
+    // the last, partial round
+    for (; g0 < n_full; g0 += n_warps) {
+        const uint4 v = ld_text16(a.text + ((size_t)g0 * 32u + lane) * 16u);
+        const uint32_t mine = span_planes(v);
+        if (lane < (uint32_t)NB) a.mask[(size_t)g0 * NB + lane] = mine;
     }
 
     // The last, partial span: complete 16-byte chunks are tested, the partial chunk at the very end is not
@@ -178,12 +203,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const Filter
             const uint32_t plane = __ballot_sync(0xffffffffu, p);
             if (lane == (uint32_t)j) mine = plane;
         }
-        if (lane < (uint32_t)NB) {
-            a.mask[(size_t)n_full * NB + lane] = mine;
-            flagged += __popc(mine);
-        }
+        if (lane < (uint32_t)NB) a.mask[(size_t)n_full * NB + lane] = mine;
     }
-    if (lane < (uint32_t)NB && flagged) atomicAdd(&a.counters[3], flagged);
 }
 
 // ------------------------------------------------------------ collect -----
@@ -219,7 +240,7 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
     __shared__ uint32_t s_n[N_WARPS];
     __shared__ uint32_t s_base;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t dense_tiles = 0;
+    uint32_t dense_tiles = 0, flagged = 0;
 
     auto load_planes = [&](uint32_t tile, uint32_t (&pl)[NB]) {
 #pragma unroll
@@ -247,6 +268,7 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
         uint32_t cnt = 0;
 #pragma unroll
         for (int j = 0; j < NB; ++j) cnt += __popc(planes[j]);
+        flagged += cnt;
         uint32_t incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -294,6 +316,10 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
         for (int j = 0; j < NB; ++j) planes[j] = next_planes[j];
     }
     if (lane == 0 && dense_tiles) atomicAdd(&a.s.counters[4], dense_tiles);
+    // flagged words of the stream (a statistic: the filter loop itself does not spend instructions on it)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) flagged += __shfl_xor_sync(0xffffffffu, flagged, d);
+    if (lane == 0 && flagged) atomicAdd(&a.s.counters[3], flagged);
 }
 
 // --------------------------------------------------------------- walk -----

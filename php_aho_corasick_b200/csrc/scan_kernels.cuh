@@ -568,6 +568,87 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_kernel(const ScanArgs
     }
 }
 
+// ------------------------------------------------------- small texts ------
+//
+// ahocorasick_match() on ONE short haystack (examples/benchmark.php:55-76 calls it 256 times on 8 KiB strings): what
+// such a call costs is not the walk but the round trips around it.  One CTA walks the text straight from the dense
+// table (no shared-memory window to stage: a few KiB of text touch a few rows), orders the events with a block
+// prefix sum and writes them — with their count and the end state — into mapped pinned host memory: the call is
+// one host-to-device copy, one launch, one wait.
+
+constexpr uint32_t SMALL_TEXT_BYTES = 32u << 10;      // texts up to this size take the one-CTA path
+constexpr int SMALL_THREADS = 1024;
+
+struct SmallArgs {
+    const uint8_t *text;          // device copy of the text, padded like ScanArgs::text
+    uint32_t total, readable, chunk, halo;
+    const void *table;
+    const uint8_t *cls_map;
+    uint32_t ncls, final_bound, root, range_lo, n_used, init_state;
+    uint2 *out;                   // mapped host memory: events {end offset, state}, ascending
+    uint32_t capacity;
+    uint32_t *hdr;                // mapped host memory: [0] events [1] end state
+};
+
+template <typename E, bool RANGE>
+__global__ void __launch_bounds__(SMALL_THREADS, 1) ac_small_kernel(const SmallArgs a)
+{
+    __shared__ uint8_t s_cls[256];
+    __shared__ uint32_t s_warp[SMALL_THREADS / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid < 256) s_cls[tid] = a.cls_map[tid];
+    __syncthreads();
+
+    Scanner<E, RANGE, false> sc;
+    sc.gtab = static_cast<const E *>(a.table); sc.text = a.text;
+    sc.ncls = a.ncls; sc.row_bytes = a.ncls * (uint32_t)sizeof(E);
+    sc.win_lo = a.final_bound; sc.win_rows = 0;           // every step reads the true entry (L1 / L2)
+    sc.s_tab = 0;
+    sc.s_cls = (uint32_t)__cvta_generic_to_shared(s_cls);
+    sc.lo = a.range_lo; sc.n_used = a.n_used;
+    sc.final_bound = a.final_bound; sc.readable = a.readable;
+    sc.out = a.out; sc.cap = a.capacity;
+    sc.found = false; sc.cnt = 0; sc.have_pend = false;
+    sc.e0p = sc.e0s = sc.e1p = sc.e1s = 0;
+
+    const uint32_t cs = min(tid * a.chunk, a.total), ce = min(cs + a.chunk, a.total);
+    uint32_t s_cs = a.root;
+    if (cs < ce) {
+        const uint32_t ws = (cs > a.halo) ? ((cs - a.halo) & ~15u) : 0u;
+        s_cs = sc.template walk<false, 0>(ws == 0u ? a.init_state : a.root, ws, cs);
+        const uint32_t s_end = sc.template walk<true, 0>(s_cs, cs, ce);
+        if (ce == a.total) a.hdr[1] = s_end;
+    }
+    // block prefix of the per-thread event counts
+    uint32_t incl = sc.cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < SMALL_THREADS / 32; ++w) {
+        const uint32_t v = (uint32_t)w < blockDim.x / 32u ? s_warp[w] : 0u;
+        if ((uint32_t)w < warp) base += v;
+        all += v;
+    }
+    if (tid == 0) a.hdr[0] = all;
+    const uint32_t off = base + incl - sc.cnt;
+    if (sc.cnt && off < a.capacity) {
+        if (sc.cnt <= 2) {
+            a.out[off] = make_uint2(sc.e0p, sc.e0s);
+            if (sc.cnt == 2 && off + 1 < a.capacity) a.out[off + 1] = make_uint2(sc.e1p, sc.e1s);
+        } else {
+            sc.obase = off;
+            sc.cnt = 0;
+            sc.template walk<true, 1>(s_cs, cs, ce);
+        }
+    }
+}
+
 // ------------------------------------------------------- hit expansion ----
 //
 // The reference's callback turns every event into one record per reported pattern

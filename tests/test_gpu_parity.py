@@ -178,3 +178,41 @@ def test_not_finalized_returns_minus_one_and_add_statuses():
         r = d.search(b"zabcz")
         assert r["rc"] == 0 and r["pos"].tolist() == [4]
         d.release()
+
+
+def test_one_cta_path_for_short_texts_equals_oracle():
+    """ac_small_kernel (one haystack of up to 32 KiB: one copy, one launch, one wait): every size class around its
+    slice boundaries, dense events (more than two per slice: the in-place second walk), binary bytes, keep=1
+    continuations whose state comes from a longer chunk, and the first size that takes the general path again."""
+    rng = np.random.default_rng(99)
+    pats = [b"a", b"aa", b"aaaa", b"ab", b"abcab", b"\x00\xff", b"bca" * 5, b"cccccccccccccccccccc"] + \
+           [bytes(rng.integers(97, 100, size=int(rng.integers(2, 12))).astype(np.uint8)) for _ in range(60)]
+    a = build([pats])
+    for n in (1, 2, 15, 16, 17, 31, 32, 33, 511, 512, 513, 4095, 4096, 4097, 8192, 32767, 32768, 32769):
+        hay = rng.integers(97, 100, size=n, dtype=np.uint8)
+        if n > 64:
+            hay[n // 3:n // 3 + 40] = ord("a")              # a dense burst
+            hay[n - 2:] = np.frombuffer(b"\x00\xff", dtype=np.uint8)
+        exp = oracle_hits([pats], [hay])
+        ev = a.search_events(hay)
+        assert (a.stats().kernel_launches == 1 and a.stats().kernel_ms == 0) == (n <= 32768) or n > 32768
+        assert_same(a, ev, 1, exp)
+        ev1 = a.search_events(hay, first_only=True)
+        assert_same(a, ev1, 1, oracle_hits([pats], [hay], first_only=True))
+    # keep=1: chunks of mixed sizes, states carried between the one-CTA path and the general one
+    hay = rng.integers(97, 100, size=200_000, dtype=np.uint8)
+    rc, whole = a.search_callback(hay.tobytes())
+    seq, at = [], 0
+    for size in (7, 1000, 40_000, 33, 32768, 100_000, 8192, 200_000):
+        piece = hay[at:at + size]
+        if piece.size == 0:
+            break
+        rc, g = a.search_callback(piece.tobytes(), keep=(at > 0))
+        assert rc == 0
+        seq += g
+        at += piece.size
+    assert at == hay.size and seq == whole
+    d = Driver("oracle"); d.add_php_order(pats); d.finalize()
+    r = d.search(hay)
+    assert [p for p, _ in whole] == sorted(set(int(x) for x in r["pos"]))
+    a.release()
