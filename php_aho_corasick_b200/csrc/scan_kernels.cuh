@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) ac_small_kernel(const SmallA
     __shared__ uint8_t s_cls[256];
     __shared__ uint32_t s_warp[SMALL_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid < 256) s_cls[tid] = a.cls_map[tid];
+    for (uint32_t i = tid; i < 256u; i += blockDim.x) s_cls[i] = a.cls_map[i];     // (the CTA may be a single warp)
     __syncthreads();
 
     Scanner<E, RANGE, false> sc;
