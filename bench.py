@@ -291,7 +291,7 @@ def main():
     import torch.distributed as dist
     from php_aho_corasick_b200 import workloads as W
     from php_aho_corasick_b200.native import Automaton, EVENT_DTYPE
-    from php_aho_corasick_b200.dist import ShardedMatcher, globalize
+    from php_aho_corasick_b200.dist import MailboxGatherer, ShardedMatcher, globalize
 
     world = env_int("WORLD_SIZE", 1)
     rank = env_int("RANK", 0)
@@ -327,12 +327,30 @@ def main():
     sm = ShardedMatcher(aut)
     peak, peak_src = hbm_peak()
 
+    mg = None
+    if world > 1:
+        # One synchronous step through the NCCL all_gather path sizes the mailbox gather (dist.MailboxGatherer): from then
+        # on every rank copies exactly its own rows into rank 0's IPC-mapped buffer with the copy engines, behind its scan.
+        n0, _ = sm.scan_and_gather(resident, offsets, 0, stream=stream, uniform_len=HAY_LEN)
+        most = torch.tensor([n0], dtype=torch.int64, device=dev)
+        dist.all_reduce(most, op=dist.ReduceOp.MAX)
+        mg = MailboxGatherer(aut, cap_rows=2 * int(most.item()) + 4096)
+
     def step_resident():
         if world > 1:
-            n, got = sm.scan_and_gather(resident, offsets, 0, stream=stream, uniform_len=HAY_LEN)
-            return n, got
+            n = mg.scan_and_send(resident, n_hays, HAY_LEN, stream=stream)
+            if mg.step >= 2:
+                mg.result(mg.step - 2)           # rank 0: the rows of the step before — they landed while this one ran
+            return n, None
         # one GPU: the C-ABI call itself; the sorted events stay in the library's device buffer (its contract)
         return aut.search_device_uniform(resident.data_ptr(), n_hays, HAY_LEN, stream=stream)[1], None
+
+    def drain():
+        """the rows of the last step are on rank 0 too before the clock stops"""
+        if mg is not None:
+            torch.cuda.current_stream().wait_stream(mg.side)
+            return mg.result(mg.step - 1)
+        return None
 
     def sync():
         if world > 1:
@@ -358,6 +376,7 @@ def main():
             acc[k] += getattr(st, k)
         launches += st.kernel_launches
         filtered_steps += st.filtered
+    drain()
     e1.record()
     sync()
     wall1 = time.time()
@@ -369,7 +388,8 @@ def main():
     kind = cpu_kind()
     threads_total = os.cpu_count() or 1
     cpu_full = cpu_leg(needles, host_stream, offsets, max(1, threads_total // world), 1, kind, digest=True)
-    n_own, got = step_resident()
+    n_own, _ = step_resident()
+    got = drain()
     if world > 1:
         exp = torch.from_numpy(np.stack([cpu_full["counts"], cpu_full["hashes"]]).view(np.int64)).to(dev)
         all_exp = [torch.empty_like(exp) for _ in range(world)]
@@ -386,7 +406,8 @@ def main():
             ordered = bool(np.all(np.diff(ev["text_idx"].astype(np.int64)) >= 0))
             parity = {"checked": True, "events": int(ev.size), "haystacks": int(world * n_hays), "hash_ok": bad == 0 and ordered,
                       "mismatching_haystacks": bad, "rows_in_global_order": ordered,
-                      "what": f"rows gathered on rank 0 over NCCL from {world} ranks vs {cpu_full['kind']} ac_trie_search, every haystack"}
+                      "what": f"rows gathered on rank 0 (copy engines over NVLink into its IPC-mapped buffer, dist.MailboxGatherer) "
+                              f"from {world} ranks vs {cpu_full['kind']} ac_trie_search, every haystack"}
     else:
         ev = packed_to_events(aut, torch, (None, n_own), n_hays, hay_len=HAY_LEN)
         counts, hashes = aut.event_digest(ev, n_hays)
@@ -544,6 +565,7 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        mg.close()
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0 and parity and not parity["hash_ok"]:

@@ -352,6 +352,22 @@ typedef struct acb200_slab
 int acb200_plan_slabs(const uint64_t *offsets, size_t n, uint32_t halo_max, int n_devices, uint64_t slab_bytes,
                       ACB200_SLAB_t *out, size_t cap, size_t *n_slabs);
 
+/* Peer-memory plumbing for callers that run ONE PROCESS PER GPU (torchrun) and collect every rank's events on one
+ * of them: a device buffer of the collecting rank is mapped into the other processes through CUDA IPC
+ * (export -> 64-byte handle -> open), each rank copies its rows into its slot of it with the copy engines
+ * (acb200_copy_async on a side stream: no collective kernel competes with the scan for SMs, the transfer of step k
+ * overlaps the scan of step k+1) and then writes the step number into its mailbox word, behind the rows on the same
+ * stream; acb200_mailbox_wait_async enqueues a one-warp kernel that returns once all n mailboxes (stride_words
+ * apart) have reached `seq` (step numbers only grow; the words may live in a peer's memory).  php_aho_corasick_b200/dist.py (MailboxGatherer) is the user.  0 / -1, NULL on failure.   */
+void *acb200_device_alloc(int device, size_t bytes);            /* cudaMalloc + zero-fill on `device` */
+int acb200_device_free(int device, void *p);
+int acb200_ipc_export(const void *dptr, unsigned char handle[64]);
+void *acb200_ipc_open(int device, const unsigned char handle[64]);
+int acb200_ipc_close(int device, void *p);
+int acb200_copy_async(void *dst, const void *src, size_t bytes, void *stream);
+int acb200_mailbox_wait_async(int device, const void *mailboxes, uint32_t n, uint32_t stride_words, uint32_t seq,
+                              void *stream);
+
 /* Pinned host memory for haystacks (optional; pageable memory works too).   */
 void *acb200_host_alloc(size_t bytes);
 void acb200_host_free(void *p);

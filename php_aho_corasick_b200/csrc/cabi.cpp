@@ -376,6 +376,17 @@ int acb200_device_count(void)
     return n;
 }
 
+void *acb200_device_alloc(int device, size_t bytes) { return device_alloc(device, bytes); }
+int acb200_device_free(int device, void *p) { return device_free(device, p) ? 0 : -1; }
+int acb200_ipc_export(const void *dptr, unsigned char handle[64]) { return ipc_export(dptr, handle) ? 0 : -1; }
+void *acb200_ipc_open(int device, const unsigned char handle[64]) { return ipc_open(device, handle); }
+int acb200_ipc_close(int device, void *p) { return ipc_close(device, p) ? 0 : -1; }
+int acb200_copy_async(void *dst, const void *src, size_t bytes, void *stream) { return copy_async(dst, src, bytes, stream) ? 0 : -1; }
+int acb200_mailbox_wait_async(int device, const void *mailboxes, uint32_t n, uint32_t stride_words, uint32_t seq, void *stream)
+{
+    return mailbox_wait_async(device, mailboxes, n, stride_words, seq, stream) ? 0 : -1;
+}
+
 void *acb200_host_alloc(size_t bytes)
 {
     void *p = nullptr;

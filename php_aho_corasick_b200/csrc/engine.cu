@@ -45,6 +45,77 @@ void set_preferred_device(int d) { g_device = d; }
 static inline cudaStream_t S(void *p) { return static_cast<cudaStream_t>(p); }
 static inline cudaEvent_t EV(void *p) { return static_cast<cudaEvent_t>(p); }
 
+// ------------------------------------------------------------ peer memory --
+
+// Waits (on the device, one warp) until the first word of each of n mailboxes has reached `seq` (step numbers only
+// grow): every sender writes its mailbox after its events, through the same copy-engine stream, so a mailbox at
+// `seq` means its rows have landed.  The same kernel makes a sender wait for the collector's acknowledgement word
+// (which may live in a peer's memory) before it overwrites a slot.
+__global__ void ac_mailbox_wait_kernel(const volatile uint32_t *mailboxes, uint32_t n, uint32_t stride_words, uint32_t seq)
+{
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        while (mailboxes[(size_t)i * stride_words] < seq) __nanosleep(200);
+}
+
+void *device_alloc(int device, size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess ||
+        cudaMemset(p, 0, bytes ? bytes : 1) != cudaSuccess) {
+        set_error(std::string("device_alloc: ") + cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+
+bool device_free(int device, void *p)
+{
+    CU_OK(cudaSetDevice(device));
+    CU_OK(cudaFree(p));
+    return true;
+}
+
+bool ipc_export(const void *dptr, unsigned char handle[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    cudaIpcMemHandle_t h;
+    CU_OK(cudaIpcGetMemHandle(&h, const_cast<void *>(dptr)));
+    memcpy(handle, &h, 64);
+    return true;
+}
+
+void *ipc_open(int device, const unsigned char handle[64])
+{
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void *p = nullptr;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { set_error(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+
+bool ipc_close(int device, void *p)
+{
+    CU_OK(cudaSetDevice(device));
+    CU_OK(cudaIpcCloseMemHandle(p));
+    return true;
+}
+
+bool copy_async(void *dst, const void *src, size_t bytes, void *stream)
+{
+    if (bytes) CU_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream ? S(stream) : cudaStreamLegacy));
+    return true;
+}
+
+bool mailbox_wait_async(int device, const void *mailboxes, uint32_t n, uint32_t stride_words, uint32_t seq, void *stream)
+{
+    CU_OK(cudaSetDevice(device));
+    ac_mailbox_wait_kernel<<<1, 32, 0, stream ? S(stream) : cudaStreamLegacy>>>((const volatile uint32_t *)mailboxes, n, stride_words, seq);
+    CU_OK(cudaGetLastError());
+    return true;
+}
+
 // --------------------------------------------------------------- lifetime --
 
 Engine::Engine() {}

@@ -24,6 +24,16 @@ const char *get_error();
 int preferred_device();
 void set_preferred_device(int d);
 
+// Peer-memory plumbing of the multi-GPU event gather (one process per GPU): device buffers that other processes map
+// through CUDA IPC, copies into them by the copy engines, and the wait for every sender's "step done" mailbox.
+void *device_alloc(int device, size_t bytes);
+bool device_free(int device, void *p);
+bool ipc_export(const void *dptr, unsigned char handle[64]);
+void *ipc_open(int device, const unsigned char handle[64]);
+bool ipc_close(int device, void *p);
+bool copy_async(void *dst, const void *src, size_t bytes, void *stream);
+bool mailbox_wait_async(int device, const void *mailboxes, uint32_t n, uint32_t stride_words, uint32_t seq, void *stream);
+
 class Engine {
 public:
     Engine();

@@ -83,6 +83,8 @@ EXPORTS = [
     "acb200_set_filter", "acb200_search_device_uniform", "acb200_search_hits", "acb200_pattern", "acb200_save", "acb200_load", "acb200_filter_probe",
     "acb200_set_direct", "acb200_direct_probe", "acb200_search_device_uniform_async", "acb200_async_finish",
     "acb200_set_devices", "acb200_set_slab_bytes", "acb200_plan_slabs", "acb200_event_digest",
+    "acb200_device_alloc", "acb200_device_free", "acb200_ipc_export", "acb200_ipc_open", "acb200_ipc_close",
+    "acb200_copy_async", "acb200_mailbox_wait_async",
 ]
 
 
@@ -156,6 +158,15 @@ def lib() -> C.CDLL:
     L.acb200_plan_slabs.restype = C.c_int
     L.acb200_event_digest.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
     L.acb200_event_digest.restype = C.c_int
+    L.acb200_device_alloc.argtypes = [C.c_int, C.c_size_t]
+    L.acb200_device_alloc.restype = C.c_void_p
+    L.acb200_device_free.argtypes = [C.c_int, C.c_void_p]
+    L.acb200_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
+    L.acb200_ipc_open.argtypes = [C.c_int, C.c_char_p]
+    L.acb200_ipc_open.restype = C.c_void_p
+    L.acb200_ipc_close.argtypes = [C.c_int, C.c_void_p]
+    L.acb200_copy_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.acb200_mailbox_wait_async.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     L.acb200_copy_events.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.acb200_copy_events.restype = C.c_long
     _lib = L

@@ -170,13 +170,30 @@ def _nccl_worker(rank, world, port, q):
     shard = torch.from_numpy(flat[rank * n_hays * hay_len:(rank + 1) * n_hays * hay_len]).cuda()
     sm = ShardedMatcher(a)
     res = []
+    goff = W.offsets_uniform(world * n_hays, hay_len)
     for step in range(3):                                    # step 0 synchronous, steps 1.. the chained form
         n, got = sm.scan_and_gather(shard, off, 0, stream=torch.cuda.current_stream().cuda_stream, uniform_len=hay_len)
         if rank == 0:
-            goff = W.offsets_uniform(world * n_hays, hay_len)
             ev = globalize(got, [(r * n_hays, (r + 1) * n_hays) for r in range(world)], goff)
             counts, hashes = a.event_digest(ev, world * n_hays)
             res.append((counts.tolist(), hashes.tolist(), bool(np.all(np.diff(ev["text_idx"].astype(np.int64)) >= 0))))
+    # the same steps through the mailbox gather (copy engines into rank 0's IPC-mapped buffer, pipelined by one step):
+    # several steps in a row, so that slots are reused and the acknowledgement flow control is exercised
+    from php_aho_corasick_b200.dist import MailboxGatherer
+    mg = MailboxGatherer(a, cap_rows=2 * n + 1024)
+    for step in range(5):
+        mg.scan_and_send(shard, n_hays, hay_len, stream=torch.cuda.current_stream().cuda_stream)
+        if step >= 1 and rank == 0:
+            got = [g.clone() for g in mg.result(step - 1)]
+            ev = globalize(got, [(r * n_hays, (r + 1) * n_hays) for r in range(world)], goff)
+            counts, hashes = a.event_digest(ev, world * n_hays)
+            res.append((counts.tolist(), hashes.tolist(), bool(np.all(np.diff(ev["text_idx"].astype(np.int64)) >= 0))))
+    torch.cuda.current_stream().wait_stream(mg.side)
+    if rank == 0:
+        ev = globalize(mg.result(4), [(r * n_hays, (r + 1) * n_hays) for r in range(world)], goff)
+        counts, hashes = a.event_digest(ev, world * n_hays)
+        res.append((counts.tolist(), hashes.tolist(), True))
+    mg.close()
     if rank == 0:
         q.put(res)
     dist.barrier()
