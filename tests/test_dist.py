@@ -223,3 +223,78 @@ def test_nccl_two_rank_gathered_rows_equal_the_cpu_reference_per_haystack():
     _, _, counts, hashes = pydriver.bench_digest(kind, needles, flat, off, 4)
     for c, h, ordered in res:
         assert ordered and c == counts.tolist() and h == hashes.tolist()
+
+
+def _mailbox_worker(rank, world, port, q, same_gpu):
+    """MailboxGatherer between separate PROCESSES: rank 0's buffer mapped through CUDA IPC, rows copied in by the copy
+    engines, mailboxes, acknowledgement flow control.  With `same_gpu` both ranks sit on GPU 0 (IPC works between
+    processes on one device; the process group is gloo because NCCL refuses two ranks on one GPU) — what a one-GPU
+    box can run; else every rank takes its own GPU."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dev = 0 if same_gpu else rank
+    torch.cuda.set_device(dev)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from php_aho_corasick_b200 import workloads as W
+    from php_aho_corasick_b200.dist import MailboxGatherer
+    from php_aho_corasick_b200.native import Automaton
+    needles, _ = W.cfg2_needles()
+    hay_len, blocks = 8192, 8
+    flat = W.cfg2_stream(0, 0, blocks * world)
+    n_hays = blocks * 256
+    goff = W.offsets_uniform(world * n_hays, hay_len)
+    ranges = [(r * n_hays, (r + 1) * n_hays) for r in range(world)]
+    a = Automaton(device=dev)
+    a.add_php_order(needles)
+    a.finalize()
+    shard = torch.from_numpy(flat[rank * n_hays * hay_len:(rank + 1) * n_hays * hay_len]).cuda()
+    mg = MailboxGatherer(a, cap_rows=3 * n_hays * 8)
+    res = []
+    steps = 6
+    for step in range(steps):
+        if rank == 1 and step == 3:
+            import time
+            time.sleep(0.3)                                  # a slow sender: rank 0 must wait for its mailbox
+        if rank == 0 and step == 4:
+            import time
+            time.sleep(0.3)                                  # a slow collector: the sender must wait for the acknowledgement
+        mg.scan_and_send(shard, n_hays, hay_len, stream=torch.cuda.current_stream().cuda_stream)
+        if step >= 1 and rank == 0:
+            got = [g.clone() for g in mg.result(step - 1)]
+            ev = globalize(got, ranges, goff)
+            counts, hashes = a.event_digest(ev, world * n_hays)
+            res.append((counts.tolist(), hashes.tolist()))
+    torch.cuda.current_stream().wait_stream(mg.side)
+    if rank == 0:
+        ev = globalize(mg.result(steps - 1), ranges, goff)
+        counts, hashes = a.event_digest(ev, world * n_hays)
+        res.append((counts.tolist(), hashes.tolist()))
+        q.put(res)
+    mg.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_mailbox_gather_between_processes_equals_the_cpu_reference_per_haystack():
+    from oracle import pydriver
+    from php_aho_corasick_b200 import workloads as W
+    same_gpu = torch.cuda.device_count() < 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_mailbox_worker, args=(r, 2, port, q, same_gpu)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    needles, _ = W.cfg2_needles()
+    flat = W.cfg2_stream(0, 0, 16)
+    off = W.offsets_uniform(16 * 256, 8192)
+    kind = "reference" if pydriver.available("reference") else "oracle"
+    _, _, counts, hashes = pydriver.bench_digest(kind, needles, flat, off, 4)
+    assert len(res) == 6
+    for c, h in res:
+        assert c == counts.tolist() and h == hashes.tolist()
