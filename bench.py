@@ -348,7 +348,7 @@ def main():
     def drain():
         """the rows of the last step are on rank 0 too before the clock stops"""
         if mg is not None:
-            torch.cuda.current_stream().wait_stream(mg.side)
+            mg.drain(stream)
             return mg.result(mg.step - 1)
         return None
 

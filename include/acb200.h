@@ -368,6 +368,23 @@ int acb200_copy_async(void *dst, const void *src, size_t bytes, void *stream);
 int acb200_mailbox_wait_async(int device, const void *mailboxes, uint32_t n, uint32_t stride_words, uint32_t seq,
                               void *stream);
 
+/* The mailbox gather built from those pieces.  Every rank creates one object over the collector's two buffers as they
+ * are mapped in ITS process (rows: 2 x world x cap_rows x 8 bytes; mailboxes: (2 x world x 4 + 2) words, zeroed).
+ * acb200_mailbox_step() is one step of one rank: scans n equal-length haystacks resident at d_bytes (the kernels of
+ * acb200_search_device_uniform_async, on `stream`), waits for this rank's own event count, then puts its rows and
+ * {step, count} on their way to the collector on a copy stream and returns the count (-1: error, e.g. more events
+ * than cap_rows).  The transfer overlaps whatever the caller enqueues next; a sender never overwrites a slot the
+ * collector still holds (per-parity acknowledgement).  On the collector acb200_mailbox_result(step) waits until
+ * every rank's rows of that step have landed and returns their counts: rank r's rows are rows[step & 1][r][0..count)
+ * and stay valid until step + 2 is sent.  acb200_mailbox_drain() makes `stream` wait for this rank's pending copies. */
+typedef struct acb200_mailbox ACB200_MAILBOX_t;
+ACB200_MAILBOX_t *acb200_mailbox_create(AC_TRIE_t *thiz, int rank, int world, int collector, size_t cap_rows,
+                                        void *rows, void *mailboxes);
+long acb200_mailbox_step(ACB200_MAILBOX_t *m, const void *d_bytes, size_t n, size_t hay_len, void *stream);
+int acb200_mailbox_result(ACB200_MAILBOX_t *m, uint32_t step, uint32_t *counts);
+int acb200_mailbox_drain(ACB200_MAILBOX_t *m, void *stream);
+void acb200_mailbox_free(ACB200_MAILBOX_t *m);
+
 /* Pinned host memory for haystacks (optional; pageable memory works too).   */
 void *acb200_host_alloc(size_t bytes);
 void acb200_host_free(void *p);

@@ -142,7 +142,7 @@ struct HaySource {
 };
 
 struct SlabResult {
-    std::vector<PackedEvent> ev;
+    std::vector<ACB200_EVENT_t> ev;      // resolved by the worker: haystack index, offset inside it, state
     ACB200_STATS_t st{};
     uint32_t end_state = 0;
     bool ready = false, ok = true;
@@ -227,7 +227,21 @@ void shard_worker(Engine *eng, const HaySource &src, const std::vector<SlabPlan>
         const uint32_t init = (mine[k] == 0) ? init_state : ROOT_STATE;
         if (!eng->scan_slab((int)(k & 1), rel.data(), p.h_end - p.h_first, fo, init)) { fail(k); return; }
         SlabResult r;
-        r.ev.assign(eng->host_events(), eng->host_events() + eng->n_events());
+        {
+            // resolve the slab's events here, on the worker (every GPU's worker does its own in parallel): the calling
+            // thread, which owns the callbacks, is the serial part of a multi-GPU call and should do nothing else
+            const PackedEvent *pe = eng->host_events();
+            const size_t ne = eng->n_events();
+            r.ev.reserve(ne);
+            size_t h = p.h_first;
+            const uint64_t base = p.b0 - p.halo;
+            for (size_t i = 0; i < ne; ++i) {
+                if (pe[i].end <= p.halo) continue;               // ends inside the halo: the slab before reported it
+                const uint64_t g = base + pe[i].end;
+                while (g > src.off[h + 1]) ++h;
+                r.ev.push_back(ACB200_EVENT_t{g - src.off[h], pe[i].state, (uint32_t)h});
+            }
+        }
         r.st = eng->stats;
         r.st.h2d_ms = eng->slab_h2d_ms((int)(k & 1));
         r.end_state = eng->end_state();
@@ -250,6 +264,7 @@ int sharded_search(ac_trie *t, const HaySource &src, bool first_only, uint32_t i
                    uint32_t *end_state, Sink &&sink)
 {
     const uint64_t total = src.off[src.n];
+    if (src.n > 0xffffffffull) { set_error("more than 2^32 haystacks in one call"); return -1; }
     std::vector<Engine *> engines{&t->engine};
     for (auto &r : t->replicas) engines.push_back(r.get());
     const int n_dev = (int)std::min<uint64_t>(engines.size(), std::max<uint64_t>(1, total / min_bytes_per_device(t)));
@@ -272,7 +287,7 @@ int sharded_search(ac_trie *t, const HaySource &src, bool first_only, uint32_t i
                              init_state, helpers, std::ref(run));
 
     int rc = 0;
-    size_t h = 0, stopped = (size_t)-1;
+    size_t stopped = (size_t)-1;
     std::vector<ACB200_STATS_t> per_dev(n_dev);
     for (size_t i = 0; i < plans.size() && rc == 0; ++i) {
         {
@@ -284,18 +299,14 @@ int sharded_search(ac_trie *t, const HaySource &src, bool first_only, uint32_t i
         const SlabPlan &p = plans[i];
         add_stats(per_dev[p.device_slot], r.st);
         if (end_state) *end_state = r.end_state;
-        h = std::max(h, p.h_first);
-        const uint64_t base = p.b0 - p.halo;
-        for (const PackedEvent &e : r.ev) {
-            if (e.end <= p.halo) continue;                   // ends inside the halo: the slab before reported it
-            const uint64_t g = base + e.end;
-            while (g > src.off[h + 1]) ++h;
+        for (const ACB200_EVENT_t &e : r.ev) {
+            const size_t h = e.text_idx;
             if (h == stopped) continue;
-            const int s = sink(h, (uint64_t)(g - src.off[h]), e.state);
+            const int s = sink(h, e.end, e.state);
             if (s && stop_all) { rc = 1; break; }
             if (s || first_only) stopped = h;
         }
-        std::vector<PackedEvent>().swap(r.ev);
+        std::vector<ACB200_EVENT_t>().swap(r.ev);
     }
     if (rc != 0) run.abort.store(true);
     for (auto &w : workers) w.join();
@@ -360,6 +371,86 @@ static int search_source(ac_trie *t, HaySource &src, int first_only, Sink &&sink
     }
     src.pinned = src.flat && is_pinned(src.flat);
     return sharded_search(t, src, first_only != 0, ROOT_STATE, false, nullptr, sink) < 0 ? -1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Mailbox gather (one process per GPU): see include/acb200.h.  One call per step — enqueue the scan with this
+// rank's send buffer as its output, wait for this rank's own count (what the one-GPU call waits for too), then put
+// the rows and the mailbox word on their way on a copy stream.  Nothing of it runs in the caller's language: the
+// first version drove the same CUDA calls from Python and lost 0.1 ms per step to interpreter time between them.
+// ------------------------------------------------------------------------------------------------------------
+struct acb200_mailbox {
+    ac_trie *t = nullptr;
+    int rank = 0, world = 1, device = 0;
+    bool collector = false;
+    size_t cap = 0;
+    char *rows = nullptr;              // the collector's row buffer as mapped in THIS process: [2][world][cap] x 8 bytes
+    uint32_t *mbox = nullptr;          // the collector's mailboxes: [2][world][4] words, then one acknowledgement word per parity
+    uint2 *send[2] = {nullptr, nullptr};   // this rank's rows of the step in flight: row 0 = {count, dense tiles}, rows 1.. events
+    uint32_t *pinned = nullptr;        // [4][4] mailbox / acknowledgement sources, [2] own {count, dense}, then [2][world][4] arrived mailboxes
+    cudaStream_t side = nullptr;
+    cudaEvent_t copy_done[2] = {nullptr, nullptr}, arrived[2] = {nullptr, nullptr};
+    uint32_t step = 0;
+    static constexpr uint32_t MBOX_WORDS = 4;
+
+    uint32_t *own_count() { return pinned + 16; }
+    uint32_t *arrived_mbox(int p) { return pinned + 24 + (size_t)p * world * MBOX_WORDS; }
+};
+
+#define MB_OK(call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) { set_error(std::string(#call) + ": " + cudaGetErrorString(e_)); return -1; } \
+    } while (0)
+
+static long mailbox_step(acb200_mailbox *m, const void *d_bytes, size_t n, size_t hay_len, void *stream)
+{
+    ac_trie *t = m->t;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : cudaStreamLegacy;
+    MB_OK(cudaSetDevice(m->device));
+    const uint32_t k = m->step++;
+    const int p = (int)(k & 1u);
+    uint2 *send = m->send[p];
+    if (k >= 2) MB_OK(cudaStreamWaitEvent(st, m->copy_done[p], 0));           // the copy of step k-2 has left this buffer
+    uint32_t count = 0, dense = 0;
+    if (t->engine.scan_device_uniform_async(d_bytes, n, hay_len, send, m->cap, (void *)st)) {
+        MB_OK(cudaMemcpyAsync(m->own_count(), send, 8, cudaMemcpyDeviceToHost, st));
+        MB_OK(cudaStreamSynchronize(st));                                      // this rank's own wait, as on one GPU
+        count = m->own_count()[0]; dense = m->own_count()[1];
+        t->engine.async_finish(count, dense);
+    } else {                                                                   // this batch needs the synchronous call (full walk)
+        if (!t->engine.scan_device_uniform(d_bytes, n, hay_len, false, (void *)st)) return -1;
+        count = (uint32_t)t->engine.n_events();
+        if (count <= m->cap && count && !t->engine.copy_events_to(send + 1, count, (void *)st)) return -1;
+        MB_OK(cudaStreamSynchronize(st));
+    }
+    t->stats = t->engine.stats; t->stats.devices = 1;
+    if (count > m->cap) {
+        set_error("mailbox gather: " + std::to_string(count) + " events in one step, sized for " + std::to_string(m->cap) + " rows per rank");
+        return -1;
+    }
+    const size_t slot = (size_t)p * m->world + m->rank;
+    uint32_t *ack = m->mbox + 2u * m->world * acb200_mailbox::MBOX_WORDS + p;
+    uint32_t *src = m->pinned + (k & 3u) * 4u;
+    if (k >= 2) {
+        // flow control: slot p still holds step k-2 until the collector has let go of it; it acknowledges here,
+        // every sender waits for the word (in the collector's memory) on its copy stream
+        if (m->collector) {
+            src[3] = k - 1u;
+            MB_OK(cudaMemcpyAsync(ack, src + 3, 4, cudaMemcpyDefault, m->side));
+        } else if (!mailbox_wait_async(m->device, ack, 1, 1, k - 1u, m->side)) return -1;
+    }
+    if (count) MB_OK(cudaMemcpyAsync(m->rows + slot * m->cap * 8, send + 1, (size_t)count * 8, cudaMemcpyDefault, m->side));
+    src[0] = k + 1u; src[1] = count; src[2] = dense;
+    MB_OK(cudaMemcpyAsync(m->mbox + slot * acb200_mailbox::MBOX_WORDS, src, 12, cudaMemcpyDefault, m->side));
+    MB_OK(cudaEventRecord(m->copy_done[p], m->side));
+    if (m->collector) {
+        uint32_t *boxes = m->mbox + (size_t)p * m->world * acb200_mailbox::MBOX_WORDS;
+        if (!mailbox_wait_async(m->device, boxes, (uint32_t)m->world, acb200_mailbox::MBOX_WORDS, k + 1u, m->side)) return -1;
+        MB_OK(cudaMemcpyAsync(m->arrived_mbox(p), boxes, (size_t)m->world * acb200_mailbox::MBOX_WORDS * 4, cudaMemcpyDefault, m->side));
+        MB_OK(cudaEventRecord(m->arrived[p], m->side));
+    }
+    return (long)count;
 }
 
 extern "C" {
@@ -645,17 +736,15 @@ static inline uint64_t tally_fold(uint64_t h, uint64_t v)
 
 int acb200_tally_cb(size_t text_idx, AC_MATCH_t *m, void *tally)
 {
+    // order-sensitive, one multiply on the dependent chain per event (a consumer that costs more than the replay
+    // loop around it would be what an end-to-end number measures)
     ACB200_TALLY_t *t = static_cast<ACB200_TALLY_t *>(tally);
     t->events++;
     t->hits += m->size;
-    uint64_t h = tally_fold(t->hash, (uint64_t)text_idx);
-    h = tally_fold(h, (uint64_t)m->position);
-    h = tally_fold(h, (uint64_t)m->size);
-    if (m->size) {
-        h = tally_fold(h, (uint64_t)(uintptr_t)m->patterns[0].aux);
-        h = tally_fold(h, (uint64_t)(uintptr_t)m->patterns[m->size - 1].aux);
-    }
-    t->hash = h;
+    uint64_t v = ((uint64_t)m->position * 0x9e3779b97f4a7c15ULL) ^ ((uint64_t)text_idx << 20) ^ ((uint64_t)m->size << 52);
+    if (m->size)
+        v ^= (uint64_t)(uintptr_t)m->patterns[0].aux * 0xc2b2ae3d27d4eb4fULL + (uint64_t)(uintptr_t)m->patterns[m->size - 1].aux;
+    t->hash = (((t->hash << 7) | (t->hash >> 57)) ^ v) * 0xff51afd7ed558ccdULL;
     return 0;
 }
 
@@ -780,6 +869,64 @@ int acb200_direct_probe(const AC_TRIE_t *t, const char *bytes, size_t length, si
     }
     if (v == GRAM_EVENT) { if (end) *end = e; if (state) *state = s; }
     return v;
+}
+
+ACB200_MAILBOX_t *acb200_mailbox_create(AC_TRIE_t *t, int rank, int world, int collector, size_t cap_rows, void *rows, void *mailboxes)
+{
+    if (t->open || !t->device_ok) { set_error("automaton is not finalized"); return nullptr; }
+    acb200_mailbox *m = new (std::nothrow) acb200_mailbox();
+    if (!m) { set_error("out of memory"); return nullptr; }
+    m->t = t; m->rank = rank; m->world = world; m->collector = collector != 0; m->cap = cap_rows;
+    m->device = t->engine.device();
+    m->rows = static_cast<char *>(rows); m->mbox = static_cast<uint32_t *>(mailboxes);
+    bool ok = cudaSetDevice(m->device) == cudaSuccess;
+    for (int p = 0; ok && p < 2; ++p) {
+        ok = cudaMalloc((void **)&m->send[p], (cap_rows + 1) * 8) == cudaSuccess && cudaMemset(m->send[p], 0, (cap_rows + 1) * 8) == cudaSuccess &&
+             cudaEventCreateWithFlags(&m->copy_done[p], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&m->arrived[p], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok = ok && cudaMallocHost((void **)&m->pinned, (24 + 2 * (size_t)world * acb200_mailbox::MBOX_WORDS) * 4) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) == cudaSuccess;
+    if (!ok) { set_error(std::string("mailbox setup: ") + cudaGetErrorString(cudaGetLastError())); acb200_mailbox_free(m); return nullptr; }
+    memset(m->pinned, 0, (24 + 2 * (size_t)world * acb200_mailbox::MBOX_WORDS) * 4);
+    return m;
+}
+
+long acb200_mailbox_step(ACB200_MAILBOX_t *m, const void *d_bytes, size_t n, size_t hay_len, void *stream)
+{
+    return mailbox_step(m, d_bytes, n, hay_len, stream);
+}
+
+int acb200_mailbox_result(ACB200_MAILBOX_t *m, uint32_t step, uint32_t *counts)
+{
+    if (!m->collector) { set_error("only the collector holds the rows"); return -1; }
+    if (step >= m->step || step + 2 < m->step) { set_error("mailbox gather: that step's rows are not held (any more)"); return -1; }
+    const int p = (int)(step & 1u);
+    MB_OK(cudaSetDevice(m->device));
+    MB_OK(cudaEventSynchronize(m->arrived[p]));
+    for (int r = 0; r < m->world; ++r) counts[r] = m->arrived_mbox(p)[(size_t)r * acb200_mailbox::MBOX_WORDS + 1];
+    return 0;
+}
+
+int acb200_mailbox_drain(ACB200_MAILBOX_t *m, void *stream)
+{
+    MB_OK(cudaSetDevice(m->device));
+    for (int p = 0; p < 2; ++p) MB_OK(cudaStreamWaitEvent(stream ? static_cast<cudaStream_t>(stream) : cudaStreamLegacy, m->copy_done[p], 0));
+    return 0;
+}
+
+void acb200_mailbox_free(ACB200_MAILBOX_t *m)
+{
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->side) { cudaStreamSynchronize(m->side); cudaStreamDestroy(m->side); }
+    for (int p = 0; p < 2; ++p) {
+        cudaFree(m->send[p]);
+        if (m->copy_done[p]) cudaEventDestroy(m->copy_done[p]);
+        if (m->arrived[p]) cudaEventDestroy(m->arrived[p]);
+    }
+    if (m->pinned) cudaFreeHost(m->pinned);
+    delete m;
 }
 
 void ac_trie_release(AC_TRIE_t *t)

@@ -262,9 +262,12 @@ class MailboxGatherer:
     the other processes map through CUDA IPC; after its scan a rank copies exactly its own rows into its slot with
     the copy engines (a side stream: NVLink, no SM), then writes {step, count} into its mailbox behind them.  The
     transfer of step k overlaps the scan of step k+1; `dst` looks at step k's mailboxes while it scans step k+1.
-    Rows and mailboxes are double-buffered by step parity.  A rank whose events outgrow `cap_rows` raises: size it
-    from a first synchronous step (ShardedMatcher.scan_and_gather, which also remains the general, ragged-batch path).
-    """
+    Rows and mailboxes are double-buffered by step parity, an acknowledgement word per parity keeps a fast sender
+    from overwriting rows `dst` still holds.  The step itself is ONE library call (acb200_mailbox_step, csrc/cabi.cpp):
+    driving the same CUDA calls from here cost 0.1 ms of interpreter time per step.  This class only sets up: buffers,
+    IPC handles through the process group, tensor views of the rows.  A rank whose events outgrow `cap_rows` raises:
+    size it from a first synchronous step (ShardedMatcher.scan_and_gather, which also remains the general path for
+    ragged batches)."""
 
     MBOX_WORDS = 4          # {step number, event count, densely flagged tiles, -}; 16 bytes apart
 
@@ -278,21 +281,20 @@ class MailboxGatherer:
         self.cap = int(cap_rows)
         self.dev = torch.cuda.current_device()
         self.step = 0
-        row_bytes = 8
-        self.rows_bytes = 2 * self.world * self.cap * row_bytes
+        self.rows_bytes = 2 * self.world * self.cap * 8
         self.mbox_bytes = 2 * self.world * self.MBOX_WORDS * 4 + 2 * 4         # mailboxes + one acknowledgement word per parity
         handles = [None, None]
+        self._own = None
         if self.rank == dst:
             self._own = (self.L.acb200_device_alloc(self.dev, self.rows_bytes), self.L.acb200_device_alloc(self.dev, self.mbox_bytes))
             if not self._own[0] or not self._own[1]:
-                raise RuntimeError("acb200_device_alloc failed")
-            hs = []
+                raise RuntimeError("acb200_device_alloc failed: " + self.L.acb200_last_error().decode())
+            handles = []
             for p in self._own:
                 h = C.create_string_buffer(64)
                 if self.L.acb200_ipc_export(C.c_void_p(p), h) != 0:
-                    raise RuntimeError("acb200_ipc_export failed")
-                hs.append(h.raw)
-            handles = hs
+                    raise RuntimeError("acb200_ipc_export failed: " + self.L.acb200_last_error().decode())
+                handles.append(h.raw)
         dist.broadcast_object_list(handles, src=dst, group=group)
         if self.rank == dst:
             self.rows_ptr, self.mbox_ptr = self._own
@@ -300,74 +302,43 @@ class MailboxGatherer:
             self.rows_ptr = self.L.acb200_ipc_open(self.dev, handles[0])
             self.mbox_ptr = self.L.acb200_ipc_open(self.dev, handles[1])
             if not self.rows_ptr or not self.mbox_ptr:
-                raise RuntimeError("acb200_ipc_open failed (no peer access between the GPUs?)")
-        d = torch.device("cuda", self.dev)
-        self.send = [torch.zeros((self.cap + 1, 2), dtype=torch.int32, device=d) for _ in range(2)]
-        self.mbox_src = torch.zeros((4, self.MBOX_WORDS), dtype=torch.int32).pin_memory()
-        self.side = torch.cuda.Stream(device=d)
-        self.copy_done = [torch.cuda.Event() for _ in range(2)]
+                raise RuntimeError("acb200_ipc_open failed: " + self.L.acb200_last_error().decode())
+        self.h = self.L.acb200_mailbox_create(self.aut.h, self.rank, self.world, int(self.rank == dst), self.cap,
+                                              C.c_void_p(self.rows_ptr), C.c_void_p(self.mbox_ptr))
+        if not self.h:
+            raise RuntimeError("acb200_mailbox_create failed: " + self.L.acb200_last_error().decode())
         if self.rank == dst:
+            d = torch.device("cuda", self.dev)
             self.rows = torch.as_tensor(_DeviceMemory(self.rows_ptr, self.rows_bytes // 4), device=d).view(2, self.world, self.cap, 2)
-            self.arrived = [torch.cuda.Event() for _ in range(2)]
-            self.mbox_host = torch.zeros((2, self.world, self.MBOX_WORDS), dtype=torch.int32).pin_memory()
+            self._counts = (C.c_uint32 * self.world)()
 
     def scan_and_send(self, dev_tensor: torch.Tensor, n_hay: int, hay_len: int, stream=0) -> int:
         """One step: scans this rank's equal-length batch and sends its rows on their way.  -> this rank's event count"""
-        k = self.step
+        n = self.L.acb200_mailbox_step(self.h, C.c_void_p(dev_tensor.data_ptr()), int(n_hay), int(hay_len), C.c_void_p(stream or LEGACY_STREAM))
+        if n < 0:
+            raise RuntimeError(self.L.acb200_last_error().decode())
         self.step += 1
-        p = k & 1
-        send = self.send[p]
-        compute = torch.cuda.current_stream()
-        compute.wait_event(self.copy_done[p])                       # the copy of step k-2 has left this buffer
-        if self.aut.search_device_uniform_async(dev_tensor.data_ptr(), n_hay, int(hay_len), send.data_ptr(), self.cap, stream=stream):
-            n, dense = (int(x) & 0xFFFFFFFF for x in send[0].cpu().tolist())       # this rank's own wait, as on one GPU
-            self.aut.async_finish(n, dense)
-        else:                                                       # this batch needs the synchronous call (full walk)
-            _, n = self.aut.search_device_uniform(dev_tensor.data_ptr(), n_hay, int(hay_len), stream=stream)
-            dense = 0
-            if n <= self.cap:
-                self.aut.copy_events(send[1:].data_ptr(), n, stream=stream or LEGACY_STREAM)
-        if n > self.cap:
-            raise RuntimeError(f"rank {self.rank}: {n} events in one step, the gather was sized for {self.cap} rows per rank")
-        self.side.wait_stream(compute)
-        side = self.side.cuda_stream
-        slot = (p * self.world + self.rank)
-        ack_ptr = self.mbox_ptr + 2 * self.world * self.MBOX_WORDS * 4 + p * 4
-        if k >= 2:
-            # flow control: slot p still holds step k-2 until the collector has let go of it (result(): "valid until
-            # step k+2 is sent").  The collector acknowledges here, every sender waits for it on its copy stream.
-            if self.rank == self.dst:
-                ack = self.mbox_src[k & 3]
-                ack[3] = (k - 1) & 0x7FFFFFFF
-                self.L.acb200_copy_async(C.c_void_p(ack_ptr), C.c_void_p(ack[3:].data_ptr()), 4, C.c_void_p(side))
-            else:
-                self.L.acb200_mailbox_wait_async(self.dev, C.c_void_p(ack_ptr), 1, 1, (k - 1) & 0x7FFFFFFF, C.c_void_p(side))
-        self.L.acb200_copy_async(C.c_void_p(self.rows_ptr + slot * self.cap * 8), C.c_void_p(send[1:].data_ptr()), n * 8, C.c_void_p(side))
-        src = self.mbox_src[k & 3]
-        src[0], src[1], src[2] = (k + 1) & 0x7FFFFFFF, n, dense
-        self.L.acb200_copy_async(C.c_void_p(self.mbox_ptr + slot * self.MBOX_WORDS * 4), C.c_void_p(src.data_ptr()), 3 * 4, C.c_void_p(side))
-        self.copy_done[p].record(self.side)
-        if self.rank == self.dst:
-            base = self.mbox_ptr + p * self.world * self.MBOX_WORDS * 4
-            self.L.acb200_mailbox_wait_async(self.dev, C.c_void_p(base), self.world, self.MBOX_WORDS, (k + 1) & 0x7FFFFFFF, C.c_void_p(side))
-            self.L.acb200_copy_async(C.c_void_p(self.mbox_host[p].data_ptr()), C.c_void_p(base), self.world * self.MBOX_WORDS * 4, C.c_void_p(side))
-            self.arrived[p].record(self.side)
-        return n
+        return int(n)
 
     def result(self, k: int):
         """On `dst`: the rows of step k from every rank (views, valid until step k+2 is sent), once they have all
         landed; elsewhere None.  Call it while a later step is in flight — the wait is then already over."""
         if self.rank != self.dst:
             return None
+        if self.L.acb200_mailbox_result(self.h, int(k), self._counts) != 0:
+            raise RuntimeError(self.L.acb200_last_error().decode())
         p = k & 1
-        self.arrived[p].synchronize()
-        counts = [int(self.mbox_host[p, r, 1]) for r in range(self.world)]
-        return [self.rows[p, r, :counts[r]] for r in range(self.world)]
+        return [self.rows[p, r, :int(self._counts[r])] for r in range(self.world)]
+
+    def drain(self, stream=0):
+        """makes `stream` wait for this rank's copies still in flight (before a clock stops, before buffers go away)"""
+        self.L.acb200_mailbox_drain(self.h, C.c_void_p(stream or LEGACY_STREAM))
 
     def close(self):
         torch.cuda.synchronize()
-        if self.group is not None or dist.is_initialized():
-            dist.barrier(group=self.group)
+        self.L.acb200_mailbox_free(self.h)
+        self.h = None
+        dist.barrier(group=self.group)
         if self.rank == self.dst:
             self.rows = None
             self.L.acb200_device_free(self.dev, self._own[0])

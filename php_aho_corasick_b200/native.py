@@ -84,7 +84,8 @@ EXPORTS = [
     "acb200_set_direct", "acb200_direct_probe", "acb200_search_device_uniform_async", "acb200_async_finish",
     "acb200_set_devices", "acb200_set_slab_bytes", "acb200_plan_slabs", "acb200_event_digest",
     "acb200_device_alloc", "acb200_device_free", "acb200_ipc_export", "acb200_ipc_open", "acb200_ipc_close",
-    "acb200_copy_async", "acb200_mailbox_wait_async",
+    "acb200_copy_async", "acb200_mailbox_wait_async", "acb200_mailbox_create", "acb200_mailbox_step", "acb200_mailbox_result",
+    "acb200_mailbox_drain", "acb200_mailbox_free",
 ]
 
 
@@ -167,6 +168,14 @@ def lib() -> C.CDLL:
     L.acb200_ipc_close.argtypes = [C.c_int, C.c_void_p]
     L.acb200_copy_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.acb200_mailbox_wait_async.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.acb200_mailbox_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
+    L.acb200_mailbox_create.restype = C.c_void_p
+    L.acb200_mailbox_step.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+    L.acb200_mailbox_step.restype = C.c_long
+    L.acb200_mailbox_result.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    L.acb200_mailbox_drain.argtypes = [C.c_void_p, C.c_void_p]
+    L.acb200_mailbox_free.argtypes = [C.c_void_p]
+    L.acb200_mailbox_free.restype = None
     L.acb200_copy_events.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.acb200_copy_events.restype = C.c_long
     _lib = L

@@ -188,7 +188,7 @@ def _nccl_worker(rank, world, port, q):
             ev = globalize(got, [(r * n_hays, (r + 1) * n_hays) for r in range(world)], goff)
             counts, hashes = a.event_digest(ev, world * n_hays)
             res.append((counts.tolist(), hashes.tolist(), bool(np.all(np.diff(ev["text_idx"].astype(np.int64)) >= 0))))
-    torch.cuda.current_stream().wait_stream(mg.side)
+    mg.drain()
     if rank == 0:
         ev = globalize(mg.result(4), [(r * n_hays, (r + 1) * n_hays) for r in range(world)], goff)
         counts, hashes = a.event_digest(ev, world * n_hays)
@@ -221,8 +221,11 @@ def test_nccl_two_rank_gathered_rows_equal_the_cpu_reference_per_haystack():
     off = W.offsets_uniform(16 * 256, 8192)
     kind = "reference" if pydriver.available("reference") else "oracle"
     _, _, counts, hashes = pydriver.bench_digest(kind, needles, flat, off, 4)
-    for c, h, ordered in res:
-        assert ordered and c == counts.tolist() and h == hashes.tolist()
+    assert len(res) == 9                                     # 3 steps through all_gather, 6 results through the mailboxes
+    for i, (c, h, ordered) in enumerate(res):
+        assert ordered, i
+        assert c == counts.tolist(), (i, int(np.sum(np.array(c) != counts)), sum(c), int(counts.sum()))
+        assert h == hashes.tolist(), i
 
 
 def _mailbox_worker(rank, world, port, q, same_gpu):
@@ -264,7 +267,7 @@ def _mailbox_worker(rank, world, port, q, same_gpu):
             ev = globalize(got, ranges, goff)
             counts, hashes = a.event_digest(ev, world * n_hays)
             res.append((counts.tolist(), hashes.tolist()))
-    torch.cuda.current_stream().wait_stream(mg.side)
+    mg.drain()
     if rank == 0:
         ev = globalize(mg.result(steps - 1), ranges, goff)
         counts, hashes = a.event_digest(ev, world * n_hays)
