@@ -228,6 +228,10 @@ typedef struct acb200_hit
 int acb200_search_hits(AC_TRIE_t *thiz, const char *bytes, const uint64_t *offsets, size_t n,
                        ACB200_HIT_t *hits, size_t cap, size_t *n_hits);
 
+/* The hits of the most recent acb200_search_hits() call again (its events are still on the device): for a caller
+ * whose buffer was too small the first time — the haystack is not scanned again.                       */
+int acb200_last_hits(AC_TRIE_t *thiz, ACB200_HIT_t *hits, size_t cap, size_t *n_hits);
+
 /* Accepted pattern number `index` (acceptance order = the order of successful ac_trie_add calls);
  * NULL if out of range or not finalized.                                                     */
 const AC_PATTERN_t *acb200_pattern(const AC_TRIE_t *thiz, size_t index);

@@ -671,6 +671,15 @@ int acb200_search_hits(AC_TRIE_t *t, const char *bytes, const uint64_t *offsets,
     return 0;
 }
 
+int acb200_last_hits(AC_TRIE_t *t, ACB200_HIT_t *hits, size_t cap, size_t *n_hits)
+{
+    if (t->open || !t->device_ok) { set_error("automaton is not finalized"); return -1; }
+    size_t total = 0;
+    if (!t->engine.expand_hits_to_host(1, hits, cap, &total)) return -1;
+    if (n_hits) *n_hits = total;
+    return 0;
+}
+
 const AC_PATTERN_t *acb200_pattern(const AC_TRIE_t *t, size_t index)
 {
     if (t->open || index >= t->flat.accepted.size()) return nullptr;

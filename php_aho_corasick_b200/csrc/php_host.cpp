@@ -204,9 +204,8 @@ int finalize_once(aho_master *m)
     return 1;
 }
 
-struct Collect {
-    std::vector<aho_hit_t> *hits;
-};
+// ahocorasick_match() on one haystack between these sizes fills its records from device-expanded hit columns
+constexpr size_t HITS_MIN_BYTES = 32u << 10, HITS_MAX_BYTES = 32u << 20;
 
 // php_ahocorasick_match_handler, src/php_ahocorasick.c:542-589
 void append_hits(std::vector<aho_hit_t> &out, const AC_MATCH_t *mt)
@@ -297,7 +296,39 @@ int ahocorasick_match_batch(const char *const *haystacks, const size_t *lens, si
     std::vector<std::vector<aho_hit_t>> per(n);
     // findAll=false: the reference's callback returns 1 after the first event (:588)
     int rc;
-    if (n == 1) {
+    if (n == 1 && find_all && lens[0] > HITS_MIN_BYTES && lens[0] <= HITS_MAX_BYTES) {
+        // One haystack that is neither tiny (one-launch path) nor huge (slab pipeline): the device expands the events
+        // into {pos, start_postion, pattern} columns and the records are filled from those — no callback per event
+        // (what php_ahocorasick_match_handler does per reported pattern, src/php_ahocorasick.c:555-584).
+        const uint64_t offs[2] = {0, (uint64_t)lens[0]};
+        std::vector<ACB200_HIT_t> hits(4096);
+        size_t total = 0;
+        rc = acb200_search_hits(m->acap, haystacks[0], offs, 1, hits.data(), hits.size(), &total);
+        if (rc == 0 && total > hits.size()) {
+            hits.resize(total);
+            rc = acb200_last_hits(m->acap, hits.data(), hits.size(), &total);
+        }
+        if (rc == 0) {
+            per[0].reserve(total);
+            for (size_t i = 0; i < total; ++i) {
+                const AC_PATTERN_t *pat = acb200_pattern(m->acap, hits[i].pattern);
+                const PatternRec *p = pat ? static_cast<const PatternRec *>(pat->aux) : nullptr;
+                if (!p) continue;
+                aho_hit_t h;
+                memset(&h, 0, sizeof(h));
+                h.pos = (long)hits[i].end;
+                if (pat->id.type == AC_PATTID_TYPE_STRING) { h.key_type = 2; h.key_opaque = p->key_opaque; }
+                else if (pat->id.type == AC_PATTID_TYPE_NUMBER) { h.key_type = 1; h.key_idx = pat->id.u.number; }
+                h.has_aux = p->has_aux ? 1 : 0;
+                h.aux_opaque = p->aux_opaque;
+                h.start_postion = (long)hits[i].start;
+                h.value_opaque = p->value_opaque;
+                h.value = p->value.data();
+                h.value_len = p->value.size();
+                per[0].push_back(h);
+            }
+        }
+    } else if (n == 1) {
         const uint64_t offs[2] = {0, (uint64_t)lens[0]};     // single haystack: no gather copy
         rc = ac_trie_search_flat(m->acap, haystacks[0], offs, 1, find_all ? 0 : 1, batch_cb, &per);
     } else {

@@ -85,7 +85,7 @@ EXPORTS = [
     "acb200_set_devices", "acb200_set_slab_bytes", "acb200_plan_slabs", "acb200_event_digest",
     "acb200_device_alloc", "acb200_device_free", "acb200_ipc_export", "acb200_ipc_open", "acb200_ipc_close",
     "acb200_copy_async", "acb200_mailbox_wait_async", "acb200_mailbox_create", "acb200_mailbox_step", "acb200_mailbox_result",
-    "acb200_mailbox_drain", "acb200_mailbox_free",
+    "acb200_mailbox_drain", "acb200_mailbox_free", "acb200_last_hits",
 ]
 
 
