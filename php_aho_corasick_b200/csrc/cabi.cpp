@@ -391,6 +391,8 @@ struct acb200_mailbox {
     cudaStream_t side = nullptr;
     cudaEvent_t copy_done[2] = {nullptr, nullptr}, arrived[2] = {nullptr, nullptr};
     uint32_t step = 0;
+    bool pending = false;              // the newest step's rows are complete in send[] but not sent yet (mailbox_flush)
+    uint32_t pending_step = 0, pending_count = 0, pending_dense = 0;
     static constexpr uint32_t MBOX_WORDS = 4;
 
     uint32_t *own_count() { return pinned + 16; }
@@ -403,32 +405,10 @@ struct acb200_mailbox {
         if (e_ != cudaSuccess) { set_error(std::string(#call) + ": " + cudaGetErrorString(e_)); return -1; } \
     } while (0)
 
-static long mailbox_step(acb200_mailbox *m, const void *d_bytes, size_t n, size_t hay_len, void *stream)
+// Puts the rows of step k (already complete in send[k & 1]) and its mailbox word on their way.
+static int mailbox_send(acb200_mailbox *m, uint32_t k, uint32_t count, uint32_t dense)
 {
-    ac_trie *t = m->t;
-    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : cudaStreamLegacy;
-    MB_OK(cudaSetDevice(m->device));
-    const uint32_t k = m->step++;
     const int p = (int)(k & 1u);
-    uint2 *send = m->send[p];
-    if (k >= 2) MB_OK(cudaStreamWaitEvent(st, m->copy_done[p], 0));           // the copy of step k-2 has left this buffer
-    uint32_t count = 0, dense = 0;
-    if (t->engine.scan_device_uniform_async(d_bytes, n, hay_len, send, m->cap, (void *)st)) {
-        MB_OK(cudaMemcpyAsync(m->own_count(), send, 8, cudaMemcpyDeviceToHost, st));
-        MB_OK(cudaStreamSynchronize(st));                                      // this rank's own wait, as on one GPU
-        count = m->own_count()[0]; dense = m->own_count()[1];
-        t->engine.async_finish(count, dense);
-    } else {                                                                   // this batch needs the synchronous call (full walk)
-        if (!t->engine.scan_device_uniform(d_bytes, n, hay_len, false, (void *)st)) return -1;
-        count = (uint32_t)t->engine.n_events();
-        if (count <= m->cap && count && !t->engine.copy_events_to(send + 1, count, (void *)st)) return -1;
-        MB_OK(cudaStreamSynchronize(st));
-    }
-    t->stats = t->engine.stats; t->stats.devices = 1;
-    if (count > m->cap) {
-        set_error("mailbox gather: " + std::to_string(count) + " events in one step, sized for " + std::to_string(m->cap) + " rows per rank");
-        return -1;
-    }
     const size_t slot = (size_t)p * m->world + m->rank;
     uint32_t *ack = m->mbox + 2u * m->world * acb200_mailbox::MBOX_WORDS + p;
     uint32_t *src = m->pinned + (k & 3u) * 4u;
@@ -440,7 +420,7 @@ static long mailbox_step(acb200_mailbox *m, const void *d_bytes, size_t n, size_
             MB_OK(cudaMemcpyAsync(ack, src + 3, 4, cudaMemcpyDefault, m->side));
         } else if (!mailbox_wait_async(m->device, ack, 1, 1, k - 1u, m->side)) return -1;
     }
-    if (count) MB_OK(cudaMemcpyAsync(m->rows + slot * m->cap * 8, send + 1, (size_t)count * 8, cudaMemcpyDefault, m->side));
+    if (count) MB_OK(cudaMemcpyAsync(m->rows + slot * m->cap * 8, m->send[p] + 1, (size_t)count * 8, cudaMemcpyDefault, m->side));
     src[0] = k + 1u; src[1] = count; src[2] = dense;
     MB_OK(cudaMemcpyAsync(m->mbox + slot * acb200_mailbox::MBOX_WORDS, src, 12, cudaMemcpyDefault, m->side));
     MB_OK(cudaEventRecord(m->copy_done[p], m->side));
@@ -450,6 +430,47 @@ static long mailbox_step(acb200_mailbox *m, const void *d_bytes, size_t n, size_
         MB_OK(cudaMemcpyAsync(m->arrived_mbox(p), boxes, (size_t)m->world * acb200_mailbox::MBOX_WORDS * 4, cudaMemcpyDefault, m->side));
         MB_OK(cudaEventRecord(m->arrived[p], m->side));
     }
+    return 0;
+}
+
+static int mailbox_flush(acb200_mailbox *m)
+{
+    if (!m->pending) return 0;
+    m->pending = false;
+    return mailbox_send(m, m->pending_step, m->pending_count, m->pending_dense);
+}
+
+static long mailbox_step(acb200_mailbox *m, const void *d_bytes, size_t n, size_t hay_len, void *stream)
+{
+    ac_trie *t = m->t;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : cudaStreamLegacy;
+    MB_OK(cudaSetDevice(m->device));
+    const uint32_t k = m->step++;
+    const int p = (int)(k & 1u);
+    uint2 *send = m->send[p];
+    if (k >= 2) MB_OK(cudaStreamWaitEvent(st, m->copy_done[p], 0));           // the copy of step k-2 has left this buffer
+    uint32_t count = 0, dense = 0;
+    if (t->engine.scan_device_uniform_async(d_bytes, n, hay_len, send, m->cap, (void *)st)) {
+        // the kernels of step k are enqueued: the rows of step k-1 are sent off while the GPU works on them (the dozen
+        // driver calls this takes would otherwise sit between two steps, with the GPU idle)
+        if (mailbox_flush(m) != 0) return -1;
+        MB_OK(cudaMemcpyAsync(m->own_count(), send, 8, cudaMemcpyDeviceToHost, st));
+        MB_OK(cudaStreamSynchronize(st));                                      // this rank's own wait, as on one GPU
+        count = m->own_count()[0]; dense = m->own_count()[1];
+        t->engine.async_finish(count, dense);
+    } else {                                                                   // this batch needs the synchronous call (full walk)
+        if (mailbox_flush(m) != 0) return -1;
+        if (!t->engine.scan_device_uniform(d_bytes, n, hay_len, false, (void *)st)) return -1;
+        count = (uint32_t)t->engine.n_events();
+        if (count <= m->cap && count && !t->engine.copy_events_to(send + 1, count, (void *)st)) return -1;
+        MB_OK(cudaStreamSynchronize(st));
+    }
+    t->stats = t->engine.stats; t->stats.devices = 1;
+    if (count > m->cap) {
+        set_error("mailbox gather: " + std::to_string(count) + " events in one step, sized for " + std::to_string(m->cap) + " rows per rank");
+        return -1;
+    }
+    m->pending = true; m->pending_step = k; m->pending_count = count; m->pending_dense = dense;
     return (long)count;
 }
 
@@ -912,6 +933,7 @@ int acb200_mailbox_result(ACB200_MAILBOX_t *m, uint32_t step, uint32_t *counts)
     if (step >= m->step || step + 2 < m->step) { set_error("mailbox gather: that step's rows are not held (any more)"); return -1; }
     const int p = (int)(step & 1u);
     MB_OK(cudaSetDevice(m->device));
+    if (m->pending && m->pending_step == step && mailbox_flush(m) != 0) return -1;
     MB_OK(cudaEventSynchronize(m->arrived[p]));
     for (int r = 0; r < m->world; ++r) counts[r] = m->arrived_mbox(p)[(size_t)r * acb200_mailbox::MBOX_WORDS + 1];
     return 0;
@@ -920,6 +942,7 @@ int acb200_mailbox_result(ACB200_MAILBOX_t *m, uint32_t step, uint32_t *counts)
 int acb200_mailbox_drain(ACB200_MAILBOX_t *m, void *stream)
 {
     MB_OK(cudaSetDevice(m->device));
+    if (mailbox_flush(m) != 0) return -1;
     for (int p = 0; p < 2; ++p) MB_OK(cudaStreamWaitEvent(stream ? static_cast<cudaStream_t>(stream) : cudaStreamLegacy, m->copy_done[p], 0));
     return 0;
 }

@@ -281,11 +281,12 @@ class MailboxGatherer:
         self.cap = int(cap_rows)
         self.dev = torch.cuda.current_device()
         self.step = 0
-        self.rows_bytes = 2 * self.world * self.cap * 8
-        self.mbox_bytes = 2 * self.world * self.MBOX_WORDS * 4 + 2 * 4         # mailboxes + one acknowledgement word per parity
-        handles = [None, None]
+        self.rows_bytes = self.mbox_bytes = 0
+        handles = [None, None, self.cap]          # the collector's capacity is everyone's: slot offsets must agree
         self._own = None
         if self.rank == dst:
+            self.rows_bytes = 2 * self.world * self.cap * 8
+            self.mbox_bytes = 2 * self.world * self.MBOX_WORDS * 4 + 2 * 4     # mailboxes + one acknowledgement word per parity
             self._own = (self.L.acb200_device_alloc(self.dev, self.rows_bytes), self.L.acb200_device_alloc(self.dev, self.mbox_bytes))
             if not self._own[0] or not self._own[1]:
                 raise RuntimeError("acb200_device_alloc failed: " + self.L.acb200_last_error().decode())
@@ -295,7 +296,9 @@ class MailboxGatherer:
                 if self.L.acb200_ipc_export(C.c_void_p(p), h) != 0:
                     raise RuntimeError("acb200_ipc_export failed: " + self.L.acb200_last_error().decode())
                 handles.append(h.raw)
+            handles.append(self.cap)
         dist.broadcast_object_list(handles, src=dst, group=group)
+        self.cap = int(handles[2])
         if self.rank == dst:
             self.rows_ptr, self.mbox_ptr = self._own
         else:
