@@ -181,7 +181,14 @@ def _nccl_worker(rank, world, port, q, same_gpu=False):
         if rank == 0:
             ev = globalize(got, [(r * n_hays, (r + 1) * n_hays) for r in range(world)], goff)
             counts, hashes = a.event_digest(ev, world * n_hays)
-            res.append((counts.tolist(), hashes.tolist(), bool(np.all(np.diff(ev["text_idx"].astype(np.int64)) >= 0))))
+            ordered = bool(np.all(np.diff(ev["text_idx"].astype(np.int64)) >= 0))
+            if not ordered:                                  # what a race between a rank's scan / copy and the collective looks like
+                for r, g_r in enumerate(got):
+                    e = g_r.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+                    down = np.flatnonzero(np.diff(e[:, 0]) <= 0)
+                    print(f"step {step}: rank {r} sent {len(e)} rows, {len(down)} not ascending, first at {down[:3].tolist()}, "
+                          f"zero rows {int(np.sum(e[:, 0] == 0))}", flush=True)
+            res.append((counts.tolist(), hashes.tolist(), ordered))
     # the same steps through the mailbox gather (copy engines into rank 0's IPC-mapped buffer, pipelined by one step):
     # several steps in a row, so that slots are reused and the acknowledgement flow control is exercised
     from php_aho_corasick_b200.dist import MailboxGatherer
