@@ -334,9 +334,19 @@ def main():
         n0, _ = sm.scan_and_gather(resident, offsets, 0, stream=stream, uniform_len=HAY_LEN)
         most = torch.tensor([n0], dtype=torch.int64, device=dev)
         dist.all_reduce(most, op=dist.ReduceOp.MAX)
-        mg = MailboxGatherer(aut, cap_rows=2 * int(most.item()) + 4096)
+        try:
+            mg = MailboxGatherer(aut, cap_rows=2 * int(most.item()) + 4096)
+        except Exception as e:                   # (e.g. CUDA IPC not permitted in this container)
+            print(f"rank {rank}: mailbox gather unavailable ({e}); using the all_gather path", file=sys.stderr)
+        ok = torch.tensor([1 if mg is not None else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0 and mg is not None:
+            mg.close()
+            mg = None
 
     def step_resident():
+        if world > 1 and mg is None:
+            return sm.scan_and_gather(resident, offsets, 0, stream=stream, uniform_len=HAY_LEN)
         if world > 1:
             n = mg.scan_and_send(resident, n_hays, HAY_LEN, stream=stream)
             if mg.step >= 2:
@@ -388,8 +398,9 @@ def main():
     kind = cpu_kind()
     threads_total = os.cpu_count() or 1
     cpu_full = cpu_leg(needles, host_stream, offsets, max(1, threads_total // world), 1, kind, digest=True)
-    n_own, _ = step_resident()
-    got = drain()
+    n_own, got = step_resident()
+    if mg is not None:
+        got = drain()
     if world > 1:
         exp = torch.from_numpy(np.stack([cpu_full["counts"], cpu_full["hashes"]]).view(np.int64)).to(dev)
         all_exp = [torch.empty_like(exp) for _ in range(world)]
@@ -406,8 +417,9 @@ def main():
             ordered = bool(np.all(np.diff(ev["text_idx"].astype(np.int64)) >= 0))
             parity = {"checked": True, "events": int(ev.size), "haystacks": int(world * n_hays), "hash_ok": bad == 0 and ordered,
                       "mismatching_haystacks": bad, "rows_in_global_order": ordered,
-                      "what": f"rows gathered on rank 0 (copy engines over NVLink into its IPC-mapped buffer, dist.MailboxGatherer) "
-                              f"from {world} ranks vs {cpu_full['kind']} ac_trie_search, every haystack"}
+                      "what": ("rows gathered on rank 0 (copy engines over NVLink into its IPC-mapped buffer, dist.MailboxGatherer) "
+                               if mg is not None else "rows gathered on rank 0 (NCCL all_gather, dist.ShardedMatcher) ")
+                              + f"from {world} ranks vs {cpu_full['kind']} ac_trie_search, every haystack"}
     else:
         ev = packed_to_events(aut, torch, (None, n_own), n_hays, hay_len=HAY_LEN)
         counts, hashes = aut.event_digest(ev, n_hays)
@@ -565,7 +577,8 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
-        mg.close()
+        if mg is not None:
+            mg.close()
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0 and parity and not parity["hash_ok"]:

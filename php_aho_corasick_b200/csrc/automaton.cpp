@@ -324,7 +324,7 @@ void HostTrie::build_filter(FlatAutomaton &flat) const {
                 uint32_t lo, hi, nb;
                 gram(p, r, lo, hi, nb);
                 for (uint32_t next : {nb, FILTER_NEXT_UNKNOWN}) {
-                    const uint32_t i = filter_mix3(lo, hi, next) >> (32 - lg);
+                    const uint32_t i = filter_l2_index(filter_mix1(lo, hi, next), lg);
                     flat.l2[i >> 5] |= 1u << (i & 31);
                 }
             }

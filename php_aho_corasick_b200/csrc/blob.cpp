@@ -16,7 +16,7 @@
 
 namespace acb200 {
 
-static const char BLOB_MAGIC[8] = {'A', 'C', 'B', '2', '0', '0', 'v', '1'};
+static const char BLOB_MAGIC[8] = {'A', 'C', 'B', '2', '0', '0', 'v', '2'};     // v2: level-2 bitmap indexed by filter_l2_index
 
 struct Writer {
     FILE *f; bool ok = true;

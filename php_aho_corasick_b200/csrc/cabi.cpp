@@ -862,7 +862,7 @@ int acb200_filter_probe(const AC_TRIE_t *t, uint64_t word, unsigned next_byte)
     const uint32_t w = f.l1[filter_l1_word(tt, next_byte == FILTER_NEXT_UNKNOWN)];
     if (!((w >> filter_bit1(tt)) & (w >> filter_bit2(tt)) & 1u)) return 0;
     if (f.l2_log2) {
-        const uint32_t i3 = filter_mix3(lo, hi, next_byte) >> (32 - f.l2_log2);
+        const uint32_t i3 = filter_l2_index(tt, f.l2_log2);
         if (!((f.l2[i3 >> 5] >> (i3 & 31)) & 1u)) return 0;
     }
     return 1;

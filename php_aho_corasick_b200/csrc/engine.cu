@@ -713,6 +713,7 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
         a.capacity = (uint32_t)std::min<size_t>(events_cap_, 0xffffffffu);
         if (async) {                 // events go straight into the caller's rows; what does not fit is counted, not written
             a.out = (uint2 *)async_rows_ + 1;
+            va.count_row = (uint2 *)async_rows_;
             a.capacity = (uint32_t)std::min<size_t>(async_cap_, 0xffffffffu);
         }
         // counters, block sums and events per tile (the walk kernel adds to both) are adjacent: one memset
@@ -757,8 +758,6 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
         stats.kernel_launches += 2;
         if (async) {
             // row 0 = {event count, dense tiles}; the caller waits (after its own work on the stream) and calls async_finish()
-            CU_OK(cudaMemcpyAsync(async_rows_, vcounters + 1, 4, cudaMemcpyDeviceToDevice, st));
-            CU_OK(cudaMemcpyAsync((uint32_t *)async_rows_ + 1, vcounters + 4, 4, cudaMemcpyDeviceToDevice, st));
             async_pending_ = true;
             async_tiles_ = n_tiles;
             return true;

@@ -55,7 +55,15 @@ ACB_HD uint32_t filter_l1_word(uint32_t t, bool next_unknown)
 ACB_HD uint32_t filter_bit1(uint32_t t) { return t & 31u; }
 ACB_HD uint32_t filter_bit2(uint32_t t) { return (t >> 5) & 31u; }
 
-// level 2: third independent hash, top `log2_bits` bits index a 2^log2_bits-bit map in global memory
+// level 2 (a 2^log2_bits-bit map in global memory) is indexed by a remix of the level-1 hash: three instructions
+// where an independent hash of the word costs eight — the filter loop is issue-bound, and with W = 4 every word of the
+// haystack pays for this index.  Two grams collide in BOTH levels only if their 32-bit level-1 hashes are equal.
+ACB_HD uint32_t filter_l2_index(uint32_t t, uint32_t log2_bits)
+{
+    return ((t ^ (t >> 15)) * 0x2C1B3C6Du) >> (32u - log2_bits);
+}
+
+// third independent hash of a gram: the home slot of the exact gram table (gram_table.hpp)
 ACB_HD uint32_t filter_mix3(uint32_t lo, uint32_t hi, uint32_t next_byte)
 {
     uint32_t t = (lo ^ 0x5bd1e995u) * 0x165667B1u + (hi ^ 0x7feb352du) * 0xD3A2646Du + next_byte * 0x9E3779B1u;

@@ -104,7 +104,7 @@ __device__ __forceinline__ bool test_word_at(const FilterArgs &a, uint32_t regio
     bool p = (__funnelshift_r(word, word, t) & __funnelshift_r(word, word, t >> 5) & 1u) != 0;
     if (L2) {
         uint32_t word3 = 0;
-        const uint32_t i3 = filter_mix3(lo, hi, nb) >> a.l2_shift;
+        const uint32_t i3 = filter_l2_index(t, 32u - a.l2_shift);
         if (p) word3 = __ldg(a.l2 + (i3 >> 5));
         p = (word3 >> (i3 & 31u)) & 1u;
     }
@@ -151,9 +151,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const Filter
             const uint32_t nb = (j == NB - 1) ? after : (((W == 8) ? w[2] : w[j + 1]) & 0xffu);
             p[j] = test_word_at<false>(a, (j == NB - 1) ? last_region : s_base, (j == NB - 1) ? last_words : FILTER_L1_KNOWN_WORDS, lo, hi, nb);
             if (L2) {
-                // level 2: the probes of all the lane's words are issued before any is looked at — one trip to L2 per
-                // span instead of one per word (config 3: every sixth word passes level 1; config 3: the filter pass was 0.55 ms/GiB with a probe per word)
-                i3[j] = filter_mix3(lo, hi, nb) >> a.l2_shift;
+                // level 2: the index is a three-instruction remix of the level-1 hash, and the probes of all the lane's
+                // words are issued before any is looked at (one trip to L2 per span, not one per word)
+                i3[j] = filter_l2_index(filter_mix1(lo, hi, nb), 32u - a.l2_shift);
                 word3[j] = 0;
                 if (p[j]) word3[j] = __ldg(a.l2 + (i3[j] >> 5));
             }
@@ -234,6 +234,7 @@ struct VerifyArgs {
     const uint4 *gt_slots;        // exact gram table (gram_table.hpp) or nullptr
     const uint32_t *gt_pat;       // its pattern store
     uint32_t gt_log2;             // 2^gt_log2 slots; 0: every flagged word is walked
+    uint2 *count_row;             // asynchronous calls: where ac_offsets_kernel leaves {event count, dense tiles}; else nullptr
     uint32_t *items;              // work items, tile runs in completion order (capacity n_tiles * VER_DENSE_MAX)
     uint2 *desc;                  // per tile {offset into items, count}
     uint2 *recs;                  // per item {state of the first event, count << 16 | first end - item origin}
@@ -685,7 +686,12 @@ __global__ void __launch_bounds__(EMIT_THREADS) ac_offsets_kernel(const __grid_c
         if ((uint32_t)w < warp) base += s_warp[w];
     }
     if (tile < a.n_tiles) a.tile_off[tile] = base + incl - len;
-    if (tile == a.n_tiles - 1) a.s.counters[1] = base + incl;        // all events of the call
+    if (tile == a.n_tiles - 1) {
+        a.s.counters[1] = base + incl;                                // all events of the call
+        // asynchronous calls: row 0 of the caller's rows = {event count, densely flagged tiles} (ac_collect_kernel, which
+        // counts the latter, has finished)
+        if (a.count_row) *a.count_row = make_uint2(base + incl, a.s.counters[4]);
+    }
 }
 
 // One warp per tile with events: write them to their final place, in item order.

@@ -68,7 +68,7 @@ def test_blob_rejects_garbage_and_unfinalized(tmp_path):
     with pytest.raises(native.AcError):
         a.save(str(tmp_path / "x.acb"))             # not finalized
     bad = tmp_path / "bad.acb"
-    bad.write_bytes(b"ACB200v1" + os.urandom(100))
+    bad.write_bytes(b"ACB200v2" + os.urandom(100))
     with pytest.raises(native.AcError):
         Automaton.load(str(bad), require_device=False)
     with pytest.raises(native.AcError):
