@@ -341,7 +341,7 @@ def main():
         ok = torch.tensor([1 if mg is not None else 0], dtype=torch.int64, device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0 and mg is not None:
-            mg.close()
+            mg.close(collective=False)
             mg = None
 
     def step_resident():

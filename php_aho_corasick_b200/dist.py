@@ -337,11 +337,13 @@ class MailboxGatherer:
         """makes `stream` wait for this rank's copies still in flight (before a clock stops, before buffers go away)"""
         self.L.acb200_mailbox_drain(self.h, C.c_void_p(stream or LEGACY_STREAM))
 
-    def close(self):
+    def close(self, collective: bool = True):
+        """collective: every rank closes now (a barrier keeps the collector's buffers alive until all copies are over)"""
         torch.cuda.synchronize()
         self.L.acb200_mailbox_free(self.h)
         self.h = None
-        dist.barrier(group=self.group)
+        if collective:
+            dist.barrier(group=self.group)
         if self.rank == self.dst:
             self.rows = None
             self.L.acb200_device_free(self.dev, self._own[0])
