@@ -915,6 +915,7 @@ ACB200_MAILBOX_t *acb200_mailbox_create(AC_TRIE_t *t, int rank, int world, int c
              cudaEventCreateWithFlags(&m->copy_done[p], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&m->arrived[p], cudaEventDisableTiming) == cudaSuccess;
     }
+    ok = ok && cudaDeviceSynchronize() == cudaSuccess;          // the zero-fills ran on the legacy stream
     ok = ok && cudaMallocHost((void **)&m->pinned, (24 + 2 * (size_t)world * acb200_mailbox::MBOX_WORDS) * 4) == cudaSuccess &&
          cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking) == cudaSuccess;
     if (!ok) { set_error(std::string("mailbox setup: ") + cudaGetErrorString(cudaGetLastError())); acb200_mailbox_free(m); return nullptr; }

@@ -61,7 +61,7 @@ void *device_alloc(int device, size_t bytes)
 {
     void *p = nullptr;
     if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess ||
-        cudaMemset(p, 0, bytes ? bytes : 1) != cudaSuccess) {
+        cudaMemset(p, 0, bytes ? bytes : 1) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
         set_error(std::string("device_alloc: ") + cudaGetErrorString(cudaGetLastError()));
         return nullptr;
     }
@@ -347,7 +347,10 @@ bool Engine::ensure_text(size_t bytes)
     cudaFree(d_text_); d_text_ = nullptr; text_cap_ = 0;
     const size_t cap = std::max(bytes + bytes / 4, (size_t)1 << 20);
     CU_OK(cudaMalloc(&d_text_, cap));
-    CU_OK(cudaMemset(d_text_, 0, cap));      // the scan prefetches 16-byte groups past the end of the stream (never used)
+    // (the scan prefetches 16-byte groups past the end of the stream, never used.)  ON the handle's stream: cudaMemset runs
+    // on the legacy default stream, which this non-blocking stream does not wait for — the zeroes could land after the
+    // haystack that the next line of the caller copies in (seen once a call got short enough: the one-CTA path).
+    CU_OK(cudaMemsetAsync(d_text_, 0, cap, S(stream_)));
     text_cap_ = cap;
     return true;
 }
@@ -942,7 +945,7 @@ bool Engine::slab_upload_async(int buf, const char *bytes, size_t n_bytes)
         cudaFree(d_slab_[buf]); d_slab_[buf] = nullptr; slab_cap_[buf] = 0;
         const size_t cap = n_bytes + n_bytes / 8 + 4096;
         CU_OK(cudaMalloc(&d_slab_[buf], cap));
-        CU_OK(cudaMemset(d_slab_[buf], 0, cap));
+        CU_OK(cudaMemsetAsync(d_slab_[buf], 0, cap, S(copy_stream_)));       // on the stream that uploads into it
         slab_cap_[buf] = cap;
     }
     CU_OK(cudaEventRecord(EV(ev_slab_[2 * buf]), S(copy_stream_)));

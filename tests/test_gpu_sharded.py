@@ -118,3 +118,33 @@ def test_cfg2_block_on_every_visible_gpu():
     assert np.array_equal(ev, ev1)
     assert_same(a, ev[ev["text_idx"] < 64], 64, oracle_hits([needles], split(hay, off)[:64]))
     a.release()
+
+
+def test_one_text_beyond_4_gib_through_the_drop_in_call():
+    """The reference scans a text of any size_t length (src/multifast/ahocorasick.c:175-241); a device launch addresses
+    its stream with 32 bits.  ac_trie_search cuts such a text into slabs itself: positions beyond 2^32 come back exact,
+    a pattern planted across the 4 GiB mark and across a slab cut is found once."""
+    total = (4 << 30) + (96 << 20) + 12345
+    try:
+        hay = np.zeros(total, dtype=np.uint8)
+    except MemoryError:
+        pytest.skip("not enough host memory for a 4.1 GiB text")
+    pats = [b"needle-in-a-very-large-haystack", b"\x01\x02\x03\x04\x05\x06\x07\x08\x09", b"tail!"]
+    from php_aho_corasick_b200.native import plan_slabs
+    cut = plan_slabs(np.array([0, total], dtype=np.uint64), len(pats[0]) - 1, 1)[0]["end"]
+    plant = {                                   # end offset -> pattern
+        1000 + len(pats[0]): 0,
+        cut + 7: 0,                             # straddles the first slab cut (ends 7 bytes behind it)
+        (1 << 32) + 11: 0,                      # straddles the 4 GiB mark
+        (1 << 32) + 5000 + len(pats[1]): 1,
+        total: 2,                               # the last bytes of the text
+    }
+    for end, k in plant.items():
+        p = np.frombuffer(pats[k], dtype=np.uint8)
+        hay[end - p.size:end] = p
+    a = build([pats])
+    ev = a.search_events(hay)
+    got = {int(e["end"]): a.state_patterns(int(e["state"]))[0][0] for e in ev}
+    assert got == plant and len(ev) == len(plant)
+    assert a.stats().bytes >= total
+    a.release()
