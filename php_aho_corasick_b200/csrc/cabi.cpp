@@ -141,8 +141,17 @@ struct HaySource {
     }
 };
 
+// one event as the slab worker hands it to the calling thread: everything the callback needs already looked up
+struct ResolvedEvent {
+    uint64_t end;                        // exclusive end offset inside its haystack
+    const AC_PATTERN_t *patterns;        // the state's output list ...
+    uint32_t size;                       // ... and its length
+    uint32_t state;
+    size_t text_idx;
+};
+
 struct SlabResult {
-    std::vector<ACB200_EVENT_t> ev;      // resolved by the worker: haystack index, offset inside it, state
+    std::vector<ResolvedEvent> ev;
     ACB200_STATS_t st{};
     uint32_t end_state = 0;
     bool ready = false, ok = true;
@@ -190,7 +199,7 @@ void add_stats(ACB200_STATS_t &sum, const ACB200_STATS_t &s)
     sum.chunk_bytes = s.chunk_bytes; sum.halo_bytes = s.halo_bytes; sum.filtered = s.filtered;
 }
 
-void shard_worker(Engine *eng, const HaySource &src, const std::vector<SlabPlan> &plans, const std::vector<size_t> &mine,
+void shard_worker(const ac_trie *t, Engine *eng, const HaySource &src, const std::vector<SlabPlan> &plans, const std::vector<size_t> &mine,
                   bool first_only, uint32_t init_state, int helpers, ShardRun &run)
 {
     std::vector<uint64_t> rel;
@@ -239,7 +248,9 @@ void shard_worker(Engine *eng, const HaySource &src, const std::vector<SlabPlan>
                 if (pe[i].end <= p.halo) continue;               // ends inside the halo: the slab before reported it
                 const uint64_t g = base + pe[i].end;
                 while (g > src.off[h + 1]) ++h;
-                r.ev.push_back(ACB200_EVENT_t{g - src.off[h], pe[i].state, (uint32_t)h});
+                const AC_PATTERN_t *pats;
+                const uint32_t size = (uint32_t)patterns_of(t, pe[i].state, &pats);
+                r.ev.push_back(ResolvedEvent{g - src.off[h], pats, size, pe[i].state, h});
             }
         }
         r.st = eng->stats;
@@ -283,7 +294,7 @@ int sharded_search(ac_trie *t, const HaySource &src, bool first_only, uint32_t i
     const int helpers = src.pinned ? 1 : (int)std::max(1u, std::min(4u, hw / (2u * (unsigned)n_dev)));
     std::vector<std::thread> workers;
     for (int d = 0; d < n_dev; ++d)
-        workers.emplace_back(shard_worker, engines[d], std::cref(src), std::cref(plans), std::cref(mine[d]), first_only,
+        workers.emplace_back(shard_worker, (const ac_trie *)t, engines[d], std::cref(src), std::cref(plans), std::cref(mine[d]), first_only,
                              init_state, helpers, std::ref(run));
 
     int rc = 0;
@@ -299,14 +310,14 @@ int sharded_search(ac_trie *t, const HaySource &src, bool first_only, uint32_t i
         const SlabPlan &p = plans[i];
         add_stats(per_dev[p.device_slot], r.st);
         if (end_state) *end_state = r.end_state;
-        for (const ACB200_EVENT_t &e : r.ev) {
+        for (const ResolvedEvent &e : r.ev) {
             const size_t h = e.text_idx;
             if (h == stopped) continue;
-            const int s = sink(h, e.end, e.state);
+            const int s = sink(e);
             if (s && stop_all) { rc = 1; break; }
             if (s || first_only) stopped = h;
         }
-        std::vector<ACB200_EVENT_t>().swap(r.ev);
+        std::vector<ResolvedEvent>().swap(r.ev);
     }
     if (rc != 0) run.abort.store(true);
     for (auto &w : workers) w.join();
@@ -345,7 +356,9 @@ static void replay_direct(ac_trie *t, const uint64_t *offsets, size_t n, int fir
         const uint64_t end = ev[i].end;
         while (h < n && end > offsets[h + 1]) ++h;
         if (h == stopped) continue;
-        const int r = sink(h, (uint64_t)(end - offsets[h]), ev[i].state);
+        const AC_PATTERN_t *pats;
+        const uint32_t size = (uint32_t)patterns_of(t, ev[i].state, &pats);
+        const int r = sink(ResolvedEvent{end - offsets[h], pats, size, ev[i].state, h});
         if (r || first_only) stopped = h;
     }
 }
@@ -591,8 +604,13 @@ int ac_trie_search(AC_TRIE_t *t, AC_TEXT_t *text, int keep, AC_MATCH_CALBACK_f c
         // a long text: slabs with a halo, over every GPU of the handle; a text of any size_t length is scanned
         HaySource src;
         src.flat = text->astring; src.off = offs; src.n = 1; src.pinned = is_pinned(text->astring);
-        const int rc = sharded_search(t, src, false, t->last_state, true, &end_state,
-                                      [&](size_t, uint64_t position, uint32_t state) { return fire(position, state); });
+        const int rc = sharded_search(t, src, false, t->last_state, true, &end_state, [&](const ResolvedEvent &e) {
+            AC_MATCH_t m;
+            m.patterns = const_cast<AC_PATTERN_t *>(e.patterns);
+            m.size = e.size;
+            m.position = (size_t)e.end + base;
+            return callback(&m, user);
+        });
         if (rc != 0) return rc;
     }
     t->last_state = end_state;                   // ahocorasick.c:236-238
@@ -606,13 +624,12 @@ int ac_trie_search_flat(AC_TRIE_t *t, const char *bytes, const uint64_t *offsets
     if (offsets[0] != 0) { set_error("offsets[0] must be 0"); return -1; }
     HaySource src;
     src.flat = bytes ? bytes : ""; src.off = offsets; src.n = n;
-    return search_source(t, src, first_only, [&](size_t h, uint64_t position, uint32_t state) {
-        const AC_PATTERN_t *pats;
+    return search_source(t, src, first_only, [&](const ResolvedEvent &e) {
         AC_MATCH_t m;
-        m.size = patterns_of(t, state, &pats);
-        m.patterns = const_cast<AC_PATTERN_t *>(pats);
-        m.position = (size_t)position;
-        return callback(h, &m, user);
+        m.patterns = const_cast<AC_PATTERN_t *>(e.patterns);
+        m.size = e.size;
+        m.position = (size_t)e.end;
+        return callback(e.text_idx, &m, user);
     });
 }
 
@@ -625,13 +642,12 @@ int ac_trie_search_batch(AC_TRIE_t *t, const AC_TEXT_t *texts, size_t n, int fir
     t->gather_off[n] = total;
     HaySource src;
     src.texts = texts; src.off = t->gather_off.data(); src.n = n;
-    return search_source(t, src, first_only, [&](size_t h, uint64_t position, uint32_t state) {
-        const AC_PATTERN_t *pats;
+    return search_source(t, src, first_only, [&](const ResolvedEvent &e) {
         AC_MATCH_t m;
-        m.size = patterns_of(t, state, &pats);
-        m.patterns = const_cast<AC_PATTERN_t *>(pats);
-        m.position = (size_t)position;
-        return callback(h, &m, user);
+        m.patterns = const_cast<AC_PATTERN_t *>(e.patterns);
+        m.size = e.size;
+        m.position = (size_t)e.end;
+        return callback(e.text_idx, &m, user);
     });
 }
 
@@ -642,11 +658,11 @@ int acb200_search_events(AC_TRIE_t *t, const char *bytes, const uint64_t *offset
     HaySource src;
     src.flat = bytes ? bytes : ""; src.off = offsets; src.n = n;
     size_t w = 0;
-    const int rc = search_source(t, src, first_only, [&](size_t h, uint64_t position, uint32_t state) {
+    const int rc = search_source(t, src, first_only, [&](const ResolvedEvent &e) {
         if (w < cap) {
-            events[w].end = position;
-            events[w].state = state;
-            events[w].text_idx = (uint32_t)h;
+            events[w].end = e.end;
+            events[w].state = e.state;
+            events[w].text_idx = (uint32_t)e.text_idx;
         }
         ++w;
         return 0;
@@ -844,6 +860,12 @@ int acb200_set_tuning(AC_TRIE_t *t, uint32_t chunk_bytes, uint32_t smem_table_by
 {
     t->engine.tune_chunk = chunk_bytes;
     t->engine.tune_smem_bytes = smem_table_bytes;
+    return 0;
+}
+
+int acb200_set_prefetch(AC_TRIE_t *t, uint32_t bytes_ahead)
+{
+    t->engine.tune_prefetch = bytes_ahead & ~127u;
     return 0;
 }
 
