@@ -863,12 +863,6 @@ int acb200_set_tuning(AC_TRIE_t *t, uint32_t chunk_bytes, uint32_t smem_table_by
     return 0;
 }
 
-int acb200_set_prefetch(AC_TRIE_t *t, uint32_t bytes_ahead)
-{
-    t->engine.tune_prefetch = bytes_ahead & ~127u;
-    return 0;
-}
-
 int acb200_set_filter(AC_TRIE_t *t, int mode)
 {
     t->engine.tune_filter = mode;

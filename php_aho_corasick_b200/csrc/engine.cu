@@ -556,7 +556,6 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     a.range_lo = range_lo_;
     a.n_used = n_used_;
     a.init_state = (init_state == ROOT_STATE) ? root_ : init_state;
-    a.prefetch = tune_prefetch;
     a.tile_status = d_tiles_;
     a.counters = d_counters_;
     a.first_end = d_first_;

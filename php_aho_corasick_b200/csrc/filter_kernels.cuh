@@ -444,7 +444,7 @@ __device__ __noinline__ ItemEvents walk_item_slow(const ScanArgs &a, uint32_t s_
     sc.lo = a.range_lo; sc.n_used = a.n_used;
     sc.final_bound = a.final_bound; sc.readable = a.readable;
     sc.out = a.out; sc.cap = a.capacity;
-    sc.found = false; sc.cnt = 0; sc.obase = obase; sc.have_pend = false; sc.prefetch = 0;
+    sc.found = false; sc.cnt = 0; sc.obase = obase; sc.have_pend = false;
     sc.e0p = sc.e0s = sc.e1p = sc.e1s = 0;
 
     if (item != ITEM_NONE && (item & ITEM_SPAN)) {

@@ -54,7 +54,6 @@ struct ScanArgs {
     uint32_t range_lo;            // RANGE kernels: class = min(byte - range_lo, n_used)
     uint32_t n_used;
     uint32_t init_state;          // state at offset 0 of haystack 0 (root, or the keep=1 continuation)
-    uint32_t prefetch;            // ac_scan_kernel: bytes ahead at which text lines are requested into L2 (0: off)
     uint2 *out;                   // events {end offset in stream, state}
     uint32_t capacity;            // events that fit in `out`
     unsigned long long *tile_status;  // n_tiles words, zeroed before launch
@@ -244,7 +243,6 @@ struct Scanner {
     uint32_t s_tab;          // shared-window byte address of row `win_lo`, minus win_lo*row_bytes
     uint32_t s_cls;          // shared-window byte address of the 256-byte class map
     uint32_t ncls, row_bytes, win_lo, win_rows, lo, n_used, final_bound, readable;
-    uint32_t prefetch;       // bytes ahead of the walk at which a line is requested into L2 (0: off)
 
     // per-thread event record
     uint32_t cnt;
@@ -413,10 +411,6 @@ struct Scanner {
                 while (true) {
                     uint4 v3 = v2;
                     if (i + 64 <= readable) v3 = ld_text16(text + i + 48);
-                    // every 128-byte line: ask L2 for the line `prefetch` bytes ahead (three 16-byte groups in registers
-                    // cover ~1.5 us of walking, about one trip to HBM: the text loads showed up as long-scoreboard stalls)
-                    if (REPORT && EMIT == 0 && prefetch && (i & 127u) == 0u && i + prefetch < readable)
-                        asm volatile("prefetch.global.L2 [%0];" :: "l"(text + i + prefetch));
                     s = walk_group<REPORT, EMIT>(s, v0, i);
                     i += 16;
                     if (REPORT && FIRST && found) return s;
@@ -502,7 +496,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_kernel(const ScanArgs
     sc.lo = a.range_lo; sc.n_used = a.n_used;
     sc.final_bound = a.final_bound; sc.readable = a.readable;
     sc.out = a.out; sc.cap = a.capacity;
-    sc.prefetch = a.prefetch;
 
     const uint32_t prior = a.counters[1];    // events of earlier launches in this call (stream-ordered)
 
@@ -615,7 +608,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) ac_small_kernel(const SmallA
     sc.lo = a.range_lo; sc.n_used = a.n_used;
     sc.final_bound = a.final_bound; sc.readable = a.readable;
     sc.out = a.out; sc.cap = a.capacity;
-    sc.found = false; sc.cnt = 0; sc.have_pend = false; sc.prefetch = 0;
+    sc.found = false; sc.cnt = 0; sc.have_pend = false;
     sc.e0p = sc.e0s = sc.e1p = sc.e1s = 0;
 
     const uint32_t cs = min(tid * a.chunk, a.total), ce = min(cs + a.chunk, a.total);

@@ -47,11 +47,6 @@ def main():
                     a.set_tuning(chunk, 0)
                     split(f"cfg2 1 GiB full walk chunk={chunk}", a, scan, reps=3)
                 a.set_tuning(0, 0)
-                import ctypes as C
-                for pf in (128, 256, 384, 512, 1024):
-                    a.L.acb200_set_prefetch(C.c_void_p(a.h), C.c_uint32(pf))
-                    split(f"cfg2 1 GiB full walk, L2 prefetch {pf} B ahead", a, scan, reps=3)
-                a.L.acb200_set_prefetch(C.c_void_p(a.h), C.c_uint32(0))
                 a.set_filter(0)
             del d
     if "cfg3" in which:
