@@ -863,6 +863,12 @@ int acb200_set_tuning(AC_TRIE_t *t, uint32_t chunk_bytes, uint32_t smem_table_by
     return 0;
 }
 
+int acb200_set_tma(AC_TRIE_t *t, int mode)
+{
+    t->engine.tune_tma = mode;
+    return 0;
+}
+
 int acb200_set_filter(AC_TRIE_t *t, int mode)
 {
     t->engine.tune_filter = mode;

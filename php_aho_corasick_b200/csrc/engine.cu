@@ -43,6 +43,32 @@ void set_preferred_device(int d) { g_device = d; }
     } while (0)
 
 static inline cudaStream_t S(void *p) { return static_cast<cudaStream_t>(p); }
+
+// 2-D view of a haystack stream for the TMA unit: rows of `chunk` bytes (row r = slice r), boxes of TMA_BOX_BYTES x 32 rows.
+// cuTensorMapEncodeTiled is a driver-API call; the library links the runtime only, so it is looked up once.
+static bool make_slice_map(CUtensorMap *map, const void *text, uint32_t chunk, uint32_t rows)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<encode_fn>(fn);
+        else cudaGetLastError();
+    }
+    if (!encode) return false;
+    const cuuint64_t dims[2] = {chunk, rows};
+    const cuuint64_t strides[1] = {chunk};                    // bytes between rows
+    const cuuint32_t box[2] = {TMA_BOX_BYTES, 32};
+    const cuuint32_t elem[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(text), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 static inline cudaEvent_t EV(void *p) { return static_cast<cudaEvent_t>(p); }
 
 // ------------------------------------------------------------ peer memory --
@@ -282,6 +308,10 @@ bool Engine::build(const FlatAutomaton &f, int dev, const Engine *table_src)
     CU_OK((set_smem_attr<uint32_t, true, true>(dyn)));
     CU_OK((set_smem_attr<uint32_t, false, false>(dyn)));
     CU_OK((set_smem_attr<uint32_t, false, true>(dyn)));
+    CU_OK(cudaFuncSetAttribute(ac_scan_tma_kernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    CU_OK(cudaFuncSetAttribute(ac_scan_tma_kernel<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    CU_OK(cudaFuncSetAttribute(ac_scan_tma_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    CU_OK(cudaFuncSetAttribute(ac_scan_tma_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
 
     // output lists for the device-side hit expansion
     {
@@ -521,8 +551,15 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
         }
     }
 
+    // Text through the TMA unit (ac_scan_tma_kernel) where its box fits: patterns of up to 33 bytes (the warm-up is one
+    // box), slices that are a whole number of boxes, enough complete rows to matter.  tune_tma: 0 auto, 1 on, -1 off.
+    CUtensorMap tmap;
+    const uint32_t full_rows = total / chunk;
+    const bool tma = tune_tma >= 0 && !first_only && halo_ <= TMA_BOX_BYTES && chunk % TMA_BOX_BYTES == 0 && chunk >= 2 * TMA_BOX_BYTES &&
+                     full_rows >= 64 && (((uintptr_t)d_text) & 15u) == 0 && make_slice_map(&tmap, d_text, chunk, full_rows);
+
     // Hot window in shared memory: B shallowest finals + A shallowest non-finals (root first).
-    const int dyn_max = max_smem_optin_ - 2048;
+    const int dyn_max = max_smem_optin_ - 2048 - (tma ? (int)TMA_RING_BYTES + 768 : 0);
     size_t smem_budget = (size_t)dyn_max;
     if (tune_smem_bytes) smem_budget = std::min<size_t>(smem_budget, tune_smem_bytes);
     uint32_t win_lo = 0, win_rows = 0;
@@ -574,7 +611,16 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
         CU_OK(cudaMemsetAsync(d_counters_, 0, 32, st));
         if (first_only) CU_OK(cudaMemsetAsync(d_first_, 0xff, n_hay * sizeof(uint32_t), st));
         CU_OK(cudaEventRecord(EV(ev_[0]), st));
-        if (entry_bytes_ == 2) {
+        if (tma) {
+            const size_t smem_tma = smem_bytes + TMA_RING_BYTES + 128;      // + alignment slack of the ring
+            if (entry_bytes_ == 2) {
+                if (range_map_) ac_scan_tma_kernel<uint16_t, true><<<grid, SCAN_THREADS, smem_tma, st>>>(a, tmap);
+                else ac_scan_tma_kernel<uint16_t, false><<<grid, SCAN_THREADS, smem_tma, st>>>(a, tmap);
+            } else {
+                if (range_map_) ac_scan_tma_kernel<uint32_t, true><<<grid, SCAN_THREADS, smem_tma, st>>>(a, tmap);
+                else ac_scan_tma_kernel<uint32_t, false><<<grid, SCAN_THREADS, smem_tma, st>>>(a, tmap);
+            }
+        } else if (entry_bytes_ == 2) {
             if (range_map_) { if (first_only) launch_kernel<uint16_t, true, true>(a, grid, smem_bytes, st); else launch_kernel<uint16_t, true, false>(a, grid, smem_bytes, st); }
             else            { if (first_only) launch_kernel<uint16_t, false, true>(a, grid, smem_bytes, st); else launch_kernel<uint16_t, false, false>(a, grid, smem_bytes, st); }
         } else {

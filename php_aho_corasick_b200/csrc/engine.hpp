@@ -82,6 +82,7 @@ public:
     ACB200_INFO_t info{};
     uint32_t tune_chunk = 0;
     uint32_t tune_smem_bytes = 0;
+    int tune_tma = 0;              // full walk: 0 auto / 1 haystack text staged by the TMA unit (ac_scan_tma_kernel), -1 plain loads
     int tune_filter = 0;           // 0 auto, 1 always use the gram prefilter when the dictionary allows, -1 never
     int tune_direct = 0;           // 0 auto (= 1), 1 direct verification of flagged words inside the walk kernel,
                                    // -1 every flagged word is walked

@@ -24,6 +24,7 @@
 #pragma once
 
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace acb200 {
@@ -549,6 +550,197 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_kernel(const ScanArgs
 
         const unsigned long long excl = tile_lookback(a, tile, total, prior, lane);
 
+        if (sc.cnt) {
+            const uint32_t off = (uint32_t)excl + (incl - sc.cnt);
+            if (sc.cnt <= 2) {
+                if (off < a.capacity) a.out[off] = make_uint2(sc.e0p, sc.e0s);
+                if (sc.cnt == 2 && off + 1 < a.capacity) a.out[off + 1] = make_uint2(sc.e1p, sc.e1s);
+            } else if (off < a.capacity) {
+                // dense slice: walk it again from the saved entry state and write in place
+                const bool very_dense = sc.cnt > DENSE_PAIRED_MIN;
+                sc.obase = off;
+                sc.cnt = 0;
+                sc.have_pend = false;
+                if (very_dense) { scan_slice<2>(a, sc, s_cs, h, cs, ce); sc.flush_pending(); }
+                else scan_slice<1>(a, sc, s_cs, h, cs, ce);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------- full walk, text by TMA --
+//
+// ac_scan_kernel is bound by the L1TEX data stage, which its two kinds of loads share: the table lookups (one LDS of
+// 32 random entries = 4.1 wavefronts per haystack byte-step of a warp) and the text (one LDG.128 per lane per 16 bytes,
+// 32 lanes in 32 different lines = 42 wavefronts per load, 2.6 per byte-step — 39 % of the stage, ncu).  One more
+// divergent request per 128 bytes (an L2 prefetch) made the kernel 12 % slower: that pipe is the limit, not latency.
+// This variant takes the text out of it.  The stream is described to the TMA unit as a 2-D array of rows of `chunk`
+// bytes — row r is slice r — and ONE cp.async.bulk.tensor per warp fetches a box of 32 bytes x 32 rows: the next 32
+// bytes of all 32 slices of the warp's tile, laid down in shared memory lane after lane.  Lanes read their 32 bytes
+// with two conflict-free LDS.128 (8 wavefronts per 32 byte-steps instead of 84), a two-stage ring per warp with one
+// mbarrier per stage keeps one box in flight (a warp needs ~4 us for 32 byte-steps, an HBM trip takes 1).  The ring
+// costs 64 KB of the table window.  Tiles the box cannot serve — a haystack boundary inside a slice, a ragged last
+// tile, patterns longer than 32 bytes (the warm-up must fit one box) — take the loads of ac_scan_kernel.
+constexpr uint32_t TMA_BOX_BYTES = 32;                        // bytes per slice and box
+constexpr uint32_t TMA_STAGE_BYTES = 32 * TMA_BOX_BYTES;      // one box: 32 slices
+constexpr uint32_t TMA_STAGES = 2;
+constexpr uint32_t TMA_RING_BYTES = (SCAN_THREADS / 32) * TMA_STAGES * TMA_STAGE_BYTES;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    // (bounded: a box that never arrives — a tensor map the driver rejected would be one — must abort the launch, not hang it)
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spins > (1u << 22)) __trap();
+    }
+}
+// box (x bytes, y rows) of the 2-D view of the stream -> shared memory at dst, completion counted on bar
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const void *tmap, int32_t x, int32_t y, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+template <typename E, bool RANGE>
+__global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_tma_kernel(const ScanArgs a, const __grid_constant__ CUtensorMap tmap)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint8_t s_cls[256];
+    __shared__ __align__(8) unsigned long long s_bar[SCAN_THREADS / 32][TMA_STAGES];
+    // the ring first, on a 128-byte boundary (what the TMA unit wants of its destination), then the table window
+    const uint32_t ring_base = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 127u) & ~127u;
+    E *s_tab = reinterpret_cast<E *>(smem_raw + (ring_base - (uint32_t)__cvta_generic_to_shared(smem_raw)) + TMA_RING_BYTES);
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    const E *gtab = static_cast<const E *>(a.table);
+    const uint32_t ring = ring_base + warp * (TMA_STAGES * TMA_STAGE_BYTES);
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[warp][0]);
+
+    stage_window<E>(s_tab, gtab, a.win_lo, a.win_rows, a.ncls, tid, SCAN_THREADS);
+    if (tid < 256) s_cls[tid] = a.cls_map[tid];
+    if (lane == 0) {
+#pragma unroll
+        for (uint32_t st = 0; st < TMA_STAGES; ++st) mbar_init(bar0 + st * 8u, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();      // the only CTA-wide barrier: from here on warps run independently
+
+    Scanner<E, RANGE, false> sc;
+    sc.gtab = gtab; sc.text = a.text;
+    sc.ncls = a.ncls; sc.row_bytes = a.ncls * (uint32_t)sizeof(E);
+    sc.win_lo = a.win_lo; sc.win_rows = a.win_rows;
+    {
+        const uint32_t t0 = (uint32_t)__cvta_generic_to_shared(s_tab) - a.win_lo * sc.row_bytes;
+        const uint32_t c0 = (uint32_t)__cvta_generic_to_shared(s_cls);
+        asm volatile("mov.u32 %0, %1;" : "=r"(sc.s_tab) : "r"(t0));
+        asm volatile("mov.u32 %0, %1;" : "=r"(sc.s_cls) : "r"(c0));
+    }
+    sc.lo = a.range_lo; sc.n_used = a.n_used;
+    sc.final_bound = a.final_bound; sc.readable = a.readable;
+    sc.out = a.out; sc.cap = a.capacity;
+    sc.have_pend = false;
+
+    const uint32_t prior = a.counters[1];
+    const uint32_t n_boxes = a.chunk / TMA_BOX_BYTES;         // boxes per tile (the warm-up box not counted)
+    uint32_t phase = 0;                                       // bit st = parity the next wait on stage st expects
+
+    while (true) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(&a.counters[0], 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= a.n_tiles) break;
+
+        const uint32_t row0 = a.chunk_begin + tile * 32u;
+        const uint32_t chunk_id = row0 + lane;
+        const bool active = chunk_id < a.chunk_end;
+        uint32_t cs = 0, ce = 0, h = 0, s_cs = 0, hb = 0;
+        sc.cnt = 0; sc.found = false;
+        bool boxed = active;
+        if (active) {
+            cs = chunk_id * a.chunk;
+            ce = min(cs + a.chunk, a.total);
+            h = find_haystack(a, cs);
+            hb = hay_begin(a, h);
+            // the box serves a slice that is complete, lies inside one haystack and starts either at its haystack's
+            // first byte (no warm-up) or at least one box behind it (the warm-up is the 32 bytes before the slice)
+            boxed = ce - cs == a.chunk && hay_end(a, h) >= ce && (cs == hb || cs - hb >= TMA_BOX_BYTES);
+        }
+        boxed = __all_sync(0xffffffffu, boxed);
+
+        if (boxed) {
+            // box q = 0: the 32 bytes before every slice (the tail of the rows above); q = 1 .. n_boxes: the slices
+            auto issue = [&](uint32_t q) {
+                if (lane == 0) {
+                    const uint32_t st = q & 1u;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the lanes' reads of this stage are over
+                    mbar_expect_tx(bar0 + st * 8u, TMA_STAGE_BYTES);
+                    if (q == 0) tma_load_box(ring + st * TMA_STAGE_BYTES, &tmap, (int32_t)(a.chunk - TMA_BOX_BYTES), (int32_t)row0 - 1, bar0 + st * 8u);
+                    else tma_load_box(ring + st * TMA_STAGE_BYTES, &tmap, (int32_t)((q - 1u) * TMA_BOX_BYTES), (int32_t)row0, bar0 + st * 8u);
+                }
+            };
+            issue(0);
+            issue(1);
+            uint32_t s = a.root;
+            for (uint32_t q = 0; q <= n_boxes; ++q) {
+                const uint32_t st = q & 1u;
+                mbar_wait(bar0 + st * 8u, (phase >> st) & 1u);
+                phase ^= 1u << st;
+                const uint32_t at = ring + st * TMA_STAGE_BYTES + lane * TMA_BOX_BYTES;
+                const uint4 v0 = lds128(at), v1 = lds128(at + 16u);
+                __syncwarp();
+                if (q + 2u <= n_boxes) issue(q + 2u);
+                if (q == 0) {
+                    if (cs == hb) s = (h == 0) ? a.init_state : a.root;
+                    else {
+                        s = sc.template walk_group<false, 0>(a.root, v0, cs - 32u);
+                        s = sc.template walk_group<false, 0>(s, v1, cs - 16u);
+                    }
+                    s_cs = s;
+                } else {
+                    const uint32_t i = cs + (q - 1u) * TMA_BOX_BYTES;
+                    s = sc.template walk_group<true, 0>(s, v0, i);
+                    s = sc.template walk_group<true, 0>(s, v1, i + 16u);
+                }
+            }
+            if (ce == a.total) a.counters[2] = s;
+        } else if (active) {
+            uint32_t ws = (cs - hb > a.halo) ? ((cs - a.halo) & ~15u) : hb;
+            if (ws < hb) ws = hb;
+            uint32_t s = (ws == hb && h == 0) ? a.init_state : a.root;
+            s = sc.template walk<false, 0>(s, ws, cs);
+            s_cs = s;
+            s = scan_slice<0>(a, sc, s, h, cs, ce);
+            if (ce == a.total) a.counters[2] = s;
+        }
+        __syncwarp();
+
+        // warp prefix of the per-lane event counts
+        uint32_t incl = sc.cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const unsigned long long excl = tile_lookback(a, tile, total, prior, lane);
         if (sc.cnt) {
             const uint32_t off = (uint32_t)excl + (incl - sc.cnt);
             if (sc.cnt <= 2) {

@@ -47,6 +47,14 @@ def main():
                     a.set_tuning(chunk, 0)
                     split(f"cfg2 1 GiB full walk chunk={chunk}", a, scan, reps=3)
                 a.set_tuning(0, 0)
+                import ctypes as C
+                for mode in (-1, 1):
+                    a.L.acb200_set_tma(C.c_void_p(a.h), C.c_int(mode))
+                    for chunk in (0, 256, 1024):
+                        a.set_tuning(chunk, 0)
+                        split(f"cfg2 1 GiB full walk tma={mode} chunk={chunk}", a, scan, reps=3)
+                a.set_tuning(0, 0)
+                a.L.acb200_set_tma(C.c_void_p(a.h), C.c_int(0))
                 a.set_filter(0)
             del d
     if "cfg3" in which:

@@ -216,3 +216,36 @@ def test_one_cta_path_for_short_texts_equals_oracle():
     r = d.search(hay)
     assert [p for p, _ in whole] == sorted(set(int(x) for x in r["pos"]))
     a.release()
+
+
+def test_text_staged_by_the_tma_unit_equals_plain_loads_and_oracle():
+    """ac_scan_tma_kernel (haystack text fetched as 32-byte x 32-slice boxes by the TMA unit into a per-warp shared-memory
+    ring) against ac_scan_kernel (per-lane 16-byte loads) and the oracle: equal-length batches whose slices the box can
+    serve, ragged batches where most tiles fall back, one long haystack (warm-up box from the row above), dense events."""
+    import ctypes as C
+    rng = np.random.default_rng(41)
+    needles, hay, off = W.cfg2(n_hay=2048, hay_len=8192, planted_per_hay=8, seed=17)
+    short = [bytes(rng.integers(97, 103, size=int(rng.integers(2, 33))).astype(np.uint8)) for _ in range(500)] + [b"ab", b"a" * 33]
+    cases = [(needles, hay, off), (needles, hay, np.array([0, hay.size], dtype=np.uint64)), (short, hay, off)]
+    lens = [5, 40_000, 0, 8192, 1_000_003, 64, 3_000_000]
+    rag = np.concatenate([rng.integers(97, 103, size=n, dtype=np.uint8) for n in lens])
+    rag[50_000:50_400] = ord("a")                               # a dense burst
+    roff = np.zeros(len(lens) + 1, dtype=np.uint64); roff[1:] = np.cumsum(lens)
+    cases.append((short, rag, roff))
+    for pats, flat, offs in cases:
+        a = build([pats])
+        a.set_filter(-1)
+        got = {}
+        for mode in (-1, 1):
+            a.L.acb200_set_tma(C.c_void_p(a.h), C.c_int(mode))
+            for chunk in (0, 64, 256):
+                a.set_tuning(chunk, 0)
+                got[(mode, chunk)] = a.search_events(flat, offs)
+                assert a.stats().filtered == 0
+        ref = got[(-1, 0)]
+        for k, ev in got.items():
+            assert np.array_equal(ev, ref), k
+        n = len(offs) - 1
+        if flat.size <= 20_000_000 and n <= 16:
+            assert_same(a, ref, n, oracle_hits([pats], split(flat, offs)))
+        a.release()
