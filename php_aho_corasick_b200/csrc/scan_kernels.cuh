@@ -251,6 +251,7 @@ struct Scanner {
     // EMIT mode
     uint2 *out;
     uint32_t obase, cap;
+    uint32_t report_from;    // count pass: events that end at or before this stream offset belong to the warm-up
     uint2 pend;              // event at an even output index, waiting to be stored together with its successor
     bool have_pend;
 
@@ -289,6 +290,9 @@ struct Scanner {
     template <int EMIT>
     __device__ __forceinline__ void hit(uint32_t pos, uint32_t s)
     {
+        // (the warm-up before a slice runs through the SAME unrolled code as the slice — one copy less of the 16-step
+        // switch in the instruction cache, which this kernel stalls on — and what it finds does not count)
+        if (EMIT == 0 && pos <= report_from) return;
         if (FIRST) {
             if (found) return;
             found = true;
@@ -526,7 +530,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_kernel(const ScanArgs
                 uint32_t ws = (cs - hb > a.halo) ? ((cs - a.halo) & ~15u) : hb;
                 if (ws < hb) ws = hb;
                 uint32_t s = (ws == hb && h == 0) ? a.init_state : a.root;
-                s = sc.template walk<false, false>(s, ws, cs);
+                sc.report_from = cs;
+                s = sc.template walk<true, 0>(s, ws, cs);
                 s_cs = s;
                 s = scan_slice<0>(a, sc, s, h, cs, ce);
                 if (ce == a.total) a.counters[2] = s;
@@ -699,6 +704,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_tma_kernel(const Scan
             issue(0);
             issue(1);
             uint32_t s = a.root;
+            sc.report_from = cs;
             for (uint32_t q = 0; q <= n_boxes; ++q) {
                 const uint32_t st = q & 1u;
                 mbar_wait(bar0 + st * 8u, (phase >> st) & 1u);
@@ -707,25 +713,21 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_tma_kernel(const Scan
                 const uint4 v0 = lds128(at), v1 = lds128(at + 16u);
                 __syncwarp();
                 if (q + 2u <= n_boxes) issue(q + 2u);
-                if (q == 0) {
-                    if (cs == hb) s = (h == 0) ? a.init_state : a.root;
-                    else {
-                        s = sc.template walk_group<false, 0>(a.root, v0, cs - 32u);
-                        s = sc.template walk_group<false, 0>(s, v1, cs - 16u);
-                    }
-                    s_cs = s;
-                } else {
-                    const uint32_t i = cs + (q - 1u) * TMA_BOX_BYTES;
-                    s = sc.template walk_group<true, 0>(s, v0, i);
-                    s = sc.template walk_group<true, 0>(s, v1, i + 16u);
-                }
+                // ONE copy of the unrolled 16-step switch serves the warm-up box and the slice's boxes, both halves
+                const uint32_t i = cs + q * TMA_BOX_BYTES - TMA_BOX_BYTES;
+                if (q != 0 || cs != hb) {
+#pragma unroll 1
+                    for (uint32_t g = 0; g < 2u; ++g) s = sc.template walk_group<true, 0>(s, g ? v1 : v0, i + 16u * g);
+                } else s = (h == 0) ? a.init_state : a.root;
+                if (q == 0) s_cs = s;
             }
             if (ce == a.total) a.counters[2] = s;
         } else if (active) {
             uint32_t ws = (cs - hb > a.halo) ? ((cs - a.halo) & ~15u) : hb;
             if (ws < hb) ws = hb;
             uint32_t s = (ws == hb && h == 0) ? a.init_state : a.root;
-            s = sc.template walk<false, 0>(s, ws, cs);
+            sc.report_from = cs;
+            s = sc.template walk<true, 0>(s, ws, cs);
             s_cs = s;
             s = scan_slice<0>(a, sc, s, h, cs, ce);
             if (ce == a.total) a.counters[2] = s;
@@ -807,7 +809,8 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) ac_small_kernel(const SmallA
     uint32_t s_cs = a.root;
     if (cs < ce) {
         const uint32_t ws = (cs > a.halo) ? ((cs - a.halo) & ~15u) : 0u;
-        s_cs = sc.template walk<false, 0>(ws == 0u ? a.init_state : a.root, ws, cs);
+        sc.report_from = cs;
+        s_cs = sc.template walk<true, 0>(ws == 0u ? a.init_state : a.root, ws, cs);
         const uint32_t s_end = sc.template walk<true, 0>(s_cs, cs, ce);
         if (ce == a.total) a.hdr[1] = s_end;
     }

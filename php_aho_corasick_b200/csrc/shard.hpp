@@ -2,8 +2,11 @@
 // over the GPUs of the box.  Pure host arithmetic, no CUDA: tested on the CPU through acb200_plan_slabs().
 //
 // The haystacks of a call form one virtual byte stream (haystack i = stream bytes [off[i], off[i+1])).  The
-// stream is cut into one contiguous range per device, balanced by bytes, and every range into slabs of at most
-// `slab_bytes`.  A cut may fall anywhere — also inside a haystack: such a slab carries the (Lmax-1) bytes before
+// stream is cut into slabs of at most `slab_bytes` — a whole number of rounds over the devices — and slab i goes
+// to device i mod n_dev: every device works on the same region of the stream at the same time, so the calling
+// thread, which must run the callbacks in stream order, replays slab i while the devices are busy with the
+// next round (one contiguous range per device left 7/8 of an eight-GPU call's events to be replayed after the
+// last copy had finished: measured 74.6 ms per 8 GiB of which 28 ms were that tail).  A cut may fall anywhere — also inside a haystack: such a slab carries the (Lmax-1) bytes before
 // the cut in front of its own bytes ("halo"), the device walks them from the root like any haystack start, and
 // the host drops the events that end inside the halo (they belong to the slab before).  After Lmax-1 bytes the
 // state reached from the root equals the state of an uninterrupted walk — the argument of scan_kernels.cuh, and
@@ -32,50 +35,43 @@ inline std::vector<SlabPlan> plan_slabs(const uint64_t *off, size_t n, uint32_t 
 {
     std::vector<SlabPlan> out;
     const uint64_t total = n ? off[n] : 0;
-    if (total == 0 || n_dev < 1) return out;
+    if (total == 0 || n_dev < 1 || slab_bytes == 0) return out;
+    // as many slabs as the size limit asks for, at least one per device, a whole number of rounds over the devices
+    uint64_t k = std::max<uint64_t>((total + slab_bytes - 1) / slab_bytes, (uint64_t)n_dev);
+    k = (k + (uint64_t)n_dev - 1) / (uint64_t)n_dev * (uint64_t)n_dev;
+    k = std::min(k, total);
+    const uint64_t nominal = total / k;
     // a cut lands on the nearest haystack boundary when one is close (no halo, equal-length batches stay uniform)
-    auto snap = [&](uint64_t t, uint64_t lo, uint64_t hi) -> uint64_t {
+    auto snap = [&](uint64_t t, uint64_t lo) -> uint64_t {
         if (t <= lo) return lo;
-        if (t >= hi) return hi;
+        if (t >= total) return total;
         const uint64_t *p = std::lower_bound(off, off + n + 1, t);          // first boundary >= t
-        uint64_t best = t, dist = slab_bytes / 8 + 1;
-        if (p != off + n + 1 && *p - t < dist && *p > lo && *p < hi) { best = *p; dist = *p - t; }
-        if (p != off) { const uint64_t q = *(p - 1); if (t - q < dist && q > lo && q < hi) best = q; }
+        uint64_t best = t, dist = nominal / 8 + 1;
+        if (p != off + n + 1 && *p - t < dist && *p > lo && *p < total) { best = *p; dist = *p - t; }
+        if (p != off) { const uint64_t q = *(p - 1); if (t - q < dist && q > lo && q < total) best = q; }
         return best;
     };
-    uint64_t dev_lo = 0;
-    for (int d = 0; d < n_dev; ++d) {
-        const uint64_t dev_hi = (d == n_dev - 1) ? total : snap(total / n_dev * (d + 1) + total % n_dev * (d + 1) / n_dev, dev_lo, total);
-        const uint64_t len = dev_hi - dev_lo;
-        if (len == 0) { dev_lo = dev_hi; continue; }
-        const uint64_t k = (len + slab_bytes - 1) / slab_bytes;
-        uint64_t lo = dev_lo;
-        for (uint64_t s = 0; s < k && lo < dev_hi; ++s) {
-            uint64_t hi = (s == k - 1) ? dev_hi : snap(dev_lo + len / k * (s + 1), lo, dev_hi);
-            if (hi - lo > slab_bytes + slab_bytes / 8) hi = lo + slab_bytes;      // snapping never grows a slab beyond 9/8
-            if (hi == lo) continue;
-            SlabPlan p;
-            p.b0 = lo; p.b1 = hi;
-            p.h_first = (size_t)(std::upper_bound(off, off + n + 1, lo) - off) - 1;     // off[h] <= lo < off[h+1]
-            p.h_end = (size_t)(std::lower_bound(off, off + n + 1, hi) - off);           // haystacks h < h_end start before hi
-            p.halo = (uint32_t)std::min<uint64_t>(halo_max, lo - off[p.h_first]);
-            p.device_slot = d;
-            out.push_back(p);
-            lo = hi;
-        }
-        // (a range whose last snapped slab stopped short: the remainder)
-        while (lo < dev_hi) {
-            const uint64_t hi = std::min(dev_hi, lo + slab_bytes);
-            SlabPlan p;
-            p.b0 = lo; p.b1 = hi;
-            p.h_first = (size_t)(std::upper_bound(off, off + n + 1, lo) - off) - 1;
-            p.h_end = (size_t)(std::lower_bound(off, off + n + 1, hi) - off);
-            p.halo = (uint32_t)std::min<uint64_t>(halo_max, lo - off[p.h_first]);
-            p.device_slot = d;
-            out.push_back(p);
-            lo = hi;
-        }
-        dev_lo = dev_hi;
+    auto push = [&](uint64_t lo, uint64_t hi) {
+        SlabPlan p;
+        p.b0 = lo; p.b1 = hi;
+        p.h_first = (size_t)(std::upper_bound(off, off + n + 1, lo) - off) - 1;     // off[h] <= lo < off[h+1]
+        p.h_end = (size_t)(std::lower_bound(off, off + n + 1, hi) - off);           // haystacks h < h_end start before hi
+        p.halo = (uint32_t)std::min<uint64_t>(halo_max, lo - off[p.h_first]);
+        p.device_slot = (int)(out.size() % (size_t)n_dev);
+        out.push_back(p);
+    };
+    uint64_t lo = 0;
+    for (uint64_t s = 0; s < k && lo < total; ++s) {
+        uint64_t hi = (s == k - 1) ? total : snap(total / k * (s + 1) + total % k * (s + 1) / k, lo);
+        if (hi - lo > slab_bytes + slab_bytes / 8) hi = lo + slab_bytes;          // snapping never grows a slab beyond 9/8
+        if (hi == lo) continue;
+        push(lo, hi);
+        lo = hi;
+    }
+    while (lo < total) {                                                          // (what a clamped last slab left over)
+        const uint64_t hi = std::min(total, lo + slab_bytes);
+        push(lo, hi);
+        lo = hi;
     }
     return out;
 }
