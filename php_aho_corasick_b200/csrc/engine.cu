@@ -496,7 +496,10 @@ uint32_t Engine::pick_chunk(uint64_t total) const
 void Engine::window_for(size_t smem_budget, uint32_t *win_lo, uint32_t *win_rows) const
 {
     const size_t row_bytes = (size_t)ncls_ * entry_bytes_;
-    const uint64_t rows_fit = smem_budget / row_bytes;
+    // one row of the budget is the staged window's sink row; window-relative ids must fit an entry
+    uint64_t rows_fit = smem_budget / row_bytes;
+    rows_fit = rows_fit ? rows_fit - 1 : 0;
+    if (entry_bytes_ == 2) rows_fit = std::min<uint64_t>(rows_fit, 65534);
     const uint64_t n_final = final_bound_ - 1, n_plain = n_rows_ - final_bound_;
     uint64_t B = std::min<uint64_t>(n_final, rows_fit / 4);
     uint64_t A = std::min<uint64_t>(n_plain, rows_fit - B);
@@ -555,7 +558,9 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     // box), slices that are a whole number of boxes, enough complete rows to matter.  tune_tma: 0 auto, 1 on, -1 off.
     CUtensorMap tmap;
     const uint32_t full_rows = total / chunk;
-    const bool tma = tune_tma >= 0 && !first_only && halo_ <= TMA_BOX_BYTES && chunk % TMA_BOX_BYTES == 0 && chunk >= 2 * TMA_BOX_BYTES &&
+    // (automatic: only after a call with few events — the ring takes 64 KB from the table window, and a text full of
+    // needles leaves a smaller window that often: 1 GiB of config 2, one needle per KiB 1.41 vs 1.27 ms, none 0.73 vs 0.98 ms)
+    const bool tma = (tune_tma > 0 || (tune_tma == 0 && last_density_ < 1.0 / 8192)) && !first_only && halo_ <= TMA_BOX_BYTES && chunk % TMA_BOX_BYTES == 0 && chunk >= 2 * TMA_BOX_BYTES &&
                      full_rows >= 64 && (((uintptr_t)d_text) & 15u) == 0 && make_slice_map(&tmap, d_text, chunk, full_rows);
 
     // Hot window in shared memory: B shallowest finals + A shallowest non-finals (root first).
@@ -565,7 +570,7 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     uint32_t win_lo = 0, win_rows = 0;
     window_for(smem_budget, &win_lo, &win_rows);
     const size_t row_bytes = (size_t)ncls_ * entry_bytes_;
-    const size_t smem_bytes = std::max<size_t>(16, (size_t)win_rows * row_bytes);
+    const size_t smem_bytes = std::max<size_t>(16, ((size_t)win_rows + 1) * row_bytes);
 
     const uint32_t n_tiles = (n_chunks + 31u) / 32u;
 

@@ -439,7 +439,7 @@ __device__ __noinline__ ItemEvents walk_item_slow(const ScanArgs &a, uint32_t s_
     sc.gtab = static_cast<const E *>(a.table); sc.text = a.text;
     sc.ncls = a.ncls; sc.row_bytes = a.ncls * (uint32_t)sizeof(E);
     sc.win_lo = a.win_lo; sc.win_rows = 0;               // no shared-memory window: every step reads the table
-    sc.s_tab = 0;
+    sc.s_tab = 0; sc.fin_rel = 1;
     sc.s_cls = s_cls_addr;
     sc.lo = a.range_lo; sc.n_used = a.n_used;
     sc.final_bound = a.final_bound; sc.readable = a.readable;

@@ -183,21 +183,23 @@ template <> __device__ __forceinline__ uint32_t lds_entry<uint32_t>(uint32_t add
     return v;
 }
 
-// Stages the window rows of the dense table into shared memory with 16-byte loads; entries whose target
-// lies outside the window become 0.  Called by all threads of the CTA (n_threads of them).
+// Stages the window rows of the dense table into shared memory with 16-byte loads, in WINDOW-RELATIVE ids: row 0 of
+// the copy is a sink (all zeros), row r + 1 is the row of state win_lo + r, and an entry is its target's row number —
+// 0 when the target lies outside the window.  A walk that steps out of the window therefore just stays in the sink,
+// reading valid shared memory, and the hot loop needs no exit in the middle of a 16-byte group.
+// s_tab must hold (win_rows + 1) rows.  Called by all threads of the CTA (n_threads of them).
 template <typename E>
 __device__ __forceinline__ void stage_window(E *s_tab, const E *gtab, uint32_t win_lo, uint32_t win_rows, uint32_t ncls,
                                              uint32_t tid, uint32_t n_threads)
 {
     constexpr uint32_t PER = 16 / sizeof(E);               // entries per 16-byte load
+    auto rel = [&](uint32_t e) -> uint32_t { e -= win_lo; return (e < win_rows) ? e + 1u : 0u; };
+    for (uint32_t idx = tid; idx < ncls; idx += n_threads) s_tab[idx] = (E)0;          // the sink row
+    E *rows = s_tab + ncls;
     const uint32_t win_entries = win_rows * ncls;
     const uint32_t win_first = win_lo * ncls;
     const uint32_t lead = min((PER - (win_first % PER)) % PER, win_entries);   // entries before the first aligned group
-    for (uint32_t idx = tid; idx < lead; idx += n_threads) {
-        uint32_t e = gtab[win_first + idx];
-        if (e - win_lo >= win_rows) e = 0;
-        s_tab[idx] = (E)e;
-    }
+    for (uint32_t idx = tid; idx < lead; idx += n_threads) rows[idx] = (E)rel(gtab[win_first + idx]);
     const uint32_t n_vec = (win_entries - lead) / PER;
     const uint4 *src = reinterpret_cast<const uint4 *>(gtab + win_first + lead);
     for (uint32_t v = tid; v < n_vec; v += n_threads) {
@@ -206,23 +208,14 @@ __device__ __forceinline__ void stage_window(E *s_tab, const E *gtab, uint32_t w
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (sizeof(E) == 2) {
-                uint32_t lo = w[k] & 0xffffu, hi = w[k] >> 16;
-                if (lo - win_lo >= win_rows) lo = 0;
-                if (hi - win_lo >= win_rows) hi = 0;
-                s_tab[lead + v * PER + 2 * k] = (E)lo;
-                s_tab[lead + v * PER + 2 * k + 1] = (E)hi;
+                rows[lead + v * PER + 2 * k] = (E)rel(w[k] & 0xffffu);
+                rows[lead + v * PER + 2 * k + 1] = (E)rel(w[k] >> 16);
             } else {
-                uint32_t e = w[k];
-                if (e - win_lo >= win_rows) e = 0;
-                s_tab[lead + v * PER + k] = (E)e;
+                rows[lead + v * PER + k] = (E)rel(w[k]);
             }
         }
     }
-    for (uint32_t idx = lead + n_vec * PER + tid; idx < win_entries; idx += n_threads) {
-        uint32_t e = gtab[win_first + idx];
-        if (e - win_lo >= win_rows) e = 0;
-        s_tab[idx] = (E)e;
-    }
+    for (uint32_t idx = lead + n_vec * PER + tid; idx < win_entries; idx += n_threads) rows[idx] = (E)rel(gtab[win_first + idx]);
 }
 
 // Per-thread walker.
@@ -230,18 +223,19 @@ __device__ __forceinline__ void stage_window(E *s_tab, const E *gtab, uint32_t w
 // Shared memory holds the rows of a contiguous window of state ids around
 // final_bound: the shallowest final states just below it and the shallowest
 // non-final states (root first) just above it — the rows a scan visits almost
-// all the time.  In that copy every entry whose target lies outside the window
-// is replaced by 0.  Real state ids start at 1 and finals are the ids below
-// final_bound, so ONE compare per byte (entry < final_bound) catches both rare
-// cases: a reporting state (record the event, keep walking) and a step out of
-// the window (finish the 16-byte group on the careful path, which reads true
-// entries from the table in HBM/L2).  The common byte costs
-// {PRMT, class, address, IMAD, LDS, ISETP}.
+// all the time — in window-relative ids (stage_window): 0 is the sink, the
+// reporting states of the window are the ids below fin_rel.  ONE compare per
+// byte (entry < fin_rel) catches both rare cases: a reporting state (record
+// the event, keep walking) and a step out of the window (remember where; the
+// rest of the 16-byte group runs on in the sink and is redone afterwards on
+// the careful path, which reads true entries from the table in HBM/L2).  The
+// common byte costs {PRMT, class, address, IMAD, LDS, ISETP, BRA}.
 template <typename E, bool RANGE, bool FIRST>
 struct Scanner {
     const E *__restrict__ gtab;
     const uint8_t *__restrict__ text;
-    uint32_t s_tab;          // shared-window byte address of row `win_lo`, minus win_lo*row_bytes
+    uint32_t s_tab;          // shared-window byte address of the staged window's sink row (row 0)
+    uint32_t fin_rel;        // window-relative ids below this are the sink (0) and the window's reporting states
     uint32_t s_cls;          // shared-window byte address of the 256-byte class map
     uint32_t ncls, row_bytes, win_lo, win_rows, lo, n_used, final_bound, readable;
 
@@ -270,7 +264,7 @@ struct Scanner {
         return v;
     }
 
-    // fast step: s must be inside the window; returns 0 when the target is outside it
+    // fast step in window-relative ids: s = row number of the state (0 = sink); returns the target's, 0 when it is outside
     __device__ __forceinline__ uint32_t hot_next(uint32_t s, uint32_t b) const
     {
         // t is off the dependent chain; the chain is LDS -> IMAD -> LDS
@@ -335,41 +329,60 @@ struct Scanner {
         const uint32_t word = (j < 8) ? ((j < 4) ? v.x : v.y) : ((j < 12) ? v.z : v.w);
         return (word >> ((j & 3) * 8)) & 0xffu;
     }
+    __device__ __forceinline__ static uint32_t group_byte_dyn(const uint4 &v, int j)
+    {
+        const uint32_t lo = (j & 4) ? v.y : v.x, hi = (j & 4) ? v.w : v.z;
+        return (((j & 8) ? hi : lo) >> ((j & 3) * 8)) & 0xffu;
+    }
 
-    // One 16-byte group.  Bytes are taken on the fast path while the state stays
-    // inside the shared-memory window; a step that leaves it is redone on the
-    // careful path (true entry from the full table) and the fast path is
-    // re-entered — through the switch, at the right byte — as soon as the state
-    // is back inside.
+    // One 16-byte group.  Inside the window the 16 steps are straight-line code in window-relative ids with NO branch:
+    // every step's entry stays in a register and one predicate collects "some entry was below fin_rel" (a reporting
+    // state, or the sink = the walk left the window; the remaining steps then stay in the sink).  Only a group with
+    // such an entry looks at its 16 entries again: events are recorded from the registers, and from the first step
+    // that left the window the compact careful loop below finishes the group (ONE copy per instantiation).
     template <bool REPORT, int EMIT>
     __device__ __forceinline__ uint32_t walk_group(uint32_t s, const uint4 &v, uint32_t i)
     {
-#define ACB_STEP(J, W)                                                                          \
-        case J: {                                                                               \
-            const uint32_t e = hot_next(s, __byte_perm(W, 0, 0x4440 | ((J) & 3)));              \
-            if (e < final_bound) {                                                              \
-                if (e == 0) { j = J; goto careful; }                                            \
-                if (REPORT) hit<EMIT>(i + (J) + 1, e);                                          \
-            }                                                                                   \
-            s = e;                                                                              \
-        }
-        int j = 0;
-        while (j < 16) {
-            if (s - win_lo < win_rows) {
-                switch (j) {
-                    ACB_STEP(0, v.x) ACB_STEP(1, v.x) ACB_STEP(2, v.x) ACB_STEP(3, v.x)
-                    ACB_STEP(4, v.y) ACB_STEP(5, v.y) ACB_STEP(6, v.y) ACB_STEP(7, v.y)
-                    ACB_STEP(8, v.z) ACB_STEP(9, v.z) ACB_STEP(10, v.z) ACB_STEP(11, v.z)
-                    ACB_STEP(12, v.w) ACB_STEP(13, v.w) ACB_STEP(14, v.w) ACB_STEP(15, v.w)
-                }
-                return s;
-            }
-        careful:
-            s = any_next(s, group_byte(v, j));
-            if (REPORT && s < final_bound) hit<EMIT>(i + j + 1, s);
-            ++j;
-        }
+        int j = 0;                                       // first byte of the group the careful loop has to take
+        if (s - win_lo < win_rows) {
+            const uint32_t q_in = s - win_lo + 1u;       // the state's row in the staged window
+            uint32_t e[16];
+            bool rare = false;
+#define ACB_STEP(J, W, P)                                                                       \
+            e[J] = hot_next(P, __byte_perm(W, 0, 0x4440 | ((J) & 3)));                          \
+            rare = rare || (e[J] < fin_rel);
+            ACB_STEP(0, v.x, q_in) ACB_STEP(1, v.x, e[0]) ACB_STEP(2, v.x, e[1]) ACB_STEP(3, v.x, e[2])
+            ACB_STEP(4, v.y, e[3]) ACB_STEP(5, v.y, e[4]) ACB_STEP(6, v.y, e[5]) ACB_STEP(7, v.y, e[6])
+            ACB_STEP(8, v.z, e[7]) ACB_STEP(9, v.z, e[8]) ACB_STEP(10, v.z, e[9]) ACB_STEP(11, v.z, e[10])
+            ACB_STEP(12, v.w, e[11]) ACB_STEP(13, v.w, e[12]) ACB_STEP(14, v.w, e[13]) ACB_STEP(15, v.w, e[14])
 #undef ACB_STEP
+            if (__builtin_expect(!rare, 1)) return e[15] + win_lo - 1u;
+            j = 16;
+            uint32_t prev = q_in;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if (j == 16 && e[k] < fin_rel) {
+                    if (e[k] == 0) { j = k; s = prev + win_lo - 1u; }
+                    else if (REPORT) hit<EMIT>(i + k + 1, e[k] + win_lo - 1u);
+                }
+                prev = e[k];
+            }
+            if (j == 16) return e[15] + win_lo - 1u;
+        }
+        // careful, from byte j on: the window's copy where the state is inside it, the true entry from the full table
+        // where it is not or the step leaves it (a planted needle walks out of the window and drops back within a few bytes)
+#pragma unroll 1
+        for (; j < 16; ++j) {
+            const uint32_t b = group_byte_dyn(v, j);
+            uint32_t e = 0;
+            if (s - win_lo < win_rows) {
+                e = hot_next(s - win_lo + 1u, b);
+                if (e) e += win_lo - 1u;
+            }
+            if (e == 0) e = any_next(s, b);
+            s = e;
+            if (REPORT && s < final_bound) hit<EMIT>(i + j + 1, s);
+        }
         return s;
     }
 
@@ -392,8 +405,9 @@ struct Scanner {
             for (uint32_t j = 0; j < n; ++j, ++i) {
                 const uint32_t b = (w >> (8u * j)) & 0xffu;
                 uint32_t e = 0;
-                if (s - win_lo < win_rows) e = hot_next(s, b);
+                if (s - win_lo < win_rows) e = hot_next(s - win_lo + 1u, b);
                 if (e == 0) e = any_next(s, b);              // outside the window, or leaving it: the true entry
+                else e += win_lo - 1u;
                 s = e;
                 if (s < final_bound) hit<2>(i + 1u, s);
                 if (FIRST && found) return s;
@@ -492,8 +506,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_kernel(const ScanArgs
     sc.gtab = gtab; sc.text = a.text;
     sc.ncls = a.ncls; sc.row_bytes = a.ncls * (uint32_t)sizeof(E);
     sc.win_lo = a.win_lo; sc.win_rows = a.win_rows;
+    sc.fin_rel = (a.final_bound > a.win_lo) ? a.final_bound - a.win_lo + 1u : 1u;
     {   // opaque moves keep the shared-window addresses in registers instead of being rematerialised
-        const uint32_t t0 = (uint32_t)__cvta_generic_to_shared(s_tab) - a.win_lo * sc.row_bytes;
+        const uint32_t t0 = (uint32_t)__cvta_generic_to_shared(s_tab);
         const uint32_t c0 = (uint32_t)__cvta_generic_to_shared(s_cls);
         asm volatile("mov.u32 %0, %1;" : "=r"(sc.s_tab) : "r"(t0));
         asm volatile("mov.u32 %0, %1;" : "=r"(sc.s_cls) : "r"(c0));
@@ -652,8 +667,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_tma_kernel(const Scan
     sc.gtab = gtab; sc.text = a.text;
     sc.ncls = a.ncls; sc.row_bytes = a.ncls * (uint32_t)sizeof(E);
     sc.win_lo = a.win_lo; sc.win_rows = a.win_rows;
+    sc.fin_rel = (a.final_bound > a.win_lo) ? a.final_bound - a.win_lo + 1u : 1u;
     {
-        const uint32_t t0 = (uint32_t)__cvta_generic_to_shared(s_tab) - a.win_lo * sc.row_bytes;
+        const uint32_t t0 = (uint32_t)__cvta_generic_to_shared(s_tab);
         const uint32_t c0 = (uint32_t)__cvta_generic_to_shared(s_cls);
         asm volatile("mov.u32 %0, %1;" : "=r"(sc.s_tab) : "r"(t0));
         asm volatile("mov.u32 %0, %1;" : "=r"(sc.s_cls) : "r"(c0));
@@ -797,7 +813,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) ac_small_kernel(const SmallA
     sc.gtab = static_cast<const E *>(a.table); sc.text = a.text;
     sc.ncls = a.ncls; sc.row_bytes = a.ncls * (uint32_t)sizeof(E);
     sc.win_lo = a.final_bound; sc.win_rows = 0;           // every step reads the true entry (L1 / L2)
-    sc.s_tab = 0;
+    sc.s_tab = 0; sc.fin_rel = 1;
     sc.s_cls = (uint32_t)__cvta_generic_to_shared(s_cls);
     sc.lo = a.range_lo; sc.n_used = a.n_used;
     sc.final_bound = a.final_bound; sc.readable = a.readable;
