@@ -536,7 +536,8 @@ def main():
     also = {}
     if not args.skip_also:
         if world == 1:
-            for name, fn in (("config3_signatures_1GiB", lambda: also_cfg3(torch, dev, peak)),
+            for name, fn in (("config2_full_walk_1GiB", lambda: also_cfg2_full_walk(torch, dev, aut, resident, n_hays, n_events, peak, filtered)),
+                             ("config3_signatures_1GiB", lambda: also_cfg3(torch, dev, peak)),
                              ("config5_adversarial_256MiB", lambda: also_cfg5(torch, dev, peak)),
                              ("literal_benchmark_php_loop", lambda: also_literal(torch, dev, aut, needles))):
                 k, rec = also_record(name, fn)
@@ -595,6 +596,38 @@ def main():
 def _roof(nbytes, kernel_ms, peak):
     ach = nbytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms else 0.0
     return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None}
+
+
+def also_cfg2_full_walk(torch, dev, aut, resident, n_hays, n_events, peak, filtered, steps=5):
+    """The headline batch through the FULL automaton walk (ac_scan_kernel / ac_scan_tma_kernel, what dictionaries with a
+    pattern shorter than 8 bytes get), and a batch of the same shape without planted needles (text that matches
+    nothing keeps every lane in the shared-memory window)."""
+    import ctypes as C
+    from php_aho_corasick_b200 import workloads as W
+    nbytes = n_hays * HAY_LEN
+    rec = {"workload": f"the headline batch ({n_hays} x {HAY_LEN} B, 8 planted needles per haystack) with the prefilter switched off",
+           "bytes": nbytes}
+    aut.set_filter(-1)
+    try:
+        scan = lambda: aut.search_device_uniform(resident.data_ptr(), n_hays, HAY_LEN)[1]
+        r = timed_device_scans(aut, torch, scan, steps)
+        k_ms = r["kernel_ms"] / steps
+        rec.update({"kernel_ms": k_ms, "ms_per_step": r["ms_per_step"], "GBps": nbytes / (r["ms_per_step"] * 1e-3) / 1e9,
+                    "roofline": _roof(nbytes, k_ms, peak), "events": int(r["events"]),
+                    "parity": {"checked": True, "ok": int(r["events"]) == int(n_events),
+                               "what": "event count equals the prefilter path's, which is checked per haystack against the CPU "
+                                       "reference above (event-level comparison of the two paths: tests/test_gpu_filter.py)"}})
+        clean = torch.from_numpy(W.cfg2_stream(7, 0, n_hays // BLOCK_HAYS, planted_per_hay=0)).to(dev)
+        for name, mode in (("text_by_tma", 1), ("text_by_ldg", -1)):
+            aut.L.acb200_set_tma(C.c_void_p(aut.h), C.c_int(mode))
+            r0 = timed_device_scans(aut, torch, lambda: aut.search_device_uniform(clean.data_ptr(), n_hays, HAY_LEN)[1], steps)
+            rec.setdefault("no_needles", {})[name] = {"kernel_ms": r0["kernel_ms"] / steps, "events": int(r0["events"]),
+                                                        "roofline_frac": _roof(nbytes, r0["kernel_ms"] / steps, peak)["frac"]}
+        del clean
+    finally:
+        aut.L.acb200_set_tma(C.c_void_p(aut.h), C.c_int(0))
+        aut.set_filter(0 if filtered else -1)
+    return rec
 
 
 def also_cfg3(torch, dev, peak, hay_bytes=1 << 30, cpu_bytes=64 << 20, steps=5):

@@ -402,6 +402,11 @@ int acb200_set_tuning(AC_TRIE_t *thiz, uint32_t chunk_bytes,
  * Results are identical either way.                                                     */
 int acb200_set_filter(AC_TRIE_t *thiz, int mode);
 
+/* Full walk: how the haystack text reaches the walking lanes.  0 = automatic (TMA boxes into shared memory where the
+ * shape allows it and the previous call found few events, else 16-byte loads), 1 = TMA wherever the shape allows,
+ * -1 = loads only.  Results are identical either way. */
+int acb200_set_tma(AC_TRIE_t *thiz, int mode);
+
 /* Diagnostic: the prefilter's decision for one aligned word, evaluated on the HOST from the tables finalize
  * built (the same hashes the filter kernel uses).  `word` = the W bytes little-endian (W from
  * acb200_info().filter_word; upper bytes zero for W = 4), `next_byte` = the byte after the word, or 0x100 for

@@ -749,6 +749,7 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     va.tile_len = vtile_len;
     va.tile_off = vtile_len + verify_tiles_cap_;
     va.block_sum = vblock_sum;
+    va.host_counters = async_rows_ ? nullptr : h_counters_;      // pinned memory, mapped into the device's address space (UVA)
 
     // tune_direct: 0 / 1 flagged words are settled by one comparison inside ac_walk_kernel where the gram table allows;
     // -1 every flagged word is walked.
@@ -816,8 +817,7 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
             async_tiles_ = n_tiles;
             return true;
         }
-        CU_OK(cudaMemcpyAsync(h_counters_, vcounters, 32, cudaMemcpyDeviceToHost, st));
-        CU_OK(cudaStreamSynchronize(st));
+        CU_OK(cudaStreamSynchronize(st));          // (the emit kernel has written the counters to h_counters_)
         float ms_f = 0, ms_v = 0, ms_r = 0;
         cudaEventElapsedTime(&ms_f, EV(ev_[0]), EV(ev_[4]));
         cudaEventElapsedTime(&ms_v, EV(ev_[4]), EV(ev_[5]));

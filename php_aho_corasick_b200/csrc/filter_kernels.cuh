@@ -235,6 +235,8 @@ struct VerifyArgs {
     const uint32_t *gt_pat;       // its pattern store
     uint32_t gt_log2;             // 2^gt_log2 slots; 0: every flagged word is walked
     uint2 *count_row;             // asynchronous calls: where ac_offsets_kernel leaves {event count, dense tiles}; else nullptr
+    uint32_t *host_counters;      // synchronous calls: pinned host memory that receives counters[0..8) from ac_emit_kernel
+                                  // (one copy-engine round trip less per call); else nullptr
     uint32_t *items;              // work items, tile runs in completion order (capacity n_tiles * VER_DENSE_MAX)
     uint2 *desc;                  // per tile {offset into items, count}
     uint2 *recs;                  // per item {state of the first event, count << 16 | first end - item origin}
@@ -704,6 +706,11 @@ __global__ void __launch_bounds__(COUNT_THREADS) ac_emit_kernel(const __grid_con
     __syncthreads();
     const uint32_t s_cls_addr = (uint32_t)__cvta_generic_to_shared(s_cls);
     const uint32_t n_warps = gridDim.x * (COUNT_THREADS / 32);
+    // the call's counters are final (every kernel that adds to them has finished): hand them to the host
+    if (a.host_counters && blockIdx.x == 0 && threadIdx.x < 8) {
+        a.host_counters[threadIdx.x] = a.s.counters[threadIdx.x];
+        __threadfence_system();
+    }
 
     // The kernel is a chain of dependent loads per tile (events of the tile -> descriptor + offset -> records -> items).
     // A warp looks two tiles ahead for the event count and one tile ahead for descriptor + offset (only where the

@@ -81,7 +81,7 @@ EXPORTS = [
     "acb200_set_device", "acb200_device_count", "acb200_host_alloc", "acb200_host_free",
     "acb200_set_tuning", "acb200_version", "acb200_copy_events", "acb200_tally_cb", "acb200_tally_match_cb",
     "acb200_set_filter", "acb200_search_device_uniform", "acb200_search_hits", "acb200_pattern", "acb200_save", "acb200_load", "acb200_filter_probe",
-    "acb200_set_direct", "acb200_direct_probe", "acb200_search_device_uniform_async", "acb200_async_finish",
+    "acb200_set_direct", "acb200_set_tma", "acb200_direct_probe", "acb200_search_device_uniform_async", "acb200_async_finish",
     "acb200_set_devices", "acb200_set_slab_bytes", "acb200_plan_slabs", "acb200_event_digest",
     "acb200_device_alloc", "acb200_device_free", "acb200_ipc_export", "acb200_ipc_open", "acb200_ipc_close",
     "acb200_copy_async", "acb200_mailbox_wait_async", "acb200_mailbox_create", "acb200_mailbox_step", "acb200_mailbox_result",
@@ -144,6 +144,7 @@ def lib() -> C.CDLL:
     L.acb200_async_finish.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t]
     L.acb200_async_finish.restype = C.c_int
     L.acb200_set_direct.argtypes = [C.c_void_p, C.c_int]
+    L.acb200_set_tma.argtypes = [C.c_void_p, C.c_int]
     L.acb200_direct_probe.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.acb200_direct_probe.restype = C.c_int
     L.acb200_save.argtypes = [C.c_void_p, C.c_char_p]
@@ -281,6 +282,10 @@ class Automaton:
     def set_direct(self, mode: int) -> None:
         """0 automatic (= 1), 1 flagged words settled by one comparison inside the walk kernel, -1 every flagged word is walked"""
         self.L.acb200_set_direct(self.h, int(mode))
+
+    def set_tma(self, mode: int) -> None:
+        """full walk: 0 automatic, 1 haystack text staged by the TMA unit wherever the shape allows, -1 plain loads"""
+        self.L.acb200_set_tma(self.h, int(mode))
 
     def direct_probe(self, text: bytes, word_index: int, hay_begin: int = 0):
         """host-side evaluation of the direct verification of one aligned word -> (verdict, end, state)"""
