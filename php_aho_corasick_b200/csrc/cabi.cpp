@@ -150,8 +150,18 @@ struct ResolvedEvent {
     size_t text_idx;
 };
 
+// ... and as a slab worker hands it over: 16 bytes.  The calling thread looks the output list up itself — what bounds an
+// 8-GPU call after the copies is the ONE thread that must run 8 M callbacks in stream order, and reading 32-byte
+// records written by eight other cores costs it more (6.3 ns per event, replay micro-benchmark) than two loads from
+// the output-list offsets it keeps in its own cache (4.8 ns).
+struct SlabEvent {
+    uint64_t end;                        // exclusive end offset inside its haystack
+    uint32_t state;
+    uint32_t text_idx;
+};
+
 struct SlabResult {
-    std::vector<ResolvedEvent> ev;
+    std::vector<SlabEvent> ev;
     ACB200_STATS_t st{};
     uint32_t end_state = 0;
     bool ready = false, ok = true;
@@ -237,8 +247,8 @@ void shard_worker(const ac_trie *t, Engine *eng, const HaySource &src, const std
         if (!eng->scan_slab((int)(k & 1), rel.data(), p.h_end - p.h_first, fo, init)) { fail(k); return; }
         SlabResult r;
         {
-            // resolve the slab's events here, on the worker (every GPU's worker does its own in parallel): the calling
-            // thread, which owns the callbacks, is the serial part of a multi-GPU call and should do nothing else
+            // the slab's events in the caller's coordinates (haystack index, offset inside it), on the worker: every
+            // GPU's worker does its own in parallel, the calling thread owns the callbacks and is the serial part
             const PackedEvent *pe = eng->host_events();
             const size_t ne = eng->n_events();
             r.ev.reserve(ne);
@@ -248,9 +258,7 @@ void shard_worker(const ac_trie *t, Engine *eng, const HaySource &src, const std
                 if (pe[i].end <= p.halo) continue;               // ends inside the halo: the slab before reported it
                 const uint64_t g = base + pe[i].end;
                 while (g > src.off[h + 1]) ++h;
-                const AC_PATTERN_t *pats;
-                const uint32_t size = (uint32_t)patterns_of(t, pe[i].state, &pats);
-                r.ev.push_back(ResolvedEvent{g - src.off[h], pats, size, pe[i].state, h});
+                r.ev.push_back(SlabEvent{g - src.off[h], pe[i].state, (uint32_t)h});
             }
         }
         r.st = eng->stats;
@@ -310,14 +318,16 @@ int sharded_search(ac_trie *t, const HaySource &src, bool first_only, uint32_t i
         const SlabPlan &p = plans[i];
         add_stats(per_dev[p.device_slot], r.st);
         if (end_state) *end_state = r.end_state;
-        for (const ResolvedEvent &e : r.ev) {
+        for (const SlabEvent &e : r.ev) {
             const size_t h = e.text_idx;
             if (h == stopped) continue;
-            const int s = sink(e);
+            const AC_PATTERN_t *pats;
+            const uint32_t size = (uint32_t)patterns_of(t, e.state, &pats);
+            const int s = sink(ResolvedEvent{e.end, pats, size, e.state, h});
             if (s && stop_all) { rc = 1; break; }
             if (s || first_only) stopped = h;
         }
-        std::vector<ResolvedEvent>().swap(r.ev);
+        std::vector<SlabEvent>().swap(r.ev);
     }
     if (rc != 0) run.abort.store(true);
     for (auto &w : workers) w.join();

@@ -78,6 +78,20 @@ def test_slice_and_table_placement_do_not_change_results(chunk, smem):
     assert_same(a, ev, 16, oracle_hits([needles], split(hay, off)))
 
 
+@pytest.mark.parametrize("smem", [0, 3000, 96 * 1024])
+def test_four_byte_entries_with_and_without_a_window(smem):
+    # more than 65,536 states: 4-byte table entries; a forced shared-memory window (window-relative ids, sink row) of a few
+    # rows, of 96 KB, and the automatic choice; planted needles walk out of every window
+    needles, hay, off = W.cfg2(n_hay=24, hay_len=5000, n_needles=7000, needle_len=14, planted_per_hay=5, seed=23)
+    a = build([needles])
+    assert a.info().entry_bytes == 4
+    a.set_filter(-1)
+    a.set_tuning(256, smem)
+    ev = a.search_events(hay, off)
+    assert a.stats().filtered == 0
+    assert_same(a, ev, 24, oracle_hits([needles], split(hay, off)))
+
+
 @pytest.mark.parametrize("planted", [0, 1, 8])
 def test_full_walk_on_uniform_batches(planted):
     # 2,048-needle dictionary (deep states fall out of the shared-memory window), 64 x 8 KiB + one long haystack
