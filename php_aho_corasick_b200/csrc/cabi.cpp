@@ -299,7 +299,7 @@ int sharded_search(ac_trie *t, const HaySource &src, bool first_only, uint32_t i
     std::vector<std::vector<size_t>> mine(n_dev);
     for (size_t i = 0; i < plans.size(); ++i) mine[plans[i].device_slot].push_back(i);
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const int helpers = src.pinned ? 1 : (int)std::max(1u, std::min(4u, hw / (2u * (unsigned)n_dev)));
+    const int helpers = src.pinned ? 1 : (int)std::max(1u, std::min(8u, hw / (2u * (unsigned)n_dev)));
     std::vector<std::thread> workers;
     for (int d = 0; d < n_dev; ++d)
         workers.emplace_back(shard_worker, (const ac_trie *)t, engines[d], std::cref(src), std::cref(plans), std::cref(mine[d]), first_only,
