@@ -477,9 +477,8 @@ static long mailbox_step(acb200_mailbox *m, const void *d_bytes, size_t n, size_
         // the kernels of step k are enqueued: the rows of step k-1 are sent off while the GPU works on them (the dozen
         // driver calls this takes would otherwise sit between two steps, with the GPU idle)
         if (mailbox_flush(m) != 0) return -1;
-        MB_OK(cudaMemcpyAsync(m->own_count(), send, 8, cudaMemcpyDeviceToHost, st));
         MB_OK(cudaStreamSynchronize(st));                                      // this rank's own wait, as on one GPU
-        count = m->own_count()[0]; dense = m->own_count()[1];
+        count = t->engine.host_counters()[1]; dense = t->engine.host_counters()[4];     // (left in pinned memory by the emit kernel)
         t->engine.async_finish(count, dense);
     } else {                                                                   // this batch needs the synchronous call (full walk)
         if (mailbox_flush(m) != 0) return -1;

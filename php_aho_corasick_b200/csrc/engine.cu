@@ -749,7 +749,7 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
     va.tile_len = vtile_len;
     va.tile_off = vtile_len + verify_tiles_cap_;
     va.block_sum = vblock_sum;
-    va.host_counters = async_rows_ ? nullptr : h_counters_;      // pinned memory, mapped into the device's address space (UVA)
+    va.host_counters = h_counters_;              // pinned memory, mapped into the device's address space (UVA)
 
     // tune_direct: 0 / 1 flagged words are settled by one comparison inside ac_walk_kernel where the gram table allows;
     // -1 every flagged word is walked.

@@ -87,6 +87,10 @@ public:
     int tune_direct = 0;           // 0 auto (= 1), 1 direct verification of flagged words inside the walk kernel,
                                    // -1 every flagged word is walked
 
+    // counters of the last prefilter-path call as its last kernel handed them to pinned host memory: [1] events,
+    // [4] densely flagged tiles — valid once the call's stream has been waited for (asynchronous calls included)
+    const uint32_t *host_counters() const { return h_counters_; }
+
 private:
     bool ensure_text(size_t bytes);
     bool ensure_events(size_t n);
