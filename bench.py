@@ -509,6 +509,19 @@ def main():
         elapsed_ms = float(tmax[0])
         acc["kernel_ms"], acc["filter_ms"], acc["verify_ms"], acc["reorder_ms"] = (float(tmax[i]) for i in (1, 3, 4, 5))
         launches = int(tsum[2])
+        # per rank, for the record: the step and kernel times the maxima above were taken from, and every GPU's clock
+        mine = torch.tensor([float(t[0]), float(t[1]), float(t[3]), float(t[4]), float(t[5]), clocks.get("sm_mhz") or 0.0,
+                             1.0 if clocks.get("reasons") else 0.0], dtype=torch.float64, device=dev)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank = {"ms_per_step": [round(float(x[0]) / args.steps, 4) for x in every],
+                    "kernel_ms": [round(float(x[1]) / args.steps, 4) for x in every],
+                    "filter_ms": [round(float(x[2]) / args.steps, 4) for x in every],
+                    "collect_walk_ms": [round(float(x[3]) / args.steps, 4) for x in every],
+                    "offsets_emit_ms": [round(float(x[4]) / args.steps, 4) for x in every],
+                    "sm_mhz": [float(x[5]) for x in every], "throttle_flagged": [bool(x[6]) for x in every]}
+    else:
+        per_rank = None
     ms_per_step = elapsed_ms / args.steps
     value = world * nbytes / (ms_per_step * 1e-3) / 1e9
     k_ms = acc["kernel_ms"] / args.steps
@@ -559,6 +572,7 @@ def main():
                                   "finalize_s": round(finalize_s, 4)},
                        events_per_step_per_gpu=int(n_events)),
         "parity": parity,
+        "per_rank": per_rank,
         "roofline": roofline,
         "e2e": e2e,
         "gpu_launches": launches,
