@@ -341,6 +341,10 @@ int acb200_device_count(void);
  * (the PHP extension).  Returns 0 / -1.                                                                      */
 int acb200_set_devices(AC_TRIE_t *thiz, const int *devices, size_t n);
 
+/* Environment read by the library — the complete list: ACB200_DEVICE (primary GPU of new handles), ACB200_DEVICES
+ * (GPUs a host call may use, above), ACB200_L2_MIN_FILL (test knob: level-1 fill above which finalize builds the
+ * level-2 bitmap of the prefilter, default 0.10; results do not depend on it). */
+
 /* Bytes per slab of the host pipeline (0 = default 64 MiB).  Tests use small slabs to force cuts. */
 int acb200_set_slab_bytes(AC_TRIE_t *thiz, uint64_t bytes);
 
