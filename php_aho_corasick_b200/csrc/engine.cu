@@ -661,18 +661,37 @@ static void launch_filter_k(const FilterArgs &fa, bool l2, unsigned grid, cudaSt
     else ac_filter_kernel<W, false><<<grid, SCAN_THREADS, FILTER_L1_BYTES, st>>>(fa);
 }
 
+// Programmatic dependent launch: the kernel is put on the SMs while the one before it in the stream (which calls
+// cudaTriggerProgrammaticLaunchCompletion at its start) is still running, stages its class map, and waits in
+// cudaGridDependencySynchronize() for that kernel's results — the launch latency and the prologue of the two short
+// kernels of a step that follow another kernel directly (walk after collect, emit after offsets) leave the critical path.
+template <typename K>
+static void launch_dependent(K kernel, const VerifyArgs &a, unsigned grid, unsigned block, cudaStream_t st)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kernel, a) != cudaSuccess) {
+        cudaGetLastError();
+        kernel<<<grid, block, 0, st>>>(a);          // (a driver that refuses the attribute: the plain, fully ordered launch)
+    }
+}
+
 template <typename E, int W>
 static void launch_walk_k(const VerifyArgs &a, bool range, unsigned grid, cudaStream_t st)
 {
-    if (range) ac_walk_kernel<E, true, W><<<grid, WALK_THREADS, 0, st>>>(a);
-    else ac_walk_kernel<E, false, W><<<grid, WALK_THREADS, 0, st>>>(a);
+    if (range) launch_dependent(ac_walk_kernel<E, true, W>, a, grid, WALK_THREADS, st);
+    else launch_dependent(ac_walk_kernel<E, false, W>, a, grid, WALK_THREADS, st);
 }
 
 template <typename E, int W>
 static void launch_emit_k(const VerifyArgs &a, bool range, unsigned grid, cudaStream_t st)
 {
-    if (range) ac_emit_kernel<E, true, W><<<grid, COUNT_THREADS, 0, st>>>(a);
-    else ac_emit_kernel<E, false, W><<<grid, COUNT_THREADS, 0, st>>>(a);
+    if (range) launch_dependent(ac_emit_kernel<E, true, W>, a, grid, COUNT_THREADS, st);
+    else launch_dependent(ac_emit_kernel<E, false, W>, a, grid, COUNT_THREADS, st);
 }
 
 // ahocorasick_match() through the gram prefilter: ac_filter_kernel streams the haystack and flags aligned

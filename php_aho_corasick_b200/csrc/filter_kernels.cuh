@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
     __shared__ uint32_t s_base;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t dense_tiles = 0, flagged = 0;
+    // ac_walk_kernel may be put on the SMs from now on (it waits for this grid to finish before it reads a single item)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     auto load_planes = [&](uint32_t tile, uint32_t (&pl)[NB]) {
 #pragma unroll
@@ -557,6 +559,9 @@ __global__ void __launch_bounds__(WALK_THREADS) ac_walk_kernel(const __grid_cons
     st.ncls = a.s.ncls; st.lo = a.s.range_lo; st.n_used = a.s.n_used;
     st.final_bound = a.s.final_bound; st.root = a.s.root;
 
+    // launched as a programmatic dependent of ac_collect_kernel: everything above overlapped with it, nothing below may
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
     // the dense list ac_collect_kernel made
     const uint32_t n_items = a.s.counters[a.counter_slot];
     const uint32_t n_threads = gridDim.x * WALK_THREADS;
@@ -664,6 +669,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) ac_offsets_kernel(const __grid_c
     __shared__ uint32_t s_warp[EMIT_THREADS / 32];
     __shared__ uint32_t s_prev[EMIT_THREADS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // ac_emit_kernel may be put on the SMs (it waits for this grid)
 
     uint32_t part = 0;
     for (uint32_t j = tid; j < blockIdx.x; j += EMIT_THREADS) part += a.block_sum[j];
@@ -706,6 +712,7 @@ __global__ void __launch_bounds__(COUNT_THREADS) ac_emit_kernel(const __grid_con
     __syncthreads();
     const uint32_t s_cls_addr = (uint32_t)__cvta_generic_to_shared(s_cls);
     const uint32_t n_warps = gridDim.x * (COUNT_THREADS / 32);
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // launched as a programmatic dependent of ac_offsets_kernel
     // the call's counters are final (every kernel that adds to them has finished): hand them to the host
     if (a.host_counters && blockIdx.x == 0 && threadIdx.x < 8) {
         a.host_counters[threadIdx.x] = a.s.counters[threadIdx.x];
