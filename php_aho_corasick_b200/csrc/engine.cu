@@ -790,8 +790,12 @@ bool Engine::launch_filtered(const void *d_text, uint32_t total, uint32_t readab
             va.count_row = (uint2 *)async_rows_;
             a.capacity = (uint32_t)std::min<size_t>(async_cap_, 0xffffffffu);
         }
-        // counters, block sums and events per tile (the walk kernel adds to both) are adjacent: one memset
-        CU_OK(cudaMemsetAsync(vcounters, 0, (size_t)((vtile_len - vcounters) + n_tiles) * sizeof(uint32_t), st));
+        // counters, block sums and events per tile (the walk kernel adds to both) start at zero: on the first attempt the
+        // filter kernel's CTA 0 clears the first two and ac_collect_kernel every tile's count — no memset in front of a call
+        fa.zero = vcounters; fa.n_zero = (uint32_t)(vtile_len - vcounters);
+        va.clear_tile_len = attempt == 0 ? 1u : 0u;
+        if (attempt != 0)
+            CU_OK(cudaMemsetAsync(vcounters, 0, (size_t)((vtile_len - vcounters) + n_tiles) * sizeof(uint32_t), st));
         CU_OK(cudaEventRecord(EV(ev_[0]), st));
         if (attempt == 0) {      // the bit planes survive a regrow of the event buffer
             fa.span_begin = 0;

@@ -71,6 +71,8 @@ struct FilterArgs {
     uint32_t *mask;               // n_spans x (16/W) words: plane j bit c <=> word (c*(16/W) + j) of the span
     uint32_t n_spans;             // ceil(total / 512)
     uint32_t span_begin, span_end;// this launch filters spans [span_begin, span_end)
+    uint32_t *zero;               // scratch words of the kernels that follow (their counters and block sums), cleared by CTA 0
+    uint32_t n_zero;              // ... instead of by a memset in front of every call; 0: nothing to clear
 };
 
 // ------------------------------------------------------------- filter -----
@@ -129,6 +131,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const Filter
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
+    if (blockIdx.x == 0)
+        for (uint32_t i = tid; i < a.n_zero; i += SCAN_THREADS) a.zero[i] = 0u;
     const uint32_t s_base = stage_bitmap(a, s_bm, tid);
     // the span's last word of lane 31 is tested on its W bytes alone, in the bitmap's "next byte unknown" part
     const uint32_t last_region = s_base + (lane == 31u ? FILTER_L1_KNOWN_WORDS * 4u : 0u);
@@ -231,6 +235,7 @@ struct VerifyArgs {
     uint32_t dense_max;           // more flagged words than this in a tile: hand on the tile's spans instead
     uint32_t warm;                // warm-up bytes before a flagged word's end offsets (halo rounded up to W)
     uint32_t want_end_state;      // also compute the state at the end of the stream (counters[2])
+    uint32_t clear_tile_len;      // ac_collect_kernel clears tile_len[tile] (first attempt of a call)
     const uint4 *gt_slots;        // exact gram table (gram_table.hpp) or nullptr
     const uint32_t *gt_pat;       // its pattern store
     uint32_t gt_log2;             // 2^gt_log2 slots; 0: every flagged word is walked
@@ -309,7 +314,10 @@ __global__ void __launch_bounds__(COLLECT_THREADS) ac_collect_kernel(const __gri
         if (threadIdx.x == 0) s_base = a.item_base + (cta_total ? atomicAdd(&a.s.counters[a.counter_slot], cta_total) : 0u);
         __syncthreads();
         const uint32_t base = s_base + __shfl_sync(0xffffffffu, wincl - v, warp);
-        if (lane == 0 && tile < a.tile_end) a.desc[tile] = make_uint2(base, n);
+        if (lane == 0 && tile < a.tile_end) {
+            a.desc[tile] = make_uint2(base, n);
+            if (a.clear_tile_len) a.tile_len[tile] = 0u;     // (the walk kernel adds to it; no memset in front of the call)
+        }
         if (n == 0) {
         } else if (dense) {
             ++dense_tiles;
