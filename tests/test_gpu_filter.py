@@ -87,6 +87,33 @@ def test_random_dictionaries_both_word_sizes_ragged_batches(seed):
         a.release()
 
 
+def test_calls_of_changing_size_on_one_handle_leave_nothing_behind():
+    """No memset runs in front of a prefilter call: the filter kernel's CTA 0 clears the counters and block sums,
+    ac_collect_kernel each tile's event count.  Batches of very different sizes and event densities back to back on ONE
+    handle (large, tiny, large again with other content, empty of matches) must each equal the full walk."""
+    needles, _, _ = W.cfg2(n_hay=1, hay_len=64)
+    a = build([needles], 1)
+    shapes = [(1024, 8192, 8, 1), (3, 700, 2, 2), (1024, 8192, 1, 3), (40, 8192, 0, 4), (512, 8192, 16, 5), (1, 17, 1, 6)]
+    for n_hay, hay_len, planted, seed in shapes:
+        _, hay, off = W.cfg2(n_hay=n_hay, hay_len=hay_len, planted_per_hay=planted, seed=seed)
+        # the dictionary is the default-seed one: plant ITS needles
+        rng = np.random.default_rng(seed)
+        for h in range(n_hay):
+            for _ in range(planted):
+                if hay_len >= 16:
+                    at = int(off[h]) + int(rng.integers(0, hay_len - 16 + 1))
+                    hay[at:at + 16] = np.frombuffer(needles[int(rng.integers(0, len(needles)))], dtype=np.uint8)
+        a.set_filter(1)
+        ev = a.search_events(hay, off)
+        assert a.stats().filtered == 1
+        a.set_filter(-1)
+        ref = a.search_events(hay, off)
+        assert a.stats().filtered == 0
+        assert np.array_equal(ev, ref), (n_hay, hay_len, planted)
+        if planted and hay_len >= 16:
+            assert len(ev) >= n_hay
+
+
 def test_find_first_through_the_prefilter_equals_the_first_only_kernel():
     needles, hay, off = W.cfg2(n_hay=300, hay_len=8192, planted_per_hay=3, seed=31)
     hay = hay.copy()
