@@ -78,6 +78,35 @@ def test_slice_and_table_placement_do_not_change_results(chunk, smem):
     assert_same(a, ev, 16, oracle_hits([needles], split(hay, off)))
 
 
+@pytest.mark.parametrize("seed", range(5))
+def test_overlapping_dictionaries_through_the_batch_walk_with_forced_windows(seed):
+    """ac_scan_kernel / ac_scan_tma_kernel (batches take them, single short texts do not): dictionaries over tiny
+    alphabets whose patterns nest and overlap — every few bytes an event, walks that leave a forced, tiny
+    shared-memory window (sink row) and come back inside one 16-byte group — against the reference, for several
+    window sizes, slice lengths and both ways of fetching the text."""
+    rng = random.Random(1000 + seed)
+    nrng = np.random.default_rng(1000 + seed)
+    alpha = rng.choice([b"ab", b"abc", b"a\x00\xff", b"abcdef"])
+    pats = list({bytes(rng.choice(alpha) for _ in range(rng.randint(1, rng.choice([4, 9, 20])))) for _ in range(rng.randint(5, 120))})
+    lut = np.frombuffer(alpha, dtype=np.uint8)
+    lens = [rng.choice([0, 1, 15, 16, 17, 500, 3000, 4096, 9000]) for _ in range(24)]
+    hays = [lut[nrng.integers(0, len(alpha), size=n)] for n in lens]
+    flat = np.concatenate(hays)
+    off = np.zeros(len(lens) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    exp = oracle_hits([pats], hays)
+    a = build([pats])
+    a.set_filter(-1)
+    for tma in (-1, 1):
+        a.set_tma(tma)
+        for chunk, smem in ((0, 0), (64, 200), (256, 1024), (512, 64), (128, 8192)):
+            a.set_tuning(chunk, smem)
+            ev = a.search_events(flat, off)
+            assert a.stats().filtered == 0
+            assert_same(a, ev, len(lens), exp)
+    a.release()
+
+
 @pytest.mark.parametrize("smem", [0, 3000, 96 * 1024])
 def test_four_byte_entries_with_and_without_a_window(smem):
     # more than 65,536 states: 4-byte table entries; a forced shared-memory window (window-relative ids, sink row) of a few
