@@ -379,8 +379,12 @@ void build_gram_table(FlatAutomaton &flat) {
         flat.gt_pat[pat_ref[pi]] = pat_state[pi];
     }
 
+    // Load factor <= 1/4 (<= 1/2 for tables beyond 64 MiB): the probe loop of a warp runs as long as its unluckiest
+    // lane's, and every step is a dependent trip to L2 — ncu's source view of ac_walk_kernel had a third of its stall
+    // samples on that loop at load 1/2 (6.5 steps per warp; absent keys, the Bloom false positives, probe longest).
     uint32_t lg = 10;
-    while ((1ull << lg) < 2ull * np * W) ++lg;
+    while ((1ull << lg) < 4ull * np * W) ++lg;
+    if (((size_t)sizeof(GramSlot) << lg) > ((size_t)64 << 20) && (1ull << (lg - 1)) >= 2ull * np * W) --lg;
     flat.gt_log2 = lg;
     flat.gt_slots.assign((size_t)1 << lg, GramSlot{0, 0, 0, 0, {0, 0, 0, 0}});
     const uint32_t mask = (1u << lg) - 1u;
