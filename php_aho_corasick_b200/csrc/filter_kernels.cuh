@@ -48,7 +48,10 @@
 namespace acb200 {
 
 constexpr uint32_t SPAN_BYTES = 512;       // one warp-wide 16-byte load; one verify lane
-constexpr int FILTER_UNROLL = 4;           // 16-byte loads in flight per thread (measured 1 GiB: 4 -> 0.184 ms, 6 -> 0.189, 8 -> 0.196)
+constexpr int FILTER_UNROLL = 3;           // 16-byte loads per thread and round; the next round's loads are issued before a round is
+                                           // looked at, so 2 x 3 are in flight (measured, 1 GiB of config 2 / 256 MiB of config 3:
+                                           // 1 -> 0.246 ms, 2 -> 0.181 / 0.130, 3 -> 0.181 / 0.127, 4 -> 0.185, 6 -> 0.197 / 0.148;
+                                           // without the overlap 4 -> 0.187, 6 -> 0.189, 8 -> 0.196)
 constexpr uint32_t VER_DENSE_MAX = 64;     // flagged words per 16 KiB tile beyond which the whole tile is walked
 constexpr uint32_t ITEM_SPAN = 0x80000000u;// work item: walk 512-byte span (item & ~ITEM_SPAN) completely
 constexpr uint32_t ITEM_NONE = 0xffffffffu;
@@ -180,15 +183,27 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_filter_kernel(const Filter
     uint32_t g0 = a.span_begin + warp;
     const uint8_t *src = a.text + ((size_t)g0 * 32u + lane) * 16u;
     const size_t span_stride = (size_t)n_warps * SPAN_BYTES;
-    for (; (uint64_t)g0 + (uint64_t)(U - 1) * n_warps < n_full; g0 += n_warps * U, src += span_stride * U) {
-        uint4 v[U];
+    // The loads of round r + 1 are issued before round r is looked at: ncu's source view had half of this kernel's
+    // stall samples on the first use of a round's first load.
+    auto round_is_full = [&](uint32_t g) { return (uint64_t)g + (uint64_t)(U - 1) * n_warps < n_full; };
+    uint4 v[U];
+    if (round_is_full(g0)) {
 #pragma unroll
         for (int u = 0; u < U; ++u) v[u] = ld_text16(src + span_stride * u);
+    }
+    for (; round_is_full(g0); g0 += n_warps * U, src += span_stride * U) {
+        uint4 nv[U];
+        if (round_is_full(g0 + n_warps * U)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) nv[u] = ld_text16(src + span_stride * (U + u));
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t mine = span_planes(v[u]);
             if (lane < (uint32_t)NB) a.mask[(size_t)(g0 + u * n_warps) * NB + lane] = mine;
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = nv[u];
     }
     // the last, partial round
     for (; g0 < n_full; g0 += n_warps) {
