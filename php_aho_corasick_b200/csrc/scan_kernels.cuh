@@ -140,7 +140,9 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long *statu
             unsigned long long v = ST_PREFIX;         // before tile 0: the events of earlier launches
             const bool virt = j < 0;
             if (!virt) {
-                do { v = ld_status(status + j); } while ((v >> 62) == 0);
+                // (a warp that finished early polls until the slowest of its 32 predecessors has published — ncu counted 480
+                // polls per tile and lane, 16 % of the kernel's instructions, issued next to the warps that still walk: sleep)
+                while (((v = ld_status(status + j)) >> 62) == 0) __nanosleep(256);
             }
             const bool is_prefix = (v >> 62) == 2;
             const unsigned pm = __ballot_sync(0xffffffffu, is_prefix);
