@@ -605,7 +605,7 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     // Tiles are handed out by ticket, so any grid is correct.  One CTA per 32 tiles (a tile per warp) left most SMs idle
     // for mid-size inputs and long patterns (config 5: 256 MiB = 1,024 tiles of 256 KiB -> 32 of 148 SMs): spread
     // the tiles over the SMs instead, at least four per CTA so that a CTA's table staging is shared by some work.
-    // (Changed after this round's last GPU run: correctness does not depend on it, its effect is not measured yet.)
+    // (Round 2, with the 2 KiB slices pick_chunk() now gives long patterns: config 5 went from 20 to 127-129 GB/s read.)
     const unsigned grid = std::min<uint32_t>(std::max<uint32_t>((n_tiles + warps_per_cta - 1) / warps_per_cta, (n_tiles + 3u) / 4u),
                                              (uint32_t)n_sms_);
 
