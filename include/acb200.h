@@ -343,7 +343,10 @@ int acb200_set_devices(AC_TRIE_t *thiz, const int *devices, size_t n);
 
 /* Environment read by the library — the complete list: ACB200_DEVICE (primary GPU of new handles), ACB200_DEVICES
  * (GPUs a host call may use, above), ACB200_L2_MIN_FILL (test knob: level-1 fill above which finalize builds the
- * level-2 bitmap of the prefilter, default 0.10; results do not depend on it). */
+ * level-2 bitmap of the prefilter, default 0.10; results do not depend on it), ACB200_GATHER_THREADS (threads that
+ * gather the scattered strings of an ac_trie_search_batch() slab into pinned staging, 1..64; default
+ * min(12, 3/4 cores / GPUs); results do not depend on it), ACB200_GATHER_NT (0: that gather uses plain memcpy
+ * instead of non-temporal stores, for A/B measurements). */
 
 /* Bytes per slab of the host pipeline (0 = default 64 MiB).  Tests use small slabs to force cuts. */
 int acb200_set_slab_bytes(AC_TRIE_t *thiz, uint64_t bytes);

@@ -153,7 +153,7 @@ void Engine::release()
     cudaSetDevice(device_);
     if (stream_) cudaStreamSynchronize(S(stream_));
     cudaFree(d_table_); cudaFree(d_cls_); cudaFree(d_text_); cudaFree(d_off_);
-    cudaFree(d_first_); cudaFree(d_events_); cudaFree(d_tiles_); cudaFree(d_counters_);
+    cudaFree(d_first_); cudaFree(d_events_); cudaFree(d_tiles_);
     cudaFree(d_l1_); cudaFree(d_l2_); cudaFree(d_mask_);
     cudaFree(d_gt_slots_); cudaFree(d_gt_pat_); d_gt_slots_ = nullptr; d_gt_pat_ = nullptr; gt_log2_ = 0;
     cudaFree(d_out_off_); cudaFree(d_out_idx_); cudaFree(d_pat_len_); cudaFree(d_hit_sums_); cudaFree(d_hits_); cudaFree(d_hit_total_);
@@ -173,7 +173,7 @@ void Engine::release()
     if (copy_stream_) { cudaStreamDestroy(S(copy_stream_)); copy_stream_ = nullptr; }
     if (stream_) cudaStreamDestroy(S(stream_));
     d_table_ = nullptr; d_cls_ = nullptr; d_text_ = nullptr; d_off_ = nullptr; d_first_ = nullptr;
-    d_events_ = nullptr; d_tiles_ = nullptr; d_counters_ = nullptr;
+    d_events_ = nullptr; d_tiles_ = nullptr;
     h_counters_ = nullptr; h_events_ = nullptr; stream_ = nullptr;
     device_ = -1;
 }
@@ -281,8 +281,6 @@ bool Engine::build(const FlatAutomaton &f, int dev, const Engine *table_src)
     CU_OK(cudaMemsetAsync(d_table_, 0, table_bytes + 16, st));
     CU_OK(cudaMalloc(&d_cls_, 256));
     CU_OK(cudaMemcpyAsync(d_cls_, f.cls_map, 256, cudaMemcpyHostToDevice, st));
-    CU_OK(cudaMalloc(&d_counters_, 64));
-    CU_OK(cudaMemsetAsync(d_counters_, 0, 64, st));
     CU_OK(cudaMallocHost(&h_counters_, 64));
 
     uint64_t launches = 0;
@@ -449,7 +447,7 @@ bool Engine::ensure_tiles(size_t n)
     if (n <= tiles_cap_) return true;
     cudaFree(d_tiles_); d_tiles_ = nullptr; tiles_cap_ = 0;
     const size_t cap = std::max(n + n / 4, (size_t)1024);
-    CU_OK(cudaMalloc(&d_tiles_, cap * sizeof(unsigned long long)));
+    CU_OK(cudaMalloc(&d_tiles_, (cap + 4) * sizeof(unsigned long long)));      // + the full walk's eight counters behind its tiles
     tiles_cap_ = cap;
     return true;
 }
@@ -565,12 +563,12 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
 
     // Hot window in shared memory: B shallowest finals + A shallowest non-finals (root first).
     const int dyn_max = max_smem_optin_ - 2048 - (tma ? (int)TMA_RING_BYTES + 768 : 0);
-    size_t smem_budget = (size_t)dyn_max;
+    size_t smem_budget = (size_t)dyn_max - 16;     // (16 bytes: stage_window's alignment shift)
     if (tune_smem_bytes) smem_budget = std::min<size_t>(smem_budget, tune_smem_bytes);
     uint32_t win_lo = 0, win_rows = 0;
     window_for(smem_budget, &win_lo, &win_rows);
     const size_t row_bytes = (size_t)ncls_ * entry_bytes_;
-    const size_t smem_bytes = std::max<size_t>(16, ((size_t)win_rows + 1) * row_bytes);
+    const size_t smem_bytes = std::max<size_t>(16, ((size_t)win_rows + 1) * row_bytes) + 16;     // (+ stage_window's alignment shift)
 
     const uint32_t n_tiles = (n_chunks + 31u) / 32u;
 
@@ -599,8 +597,9 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     a.n_used = n_used_;
     a.init_state = (init_state == ROOT_STATE) ? root_ : init_state;
     a.tile_status = d_tiles_;
-    a.counters = d_counters_;
+    a.counters = reinterpret_cast<uint32_t *>(d_tiles_ + n_tiles);       // right behind the tile status words: ONE memset clears both
     a.first_end = d_first_;
+    a.host_counters = h_counters_;               // pinned memory, mapped into the device's address space (UVA)
     const unsigned warps_per_cta = SCAN_THREADS / 32;
     // Tiles are handed out by ticket, so any grid is correct.  One CTA per 32 tiles (a tile per warp) left most SMs idle
     // for mid-size inputs and long patterns (config 5: 256 MiB = 1,024 tiles of 256 KiB -> 32 of 148 SMs): spread
@@ -612,9 +611,9 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
     for (int attempt = 0; attempt < 2; ++attempt) {
         a.out = (uint2 *)d_events_;
         a.capacity = (uint32_t)std::min<size_t>(events_cap_, 0xffffffffu);
-        CU_OK(cudaMemsetAsync(d_tiles_, 0, (size_t)n_tiles * sizeof(unsigned long long), st));
-        CU_OK(cudaMemsetAsync(d_counters_, 0, 32, st));
+        CU_OK(cudaMemsetAsync(d_tiles_, 0, ((size_t)n_tiles + 4) * sizeof(unsigned long long), st));
         if (first_only) CU_OK(cudaMemsetAsync(d_first_, 0xff, n_hay * sizeof(uint32_t), st));
+        h_counters_[1] = 0; h_counters_[2] = 0;     // (a findAll=false call may skip its last slice and with it the end state)
         CU_OK(cudaEventRecord(EV(ev_[0]), st));
         if (tma) {
             const size_t smem_tma = smem_bytes + TMA_RING_BYTES + 128;      // + alignment slack of the ring
@@ -635,8 +634,7 @@ bool Engine::launch_scan(const void *d_text, uint32_t total, uint32_t readable, 
         CU_OK(cudaGetLastError());
         CU_OK(cudaEventRecord(EV(ev_[1]), st));
         stats.kernel_launches += 1;
-        CU_OK(cudaMemcpyAsync(h_counters_, d_counters_, 16, cudaMemcpyDeviceToHost, st));
-        CU_OK(cudaStreamSynchronize(st));
+        CU_OK(cudaStreamSynchronize(st));          // (the kernel has written the event total and the end state to h_counters_)
         float ms = 0;
         cudaEventElapsedTime(&ms, EV(ev_[0]), EV(ev_[1]));
         stats.kernel_ms += ms;

@@ -150,7 +150,6 @@ private:
     uint32_t *d_first_ = nullptr; size_t first_cap_ = 0;
     void *d_events_ = nullptr;    size_t events_cap_ = 0;
     unsigned long long *d_tiles_ = nullptr; size_t tiles_cap_ = 0;
-    uint32_t *d_counters_ = nullptr;
     uint32_t *h_counters_ = nullptr;          // pinned
     PackedEvent *h_events_ = nullptr; size_t h_events_cap_ = 0;   // pinned
     const PackedEvent *last_host_events_ = nullptr;               // where the most recent host-side scan left its events

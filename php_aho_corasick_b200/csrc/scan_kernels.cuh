@@ -61,6 +61,8 @@ struct ScanArgs {
     uint32_t *counters;           // [0] ticket (zeroed per launch) [1] running event total [2] end state
                                   // [3] words flagged by the filter [4] tiles handed on for a complete walk [5] work items
     uint32_t *first_end;          // FIRST kernels: per haystack earliest event end seen (init 0xffffffff)
+    uint32_t *host_counters;      // pinned host memory that also receives counters[1] and counters[2] (the host reads them
+                                  // after its wait: one copy-engine round trip less per call); or nullptr
 };
 
 // ------------------------------------------------------------ finalize ----
@@ -166,7 +168,10 @@ __device__ __forceinline__ unsigned long long tile_lookback(const ScanArgs &a, u
                                                             uint32_t prior, uint32_t lane)
 {
     const unsigned long long excl = lookback(a.tile_status, tile, total, prior, lane);
-    if (lane == 0 && tile == a.n_tiles - 1) a.counters[1] = (uint32_t)(excl + total);
+    if (lane == 0 && tile == a.n_tiles - 1) {
+        a.counters[1] = (uint32_t)(excl + total);
+        if (a.host_counters) a.host_counters[1] = (uint32_t)(excl + total);
+    }
     return excl;
 }
 
@@ -189,35 +194,46 @@ template <> __device__ __forceinline__ uint32_t lds_entry<uint32_t>(uint32_t add
 // the copy is a sink (all zeros), row r + 1 is the row of state win_lo + r, and an entry is its target's row number —
 // 0 when the target lies outside the window.  A walk that steps out of the window therefore just stays in the sink,
 // reading valid shared memory, and the hot loop needs no exit in the middle of a 16-byte group.
-// s_tab must hold (win_rows + 1) rows.  Called by all threads of the CTA (n_threads of them).
+// The copy starts up to 15 bytes into s_base, so that the table's aligned 16-byte groups are aligned in shared memory
+// as well: a group is ONE 16-byte load, four of them in flight per thread, and ONE conflict-free 16-byte store.
+// (ncu on a 0.25 MiB call, where the kernel is 35 us long: a third of the active cycles went into this copy when every
+// load was waited for and its eight entries left as eight 2-byte stores, four-way bank-conflicted each.)
+// s_base must hold (win_rows + 1) rows + 16 bytes.  Called by all threads of the CTA (n_threads of them); returns
+// the address of the sink row.
 template <typename E>
-__device__ __forceinline__ void stage_window(E *s_tab, const E *gtab, uint32_t win_lo, uint32_t win_rows, uint32_t ncls,
-                                             uint32_t tid, uint32_t n_threads)
+__device__ __forceinline__ E *stage_window(E *s_base, const E *gtab, uint32_t win_lo, uint32_t win_rows, uint32_t ncls,
+                                           uint32_t tid, uint32_t n_threads)
 {
     constexpr uint32_t PER = 16 / sizeof(E);               // entries per 16-byte load
     auto rel = [&](uint32_t e) -> uint32_t { e -= win_lo; return (e < win_rows) ? e + 1u : 0u; };
-    for (uint32_t idx = tid; idx < ncls; idx += n_threads) s_tab[idx] = (E)0;          // the sink row
-    E *rows = s_tab + ncls;
+    auto rel_group = [&](const uint4 &q) -> uint4 {
+        if (sizeof(E) == 2) {
+            auto two = [&](uint32_t w) -> uint32_t { return rel(w & 0xffffu) | (rel(w >> 16) << 16); };
+            return make_uint4(two(q.x), two(q.y), two(q.z), two(q.w));
+        }
+        return make_uint4(rel(q.x), rel(q.y), rel(q.z), rel(q.w));
+    };
     const uint32_t win_entries = win_rows * ncls;
     const uint32_t win_first = win_lo * ncls;
     const uint32_t lead = min((PER - (win_first % PER)) % PER, win_entries);   // entries before the first aligned group
+    E *s_tab = s_base + (PER - (ncls + lead) % PER) % PER;
+    for (uint32_t idx = tid; idx < ncls; idx += n_threads) s_tab[idx] = (E)0;          // the sink row
+    E *rows = s_tab + ncls;
     for (uint32_t idx = tid; idx < lead; idx += n_threads) rows[idx] = (E)rel(gtab[win_first + idx]);
     const uint32_t n_vec = (win_entries - lead) / PER;
     const uint4 *src = reinterpret_cast<const uint4 *>(gtab + win_first + lead);
-    for (uint32_t v = tid; v < n_vec; v += n_threads) {
-        const uint4 q = __ldg(src + v);
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint4 *dst = reinterpret_cast<uint4 *>(rows + lead);
+    uint32_t v = tid;
+    for (; v + 3u * n_threads < n_vec; v += 4u * n_threads) {
+        uint4 q[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (sizeof(E) == 2) {
-                rows[lead + v * PER + 2 * k] = (E)rel(w[k] & 0xffffu);
-                rows[lead + v * PER + 2 * k + 1] = (E)rel(w[k] >> 16);
-            } else {
-                rows[lead + v * PER + k] = (E)rel(w[k]);
-            }
-        }
+        for (int k = 0; k < 4; ++k) q[k] = __ldg(src + v + k * n_threads);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[v + k * n_threads] = rel_group(q[k]);
     }
+    for (; v < n_vec; v += n_threads) dst[v] = rel_group(__ldg(src + v));
     for (uint32_t idx = lead + n_vec * PER + tid; idx < win_entries; idx += n_threads) rows[idx] = (E)rel(gtab[win_first + idx]);
+    return s_tab;
 }
 
 // Per-thread walker.
@@ -502,7 +518,6 @@ template <typename E, bool RANGE, bool FIRST>
 __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_kernel(const ScanArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    E *s_tab = reinterpret_cast<E *>(smem_raw);
     __shared__ uint8_t s_cls[256];
 
     const uint32_t tid = threadIdx.x;
@@ -510,7 +525,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_kernel(const ScanArgs
     const E *gtab = static_cast<const E *>(a.table);
 
     // window rows, with targets outside the window replaced by 0
-    stage_window<E>(s_tab, gtab, a.win_lo, a.win_rows, a.ncls, tid, SCAN_THREADS);
+    E *s_tab = stage_window<E>(reinterpret_cast<E *>(smem_raw), gtab, a.win_lo, a.win_rows, a.ncls, tid, SCAN_THREADS);
     if (tid < 256) s_cls[tid] = a.cls_map[tid];
     __syncthreads();      // the only CTA-wide barrier: from here on warps run independently
 
@@ -561,7 +576,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_kernel(const ScanArgs
                 s = sc.template walk<true, 0>(s, ws, cs);
                 s_cs = s;
                 s = scan_slice<0>(a, sc, s, h, cs, ce);
-                if (ce == a.total) a.counters[2] = s;
+                if (ce == a.total) { a.counters[2] = s; if (a.host_counters) a.host_counters[2] = s; }
                 if (FIRST && sc.cnt) {
                     // publish the earliest event of the slice's first reporting haystack
                     const uint32_t hh = find_haystack(a, sc.e0p - 1);
@@ -658,7 +673,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_tma_kernel(const Scan
     __shared__ __align__(8) unsigned long long s_bar[SCAN_THREADS / 32][TMA_STAGES];
     // the ring first, on a 128-byte boundary (what the TMA unit wants of its destination), then the table window
     const uint32_t ring_base = ((uint32_t)__cvta_generic_to_shared(smem_raw) + 127u) & ~127u;
-    E *s_tab = reinterpret_cast<E *>(smem_raw + (ring_base - (uint32_t)__cvta_generic_to_shared(smem_raw)) + TMA_RING_BYTES);
+    E *s_tab = reinterpret_cast<E *>(smem_raw + (ring_base - (uint32_t)__cvta_generic_to_shared(smem_raw)) + TMA_RING_BYTES);   // (moved by stage_window)
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u, warp = tid >> 5;
@@ -666,7 +681,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_tma_kernel(const Scan
     const uint32_t ring = ring_base + warp * (TMA_STAGES * TMA_STAGE_BYTES);
     const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[warp][0]);
 
-    stage_window<E>(s_tab, gtab, a.win_lo, a.win_rows, a.ncls, tid, SCAN_THREADS);
+    s_tab = stage_window<E>(s_tab, gtab, a.win_lo, a.win_rows, a.ncls, tid, SCAN_THREADS);
     if (tid < 256) s_cls[tid] = a.cls_map[tid];
     if (lane == 0) {
 #pragma unroll
@@ -749,7 +764,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_tma_kernel(const Scan
                 } else s = (h == 0) ? a.init_state : a.root;
                 if (q == 0) s_cs = s;
             }
-            if (ce == a.total) a.counters[2] = s;
+            if (ce == a.total) { a.counters[2] = s; if (a.host_counters) a.host_counters[2] = s; }
         } else if (active) {
             uint32_t ws = (cs - hb > a.halo) ? ((cs - a.halo) & ~15u) : hb;
             if (ws < hb) ws = hb;
@@ -758,7 +773,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) ac_scan_tma_kernel(const Scan
             s = sc.template walk<true, 0>(s, ws, cs);
             s_cs = s;
             s = scan_slice<0>(a, sc, s, h, cs, ce);
-            if (ce == a.total) a.counters[2] = s;
+            if (ce == a.total) { a.counters[2] = s; if (a.host_counters) a.host_counters[2] = s; }
         }
         __syncwarp();
 
