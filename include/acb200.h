@@ -346,7 +346,10 @@ int acb200_set_devices(AC_TRIE_t *thiz, const int *devices, size_t n);
  * level-2 bitmap of the prefilter, default 0.10; results do not depend on it), ACB200_GATHER_THREADS (threads that
  * gather the scattered strings of an ac_trie_search_batch() slab into pinned staging, 1..64; default
  * min(12, 3/4 cores / GPUs); results do not depend on it), ACB200_GATHER_NT (0: that gather uses plain memcpy
- * instead of non-temporal stores, for A/B measurements). */
+ * instead of non-temporal stores, for A/B measurements), ACB200_STAGE_MIN (bytes from which a pageable text or the
+ * strings of a batch that fit one launch are copied into pinned staging by the handle's helper threads, piece by
+ * piece with each piece's DMA queued behind it, instead of by one cudaMemcpyAsync on the pageable pointer; default
+ * 3 MiB; results do not depend on it). */
 
 /* Bytes per slab of the host pipeline (0 = default 64 MiB).  Tests use small slabs to force cuts. */
 int acb200_set_slab_bytes(AC_TRIE_t *thiz, uint64_t bytes);

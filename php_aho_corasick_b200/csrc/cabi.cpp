@@ -11,6 +11,8 @@
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <functional>
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
@@ -31,6 +33,64 @@
 
 using namespace acb200;
 
+// A few parked threads per handle and device slot for the host-side copies of a call (the gather of pageable or
+// scattered haystacks into pinned staging).  Creating a dozen threads per slab or per call costs 0.1-0.2 ms — more
+// than the copy of a mid-size haystack they are there to speed up.  run() hands out the indices 0..n-1 one at a time
+// (the caller takes part) and returns when all of them are done.
+class HelperPool {
+public:
+    explicit HelperPool(int n_threads)
+    {
+        for (int i = 0; i < n_threads; ++i) th_.emplace_back([this] { loop(); });
+    }
+    ~HelperPool()
+    {
+        { std::lock_guard<std::mutex> g(m_); quit_ = true; }
+        cv_.notify_all();
+        for (auto &x : th_) x.join();
+    }
+    int helpers() const { return (int)th_.size(); }
+    void run(int n, const std::function<void(int)> &f)
+    {
+        if (n <= 0) return;
+        std::unique_lock<std::mutex> g(m_);
+        job_ = &f; n_ = n; next_ = 0; pending_ = n;
+        g.unlock();
+        if (n > 1) cv_.notify_all();
+        g.lock();
+        while (next_ < n_) {
+            const int i = next_++;
+            g.unlock();
+            f(i);
+            g.lock();
+            --pending_;
+        }
+        done_.wait(g, [this] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+private:
+    void loop()
+    {
+        std::unique_lock<std::mutex> g(m_);
+        while (true) {
+            cv_.wait(g, [this] { return quit_ || (job_ && next_ < n_); });
+            if (quit_) return;
+            const std::function<void(int)> *f = job_;
+            const int i = next_++;
+            g.unlock();
+            (*f)(i);
+            g.lock();
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)> *job_ = nullptr;
+    int n_ = 0, next_ = 0, pending_ = 0;
+    bool quit_ = false;
+};
+
 struct ac_trie {
     HostTrie trie;
     FlatAutomaton flat;
@@ -45,6 +105,7 @@ struct ac_trie {
     std::deque<std::string> blob_arena;   // pattern bytes / string ids of an automaton loaded from a blob
     ACB200_STATS_t stats{};    // statistics of the most recent search (summed over slabs and devices)
     uint64_t slab_bytes = 64ull << 20;
+    std::vector<std::unique_ptr<HelperPool>> pools;   // per device slot of a call, made on first use (pool_for)
 };
 
 static inline size_t patterns_of(const ac_trie *t, uint32_t state, const AC_PATTERN_t **p)
@@ -217,22 +278,47 @@ bool is_pinned(const void *p)
     return at.type == cudaMemoryTypeHost;
 }
 
-// The gather of one slab into pinned staging, cut over a few helper threads (one core copies ~10 GB/s, PCIe
-// takes 55).
-void gather_slab(const HaySource &src, char *dst, const SlabPlan &p, int helpers)
+// threads that copy for one device slot of a call: hw cores, n_dev devices at work side by side
+// (16-core host, one GPU, 1 GiB of 8 KiB strings: 4 / 8 / 12 / 16 threads gather at 27.6 / 36.1 / 38.0 / 38.4 GB/s
+// with non-temporal stores, 21.5 / 25.8 / 23.4 / 24.9 GB/s with memcpy, whose read-for-ownership traffic also slows
+// the copy engine's reads of the slab before: 27-36 ms of H2D per GiB instead of 20 — profiles/r02_gather_probe.txt)
+int copy_threads(int n_dev)
+{
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    int helpers = (int)std::max(1u, std::min(12u, hw * 3u / (4u * (unsigned)std::max(1, n_dev))));
+    if (const char *e = getenv("ACB200_GATHER_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 64) helpers = v; }
+    return helpers;
+}
+
+// the parked helper threads of device slot `slot` (the caller of HelperPool::run is one more)
+HelperPool &pool_for(ac_trie *t, size_t slot, int threads)
+{
+    if (t->pools.size() <= slot) t->pools.resize(slot + 1);
+    if (!t->pools[slot] || t->pools[slot]->helpers() != threads - 1) t->pools[slot].reset(new HelperPool(threads - 1));
+    return *t->pools[slot];
+}
+
+// haystack that contains stream byte b (off[h] <= b < off[h + 1]; empty haystacks skipped)
+inline size_t haystack_at(const HaySource &src, uint64_t b)
+{
+    return (size_t)(std::upper_bound(src.off, src.off + src.n + 1, b) - src.off) - 1;
+}
+
+constexpr uint64_t COPY_PIECE_BYTES = 256u << 10;
+
+// The gather of one slab into pinned staging, in pieces handed to the slot's helper threads (one core copies
+// 5-10 GB/s, PCIe takes 55).
+void gather_slab(const HaySource &src, char *dst, const SlabPlan &p, HelperPool *pool)
 {
     const uint64_t b = p.b0 - p.halo, e = p.b1;
     const uint64_t len = e - b;
-    if (helpers <= 1 || len < (8u << 20)) { src.copy(dst, b, e, p.h_first); return; }
-    std::vector<std::thread> th;
-    const uint64_t part = (len + helpers - 1) / helpers;
-    for (int k = 1; k < helpers; ++k) {
-        const uint64_t pb = b + part * k, pe = std::min(e, pb + part);
-        if (pb >= pe) break;
-        th.emplace_back([&src, dst, b, pb, pe, &p] { src.copy(dst + (pb - b), pb, pe, p.h_first); });
-    }
-    src.copy(dst, b, std::min(e, b + part), p.h_first);
-    for (auto &x : th) x.join();
+    if (!pool || len < (1u << 20)) { src.copy(dst, b, e, p.h_first); return; }
+    const uint64_t piece = std::max<uint64_t>(COPY_PIECE_BYTES, (len / 256 + 4095) & ~(uint64_t)4095);
+    const int n_pieces = (int)((len + piece - 1) / piece);
+    pool->run(n_pieces, [&](int i) {
+        const uint64_t pb = b + (uint64_t)i * piece, pe = std::min(e, pb + piece);
+        src.copy(dst + (pb - b), pb, pe, src.flat ? 0 : haystack_at(src, pb));
+    });
 }
 
 void add_stats(ACB200_STATS_t &sum, const ACB200_STATS_t &s)
@@ -245,7 +331,7 @@ void add_stats(ACB200_STATS_t &sum, const ACB200_STATS_t &s)
 }
 
 void shard_worker(const ac_trie *t, Engine *eng, const HaySource &src, const std::vector<SlabPlan> &plans, const std::vector<size_t> &mine,
-                  bool first_only, uint32_t init_state, int helpers, ShardRun &run)
+                  bool first_only, uint32_t init_state, HelperPool *pool, ShardRun &run)
 {
     std::vector<uint64_t> rel;
     auto fail = [&](size_t from) {
@@ -263,7 +349,7 @@ void shard_worker(const ac_trie *t, Engine *eng, const HaySource &src, const std
         else {
             char *stage = eng->slab_staging(buf, n_bytes);
             if (!stage) return false;
-            gather_slab(src, stage, p, helpers);
+            gather_slab(src, stage, p, pool);
             from = stage;
         }
         return eng->slab_upload_async(buf, from, n_bytes);
@@ -333,16 +419,13 @@ int sharded_search(ac_trie *t, const HaySource &src, bool first_only, uint32_t i
     run.res.resize(plans.size());
     std::vector<std::vector<size_t>> mine(n_dev);
     for (size_t i = 0; i < plans.size(); ++i) mine[plans[i].device_slot].push_back(i);
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    // (16-core host, one GPU, 1 GiB of 8 KiB strings: 4 / 8 / 12 / 16 threads gather at 27.6 / 36.1 / 38.0 / 38.4 GB/s
-    // with non-temporal stores, 21.5 / 25.8 / 23.4 / 24.9 GB/s with memcpy, whose read-for-ownership traffic also slows
-    // the copy engine's reads of the slab before: 27-36 ms of H2D per GiB instead of 20 — profiles/r02_gather_probe.txt)
-    int helpers = src.pinned ? 1 : (int)std::max(1u, std::min(12u, hw * 3u / (4u * (unsigned)n_dev)));
-    if (const char *e = getenv("ACB200_GATHER_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 64 && !src.pinned) helpers = v; }
+    // (the pools are made here, on the calling thread: the workers only use them)
+    std::vector<HelperPool *> pools(n_dev, nullptr);
+    if (!src.pinned) { const int thr = copy_threads(n_dev); for (int d = 0; d < n_dev; ++d) pools[d] = &pool_for(t, (size_t)d, thr); }
     std::vector<std::thread> workers;
     for (int d = 0; d < n_dev; ++d)
         workers.emplace_back(shard_worker, (const ac_trie *)t, engines[d], std::cref(src), std::cref(plans), std::cref(mine[d]), first_only,
-                             init_state, helpers, std::ref(run));
+                             init_state, pools[d], std::ref(run));
 
     int rc = 0;
     size_t stopped = (size_t)-1;
@@ -412,6 +495,48 @@ static void replay_direct(ac_trie *t, const uint64_t *offsets, size_t n, int fir
     }
 }
 
+// The direct path (one launch) for a source that is not page-locked — a PHP string, or the strings of a batch:
+// the handle's helper threads copy it into pinned staging piece by piece (non-temporal stores) and queue each piece's
+// DMA as soon as it is there, so the copy engine runs behind the cores instead of after them.  (cudaMemcpyAsync on a
+// pageable pointer stages through the driver on ONE thread: 19 GB/s on the box this was measured on — a 16 MiB
+// haystack spent 0.83 ms of its 0.95 ms call there; the pinned copy takes 55 GB/s.)
+// Below 3 MiB waking the helpers costs more than it brings (profiles/r02_hostcall_probe.txt, one text, staged against
+// the driver's pageable copy: 2 MiB 227 / 206 us, 4 MiB 278 / 312, 8 MiB 385 / 525, 16 MiB 586 / 948, 32 MiB 976 / 1,832 us;
+// the strings of a batch, until now gathered by the calling thread alone: 32 MiB 997 / 2,383 us).
+static uint64_t staged_min_bytes()
+{
+    if (const char *e = getenv("ACB200_STAGE_MIN")) { const long long v = atoll(e); if (v > 0) return (uint64_t)v; }
+    return 3ull << 20;
+}
+
+static bool staged_direct_scan(ac_trie *t, const HaySource &src, uint64_t total, bool first_only, uint32_t init_state)
+{
+    Engine &eng = t->engine;
+    char *stage = eng.slab_staging(0, (size_t)total);
+    if (!stage || !eng.slab_upload_begin(0, (size_t)total)) return false;
+    // two pieces per thread: every piece costs a cudaMemcpyAsync call (~3 us, serialised inside the driver), and the copy
+    // engine should start well before the last core is done
+    const int threads = copy_threads(1);
+    const uint64_t piece = std::max<uint64_t>(64u << 10, (total / (2u * (uint64_t)threads) + 4095) & ~(uint64_t)4095);
+    const int n_pieces = (int)((total + piece - 1) / piece);
+    std::mutex em;
+    std::string err;
+    bool ok = true;
+    pool_for(t, 0, threads).run(n_pieces, [&](int i) {
+        const uint64_t pb = (uint64_t)i * piece, pe = std::min(total, pb + piece);
+        src.copy(stage + pb, pb, pe, src.flat ? 0 : haystack_at(src, pb));
+        if (!eng.slab_upload_part(0, (size_t)pb, (size_t)(pe - pb))) {
+            std::lock_guard<std::mutex> g(em);
+            ok = false; err = get_error();            // (errors are per thread)
+        }
+    });
+    if (!ok) { set_error(err); return false; }
+    if (!eng.slab_upload_end(0)) return false;
+    if (!eng.scan_slab(0, src.off, src.n, first_only, init_state)) return false;
+    eng.stats.h2d_ms = eng.slab_h2d_ms(0);           // staging and DMA together
+    return true;
+}
+
 template <class Sink>
 static int search_source(ac_trie *t, HaySource &src, int first_only, Sink &&sink)
 {
@@ -421,13 +546,17 @@ static int search_source(ac_trie *t, HaySource &src, int first_only, Sink &&sink
     const uint64_t total = src.off[src.n];
     if (takes_direct_path(t, total)) {
         const char *bytes = src.flat;
-        if (!bytes && total) {                   // scattered haystacks: gathered straight into pinned staging
-            char *stage = t->engine.slab_staging(0, (size_t)total);
-            if (!stage) return -1;
-            src.copy(stage, 0, total, 0);
-            bytes = stage;
+        if (total >= staged_min_bytes() && !(src.flat && is_pinned(src.flat))) {
+            if (!staged_direct_scan(t, src, total, first_only != 0, ROOT_STATE)) return -1;
+        } else {
+            if (!bytes && total) {               // a few scattered haystacks: gathered straight into pinned staging
+                char *stage = t->engine.slab_staging(0, (size_t)total);
+                if (!stage) return -1;
+                src.copy(stage, 0, total, 0);
+                bytes = stage;
+            }
+            if (!t->engine.scan_host(bytes, src.off, src.n, first_only != 0, ROOT_STATE)) return -1;
         }
-        if (!t->engine.scan_host(bytes, src.off, src.n, first_only != 0, ROOT_STATE)) return -1;
         t->stats = t->engine.stats; t->stats.devices = 1;
         replay_direct(t, src.off, src.n, first_only, sink);
         return 0;
@@ -642,7 +771,12 @@ int ac_trie_search(AC_TRIE_t *t, AC_TEXT_t *text, int keep, AC_MATCH_CALBACK_f c
     };
     uint32_t end_state;
     if (takes_direct_path(t, offs[1])) {
-        if (!t->engine.scan_host(text->astring, offs, 1, false, t->last_state)) return -1;
+        if (offs[1] >= staged_min_bytes() && !is_pinned(text->astring)) {
+            HaySource src;
+            src.flat = text->astring; src.off = offs; src.n = 1;
+            if (const char *e = getenv("ACB200_GATHER_NT")) src.stream_stores = atoi(e) != 0;
+            if (!staged_direct_scan(t, src, offs[1], false, t->last_state)) return -1;
+        } else if (!t->engine.scan_host(text->astring, offs, 1, false, t->last_state)) return -1;
         t->stats = t->engine.stats; t->stats.devices = 1;
         const PackedEvent *ev = t->engine.host_events();
         const size_t n = t->engine.n_events();

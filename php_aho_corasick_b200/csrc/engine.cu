@@ -1003,7 +1003,7 @@ char *Engine::slab_staging(int buf, size_t n_bytes)
     return (char *)h_slab_[buf];
 }
 
-bool Engine::slab_upload_async(int buf, const char *bytes, size_t n_bytes)
+bool Engine::slab_upload_begin(int buf, size_t n_bytes)
 {
     if (device_ < 0) { set_error("automaton has no device table (finalize failed?)"); return false; }
     CU_OK(cudaSetDevice(device_));
@@ -1021,9 +1021,30 @@ bool Engine::slab_upload_async(int buf, const char *bytes, size_t n_bytes)
         slab_cap_[buf] = cap;
     }
     CU_OK(cudaEventRecord(EV(ev_slab_[2 * buf]), S(copy_stream_)));
-    if (n_bytes) CU_OK(cudaMemcpyAsync(d_slab_[buf], bytes, n_bytes, cudaMemcpyHostToDevice, S(copy_stream_)));
+    return true;
+}
+
+// bytes [offset, offset + n_bytes) of slab_staging(buf) -> the same bytes of the device slab.  Any thread.
+bool Engine::slab_upload_part(int buf, size_t offset, size_t n_bytes)
+{
+    if (!n_bytes) return true;
+    CU_OK(cudaSetDevice(device_));
+    CU_OK(cudaMemcpyAsync((char *)d_slab_[buf] + offset, (const char *)h_slab_[buf] + offset, n_bytes, cudaMemcpyHostToDevice, S(copy_stream_)));
+    return true;
+}
+
+bool Engine::slab_upload_end(int buf)
+{
+    CU_OK(cudaSetDevice(device_));
     CU_OK(cudaEventRecord(EV(ev_slab_[2 * buf + 1]), S(copy_stream_)));
     return true;
+}
+
+bool Engine::slab_upload_async(int buf, const char *bytes, size_t n_bytes)
+{
+    if (!slab_upload_begin(buf, n_bytes)) return false;
+    if (n_bytes) CU_OK(cudaMemcpyAsync(d_slab_[buf], bytes, n_bytes, cudaMemcpyHostToDevice, S(copy_stream_)));
+    return slab_upload_end(buf);
 }
 
 float Engine::slab_h2d_ms(int buf)

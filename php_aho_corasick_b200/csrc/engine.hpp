@@ -54,6 +54,11 @@ public:
     // `bytes` is page-locked memory: the caller's own (acb200_host_alloc) or slab_staging(buf, n).
     char *slab_staging(int buf, size_t n_bytes);
     bool slab_upload_async(int buf, const char *bytes, size_t n_bytes);
+    // ... or piece by piece while the staging buffer is still being filled: begin, then any number of parts of
+    // slab_staging(buf) — slab_upload_part may be called from several threads at once —, then end.
+    bool slab_upload_begin(int buf, size_t n_bytes);
+    bool slab_upload_part(int buf, size_t offset, size_t n_bytes);
+    bool slab_upload_end(int buf);
     bool scan_slab(int buf, const uint64_t *offsets, size_t n, bool first_only, uint32_t init_state = ROOT_STATE);
     float slab_h2d_ms(int buf);
     // Same for a stream already resident in device memory; events stay on the device.

@@ -315,7 +315,7 @@ class Automaton:
             offsets = np.array([0, buf.size], dtype=np.uint64)
         off = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = off.size - 1
-        cap = 1 << 12
+        cap = max(1 << 12, buf.size >> 10)       # (a second call only where events are denser than one per KiB)
         while True:
             ev = np.empty(cap, dtype=EVENT_DTYPE)
             ne = C.c_size_t(0)

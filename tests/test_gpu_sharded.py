@@ -106,6 +106,47 @@ def test_one_long_haystack_spread_over_pipelines_and_keep_streaming():
     a.release()
 
 
+@pytest.mark.parametrize("stage_min,threads", [("1", "5"), ("1", "1"), (str(1 << 40), "3")])
+def test_direct_path_staged_by_helper_threads_equals_oracle(monkeypatch, stage_min, threads):
+    """A pageable text / scattered strings below half a slab: the handle's parked helper threads copy them into pinned
+    staging piece by piece and queue each piece's DMA (ACB200_STAGE_MIN=1 forces that route for every size, a huge value
+    the plain cudaMemcpyAsync on the pageable pointer).  Same events either way, as the reference reports them — also
+    for a keep=1 continuation, whose carried state enters the staged slab."""
+    monkeypatch.setenv("ACB200_STAGE_MIN", stage_min)
+    monkeypatch.setenv("ACB200_GATHER_THREADS", threads)
+    rng = np.random.default_rng(21)
+    pyr = random.Random(21)
+    pats = [rand_bytes(rng, pyr.randint(3, 24), b"abc").tobytes() for _ in range(200)] + [b"abcabcabcabcabcabcabcabc"]
+    lens = [0, 5, 300_000, 0, 65_536, 65_537, 1, 900_001, 0, 17]
+    hays = [rand_bytes(rng, n, b"abc") for n in lens]
+    off = np.zeros(len(lens) + 1, dtype=np.uint64); off[1:] = np.cumsum(lens)
+    flat = np.concatenate(hays)
+    a = build([pats])
+    exp = oracle_hits([pats], hays)
+    ev = a.search_events(flat, off)                  # flat pageable buffer
+    assert a.stats().devices == 1
+    assert_same(a, ev, len(lens), exp)
+    t_batch = a.search_batch_tally(hays)             # separately allocated strings
+    t_flat = a.search_flat_tally(flat.ctypes.data, off)
+    assert (t_batch.events, t_batch.hits, t_batch.hash) == (t_flat.events, t_flat.hits, t_flat.hash)
+    assert t_batch.events == len(ev)
+    ev1 = a.search_events(flat, off, first_only=True)
+    assert_same(a, ev1, len(lens), oracle_hits([pats], hays, first_only=True))
+    # ac_trie_search, whole and as a keep=1 stream of ragged chunks (tiny ones take the one-CTA path unless staged)
+    text = hays[7]
+    rc, got = a.search_callback(text.tobytes())
+    e7 = exp[7]
+    assert rc == 0 and [p for p, _ in got] == sorted({int(x) for x in e7[0]})
+    cuts = [0, 3, 200_000, 200_001, 700_123, text.size]
+    seq = []
+    for i in range(len(cuts) - 1):
+        rc, g = a.search_callback(text[cuts[i]:cuts[i + 1]].tobytes(), keep=(i > 0))
+        assert rc == 0
+        seq += g
+    assert seq == got
+    a.release()
+
+
 def test_cfg2_block_on_every_visible_gpu():
     n = lib().acb200_device_count()
     needles, hay, off = W.cfg2(n_hay=2048, hay_len=8192, planted_per_hay=8, seed=5)
