@@ -306,19 +306,37 @@ inline size_t haystack_at(const HaySource &src, uint64_t b)
 
 constexpr uint64_t COPY_PIECE_BYTES = 256u << 10;
 
-// The gather of one slab into pinned staging, in pieces handed to the slot's helper threads (one core copies
-// 5-10 GB/s, PCIe takes 55).
-void gather_slab(const HaySource &src, char *dst, const SlabPlan &p, HelperPool *pool)
+// The gather of one slab into pinned staging buffer `buf` of `eng` and its upload, in pieces handed to the slot's
+// helper threads (one core copies 5-10 GB/s, PCIe takes 55): every piece's DMA is queued as soon as the piece is there.
+bool gather_and_upload_slab(const HaySource &src, Engine *eng, int buf, const SlabPlan &p, HelperPool *pool)
 {
     const uint64_t b = p.b0 - p.halo, e = p.b1;
     const uint64_t len = e - b;
-    if (!pool || len < (1u << 20)) { src.copy(dst, b, e, p.h_first); return; }
-    const uint64_t piece = std::max<uint64_t>(COPY_PIECE_BYTES, (len / 256 + 4095) & ~(uint64_t)4095);
+    char *dst = eng->slab_staging(buf, (size_t)len);
+    if (!dst) return false;
+    if (!pool || len < (1u << 20)) {
+        src.copy(dst, b, e, p.h_first);
+        return eng->slab_upload_async(buf, dst, (size_t)len);
+    }
+    if (!eng->slab_upload_begin(buf, (size_t)len)) return false;
+    // two or three pieces per thread: every piece costs a cudaMemcpyAsync call, and those serialise inside the driver
+    // (256 KiB pieces = 256 calls per 64 MiB slab from twelve threads: 1 GiB of strings took 38.5 ms instead of 31)
+    const uint64_t per = len / (3u * (uint64_t)(pool->helpers() + 1));
+    const uint64_t piece = std::max<uint64_t>(COPY_PIECE_BYTES, (per + 4095) & ~(uint64_t)4095);
     const int n_pieces = (int)((len + piece - 1) / piece);
+    std::mutex em;
+    std::string err;
+    bool ok = true;
     pool->run(n_pieces, [&](int i) {
         const uint64_t pb = b + (uint64_t)i * piece, pe = std::min(e, pb + piece);
         src.copy(dst + (pb - b), pb, pe, src.flat ? 0 : haystack_at(src, pb));
+        if (!eng->slab_upload_part(buf, (size_t)(pb - b), (size_t)(pe - pb))) {
+            std::lock_guard<std::mutex> g(em);
+            ok = false; err = get_error();            // (errors are per thread)
+        }
     });
+    if (!ok) { set_error(err); return false; }
+    return eng->slab_upload_end(buf);
 }
 
 void add_stats(ACB200_STATS_t &sum, const ACB200_STATS_t &s)
@@ -344,15 +362,8 @@ void shard_worker(const ac_trie *t, Engine *eng, const HaySource &src, const std
         const SlabPlan &p = plans[mine[k]];
         const size_t n_bytes = (size_t)(p.halo + (p.b1 - p.b0));
         const int buf = (int)(k & 1);
-        const char *from;
-        if (src.pinned) from = src.flat + (p.b0 - p.halo);
-        else {
-            char *stage = eng->slab_staging(buf, n_bytes);
-            if (!stage) return false;
-            gather_slab(src, stage, p, pool);
-            from = stage;
-        }
-        return eng->slab_upload_async(buf, from, n_bytes);
+        if (src.pinned) return eng->slab_upload_async(buf, src.flat + (p.b0 - p.halo), n_bytes);
+        return gather_and_upload_slab(src, eng, buf, p, pool);
     };
     if (mine.empty()) return;
     if (!prepare(0)) { fail(0); return; }
