@@ -483,7 +483,9 @@ uint32_t Engine::pick_chunk(uint64_t total) const
     // short that the halo dominates.
     // (2x the halo: measured on the adversarial shape — Lmax 1024, every byte an event — 2 KiB slices give 129 GB/s,
     // 4 KiB 96, 8 KiB 62: with long patterns the walk needs the lanes more than it minds re-reading the halo)
-    const uint64_t floor_ = std::max<uint64_t>(64, up16(2ull * halo_));
+    // (and 32 bytes at least: a 0.25 / 1 / 4 MiB batch of config 2 walks in 25.5 / 28.7 / 32.8 us with 32-byte slices,
+    // 31 / 33 / 37 us with 64-byte ones and 23.5 / 28.7 / 45.9 us with 16-byte ones — profiles/r02_midsize_calls.txt)
+    const uint64_t floor_ = std::max<uint64_t>(32, up16(2ull * halo_));
     const uint64_t want = (uint64_t)n_sms_ * SCAN_THREADS;
     uint64_t c = ideal;
     if (total / ideal < want) c = std::max(floor_, up16(total / std::max<uint64_t>(want, 1)));
