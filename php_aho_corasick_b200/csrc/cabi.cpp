@@ -39,9 +39,11 @@ using namespace acb200;
 // (the caller takes part) and returns when all of them are done.
 class HelperPool {
 public:
-    explicit HelperPool(int n_threads)
+    explicit HelperPool(int n_threads) : wanted_(n_threads)
     {
-        for (int i = 0; i < n_threads; ++i) th_.emplace_back([this] { loop(); });
+        try {
+            for (int i = 0; i < n_threads; ++i) th_.emplace_back([this] { loop(); });
+        } catch (...) {}        // (thread limit reached: fewer helpers, the caller of run() does the rest itself)
     }
     ~HelperPool()
     {
@@ -50,6 +52,7 @@ public:
         for (auto &x : th_) x.join();
     }
     int helpers() const { return (int)th_.size(); }
+    int wanted() const { return wanted_; }
     void run(int n, const std::function<void(int)> &f)
     {
         if (n <= 0) return;
@@ -89,6 +92,7 @@ private:
     const std::function<void(int)> *job_ = nullptr;
     int n_ = 0, next_ = 0, pending_ = 0;
     bool quit_ = false;
+    int wanted_ = 0;
 };
 
 struct ac_trie {
@@ -294,7 +298,7 @@ int copy_threads(int n_dev)
 HelperPool &pool_for(ac_trie *t, size_t slot, int threads)
 {
     if (t->pools.size() <= slot) t->pools.resize(slot + 1);
-    if (!t->pools[slot] || t->pools[slot]->helpers() != threads - 1) t->pools[slot].reset(new HelperPool(threads - 1));
+    if (!t->pools[slot] || t->pools[slot]->wanted() != threads - 1) t->pools[slot].reset(new HelperPool(threads - 1));
     return *t->pools[slot];
 }
 
