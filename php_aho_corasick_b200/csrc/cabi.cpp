@@ -29,71 +29,10 @@
 #include "automaton.hpp"
 #include "engine.hpp"
 #include "filter_hash.hpp"
+#include "helper_pool.hpp"
 #include "shard.hpp"
 
 using namespace acb200;
-
-// A few parked threads per handle and device slot for the host-side copies of a call (the gather of pageable or
-// scattered haystacks into pinned staging).  Creating a dozen threads per slab or per call costs 0.1-0.2 ms — more
-// than the copy of a mid-size haystack they are there to speed up.  run() hands out the indices 0..n-1 one at a time
-// (the caller takes part) and returns when all of them are done.
-class HelperPool {
-public:
-    explicit HelperPool(int n_threads) : wanted_(n_threads)
-    {
-        try {
-            for (int i = 0; i < n_threads; ++i) th_.emplace_back([this] { loop(); });
-        } catch (...) {}        // (thread limit reached: fewer helpers, the caller of run() does the rest itself)
-    }
-    ~HelperPool()
-    {
-        { std::lock_guard<std::mutex> g(m_); quit_ = true; }
-        cv_.notify_all();
-        for (auto &x : th_) x.join();
-    }
-    int helpers() const { return (int)th_.size(); }
-    int wanted() const { return wanted_; }
-    void run(int n, const std::function<void(int)> &f)
-    {
-        if (n <= 0) return;
-        std::unique_lock<std::mutex> g(m_);
-        job_ = &f; n_ = n; next_ = 0; pending_ = n;
-        g.unlock();
-        if (n > 1) cv_.notify_all();
-        g.lock();
-        while (next_ < n_) {
-            const int i = next_++;
-            g.unlock();
-            f(i);
-            g.lock();
-            --pending_;
-        }
-        done_.wait(g, [this] { return pending_ == 0; });
-        job_ = nullptr;
-    }
-private:
-    void loop()
-    {
-        std::unique_lock<std::mutex> g(m_);
-        while (true) {
-            cv_.wait(g, [this] { return quit_ || (job_ && next_ < n_); });
-            if (quit_) return;
-            const std::function<void(int)> *f = job_;
-            const int i = next_++;
-            g.unlock();
-            (*f)(i);
-            g.lock();
-            if (--pending_ == 0) done_.notify_all();
-        }
-    }
-    std::vector<std::thread> th_;
-    std::mutex m_;
-    std::condition_variable cv_, done_;
-    const std::function<void(int)> *job_ = nullptr;
-    int n_ = 0, next_ = 0, pending_ = 0;
-    bool quit_ = false;
-    int wanted_ = 0;
-};
 
 struct ac_trie {
     HostTrie trie;
@@ -298,7 +237,9 @@ int copy_threads(int n_dev)
 HelperPool &pool_for(ac_trie *t, size_t slot, int threads)
 {
     if (t->pools.size() <= slot) t->pools.resize(slot + 1);
-    if (!t->pools[slot] || t->pools[slot]->wanted() != threads - 1) t->pools[slot].reset(new HelperPool(threads - 1));
+    // (a pool only grows: a handle that is used for one-GPU and for all-GPU calls in turn keeps its threads)
+    if (!t->pools[slot] || t->pools[slot]->wanted() < threads - 1) t->pools[slot].reset(new HelperPool(threads - 1));
+    t->pools[slot]->set_limit(threads - 1);
     return *t->pools[slot];
 }
 
